@@ -1,0 +1,383 @@
+"""Plain-PyTorch (CPU, fp32/fp64) restatement of the reference's ray-rendering
+hot path.  TEST INFRASTRUCTURE - see ``oracle/__init__.py``.
+
+Every function cites the file:line of ``wagnva/semantic-nerf-for-satellite-data``
+it follows (paths relative to the reference root).  The code is written from the
+math in SURVEY.md Appendix A, in a functional style over a ``state_dict``-shaped
+parameter dictionary (the reference's own parameter names), so the same
+parameters can be loaded into the reference ``nn.Module`` for pinning.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+__all__ = [
+    "ModelSpec",
+    "param_shapes",
+    "make_params",
+    "linspace01",
+    "sample_z",
+    "sample_points",
+    "posenc",
+    "mlp_forward",
+    "convert_sigmas",
+    "composite",
+    "inference",
+    "render_rays",
+    "synthetic_rays",
+    "snerf_loss",
+    "satnerf_loss",
+    "depth_loss",
+    "semantic_loss",
+    "car_reg_loss",
+    "psnr",
+]
+
+
+# --------------------------------------------------------------------------------------
+# model description
+# --------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class ModelSpec:
+    """Architecture of the two models on the path.
+
+    kind = "satnerf":  baseline/models/satnerf.py:101-206 (mapping=False: raw xyz input,
+                       baseline/pipelines/satnerf.py:53-59 never overrides the default)
+    kind = "semantic": semantic/models/rs_semantic.py:139-258 (positional Mapping always on)
+    """
+
+    kind: str = "semantic"
+    n_classes: int = 6
+    feat: int = 512
+    layers: int = 8
+    skips: tuple = (4,)
+    tau: int = 4
+    vocab: int = 50
+    n_freq: int = 10
+    full_features: bool = False
+    semantic_sigmoid: bool = True  # configs/pipelines/rs_semantic.toml:55
+
+    @property
+    def k0(self) -> int:
+        return 2 * self.n_freq * 3 if self.kind == "semantic" else 3
+
+    @property
+    def feat_last(self) -> int:
+        return self.feat if self.full_features else self.feat // 2
+
+    @property
+    def n_out(self) -> int:
+        return 9 + (self.n_classes if self.kind == "semantic" else 0)
+
+
+def param_shapes(spec: ModelSpec) -> Dict[str, tuple]:
+    """Parameter names/shapes exactly as the reference ``state_dict`` has them
+    (satnerf.py:143-206, rs_semantic.py:176-258)."""
+    f, fl, k0 = spec.feat, spec.feat_last, spec.k0
+    s: Dict[str, tuple] = {}
+    for i in range(spec.layers):
+        if i == 0:
+            kin = k0
+        elif i in spec.skips:
+            kin = f + k0
+        else:
+            kin = f
+        s[f"fc_net.{2 * i}.weight"] = (f, kin)
+        s[f"fc_net.{2 * i}.bias"] = (f,)
+    s["sigma_from_xyz.0.weight"] = (1, f)
+    s["sigma_from_xyz.0.bias"] = (1,)
+    s["feats_from_xyz.weight"] = (f, f)
+    s["feats_from_xyz.bias"] = (f,)
+    s["rgb_from_xyzdir.0.weight"] = (fl, f)
+    s["rgb_from_xyzdir.0.bias"] = (fl,)
+    s["rgb_from_xyzdir.2.weight"] = (3, fl)
+    s["rgb_from_xyzdir.2.bias"] = (3,)
+    if spec.kind == "semantic":
+        s["semantic_prediction.0.weight"] = (fl, f)
+        s["semantic_prediction.0.bias"] = (fl,)
+        s["semantic_prediction.2.weight"] = (spec.n_classes, fl)
+        s["semantic_prediction.2.bias"] = (spec.n_classes,)
+    s["sun_v_net.0.weight"] = (fl, f + 3)
+    s["sun_v_net.0.bias"] = (fl,)
+    for j in (2, 4):
+        s[f"sun_v_net.{j}.weight"] = (fl, fl)
+        s[f"sun_v_net.{j}.bias"] = (fl,)
+    s["sun_v_net.6.weight"] = (1, fl)
+    s["sun_v_net.6.bias"] = (1,)
+    s["sky_color.0.weight"] = (fl, 3)
+    s["sky_color.0.bias"] = (fl,)
+    s["sky_color.2.weight"] = (3, fl)
+    s["sky_color.2.bias"] = (3,)
+    s["beta_from_xyz.0.weight"] = (fl, f + spec.tau)
+    s["beta_from_xyz.0.bias"] = (fl,)
+    s["beta_from_xyz.2.weight"] = (1, fl)
+    s["beta_from_xyz.2.bias"] = (1,)
+    return s
+
+
+def make_params(spec: ModelSpec, seed: int = 0, dtype=torch.float32, trained_like: bool = False):
+    """Deterministic parameters drawn with numpy's PCG64 (stable across torch
+    versions, so golden vectors regenerate anywhere).  Distributions follow the
+    reference initialisers: SIREN init on ``fc_net`` and ``sun_v_net``
+    (commons.py:5-18, rs_semantic.py:239-243), PyTorch ``nn.Linear`` default
+    (U(+-1/sqrt(fan_in)) for weight and bias) elsewhere, N(0,1) embedding.
+
+    trained_like=True widens the head weights so that composited outputs have
+    non-trivial dynamic range (used for bf16 statistical parity).
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    params: Dict[str, torch.Tensor] = {}
+    for name, shape in param_shapes(spec).items():
+        if name.endswith(".bias"):
+            wshape = param_shapes(spec)[name[:-4] + "weight"]
+            bound = 1.0 / math.sqrt(wshape[1])
+        else:
+            fan_in = shape[1]
+            siren_net = name.startswith("fc_net.") or name.startswith("sun_v_net.")
+            if siren_net:
+                first = name in ("fc_net.0.weight", "sun_v_net.0.weight")
+                bound = 1.0 / fan_in if first else math.sqrt(6.0 / fan_in)
+            else:
+                bound = 1.0 / math.sqrt(fan_in)
+                if trained_like and name.split(".")[0] in (
+                    "rgb_from_xyzdir", "semantic_prediction", "sigma_from_xyz", "beta_from_xyz", "sky_color"):
+                    bound *= 4.0
+        arr = rng.uniform(-bound, bound, size=shape)
+        params[name] = torch.from_numpy(arr).to(dtype)
+    emb = torch.from_numpy(rng.standard_normal(size=(spec.vocab, spec.tau))).to(dtype)
+    return params, emb
+
+
+# --------------------------------------------------------------------------------------
+# K1: sampling + encoding
+# --------------------------------------------------------------------------------------
+def linspace01(n: int, dtype=torch.float32) -> torch.Tensor:
+    """torch.linspace(0, 1, n) as the reference calls it
+    (framework/components/rendering.py:95).  Kept as a separate function so the
+    CUDA kernel's closed form (i*step for the lower half, 1-(n-1-i)*step for the
+    upper half) can be pinned against it."""
+    return torch.linspace(0, 1, n, dtype=dtype)
+
+
+def sample_z(rays: torch.Tensor, n_samples: int, u: Optional[torch.Tensor]) -> torch.Tensor:
+    """Stratified depths along each ray.  framework/components/rendering.py:95-110
+    with ``use_disp=False, perturb=1.0``; ``u`` is the U[0,1) jitter the reference
+    draws with ``torch.rand_like`` (u=None -> no perturbation, the perturb=0 branch)."""
+    near, far = rays[:, 6:7], rays[:, 7:8]
+    t = linspace01(n_samples, rays.dtype)
+    z = near * (1 - t) + far * t
+    if u is not None:
+        mid = 0.5 * (z[:, :-1] + z[:, 1:])
+        upper = torch.cat([mid, z[:, -1:]], -1)
+        lower = torch.cat([z[:, :1], mid], -1)
+        z = lower + (upper - lower) * u
+    return z
+
+
+def sample_points(origins: torch.Tensor, dirs: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+    """xyz = o + d*z  (framework/components/rendering.py:113-115; the solar-correction
+    pass uses dirs = sun_d with the same z: semantic/components/rendering.py:61-63)."""
+    return origins.unsqueeze(1) + dirs.unsqueeze(1) * z.unsqueeze(2)
+
+
+def posenc(x: torch.Tensor, n_freq: int = 10) -> torch.Tensor:
+    """[sin(2^k x), cos(2^k x)]_{k<n_freq}, no identity term.  baseline/models/commons.py:54,68-74."""
+    out = []
+    for k in range(n_freq):
+        f = float(2.0 ** k)
+        out += [torch.sin(f * x), torch.cos(f * x)]
+    return torch.cat(out, -1)
+
+
+# --------------------------------------------------------------------------------------
+# K2: the MLP
+# --------------------------------------------------------------------------------------
+def _lin(p, name, x):
+    return F.linear(x, p[name + ".weight"], p[name + ".bias"])
+
+
+def mlp_forward(p: Dict[str, torch.Tensor], spec: ModelSpec, xyz: torch.Tensor,
+                sun_d: torch.Tensor, t: torch.Tensor, return_hidden: bool = False):
+    """(B,3),(B,3),(B,tau) -> (B, 9[+C]) packed [rgb 0:3 | sigma 3 | sun 4 | sky 5:8 | beta 8 | sem 9:].
+    satnerf.py:208-255 / rs_semantic.py:260-340; Siren: commons.py:27-38 (w0=30 on the
+    first trunk layer only, satnerf.py:146)."""
+    enc = posenc(xyz, spec.n_freq) if spec.kind == "semantic" else xyz
+    h = enc
+    hidden = []
+    for i in range(spec.layers):
+        if i in spec.skips:
+            h = torch.cat([enc, h], -1)
+        y = _lin(p, f"fc_net.{2 * i}", h)
+        h = torch.sin(30.0 * y) if i == 0 else torch.sin(y)
+        hidden.append(h)
+    sigma = F.softplus(_lin(p, "sigma_from_xyz.0", h))
+    f = _lin(p, "feats_from_xyz", h)
+    rgb = torch.sigmoid(_lin(p, "rgb_from_xyzdir.2", torch.sin(_lin(p, "rgb_from_xyzdir.0", f))))
+    rgb = rgb * (1 + 2 * 0.001) - 0.001
+    s = torch.cat([f, sun_d], -1)
+    s = torch.sin(_lin(p, "sun_v_net.0", s))
+    s = torch.sin(_lin(p, "sun_v_net.2", s))
+    s = torch.sin(_lin(p, "sun_v_net.4", s))
+    sun_v = torch.sigmoid(_lin(p, "sun_v_net.6", s))
+    sky = torch.sigmoid(_lin(p, "sky_color.2", torch.relu(_lin(p, "sky_color.0", sun_d))))
+    beta = F.softplus(_lin(p, "beta_from_xyz.2", torch.sin(_lin(p, "beta_from_xyz.0", torch.cat([f, t], -1)))))
+    cols = [rgb, sigma, sun_v, sky, beta]
+    if spec.kind == "semantic":
+        sem = _lin(p, "semantic_prediction.2", torch.sin(_lin(p, "semantic_prediction.0", f)))
+        if spec.semantic_sigmoid:
+            sem = torch.sigmoid(sem)
+        cols.append(sem)
+    out = torch.cat(cols, 1)
+    if return_hidden:
+        return out, hidden, f
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# K3: compositing
+# --------------------------------------------------------------------------------------
+def convert_sigmas(sigmas: torch.Tensor, z: torch.Tensor):
+    """framework/util/rendering.py:4-34."""
+    deltas = z[:, 1:] - z[:, :-1]
+    # NB: exactly as the reference builds it (ones_like of a slice of ``deltas``): for S == 1 that
+    # slice is empty and every per-sample tensor collapses to (N,0) - the reference does not support
+    # S < 2, and neither does the CUDA path (it returns SNB_ERR_UNSUPPORTED).
+    deltas = torch.cat([deltas, 1e10 * torch.ones_like(deltas[:, :1])], -1)
+    alphas = 1 - torch.exp(-deltas * torch.relu(sigmas))
+    shifted = torch.cat([torch.ones_like(alphas[:, :1]), 1 - alphas + 1e-10], -1)
+    transparency = torch.cumprod(shifted, -1)[:, :-1]
+    weights = alphas * transparency
+    depth = torch.sum(weights * z, -1)
+    return weights, depth, transparency, alphas
+
+
+def composite(out: torch.Tensor, z: torch.Tensor, n_classes: int = 0) -> Dict[str, torch.Tensor]:
+    """Tail of ``inference``: satnerf.py:73-96 / rs_semantic.py:81-126.  ``out`` is (N,S,9[+C])."""
+    rgbs, sigmas = out[..., :3], out[..., 3]
+    sun_v, sky, beta = out[..., 4:5], out[..., 5:8], out[..., 8:9]
+    weights, depth, transparency, _ = convert_sigmas(sigmas, z)
+    irradiance = sun_v + (1 - sun_v) * sky
+    rgb = torch.clamp(torch.sum(weights.unsqueeze(-1) * rgbs * irradiance, -2), min=0.0, max=1.0)
+    res = {
+        "rgb": rgb, "depth": depth, "weights": weights, "transparency": transparency,
+        "albedo": rgbs, "sun": sun_v, "sky": sky, "beta": beta, "sigmas": sigmas,
+    }
+    if n_classes > 0:
+        sem = out[..., 9:9 + n_classes]
+        logits = torch.sum(weights.unsqueeze(-1) * sem, -2)
+        res["semantic_logits"] = logits
+        # rs_semantic.py:131-136: argmax(softmax(x)) == argmax(x)
+        res["semantic_label"] = torch.argmax(torch.softmax(logits, dim=-1), dim=-1)
+    return res
+
+
+def inference(p, spec: ModelSpec, xyz: torch.Tensor, z: torch.Tensor, sun_d: torch.Tensor,
+              t: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """satnerf.py:8-98 / rs_semantic.py:8-128 (per-ray inputs broadcast over samples,
+    model evaluated on all points, then composited)."""
+    n, s = z.shape
+    out = mlp_forward(p, spec, xyz.reshape(-1, 3),
+                      torch.repeat_interleave(sun_d, s, 0), torch.repeat_interleave(t, s, 0))
+    return composite(out.view(n, s, -1), z, spec.n_classes if spec.kind == "semantic" else 0)
+
+
+def render_rays(p, emb: torch.Tensor, spec: ModelSpec, rays: torch.Tensor, extras: torch.Tensor,
+                n_samples: int, u: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None,
+                sc_lambda: float = 0.05) -> Dict[str, torch.Tensor]:
+    """BaseRenderer.render_rays (framework/components/rendering.py:125-157) +
+    {SatNeRF,RSSemantic}Rendering._model_rendering (baseline/components/rendering.py:12-67,
+    semantic/components/rendering.py:18-80): main pass, optional solar-correction pass on
+    o + sun_d*z, ``_coarse`` suffix on every key."""
+    if z is None:
+        z = sample_z(rays, n_samples, u)
+    o, d = rays[:, 0:3], rays[:, 3:6]
+    sun_d = extras[:, 0:3]
+    ts = extras[:, 3].long()
+    t = emb[ts]
+    res = inference(p, spec, sample_points(o, d, z), z, sun_d, t)
+    if sc_lambda > 0:
+        tmp = inference(p, spec, sample_points(o, sun_d, z), z, sun_d, t)
+        res["weights_sc"] = tmp["weights"]
+        res["transparency_sc"] = tmp["transparency"]
+        res["sun_sc"] = tmp["sun"]
+    out = {f"{k}_coarse": v for k, v in res.items()}
+    out["_z_vals"] = z  # not a reference key; convenience for tests
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# synthetic inputs - shared by tests, smoke and bench
+# --------------------------------------------------------------------------------------
+def synthetic_rays(n_rays: int, seed: int = 0, n_images: int = 17, dtype=torch.float32):
+    """rays (N,8) = [o, d, near, far]; extras (N,4) = [sun_d, ts]
+    (layout: framework/components/rays.py:7-64; value ranges: SURVEY 8d)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 1000))
+    o = np.concatenate([rng.uniform(-1, 1, (n_rays, 2)), rng.uniform(0.15, 0.35, (n_rays, 1))], 1)
+    d = np.array([0.10, 0.05, -1.0]) + 0.02 * rng.standard_normal((n_rays, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    near = np.zeros((n_rays, 1))
+    far = rng.uniform(0.45, 0.65, (n_rays, 1))
+    el = np.deg2rad(rng.uniform(30, 70, n_images))
+    az = np.deg2rad(rng.uniform(100, 200, n_images))
+    sun = np.stack([np.sin(az) * np.cos(el), np.cos(az) * np.cos(el), np.sin(el)], 1)
+    ts = rng.integers(0, n_images, n_rays)
+    rays = np.concatenate([o, d, near, far], 1)
+    extras = np.concatenate([sun[ts], ts[:, None].astype(np.float64)], 1)
+    return torch.from_numpy(rays).to(dtype), torch.from_numpy(extras).to(dtype)
+
+
+# --------------------------------------------------------------------------------------
+# losses that sit directly on the path's outputs (used for gradient parity)
+# --------------------------------------------------------------------------------------
+def _solar_correction(res, lambda_sc):
+    """baseline/components/loss.py:4-13."""
+    sun_sc = res["sun_sc_coarse"].squeeze(-1)
+    term2 = torch.sum(torch.square(res["transparency_sc_coarse"].detach() - sun_sc), -1)
+    term3 = 1 - torch.sum(res["weights_sc_coarse"].detach() * sun_sc, -1)
+    return lambda_sc / 3.0 * torch.mean(term2) + lambda_sc / 3.0 * torch.mean(term3)
+
+
+def snerf_loss(res, gt_rgb, lambda_sc=0.05):
+    """SNerfLoss, baseline/components/loss.py:71-94 (the ``loss_without_beta`` of the first epochs)."""
+    loss = F.mse_loss(res["rgb_coarse"], gt_rgb)
+    if lambda_sc > 0:
+        loss = loss + _solar_correction(res, lambda_sc)
+    return loss
+
+
+def satnerf_loss(res, gt_rgb, lambda_sc=0.05, beta_min=0.05):
+    """SatNerfLoss + uncertainty_aware_loss, baseline/components/loss.py:16-27,50-68."""
+    beta = torch.sum(res["weights_coarse"].unsqueeze(-1) * res["beta_coarse"], -2) + beta_min
+    loss = ((res["rgb_coarse"] - gt_rgb) ** 2 / (2 * beta ** 2)).mean()
+    loss = loss + (3 + torch.log(beta).mean()) / 2
+    if lambda_sc > 0:
+        loss = loss + _solar_correction(res, lambda_sc)
+    return loss
+
+
+def depth_loss(res, depths, weights=1.0, lambda_ds=1000.0):
+    """DepthLoss, baseline/components/loss.py:30-47."""
+    return lambda_ds / 3.0 * torch.mean(weights * (res["depth_coarse"] - depths) ** 2)
+
+
+def semantic_loss(res, labels, lambda_s=0.04, ignore_index=-100):
+    """SemanticLoss, semantic/components/loss.py:35-65 (CE over the composited class scores)."""
+    return lambda_s * F.cross_entropy(res["semantic_logits_coarse"], labels, ignore_index=ignore_index)
+
+
+def car_reg_loss(res, labels, car_label, lambda_c=0.1):
+    """SemanticCarRegLoss, semantic/components/loss.py:117-157."""
+    unc = torch.sum(res["weights_coarse"].unsqueeze(-1) * res["beta_coarse"], -2)
+    sel = unc[labels == car_label]
+    return lambda_c * F.mse_loss(torch.ones_like(sel), sel)
+
+
+def psnr(a: torch.Tensor, b: torch.Tensor) -> float:
+    """eval/utils/metrics.py:17-18: -10*log10(mse)."""
+    return float(-10.0 * torch.log10(torch.mean((a - b) ** 2)))
