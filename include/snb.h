@@ -1,0 +1,172 @@
+/*
+ * snb.h - C ABI of libsnb.so, the B200 (sm_100a) implementation of the ray-rendering hot
+ * path of wagnva/semantic-nerf-for-satellite-data.
+ *
+ * Boundary.  The reference is pure Python/PyTorch; the functions below are what a binding for
+ * this path would call (the ctypes stub a reference maintainer would add is in INTEGRATION.md,
+ * the in-tree one is semantic-nerf-for-satellite-data_b200/_lib.py).  Each entry names the
+ * reference interface it replaces (file:line relative to the reference root).
+ *
+ * Conventions.
+ *   - All pointers are DEVICE pointers unless the name ends in _host.  Buffers are owned by the
+ *     caller (PyTorch's allocator); nothing here allocates device memory.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - Every function returns 0 on success, a negative SNB_ERR_* for a rejected argument, or a
+ *     positive cudaError_t.  snb_last_error() returns a thread-local description.
+ *   - There is no CPU fallback: without a CUDA device every compute entry fails.
+ *   - bf16 buffers are passed as void* (raw __nv_bfloat16).
+ */
+#ifndef SNB_H_
+#define SNB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNB_VERSION 100
+
+enum {
+  SNB_OK = 0,
+  SNB_ERR_INVALID = -1,     /* null pointer / negative size / misaligned buffer          */
+  SNB_ERR_UNSUPPORTED = -2, /* shape outside what the kernels implement (e.g. S < 2)      */
+  SNB_ERR_NO_DEVICE = -3,   /* no sm_100 device / driver entry point missing              */
+  SNB_ERR_WORKSPACE = -4    /* workspace too small                                        */
+};
+
+/* model kinds: baseline/models/satnerf.py:101 (raw xyz input) and
+ * semantic/models/rs_semantic.py:139 (positional mapping, semantic head) */
+enum { SNB_MODEL_SATNERF = 0, SNB_MODEL_SEMANTIC = 1 };
+
+/* which heads a pass evaluates (bit mask).  SNB_HEADS_ALL is the reference's forward();
+ * SNB_HEADS_SOLAR is what the solar-correction pass keeps (semantic/components/rendering.py:76-78);
+ * SNB_HEADS_DEPTH is what the depth-supervision batch consumes (baseline/components/loss.py:40). */
+enum {
+  SNB_HEAD_SIGMA = 1, SNB_HEAD_RGB = 2, SNB_HEAD_SUN = 4, SNB_HEAD_BETA = 8, SNB_HEAD_SEM = 16, SNB_HEAD_SKY = 32,
+  SNB_HEADS_ALL = 63, SNB_HEADS_SOLAR = 1 | 4, SNB_HEADS_DEPTH = 1
+};
+
+int snb_version(void);
+const char* snb_last_error(void);
+/* number of SMs of the current device; <0 on error */
+int snb_device_sms(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  sample generation + encoding
+ * replaces framework/components/rendering.py:84-116 (sample_rays), baseline/models/commons.py:58-74
+ * (Mapping.forward), the nn.Embedding lookup + int cast of semantic/components/rendering.py:35-45,
+ * the repeat_interleave broadcasts of semantic/models/rs_semantic.py:42-61 and sky_color(sun_d)
+ * (rs_semantic.py:222-227, a per-ray function).
+ *
+ *   rays   (N,8) f32  [o(3) d(3) near far]          framework/components/rays.py:7-38
+ *   extras (N,4) f32  [sun_d(3) ts]                 framework/components/rays.py:41-64
+ *   u      (N,S) f32  jitter in [0,1) or NULL -> in-kernel Philox4x32-10 keyed on (seed, ray_offset+ray, sample)
+ *   z_vals (N,S) f32  written (z_given=0) or read (z_given=1: the reference's given_z_vals)
+ *   enc    bf16 (N*S, enc_ld): [hi(k0) | hi(k0) | lo(k0) | 0] where hi+lo is the bf16 split of the
+ *          fp32 encoding (k0 = 3 raw xyz / 60 posenc), enc_ld = 64 / 192.  NULL to skip.
+ *   enc_sc same for the solar-correction points o + sun_d*z. NULL to skip.
+ *   aux    bf16 (N*S,16): [1, sun_d(3), t(tau), 0..] - per-ray terms of the heads as a K-segment.
+ *   sky    f32  (N,3): sigmoid(W2 relu(W1 sun_d + b1) + b2).  NULL to skip.
+ * ---------------------------------------------------------------------------------------------- */
+/*   t_steps (S) f32  linspace(0,1,S) exactly as the reference's host computes it (rendering.py:95);
+ *          passed in so the stratification bins are bit-identical to the reference's. */
+int snb_sample_encode(const float* rays, const float* extras, const float* u, uint64_t seed,
+                      uint64_t ray_offset, const float* t_steps, const float* t_table, int vocab, int tau,
+                      const float* sky_w1, const float* sky_b1, const float* sky_w2, const float* sky_b2,
+                      int sky_hidden, int n_rays, int n_samples, int model_kind, int z_given,
+                      float* z_vals, void* enc, void* enc_sc, void* aux, float* sky, void* stream);
+
+/* Model.forward entry on caller-supplied points (no ray structure): encodes xyz (P,3), builds aux
+ * from per-point sun_d (P,3) and t (P,tau), sky per point (P,3).
+ * replaces the input side of satnerf.py:208-222 / rs_semantic.py:260-277,325-328. */
+int snb_encode_points(const float* xyz, const float* sun_d, const float* t, int tau,
+                      const float* sky_w1, const float* sky_b1, const float* sky_w2, const float* sky_b2,
+                      int sky_hidden, int n_points, int model_kind, void* enc, void* aux, float* sky,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K2  the MLP (trunk + heads), forward and backward, as tcgen05 GEMMs
+ * replaces SatNeRF.forward (baseline/models/satnerf.py:208-255) and RSSemanticNeRF.forward/.sigma/
+ * .semantic (semantic/models/rs_semantic.py:260-340) and their autograd.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct snb_model snb_model; /* opaque host object: architecture + packed-weight layout */
+
+int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid);
+void snb_model_destroy(snb_model* m);
+/* number of fp32 parameters / the offset table: parameters live in ONE flat fp32 buffer in the
+ * reference state_dict order; names[i], offsets[i], rows[i], cols[i]. */
+int64_t snb_model_param_count(const snb_model* m);
+int snb_model_num_tensors(const snb_model* m);
+int snb_model_tensor_info(const snb_model* m, int i, const char** name, int64_t* offset, int* rows, int* cols);
+/* bytes of the packed bf16 weight image (forward + transposed copies) */
+size_t snb_model_packed_bytes(const snb_model* m);
+/* fp32 flat params -> packed bf16 image (call after every optimiser step) */
+int snb_model_pack(const snb_model* m, const float* params, void* packed, void* stream);
+
+/* workspace (activations saved for backward, scratch) for P points; train=0: inference only */
+size_t snb_mlp_workspace_bytes(const snb_model* m, int64_t n_points, int train);
+
+/* forward: enc/aux/sky from K1 -> out (P, n_out) f32 packed [rgb 0:3 | sigma 3 | sun 4 | sky 5:8 | beta 8 | sem 9:]
+ * (rs_semantic.py:291-311).  Columns of heads not in head_mask are written as 0.
+ * rows_per_ray: sky/aux are per ray when >0 (sky indexed by row / rows_per_ray), per point when 0. */
+int snb_mlp_forward(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
+                    int64_t n_points, const void* enc, const void* aux, const float* sky,
+                    int rows_per_ray, int head_mask, int train, float* out, void* stream);
+
+/* backward: g_out (P, n_out) f32 (gradient w.r.t. `out`) -> accumulates into grads (flat fp32, same
+ * layout as params), g_aux (P,16) f32 [.., d t(tau) at cols 4..] (NULL to skip), g_sky (P or N,3) summed
+ * by the caller.  Must follow snb_mlp_forward(train=1) on the same workspace. */
+int snb_mlp_backward(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
+                     int64_t n_points, const void* enc, const void* aux, const float* out,
+                     const float* g_out, int head_mask, float* grads, float* g_aux, void* stream);
+
+/* sky_color / embedding parameter gradients (tiny per-ray kernel).
+ *   sky   (N,3) f32 from K1 (NULL: skip the sky_color gradients)
+ *   g_out (P, n_out) f32 - columns 5:8 (sky) are summed per ray
+ *   g_aux (P,16) f32 from snb_mlp_backward - columns 4..4+tau are summed per ray and scattered into
+ *         g_t_table (vocab,tau) by ts = extras[:,3]  (NULL: skip the embedding gradient)
+ * replaces autograd through sky_color (satnerf.py:188-193,248) and nn.Embedding
+ * (semantic/components/rendering.py:42). */
+int snb_ray_param_backward(const snb_model* m, const float* params, const float* extras, const float* sky,
+                           const float* g_out, const float* g_aux, int n_rays, int n_samples, int n_out,
+                           int tau, int vocab, float* grads, float* g_t_table, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3  per-ray compositing
+ * replaces framework/util/rendering.py:4-34 (convert_sigmas) and the tails of `inference`
+ * (satnerf.py:73-96, rs_semantic.py:81-126, _logit_to_label :131-136) and their autograd.
+ * ---------------------------------------------------------------------------------------------- */
+int snb_composite_forward(const float* out, const float* z_vals, int n_rays, int n_samples, int n_out,
+                          int n_classes, float* rgb, float* depth, float* weights, float* transparency,
+                          float* sem_logits, int64_t* sem_label, void* stream);
+
+/* any g_* may be NULL (treated as zero).  g_out_direct: gradient flowing straight into the
+ * per-sample tensors (albedo/sun/sky/beta/sigmas views of `out`).  Writes g_out (P, n_out). */
+int snb_composite_backward(const float* out, const float* z_vals, int n_rays, int n_samples, int n_out,
+                           int n_classes, const float* g_rgb, const float* g_depth, const float* g_weights,
+                           const float* g_transparency, const float* g_sem_logits,
+                           const float* g_out_direct, float* g_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * optimiser step on the flat buffers (Adam, torch.optim.Adam semantics, weight_decay = 0:
+ * baseline/pipelines/base_ray_pipeline.py:246-269).  grad_scale multiplies the gradient first
+ * (1/world_size after the all-reduce). */
+int snb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * test hook: one bf16 GEMM through the tcgen05 kernel.  D = A (M,K) x B (N,K)^T (+ epilogue).
+ * a_mn / b_mn = 1: operand stored (K,M) / (K,N) row-major (the wgrad form).
+ * epi: 0 sin(w0*(acc+bias)) -> out0 bf16 [+ out1 = w0*cos(..)], 1 acc+bias -> bf16, 2 acc*mul -> bf16,
+ *      4 f32 rows (N==16), 5 f32 += acc (split-K reduce).
+ * ---------------------------------------------------------------------------------------------- */
+int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int N, int K,
+                  int a_mn, int b_mn, int epi, void* out0, void* out1, int64_t ldo, const void* mul,
+                  const float* bias, float w0, int splits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNB_H_ */

@@ -1,0 +1,199 @@
+"""torch.autograd.Function wrappers around the C ABI (K1 encode, K2 MLP, K3 composite).
+
+These replace the autograd graph PyTorch would build for the reference's eager implementation
+(SURVEY 8a row a10).  All tensors stay PyTorch-owned; the kernels run on the current stream.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, check, ptr, stream
+
+_T_STEPS = {}
+
+
+def t_steps(n_samples: int, device) -> torch.Tensor:
+    """linspace(0,1,S) computed by the host exactly as the reference does (rendering.py:95)."""
+    key = (n_samples, str(device))
+    if key not in _T_STEPS:
+        _T_STEPS[key] = torch.linspace(0, 1, n_samples).to(device)
+    return _T_STEPS[key]
+
+
+def _f32c(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def encode_rays(model, emb_weight, rays, extras, n_samples, u=None, z=None, seed=0, ray_offset=0, want_sc=False,
+                want_sky=True):
+    """K1: z_vals (N,S), enc / enc_sc (P, enc_ld) bf16, aux (P,16) bf16, sky (N,3).  No autograd here:
+    the embedding gradient comes back through the MLP backward's aux gradient."""
+    lib = _lib.load()
+    rays, extras = _f32c(rays), _f32c(extras)
+    n = rays.shape[0]
+    dev = rays.device
+    P = n * n_samples
+    z_given = z is not None
+    z_vals = _f32c(z).clone() if z_given else torch.empty(n, n_samples, dtype=torch.float32, device=dev)
+    enc = torch.empty(P, model.enc_ld, dtype=torch.bfloat16, device=dev)
+    enc_sc = torch.empty(P, model.enc_ld, dtype=torch.bfloat16, device=dev) if want_sc else None
+    aux = torch.empty(P, 16, dtype=torch.bfloat16, device=dev)
+    sky = torch.empty(n, 3, dtype=torch.float32, device=dev) if want_sky else None
+    w1, b1, w2, b2 = model.sky_params()
+    ew = _f32c(emb_weight.detach()) if emb_weight is not None else None
+    check(lib.snb_sample_encode(ptr(rays), ptr(extras), ptr(_f32c(u)), seed, ray_offset, ptr(t_steps(n_samples, dev)),
+                                ptr(ew), ew.shape[0] if ew is not None else 0, ew.shape[1] if ew is not None else 0,
+                                ptr(w1), ptr(b1), ptr(w2), ptr(b2), w1.shape[0], n, n_samples, model.kind,
+                                1 if z_given else 0, ptr(z_vals), ptr(enc), ptr(enc_sc), ptr(aux), ptr(sky), stream()),
+          "snb_sample_encode")
+    return z_vals, enc, enc_sc, aux, sky
+
+
+def _workspace(model, P, train, device):
+    lib = _lib.load()
+    nbytes = lib.snb_mlp_workspace_bytes(model._h, P, 1 if train else 0)
+    if train:
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    cache = model.__dict__.setdefault("_ws_infer", {})
+    key = (P, str(device))
+    if key not in cache:
+        cache.clear()
+        cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return cache[key]
+
+
+class MLPRays(torch.autograd.Function):
+    """K2 on ray samples: (flat params, embedding table) -> packed (P, n_out) head outputs."""
+
+    @staticmethod
+    def forward(ctx, flat, emb_weight, model, enc, aux, sky, extras, n_rays, n_samples, head_mask):
+        lib = _lib.load()
+        P = n_rays * n_samples
+        train = torch.is_grad_enabled() and (flat.requires_grad or (emb_weight is not None and emb_weight.requires_grad))
+        ws = _workspace(model, P, train, enc.device)
+        out = torch.empty(P, model.number_of_outputs, dtype=torch.float32, device=enc.device)
+        packed = model.packed()
+        check(lib.snb_mlp_forward(model._h, ptr(packed), ptr(ws), ws.numel(), P, ptr(enc), ptr(aux), ptr(sky),
+                                  n_samples, head_mask, 1 if train else 0, ptr(out), stream()), "snb_mlp_forward")
+        ctx.model, ctx.head_mask, ctx.dims = model, head_mask, (n_rays, n_samples)
+        ctx.has_emb = emb_weight is not None
+        if train:
+            ctx.save_for_backward(flat, packed, ws, enc, aux, sky, extras, out,
+                                  emb_weight if emb_weight is not None else flat.new_empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        model, head_mask = ctx.model, ctx.head_mask
+        n_rays, S = ctx.dims
+        P = n_rays * S
+        flat, packed, ws, enc, aux, sky, extras, out, emb_weight = ctx.saved_tensors
+        g_out = _f32c(g_out)
+        g_flat = torch.zeros_like(flat)
+        want_emb = ctx.has_emb and head_mask == HEADS_ALL
+        g_aux = torch.empty(P, 16, dtype=torch.float32, device=enc.device) if want_emb else None
+        check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws), ws.numel(), P, ptr(enc), ptr(aux), ptr(out),
+                                   ptr(g_out), head_mask, ptr(g_flat), ptr(g_aux), stream()), "snb_mlp_backward")
+        g_emb = torch.zeros_like(emb_weight) if want_emb else None
+        sky_arg = sky if head_mask == HEADS_ALL else None
+        if sky_arg is not None or g_aux is not None:
+            vocab, tau = (emb_weight.shape if want_emb else (1, 0))
+            check(lib.snb_ray_param_backward(model._h, ptr(flat.detach()), ptr(extras), ptr(sky_arg), ptr(g_out),
+                                             ptr(g_aux), n_rays, S, model.number_of_outputs, tau, vocab,
+                                             ptr(g_flat), ptr(g_emb), stream()), "snb_ray_param_backward")
+        return g_flat, g_emb, None, None, None, None, None, None, None, None
+
+
+class MLPPoints(torch.autograd.Function):
+    """K2 on caller-supplied points: the reference's Model.forward (satnerf.py:208, rs_semantic.py:260)."""
+
+    @staticmethod
+    def forward(ctx, flat, t, model, xyz, sun_d):
+        lib = _lib.load()
+        xyz, sun_d, tt = _f32c(xyz), _f32c(sun_d), _f32c(t.detach())
+        P = xyz.shape[0]
+        dev = xyz.device
+        train = torch.is_grad_enabled() and (flat.requires_grad or t.requires_grad)
+        enc = torch.empty(P, model.enc_ld, dtype=torch.bfloat16, device=dev)
+        aux = torch.empty(P, 16, dtype=torch.bfloat16, device=dev)
+        sky = torch.empty(P, 3, dtype=torch.float32, device=dev)
+        w1, b1, w2, b2 = model.sky_params()
+        check(lib.snb_encode_points(ptr(xyz), ptr(sun_d), ptr(tt), tt.shape[1], ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+                                    w1.shape[0], P, model.kind, ptr(enc), ptr(aux), ptr(sky), stream()),
+              "snb_encode_points")
+        ws = _workspace(model, P, train, dev)
+        out = torch.empty(P, model.number_of_outputs, dtype=torch.float32, device=dev)
+        packed = model.packed()
+        check(lib.snb_mlp_forward(model._h, ptr(packed), ptr(ws), ws.numel(), P, ptr(enc), ptr(aux), ptr(sky), 0,
+                                  HEADS_ALL, 1 if train else 0, ptr(out), stream()), "snb_mlp_forward")
+        ctx.model = model
+        if train:
+            ctx.save_for_backward(flat, packed, ws, enc, aux, sky, sun_d, out)
+            ctx.tau = tt.shape[1]
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        model = ctx.model
+        flat, packed, ws, enc, aux, sky, sun_d, out = ctx.saved_tensors
+        P = out.shape[0]
+        g_out = _f32c(g_out)
+        g_flat = torch.zeros_like(flat)
+        g_aux = torch.empty(P, 16, dtype=torch.float32, device=enc.device)
+        check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws), ws.numel(), P, ptr(enc), ptr(aux), ptr(out),
+                                   ptr(g_out), HEADS_ALL, ptr(g_flat), ptr(g_aux), stream()), "snb_mlp_backward")
+        extras = torch.cat([sun_d, torch.zeros(P, 1, device=sun_d.device)], 1).contiguous()
+        check(lib.snb_ray_param_backward(model._h, ptr(flat.detach()), ptr(extras), ptr(sky), ptr(g_out), None, P, 1,
+                                         model.number_of_outputs, 0, 1, ptr(g_flat), None, stream()),
+              "snb_ray_param_backward")
+        return g_flat, g_aux[:, 4:4 + ctx.tau].contiguous(), None, None, None
+
+
+def mlp_points(model, xyz, sun_d, t):
+    return MLPPoints.apply(model.flat, t, model, xyz, sun_d)
+
+
+class Composite(torch.autograd.Function):
+    """K3: packed head outputs (N,S,n_out) + z_vals (N,S) -> rgb, depth, weights, transparency,
+    semantic scores, label  (framework/util/rendering.py:4-34 + the tail of `inference`)."""
+
+    @staticmethod
+    def forward(ctx, out, z_vals, n_classes):
+        lib = _lib.load()
+        out, z_vals = _f32c(out), _f32c(z_vals)
+        n, s, n_out = out.shape
+        dev = out.device
+        rgb = torch.empty(n, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(n, dtype=torch.float32, device=dev)
+        weights = torch.empty(n, s, dtype=torch.float32, device=dev)
+        transp = torch.empty(n, s, dtype=torch.float32, device=dev)
+        sem = torch.empty(n, n_classes, dtype=torch.float32, device=dev)
+        label = torch.empty(n, dtype=torch.int64, device=dev)
+        check(lib.snb_composite_forward(ptr(out), ptr(z_vals), n, s, n_out, n_classes, ptr(rgb), ptr(depth),
+                                        ptr(weights), ptr(transp), ptr(sem) if n_classes else None,
+                                        ptr(label) if n_classes else None, stream()), "snb_composite_forward")
+        ctx.save_for_backward(out, z_vals)
+        ctx.n_classes = n_classes
+        ctx.mark_non_differentiable(label)
+        return rgb, depth, weights, transp, sem, label
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_w, g_t, g_sem, _g_label):
+        lib = _lib.load()
+        out, z_vals = ctx.saved_tensors
+        n, s, n_out = out.shape
+        g_out = torch.empty_like(out)
+        check(lib.snb_composite_backward(ptr(out), ptr(z_vals), n, s, n_out, ctx.n_classes, ptr(_f32c(g_rgb)),
+                                         ptr(_f32c(g_depth)), ptr(_f32c(g_w)), ptr(_f32c(g_t)),
+                                         ptr(_f32c(g_sem)) if ctx.n_classes else None, None, ptr(g_out), stream()),
+              "snb_composite_backward")
+        return g_out, None, None

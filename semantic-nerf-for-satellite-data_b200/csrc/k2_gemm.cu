@@ -1,0 +1,623 @@
+// K2 GEMM kernel - see k2_gemm.cuh for the design.  sm_100a only (tcgen05 / TMEM / TMA).
+#include "k2_gemm.cuh"
+
+#include <mutex>
+
+namespace snb {
+
+// ================================================================================================
+// PTX wrappers
+// ================================================================================================
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a trap (CUDA error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 8000000000LL) {  // ~4 s
+      printf("snb gemm: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, addr, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
+         ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ================================================================================================
+// the kernel
+// ================================================================================================
+struct TileCoord {
+  int m_blk, n_blk, kb0, kb1;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& a, int tile) {
+  TileCoord t;
+  t.n_blk = tile % a.n_tiles;
+  int r = tile / a.n_tiles;
+  t.m_blk = r % a.m_tiles;
+  int split = r / a.m_tiles;
+  t.kb0 = (int)(((long long)a.kb_total * split) / a.splits);
+  t.kb1 = (int)(((long long)a.kb_total * (split + 1)) / a.splits);
+  return t;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_constant__ GemmArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + GEMM_STAGES * GEMM_A_STAGE;
+  uint8_t* sStg = sB + GEMM_STAGES * GEMM_B_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sStg + GEMM_NUM_STAGING * GEMM_STAGING);
+  uint64_t* empty = full + GEMM_STAGES;
+  uint64_t* tfull = empty + GEMM_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* mfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mfull + GEMM_NUM_STAGING);
+
+  const int warp = threadIdx.x >> 5;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < args.nseg; ++s) tma_prefetch_desc(&args.tmA[s]);
+    tma_prefetch_desc(&args.tmB);
+    for (int s = 0; s < GEMM_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 128);
+    }
+    for (int s = 0; s < GEMM_NUM_STAGING; ++s) mbar_init(&mfull[s], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = args.m_tiles * args.n_tiles * args.splits;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const int nb_boxes = (args.block_n + 63) / 64;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(args, tile);
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], args.a_bytes + args.b_bytes);
+          uint8_t* a_dst = sA + stage * GEMM_A_STAGE;
+          uint8_t* b_dst = sB + stage * GEMM_B_STAGE;
+          if (!args.a_mn) {
+            int s = 0, kk = kb;
+            while (s + 1 < args.nseg && kk >= args.seg_kb[s]) {
+              kk -= args.seg_kb[s];
+              ++s;
+            }
+            tma_load_2d(a_dst, &args.tmA[s], &full[stage], kk * GEMM_BLOCK_K, t.m_blk * GEMM_BLOCK_M);
+          } else {
+            // [64 samples x 64 features] boxes; feature atoms 8 KB apart (UMMA LBO)
+            tma_load_2d(a_dst, &args.tmA[0], &full[stage], t.m_blk * GEMM_BLOCK_M, kb * GEMM_BLOCK_K);
+            tma_load_2d(a_dst + 8192, &args.tmA[0], &full[stage], t.m_blk * GEMM_BLOCK_M + 64, kb * GEMM_BLOCK_K);
+          }
+          if (!args.b_mn) {
+            tma_load_2d(b_dst, &args.tmB, &full[stage], kb * GEMM_BLOCK_K, t.n_blk * args.block_n);
+          } else {
+            for (int j = 0; j < nb_boxes; ++j)
+              tma_load_2d(b_dst + j * 8192, &args.tmB, &full[stage], t.n_blk * args.block_n + j * 64,
+                          kb * GEMM_BLOCK_K);
+          }
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ========================================
+    if (lane == 0) {
+      // cute::UMMA::InstrDescriptor: c_format f32 (1<<4), a/b format bf16 (1<<7, 1<<10),
+      // a_major bit 15, b_major bit 16, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)args.a_mn << 15) |
+                             ((uint32_t)args.b_mn << 16) | ((uint32_t)(args.block_n >> 3) << 17) |
+                             ((uint32_t)(GEMM_BLOCK_M >> 4) << 24);
+      // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused (1).  MN-major SW128: 8-k groups
+      // 1024 B apart (SBO), 64-element MN atoms 8192 B apart (LBO).
+      const uint32_t a_lbo = args.a_mn ? 8192u : 16u, b_lbo = args.b_mn ? 8192u : 16u;
+      const uint32_t a_kstep = args.a_mn ? 2048u : 32u, b_kstep = args.b_mn ? 2048u : 32u;
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const TileCoord t = decode_tile(args, tile);
+        const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * GEMM_MAX_BLOCK_N;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * GEMM_A_STAGE);
+          const uint32_t b_addr = smem_u32(sB + stage * GEMM_B_STAGE);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            const uint64_t adesc = umma_desc(a_addr + k * a_kstep, a_lbo, 1024u);
+            const uint64_t bdesc = umma_desc(b_addr + k * b_kstep, b_lbo, 1024u);
+            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
+          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================================== epilogue (128 threads) ============================
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read (warp id % 4)
+    const int row = quad * 32 + lane;   // row of the 128-row tile == TMEM lane
+    const int etid = threadIdx.x - 64;  // 0..127
+    const bool leader = (etid == 0);
+    const uint32_t stg0 = smem_u32(sStg);
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    uint32_t it = 0;
+    uint32_t cn = 0;  // running chunk counter = position in the staging ring
+
+    // EPI_MUL: chunks of the saved SIREN derivative are prefetched two chunks ahead into the ring
+    const uint32_t mul_chunks = (uint32_t)(args.block_n / 64);
+    auto mul_issue = [&](uint32_t n) {
+      const uint32_t tl = n / mul_chunks, c = n % mul_chunks;
+      const long long tile = (long long)blockIdx.x + (long long)tl * gridDim.x;
+      if (tile >= total_tiles) return;
+      const TileCoord t = decode_tile(args, (int)tile);
+      mbar_expect_tx(&mfull[n & 3], GEMM_STAGING);
+      tma_load_2d(sStg + (n & 3) * GEMM_STAGING, &args.tmMul, &mfull[n & 3], t.n_blk * args.block_n + (int)c * 64,
+                  t.m_blk * GEMM_BLOCK_M);
+    };
+    if (EPI == EPI_MUL && leader) {
+      mul_issue(0);
+      mul_issue(1);
+    }
+
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(args, tile);
+      const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * GEMM_MAX_BLOCK_N;
+      const int m0 = t.m_blk * GEMM_BLOCK_M;
+      const int n0 = t.n_blk * args.block_n;
+
+      if constexpr (EPI == EPI_SIN || EPI == EPI_LINEAR || EPI == EPI_MUL) {
+        // ---- bf16 outputs, 64-column chunks through the swizzled staging ring + TMA store -------
+        const bool two = (EPI == EPI_SIN) && args.two_out;
+        const int chunks = args.block_n / 64;
+        for (int c = 0; c < chunks; ++c, ++cn) {
+          uint32_t buf0, buf1 = 0;
+          if (two) {
+            buf0 = stg0 + (2 * (cn & 1)) * GEMM_STAGING;
+            buf1 = buf0 + GEMM_STAGING;
+          } else {
+            buf0 = stg0 + (cn & 3) * GEMM_STAGING;
+          }
+          if constexpr (EPI == EPI_MUL) mbar_wait(&mfull[cn & 3], (cn >> 2) & 1);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 64 + half * 32, v);
+            tc_wait_ld();
+            const int colbase = n0 + c * 64 + half * 32;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t off = row_off + ((((uint32_t)(half * 4 + g)) ^ sw) << 4);
+              float x[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
+              if constexpr (EPI == EPI_MUL) {
+                uint32_t q0, q1, q2, q3;
+                ld_shared_v4(buf0 + off, q0, q1, q2, q3);
+                x[0] *= bf16_lo(q0); x[1] *= bf16_hi(q0); x[2] *= bf16_lo(q1); x[3] *= bf16_hi(q1);
+                x[4] *= bf16_lo(q2); x[5] *= bf16_hi(q2); x[6] *= bf16_lo(q3); x[7] *= bf16_hi(q3);
+                st_shared_v4(buf0 + off, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
+                             pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+              } else {
+                if (args.bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + colbase + g * 8));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + colbase + g * 8 + 4));
+                  x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                  x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                }
+                if constexpr (EPI == EPI_SIN) {
+                  float s[8], cs[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float y = args.w0 * x[j];
+                    s[j] = __sinf(y);
+                    cs[j] = args.w0 * __cosf(y);
+                  }
+                  st_shared_v4(buf0 + off, pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]),
+                               pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
+                  if (two)
+                    st_shared_v4(buf1 + off, pack_bf16x2(cs[0], cs[1]), pack_bf16x2(cs[2], cs[3]),
+                                 pack_bf16x2(cs[4], cs[5]), pack_bf16x2(cs[6], cs[7]));
+                } else {
+                  st_shared_v4(buf0 + off, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
+                               pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+                }
+              }
+            }
+          }
+          fence_proxy_async();
+          if (EPI != EPI_MUL && leader) {
+            // the buffer(s) the NEXT chunk writes must have been drained by their previous TMA store
+            if (two) bulk_wait_read<0>();
+            else bulk_wait_read<2>();
+          }
+          epi_bar_sync();
+          if (leader) {
+            tma_store_2d(&args.tmO0, buf0, n0 + c * 64, m0);
+            if (two) tma_store_2d(&args.tmO1, buf1, n0 + c * 64, m0);
+            bulk_commit();
+            if constexpr (EPI == EPI_MUL) {
+              // ring slot (cn+2)&3 was last stored by chunk cn-2: allow {cn, cn-1} to be pending
+              bulk_wait_read<2>();
+              mul_issue(cn + 2);
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_HEADOUT) {
+        // ---- N=16 head pre-activations -> packed (P, n_out) fp32 rows ---------------------------
+        uint32_t v[16];
+        tmem_ld16(taddr, v);
+        tc_wait_ld();
+        float* stg = reinterpret_cast<float*>(sStg);
+        const int n_out = args.n_out;
+        const long long grow = (long long)m0 + row;
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + (args.bias ? __ldg(args.bias + j) : 0.f);
+        float* o = stg + row * n_out;
+        const int hm = args.head_mask;
+        // rs_semantic.py:282-284: rgb = sigmoid(.) * (1 + 2*0.001) - 0.001
+#pragma unroll
+        for (int j = 0; j < 3; ++j) o[j] = (hm & SNB_HEAD_RGB) ? (1.0f / (1.0f + expf(-x[j]))) * 1.002f - 0.001f : 0.f;
+        o[3] = (hm & SNB_HEAD_SIGMA) ? (x[3] > 20.f ? x[3] : log1pf(expf(x[3]))) : 0.f;
+        o[4] = (hm & SNB_HEAD_SUN) ? 1.0f / (1.0f + expf(-x[4])) : 0.f;
+        if ((hm & SNB_HEAD_SKY) && args.sky && grow < args.M) {
+          const long long ray = args.rows_per_ray > 0 ? grow / args.rows_per_ray : grow;
+          o[5] = __ldg(args.sky + ray * 3);
+          o[6] = __ldg(args.sky + ray * 3 + 1);
+          o[7] = __ldg(args.sky + ray * 3 + 2);
+        } else {
+          o[5] = o[6] = o[7] = 0.f;
+        }
+        o[8] = (hm & SNB_HEAD_BETA) ? (x[5] > 20.f ? x[5] : log1pf(expf(x[5]))) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
+          if (c < args.n_classes) {
+            const float s = x[6 + c];
+            o[9 + c] = (hm & SNB_HEAD_SEM) ? (args.sem_sigmoid ? 1.0f / (1.0f + expf(-s)) : s) : 0.f;
+          }
+        }
+        epi_bar_sync();
+        const int valid = min(GEMM_BLOCK_M, args.M - m0);
+        const int total = valid * n_out;
+        float* dst = args.out_packed + (size_t)m0 * n_out;
+        for (int i = etid; i < total; i += 128) dst[i] = stg[i];
+        epi_bar_sync();
+      } else if constexpr (EPI == EPI_F32ROWS) {
+        uint32_t v[16];
+        tmem_ld16(taddr, v);
+        tc_wait_ld();
+        const long long grow = (long long)m0 + row;
+        if (grow < args.M) {
+          float4* dst = reinterpret_cast<float4*>(args.f32out + grow * args.ldo);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      } else {  // EPI_WGRAD
+        if (args.block_n >= 32 && (args.block_n & 31) == 0 && args.f32out == nullptr) {
+          // fp32 tile -> 32-column swizzled chunks -> TMA reduce-add (split-K accumulation in L2)
+          const int chunks = args.block_n / 32;
+          for (int c = 0; c < chunks; ++c, ++cn) {
+            const uint32_t buf0 = stg0 + (cn & 3) * GEMM_STAGING;
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              st_shared_v4(buf0 + row_off + ((((uint32_t)g) ^ sw) << 4), v[4 * g], v[4 * g + 1], v[4 * g + 2],
+                           v[4 * g + 3]);
+            fence_proxy_async();
+            if (leader) bulk_wait_read<2>();
+            epi_bar_sync();
+            if (leader) {
+              tma_reduce_add_2d(&args.tmO0, buf0, n0 + c * 32, m0);
+              bulk_commit();
+            }
+          }
+        } else {
+          // narrow outputs (bias / per-ray columns, N = 16 or 64): red.global.add.f32
+          const long long grow = (long long)m0 + row;
+          for (int c0 = 0; c0 < args.block_n; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
+            tc_wait_ld();
+            if (grow < args.M) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int col = n0 + c0 + j;
+                if (col < args.N) atomicAdd(args.f32out + grow * args.ldo + col, __uint_as_float(v[j]));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+    }
+    if (leader) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    // no link-time dependency on libcuda: resolved through the runtime
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  SNB_CHECK_ARG(fn != nullptr, SNB_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  SNB_CHECK_ARG(ptr != nullptr && ((uintptr_t)ptr & 15) == 0, SNB_ERR_INVALID, "tensor map: base %p not 16B aligned", ptr);
+  SNB_CHECK_ARG((row_stride_bytes & 15) == 0, SNB_ERR_INVALID, "tensor map: row stride %llu not a multiple of 16",
+                (unsigned long long)row_stride_bytes);
+  SNB_CHECK_ARG(box_inner * elem_bytes <= 128 && box_outer <= 256 && box_outer >= 1, SNB_ERR_INVALID,
+                "tensor map: box %u x %u unsupported", box_inner, box_outer);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SNB_CHECK_ARG(r == CUDA_SUCCESS, SNB_ERR_INVALID,
+                "cuTensorMapEncodeTiled failed (%d): inner %llu outer %llu stride %llu box %ux%u", (int)r,
+                (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes, box_inner,
+                box_outer);
+  return 0;
+}
+
+void gemm_finalize(GemmArgs& a) {
+  a.m_tiles = (a.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  a.n_tiles = (a.N + a.block_n - 1) / a.block_n;
+  if (a.splits < 1) a.splits = 1;
+  if (a.splits > a.kb_total) a.splits = a.kb_total;
+  a.a_bytes = GEMM_A_STAGE;
+  a.b_bytes = a.b_mn ? (unsigned)(((a.block_n + 63) / 64) * 8192) : (unsigned)(a.block_n * GEMM_BLOCK_K * 2);
+}
+
+template <int EPI>
+static int launch_epi(const GemmArgs& a, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SNB_CUDA(cudaFuncSetAttribute(snb_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    attr_set = true;
+  }
+  snb_gemm_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(a);
+  return launch_status("snb_gemm_kernel");
+}
+
+int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
+  SNB_CHECK_ARG(a.block_n >= 16 && a.block_n <= GEMM_MAX_BLOCK_N && (a.block_n % 16) == 0, SNB_ERR_UNSUPPORTED,
+                "gemm: block_n %d unsupported", a.block_n);
+  SNB_CHECK_ARG(a.kb_total >= 1 && a.M >= 1 && a.N >= 1, SNB_ERR_INVALID, "gemm: empty problem");
+  SNB_CHECK_ARG(a.splits == 1 || epi == EPI_WGRAD, SNB_ERR_INVALID, "gemm: split-K only for the accumulate epilogue");
+  if (epi == EPI_SIN || epi == EPI_LINEAR || epi == EPI_MUL)
+    SNB_CHECK_ARG(a.block_n % 64 == 0, SNB_ERR_UNSUPPORTED, "gemm: bf16 epilogues need block_n %% 64 == 0");
+  if (epi == EPI_HEADOUT || epi == EPI_F32ROWS)
+    SNB_CHECK_ARG(a.block_n == 16 && a.n_tiles == 1, SNB_ERR_UNSUPPORTED, "gemm: row epilogues need N == 16");
+  const int sms = num_sms();
+  if (sms <= 0) return SNB_ERR_NO_DEVICE;
+  const long long tiles = (long long)a.m_tiles * a.n_tiles * a.splits;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  switch (epi) {
+    case EPI_SIN: return launch_epi<EPI_SIN>(a, grid, st);
+    case EPI_LINEAR: return launch_epi<EPI_LINEAR>(a, grid, st);
+    case EPI_MUL: return launch_epi<EPI_MUL>(a, grid, st);
+    case EPI_HEADOUT: return launch_epi<EPI_HEADOUT>(a, grid, st);
+    case EPI_F32ROWS: return launch_epi<EPI_F32ROWS>(a, grid, st);
+    case EPI_WGRAD: return launch_epi<EPI_WGRAD>(a, grid, st);
+  }
+  SNB_CHECK_ARG(false, SNB_ERR_INVALID, "gemm: unknown epilogue %d", epi);
+}
+
+}  // namespace snb
+
+// ---- test hook ---------------------------------------------------------------------------------
+extern "C" int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int N, int K,
+                             int a_mn, int b_mn, int epi, void* out0, void* out1, int64_t ldo, const void* mul,
+                             const float* bias, float w0, int splits, void* stream) {
+  using namespace snb;
+  SNB_CHECK_ARG(A && B && out0, SNB_ERR_INVALID, "gemm_bf16: null operand");
+  SNB_CHECK_ARG(M > 0 && N > 0 && K > 0 && M < (1ll << 31), SNB_ERR_INVALID, "gemm_bf16: bad shape");
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = (int)M;
+  a.N = N;
+  a.block_n = N >= 256 ? 256 : (N >= 128 ? 128 : (N >= 64 ? 64 : (N >= 32 && epi == EPI_WGRAD ? 32 : 16)));
+  a.kb_total = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  a.nseg = 1;
+  a.seg_kb[0] = a.kb_total;
+  a.a_mn = a_mn;
+  a.b_mn = b_mn;
+  a.splits = splits;
+  a.bias = bias;
+  a.w0 = w0;
+  a.two_out = (out1 != nullptr);
+  a.ldo = ldo;
+  int r;
+  // K-major operand: [rows, K] box {64 k, rows};  MN-major: [K, rows] box {64 rows, 64 k}
+  if (!a_mn) r = make_tmap_2d(&a.tmA[0], A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, GEMM_BLOCK_M);
+  else r = make_tmap_2d(&a.tmA[0], A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, 64);
+  if (r) return r;
+  if (!b_mn) r = make_tmap_2d(&a.tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, (uint32_t)a.block_n);
+  else r = make_tmap_2d(&a.tmB, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64);
+  if (r) return r;
+  if (epi == EPI_SIN || epi == EPI_LINEAR || epi == EPI_MUL) {
+    if ((r = make_tmap_2d(&a.tmO0, out0, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M))) return r;
+    if (out1 && (r = make_tmap_2d(&a.tmO1, out1, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M))) return r;
+    if (epi == EPI_MUL) {
+      SNB_CHECK_ARG(mul != nullptr, SNB_ERR_INVALID, "gemm_bf16: mul operand required");
+      if ((r = make_tmap_2d(&a.tmMul, mul, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M))) return r;
+    }
+  } else if (epi == EPI_F32ROWS) {
+    a.f32out = (float*)out0;
+  } else if (epi == EPI_WGRAD) {
+    if (a.block_n >= 32 && N % 32 == 0) {
+      if ((r = make_tmap_2d(&a.tmO0, out0, 4, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 4, 32, GEMM_BLOCK_M))) return r;
+    } else {
+      a.f32out = (float*)out0;
+    }
+  } else {
+    SNB_CHECK_ARG(false, SNB_ERR_UNSUPPORTED, "gemm_bf16: epilogue %d not available through the test hook", epi);
+  }
+  gemm_finalize(a);
+  return gemm_launch(a, epi, (cudaStream_t)stream);
+}

@@ -1,0 +1,75 @@
+// K2 - the dense contraction: a persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] (+)= sum over K-segments  A_seg[M,K_seg] * B[N,K]^T        (bf16 in, fp32 accumulate in TMEM)
+//
+// One CTA per SM, 6 warps:  warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+ TMEM owner),
+// warps 2-5 = epilogue (tcgen05.ld -> bias/activation -> bf16 -> swizzled smem -> TMA store).
+// Tile 128 x block_n (<=256) x 64, 3-stage smem ring, two 256-column TMEM accumulators so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Operand layouts (all 128-byte swizzle, filled by TMA, consumed through UMMA smem descriptors):
+//   K-major  : row-major [rows, K]   - forward (activations x weights) and dgrad (dY x W^T copy)
+//   MN-major : row-major [K, rows]   - wgrad (dY^T x X: the reduction runs over samples)
+// A may be split into up to 3 K-segments read from different tensors (skip connection
+// cat(enc,h), cat(f,sun_d,t) heads, the packed head-output layer) - no concat is materialised.
+#pragma once
+#include "snb_common.cuh"
+
+namespace snb {
+
+enum GemmEpi {
+  EPI_SIN = 0,      // h = sin(w0*(acc+bias)) -> out0 bf16 ; optional out1 = w0*cos(w0*(acc+bias)) bf16
+  EPI_LINEAR = 1,   // acc + bias -> out0 bf16
+  EPI_MUL = 2,      // acc * mul[m,n] -> out0 bf16           (dgrad through the saved SIREN derivative)
+  EPI_HEADOUT = 3,  // N=16 head pre-activations -> packed (P, n_out) fp32 with the reference activations
+  EPI_F32ROWS = 4,  // N=16 raw fp32 rows -> f32rows[M,16]
+  EPI_WGRAD = 5     // fp32 += acc (split-K): TMA reduce-add (block_n % 32 == 0, >= 32) or red.global
+};
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;
+constexpr int GEMM_MAX_BLOCK_N = 256;
+constexpr int GEMM_STAGES = 3;
+constexpr int GEMM_A_STAGE = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;      // 16 KB
+constexpr int GEMM_B_STAGE = GEMM_MAX_BLOCK_N * GEMM_BLOCK_K * 2;  // 32 KB
+constexpr int GEMM_STAGING = 16384;                                // one 128 x 128B swizzled chunk
+constexpr int GEMM_NUM_STAGING = 4;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_BYTES =
+    GEMM_STAGES * (GEMM_A_STAGE + GEMM_B_STAGE) + GEMM_NUM_STAGING * GEMM_STAGING + 256 + 1024;
+
+struct GemmArgs {
+  CUtensorMap tmA[3];
+  CUtensorMap tmB;
+  CUtensorMap tmO0, tmO1;
+  CUtensorMap tmMul;
+  int seg_kb[3];
+  int nseg;
+  int kb_total;
+  int M, N;
+  int block_n;
+  int m_tiles, n_tiles, splits;
+  int a_mn, b_mn;
+  unsigned a_bytes, b_bytes;
+  int two_out;
+  const float* bias;
+  float w0;
+  // EPI_HEADOUT
+  float* out_packed;
+  const float* sky;
+  int n_out, rows_per_ray, n_classes, sem_sigmoid, head_mask;
+  // EPI_F32ROWS / small-N EPI_WGRAD
+  float* f32out;
+  long long ldo;
+};
+
+// ---- host side -------------------------------------------------------------------------------
+// 2-D tensor map over a row-major [outer, inner] array, 128B swizzle, zero OOB fill.
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
+                 uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+
+// fills tile counts / byte counts from M, N, block_n, kb_total, splits, a_mn, b_mn
+void gemm_finalize(GemmArgs& a);
+int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st);
+
+}  // namespace snb

@@ -1,0 +1,752 @@
+// K2 - the SatNeRF / Semantic-NeRF MLP (8x512 SIREN trunk + heads) as chains of tcgen05 GEMMs.
+//
+// Follows baseline/models/satnerf.py:208-255 and semantic/models/rs_semantic.py:260-340.
+// Algebraic restructuring (results identical up to bf16 rounding):
+//   * skip connection cat(enc, h3) (satnerf.py:225-226): two K-segments into one accumulator;
+//   * first trunk layer (w0 = 30): bf16x2 split of input and weight, three K-segments
+//     hi*Whi + hi*Wlo + lo*Whi, so the phase 30*(W enc + b) keeps ~16 mantissa bits;
+//   * rgb / beta / semantic / sun first layers share their input f: ONE GEMM with N = 768/1024;
+//     their cat(f, sun_d) / cat(f, t) columns and biases ride in a 16-wide per-row K-segment `aux`;
+//   * the 1..C-wide output layers (sigma, rgb.2, sun.6, beta.2, semantic.2) are one N=16 GEMM over
+//     the K-segments [h7 | s3 | hh] whose epilogue applies softplus/sigmoid and writes the packed
+//     (P, 9+C) fp32 tensor in the reference's column order (rs_semantic.py:291-311).
+// Backward = dgrad GEMMs against transposed bf16 weight copies with the saved SIREN derivative
+// multiplied in the epilogue, and split-K wgrad GEMMs (reduction over samples, MN-major operands)
+// accumulated with TMA reduce-add; bias / per-ray-column gradients are dY^T x aux.
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "k2_gemm.cuh"
+
+namespace snb {
+
+constexpr int F = 512;    // fc_units (configs/pipelines/*.toml: fc_units = 512)
+constexpr int FL = 256;   // feat_last = fc_units / 2 (fc_use_full_features = false)
+constexpr int LAYERS = 8; // fc_layers, skip at layer 4
+
+struct TensorInfo {
+  std::string name;
+  int64_t offset;
+  int rows, cols;  // cols == 0: bias vector of `rows`
+};
+
+struct PackJob {
+  long long dst;  // element offset in the destination image
+  long long src;  // element offset in the flat fp32 source
+  int ldd, lds;
+  int rows, cols;  // destination extent
+  int transpose;   // dst[i, j] = src[j, i]
+  int mode;        // 0 bf16(v)  1 bf16(v - bf16(v))  2 fp32 copy  (pack);   unpack: accumulate
+};
+
+}  // namespace snb
+
+struct snb_model {
+  int kind, n_classes, sem_sigmoid;
+  int k0, enc_ld, hhw, n_out, tau;
+  int hh_rgb, hh_beta, hh_sem, hh_sun;
+  int kho;  // K of the head-output layer: 512 + 256 + hhw
+  std::vector<snb::TensorInfo> tensors;
+  int64_t n_params;
+  // packed bf16 image (element offsets) ----------------------------------------------------------
+  long long wl[8], wf, wh1, ws2, ws4, who;           // forward  [N, Kp]
+  long long tl[8], tf, th1, ts4, ts2, tho, taux;     // transposed copies for dgrad
+  long long packed_bf16_elems;
+  long long bias_off;  // fp32 section (byte offset = packed_bf16_elems*2), element offsets below
+  long long bl[8], bfe, bs2, bs4, bho;
+  long long bias_elems;
+  std::vector<snb::PackJob> pack_jobs;
+  // fp32 packed-gradient scratch (element offsets) ----------------------------------------------------
+  long long gl[8], gl4e, gf, gh1, gh1aux, gs2, gs4, ghot, gbl[8], gbf, gbs2, gbs4, gbho;
+  long long gscratch_elems;
+  std::vector<snb::PackJob> unpack_jobs;
+  int64_t find(const char* name) const {
+    for (auto& t : tensors)
+      if (t.name == name) return t.offset;
+    return -1;
+  }
+};
+
+namespace snb {
+
+// ---- pack / unpack kernels ----------------------------------------------------------------------
+constexpr int MAX_JOBS = 80;
+struct JobTable {
+  PackJob jobs[MAX_JOBS];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ JobTable tab, const float* __restrict__ src,
+                                                   __nv_bfloat16* __restrict__ dst_bf16, float* __restrict__ dst_f32) {
+  const PackJob& j = tab.jobs[blockIdx.y];
+  const long long n = (long long)j.rows * j.cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / j.cols), c = (int)(i - (long long)r * j.cols);
+    const float v = j.transpose ? src[j.src + (long long)c * j.lds + r] : src[j.src + (long long)r * j.lds + c];
+    const long long d = j.dst + (long long)r * j.ldd + c;
+    if (j.mode == 2) {
+      dst_f32[d] = v;
+    } else {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      dst_bf16[d] = (j.mode == 0) ? hi : __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+  }
+}
+
+// grads[dst(r,c)] += scratch[src(r,c)]  (same job description, roles of src/dst swapped)
+__global__ void __launch_bounds__(256) unpack_kernel(const __grid_constant__ JobTable tab,
+                                                     const float* __restrict__ scratch, float* __restrict__ grads) {
+  const PackJob& j = tab.jobs[blockIdx.y];
+  const long long n = (long long)j.rows * j.cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / j.cols), c = (int)(i - (long long)r * j.cols);
+    const float v = j.transpose ? scratch[j.src + (long long)c * j.lds + r] : scratch[j.src + (long long)r * j.lds + c];
+    grads[j.dst + (long long)r * j.ldd + c] += v;
+  }
+}
+
+// g_out (P, n_out) fp32 + out -> gradient w.r.t. the 16 head pre-activations (bf16) + their column sums
+__global__ void __launch_bounds__(256)
+head_grad_kernel(const float* __restrict__ out, const float* __restrict__ g_out, long long P, int n_out, int C,
+                 int sem_sigmoid, int head_mask, __nv_bfloat16* __restrict__ dpre, float* __restrict__ gb_ho) {
+  __shared__ float red[16];
+  if (threadIdx.x < 16) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (long long)gridDim.x * blockDim.x) {
+    const float* o = out + p * n_out;
+    const float* g = g_out + p * n_out;
+    float d[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) d[j] = 0.f;
+    if (head_mask & SNB_HEAD_RGB) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float s = (o[j] + 0.001f) * (1.0f / 1.002f);  // sigmoid value
+        d[j] = g[j] * 1.002f * s * (1.0f - s);
+      }
+    }
+    if (head_mask & SNB_HEAD_SIGMA) d[3] = g[3] * (1.0f - expf(-o[3]));  // softplus' = sigmoid(x) = 1 - exp(-softplus)
+    if (head_mask & SNB_HEAD_SUN) d[4] = g[4] * o[4] * (1.0f - o[4]);
+    if (head_mask & SNB_HEAD_BETA) d[5] = g[8] * (1.0f - expf(-o[8]));
+    if (head_mask & SNB_HEAD_SEM) {
+#pragma unroll
+      for (int c = 0; c < 10; ++c)
+        if (c < C) d[6 + c] = sem_sigmoid ? g[9 + c] * o[9 + c] * (1.0f - o[9 + c]) : g[9 + c];
+    }
+    __align__(16) __nv_bfloat16 row[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      row[j] = __float2bfloat16_rn(d[j]);
+      acc[j] += d[j];
+    }
+    uint4* dst = reinterpret_cast<uint4*>(dpre + p * 16);
+    dst[0] = reinterpret_cast<const uint4*>(row)[0];
+    dst[1] = reinterpret_cast<const uint4*>(row)[1];
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float v = acc[j];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[j], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) atomicAdd(gb_ho + threadIdx.x, red[threadIdx.x]);
+}
+
+// ---- model description ----------------------------------------------------------------------------
+static void add_tensor(snb_model* m, const std::string& name, int rows, int cols) {
+  m->tensors.push_back({name, m->n_params, rows, cols});
+  m->n_params += (int64_t)rows * (cols ? cols : 1);
+}
+
+static long long take(long long& cursor, long long elems) {
+  long long o = cursor;
+  cursor += (elems + 63) & ~63ll;  // keep every matrix 128-byte aligned
+  return o;
+}
+
+static void build_layout(snb_model* m) {
+  const int k0 = m->k0, hhw = m->hhw, tau = m->tau, C = m->n_classes;
+  const bool sem = m->kind == SNB_MODEL_SEMANTIC;
+  // ---- flat fp32 parameter order = reference state_dict order ----
+  m->n_params = 0;
+  for (int i = 0; i < LAYERS; ++i) {
+    int kin = i == 0 ? k0 : (i == 4 ? F + k0 : F);
+    add_tensor(m, "fc_net." + std::to_string(2 * i) + ".weight", F, kin);
+    add_tensor(m, "fc_net." + std::to_string(2 * i) + ".bias", F, 0);
+  }
+  add_tensor(m, "sigma_from_xyz.0.weight", 1, F);
+  add_tensor(m, "sigma_from_xyz.0.bias", 1, 0);
+  add_tensor(m, "feats_from_xyz.weight", F, F);
+  add_tensor(m, "feats_from_xyz.bias", F, 0);
+  add_tensor(m, "rgb_from_xyzdir.0.weight", FL, F);
+  add_tensor(m, "rgb_from_xyzdir.0.bias", FL, 0);
+  add_tensor(m, "rgb_from_xyzdir.2.weight", 3, FL);
+  add_tensor(m, "rgb_from_xyzdir.2.bias", 3, 0);
+  if (sem) {
+    add_tensor(m, "semantic_prediction.0.weight", FL, F);
+    add_tensor(m, "semantic_prediction.0.bias", FL, 0);
+    add_tensor(m, "semantic_prediction.2.weight", C, FL);
+    add_tensor(m, "semantic_prediction.2.bias", C, 0);
+  }
+  add_tensor(m, "sun_v_net.0.weight", FL, F + 3);
+  add_tensor(m, "sun_v_net.0.bias", FL, 0);
+  add_tensor(m, "sun_v_net.2.weight", FL, FL);
+  add_tensor(m, "sun_v_net.2.bias", FL, 0);
+  add_tensor(m, "sun_v_net.4.weight", FL, FL);
+  add_tensor(m, "sun_v_net.4.bias", FL, 0);
+  add_tensor(m, "sun_v_net.6.weight", 1, FL);
+  add_tensor(m, "sun_v_net.6.bias", 1, 0);
+  add_tensor(m, "sky_color.0.weight", FL, 3);
+  add_tensor(m, "sky_color.0.bias", FL, 0);
+  add_tensor(m, "sky_color.2.weight", 3, FL);
+  add_tensor(m, "sky_color.2.bias", 3, 0);
+  add_tensor(m, "beta_from_xyz.0.weight", FL, F + tau);
+  add_tensor(m, "beta_from_xyz.0.bias", FL, 0);
+  add_tensor(m, "beta_from_xyz.2.weight", 1, FL);
+  add_tensor(m, "beta_from_xyz.2.bias", 1, 0);
+
+  auto P = [&](const std::string& n) { return m->find(n.c_str()); };
+  auto fcw = [&](int i) { return P("fc_net." + std::to_string(2 * i) + ".weight"); };
+  auto fcb = [&](int i) { return P("fc_net." + std::to_string(2 * i) + ".bias"); };
+
+  // ---- packed bf16 image ----
+  long long cur = 0;
+  const int kl4 = 64 + F;       // packed K of layer 4: [enc(64) | h3(512)]
+  const int kh1 = F + 64;       // packed K of the fused head first layers: [f(512) | aux(64)]
+  const int ktf = F + 64;       // packed K of the feats dgrad: [dF(512) | dPre16(64)]
+  m->kho = F + FL + hhw;        // [h7 | s3 | hh]
+  for (int i = 0; i < LAYERS; ++i) m->wl[i] = take(cur, (long long)F * (i == 0 ? m->enc_ld : (i == 4 ? kl4 : F)));
+  m->wf = take(cur, (long long)F * F);
+  m->wh1 = take(cur, (long long)hhw * kh1);
+  m->ws2 = take(cur, (long long)FL * FL);
+  m->ws4 = take(cur, (long long)FL * FL);
+  m->who = take(cur, 16ll * m->kho);
+  for (int i = 1; i < LAYERS; ++i) m->tl[i] = take(cur, (long long)F * F);
+  m->tl[0] = -1;
+  m->tf = take(cur, (long long)F * ktf);
+  m->th1 = take(cur, (long long)F * hhw);
+  m->ts4 = take(cur, (long long)FL * FL);
+  m->ts2 = take(cur, (long long)FL * FL);
+  m->tho = take(cur, (long long)(FL + hhw) * 16);
+  m->taux = take(cur, 16ll * FL);
+  m->packed_bf16_elems = cur;
+  long long bc = 0;
+  for (int i = 0; i < LAYERS; ++i) m->bl[i] = take(bc, F);
+  m->bfe = take(bc, F);
+  m->bs2 = take(bc, FL);
+  m->bs4 = take(bc, FL);
+  m->bho = take(bc, 16);
+  m->bias_elems = bc;
+
+  auto& J = m->pack_jobs;
+  auto job = [&](long long dst, int ldd, long long src, int lds, int rows, int cols, int tr, int mode) {
+    J.push_back({dst, src, ldd, lds, rows, cols, tr, mode});
+  };
+  // layer 0: [hi | lo | hi] against the input row [hi | hi | lo]
+  job(m->wl[0], m->enc_ld, fcw(0), k0, F, k0, 0, 0);
+  job(m->wl[0] + k0, m->enc_ld, fcw(0), k0, F, k0, 0, 1);
+  job(m->wl[0] + 2 * k0, m->enc_ld, fcw(0), k0, F, k0, 0, 0);
+  for (int i = 1; i < LAYERS; ++i) {
+    if (i == 4) {
+      job(m->wl[4], kl4, fcw(4), F + k0, F, k0, 0, 0);            // enc columns (first k0 of the 64-wide segment)
+      job(m->wl[4] + 64, kl4, fcw(4) + k0, F + k0, F, F, 0, 0);   // h3 columns
+      job(m->tl[4], F, fcw(4) + k0, F + k0, F, F, 1, 0);
+    } else {
+      job(m->wl[i], F, fcw(i), F, F, F, 0, 0);
+      job(m->tl[i], F, fcw(i), F, F, F, 1, 0);
+    }
+  }
+  job(m->wf, F, P("feats_from_xyz.weight"), F, F, F, 0, 0);
+  job(m->tf, ktf, P("feats_from_xyz.weight"), F, F, F, 1, 0);
+  job(m->tf + F + 3, ktf, P("sigma_from_xyz.0.weight"), F, F, 1, 1, 0);  // dPre16 column 3 = sigma
+  // fused head first layers: rows [rgb | beta | (sem) | sun]
+  struct Blk { int row; const char* w; const char* b; int kin; };
+  std::vector<Blk> blks = {{m->hh_rgb, "rgb_from_xyzdir.0", "rgb_from_xyzdir.0", F},
+                           {m->hh_beta, "beta_from_xyz.0", "beta_from_xyz.0", F + tau},
+                           {m->hh_sun, "sun_v_net.0", "sun_v_net.0", F + 3}};
+  if (sem) blks.push_back({m->hh_sem, "semantic_prediction.0", "semantic_prediction.0", F});
+  for (auto& b : blks) {
+    const long long w = P(std::string(b.w) + ".weight"), bb = P(std::string(b.b) + ".bias");
+    job(m->wh1 + (long long)b.row * kh1, kh1, w, b.kin, FL, F, 0, 0);
+    job(m->wh1 + (long long)b.row * kh1 + F, kh1, bb, 1, FL, 1, 0, 0);  // aux column 0 = 1 -> bias
+    job(m->th1 + b.row, hhw, w, b.kin, F, FL, 1, 0);
+  }
+  job(m->wh1 + (long long)m->hh_sun * kh1 + F + 1, kh1, P("sun_v_net.0.weight") + F, F + 3, FL, 3, 0, 0);
+  job(m->wh1 + (long long)m->hh_beta * kh1 + F + 4, kh1, P("beta_from_xyz.0.weight") + F, F + tau, FL, tau, 0, 0);
+  job(m->taux + 4 * FL, FL, P("beta_from_xyz.0.weight") + F, F + tau, tau, FL, 1, 0);
+  job(m->ws2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 0, 0);
+  job(m->ts2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 1, 0);
+  job(m->ws4, FL, P("sun_v_net.4.weight"), FL, FL, FL, 0, 0);
+  job(m->ts4, FL, P("sun_v_net.4.weight"), FL, FL, FL, 1, 0);
+  // head output layer: rows [rgb0-2, sigma, sun, beta, sem...], K = [h7 | s3 | hh]
+  const int kho = m->kho;
+  job(m->who + 3ll * kho, kho, P("sigma_from_xyz.0.weight"), F, 1, F, 0, 0);
+  job(m->who + 4ll * kho + F, kho, P("sun_v_net.6.weight"), FL, 1, FL, 0, 0);
+  job(m->who + 0ll * kho + F + FL + m->hh_rgb, kho, P("rgb_from_xyzdir.2.weight"), FL, 3, FL, 0, 0);
+  job(m->who + 5ll * kho + F + FL + m->hh_beta, kho, P("beta_from_xyz.2.weight"), FL, 1, FL, 0, 0);
+  if (sem) job(m->who + 6ll * kho + F + FL + m->hh_sem, kho, P("semantic_prediction.2.weight"), FL, C, FL, 0, 0);
+  // transposed head output for dgrad: rows = [s3 | hh] features, 16 columns
+  job(m->tho + 4, 16, P("sun_v_net.6.weight"), FL, FL, 1, 1, 0);
+  job(m->tho + (long long)(FL + m->hh_rgb) * 16 + 0, 16, P("rgb_from_xyzdir.2.weight"), FL, FL, 3, 1, 0);
+  job(m->tho + (long long)(FL + m->hh_beta) * 16 + 5, 16, P("beta_from_xyz.2.weight"), FL, FL, 1, 1, 0);
+  if (sem) job(m->tho + (long long)(FL + m->hh_sem) * 16 + 6, 16, P("semantic_prediction.2.weight"), FL, FL, C, 1, 0);
+  // fp32 biases
+  for (int i = 0; i < LAYERS; ++i) job(m->bl[i], 1, fcb(i), 1, F, 1, 0, 2);
+  job(m->bfe, 1, P("feats_from_xyz.bias"), 1, F, 1, 0, 2);
+  job(m->bs2, 1, P("sun_v_net.2.bias"), 1, FL, 1, 0, 2);
+  job(m->bs4, 1, P("sun_v_net.4.bias"), 1, FL, 1, 0, 2);
+  job(m->bho + 0, 1, P("rgb_from_xyzdir.2.bias"), 1, 3, 1, 0, 2);
+  job(m->bho + 3, 1, P("sigma_from_xyz.0.bias"), 1, 1, 1, 0, 2);
+  job(m->bho + 4, 1, P("sun_v_net.6.bias"), 1, 1, 1, 0, 2);
+  job(m->bho + 5, 1, P("beta_from_xyz.2.bias"), 1, 1, 1, 0, 2);
+  if (sem) job(m->bho + 6, 1, P("semantic_prediction.2.bias"), 1, C, 1, 0, 2);
+
+  // ---- fp32 packed-gradient scratch + unpack jobs (grads[dst] += scratch[src]) ----
+  long long gc = 0;
+  for (int i = 0; i < LAYERS; ++i) m->gl[i] = take(gc, (long long)F * (i == 0 ? 64 : F));
+  m->gl4e = take(gc, (long long)F * 64);
+  m->gf = take(gc, (long long)F * F);
+  m->gh1 = take(gc, (long long)hhw * F);
+  m->gh1aux = take(gc, (long long)hhw * 16);
+  m->gs2 = take(gc, (long long)FL * FL);
+  m->gs4 = take(gc, (long long)FL * FL);
+  m->ghot = take(gc, (long long)kho * 16);
+  for (int i = 0; i < LAYERS; ++i) m->gbl[i] = take(gc, (long long)F * 16);
+  m->gbf = take(gc, (long long)F * 16);
+  m->gbs2 = take(gc, (long long)FL * 16);
+  m->gbs4 = take(gc, (long long)FL * 16);
+  m->gbho = take(gc, 16);
+  m->gscratch_elems = gc;
+  auto& U = m->unpack_jobs;
+  auto ujob = [&](long long dst, int ldd, long long src, int lds, int rows, int cols, int tr) {
+    U.push_back({dst, src, ldd, lds, rows, cols, tr, 0});
+  };
+  ujob(fcw(0), k0, m->gl[0], 64, F, k0, 0);
+  for (int i = 1; i < LAYERS; ++i) {
+    if (i == 4) {
+      ujob(fcw(4), F + k0, m->gl4e, 64, F, k0, 0);
+      ujob(fcw(4) + k0, F + k0, m->gl[4], F, F, F, 0);
+    } else {
+      ujob(fcw(i), F, m->gl[i], F, F, F, 0);
+    }
+  }
+  for (int i = 0; i < LAYERS; ++i) ujob(fcb(i), 1, m->gbl[i], 16, F, 1, 0);
+  ujob(P("feats_from_xyz.weight"), F, m->gf, F, F, F, 0);
+  ujob(P("feats_from_xyz.bias"), 1, m->gbf, 16, F, 1, 0);
+  for (auto& b : blks) {
+    const long long w = P(std::string(b.w) + ".weight"), bb = P(std::string(b.b) + ".bias");
+    ujob(w, b.kin, m->gh1 + (long long)b.row * F, F, FL, F, 0);
+    ujob(bb, 1, m->gh1aux + (long long)b.row * 16, 16, FL, 1, 0);
+  }
+  ujob(P("sun_v_net.0.weight") + F, F + 3, m->gh1aux + (long long)m->hh_sun * 16 + 1, 16, FL, 3, 0);
+  ujob(P("beta_from_xyz.0.weight") + F, F + tau, m->gh1aux + (long long)m->hh_beta * 16 + 4, 16, FL, tau, 0);
+  ujob(P("sun_v_net.2.weight"), FL, m->gs2, FL, FL, FL, 0);
+  ujob(P("sun_v_net.2.bias"), 1, m->gbs2, 16, FL, 1, 0);
+  ujob(P("sun_v_net.4.weight"), FL, m->gs4, FL, FL, FL, 0);
+  ujob(P("sun_v_net.4.bias"), 1, m->gbs4, 16, FL, 1, 0);
+  // head output layer: scratch is transposed [K features, 16]
+  ujob(P("sigma_from_xyz.0.weight"), F, m->ghot + 3, 16, 1, F, 1);
+  ujob(P("sun_v_net.6.weight"), FL, m->ghot + (long long)F * 16 + 4, 16, 1, FL, 1);
+  ujob(P("rgb_from_xyzdir.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_rgb) * 16 + 0, 16, 3, FL, 1);
+  ujob(P("beta_from_xyz.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_beta) * 16 + 5, 16, 1, FL, 1);
+  if (sem) ujob(P("semantic_prediction.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_sem) * 16 + 6, 16, C, FL, 1);
+  ujob(P("rgb_from_xyzdir.2.bias"), 1, m->gbho + 0, 1, 3, 1, 0);
+  ujob(P("sigma_from_xyz.0.bias"), 1, m->gbho + 3, 1, 1, 1, 0);
+  ujob(P("sun_v_net.6.bias"), 1, m->gbho + 4, 1, 1, 1, 0);
+  ujob(P("beta_from_xyz.2.bias"), 1, m->gbho + 5, 1, 1, 1, 0);
+  if (sem) ujob(P("semantic_prediction.2.bias"), 1, m->gbho + 6, 1, C, 1, 0);
+}
+
+static int run_jobs(const std::vector<PackJob>& jobs, bool unpack, const float* src, void* dst_bf16, float* dst_f32,
+                    cudaStream_t st) {
+  for (size_t base = 0; base < jobs.size(); base += MAX_JOBS) {
+    JobTable tab;
+    tab.n = (int)std::min<size_t>(MAX_JOBS, jobs.size() - base);
+    for (int i = 0; i < tab.n; ++i) tab.jobs[i] = jobs[base + i];
+    dim3 grid(64, tab.n);
+    if (unpack) unpack_kernel<<<grid, 256, 0, st>>>(tab, src, dst_f32);
+    else pack_kernel<<<grid, 256, 0, st>>>(tab, src, (__nv_bfloat16*)dst_bf16, dst_f32);
+    if (int r = launch_status(unpack ? "unpack_kernel" : "pack_kernel")) return r;
+  }
+  return 0;
+}
+
+// ---- workspace layout -----------------------------------------------------------------------------
+struct Workspace {
+  // all offsets in bytes from the workspace base; 0-sized members are absent
+  size_t h[8], c[8], f, hh, chh, s2, cs2, s3, cs3;  // forward (c*: saved SIREN derivatives, train only)
+  size_t dpre, dy[2], df, dyhh, dys3, dys2;         // backward
+  size_t gscratch;                                  // fp32 packed gradients
+  size_t total;
+};
+
+static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
+  Workspace w;
+  memset(&w, 0, sizeof(w));
+  size_t cur = 0;
+  auto take_b = [&](size_t bytes) {
+    size_t o = cur;
+    cur += (bytes + 1023) & ~(size_t)1023;
+    return o;
+  };
+  const size_t rowF = (size_t)P * F * 2, rowFL = (size_t)P * FL * 2, rowHH = (size_t)P * m->hhw * 2;
+  if (train) {
+    for (int i = 0; i < 8; ++i) w.h[i] = take_b(rowF);
+    for (int i = 0; i < 8; ++i) w.c[i] = take_b(rowF);
+  } else {
+    size_t a = take_b(rowF), b = take_b(rowF);
+    for (int i = 0; i < 8; ++i) w.h[i] = (i & 1) ? b : a;  // ping-pong (layer 4 reads h3, writes h4: distinct)
+  }
+  w.f = take_b(rowF);
+  w.hh = take_b(rowHH);
+  w.s2 = take_b(rowFL);
+  w.s3 = take_b(rowFL);
+  if (train) {
+    w.chh = take_b(rowHH);
+    w.cs2 = take_b(rowFL);
+    w.cs3 = take_b(rowFL);
+    w.dpre = take_b((size_t)P * 16 * 2);
+    w.dy[0] = take_b(rowF);
+    w.dy[1] = take_b(rowF);
+    w.df = take_b(rowF);
+    w.dyhh = take_b(rowHH);
+    w.dys3 = take_b(rowFL);
+    w.dys2 = take_b(rowFL);
+    w.gscratch = take_b((size_t)m->gscratch_elems * 4);
+  }
+  w.total = cur;
+  return w;
+}
+
+// ---- GEMM plan builders -----------------------------------------------------------------------------
+struct Seg {
+  const void* ptr;   // bf16, row-major, first column of the segment
+  long long ld;      // leading dimension (elements)
+  int cols;          // readable columns from ptr (TMA zero-fills beyond)
+  int kb;            // 64-wide k-blocks this segment contributes
+};
+
+struct Plan {
+  std::vector<GemmArgs> g;
+  std::vector<int> epi;
+  int rc = 0;
+  GemmArgs& add(int e) {
+    g.emplace_back();
+    memset(&g.back(), 0, sizeof(GemmArgs));
+    epi.push_back(e);
+    return g.back();
+  }
+  void chk(int r) {
+    if (r && !rc) rc = r;
+  }
+};
+
+// D[M,N] = sum_seg A_seg[M,K] * B[N,Kp]^T  (K-major operands)
+static GemmArgs& add_kmajor(Plan& p, int epi, long long M, int N, const Seg* segs, int nseg, const void* B, long long ldb,
+                            int b_cols, void* out0, void* out1, long long ldo, const void* mul, long long ldmul,
+                            const float* bias, float w0) {
+  GemmArgs& a = p.add(epi);
+  a.M = (int)M;
+  a.N = N;
+  a.block_n = N >= 256 ? 256 : N;
+  a.nseg = nseg;
+  a.kb_total = 0;
+  for (int s = 0; s < nseg; ++s) {
+    a.seg_kb[s] = segs[s].kb;
+    a.kb_total += segs[s].kb;
+    p.chk(make_tmap_2d(&a.tmA[s], segs[s].ptr, 2, (uint64_t)segs[s].cols, (uint64_t)M, (uint64_t)segs[s].ld * 2, 64,
+                       GEMM_BLOCK_M));
+  }
+  p.chk(make_tmap_2d(&a.tmB, B, 2, (uint64_t)b_cols, (uint64_t)N, (uint64_t)ldb * 2, 64, (uint32_t)a.block_n));
+  if (epi == EPI_SIN || epi == EPI_LINEAR || epi == EPI_MUL) {
+    p.chk(make_tmap_2d(&a.tmO0, out0, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
+    if (out1) p.chk(make_tmap_2d(&a.tmO1, out1, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
+    if (epi == EPI_MUL)
+      p.chk(make_tmap_2d(&a.tmMul, mul, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldmul * 2, 64, GEMM_BLOCK_M));
+  }
+  a.two_out = out1 != nullptr;
+  a.bias = bias;
+  a.w0 = w0;
+  a.splits = 1;
+  gemm_finalize(a);
+  return a;
+}
+
+// G[Mf,Nf] += dY[P,Mf]^T * X[P,Nf]   (reduction over the P samples; MN-major operands; split-K)
+static void add_wgrad(Plan& p, int Mf, int Nf, const void* dY, long long ld_dy, const void* X, long long ld_x,
+                      long long P, float* G, long long ldg, int sms) {
+  GemmArgs& a = p.add(EPI_WGRAD);
+  a.M = Mf;
+  a.N = Nf;
+  a.block_n = Nf >= 256 ? 256 : Nf;
+  a.nseg = 1;
+  a.kb_total = (int)((P + 63) / 64);
+  a.seg_kb[0] = a.kb_total;
+  a.a_mn = 1;
+  a.b_mn = 1;
+  p.chk(make_tmap_2d(&a.tmA[0], dY, 2, (uint64_t)Mf, (uint64_t)P, (uint64_t)ld_dy * 2, 64, 64));
+  p.chk(make_tmap_2d(&a.tmB, X, 2, (uint64_t)Nf, (uint64_t)P, (uint64_t)ld_x * 2, 64, 64));
+  if (a.block_n >= 32 && Nf % 32 == 0) {
+    p.chk(make_tmap_2d(&a.tmO0, G, 4, (uint64_t)Nf, (uint64_t)Mf, (uint64_t)ldg * 4, 32, GEMM_BLOCK_M));
+  } else {
+    a.f32out = G;
+    a.ldo = ldg;
+  }
+  const int tiles = ((Mf + 127) / 128) * ((Nf + a.block_n - 1) / a.block_n);
+  int splits = (sms + tiles - 1) / tiles;
+  // narrow (N=16) products are operand-read bound, not MMA bound: a quarter of the CTAs is plenty
+  if (Nf <= 16) splits = (splits + 3) / 4;
+  // keep at least 8 k-blocks per split so the accumulate traffic stays small against the operand reads
+  const int max_splits = a.kb_total / 8 > 0 ? a.kb_total / 8 : 1;
+  a.splits = splits < max_splits ? splits : max_splits;
+  if (a.splits < 1) a.splits = 1;
+  gemm_finalize(a);
+}
+
+static int run_plan(const Plan& p, cudaStream_t st) {
+  if (p.rc) return p.rc;
+  for (size_t i = 0; i < p.g.size(); ++i)
+    if (int r = gemm_launch(p.g[i], p.epi[i], st)) return r;
+  return 0;
+}
+
+static bool mask_supported(int head_mask) {
+  return head_mask == SNB_HEADS_ALL || head_mask == SNB_HEADS_SOLAR || head_mask == SNB_HEADS_DEPTH;
+}
+
+}  // namespace snb
+
+using namespace snb;
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid) {
+  SNB_CHECK_ARG(out != nullptr, SNB_ERR_INVALID, "model_create: null out");
+  SNB_CHECK_ARG(model_kind == SNB_MODEL_SATNERF || model_kind == SNB_MODEL_SEMANTIC, SNB_ERR_INVALID,
+                "model_create: bad kind %d", model_kind);
+  if (model_kind == SNB_MODEL_SATNERF) n_classes = 0;
+  SNB_CHECK_ARG(n_classes >= 0 && n_classes <= 10 && (model_kind == SNB_MODEL_SATNERF || n_classes >= 1),
+                SNB_ERR_UNSUPPORTED, "model_create: n_classes %d outside [1,10]", n_classes);
+  snb_model* m = new snb_model();
+  m->kind = model_kind;
+  m->n_classes = n_classes;
+  m->sem_sigmoid = semantic_sigmoid;
+  m->tau = 4;  // t_embedding_tau (configs/pipelines/*.toml)
+  m->k0 = model_kind == SNB_MODEL_SEMANTIC ? 60 : 3;
+  m->enc_ld = model_kind == SNB_MODEL_SEMANTIC ? 192 : 64;
+  m->n_out = 9 + n_classes;
+  // hidden block order of the fused head first layers: [rgb | beta | (sem) | sun]
+  m->hh_rgb = 0;
+  m->hh_beta = FL;
+  m->hh_sem = 2 * FL;
+  m->hhw = model_kind == SNB_MODEL_SEMANTIC ? 4 * FL : 3 * FL;
+  m->hh_sun = m->hhw - FL;
+  build_layout(m);
+  *out = m;
+  return 0;
+}
+
+extern "C" void snb_model_destroy(snb_model* m) { delete m; }
+extern "C" int64_t snb_model_param_count(const snb_model* m) { return m ? m->n_params : -1; }
+extern "C" int snb_model_num_tensors(const snb_model* m) { return m ? (int)m->tensors.size() : -1; }
+extern "C" int snb_model_tensor_info(const snb_model* m, int i, const char** name, int64_t* offset, int* rows,
+                                     int* cols) {
+  SNB_CHECK_ARG(m && i >= 0 && i < (int)m->tensors.size(), SNB_ERR_INVALID, "tensor_info: bad index");
+  if (name) *name = m->tensors[i].name.c_str();
+  if (offset) *offset = m->tensors[i].offset;
+  if (rows) *rows = m->tensors[i].rows;
+  if (cols) *cols = m->tensors[i].cols;
+  return 0;
+}
+extern "C" size_t snb_model_packed_bytes(const snb_model* m) {
+  return m ? (size_t)m->packed_bf16_elems * 2 + (size_t)m->bias_elems * 4 : 0;
+}
+
+extern "C" int snb_model_pack(const snb_model* m, const float* params, void* packed, void* stream) {
+  SNB_CHECK_ARG(m && params && packed, SNB_ERR_INVALID, "model_pack: null argument");
+  SNB_CHECK_ARG(((uintptr_t)packed & 127) == 0, SNB_ERR_INVALID, "model_pack: packed image must be 128-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  SNB_CUDA(cudaMemsetAsync(packed, 0, snb_model_packed_bytes(m), st));
+  float* f32 = reinterpret_cast<float*>(reinterpret_cast<char*>(packed) + (size_t)m->packed_bf16_elems * 2);
+  return run_jobs(m->pack_jobs, false, params, packed, f32, st);
+}
+
+extern "C" size_t snb_mlp_workspace_bytes(const snb_model* m, int64_t n_points, int train) {
+  if (!m || n_points <= 0) return 0;
+  return layout_workspace(m, n_points, train).total;
+}
+
+extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
+                               int64_t n_points, const void* enc, const void* aux, const float* sky,
+                               int rows_per_ray, int head_mask, int train, float* out, void* stream) {
+  SNB_CHECK_ARG(m && packed && workspace && enc && out, SNB_ERR_INVALID, "mlp_forward: null argument");
+  SNB_CHECK_ARG(n_points > 0 && n_points < (1ll << 31), SNB_ERR_INVALID, "mlp_forward: n_points out of range");
+  SNB_CHECK_ARG(mask_supported(head_mask), SNB_ERR_UNSUPPORTED,
+                "mlp_forward: head_mask %d (supported: ALL=63, SOLAR=5, DEPTH=1)", head_mask);
+  SNB_CHECK_ARG(head_mask == SNB_HEADS_DEPTH || aux != nullptr, SNB_ERR_INVALID, "mlp_forward: aux required");
+  SNB_CHECK_ARG((((uintptr_t)workspace | (uintptr_t)packed | (uintptr_t)enc) & 127) == 0, SNB_ERR_INVALID,
+                "mlp_forward: workspace/packed/enc must be 128-byte aligned");
+  const Workspace w = layout_workspace(m, n_points, train);
+  SNB_CHECK_ARG(workspace_bytes >= w.total, SNB_ERR_WORKSPACE, "mlp_forward: workspace %zu < required %zu",
+                workspace_bytes, w.total);
+  const long long P = n_points;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const __nv_bfloat16* pk = reinterpret_cast<const __nv_bfloat16*>(packed);
+  const float* pb = reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + (size_t)m->packed_bf16_elems * 2);
+  auto H = [&](int i) { return (void*)(ws + w.h[i]); };
+  auto Cs = [&](int i) { return train ? (void*)(ws + w.c[i]) : (void*)nullptr; };
+  const int hhw = m->hhw;
+  Plan p;
+  // trunk ----------------------------------------------------------------------------------------
+  {
+    Seg s0[1] = {{enc, m->enc_ld, m->enc_ld, m->enc_ld / 64}};
+    add_kmajor(p, EPI_SIN, P, F, s0, 1, pk + m->wl[0], m->enc_ld, m->enc_ld, H(0), Cs(0), F, nullptr, 0, pb + m->bl[0], 30.0f);
+  }
+  for (int i = 1; i < LAYERS; ++i) {
+    if (i == 4) {
+      Seg s[2] = {{enc, m->enc_ld, 64, 1}, {H(3), F, F, F / 64}};
+      add_kmajor(p, EPI_SIN, P, F, s, 2, pk + m->wl[4], 64 + F, 64 + F, H(4), Cs(4), F, nullptr, 0, pb + m->bl[4], 1.0f);
+    } else {
+      Seg s[1] = {{H(i - 1), F, F, F / 64}};
+      add_kmajor(p, EPI_SIN, P, F, s, 1, pk + m->wl[i], F, F, H(i), Cs(i), F, nullptr, 0, pb + m->bl[i], 1.0f);
+    }
+  }
+  const bool need_f = head_mask != SNB_HEADS_DEPTH;
+  const bool all = head_mask == SNB_HEADS_ALL;
+  if (need_f) {
+    Seg s[1] = {{H(7), F, F, F / 64}};
+    add_kmajor(p, EPI_LINEAR, P, F, s, 1, pk + m->wf, F, F, ws + w.f, nullptr, F, nullptr, 0, pb + m->bfe, 1.0f);
+    // fused head first layers (all blocks, or only the sun block for the solar pass)
+    const int r0 = all ? 0 : m->hh_sun, n = all ? hhw : FL;
+    Seg s1[2] = {{ws + w.f, F, F, F / 64}, {aux, 16, 16, 1}};
+    add_kmajor(p, EPI_SIN, P, n, s1, 2, pk + m->wh1 + (long long)r0 * (F + 64), F + 64, F + 64,
+               ws + w.hh + (size_t)r0 * 2, train ? ws + w.chh + (size_t)r0 * 2 : nullptr, hhw, nullptr, 0, nullptr, 1.0f);
+    Seg s2[1] = {{ws + w.hh + (size_t)m->hh_sun * 2, hhw, FL, FL / 64}};
+    add_kmajor(p, EPI_SIN, P, FL, s2, 1, pk + m->ws2, FL, FL, ws + w.s2, train ? ws + w.cs2 : nullptr, FL, nullptr, 0,
+               pb + m->bs2, 1.0f);
+    Seg s3[1] = {{ws + w.s2, FL, FL, FL / 64}};
+    add_kmajor(p, EPI_SIN, P, FL, s3, 1, pk + m->ws4, FL, FL, ws + w.s3, train ? ws + w.cs3 : nullptr, FL, nullptr, 0,
+               pb + m->bs4, 1.0f);
+  }
+  {
+    Seg s[3] = {{H(7), F, F, F / 64}, {ws + w.s3, FL, FL, FL / 64}, {ws + w.hh, hhw, hhw, hhw / 64}};
+    const int nseg = head_mask == SNB_HEADS_DEPTH ? 1 : (all ? 3 : 2);
+    GemmArgs& a = add_kmajor(p, EPI_HEADOUT, P, 16, s, nseg, pk + m->who, m->kho, m->kho, nullptr, nullptr, 0, nullptr, 0,
+                             pb + m->bho, 1.0f);
+    a.out_packed = out;
+    a.sky = sky;
+    a.n_out = m->n_out;
+    a.rows_per_ray = rows_per_ray;
+    a.n_classes = m->n_classes;
+    a.sem_sigmoid = m->sem_sigmoid;
+    a.head_mask = head_mask;
+  }
+  return run_plan(p, (cudaStream_t)stream);
+}
+
+extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
+                                int64_t n_points, const void* enc, const void* aux, const float* out,
+                                const float* g_out, int head_mask, float* grads, float* g_aux, void* stream) {
+  SNB_CHECK_ARG(m && packed && workspace && enc && aux && out && g_out && grads, SNB_ERR_INVALID,
+                "mlp_backward: null argument");
+  SNB_CHECK_ARG(n_points > 0 && n_points < (1ll << 31), SNB_ERR_INVALID, "mlp_backward: n_points out of range");
+  SNB_CHECK_ARG(mask_supported(head_mask), SNB_ERR_UNSUPPORTED, "mlp_backward: head_mask %d unsupported", head_mask);
+  const Workspace w = layout_workspace(m, n_points, 1);
+  SNB_CHECK_ARG(workspace_bytes >= w.total, SNB_ERR_WORKSPACE, "mlp_backward: workspace %zu < required %zu",
+                workspace_bytes, w.total);
+  const int sms = num_sms();
+  if (sms <= 0) return SNB_ERR_NO_DEVICE;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long P = n_points;
+  char* ws = reinterpret_cast<char*>(workspace);
+  const __nv_bfloat16* pk = reinterpret_cast<const __nv_bfloat16*>(packed);
+  float* gs = reinterpret_cast<float*>(ws + w.gscratch);
+  auto H = [&](int i) { return (void*)(ws + w.h[i]); };
+  auto Cs = [&](int i) { return (void*)(ws + w.c[i]); };
+  const int hhw = m->hhw;
+  const bool all = head_mask == SNB_HEADS_ALL;
+  const bool solar = head_mask == SNB_HEADS_SOLAR;
+  const bool depth = head_mask == SNB_HEADS_DEPTH;
+  void* dpre = ws + w.dpre;
+
+  SNB_CUDA(cudaMemsetAsync(gs, 0, (size_t)m->gscratch_elems * 4, st));
+  {
+    long long blocks = (P + 255) / 256;
+    if (blocks > sms * 8) blocks = sms * 8;
+    head_grad_kernel<<<(int)blocks, 256, 0, st>>>(out, g_out, P, m->n_out, m->n_classes, m->sem_sigmoid, head_mask,
+                                                  (__nv_bfloat16*)dpre, gs + m->gbho);
+    if (int r = launch_status("head_grad_kernel")) return r;
+  }
+  Plan p;
+  // head output layer: weight gradients (transposed scratch [features, 16]) -----------------------------
+  add_wgrad(p, F, 16, H(7), F, dpre, 16, P, gs + m->ghot, 16, sms);
+  if (!depth) add_wgrad(p, FL, 16, ws + w.s3, FL, dpre, 16, P, gs + m->ghot + (long long)F * 16, 16, sms);
+  if (all) add_wgrad(p, hhw, 16, ws + w.hh, hhw, dpre, 16, P, gs + m->ghot + (long long)(F + FL) * 16, 16, sms);
+  Seg sdpre[1] = {{dpre, 16, 16, 1}};
+  if (!depth) {
+    // sun head: s3 <- head output, then back through sun.4, sun.2 into the sun block of hh
+    add_kmajor(p, EPI_MUL, P, FL, sdpre, 1, pk + m->tho, 16, 16, ws + w.dys3, nullptr, FL, ws + w.cs3, FL, nullptr, 1.0f);
+    if (all)  // rgb / beta / sem blocks of hh (columns [0, hhw-256))
+      add_kmajor(p, EPI_MUL, P, hhw - FL, sdpre, 1, pk + m->tho + (long long)FL * 16, 16, 16, ws + w.dyhh, nullptr, hhw,
+                 ws + w.chh, hhw, nullptr, 1.0f);
+    add_wgrad(p, FL, FL, ws + w.dys3, FL, ws + w.s2, FL, P, gs + m->gs4, FL, sms);
+    add_wgrad(p, FL, 16, ws + w.dys3, FL, aux, 16, P, gs + m->gbs4, 16, sms);
+    Seg s3[1] = {{ws + w.dys3, FL, FL, FL / 64}};
+    add_kmajor(p, EPI_MUL, P, FL, s3, 1, pk + m->ts4, FL, FL, ws + w.dys2, nullptr, FL, ws + w.cs2, FL, nullptr, 1.0f);
+    add_wgrad(p, FL, FL, ws + w.dys2, FL, ws + w.hh + (size_t)m->hh_sun * 2, hhw, P, gs + m->gs2, FL, sms);
+    add_wgrad(p, FL, 16, ws + w.dys2, FL, aux, 16, P, gs + m->gbs2, 16, sms);
+    Seg s2[1] = {{ws + w.dys2, FL, FL, FL / 64}};
+    add_kmajor(p, EPI_MUL, P, FL, s2, 1, pk + m->ts2, FL, FL, ws + w.dyhh + (size_t)m->hh_sun * 2, nullptr, hhw,
+               ws + w.chh + (size_t)m->hh_sun * 2, hhw, nullptr, 1.0f);
+    // fused head first layers: weight / bias / per-ray-column gradients, then dF
+    const int r0 = all ? 0 : m->hh_sun, n = all ? hhw : FL;
+    const char* dyhh = ws + w.dyhh + (size_t)r0 * 2;
+    add_wgrad(p, n, F, dyhh, hhw, ws + w.f, F, P, gs + m->gh1 + (long long)r0 * F, F, sms);
+    add_wgrad(p, n, 16, dyhh, hhw, aux, 16, P, gs + m->gh1aux + (long long)r0 * 16, 16, sms);
+    if (all && g_aux) {
+      // d aux = dY_beta * W_beta0[:, 512:]  -> embedding gradient (summed per ray by the caller-side kernel)
+      Seg sb[1] = {{ws + w.dyhh + (size_t)m->hh_beta * 2, hhw, FL, FL / 64}};
+      GemmArgs& a = add_kmajor(p, EPI_F32ROWS, P, 16, sb, 1, pk + m->taux, FL, FL, nullptr, nullptr, 0, nullptr, 0, nullptr, 1.0f);
+      a.f32out = g_aux;
+      a.ldo = 16;
+    }
+    Seg sh[1] = {{dyhh, hhw, n, n / 64}};
+    add_kmajor(p, EPI_LINEAR, P, F, sh, 1, pk + m->th1 + r0, hhw, n, ws + w.df, nullptr, F, nullptr, 0, nullptr, 1.0f);
+    add_wgrad(p, F, F, ws + w.df, F, H(7), F, P, gs + m->gf, F, sms);
+    add_wgrad(p, F, 16, ws + w.df, F, aux, 16, P, gs + m->gbf, 16, sms);
+  }
+  // dY7 = ([dF | dPre16] * [Wf ; w_sigma]) * c7 ------------------------------------------------------------
+  int cur = 0;
+  if (!depth) {
+    Seg s[2] = {{ws + w.df, F, F, F / 64}, {dpre, 16, 16, 1}};
+    add_kmajor(p, EPI_MUL, P, F, s, 2, pk + m->tf, F + 64, F + 64, ws + w.dy[cur], nullptr, F, Cs(7), F, nullptr, 1.0f);
+  } else {
+    add_kmajor(p, EPI_MUL, P, F, sdpre, 1, pk + m->tf + F, F + 64, 64, ws + w.dy[cur], nullptr, F, Cs(7), F, nullptr, 1.0f);
+  }
+  for (int i = LAYERS - 1; i >= 0; --i) {
+    const void* dy = ws + w.dy[cur];
+    // weight / bias gradients of layer i
+    if (i == 0) {
+      add_wgrad(p, F, 64, dy, F, enc, m->enc_ld, P, gs + m->gl[0], 64, sms);
+    } else {
+      add_wgrad(p, F, F, dy, F, H(i - 1), F, P, gs + m->gl[i], F, sms);
+      if (i == 4) add_wgrad(p, F, 64, dy, F, enc, m->enc_ld, P, gs + m->gl4e, 64, sms);
+    }
+    add_wgrad(p, F, 16, dy, F, aux, 16, P, gs + m->gbl[i], 16, sms);
+    if (i > 0) {
+      Seg s[1] = {{dy, F, F, F / 64}};
+      add_kmajor(p, EPI_MUL, P, F, s, 1, pk + m->tl[i], F, F, ws + w.dy[cur ^ 1], nullptr, F, Cs(i - 1), F, nullptr, 1.0f);
+      cur ^= 1;
+    }
+  }
+  if (int r = run_plan(p, st)) return r;
+  return run_jobs(m->unpack_jobs, true, gs, nullptr, grads, st);
+}

@@ -1,0 +1,308 @@
+// K3 - per-ray alpha compositing with the irradiance lighting model and semantic compositing,
+// forward and backward.  One warp per ray; the transmittance cumprod is a warp product-scan
+// (lane-local serial products over SPL consecutive samples + a 5-step shuffle scan), the
+// cumprod gradient is the matching suffix-sum scan.
+//
+// Follows framework/util/rendering.py:4-34 (convert_sigmas) and the tail of `inference`
+// (baseline/models/satnerf.py:73-96, semantic/models/rs_semantic.py:81-126,131-136).
+//
+// HBM-bound: forward reads (n_out + 1) floats per sample and writes 2 (weights, transparency);
+// each ray's packed rows are staged through shared memory with fully coalesced 4-byte accesses.
+#include "snb_common.cuh"
+
+namespace snb {
+
+constexpr int K3_WARPS = 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+  return v;
+}
+
+// exclusive product scan across lanes
+__device__ __forceinline__ float warp_excl_prod(float v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float o = __shfl_up_sync(FULL, v, d);
+    if (lane >= d) v *= o;
+  }
+  float e = __shfl_up_sync(FULL, v, 1);
+  return lane == 0 ? 1.0f : e;
+}
+
+// exclusive suffix sum across lanes: sum over lanes > lane
+__device__ __forceinline__ float warp_excl_suffix_sum(float v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    float o = __shfl_down_sync(FULL, v, d);
+    if (lane + d < 32) v += o;
+  }
+  float e = __shfl_down_sync(FULL, v, 1);
+  return lane == 31 ? 0.0f : e;
+}
+
+struct SampleVals {
+  float alpha, e, q, delta, sigma;
+};
+
+__device__ __forceinline__ SampleVals sample_alpha(const float* zs, const float* row, int s, int S) {
+  SampleVals v;
+  v.sigma = row[3];
+  // framework/util/rendering.py:12-16: last delta is 1e10
+  v.delta = (s < S - 1) ? __fsub_rn(zs[s + 1], zs[s]) : 1e10f;
+  float x = __fmul_rn(v.delta, fmaxf(v.sigma, 0.0f));
+  v.e = expf(-x);
+  v.alpha = __fsub_rn(1.0f, v.e);                       // :24
+  v.q = __fadd_rn(__fsub_rn(1.0f, v.alpha), 1e-10f);    // :25-27
+  return v;
+}
+
+template <int SPL, bool BWD>
+__global__ void __launch_bounds__(K3_WARPS * 32)
+k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, int n_rays, int S,
+                    int n_out, int C,
+                    // forward outputs
+                    float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ weights,
+                    float* __restrict__ transparency, float* __restrict__ sem_logits,
+                    long long* __restrict__ sem_label,
+                    // backward inputs / output
+                    const float* __restrict__ g_rgb, const float* __restrict__ g_depth,
+                    const float* __restrict__ g_weights, const float* __restrict__ g_transp,
+                    const float* __restrict__ g_sem, const float* __restrict__ g_direct,
+                    float* __restrict__ g_out) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_words = S * n_out;
+  // per warp: packed rows [S*n_out] (+ gradient rows in BWD) + z [S]
+  const int per_warp = (BWD ? 2 : 1) * row_words + S;
+  float* rows = smem + warp * per_warp;
+  float* grow = rows + row_words;  // BWD only
+  float* zs = rows + (BWD ? 2 : 1) * row_words;
+
+  for (int ray = blockIdx.x * K3_WARPS + warp; ray < n_rays; ray += gridDim.x * K3_WARPS) {
+    const float* src = out + (size_t)ray * row_words;
+    for (int i = lane; i < row_words; i += 32) rows[i] = __ldg(src + i);
+    for (int i = lane; i < S; i += 32) zs[i] = __ldg(z_vals + (size_t)ray * S + i);
+    __syncwarp();
+
+    // ---- forward pass over this lane's SPL consecutive samples --------------------------------
+    float alpha[SPL], tloc[SPL], qv[SPL];
+    float Q = 1.0f;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      int s = lane * SPL + j;
+      tloc[j] = Q;
+      if (s < S) {
+        SampleVals v = sample_alpha(zs, rows + s * n_out, s, S);
+        alpha[j] = v.alpha;
+        qv[j] = v.q;
+        Q *= v.q;
+      } else {
+        alpha[j] = 0.0f;
+        qv[j] = 1.0f;
+      }
+    }
+    const float prefix = warp_excl_prod(Q, lane);
+
+    float acc_d = 0.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
+    float acc_s[10];
+#pragma unroll
+    for (int c = 0; c < 10; ++c) acc_s[c] = 0.f;
+    float T[SPL], w[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      int s = lane * SPL + j;
+      T[j] = prefix * tloc[j];
+      w[j] = alpha[j] * T[j];
+      if (s < S) {
+        const float* r = rows + s * n_out;
+        float v = r[4];
+        acc_d += w[j] * zs[s];
+        // rs_semantic.py:101-102: irradiance = sun + (1 - sun) * sky ; rgb = sum w * albedo * irradiance
+        acc_r += w[j] * r[0] * (v + (1.0f - v) * r[5]);
+        acc_g += w[j] * r[1] * (v + (1.0f - v) * r[6]);
+        acc_b += w[j] * r[2] * (v + (1.0f - v) * r[7]);
+#pragma unroll
+        for (int c = 0; c < 10; ++c)
+          if (c < C) acc_s[c] += w[j] * r[9 + c];
+        if (!BWD) {
+          weights[(size_t)ray * S + s] = w[j];
+          transparency[(size_t)ray * S + s] = T[j];
+        }
+      }
+    }
+    acc_d = warp_sum(acc_d);
+    acc_r = warp_sum(acc_r);
+    acc_g = warp_sum(acc_g);
+    acc_b = warp_sum(acc_b);
+#pragma unroll
+    for (int c = 0; c < 10; ++c)
+      if (c < C) acc_s[c] = warp_sum(acc_s[c]);
+
+    if (!BWD) {
+      if (lane == 0) {
+        rgb[ray * 3 + 0] = fminf(fmaxf(acc_r, 0.f), 1.f);  // rs_semantic.py:103
+        rgb[ray * 3 + 1] = fminf(fmaxf(acc_g, 0.f), 1.f);
+        rgb[ray * 3 + 2] = fminf(fmaxf(acc_b, 0.f), 1.f);
+        depth[ray] = acc_d;
+        if (C > 0) {
+          int best = 0;
+          float bv = acc_s[0];
+#pragma unroll
+          for (int c = 0; c < 10; ++c) {
+            if (c < C) {
+              sem_logits[(size_t)ray * C + c] = acc_s[c];
+              if (acc_s[c] > bv) { bv = acc_s[c]; best = c; }
+            }
+          }
+          sem_label[ray] = best;  // argmax(softmax(x)) == argmax(x), first maximum (rs_semantic.py:131-136)
+        }
+      }
+    } else {
+      // ---- backward -------------------------------------------------------------------------
+      // clamp passes gradient where 0 <= raw <= 1
+      float gr = g_rgb ? g_rgb[ray * 3 + 0] : 0.f, gg = g_rgb ? g_rgb[ray * 3 + 1] : 0.f,
+            gb = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
+      if (!(acc_r >= 0.f && acc_r <= 1.f)) gr = 0.f;
+      if (!(acc_g >= 0.f && acc_g <= 1.f)) gg = 0.f;
+      if (!(acc_b >= 0.f && acc_b <= 1.f)) gb = 0.f;
+      const float gd = g_depth ? g_depth[ray] : 0.f;
+      float gs[10];
+#pragma unroll
+      for (int c = 0; c < 10; ++c) gs[c] = (g_sem && c < C) ? g_sem[(size_t)ray * C + c] : 0.f;
+
+      float Gw[SPL], B[SPL];
+      float Bsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < SPL; ++j) {
+        int s = lane * SPL + j;
+        Gw[j] = 0.f;
+        B[j] = 0.f;
+        if (s < S) {
+          const float* r = rows + s * n_out;
+          float v = r[4];
+          float g = g_weights ? g_weights[(size_t)ray * S + s] : 0.f;
+          g += gd * zs[s];
+          g += gr * r[0] * (v + (1.0f - v) * r[5]) + gg * r[1] * (v + (1.0f - v) * r[6]) +
+               gb * r[2] * (v + (1.0f - v) * r[7]);
+#pragma unroll
+          for (int c = 0; c < 10; ++c)
+            if (c < C) g += gs[c] * r[9 + c];
+          Gw[j] = g;
+          float dT = (g_transp ? g_transp[(size_t)ray * S + s] : 0.f) + g * alpha[j];
+          B[j] = dT * T[j];
+          Bsum += B[j];
+        }
+      }
+      // R_j = sum_{s > j} B_s : lanes above + later samples in this lane
+      float R = warp_excl_suffix_sum(Bsum, lane);
+#pragma unroll
+      for (int j = SPL - 1; j >= 0; --j) {
+        int s = lane * SPL + j;
+        if (s < S) {
+          const float* r = rows + s * n_out;
+          float* go = grow + s * n_out;
+          float dq = R / qv[j];
+          float dalpha = Gw[j] * T[j] - dq;
+          SampleVals sv = sample_alpha(zs, r, s, S);
+          float dsig = (sv.sigma > 0.f) ? dalpha * sv.e * sv.delta : 0.f;
+          float v = r[4];
+          float wj = w[j];
+          go[0] = gr * wj * (v + (1.0f - v) * r[5]);
+          go[1] = gg * wj * (v + (1.0f - v) * r[6]);
+          go[2] = gb * wj * (v + (1.0f - v) * r[7]);
+          go[3] = dsig;
+          go[4] = wj * (gr * r[0] * (1.0f - r[5]) + gg * r[1] * (1.0f - r[6]) + gb * r[2] * (1.0f - r[7]));
+          go[5] = gr * wj * r[0] * (1.0f - v);
+          go[6] = gg * wj * r[1] * (1.0f - v);
+          go[7] = gb * wj * r[2] * (1.0f - v);
+          go[8] = 0.f;
+#pragma unroll
+          for (int c = 0; c < 10; ++c)
+            if (c < C) go[9 + c] = gs[c] * wj;
+          for (int c = 9 + C; c < n_out; ++c) go[c] = 0.f;
+        }
+        R += B[j];
+      }
+      __syncwarp();
+      float* dst = g_out + (size_t)ray * row_words;
+      if (g_direct) {
+        const float* gdir = g_direct + (size_t)ray * row_words;
+        for (int i = lane; i < row_words; i += 32) dst[i] = grow[i] + __ldg(gdir + i);
+      } else {
+        for (int i = lane; i < row_words; i += 32) dst[i] = grow[i];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <bool BWD>
+static int launch_k3(const float* out, const float* z, int n_rays, int S, int n_out, int C, float* rgb,
+                     float* depth, float* weights, float* transp, float* sem, long long* label,
+                     const float* g_rgb, const float* g_depth, const float* g_w, const float* g_t,
+                     const float* g_sem, const float* g_direct, float* g_out, cudaStream_t st) {
+  const int spl = (S + 31) / 32;
+  const size_t smem = (size_t)K3_WARPS * ((BWD ? 2 : 1) * S * n_out + S) * sizeof(float);
+  int sms = num_sms();
+  if (sms <= 0) return SNB_ERR_NO_DEVICE;
+  int blocks = (n_rays + K3_WARPS - 1) / K3_WARPS;
+  const int max_blocks = sms * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+#define K3_LAUNCH(SPL_)                                                                               \
+  do {                                                                                                \
+    auto kfn = k3_composite_kernel<SPL_, BWD>;                                                        \
+    if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kfn<<<blocks, K3_WARPS * 32, smem, st>>>(out, z, n_rays, S, n_out, C, rgb, depth, weights, transp, sem, label, \
+                                             g_rgb, g_depth, g_w, g_t, g_sem, g_direct, g_out);       \
+  } while (0)
+  if (spl <= 1) K3_LAUNCH(1);
+  else if (spl <= 2) K3_LAUNCH(2);
+  else if (spl <= 4) K3_LAUNCH(4);
+  else K3_LAUNCH(8);
+#undef K3_LAUNCH
+  return launch_status("k3_composite_kernel");
+}
+
+static int check_k3(const float* out, const float* z, int n_rays, int S, int n_out, int C) {
+  SNB_CHECK_ARG(out && z, SNB_ERR_INVALID, "composite: null input");
+  SNB_CHECK_ARG(n_rays >= 0, SNB_ERR_INVALID, "composite: n_rays < 0");
+  // S < 2: the reference itself degenerates (framework/util/rendering.py:13 builds delta_inf from
+  // an empty slice, so every per-sample tensor collapses to (N,0)); not supported here.
+  SNB_CHECK_ARG(S >= 2 && S <= 256, SNB_ERR_UNSUPPORTED, "composite: n_samples %d outside [2,256]", S);
+  // n_out > 9 + C is allowed: trailing columns are ignored (the solar pass composites no semantics)
+  SNB_CHECK_ARG(C >= 0 && C <= 10 && n_out >= 9 + C && n_out <= 32, SNB_ERR_UNSUPPORTED,
+                "composite: n_out %d / n_classes %d unsupported (need 9 + C <= n_out <= 32, C <= 10)", n_out, C);
+  return 0;
+}
+
+}  // namespace snb
+
+extern "C" int snb_composite_forward(const float* out, const float* z_vals, int n_rays, int n_samples,
+                                     int n_out, int n_classes, float* rgb, float* depth, float* weights,
+                                     float* transparency, float* sem_logits, int64_t* sem_label,
+                                     void* stream) {
+  if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes)) return r;
+  SNB_CHECK_ARG(rgb && depth && weights && transparency, SNB_ERR_INVALID, "composite_forward: null output");
+  SNB_CHECK_ARG(n_classes == 0 || (sem_logits && sem_label), SNB_ERR_INVALID,
+                "composite_forward: semantic outputs required when n_classes > 0");
+  if (n_rays == 0) return 0;
+  return snb::launch_k3<false>(out, z_vals, n_rays, n_samples, n_out, n_classes, rgb, depth, weights,
+                               transparency, sem_logits, reinterpret_cast<long long*>(sem_label), nullptr,
+                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int snb_composite_backward(const float* out, const float* z_vals, int n_rays, int n_samples,
+                                      int n_out, int n_classes, const float* g_rgb, const float* g_depth,
+                                      const float* g_weights, const float* g_transparency,
+                                      const float* g_sem_logits, const float* g_out_direct, float* g_out,
+                                      void* stream) {
+  if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes)) return r;
+  SNB_CHECK_ARG(g_out, SNB_ERR_INVALID, "composite_backward: null g_out");
+  if (n_rays == 0) return 0;
+  return snb::launch_k3<true>(out, z_vals, n_rays, n_samples, n_out, n_classes, nullptr, nullptr, nullptr,
+                              nullptr, nullptr, nullptr, g_rgb, g_depth, g_weights, g_transparency,
+                              g_sem_logits, g_out_direct, g_out, (cudaStream_t)stream);
+}

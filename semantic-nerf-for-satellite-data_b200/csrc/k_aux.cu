@@ -1,0 +1,159 @@
+// Small per-ray / per-parameter kernels around K2: sky_color and embedding parameter gradients,
+// and the Adam step on the flat parameter buffer.
+#include "snb_common.cuh"
+
+struct snb_model;
+extern "C" int64_t snb_model_param_count(const snb_model* m);
+extern "C" int snb_model_num_tensors(const snb_model* m);
+extern "C" int snb_model_tensor_info(const snb_model* m, int i, const char** name, int64_t* offset, int* rows, int* cols);
+
+namespace snb {
+
+// sky_color(sun_d) = sigmoid(W2 relu(W1 sun_d + b1) + b2) (satnerf.py:188-193) is evaluated once
+// per ray; its parameter gradients are reduced here from the per-sample gradient of `out[:, 5:8]`.
+// The embedding gradient (semantic/components/rendering.py:42: models["t"](ts)) is the per-ray sum of
+// the gradient of the aux columns 4..4+tau, scattered by ts.
+__global__ void __launch_bounds__(256)
+ray_param_bwd_kernel(const float* __restrict__ extras, const float* __restrict__ sky, const float* __restrict__ g_out,
+                     const float* __restrict__ g_aux, int n_rays, int S, int n_out, int tau, int vocab, int hidden,
+                     const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                     float* __restrict__ gw1, float* __restrict__ gb1, float* __restrict__ gw2, float* __restrict__ gb2,
+                     float* __restrict__ g_t_table) {
+  __shared__ float part[8][16];
+  __shared__ float fin[16];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nv = 3 + tau;
+  float a_w2[3] = {0.f, 0.f, 0.f}, a_w1[3] = {0.f, 0.f, 0.f}, a_b1 = 0.f, a_b2[3] = {0.f, 0.f, 0.f};
+  const bool hid = tid < hidden;
+  float w1r[3] = {0.f, 0.f, 0.f}, b1r = 0.f, w2r[3] = {0.f, 0.f, 0.f};
+  if (hid && sky) {
+    w1r[0] = w1[tid * 3]; w1r[1] = w1[tid * 3 + 1]; w1r[2] = w1[tid * 3 + 2];
+    b1r = b1[tid];
+    w2r[0] = w2[tid]; w2r[1] = w2[hidden + tid]; w2r[2] = w2[2 * hidden + tid];
+  }
+  for (int ray = blockIdx.x; ray < n_rays; ray += gridDim.x) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    for (int s = tid; s < S; s += 256) {
+      const size_t p = (size_t)ray * S + s;
+      if (sky) {
+        v[0] += g_out[p * n_out + 5]; v[1] += g_out[p * n_out + 6]; v[2] += g_out[p * n_out + 7];
+      }
+      if (g_aux)
+        for (int j = 0; j < tau; ++j) v[3 + j] += g_aux[p * 16 + 4 + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (j < nv) {
+        float x = v[j];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+        if (lane == 0) part[warp][j] = x;
+      }
+    }
+    __syncthreads();
+    if (tid < nv) {
+      float x = 0.f;
+      for (int wv = 0; wv < 8; ++wv) x += part[wv][tid];
+      fin[tid] = x;
+    }
+    __syncthreads();
+    const float* e = extras + (size_t)ray * 4;
+    if (g_aux && tid < tau) {
+      int ti = (int)e[3];
+      ti = min(max(ti, 0), vocab - 1);
+      atomicAdd(g_t_table + (size_t)ti * tau + tid, fin[3 + tid]);
+    }
+    if (sky && hid) {
+      const float sx = e[0], sy = e[1], sz = e[2];
+      const float y = fmaxf(fmaf(w1r[2], sz, fmaf(w1r[1], sy, fmaf(w1r[0], sx, b1r))), 0.f);
+      float dy = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float o = sky[(size_t)ray * 3 + c];
+        const float d = fin[c] * o * (1.0f - o);
+        a_w2[c] += d * y;
+        if (tid == 0) a_b2[c] += d;
+        dy += d * w2r[c];
+      }
+      if (y <= 0.f) dy = 0.f;
+      a_w1[0] += dy * sx; a_w1[1] += dy * sy; a_w1[2] += dy * sz;
+      a_b1 += dy;
+    }
+    __syncthreads();
+  }
+  if (sky && hid) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      atomicAdd(gw2 + c * hidden + tid, a_w2[c]);
+      atomicAdd(gw1 + tid * 3 + c, a_w1[c]);
+      if (tid == 0) atomicAdd(gb2 + c, a_b2[c]);
+    }
+    atomicAdd(gb1 + tid, a_b1);
+  }
+}
+
+// torch.optim.Adam (amsgrad=False, weight_decay=0, maximize=False)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.0f - b1) * gi;
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace snb
+
+static int64_t tensor_offset(const snb_model* m, const char* want) {
+  const int n = snb_model_num_tensors(m);
+  for (int i = 0; i < n; ++i) {
+    const char* name;
+    int64_t off;
+    int r, c;
+    snb_model_tensor_info(m, i, &name, &off, &r, &c);
+    if (strcmp(name, want) == 0) return off;
+  }
+  return -1;
+}
+
+extern "C" int snb_ray_param_backward(const snb_model* m, const float* params, const float* extras, const float* sky,
+                                      const float* g_out, const float* g_aux, int n_rays, int n_samples, int n_out,
+                                      int tau, int vocab, float* grads, float* g_t_table, void* stream) {
+  using namespace snb;
+  SNB_CHECK_ARG(m && params && extras && grads, SNB_ERR_INVALID, "ray_param_backward: null argument");
+  SNB_CHECK_ARG(!sky || g_out, SNB_ERR_INVALID, "ray_param_backward: g_out required with sky");
+  SNB_CHECK_ARG(!g_aux || g_t_table, SNB_ERR_INVALID, "ray_param_backward: g_t_table required with g_aux");
+  SNB_CHECK_ARG(tau >= 0 && tau <= 12, SNB_ERR_UNSUPPORTED, "ray_param_backward: tau %d", tau);
+  if (n_rays <= 0 || (!sky && !g_aux)) return 0;
+  const int64_t w1 = tensor_offset(m, "sky_color.0.weight"), b1 = tensor_offset(m, "sky_color.0.bias"),
+                w2 = tensor_offset(m, "sky_color.2.weight"), b2 = tensor_offset(m, "sky_color.2.bias");
+  SNB_CHECK_ARG(w1 >= 0 && b1 >= 0 && w2 >= 0 && b2 >= 0, SNB_ERR_INVALID, "ray_param_backward: sky tensors missing");
+  int sms = num_sms();
+  if (sms <= 0) return SNB_ERR_NO_DEVICE;
+  int blocks = n_rays < sms * 4 ? n_rays : sms * 4;
+  ray_param_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      extras, sky, g_out, g_aux, n_rays, n_samples, n_out, tau, vocab, 256, params + w1, params + b1, params + w2,
+      grads + w1, grads + b1, grads + w2, grads + b2, g_t_table);
+  return launch_status("ray_param_bwd_kernel");
+}
+
+extern "C" int snb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+  using namespace snb;
+  SNB_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, SNB_ERR_INVALID, "adam_step: bad argument");
+  if (n == 0) return 0;
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2 = 1.0f - powf(beta2, (float)step);
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                             bc1, sqrtf(bc2), grad_scale);
+  return launch_status("adam_kernel");
+}

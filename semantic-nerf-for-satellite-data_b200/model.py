@@ -1,0 +1,184 @@
+"""nn.Modules mirroring the reference models (same constructor inputs, same ``forward`` signature,
+same ``state_dict`` names/shapes) whose math runs in libsnb's CUDA kernels.
+
+Reference: baseline/models/satnerf.py:101-255 (SatNeRF), semantic/models/rs_semantic.py:139-340
+(RSSemanticNeRF).  Parameters live in ONE flat fp32 ``nn.Parameter`` (so the optimiser step, the
+bf16 re-pack and the data-parallel all-reduce are single contiguous passes); ``state_dict()`` /
+``load_state_dict()`` expose them under the reference's names (``fc_net.0.weight`` ...), so
+reference checkpoints load here and ours load into the reference (SURVEY trap #12).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import HEADS_ALL, MODEL_SATNERF, MODEL_SEMANTIC, check, ptr, stream
+
+
+class SnbMLP(torch.nn.Module):
+    """Common base: owns the libsnb model handle, the flat parameter and the packed bf16 image."""
+
+    def __init__(self, kind: int, n_classes: int, semantic_sigmoid: bool, tau: int, cfgs=None):
+        super().__init__()
+        if tau != 4:
+            raise _lib.SnbError("libsnb implements t_embedding_tau = 4 (the value in every shipped config)")
+        lib = _lib.load()
+        h = C.c_void_p()
+        check(lib.snb_model_create(C.byref(h), kind, n_classes, 1 if semantic_sigmoid else 0), "snb_model_create")
+        self._h = h
+        self.kind = kind
+        self.semantic_n_classes = n_classes          # read by the reference's inference(), rs_semantic.py:95
+        self.number_of_outputs = 9 + n_classes       # satnerf.py:120
+        self.t_embedding_dims = tau
+        self.enc_ld = 192 if kind == MODEL_SEMANTIC else 64
+        n = lib.snb_model_param_count(h)
+        self.table: List[Tuple[str, int, Tuple[int, ...]]] = []
+        for i in range(lib.snb_model_num_tensors(h)):
+            name, off, r, c = C.c_char_p(), C.c_int64(), C.c_int(), C.c_int()
+            check(lib.snb_model_tensor_info(h, i, C.byref(name), C.byref(off), C.byref(r), C.byref(c)), "tensor_info")
+            shape = (r.value, c.value) if c.value else (r.value,)
+            self.table.append((name.value.decode(), off.value, shape))
+        self.flat = torch.nn.Parameter(torch.zeros(n, dtype=torch.float32))
+        self.reset_parameters()
+        self._packed = None
+        self._packed_version = None
+
+    # ---- initialisation: same distributions as the reference -------------------------------------
+    def reset_parameters(self):
+        """SIREN init on fc_net / sun_v_net (commons.py:5-18, rs_semantic.py:239-243: U(+-sqrt(6/fan_in)),
+        first layers U(+-1/fan_in)); nn.Linear default init elsewhere (biases everywhere)."""
+        with torch.no_grad():
+            views = self.named_tensors()
+            for name, t in views.items():
+                if name.endswith(".bias"):
+                    fan_in = views[name[:-4] + "weight"].shape[1]
+                    b = 1.0 / math.sqrt(fan_in)
+                    t.uniform_(-b, b)
+                    continue
+                fan_in = t.shape[1]
+                if name.startswith("fc_net.") or name.startswith("sun_v_net."):
+                    first = name in ("fc_net.0.weight", "sun_v_net.0.weight")
+                    b = 1.0 / fan_in if first else math.sqrt(6.0 / fan_in)
+                else:
+                    b = 1.0 / math.sqrt(fan_in)  # kaiming_uniform(a=sqrt(5)) bound of nn.Linear
+                t.uniform_(-b, b)
+
+    def named_tensors(self) -> "OrderedDict[str, torch.Tensor]":
+        """Reference-named views into the flat parameter."""
+        out = OrderedDict()
+        for name, off, shape in self.table:
+            n = int(torch.tensor(shape).prod())
+            out[name] = self.flat.detach()[off:off + n].view(shape)  # detach(): shares the version counter
+        return out
+
+    def named_grads(self) -> Dict[str, torch.Tensor]:
+        g = self.flat.grad
+        out = {}
+        for name, off, shape in self.table:
+            n = int(torch.tensor(shape).prod())
+            out[name] = None if g is None else g[off:off + n].view(shape)
+        return out
+
+    def offset_of(self, name: str) -> int:
+        for n_, off, _ in self.table:
+            if n_ == name:
+                return off
+        raise KeyError(name)
+
+    # ---- state_dict under the reference's names ---------------------------------------------------
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        for name, t in self.named_tensors().items():
+            destination[prefix + name] = t if keep_vars else t.detach().clone()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys,
+                              error_msgs):
+        views = self.named_tensors()
+        for name, t in views.items():
+            key = prefix + name
+            if key not in state_dict:
+                missing_keys.append(key)
+                continue
+            src = state_dict[key]
+            if tuple(src.shape) != tuple(t.shape):
+                error_msgs.append(f"size mismatch for {key}: checkpoint {tuple(src.shape)} vs model {tuple(t.shape)}")
+                continue
+            with torch.no_grad():
+                t.copy_(src)
+        if strict:
+            for key in state_dict.keys():
+                if key.startswith(prefix) and key[len(prefix):] not in views:
+                    unexpected_keys.append(key)
+
+    # ---- packed bf16 weights ----------------------------------------------------------------------------
+    def packed(self) -> torch.Tensor:
+        """bf16 weight image for the GEMMs; re-packed whenever the flat parameter was modified."""
+        flat = self.flat
+        if not flat.is_cuda:
+            raise _lib.SnbError("the model must be on a CUDA device (libsnb has no CPU path)")
+        key = (flat.data_ptr(), flat._version)
+        if self._packed is None or self._packed.device != flat.device or self._packed_version != key:
+            lib = _lib.load()
+            if self._packed is None or self._packed.device != flat.device:
+                nbytes = lib.snb_model_packed_bytes(self._h)
+                self._packed = torch.empty(nbytes, dtype=torch.uint8, device=flat.device)
+            check(lib.snb_model_pack(self._h, ptr(flat.data), ptr(self._packed), stream()), "snb_model_pack")
+            self._packed_version = key
+        return self._packed
+
+    def mark_dirty(self):
+        """call after the parameters were modified behind PyTorch's back (snb_adam_step on raw pointers)."""
+        self._packed_version = None
+
+    def sky_params(self):
+        v = self.named_tensors()
+        return (v["sky_color.0.weight"], v["sky_color.0.bias"], v["sky_color.2.weight"], v["sky_color.2.bias"])
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().snb_model_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- reference forward signature ----------------------------------------------------------------
+    def forward(self, input_xyz, input_dir=None, input_sun_dir=None, input_t=None, input_t_s=None, epoch=None):
+        """(B,3),(B,3),(B,tau) -> (B, 9[+C]) packed exactly like the reference's forward
+        (satnerf.py:208-255, rs_semantic.py:260-313)."""
+        from .autograd import mlp_points
+        return mlp_points(self, input_xyz, input_sun_dir, input_t)
+
+
+class SatNeRFB200(SnbMLP):
+    """Drop-in for baseline.models.satnerf.SatNeRF (constructor signature: satnerf.py:101-112)."""
+
+    def __init__(self, cfgs=None, layers=8, feat=512, mapping=False, mapping_sizes=(10, 4), skips=(4,), siren=True,
+                 t_embedding_dims=4):
+        if layers != 8 or feat != 512 or list(skips) != [4] or mapping or not siren:
+            raise _lib.SnbError("libsnb implements the shipped SatNeRF configuration: 8x512 SIREN, skip [4], "
+                                "raw-xyz input (configs/pipelines/satnerf.toml)")
+        if cfgs is not None and getattr(cfgs.pipeline, "fc_use_full_features", False):
+            raise _lib.SnbError("fc_use_full_features=true is not implemented")
+        super().__init__(MODEL_SATNERF, 0, True, t_embedding_dims, cfgs)
+        self.layers, self.skips = layers, list(skips)
+
+
+class RSSemanticNeRFB200(SnbMLP):
+    """Drop-in for semantic.models.rs_semantic.RSSemanticNeRF (constructor: rs_semantic.py:139-141)."""
+
+    def __init__(self, cfgs, dataset_semantic):
+        p = cfgs.pipeline
+        unsupported = [k for k in ("use_tj_for_s", "use_tj_instead_of_beta", "use_separate_beta_for_s",
+                                   "use_separate_tj_for_semantic", "fc_use_full_features") if getattr(p, k, False)]
+        if unsupported or p.fc_layers != 8 or p.fc_units != 512 or list(p.fc_skips) != [4] \
+                or p.activation_function != "siren" or p.mapping_pos_n_freq != 10:
+            raise _lib.SnbError(f"libsnb implements the shipped rs_semantic.toml architecture; unsupported: {unsupported}")
+        sig = p.semantic_activation_function == "sigmoid"
+        super().__init__(MODEL_SEMANTIC, int(dataset_semantic.semantic_n_classes), sig, p.t_embedding_tau, cfgs)
+        self.cfg = p
+        self.layers, self.skips = p.fc_layers, list(p.fc_skips)

@@ -1,0 +1,80 @@
+"""Renderers mirroring the reference's components interface.
+
+``B200Renderer.render_rays(models, rays, extras, epoch, progress, render_options)`` has the
+signature and the output dictionary (``*_coarse`` keys) of ``BaseRenderer.render_rays``
+(framework/components/rendering.py:125-157) combined with ``SatNeRFRendering._model_rendering``
+(baseline/components/rendering.py:12-67) / ``RSSemanticRendering._model_rendering``
+(semantic/components/rendering.py:18-80), so ``BaseRayPipeline.forward``
+(baseline/pipelines/base_ray_pipeline.py:34-52) and ``batched_inference``
+(eval/utils/util.py:13-42) can call it unchanged.
+
+render_options (all optional, default = reference behaviour):
+  "u" (N,S) / "z_vals" (N,S): replace the random jitter (parity tests; the reference's
+      ``given_z_vals`` hook, rendering.py:91-92);  "seed", "ray_offset": Philox key / global ray index;
+  "heads": "all" | "depth" - "depth" evaluates only trunk + sigma (what the depth-supervision
+      batch consumes, semantic/components/training_step.py:32-46) and skips the solar pass.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, MODEL_SEMANTIC
+from .autograd import Composite, MLPRays, encode_rays
+
+
+class B200Renderer:
+    def __init__(self, cfgs):
+        self.cfgs = cfgs
+        self.N_samples = cfgs.pipeline.n_samples
+        self._calls = 0
+
+    def render_rays(self, models: dict, rays, extras, epoch=None, progress=1.0, render_options={}):
+        res = self._model_rendering(models, "coarse", self.cfgs, rays, extras, None, None, None, epoch=epoch,
+                                    progress=progress, render_options=render_options)
+        return {f"{k}_coarse": v for k, v in res.items()}
+
+    def _model_rendering(self, models, typ, cfgs, rays, extras, xyz, z_vals, rays_d, epoch=None, progress=1.0,
+                         render_options=None):
+        opts = render_options or {}
+        model = models[typ]
+        emb = models["t"].weight if "t" in models else None
+        n, S = rays.shape[0], self.N_samples
+        if z_vals is None:
+            z_vals = opts.get("z_vals")
+        depth_only = opts.get("heads", "all") == "depth"
+        sc = cfgs.pipeline.sc_lambda > 0 and not depth_only
+        self._calls += 1
+        z, enc, enc_sc, aux, sky = encode_rays(model, emb, rays, extras, S, u=opts.get("u"), z=z_vals,
+                                               seed=int(opts.get("seed", self._calls)),
+                                               ray_offset=int(opts.get("ray_offset", 0)), want_sc=sc)
+        C = model.semantic_n_classes
+        mask = HEADS_DEPTH if depth_only else HEADS_ALL
+        out = MLPRays.apply(model.flat, emb, model, enc, aux, sky, extras, n, S, mask).view(n, S, -1)
+        rgb, depth, weights, transp, sem, label = Composite.apply(out, z, C)
+        result = {
+            "rgb": rgb, "depth": depth, "weights": weights, "transparency": transp,
+            "albedo": out[..., :3], "sun": out[..., 4:5], "sky": out[..., 5:8], "beta": out[..., 8:9],
+            "sigmas": out[..., 3],
+        }
+        if model.kind == MODEL_SEMANTIC:
+            result["semantic_logits"] = sem
+            result["semantic_label"] = label
+        if sc:
+            # solar correction: second pass on o + sun_d*z, keeping weights / transparency / sun
+            out_sc = MLPRays.apply(model.flat, emb, model, enc_sc, aux, None, extras, n, S, HEADS_SOLAR).view(n, S, -1)
+            _, _, w_sc, t_sc, _, _ = Composite.apply(out_sc, z, 0)  # no semantic columns to composite
+            result["weights_sc"] = w_sc
+            result["transparency_sc"] = t_sc
+            result["sun_sc"] = out_sc[..., 4:5]
+        result["_z_vals"] = z
+        return result
+
+
+# the reference's two renderer class names, for configs / code that instantiate them by name
+class SatNeRFB200Rendering(B200Renderer):
+    pass
+
+
+class RSSemanticB200Rendering(B200Renderer):
+    def __init__(self, cfgs, inference=None):
+        super().__init__(cfgs)

@@ -1,0 +1,49 @@
+"""Shared test helpers (config stub, golden loader)."""
+from __future__ import annotations
+
+import os
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def make_cfgs(spec, n_samples: int, sc_lambda: float):
+    """The attribute bag the hot path reads from ``cfgs.pipeline`` (same field names as the reference's
+    pydantic config: baseline/pipelines/satnerf.py:115-132, semantic/pipelines/rs_semantic.py:125-175)."""
+    pl = types.SimpleNamespace(
+        n_samples=n_samples, render_chunk_size=40960, fc_units=spec.feat, fc_layers=spec.layers,
+        fc_skips=list(spec.skips), fc_use_full_features=spec.full_features, sc_lambda=sc_lambda,
+        t_embedding_tau=spec.tau, t_embedding_vocab=spec.vocab, activation_function="siren",
+        mapping_pos_n_freq=spec.n_freq, mapping_dir_n_freq=4,
+        semantic_activation_function="sigmoid" if spec.semantic_sigmoid else "none",
+        use_tj_for_s=False, use_tj_instead_of_beta=False, use_beta_for_s=False,
+        use_separate_beta_for_s=False, use_separate_tj_for_semantic=False)
+    return types.SimpleNamespace(pipeline=pl)
+
+
+# must match oracle/pin_against_reference.py::CASES (name, kind, C, feat, n_rays, n_samples, sc_lambda, seed)
+GOLDEN_CASES = [
+    ("sem_c6_s64", "semantic", 6, 512, 24, 64, 0.05, 1),
+    ("sem_c5_s8", "semantic", 5, 512, 16, 8, 0.05, 2),
+    ("sem_c6_s2", "semantic", 6, 512, 8, 2, 0.0, 3),
+    ("sem_c6_s128", "semantic", 6, 512, 8, 128, 0.0, 4),
+    ("sat_s64", "satnerf", 0, 512, 24, 64, 0.05, 5),
+    ("sat_s8_nosc", "satnerf", 0, 512, 16, 8, 0.0, 6),
+    ("sem_c6_s64_trained", "semantic", 6, 512, 24, 64, 0.05, 7),
+]
+
+
+def golden_inputs(case):
+    from oracle import render_oracle as O
+    name, kind, C, feat, n, s, sc, seed = case
+    spec = O.ModelSpec(kind=kind, n_classes=C, feat=feat)
+    params, emb = O.make_params(spec, seed=seed, trained_like=name.endswith("trained"))
+    rays, extras = O.synthetic_rays(n, seed=seed)
+    rng = np.random.Generator(np.random.PCG64(seed + 77))
+    u = torch.from_numpy(rng.uniform(0, 1, (n, s))).float()
+    gold = dict(np.load(os.path.join(GOLDEN, f"{name}.npz")))
+    return spec, params, emb, rays, extras, u, gold
