@@ -76,7 +76,7 @@ class MLPRays(torch.autograd.Function):
     def forward(ctx, flat, emb_weight, model, enc, aux, sky, extras, n_rays, n_samples, head_mask):
         lib = _lib.load()
         P = n_rays * n_samples
-        train = torch.is_grad_enabled() and (flat.requires_grad or (emb_weight is not None and emb_weight.requires_grad))
+        train = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])  # grad mode is off inside forward()
         ws = _workspace(model, P, train, enc.device)
         out = torch.empty(P, model.number_of_outputs, dtype=torch.float32, device=enc.device)
         packed = model.packed()
@@ -121,7 +121,7 @@ class MLPPoints(torch.autograd.Function):
         xyz, sun_d, tt = _f32c(xyz), _f32c(sun_d), _f32c(t.detach())
         P = xyz.shape[0]
         dev = xyz.device
-        train = torch.is_grad_enabled() and (flat.requires_grad or t.requires_grad)
+        train = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])  # grad mode is off inside forward()
         enc = torch.empty(P, model.enc_ld, dtype=torch.bfloat16, device=dev)
         aux = torch.empty(P, 16, dtype=torch.bfloat16, device=dev)
         sky = torch.empty(P, 3, dtype=torch.float32, device=dev)

@@ -1,0 +1,96 @@
+"""Host-side mirror of the reference interfaces: parameter names/shapes, state_dict round trips,
+initialiser ranges, renderer signature.  CPU only."""
+import inspect
+import math
+
+import pytest
+import torch
+
+from oracle import render_oracle as O
+from semnerf_b200 import _lib
+from semnerf_b200.model import RSSemanticNeRFB200, SatNeRFB200
+from semnerf_b200.renderer import B200Renderer
+from tests.helpers import make_cfgs
+
+
+def build(kind, C=6):
+    spec = O.ModelSpec(kind=kind, n_classes=C)
+    cfgs = make_cfgs(spec, 64, 0.05)
+    if kind == "semantic":
+        return spec, RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": C})())
+    return spec, SatNeRFB200(cfgs, layers=8, feat=512, skips=[4], t_embedding_dims=4)
+
+
+@pytest.mark.parametrize("kind,C", [("semantic", 6), ("semantic", 5), ("satnerf", 0)])
+def test_state_dict_names_and_shapes_match_reference(kind, C):
+    spec, m = build(kind, C)
+    want = O.param_shapes(spec)   # pinned against the reference modules by oracle/pin_against_reference.py
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(want.keys())
+    for k, shape in want.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert m.semantic_n_classes == C and m.number_of_outputs == 9 + C
+
+
+def test_state_dict_round_trip_and_strictness():
+    spec, m = build("semantic")
+    params, _ = O.make_params(spec, seed=4)
+    res = m.load_state_dict(params, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    sd = m.state_dict()
+    assert all(torch.equal(sd[k], params[k]) for k in params)
+    bad = dict(params)
+    bad.pop("fc_net.8.weight")
+    bad["bogus.weight"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(bad, strict=True)
+    res = m.load_state_dict(bad, strict=False)
+    assert res.missing_keys == ["fc_net.8.weight"]
+    # Lightning-style prefixes (framework/pipelines.py:204-214: model_coarse.*)
+    holder = torch.nn.Module()
+    holder.model_coarse = m
+    assert "model_coarse.fc_net.0.weight" in holder.state_dict()
+
+
+def test_loading_bumps_the_repack_version():
+    spec, m = build("satnerf", 0)
+    v0 = m.flat._version
+    m.load_state_dict(O.make_params(spec, seed=1)[0])
+    assert m.flat._version > v0
+
+
+def test_initialiser_ranges_follow_the_reference():
+    torch.manual_seed(0)
+    _, m = build("semantic")
+    t = m.named_tensors()
+    assert t["fc_net.0.weight"].abs().max() <= 1 / 60 + 1e-7                   # first_layer_sine_init
+    assert t["fc_net.8.weight"].abs().max() <= math.sqrt(6 / 572) + 1e-7        # sine_init, skip layer
+    assert t["fc_net.8.weight"].abs().max() > 0.9 * math.sqrt(6 / 572)
+    assert t["sun_v_net.0.weight"].abs().max() <= 1 / 515 + 1e-7
+    assert t["rgb_from_xyzdir.0.weight"].abs().max() <= 1 / math.sqrt(512) + 1e-7
+    assert t["beta_from_xyz.0.bias"].abs().max() <= 1 / math.sqrt(516) + 1e-7
+
+
+def test_unsupported_configurations_fail_loudly():
+    spec = O.ModelSpec(kind="semantic")
+    cfgs = make_cfgs(spec, 64, 0.05)
+    cfgs.pipeline.use_separate_beta_for_s = True
+    with pytest.raises(_lib.SnbError):
+        RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": 6})())
+    with pytest.raises(_lib.SnbError):
+        SatNeRFB200(make_cfgs(O.ModelSpec(kind="satnerf"), 64, 0.05), feat=256)
+
+
+def test_renderer_signature_matches_reference_baserenderer():
+    # framework/components/rendering.py:125-133
+    sig = inspect.signature(B200Renderer.render_rays)
+    assert list(sig.parameters)[1:] == ["models", "rays", "extras", "epoch", "progress", "render_options"]
+    sig = inspect.signature(B200Renderer._model_rendering)
+    assert list(sig.parameters)[1:] == ["models", "typ", "cfgs", "rays", "extras", "xyz", "z_vals", "rays_d", "epoch",
+                                        "progress", "render_options"]
+
+
+def test_no_cpu_fallback():
+    _, m = build("satnerf", 0)
+    with pytest.raises(_lib.SnbError):
+        m(torch.zeros(4, 3), input_sun_dir=torch.zeros(4, 3), input_t=torch.zeros(4, 4))

@@ -300,6 +300,8 @@ def group_render():
 
 
 if __name__ == "__main__":
+    from semnerf_b200 import build as _build_lib
+    _build_lib.build()
     sel = [a for a in sys.argv[1:] if not a.startswith("-")]
     if sel:
         for gname in sel:
