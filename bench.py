@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Benchmark of the ray-rendering hot path (BASELINE.json: training rays/s, render samples/s,
+MLP tensor-pipe fraction of peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch RAYS_PER_GPU] [--impl reference]
+
+A "step" is one optimisation step of the Semantic-NeRF pipeline (BASELINE.json configs[1]: semantic
+model, 6 classes, transient/car regularisation, solar-correction pass, bf16) on a synthetic batch of
+rays: sample + encode -> MLP (main + solar pass) -> composite -> losses -> backward -> Adam.
+For N > 1 launch under torchrun (one rank per GPU, NCCL); per-GPU work is fixed ("weak" scaling).
+Prints ONE JSON line on rank 0.
+
+--impl reference times the CPU port of the reference's path (oracle/) on the host cores; the
+reference itself is pure Python that cannot travel to the GPU box (no /root/reference there).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CLASSES, N_SAMPLES, CAR_INDEX = 6, 64, 4
+# algorithmic MLP FLOPs per training ray (semantic, C=6, S=64): main pass 16.862 MFLOP/sample
+# (fwd + dgrad + wgrad, no dgrad into the inputs) + solar pass 14.470 MFLOP/sample.
+ALG_FLOP_PER_TRAIN_RAY = 64 * (16_862_208 + 14_470_144)
+ALG_FLOP_PER_RENDER_SAMPLE = 5_641_216 + 4_844_544  # all heads + the solar pass forward
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["bf16_tflops_sustained"], d["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = f"/tmp/snb_clocks_{os.getpid()}.csv"
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], None, set()
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx = float(parts[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_batch(n, seed, pinned=False):
+    from semnerf_b200 import synth
+    rays, extras = synth.make_rays(n, seed=seed)
+    rgbs, labels, _ = synth.make_targets(rays, N_CLASSES, seed=seed)
+    b = {"rays": rays, "extras": extras, "rgbs": rgbs, "semantic": labels}
+    if pinned:
+        b = {k: v.pin_memory() for k, v in b.items()}
+    return b
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, one optimisation step on a bounded sample
+# ------------------------------------------------------------------------------------------------------
+def cpu_training_steps(n_rays: int, steps: int, warmup: int):
+    from oracle import render_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = O.ModelSpec(kind="semantic", n_classes=N_CLASSES)
+    params, emb = O.make_params(spec, seed=0)
+    params = {k: v.requires_grad_(True) for k, v in params.items()}
+    emb = emb.requires_grad_(True)
+    opt = torch.optim.Adam(list(params.values()) + [emb], lr=5e-4)
+    b = make_batch(n_rays, seed=0)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        u = torch.rand(n_rays, N_SAMPLES)
+        res = O.render_rays(params, emb, spec, b["rays"], b["extras"], N_SAMPLES, u=u, sc_lambda=0.05)
+        loss = O.satnerf_loss(res, b["rgbs"]) + O.semantic_loss(res, b["semantic"], ignore_index=CAR_INDEX) + \
+            O.car_reg_loss(res, b["semantic"], CAR_INDEX)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return n_rays * len(times) / sum(times), torch.get_num_threads(), sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_rays
+    rps, cores, sec = cpu_training_steps(n, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "train_rays_per_s", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cpu=True),
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} rays x {N_SAMPLES} samples per step (same step, bounded batch)"},
+        "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cpu=False):
+    return {
+        "workload": "Semantic-NeRF training step (BASELINE configs[1]): semantic 8x512 SIREN MLP, C=6, S=64, "
+                    "solar-correction pass (sc_lambda=0.05), SatNerfLoss + SemanticLoss(ignore car) + "
+                    "SemanticCarRegLoss, Adam; steady-state step (after the depth-supervision drop)",
+        "rays_per_gpu_per_step": args.cpu_rays if cpu else args.batch, "samples_per_ray": N_SAMPLES,
+        "n_classes": N_CLASSES, "parallelism": f"dp{args.gpus}",
+        "l2": "per-step activation working set (~30 GB at 8192 rays) >> 126 MB L2; no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    from semnerf_b200 import _lib, build, dist as snb_dist
+    from semnerf_b200.trainer import Trainer, default_cfgs
+    rank, local, world = snb_dist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if rank == 0:
+        build.build()
+    snb_dist.barrier()
+    lib = _lib.load()
+    B = args.batch
+    cfgs = default_cfgs("semantic", n_samples=N_SAMPLES, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=0)
+    tr = Trainer(cfgs, "semantic", N_CLASSES, device=dev, car_index=CAR_INDEX, world=world, rank=rank, seed=0)
+    host = [make_batch(B, seed=100 * rank + i, pinned=True) for i in range(4)]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+
+    def step_resident(i):
+        return tr.training_step(resident[i % len(resident)], epoch=3, ray_offset=rank * B)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    torch.cuda.synchronize()
+    # ---- timed region 1: inputs resident in HBM, device-timed ----------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib.snb_profile_begin(0)
+    snb_dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step_resident(i)
+    e1.record()
+    torch.cuda.synchronize()
+    snb_dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms_total = ms.item()
+    clocks = sampler.stop() if sampler else None
+    gl, tl = C.c_int64(), C.c_int64()
+    lib.snb_profile_end(None, C.byref(gl), C.byref(tl), None)
+    launches = tl.value
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- timed region 2: end to end through the public API, host buffers ------------------------------
+    snb_dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        hb = host[i % len(host)]
+        b = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        loss = tr.training_step(b, epoch=3, ray_offset=rank * B)
+        loss_host = loss.item()          # device -> host read of the step's result
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t_e2e, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / t_e2e.item()
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM), timed live with CUDA events per launch ------
+    roof = cpu = render = None
+    if rank == 0:
+        peak_tf, peak_hbm, which = peaks()
+        nprof = 2
+        lib.snb_profile_begin(1)
+        for i in range(nprof):
+            step_resident(i)
+        gms, gl2, tl2, macs = C.c_double(), C.c_int64(), C.c_int64(), C.c_double()
+        lib.snb_profile_end(C.byref(gms), C.byref(gl2), C.byref(tl2), C.byref(macs))
+        gemm_ms_step = gms.value / nprof
+        alg = ALG_FLOP_PER_TRAIN_RAY * B
+        achieved = alg / (gemm_ms_step * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "snb_gemm_kernel (tcgen05 GEMM, all epilogues)", "achieved": achieved,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": which, "per": "step: algorithmic MLP FLOPs of one step / summed GEMM launch time",
+                "gemm_launches_per_step": gl2.value // nprof, "gemm_ms_per_step": gemm_ms_step,
+                "executed_tflops": 2 * macs.value / nprof / (gemm_ms_step * 1e-3) / 1e12,
+                "gemm_share_of_step": gemm_ms_step / (ms_total / args.steps)}
+        # secondary metric: no-grad render throughput (samples/s), chunked like batched_inference
+        nr = 4 * 40960
+        from semnerf_b200 import synth
+        rr, ee = synth.make_rays(nr, seed=7)
+        rr, ee = rr.to(dev), ee.to(dev)
+        tr.render_image(rr[:40960], ee[:40960])
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        tr.render_image(rr, ee)
+        r1.record()
+        torch.cuda.synchronize()
+        rs = nr * N_SAMPLES / (r0.elapsed_time(r1) * 1e-3)
+        render = {"samples_per_s": rs, "rays": nr, "chunk_rays": 40960, "passes": "main + solar-correction",
+                  "tensor_frac": rs * ALG_FLOP_PER_RENDER_SAMPLE / 1e12 / peak_tf}
+        if world == 1 and not args.no_cpu:
+            rps, cores, _ = cpu_training_steps(args.cpu_rays, 2, 1)
+            cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                   "sample": f"{args.cpu_rays} rays x {N_SAMPLES} samples, 2 timed steps of the same training step"}
+    if rank == 0:
+        line = {
+            "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "clocks": clocks, "render": render, "loss": loss_host,
+        }
+        print(json.dumps(line), flush=True)
+    snb_dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8192, help="rays per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

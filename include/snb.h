@@ -157,6 +157,14 @@ int snb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * measurement hooks (bench.py): count kernel launches made by this library and time every GEMM
+ * launch with CUDA events on the launching stream.  snb_profile_end synchronises the device and
+ * returns the summed GEMM device time (ms), the number of GEMM launches, all launches, and the MACs
+ * the GEMM launches executed (padded tile work, for reference next to the algorithmic count). */
+void snb_profile_begin(int time_gemms);
+int snb_profile_end(double* gemm_ms, int64_t* gemm_launches, int64_t* total_launches, double* gemm_macs);
+
+/* ------------------------------------------------------------------------------------------------
  * test hook: one bf16 GEMM through the tcgen05 kernel.  D = A (M,K) x B (N,K)^T (+ epilogue).
  * a_mn / b_mn = 1: operand stored (K,M) / (K,N) row-major (the wgrad form).
  * epi: 0 sin(w0*(acc+bias)) -> out0 bf16 [+ out1 = w0*cos(..)], 1 acc+bias -> bf16, 2 acc*mul -> bf16,

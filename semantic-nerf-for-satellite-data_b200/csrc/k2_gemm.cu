@@ -5,6 +5,9 @@
 
 namespace snb {
 
+bool profile_gemm_begin(cudaStream_t st, double macs);
+void profile_gemm_end(cudaStream_t st);
+
 // ================================================================================================
 // PTX wrappers
 // ================================================================================================
@@ -557,15 +560,20 @@ int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
   if (sms <= 0) return SNB_ERR_NO_DEVICE;
   const long long tiles = (long long)a.m_tiles * a.n_tiles * a.splits;
   const int grid = (int)(tiles < sms ? tiles : sms);
+  const double macs = (double)a.m_tiles * GEMM_BLOCK_M * (double)a.n_tiles * a.block_n * (double)a.kb_total * GEMM_BLOCK_K;
+  const bool timed = profile_gemm_begin(st, macs);
+  int rc;
   switch (epi) {
-    case EPI_SIN: return launch_epi<EPI_SIN>(a, grid, st);
-    case EPI_LINEAR: return launch_epi<EPI_LINEAR>(a, grid, st);
-    case EPI_MUL: return launch_epi<EPI_MUL>(a, grid, st);
-    case EPI_HEADOUT: return launch_epi<EPI_HEADOUT>(a, grid, st);
-    case EPI_F32ROWS: return launch_epi<EPI_F32ROWS>(a, grid, st);
-    case EPI_WGRAD: return launch_epi<EPI_WGRAD>(a, grid, st);
+    case EPI_SIN: rc = launch_epi<EPI_SIN>(a, grid, st); break;
+    case EPI_LINEAR: rc = launch_epi<EPI_LINEAR>(a, grid, st); break;
+    case EPI_MUL: rc = launch_epi<EPI_MUL>(a, grid, st); break;
+    case EPI_HEADOUT: rc = launch_epi<EPI_HEADOUT>(a, grid, st); break;
+    case EPI_F32ROWS: rc = launch_epi<EPI_F32ROWS>(a, grid, st); break;
+    case EPI_WGRAD: rc = launch_epi<EPI_WGRAD>(a, grid, st); break;
+    default: set_error("gemm: unknown epilogue %d", epi); rc = SNB_ERR_INVALID;
   }
-  SNB_CHECK_ARG(false, SNB_ERR_INVALID, "gemm: unknown epilogue %d", epi);
+  if (timed) profile_gemm_end(st);
+  return rc;
 }
 
 }  // namespace snb

@@ -28,7 +28,10 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_e != cudaSuccess) return snb::cuda_fail(_e, #expr); \
   } while (0)
 
+void count_launch();
+
 inline int launch_status(const char* what) {
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, what);
   return 0;

@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "snb_common.cuh"
 
 namespace snb {
@@ -43,7 +45,60 @@ int num_sms() {
   return cached;
 }
 
+// ---- measurement hooks ------------------------------------------------------------------------------
+static bool g_prof_time = false;
+static long long g_launches = 0, g_gemm_launches = 0;
+static double g_gemm_macs = 0.0;
+static std::vector<cudaEvent_t> g_ev_pool;
+static size_t g_ev_used = 0;
+
+void count_launch() { ++g_launches; }
+
+bool profile_gemm_begin(cudaStream_t st, double macs) {
+  ++g_gemm_launches;
+  g_gemm_macs += macs;
+  if (!g_prof_time) return false;
+  if (g_ev_used + 2 > g_ev_pool.size()) {
+    for (int i = 0; i < 256; ++i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      g_ev_pool.push_back(e);
+    }
+  }
+  cudaEventRecord(g_ev_pool[g_ev_used], st);
+  return true;
+}
+void profile_gemm_end(cudaStream_t st) {
+  cudaEventRecord(g_ev_pool[g_ev_used + 1], st);
+  g_ev_used += 2;
+}
+
 }  // namespace snb
+
+extern "C" void snb_profile_begin(int time_gemms) {
+  snb::g_prof_time = time_gemms != 0;
+  snb::g_launches = snb::g_gemm_launches = 0;
+  snb::g_gemm_macs = 0.0;
+  snb::g_ev_used = 0;
+}
+
+extern "C" int snb_profile_end(double* gemm_ms, int64_t* gemm_launches, int64_t* total_launches, double* gemm_macs) {
+  using namespace snb;
+  SNB_CUDA(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < g_ev_used; i += 2) {
+    float t = 0.f;
+    SNB_CUDA(cudaEventElapsedTime(&t, g_ev_pool[i], g_ev_pool[i + 1]));
+    ms += t;
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_launches) *gemm_launches = g_gemm_launches;
+  if (total_launches) *total_launches = g_launches;
+  if (gemm_macs) *gemm_macs = g_gemm_macs;
+  g_prof_time = false;
+  g_ev_used = 0;
+  return 0;
+}
 
 extern "C" int snb_version(void) { return SNB_VERSION; }
 extern "C" const char* snb_last_error(void) { return snb::g_err; }

@@ -1,0 +1,160 @@
+"""-m gpu: the MLP and the whole render path through the reference-facing interface
+(Model.forward / render_rays), against the oracle and the golden vectors frozen from the reference.
+
+Tolerances (BASELINE.json north_star): rgb/depth within 1e-3 abs at the reference's initialisation;
+bf16 mode PSNR within 0.05 dB; gradient cosine >= 0.999."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import render_oracle as O
+from tests.helpers import GOLDEN_CASES, golden_inputs, make_cfgs
+from tests.test_gpu_kernels import DEV, _lib_or_fail, _model
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float(a @ b) / max(1e-300, float(a.norm() * b.norm()))
+
+
+@pytest.mark.parametrize("kind,C", [("semantic", 6), ("semantic", 5), ("satnerf", 0)])
+def test_model_forward_backward_matches_oracle(kind, C):
+    """Model.forward(xyz, sun_d, t) -> (B, 9+C): per-head outputs and every parameter gradient."""
+    _lib_or_fail()
+    spec, params, emb, cfgs, model, t = _model(kind, C, seed=1)
+    P = 1000
+    g = torch.Generator().manual_seed(0)
+    xyz = torch.rand(P, 3, generator=g) * 2 - 1
+    sun = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=1)
+    tt = torch.randn(P, 4, generator=g)
+    p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    tt64 = tt.double().requires_grad_(True)
+    ref = O.mlp_forward(p64, spec, xyz.double(), sun.double(), tt64)
+    tg = tt.to(DEV).requires_grad_(True)
+    out = model(xyz.to(DEV), input_sun_dir=sun.to(DEV), input_t=tg)
+    assert out.shape == (P, 9 + C) and out.dtype == torch.float32
+    d = (out.detach().cpu() - ref.detach()).abs()
+    # bf16 operands, fp32 accumulation, 8 SIREN layers: sigmoid heads 2e-3, softplus heads (unbounded) 1e-2
+    assert d[:, [0, 1, 2, 4]].max() <= 2e-3 and d[:, 5:8].max() <= 1e-6
+    assert d[:, 3].max() <= 1e-2 and d[:, 8].max() <= 5e-3
+    if C:
+        assert d[:, 9:].max() <= 2e-3
+    w = torch.randn(ref.shape, generator=g).double()
+    (ref * w).sum().backward()
+    (out * w.to(DEV).float()).sum().backward()
+    grads = model.named_grads()
+    for k in p64:
+        assert _cos(grads[k].cpu(), p64[k].grad) >= 0.999, k
+    assert _cos(model.flat.grad.cpu(), torch.cat([p64[k].grad.flatten() for k in p64])) >= 0.9995
+    assert _cos(tg.grad.cpu(), tt64.grad) >= 0.999
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c[0] for c in GOLDEN_CASES])
+def test_render_rays_against_reference_golden(case):
+    """render_rays through the reference-facing renderer vs vectors produced by the reference itself."""
+    from semnerf_b200.renderer import B200Renderer
+    _lib_or_fail()
+    name, kind, C, feat, n, s, sc, seed = case
+    spec, params, emb, rays, extras, u, gold = golden_inputs(case)
+    _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"))
+    renderer = B200Renderer(cfgs)
+    with torch.no_grad():
+        res = renderer.render_rays({"coarse": model, "t": t}, rays.to(DEV), extras.to(DEV),
+                                   render_options={"u": u.to(DEV)})
+    trained = name.endswith("trained")
+    for k, g in gold.items():
+        if k in ("loss_satnerf", "model_forward", "grad_norms"):
+            continue
+        got = res[k].cpu().numpy()
+        assert got.shape == g.shape and got.dtype == g.dtype, k
+        if k == "semantic_label_coarse":
+            continue
+        tol = {"rgb_coarse": 1e-3, "depth_coarse": 1e-3, "weights_coarse": 2e-3, "transparency_coarse": 2e-3,
+               "weights_sc_coarse": 2e-3, "semantic_logits_coarse": 2e-3, "sun_coarse": 2e-3, "sun_sc_coarse": 2e-3,
+               "beta_coarse": 5e-3, "sigmas_coarse": 1.5e-2}[k]
+        if trained:
+            tol *= 8      # heads 4x wider than any initialiser: bf16 rounding scales with them
+        assert np.abs(got - g).max() <= tol, (k, np.abs(got - g).max())
+
+
+@pytest.mark.parametrize("kind,C,sc", [("semantic", 6, 0.05), ("satnerf", 0, 0.05), ("semantic", 6, 0.0)])
+def test_render_rays_keys_values_and_gradients(kind, C, sc):
+    from semnerf_b200.renderer import B200Renderer
+    _lib_or_fail()
+    S, n = 64, 512
+    spec, params, emb, cfgs, model, t = _model(kind, C, seed=1, S=S, sc=sc)
+    rays, extras = O.synthetic_rays(n, seed=11)
+    u = torch.rand(n, S, generator=torch.Generator().manual_seed(3))
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    e = emb.clone().requires_grad_(True)
+    ref = O.render_rays(p, e, spec, rays, extras, S, u=u, sc_lambda=sc)
+    res = B200Renderer(cfgs).render_rays({"coarse": model, "t": t}, rays.to(DEV), extras.to(DEV),
+                                         render_options={"u": u.to(DEV)})
+    ref_keys = {k for k in ref if not k.startswith("_")}
+    assert ref_keys <= set(res.keys())                       # same dictionary keys (*_coarse, *_sc_coarse)
+    for k in ref_keys:
+        assert res[k].shape == ref[k].shape and res[k].dtype == ref[k].dtype, k
+    assert (res["rgb_coarse"].detach().cpu() - ref["rgb_coarse"].detach()).abs().max() <= 1e-3
+    assert (res["depth_coarse"].detach().cpu() - ref["depth_coarse"].detach()).abs().max() <= 1e-3
+    # PSNR against a synthetic target must agree within 0.05 dB (bf16 mode criterion)
+    gt = (ref["rgb_coarse"].detach() + 0.03 * torch.randn(n, 3, generator=torch.Generator().manual_seed(9))).clamp(0, 1)
+    assert abs(O.psnr(res["rgb_coarse"].detach().cpu(), gt) - O.psnr(ref["rgb_coarse"].detach(), gt)) <= 0.05
+    if C:
+        agree = (res["semantic_label_coarse"].cpu() == ref["semantic_label_coarse"]).float().mean().item()
+        margin = ref["semantic_logits_coarse"].detach().topk(2, -1)[0]
+        clear = (margin[:, 0] - margin[:, 1]) > 5e-3       # rays whose top-2 margin exceeds the bf16 noise floor
+        agree_clear = (res["semantic_label_coarse"].cpu() == ref["semantic_label_coarse"])[clear].float().mean().item()
+        assert agree >= 0.98 and agree_clear >= 0.999
+    # gradients through the losses that sit on the path's outputs
+    lab = torch.randint(0, max(C, 1), (n,), generator=torch.Generator().manual_seed(4))
+    lr = O.satnerf_loss(ref, gt, lambda_sc=sc) + (O.semantic_loss(ref, lab) if C else 0)
+    lg = O.satnerf_loss(res, gt.to(DEV), lambda_sc=sc) + (O.semantic_loss(res, lab.to(DEV)) if C else 0)
+    assert abs(lr.item() - lg.item()) <= 1e-3 * abs(lr.item())
+    lr.backward()
+    lg.backward()
+    grads = model.named_grads()
+    for k in p:
+        assert _cos(grads[k].cpu(), p[k].grad) >= 0.999, k     # gradient cosine >= 0.999 per parameter
+    assert _cos(model.flat.grad.cpu(), torch.cat([p[k].grad.flatten() for k in p])) >= 0.9995
+    assert _cos(t.weight.grad.cpu(), e.grad) >= 0.999
+
+
+def test_render_depth_only_heads_and_no_grad_path():
+    from semnerf_b200.renderer import B200Renderer
+    _lib_or_fail()
+    S, n = 64, 256
+    spec, params, emb, cfgs, model, t = _model("semantic", 6, seed=2, S=S)
+    rays, extras = O.synthetic_rays(n, seed=5)
+    u = torch.rand(n, S, generator=torch.Generator().manual_seed(1))
+    models = {"coarse": model, "t": t}
+    r = B200Renderer(cfgs)
+    with torch.no_grad():
+        full = r.render_rays(models, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV)})
+        dep = r.render_rays(models, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV), "heads": "depth"})
+    assert torch.equal(full["depth_coarse"], dep["depth_coarse"]) and torch.equal(full["weights_coarse"], dep["weights_coarse"])
+    assert "weights_sc_coarse" not in dep
+    # depth-only backward touches trunk + sigma only
+    dep = r.render_rays(models, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV), "heads": "depth"})
+    dep["depth_coarse"].sum().backward()
+    g = model.named_grads()
+    assert g["fc_net.0.weight"].abs().sum() > 0 and g["sigma_from_xyz.0.weight"].abs().sum() > 0
+    assert g["rgb_from_xyzdir.0.weight"].abs().sum() == 0 and g["feats_from_xyz.weight"].abs().sum() == 0
+
+
+def test_state_dict_interchange_changes_results():
+    """loading a checkpoint re-packs the bf16 image (the packed weights follow the parameters)."""
+    from semnerf_b200.renderer import B200Renderer
+    _lib_or_fail()
+    spec, params, emb, cfgs, model, t = _model("satnerf", 0, seed=1)
+    rays, extras = O.synthetic_rays(128, seed=1)
+    u = torch.rand(128, 64, generator=torch.Generator().manual_seed(1)).to(DEV)
+    r = B200Renderer(cfgs)
+    with torch.no_grad():
+        a = r.render_rays({"coarse": model, "t": t}, rays.to(DEV), extras.to(DEV), render_options={"u": u})["rgb_coarse"]
+        model.load_state_dict(O.make_params(spec, seed=99)[0])
+        b = r.render_rays({"coarse": model, "t": t}, rays.to(DEV), extras.to(DEV), render_options={"u": u})["rgb_coarse"]
+        model.load_state_dict(params)
+        c = r.render_rays({"coarse": model, "t": t}, rays.to(DEV), extras.to(DEV), render_options={"u": u})["rgb_coarse"]
+    assert not torch.equal(a, b) and torch.equal(a, c)
