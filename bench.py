@@ -54,7 +54,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

@@ -1,6 +1,8 @@
 // K2 GEMM kernel - see k2_gemm.cuh for the design.  sm_100a only (tcgen05 / TMEM / TMA).
 #include "k2_gemm.cuh"
 
+#include <stdlib.h>
+
 #include <mutex>
 
 namespace snb {
@@ -57,6 +59,33 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2-SM form: issued by each CTA of a pair for its own smem; the transaction bytes are reported to
+// the LEADER CTA's barrier (same smem offset, peer bit cleared) - cute::SM100_TMA_2SM_LOAD_2D.
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_op(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  if constexpr (CG == 2) tma_load_2d_2sm(smem_dst, m, bar, c0, c1);
+  else tma_load_2d(smem_dst, m, bar, c0, c1);
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remAddr32;\n"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
@@ -94,6 +123,26 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// cta_group::2: issued by the leader CTA of a pair; M = 256 spans both CTAs' TMEM; arrivals are
+// multicast to the same barrier offset in both CTAs (cutlass::arch::umma_arrive_multicast_2x1SM)
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -118,7 +167,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -151,170 +199,222 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& a, int tile) {
   return t;
 }
 
-template <int EPI>
+// CG = 1: one CTA per 128 x block_n tile.  CG = 2: an SM pair (cluster of 2) per 256 x block_n tile -
+// each CTA holds its 128 rows of A and HALF of the B tile, the leader CTA issues cta_group::2 MMAs.
+template <int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_constant__ GemmArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
-  uint8_t* sB = sA + GEMM_STAGES * GEMM_A_STAGE;
-  uint8_t* sStg = sB + GEMM_STAGES * GEMM_B_STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sStg + GEMM_NUM_STAGING * GEMM_STAGING);
-  uint64_t* empty = full + GEMM_STAGES;
-  uint64_t* tfull = empty + GEMM_STAGES;
+  uint8_t* sB = sA + args.a_stages * GEMM_A_STAGE;
+  uint8_t* sStg = smem + GEMM_OPERAND_BYTES;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(sStg + GEMM_NUM_STAGING * GEMM_STAGING);
+  uint64_t* emptyA = fullA + GEMM_MAX_RING;
+  uint64_t* fullB = emptyA + GEMM_MAX_RING;
+  uint64_t* emptyB = fullB + GEMM_MAX_RING;
+  uint64_t* tfull = emptyB + GEMM_MAX_RING;
   uint64_t* tempty = tfull + 2;
   uint64_t* mfull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mfull + GEMM_NUM_STAGING);
+  const uint32_t a_stages = (uint32_t)args.a_stages, b_stages = (uint32_t)args.b_stages;
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
+  uint32_t cta_rank = 0;
+  if constexpr (CG == 2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool lead_cta = (cta_rank == 0);
+  const int unit = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;    // tile-scheduling unit: CTA or CTA pair
+  const int n_units = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t b_slot = args.b_slot;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < args.nseg; ++s) tma_prefetch_desc(&args.tmA[s]);
     tma_prefetch_desc(&args.tmB);
-    for (int s = 0; s < GEMM_STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+    for (int s = 0; s < GEMM_MAX_RING; ++s) {
+      mbar_init(&fullA[s], CG);   // CG == 2: the leader's expect_tx arrive + the peer's remote arrive
+      mbar_init(&emptyA[s], 1);
+      mbar_init(&fullB[s], CG);
+      mbar_init(&emptyB[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 128);
+      mbar_init(&tempty[s], CG * GEMM_EPI_THREADS);
     }
     for (int s = 0; s < GEMM_NUM_STAGING; ++s) mbar_init(&mfull[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // peer barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int total_tiles = args.m_tiles * args.n_tiles * args.splits;
 
   if (warp == 0) {
-    // ===================================== TMA producer =====================================
+    // ===================================== TMA producer: operand A ===========================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      const int nb_boxes = (args.block_n + 63) / 64;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
         const TileCoord t = decode_tile(args, tile);
+        const int m_row = t.m_blk * (GEMM_BLOCK_M * CG) + (int)cta_rank * GEMM_BLOCK_M;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], args.a_bytes + args.b_bytes);
+          mbar_wait(&emptyA[stage], phase ^ 1);
+          if (lead_cta) mbar_expect_tx(&fullA[stage], args.a_bytes * CG);
+          else mbar_arrive_remote(&fullA[stage], 0);
           uint8_t* a_dst = sA + stage * GEMM_A_STAGE;
-          uint8_t* b_dst = sB + stage * GEMM_B_STAGE;
           if (!args.a_mn) {
             int s = 0, kk = kb;
             while (s + 1 < args.nseg && kk >= args.seg_kb[s]) {
               kk -= args.seg_kb[s];
               ++s;
             }
-            tma_load_2d(a_dst, &args.tmA[s], &full[stage], kk * GEMM_BLOCK_K, t.m_blk * GEMM_BLOCK_M);
+            tma_load_op<CG>(a_dst, &args.tmA[s], &fullA[stage], kk * GEMM_BLOCK_K, m_row);
           } else {
             // [64 samples x 64 features] boxes; feature atoms 8 KB apart (UMMA LBO)
-            tma_load_2d(a_dst, &args.tmA[0], &full[stage], t.m_blk * GEMM_BLOCK_M, kb * GEMM_BLOCK_K);
-            tma_load_2d(a_dst + 8192, &args.tmA[0], &full[stage], t.m_blk * GEMM_BLOCK_M + 64, kb * GEMM_BLOCK_K);
+            tma_load_op<CG>(a_dst, &args.tmA[0], &fullA[stage], m_row, kb * GEMM_BLOCK_K);
+            tma_load_op<CG>(a_dst + 8192, &args.tmA[0], &fullA[stage], m_row + 64, kb * GEMM_BLOCK_K);
           }
+          if (++stage == a_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================== TMA producer: operand B ===========================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      const int n_half = args.block_n / CG;   // B rows this CTA holds
+      const int nb_boxes = (n_half + 63) / 64;
+      for (int tile = unit; tile < total_tiles; tile += n_units) {
+        const TileCoord t = decode_tile(args, tile);
+        const int n_row = t.n_blk * args.block_n + (int)cta_rank * n_half;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(&emptyB[stage], phase ^ 1);
+          if (lead_cta) mbar_expect_tx(&fullB[stage], args.b_bytes * CG);
+          else mbar_arrive_remote(&fullB[stage], 0);
+          uint8_t* b_dst = sB + stage * b_slot;
           if (!args.b_mn) {
-            tma_load_2d(b_dst, &args.tmB, &full[stage], kb * GEMM_BLOCK_K, t.n_blk * args.block_n);
+            tma_load_op<CG>(b_dst, &args.tmB, &fullB[stage], kb * GEMM_BLOCK_K, n_row);
           } else {
             for (int j = 0; j < nb_boxes; ++j)
-              tma_load_2d(b_dst + j * 8192, &args.tmB, &full[stage], t.n_blk * args.block_n + j * 64,
-                          kb * GEMM_BLOCK_K);
+              tma_load_op<CG>(b_dst + j * 8192, &args.tmB, &fullB[stage], n_row + j * 64, kb * GEMM_BLOCK_K);
           }
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == b_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0) {
+    if (lane == 0 && lead_cta) {
       // cute::UMMA::InstrDescriptor: c_format f32 (1<<4), a/b format bf16 (1<<7, 1<<10),
       // a_major bit 15, b_major bit 16, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)args.a_mn << 15) |
                              ((uint32_t)args.b_mn << 16) | ((uint32_t)(args.block_n >> 3) << 17) |
-                             ((uint32_t)(GEMM_BLOCK_M >> 4) << 24);
+                             ((uint32_t)((GEMM_BLOCK_M * CG) >> 4) << 24);
       // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused (1).  MN-major SW128: 8-k groups
       // 1024 B apart (SBO), 64-element MN atoms 8192 B apart (LBO).
       const uint32_t a_lbo = args.a_mn ? 8192u : 16u, b_lbo = args.b_mn ? 8192u : 16u;
       const uint32_t a_kstep = args.a_mn ? 2048u : 32u, b_kstep = args.b_mn ? 2048u : 32u;
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+      for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
         const TileCoord t = decode_tile(args, tile);
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * GEMM_MAX_BLOCK_N;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&fullA[sa], pa);
+          mbar_wait(&fullB[sb], pb);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * GEMM_A_STAGE);
-          const uint32_t b_addr = smem_u32(sB + stage * GEMM_B_STAGE);
+          const uint32_t a_addr = smem_u32(sA + sa * GEMM_A_STAGE);
+          const uint32_t b_addr = smem_u32(sB + sb * b_slot);
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             const uint64_t adesc = umma_desc(a_addr + k * a_kstep, a_lbo, 1024u);
             const uint64_t bdesc = umma_desc(b_addr + k * b_kstep, b_lbo, 1024u);
-            tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            if constexpr (CG == 2) tc_mma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(&empty[stage]);  // frees the smem stage once these MMAs have read it
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
+          // frees the smem slots (in both CTAs of a pair) once these MMAs have read them
+          if constexpr (CG == 2) { tc_commit_2sm(&emptyA[sa]); tc_commit_2sm(&emptyB[sb]); }
+          else { tc_commit(&emptyA[sa]); tc_commit(&emptyB[sb]); }
+          if (++sa == a_stages) { sa = 0; pa ^= 1; }
+          if (++sb == b_stages) { sb = 0; pb ^= 1; }
         }
-        tc_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        if constexpr (CG == 2) tc_commit_2sm(&tfull[acc]);   // accumulator complete -> both CTAs' epilogues
+        else tc_commit(&tfull[acc]);
       }
     }
   } else {
-    // ===================================== epilogue (128 threads) ============================
-    const int quad = warp & 3;          // TMEM lane quadrant this warp may read (warp id % 4)
-    const int row = quad * 32 + lane;   // row of the 128-row tile == TMEM lane
-    const int etid = threadIdx.x - 64;  // 0..127
-    const bool leader = (etid == 0);
-    const uint32_t stg0 = smem_u32(sStg);
+    // ===================================== epilogue (2 x 128 threads) ========================
+    // Two warpgroups share every tile: group g takes the column chunks c with (c & 1) == g, so each
+    // SM sub-partition has two epilogue warps to hide the TMEM-load / MUFU latencies behind each other.
+    const int ewarp = warp - 3;             // 0..7
+    const int grp = ewarp >> 2;             // epilogue group
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may read (warp id % 4)
+    const int row = quad * 32 + lane;       // row of the 128-row tile == TMEM lane
+    const int gtid = (ewarp & 3) * 32 + lane;  // 0..127 within the group
+    const bool leader = (gtid == 0);
+    const uint32_t stg0 = smem_u32(sStg) + grp * 2 * GEMM_STAGING;   // this group's two staging buffers
+    uint8_t* stg_ptr = sStg + grp * 2 * GEMM_STAGING;
+    uint64_t* gmfull = mfull + grp * 2;
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
+    const int bar_id = 1 + grp;
+    auto gbar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
     uint32_t it = 0;
-    uint32_t cn = 0;  // running chunk counter = position in the staging ring
+    uint32_t cn = 0;  // this group's running chunk counter (position in its staging ring)
 
-    // EPI_MUL: chunks of the saved SIREN derivative are prefetched two chunks ahead into the ring
-    const uint32_t mul_chunks = (uint32_t)(args.block_n / 64);
+    // EPI_MUL: this group's chunk n+1 of the saved SIREN derivative is prefetched while chunk n is processed
+    const uint32_t grp_chunks = (uint32_t)(args.block_n / 128);   // chunks per tile per group (64-wide chunks)
     auto mul_issue = [&](uint32_t n) {
-      const uint32_t tl = n / mul_chunks, c = n % mul_chunks;
-      const long long tile = (long long)blockIdx.x + (long long)tl * gridDim.x;
+      const uint32_t tl = n / grp_chunks, c = (n % grp_chunks) * 2 + grp;
+      const long long tile = (long long)unit + (long long)tl * n_units;
       if (tile >= total_tiles) return;
       const TileCoord t = decode_tile(args, (int)tile);
-      mbar_expect_tx(&mfull[n & 3], GEMM_STAGING);
-      tma_load_2d(sStg + (n & 3) * GEMM_STAGING, &args.tmMul, &mfull[n & 3], t.n_blk * args.block_n + (int)c * 64,
-                  t.m_blk * GEMM_BLOCK_M);
+      mbar_expect_tx(&gmfull[n & 1], GEMM_STAGING);
+      tma_load_2d(stg_ptr + (n & 1) * GEMM_STAGING, &args.tmMul, &gmfull[n & 1], t.n_blk * args.block_n + (int)c * 64,
+                  t.m_blk * (GEMM_BLOCK_M * CG) + (int)cta_rank * GEMM_BLOCK_M);
     };
-    if (EPI == EPI_MUL && leader) {
-      mul_issue(0);
-      mul_issue(1);
-    }
+    if (EPI == EPI_MUL && leader && grp_chunks > 0) mul_issue(0);
 
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
       const TileCoord t = decode_tile(args, tile);
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * GEMM_MAX_BLOCK_N;
-      const int m0 = t.m_blk * GEMM_BLOCK_M;
+      const int m0 = t.m_blk * (GEMM_BLOCK_M * CG) + (int)cta_rank * GEMM_BLOCK_M;
       const int n0 = t.n_blk * args.block_n;
 
       if constexpr (EPI == EPI_SIN || EPI == EPI_LINEAR || EPI == EPI_MUL) {
-        // ---- bf16 outputs, 64-column chunks through the swizzled staging ring + TMA store -------
+        // ---- bf16 outputs, 64-column chunks through swizzled staging + TMA store ---------------------
         const bool two = (EPI == EPI_SIN) && args.two_out;
         const int chunks = args.block_n / 64;
-        for (int c = 0; c < chunks; ++c, ++cn) {
-          uint32_t buf0, buf1 = 0;
-          if (two) {
-            buf0 = stg0 + (2 * (cn & 1)) * GEMM_STAGING;
-            buf1 = buf0 + GEMM_STAGING;
-          } else {
-            buf0 = stg0 + (cn & 3) * GEMM_STAGING;
+        for (int c = grp; c < chunks; c += 2, ++cn) {
+          // two outputs: both buffers per chunk; one output: the buffers alternate
+          const uint32_t buf0 = two ? stg0 : stg0 + (cn & 1) * GEMM_STAGING;
+          const uint32_t buf1 = stg0 + GEMM_STAGING;
+          if constexpr (EPI == EPI_MUL) {
+            if (leader) {
+              bulk_wait_read<0>();   // store of chunk cn-1 has drained its buffer ...
+              mul_issue(cn + 1);     // ... which now receives the derivative chunk after this one
+            }
+            mbar_wait(&gmfull[cn & 1], (cn >> 1) & 1);
           }
-          if constexpr (EPI == EPI_MUL) mbar_wait(&mfull[cn & 3], (cn >> 2) & 1);
+          uint32_t outw[2][16], outc[2][16];  // packed bf16x2 results of the two 32-column halves
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t v[32];
@@ -342,111 +442,126 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
                   x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
                 }
                 if constexpr (EPI == EPI_SIN) {
-                  float s[8], cs[8];
+                  float sn[8], cs[8];
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
                     const float y = args.w0 * x[j];
-                    s[j] = __sinf(y);
+                    sn[j] = __sinf(y);
                     cs[j] = args.w0 * __cosf(y);
                   }
-                  st_shared_v4(buf0 + off, pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]),
-                               pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
-                  if (two)
-                    st_shared_v4(buf1 + off, pack_bf16x2(cs[0], cs[1]), pack_bf16x2(cs[2], cs[3]),
-                                 pack_bf16x2(cs[4], cs[5]), pack_bf16x2(cs[6], cs[7]));
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    outw[half][g * 4 + j] = pack_bf16x2(sn[2 * j], sn[2 * j + 1]);
+                    outc[half][g * 4 + j] = pack_bf16x2(cs[2 * j], cs[2 * j + 1]);
+                  }
                 } else {
-                  st_shared_v4(buf0 + off, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
-                               pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) outw[half][g * 4 + j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
                 }
               }
             }
           }
-          fence_proxy_async();
-          if (EPI != EPI_MUL && leader) {
-            // the buffer(s) the NEXT chunk writes must have been drained by their previous TMA store
-            if (two) bulk_wait_read<0>();
-            else bulk_wait_read<2>();
+          if constexpr (EPI != EPI_MUL) {
+            // results are in registers: now make sure the previous TMA store(s) of the buffer(s) about
+            // to be overwritten have drained (they had the whole compute phase above to do so)
+            if (leader) {
+              if (two) bulk_wait_read<0>();
+              else bulk_wait_read<1>();
+            }
+            gbar();
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t off = row_off + ((((uint32_t)(half * 4 + g)) ^ sw) << 4);
+                st_shared_v4(buf0 + off, outw[half][g * 4], outw[half][g * 4 + 1], outw[half][g * 4 + 2],
+                             outw[half][g * 4 + 3]);
+                if (two)
+                  st_shared_v4(buf1 + off, outc[half][g * 4], outc[half][g * 4 + 1], outc[half][g * 4 + 2],
+                               outc[half][g * 4 + 3]);
+              }
           }
-          epi_bar_sync();
+          fence_proxy_async();
+          gbar();
           if (leader) {
             tma_store_2d(&args.tmO0, buf0, n0 + c * 64, m0);
             if (two) tma_store_2d(&args.tmO1, buf1, n0 + c * 64, m0);
             bulk_commit();
-            if constexpr (EPI == EPI_MUL) {
-              // ring slot (cn+2)&3 was last stored by chunk cn-2: allow {cn, cn-1} to be pending
-              bulk_wait_read<2>();
-              mul_issue(cn + 2);
-            }
           }
         }
       } else if constexpr (EPI == EPI_HEADOUT) {
-        // ---- N=16 head pre-activations -> packed (P, n_out) fp32 rows ---------------------------
-        uint32_t v[16];
-        tmem_ld16(taddr, v);
-        tc_wait_ld();
-        float* stg = reinterpret_cast<float*>(sStg);
-        const int n_out = args.n_out;
-        const long long grow = (long long)m0 + row;
-        float x[16];
+        // ---- N=16 head pre-activations -> packed (P, n_out) fp32 rows (group 0 only) -----------------
+        if (grp == 0) {
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
+          tc_wait_ld();
+          float* stg = reinterpret_cast<float*>(sStg);
+          const int n_out = args.n_out;
+          const long long grow = (long long)m0 + row;
+          float x[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + (args.bias ? __ldg(args.bias + j) : 0.f);
-        float* o = stg + row * n_out;
-        const int hm = args.head_mask;
-        // rs_semantic.py:282-284: rgb = sigmoid(.) * (1 + 2*0.001) - 0.001
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + (args.bias ? __ldg(args.bias + j) : 0.f);
+          float* o = stg + row * n_out;
+          const int hm = args.head_mask;
+          // rs_semantic.py:282-284: rgb = sigmoid(.) * (1 + 2*0.001) - 0.001
 #pragma unroll
-        for (int j = 0; j < 3; ++j) o[j] = (hm & SNB_HEAD_RGB) ? (1.0f / (1.0f + expf(-x[j]))) * 1.002f - 0.001f : 0.f;
-        o[3] = (hm & SNB_HEAD_SIGMA) ? (x[3] > 20.f ? x[3] : log1pf(expf(x[3]))) : 0.f;
-        o[4] = (hm & SNB_HEAD_SUN) ? 1.0f / (1.0f + expf(-x[4])) : 0.f;
-        if ((hm & SNB_HEAD_SKY) && args.sky && grow < args.M) {
-          const long long ray = args.rows_per_ray > 0 ? grow / args.rows_per_ray : grow;
-          o[5] = __ldg(args.sky + ray * 3);
-          o[6] = __ldg(args.sky + ray * 3 + 1);
-          o[7] = __ldg(args.sky + ray * 3 + 2);
-        } else {
-          o[5] = o[6] = o[7] = 0.f;
-        }
-        o[8] = (hm & SNB_HEAD_BETA) ? (x[5] > 20.f ? x[5] : log1pf(expf(x[5]))) : 0.f;
-#pragma unroll
-        for (int c = 0; c < 10; ++c) {
-          if (c < args.n_classes) {
-            const float s = x[6 + c];
-            o[9 + c] = (hm & SNB_HEAD_SEM) ? (args.sem_sigmoid ? 1.0f / (1.0f + expf(-s)) : s) : 0.f;
+          for (int j = 0; j < 3; ++j) o[j] = (hm & SNB_HEAD_RGB) ? (1.0f / (1.0f + expf(-x[j]))) * 1.002f - 0.001f : 0.f;
+          o[3] = (hm & SNB_HEAD_SIGMA) ? (x[3] > 20.f ? x[3] : log1pf(expf(x[3]))) : 0.f;
+          o[4] = (hm & SNB_HEAD_SUN) ? 1.0f / (1.0f + expf(-x[4])) : 0.f;
+          if ((hm & SNB_HEAD_SKY) && args.sky && grow < args.M) {
+            const long long ray = args.rows_per_ray > 0 ? grow / args.rows_per_ray : grow;
+            o[5] = __ldg(args.sky + ray * 3);
+            o[6] = __ldg(args.sky + ray * 3 + 1);
+            o[7] = __ldg(args.sky + ray * 3 + 2);
+          } else {
+            o[5] = o[6] = o[7] = 0.f;
           }
-        }
-        epi_bar_sync();
-        const int valid = min(GEMM_BLOCK_M, args.M - m0);
-        const int total = valid * n_out;
-        float* dst = args.out_packed + (size_t)m0 * n_out;
-        for (int i = etid; i < total; i += 128) dst[i] = stg[i];
-        epi_bar_sync();
-      } else if constexpr (EPI == EPI_F32ROWS) {
-        uint32_t v[16];
-        tmem_ld16(taddr, v);
-        tc_wait_ld();
-        const long long grow = (long long)m0 + row;
-        if (grow < args.M) {
-          float4* dst = reinterpret_cast<float4*>(args.f32out + grow * args.ldo);
+          o[8] = (hm & SNB_HEAD_BETA) ? (x[5] > 20.f ? x[5] : log1pf(expf(x[5]))) : 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          for (int c = 0; c < 10; ++c) {
+            if (c < args.n_classes) {
+              const float sv = x[6 + c];
+              o[9 + c] = (hm & SNB_HEAD_SEM) ? (args.sem_sigmoid ? 1.0f / (1.0f + expf(-sv)) : sv) : 0.f;
+            }
+          }
+          gbar();
+          const int valid = min(GEMM_BLOCK_M, args.M - m0);
+          const int total = valid * n_out;
+          float* dst = args.out_packed + (size_t)m0 * n_out;
+          for (int i = gtid; i < total; i += 128) dst[i] = stg[i];
+          gbar();
+        }
+      } else if constexpr (EPI == EPI_F32ROWS) {
+        if (grp == 0) {
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
+          tc_wait_ld();
+          const long long grow = (long long)m0 + row;
+          if (grow < args.M) {
+            float4* dst = reinterpret_cast<float4*>(args.f32out + grow * args.ldo);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          }
         }
       } else {  // EPI_WGRAD
         if (args.block_n >= 32 && (args.block_n & 31) == 0 && args.f32out == nullptr) {
           // fp32 tile -> 32-column swizzled chunks -> TMA reduce-add (split-K accumulation in L2)
           const int chunks = args.block_n / 32;
-          for (int c = 0; c < chunks; ++c, ++cn) {
-            const uint32_t buf0 = stg0 + (cn & 3) * GEMM_STAGING;
+          for (int c = grp; c < chunks; c += 2, ++cn) {
+            const uint32_t buf0 = stg0 + (cn & 1) * GEMM_STAGING;
             uint32_t v[32];
             tmem_ld32(taddr + c * 32, v);
             tc_wait_ld();
+            if (leader) bulk_wait_read<1>();
+            gbar();
 #pragma unroll
             for (int g = 0; g < 8; ++g)
               st_shared_v4(buf0 + row_off + ((((uint32_t)g) ^ sw) << 4), v[4 * g], v[4 * g + 1], v[4 * g + 2],
                            v[4 * g + 3]);
             fence_proxy_async();
-            if (leader) bulk_wait_read<2>();
-            epi_bar_sync();
+            gbar();
             if (leader) {
               tma_reduce_add_2d(&args.tmO0, buf0, n0 + c * 32, m0);
               bulk_commit();
@@ -455,7 +570,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
         } else {
           // narrow outputs (bias / per-ray columns, N = 16 or 64): red.global.add.f32
           const long long grow = (long long)m0 + row;
-          for (int c0 = 0; c0 < args.block_n; c0 += 16) {
+          for (int c0 = grp * 16; c0 < args.block_n; c0 += 32) {
             uint32_t v[16];
             tmem_ld16(taddr + c0, v);
             tc_wait_ld();
@@ -470,16 +585,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      if (lead_cta) mbar_arrive(&tempty[acc]);
+      else mbar_arrive_remote(&tempty[acc], 0);   // the leader CTA's MMA warp owns the accumulator hand-shake
     }
     if (leader) bulk_wait_all();
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // neither CTA may exit while its peer can still signal it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    if constexpr (CG == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -527,23 +647,71 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t inn
   return 0;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+int gemm_pick_cta_group(int epi, long long M, int N, int block_n) {
+  static const int allow = env_int("SNB_CG", 2);
+  if (allow < 2) return 1;
+  // SM pairs for the big tiles: 256 x 256, each CTA ingests 32 KB per k-block instead of 48 KB
+  if (block_n == 256 && N % 256 == 0 && M >= 256 && epi != EPI_HEADOUT && epi != EPI_F32ROWS) return 2;
+  return 1;
+}
+
 void gemm_finalize(GemmArgs& a) {
-  a.m_tiles = (a.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  if (a.cta_group != 2) a.cta_group = 1;
+  const int cg = a.cta_group;
+  a.m_tiles = (a.M + GEMM_BLOCK_M * cg - 1) / (GEMM_BLOCK_M * cg);
   a.n_tiles = (a.N + a.block_n - 1) / a.block_n;
   if (a.splits < 1) a.splits = 1;
   if (a.splits > a.kb_total) a.splits = a.kb_total;
+  const int n_half = a.block_n / cg;
   a.a_bytes = GEMM_A_STAGE;
-  a.b_bytes = a.b_mn ? (unsigned)(((a.block_n + 63) / 64) * 8192) : (unsigned)(a.block_n * GEMM_BLOCK_K * 2);
+  a.b_bytes = a.b_mn ? (unsigned)(((n_half + 63) / 64) * 8192) : (unsigned)(n_half * GEMM_BLOCK_K * 2);
+  a.b_slot = cg == 2 ? GEMM_B_STAGE / 2 : GEMM_B_STAGE;
+  if (a.a_stages <= 0 || a.b_stages <= 0) {
+    static int ov[6] = {0, 0, 0, 0, 0, 0};
+    static bool parsed = false;
+    if (!parsed) {
+      parsed = true;  // tuning override: SNB_RINGS="aK,bK,aMN,bMN,a2,b2"
+      if (const char* e = getenv("SNB_RINGS")) sscanf(e, "%d,%d,%d,%d,%d,%d", &ov[0], &ov[1], &ov[2], &ov[3], &ov[4], &ov[5]);
+    }
+    if (cg == 2) { a.a_stages = 5; a.b_stages = 5; }          // 16 KB slots each: 160 KB
+    else if (!a.a_mn) { a.a_stages = 4; a.b_stages = 3; }
+    else { a.a_stages = 4; a.b_stages = 3; }
+    if (cg == 2 && ov[4] > 0 && ov[5] > 0) { a.a_stages = ov[4]; a.b_stages = ov[5]; }
+    if (cg == 1 && !a.a_mn && ov[0] > 0 && ov[1] > 0) { a.a_stages = ov[0]; a.b_stages = ov[1]; }
+    if (cg == 1 && a.a_mn && ov[2] > 0 && ov[3] > 0) { a.a_stages = ov[2]; a.b_stages = ov[3]; }
+  }
 }
 
-template <int EPI>
-static int launch_epi(const GemmArgs& a, int grid, cudaStream_t st) {
+template <int EPI, int CG>
+static int launch_epi(const GemmArgs& a, int units, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SNB_CUDA(cudaFuncSetAttribute(snb_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    SNB_CUDA(cudaFuncSetAttribute(snb_gemm_kernel<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     attr_set = true;
   }
-  snb_gemm_kernel<EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(a);
+  if (CG == 1) {
+    snb_gemm_kernel<EPI, CG><<<units, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(a);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * units);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SNB_CUDA(cudaLaunchKernelEx(&cfg, snb_gemm_kernel<EPI, CG>, a));
+  }
   return launch_status("snb_gemm_kernel");
 }
 
@@ -551,6 +719,9 @@ int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
   SNB_CHECK_ARG(a.block_n >= 16 && a.block_n <= GEMM_MAX_BLOCK_N && (a.block_n % 16) == 0, SNB_ERR_UNSUPPORTED,
                 "gemm: block_n %d unsupported", a.block_n);
   SNB_CHECK_ARG(a.kb_total >= 1 && a.M >= 1 && a.N >= 1, SNB_ERR_INVALID, "gemm: empty problem");
+  SNB_CHECK_ARG(a.a_stages >= 1 && a.b_stages >= 1 && a.a_stages <= GEMM_MAX_RING && a.b_stages <= GEMM_MAX_RING &&
+                    a.a_stages * GEMM_A_STAGE + a.b_stages * (int)a.b_slot <= GEMM_OPERAND_BYTES,
+                SNB_ERR_INVALID, "gemm: ring depths %d/%d exceed the operand smem", a.a_stages, a.b_stages);
   SNB_CHECK_ARG(a.splits == 1 || epi == EPI_WGRAD, SNB_ERR_INVALID, "gemm: split-K only for the accumulate epilogue");
   if (epi == EPI_SIN || epi == EPI_LINEAR || epi == EPI_MUL)
     SNB_CHECK_ARG(a.block_n % 64 == 0, SNB_ERR_UNSUPPORTED, "gemm: bf16 epilogues need block_n %% 64 == 0");
@@ -559,17 +730,21 @@ int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
   const int sms = num_sms();
   if (sms <= 0) return SNB_ERR_NO_DEVICE;
   const long long tiles = (long long)a.m_tiles * a.n_tiles * a.splits;
-  const int grid = (int)(tiles < sms ? tiles : sms);
+  const int max_units = a.cta_group == 2 ? sms / 2 : sms;
+  const int grid = (int)(tiles < max_units ? tiles : max_units);
+  SNB_CHECK_ARG(a.b_stages * (int)a.b_slot + a.a_stages * GEMM_A_STAGE <= GEMM_OPERAND_BYTES, SNB_ERR_INVALID,
+                "gemm: rings %d/%d exceed the operand smem", a.a_stages, a.b_stages);
   const double macs = (double)a.m_tiles * GEMM_BLOCK_M * (double)a.n_tiles * a.block_n * (double)a.kb_total * GEMM_BLOCK_K;
   const bool timed = profile_gemm_begin(st, macs);
   int rc;
+  const bool two = a.cta_group == 2;
   switch (epi) {
-    case EPI_SIN: rc = launch_epi<EPI_SIN>(a, grid, st); break;
-    case EPI_LINEAR: rc = launch_epi<EPI_LINEAR>(a, grid, st); break;
-    case EPI_MUL: rc = launch_epi<EPI_MUL>(a, grid, st); break;
-    case EPI_HEADOUT: rc = launch_epi<EPI_HEADOUT>(a, grid, st); break;
-    case EPI_F32ROWS: rc = launch_epi<EPI_F32ROWS>(a, grid, st); break;
-    case EPI_WGRAD: rc = launch_epi<EPI_WGRAD>(a, grid, st); break;
+    case EPI_SIN: rc = two ? launch_epi<EPI_SIN, 2>(a, grid, st) : launch_epi<EPI_SIN, 1>(a, grid, st); break;
+    case EPI_LINEAR: rc = two ? launch_epi<EPI_LINEAR, 2>(a, grid, st) : launch_epi<EPI_LINEAR, 1>(a, grid, st); break;
+    case EPI_MUL: rc = two ? launch_epi<EPI_MUL, 2>(a, grid, st) : launch_epi<EPI_MUL, 1>(a, grid, st); break;
+    case EPI_HEADOUT: rc = launch_epi<EPI_HEADOUT, 1>(a, grid, st); break;
+    case EPI_F32ROWS: rc = launch_epi<EPI_F32ROWS, 1>(a, grid, st); break;
+    case EPI_WGRAD: rc = two ? launch_epi<EPI_WGRAD, 2>(a, grid, st) : launch_epi<EPI_WGRAD, 1>(a, grid, st); break;
     default: set_error("gemm: unknown epilogue %d", epi); rc = SNB_ERR_INVALID;
   }
   if (timed) profile_gemm_end(st);
@@ -591,6 +766,8 @@ extern "C" int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t 
   a.N = N;
   a.block_n = N >= 256 ? 256 : (N >= 128 ? 128 : (N >= 64 ? 64 : (N >= 32 && epi == EPI_WGRAD ? 32 : 16)));
   a.kb_total = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  a.cta_group = gemm_pick_cta_group(epi, M, N, a.block_n);
+  const uint32_t b_rows = (uint32_t)(a.block_n / a.cta_group);
   a.nseg = 1;
   a.seg_kb[0] = a.kb_total;
   a.a_mn = a_mn;
@@ -605,7 +782,7 @@ extern "C" int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t 
   if (!a_mn) r = make_tmap_2d(&a.tmA[0], A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, GEMM_BLOCK_M);
   else r = make_tmap_2d(&a.tmA[0], A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, 64);
   if (r) return r;
-  if (!b_mn) r = make_tmap_2d(&a.tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, (uint32_t)a.block_n);
+  if (!b_mn) r = make_tmap_2d(&a.tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, b_rows);
   else r = make_tmap_2d(&a.tmB, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64);
   if (r) return r;
   if (epi == EPI_SIN || epi == EPI_LINEAR || epi == EPI_MUL) {

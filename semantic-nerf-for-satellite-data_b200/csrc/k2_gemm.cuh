@@ -2,9 +2,10 @@
 //
 //   D[M,N] (+)= sum over K-segments  A_seg[M,K_seg] * B[N,K]^T        (bf16 in, fp32 accumulate in TMEM)
 //
-// One CTA per SM, 6 warps:  warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+ TMEM owner),
-// warps 2-5 = epilogue (tcgen05.ld -> bias/activation -> bf16 -> swizzled smem -> TMA store).
-// Tile 128 x block_n (<=256) x 64, 3-stage smem ring, two 256-column TMEM accumulators so the
+// One CTA per SM, 11 warps:  warp 0 = TMA producer for A, warp 1 = tcgen05.mma issuer (+ TMEM owner),
+// warp 2 = TMA producer for B, warps 3-10 = two epilogue warpgroups (tcgen05.ld -> bias/activation -> bf16 -> swizzled smem -> TMA
+// store) that split the column chunks of every tile.
+// Tile 128 x block_n (<=256) x 64, decoupled A/B smem rings, two 256-column TMEM accumulators so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Operand layouts (all 128-byte swizzle, filled by TMA, consumed through UMMA smem descriptors):
@@ -29,14 +30,18 @@ enum GemmEpi {
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;
 constexpr int GEMM_MAX_BLOCK_N = 256;
-constexpr int GEMM_STAGES = 3;
 constexpr int GEMM_A_STAGE = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;      // 16 KB
 constexpr int GEMM_B_STAGE = GEMM_MAX_BLOCK_N * GEMM_BLOCK_K * 2;  // 32 KB
+// The A and B operands have independent smem rings (and producer warps): activations come from
+// DRAM (~2500 clk under load) and need depth, weights come from L2 and do not.  The ring depths are
+// per-launch parameters; together they may use GEMM_OPERAND_BYTES.
+constexpr int GEMM_OPERAND_BYTES = 160 * 1024;
+constexpr int GEMM_MAX_RING = 8;
 constexpr int GEMM_STAGING = 16384;                                // one 128 x 128B swizzled chunk
 constexpr int GEMM_NUM_STAGING = 4;
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM_BYTES =
-    GEMM_STAGES * (GEMM_A_STAGE + GEMM_B_STAGE) + GEMM_NUM_STAGING * GEMM_STAGING + 256 + 1024;
+constexpr int GEMM_EPI_THREADS = 256;  // two epilogue warpgroups
+constexpr int GEMM_THREADS = 96 + GEMM_EPI_THREADS;  // warp 0: A producer, 1: MMA, 2: B producer, 3-10: epilogue
+constexpr int GEMM_SMEM_BYTES = GEMM_OPERAND_BYTES + GEMM_NUM_STAGING * GEMM_STAGING + 512 + 1024;
 
 struct GemmArgs {
   CUtensorMap tmA[3];
@@ -51,6 +56,9 @@ struct GemmArgs {
   int m_tiles, n_tiles, splits;
   int a_mn, b_mn;
   unsigned a_bytes, b_bytes;
+  int a_stages, b_stages;  // ring depths: a_stages*16 KB + b_stages*b_slot <= GEMM_OPERAND_BYTES
+  int cta_group;           // 1, or 2 = SM pair per 256 x block_n tile (set before building tmB: its box is block_n/cta_group rows)
+  unsigned b_slot;         // bytes per B ring slot
   int two_out;
   const float* bias;
   float w0;
@@ -69,6 +77,7 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t inn
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
 // fills tile counts / byte counts from M, N, block_n, kb_total, splits, a_mn, b_mn
+int gemm_pick_cta_group(int epi, long long M, int N, int block_n);
 void gemm_finalize(GemmArgs& a);
 int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st);
 

@@ -456,6 +456,7 @@ static GemmArgs& add_kmajor(Plan& p, int epi, long long M, int N, const Seg* seg
   a.M = (int)M;
   a.N = N;
   a.block_n = N >= 256 ? 256 : N;
+  a.cta_group = gemm_pick_cta_group(epi, M, N, a.block_n);
   a.nseg = nseg;
   a.kb_total = 0;
   for (int s = 0; s < nseg; ++s) {
@@ -464,7 +465,7 @@ static GemmArgs& add_kmajor(Plan& p, int epi, long long M, int N, const Seg* seg
     p.chk(make_tmap_2d(&a.tmA[s], segs[s].ptr, 2, (uint64_t)segs[s].cols, (uint64_t)M, (uint64_t)segs[s].ld * 2, 64,
                        GEMM_BLOCK_M));
   }
-  p.chk(make_tmap_2d(&a.tmB, B, 2, (uint64_t)b_cols, (uint64_t)N, (uint64_t)ldb * 2, 64, (uint32_t)a.block_n));
+  p.chk(make_tmap_2d(&a.tmB, B, 2, (uint64_t)b_cols, (uint64_t)N, (uint64_t)ldb * 2, 64, (uint32_t)(a.block_n / a.cta_group)));
   if (epi == EPI_SIN || epi == EPI_LINEAR || epi == EPI_MUL) {
     p.chk(make_tmap_2d(&a.tmO0, out0, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
     if (out1) p.chk(make_tmap_2d(&a.tmO1, out1, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
@@ -486,6 +487,7 @@ static void add_wgrad(Plan& p, int Mf, int Nf, const void* dY, long long ld_dy, 
   a.M = Mf;
   a.N = Nf;
   a.block_n = Nf >= 256 ? 256 : Nf;
+  a.cta_group = (Mf % 256 == 0) ? gemm_pick_cta_group(EPI_WGRAD, Mf, Nf, a.block_n) : 1;
   a.nseg = 1;
   a.kb_total = (int)((P + 63) / 64);
   a.seg_kb[0] = a.kb_total;
@@ -499,14 +501,13 @@ static void add_wgrad(Plan& p, int Mf, int Nf, const void* dY, long long ld_dy, 
     a.f32out = G;
     a.ldo = ldg;
   }
-  const int tiles = ((Mf + 127) / 128) * ((Nf + a.block_n - 1) / a.block_n);
-  int splits = (sms + tiles - 1) / tiles;
-  // narrow (N=16) products are operand-read bound, not MMA bound: a quarter of the CTAs is plenty
-  if (Nf <= 16) splits = (splits + 3) / 4;
-  // keep at least 8 k-blocks per split so the accumulate traffic stays small against the operand reads
-  const int max_splits = a.kb_total / 8 > 0 ? a.kb_total / 8 : 1;
+  const int tiles = ((Mf + 128 * a.cta_group - 1) / (128 * a.cta_group)) * ((Nf + a.block_n - 1) / a.block_n);
+  // one wave: the largest split count whose tile total still fits the SMs / SM pairs (one more tile would double the time)
+  int splits = (sms / a.cta_group) / tiles;
+  if (splits < 1) splits = 1;
+  // keep at least 4 k-blocks per split so the accumulate traffic stays small against the operand reads
+  const int max_splits = a.kb_total / 4 > 0 ? a.kb_total / 4 : 1;
   a.splits = splits < max_splits ? splits : max_splits;
-  if (a.splits < 1) a.splits = 1;
   gemm_finalize(a);
 }
 

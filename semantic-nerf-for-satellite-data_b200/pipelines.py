@@ -1,0 +1,56 @@
+"""Pipeline plug-ins for a checkout of the reference (needs its own dependencies, e.g. Lightning).
+
+The reference selects a pipeline by dotted class path in the pipeline TOML
+(`pipeline = "semantic.pipelines.rs_semantic.RSSemanticPipeline"`, configs/pipelines/rs_semantic.toml:5;
+resolved by framework/pipelines.py:341-352).  Pointing that line at
+`semnerf_b200.pipelines.RSSemanticB200Pipeline` / `SatNeRFB200Pipeline` swaps the B200 model and
+renderer in; datasets, losses, training step, visualisers and checkpoints are the reference's own.
+Only `_init_models` and `_init_renderer` are overridden (semantic/pipelines/rs_semantic.py:61-79,
+baseline/pipelines/satnerf.py:51-69).
+
+The classes are built lazily because the reference modules import pytorch_lightning, which is not
+installed in the build image: `get_pipeline_classes()` raises ImportError with the missing module.
+"""
+from __future__ import annotations
+
+import torch
+
+from .model import RSSemanticNeRFB200, SatNeRFB200
+from .renderer import RSSemanticB200Rendering, SatNeRFB200Rendering
+
+_CACHE = {}
+
+
+def get_pipeline_classes():
+    if _CACHE:
+        return _CACHE
+    from baseline.pipelines.satnerf import SatNeRFPipeline          # reference checkout on sys.path
+    from semantic.pipelines.rs_semantic import RSSemanticPipeline
+
+    class SatNeRFB200Pipeline(SatNeRFPipeline):
+        def _init_models(self) -> dict:
+            p = self.cfgs.pipeline
+            return {"coarse": SatNeRFB200(self.cfgs, layers=p.fc_layers, feat=p.fc_units, skips=p.fc_skips,
+                                          t_embedding_dims=p.t_embedding_tau),
+                    "t": torch.nn.Embedding(p.t_embedding_vocab, p.t_embedding_tau)}
+
+        def _init_renderer(self):
+            return SatNeRFB200Rendering(self.cfgs)
+
+    class RSSemanticB200Pipeline(RSSemanticPipeline):
+        def _init_models(self) -> dict:
+            p = self.cfgs.pipeline
+            return {"coarse": RSSemanticNeRFB200(self.cfgs, self.datasets["rgb"]),
+                    "t": torch.nn.Embedding(p.t_embedding_vocab, p.t_embedding_tau)}
+
+        def _init_renderer(self):
+            return RSSemanticB200Rendering(self.cfgs)
+
+    _CACHE.update(SatNeRFB200Pipeline=SatNeRFB200Pipeline, RSSemanticB200Pipeline=RSSemanticB200Pipeline)
+    return _CACHE
+
+
+def __getattr__(name):  # `semnerf_b200.pipelines.RSSemanticB200Pipeline` resolves through importlib
+    if name in ("SatNeRFB200Pipeline", "RSSemanticB200Pipeline"):
+        return get_pipeline_classes()[name]
+    raise AttributeError(name)

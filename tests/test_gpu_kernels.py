@@ -78,10 +78,10 @@ def test_gemm_wgrad_splitk_accumulates(P, Mf, Nf, splits):
 
 def test_gemm_rejects_bad_arguments():
     lib = _lib_or_fail()
-    a = torch.zeros(128, 64, device=DEV, dtype=torch.bfloat16)
-    assert lib.snb_gemm_bf16(ptr(a), 64, ptr(a), 64, 128, 128, 64, 0, 0, _lib.EPI_LINEAR, ptr(a), None, 128, None, None,
-                             1.0, 4, stream()) == -1          # split-K only with the accumulate epilogue
-    assert lib.snb_gemm_bf16(None, 64, ptr(a), 64, 128, 128, 64, 0, 0, 1, ptr(a), None, 128, None, None, 1.0, 1,
+    a = torch.zeros(128, 256, device=DEV, dtype=torch.bfloat16)
+    assert lib.snb_gemm_bf16(ptr(a), 256, ptr(a), 256, 128, 128, 256, 0, 0, _lib.EPI_LINEAR, ptr(a), None, 128, None,
+                             None, 1.0, 4, stream()) == -1    # split-K only with the accumulate epilogue
+    assert lib.snb_gemm_bf16(None, 256, ptr(a), 256, 128, 128, 256, 0, 0, 1, ptr(a), None, 128, None, None, 1.0, 1,
                              stream()) == -1
 
 

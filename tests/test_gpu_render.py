@@ -98,9 +98,10 @@ def test_render_rays_keys_values_and_gradients(kind, C, sc):
         assert res[k].shape == ref[k].shape and res[k].dtype == ref[k].dtype, k
     assert (res["rgb_coarse"].detach().cpu() - ref["rgb_coarse"].detach()).abs().max() <= 1e-3
     assert (res["depth_coarse"].detach().cpu() - ref["depth_coarse"].detach()).abs().max() <= 1e-3
-    # PSNR against a synthetic target must agree within 0.05 dB (bf16 mode criterion)
-    gt = (ref["rgb_coarse"].detach() + 0.03 * torch.randn(n, 3, generator=torch.Generator().manual_seed(9))).clamp(0, 1)
-    assert abs(O.psnr(res["rgb_coarse"].detach().cpu(), gt) - O.psnr(ref["rgb_coarse"].detach(), gt)) <= 0.05
+    # PSNR against a synthetic target image (~30 dB) must agree within 0.05 dB (bf16 mode criterion)
+    tgt = (ref["rgb_coarse"].detach() + 0.03 * torch.randn(n, 3, generator=torch.Generator().manual_seed(9))).clamp(0, 1)
+    assert abs(O.psnr(res["rgb_coarse"].detach().cpu(), tgt) - O.psnr(ref["rgb_coarse"].detach(), tgt)) <= 0.05
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(9))   # training target for the gradient check
     if C:
         agree = (res["semantic_label_coarse"].cpu() == ref["semantic_label_coarse"]).float().mean().item()
         margin = ref["semantic_logits_coarse"].detach().topk(2, -1)[0]
