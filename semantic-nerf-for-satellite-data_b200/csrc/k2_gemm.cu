@@ -389,6 +389,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
                   t.m_blk * (GEMM_BLOCK_M * CG) + (int)cta_rank * GEMM_BLOCK_M);
     };
     if (EPI == EPI_MUL && leader && grp_chunks > 0) mul_issue(0);
+    // bias-gradient column sums (EPI_MUL / EPI_LINEAR with args.colsum): thread (cj, half) owns column cj of
+    // this group's chunks over 64 of the 128 rows; sums live in registers across tiles and are flushed
+    // with one atomicAdd per column whenever the CTA moves to another n-block (and at the end).
+    const int cs_col = gtid & 63, cs_half = gtid >> 6;
+    float cs_acc[2] = {0.f, 0.f};
+    int cs_nblk = -1;
+    auto cs_flush = [&]() {
+      if (cs_nblk >= 0) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int col = cs_nblk * args.block_n + (2 * q + grp) * 64 + cs_col;
+          if ((2 * q + grp) * 64 < args.block_n && col < args.N && cs_acc[q] != 0.f) atomicAdd(args.colsum + col, cs_acc[q]);
+          cs_acc[q] = 0.f;
+        }
+      }
+    };
 
     for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
       const TileCoord t = decode_tile(args, tile);
@@ -402,6 +418,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
       if constexpr (EPI == EPI_SIN || EPI == EPI_LINEAR || EPI == EPI_MUL) {
         // ---- bf16 outputs, 64-column chunks through swizzled staging + TMA store ---------------------
         const bool two = (EPI == EPI_SIN) && args.two_out;
+        const bool do_cs = (EPI != EPI_SIN) && args.colsum != nullptr;
+        if (do_cs && t.n_blk != cs_nblk) {
+          cs_flush();
+          cs_nblk = t.n_blk;
+        }
         const int chunks = args.block_n / 64;
         for (int c = grp; c < chunks; c += 2, ++cn) {
           // two outputs: both buffers per chunk; one output: the buffers alternate
@@ -480,6 +501,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
                   st_shared_v4(buf1 + off, outc[half][g * 4], outc[half][g * 4 + 1], outc[half][g * 4 + 2],
                                outc[half][g * 4 + 3]);
               }
+          }
+          if (do_cs) {
+            gbar();   // every row of the chunk is in the staging buffer
+            float sum = 0.f;
+            const uint32_t cbase = buf0 + (uint32_t)(cs_col & 7) * 2u;
+#pragma unroll 8
+            for (int r = cs_half * 64; r < cs_half * 64 + 64; ++r) {
+              uint16_t hv;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(cbase + (uint32_t)r * 128u + ((((uint32_t)cs_col >> 3) ^ ((uint32_t)r & 7u)) << 4)));
+              sum += __uint_as_float(((uint32_t)hv) << 16);
+            }
+            if (c < 2) cs_acc[0] += sum;
+            else cs_acc[1] += sum;
           }
           fence_proxy_async();
           gbar();
@@ -587,6 +621,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
       tc_fence_before();
       if (lead_cta) mbar_arrive(&tempty[acc]);
       else mbar_arrive_remote(&tempty[acc], 0);   // the leader CTA's MMA warp owns the accumulator hand-shake
+    }
+    if constexpr (EPI == EPI_MUL || EPI == EPI_LINEAR) {
+      if (args.colsum != nullptr) cs_flush();
     }
     if (leader) bulk_wait_all();
   }
@@ -734,7 +771,7 @@ int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
   const int grid = (int)(tiles < max_units ? tiles : max_units);
   SNB_CHECK_ARG(a.b_stages * (int)a.b_slot + a.a_stages * GEMM_A_STAGE <= GEMM_OPERAND_BYTES, SNB_ERR_INVALID,
                 "gemm: rings %d/%d exceed the operand smem", a.a_stages, a.b_stages);
-  const double macs = (double)a.m_tiles * GEMM_BLOCK_M * (double)a.n_tiles * a.block_n * (double)a.kb_total * GEMM_BLOCK_K;
+  const double macs = (double)a.m_tiles * GEMM_BLOCK_M * a.cta_group * (double)a.n_tiles * a.block_n * (double)a.kb_total * GEMM_BLOCK_K;
   const bool timed = profile_gemm_begin(st, macs);
   int rc;
   const bool two = a.cta_group == 2;

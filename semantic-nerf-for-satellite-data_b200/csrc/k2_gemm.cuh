@@ -62,6 +62,7 @@ struct GemmArgs {
   int two_out;
   const float* bias;
   float w0;
+  float* colsum;  // EPI_MUL / EPI_LINEAR: if set, colsum[n] += sum over rows of the bf16 output (bias gradient)
   // EPI_HEADOUT
   float* out_packed;
   const float* sky;

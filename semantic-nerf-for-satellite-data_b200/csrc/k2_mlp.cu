@@ -12,7 +12,8 @@
 //     (P, 9+C) fp32 tensor in the reference's column order (rs_semantic.py:291-311).
 // Backward = dgrad GEMMs against transposed bf16 weight copies with the saved SIREN derivative
 // multiplied in the epilogue, and split-K wgrad GEMMs (reduction over samples, MN-major operands)
-// accumulated with TMA reduce-add; bias / per-ray-column gradients are dY^T x aux.
+// accumulated with TMA reduce-add; bias gradients are column sums taken in the dgrad epilogue that
+// produces dY, the per-ray columns of the fused head layer are dY^T x aux.
 #include <string.h>
 
 #include <string>
@@ -337,9 +338,9 @@ static void build_layout(snb_model* m) {
       ujob(fcw(i), F, m->gl[i], F, F, F, 0);
     }
   }
-  for (int i = 0; i < LAYERS; ++i) ujob(fcb(i), 1, m->gbl[i], 16, F, 1, 0);
+  for (int i = 0; i < LAYERS; ++i) ujob(fcb(i), 1, m->gbl[i], 1, F, 1, 0);
   ujob(P("feats_from_xyz.weight"), F, m->gf, F, F, F, 0);
-  ujob(P("feats_from_xyz.bias"), 1, m->gbf, 16, F, 1, 0);
+  ujob(P("feats_from_xyz.bias"), 1, m->gbf, 1, F, 1, 0);
   for (auto& b : blks) {
     const long long w = P(std::string(b.w) + ".weight"), bb = P(std::string(b.b) + ".bias");
     ujob(w, b.kin, m->gh1 + (long long)b.row * F, F, FL, F, 0);
@@ -348,9 +349,9 @@ static void build_layout(snb_model* m) {
   ujob(P("sun_v_net.0.weight") + F, F + 3, m->gh1aux + (long long)m->hh_sun * 16 + 1, 16, FL, 3, 0);
   ujob(P("beta_from_xyz.0.weight") + F, F + tau, m->gh1aux + (long long)m->hh_beta * 16 + 4, 16, FL, tau, 0);
   ujob(P("sun_v_net.2.weight"), FL, m->gs2, FL, FL, FL, 0);
-  ujob(P("sun_v_net.2.bias"), 1, m->gbs2, 16, FL, 1, 0);
+  ujob(P("sun_v_net.2.bias"), 1, m->gbs2, 1, FL, 1, 0);
   ujob(P("sun_v_net.4.weight"), FL, m->gs4, FL, FL, FL, 0);
-  ujob(P("sun_v_net.4.bias"), 1, m->gbs4, 16, FL, 1, 0);
+  ujob(P("sun_v_net.4.bias"), 1, m->gbs4, 1, FL, 1, 0);
   // head output layer: scratch is transposed [K features, 16]
   ujob(P("sigma_from_xyz.0.weight"), F, m->ghot + 3, 16, 1, F, 1);
   ujob(P("sun_v_net.6.weight"), FL, m->ghot + (long long)F * 16 + 4, 16, 1, FL, 1);
@@ -451,7 +452,7 @@ struct Plan {
 // D[M,N] = sum_seg A_seg[M,K] * B[N,Kp]^T  (K-major operands)
 static GemmArgs& add_kmajor(Plan& p, int epi, long long M, int N, const Seg* segs, int nseg, const void* B, long long ldb,
                             int b_cols, void* out0, void* out1, long long ldo, const void* mul, long long ldmul,
-                            const float* bias, float w0) {
+                            const float* bias, float w0, float* colsum = nullptr) {
   GemmArgs& a = p.add(epi);
   a.M = (int)M;
   a.N = N;
@@ -475,6 +476,7 @@ static GemmArgs& add_kmajor(Plan& p, int epi, long long M, int N, const Seg* seg
   a.two_out = out1 != nullptr;
   a.bias = bias;
   a.w0 = w0;
+  a.colsum = colsum;
   a.splits = 1;
   gemm_finalize(a);
   return a;
@@ -694,16 +696,16 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
   Seg sdpre[1] = {{dpre, 16, 16, 1}};
   if (!depth) {
     // sun head: s3 <- head output, then back through sun.4, sun.2 into the sun block of hh
-    add_kmajor(p, EPI_MUL, P, FL, sdpre, 1, pk + m->tho, 16, 16, ws + w.dys3, nullptr, FL, ws + w.cs3, FL, nullptr, 1.0f);
+    add_kmajor(p, EPI_MUL, P, FL, sdpre, 1, pk + m->tho, 16, 16, ws + w.dys3, nullptr, FL, ws + w.cs3, FL, nullptr, 1.0f,
+               gs + m->gbs4);
     if (all)  // rgb / beta / sem blocks of hh (columns [0, hhw-256))
       add_kmajor(p, EPI_MUL, P, hhw - FL, sdpre, 1, pk + m->tho + (long long)FL * 16, 16, 16, ws + w.dyhh, nullptr, hhw,
                  ws + w.chh, hhw, nullptr, 1.0f);
     add_wgrad(p, FL, FL, ws + w.dys3, FL, ws + w.s2, FL, P, gs + m->gs4, FL, sms);
-    add_wgrad(p, FL, 16, ws + w.dys3, FL, aux, 16, P, gs + m->gbs4, 16, sms);
     Seg s3[1] = {{ws + w.dys3, FL, FL, FL / 64}};
-    add_kmajor(p, EPI_MUL, P, FL, s3, 1, pk + m->ts4, FL, FL, ws + w.dys2, nullptr, FL, ws + w.cs2, FL, nullptr, 1.0f);
+    add_kmajor(p, EPI_MUL, P, FL, s3, 1, pk + m->ts4, FL, FL, ws + w.dys2, nullptr, FL, ws + w.cs2, FL, nullptr, 1.0f,
+               gs + m->gbs2);
     add_wgrad(p, FL, FL, ws + w.dys2, FL, ws + w.hh + (size_t)m->hh_sun * 2, hhw, P, gs + m->gs2, FL, sms);
-    add_wgrad(p, FL, 16, ws + w.dys2, FL, aux, 16, P, gs + m->gbs2, 16, sms);
     Seg s2[1] = {{ws + w.dys2, FL, FL, FL / 64}};
     add_kmajor(p, EPI_MUL, P, FL, s2, 1, pk + m->ts2, FL, FL, ws + w.dyhh + (size_t)m->hh_sun * 2, nullptr, hhw,
                ws + w.chh + (size_t)m->hh_sun * 2, hhw, nullptr, 1.0f);
@@ -720,17 +722,19 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
       a.ldo = 16;
     }
     Seg sh[1] = {{dyhh, hhw, n, n / 64}};
-    add_kmajor(p, EPI_LINEAR, P, F, sh, 1, pk + m->th1 + r0, hhw, n, ws + w.df, nullptr, F, nullptr, 0, nullptr, 1.0f);
+    add_kmajor(p, EPI_LINEAR, P, F, sh, 1, pk + m->th1 + r0, hhw, n, ws + w.df, nullptr, F, nullptr, 0, nullptr, 1.0f,
+               gs + m->gbf);
     add_wgrad(p, F, F, ws + w.df, F, H(7), F, P, gs + m->gf, F, sms);
-    add_wgrad(p, F, 16, ws + w.df, F, aux, 16, P, gs + m->gbf, 16, sms);
   }
   // dY7 = ([dF | dPre16] * [Wf ; w_sigma]) * c7 ------------------------------------------------------------
   int cur = 0;
   if (!depth) {
     Seg s[2] = {{ws + w.df, F, F, F / 64}, {dpre, 16, 16, 1}};
-    add_kmajor(p, EPI_MUL, P, F, s, 2, pk + m->tf, F + 64, F + 64, ws + w.dy[cur], nullptr, F, Cs(7), F, nullptr, 1.0f);
+    add_kmajor(p, EPI_MUL, P, F, s, 2, pk + m->tf, F + 64, F + 64, ws + w.dy[cur], nullptr, F, Cs(7), F, nullptr, 1.0f,
+               gs + m->gbl[7]);
   } else {
-    add_kmajor(p, EPI_MUL, P, F, sdpre, 1, pk + m->tf + F, F + 64, 64, ws + w.dy[cur], nullptr, F, Cs(7), F, nullptr, 1.0f);
+    add_kmajor(p, EPI_MUL, P, F, sdpre, 1, pk + m->tf + F, F + 64, 64, ws + w.dy[cur], nullptr, F, Cs(7), F, nullptr, 1.0f,
+               gs + m->gbl[7]);
   }
   for (int i = LAYERS - 1; i >= 0; --i) {
     const void* dy = ws + w.dy[cur];
@@ -741,10 +745,11 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
       add_wgrad(p, F, F, dy, F, H(i - 1), F, P, gs + m->gl[i], F, sms);
       if (i == 4) add_wgrad(p, F, 64, dy, F, enc, m->enc_ld, P, gs + m->gl4e, 64, sms);
     }
-    add_wgrad(p, F, 16, dy, F, aux, 16, P, gs + m->gbl[i], 16, sms);
     if (i > 0) {
+      // dY_{i-1} = (dY_i W_i) * c_{i-1}; its column sums are the bias gradient of layer i-1
       Seg s[1] = {{dy, F, F, F / 64}};
-      add_kmajor(p, EPI_MUL, P, F, s, 1, pk + m->tl[i], F, F, ws + w.dy[cur ^ 1], nullptr, F, Cs(i - 1), F, nullptr, 1.0f);
+      add_kmajor(p, EPI_MUL, P, F, s, 1, pk + m->tl[i], F, F, ws + w.dy[cur ^ 1], nullptr, F, Cs(i - 1), F, nullptr, 1.0f,
+                 gs + m->gbl[i - 1]);
       cur ^= 1;
     }
   }
