@@ -64,8 +64,9 @@ int snb_device_sms(void);
  *   extras (N,4) f32  [sun_d(3) ts]                 framework/components/rays.py:41-64
  *   u      (N,S) f32  jitter in [0,1) or NULL -> in-kernel Philox4x32-10 keyed on (seed, ray_offset+ray, sample)
  *   z_vals (N,S) f32  written (z_given=0) or read (z_given=1: the reference's given_z_vals)
- *   enc    bf16 (N*S, enc_ld): [hi(k0) | hi(k0) | lo(k0) | 0] where hi+lo is the bf16 split of the
- *          fp32 encoding (k0 = 3 raw xyz / 60 posenc), enc_ld = 64 / 192.  NULL to skip.
+ *   enc    bf16 (N*S, enc_ld): hi+lo is the two-term bf16 split of the fp32 encoding (k0 = 3 raw xyz /
+ *          60 posenc).  satnerf: enc_ld = 64, [hi(3) | hi(3) | lo(3) | 0];  semantic: enc_ld = 128,
+ *          [hi(60) | lo(60) | 0(8)].  NULL to skip.
  *   enc_sc same for the solar-correction points o + sun_d*z. NULL to skip.
  *   aux    bf16 (N*S,16): [1, sun_d(3), t(tau), 0..] - per-ray terms of the heads as a K-segment.
  *   sky    f32  (N,3): sigmoid(W2 relu(W1 sun_d + b1) + b2).  NULL to skip.

@@ -8,7 +8,7 @@
 
 namespace snb {
 
-bool profile_gemm_begin(cudaStream_t st, double macs);
+bool profile_gemm_begin(cudaStream_t st, double macs, int epi, int M, int N, int K, int cg, int splits);
 void profile_gemm_end(cudaStream_t st);
 
 // ================================================================================================
@@ -146,7 +146,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0 && lead_cta) {
+    // The whole warp runs the loop (warp-uniform control flow and operands, so the descriptors live in
+    // uniform registers); one elected lane issues the tcgen05 instructions.
+    if (lead_cta) {
       // cute::UMMA::InstrDescriptor: c_format f32 (1<<4), a/b format bf16 (1<<7, 1<<10),
       // a_major bit 15, b_major bit 16, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)args.a_mn << 15) |
@@ -155,7 +157,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
       // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused (1).  MN-major SW128: 8-k groups
       // 1024 B apart (SBO), 64-element MN atoms 8192 B apart (LBO).
       const uint32_t a_lbo = args.a_mn ? 8192u : 16u, b_lbo = args.b_mn ? 8192u : 16u;
-      const uint32_t a_kstep = args.a_mn ? 2048u : 32u, b_kstep = args.b_mn ? 2048u : 32u;
+      const uint32_t a_kstep = (args.a_mn ? 2048u : 32u) >> 4, b_kstep = (args.b_mn ? 2048u : 32u) >> 4;
+      // descriptor = constant high part | (smem address >> 4): only the low word changes per k-step
+      const uint64_t adesc0 = umma_desc(0, a_lbo, 1024u), bdesc0 = umma_desc(0, b_lbo, 1024u);
+      const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4;
+      const uint32_t b_slot16 = b_slot >> 4;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
         const TileCoord t = decode_tile(args, tile);
@@ -167,23 +173,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
           mbar_wait(&fullA[sa], pa);
           mbar_wait(&fullB[sb], pb);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + sa * GEMM_A_STAGE);
-          const uint32_t b_addr = smem_u32(sB + sb * b_slot);
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + (uint64_t)(a_base + sa * (GEMM_A_STAGE >> 4));
+            const uint64_t bd = bdesc0 + (uint64_t)(b_base + sb * b_slot16);
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-            const uint64_t adesc = umma_desc(a_addr + k * a_kstep, a_lbo, 1024u);
-            const uint64_t bdesc = umma_desc(b_addr + k * b_kstep, b_lbo, 1024u);
-            if constexpr (CG == 2) tc_mma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
-            else tc_mma_bf16(d_tmem, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+              if constexpr (CG == 2) tc_mma_bf16_2sm(d_tmem, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_bf16(d_tmem, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem slots (in both CTAs of a pair) once these MMAs have read them
+            if constexpr (CG == 2) { tc_commit_2sm(&emptyA[sa]); tc_commit_2sm(&emptyB[sb]); }
+            else { tc_commit(&emptyA[sa]); tc_commit(&emptyB[sb]); }
           }
-          // frees the smem slots (in both CTAs of a pair) once these MMAs have read them
-          if constexpr (CG == 2) { tc_commit_2sm(&emptyA[sa]); tc_commit_2sm(&emptyB[sb]); }
-          else { tc_commit(&emptyA[sa]); tc_commit(&emptyB[sb]); }
+          __syncwarp();
           if (++sa == a_stages) { sa = 0; pa ^= 1; }
           if (++sb == b_stages) { sb = 0; pb ^= 1; }
         }
-        if constexpr (CG == 2) tc_commit_2sm(&tfull[acc]);   // accumulator complete -> both CTAs' epilogues
-        else tc_commit(&tfull[acc]);
+        if (elect_one()) {
+          if constexpr (CG == 2) tc_commit_2sm(&tfull[acc]);   // accumulator complete -> both CTAs' epilogues
+          else tc_commit(&tfull[acc]);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -292,17 +302,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
                   x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
                 }
                 if constexpr (EPI == EPI_SIN) {
-                  float sn[8], cs[8];
+                  if (two) {   // training: h and the derivative w0*cos(.) (2 MUFU ops per element)
+                    float sn[8], cs[8];
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
-                    const float y = args.w0 * x[j];
-                    sn[j] = __sinf(y);
-                    cs[j] = args.w0 * __cosf(y);
-                  }
+                    for (int j = 0; j < 8; ++j) {
+                      const float y = args.w0 * x[j];
+                      sn[j] = __sinf(y);
+                      cs[j] = args.w0 * __cosf(y);
+                    }
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    outw[half][g * 4 + j] = pack_bf16x2(sn[2 * j], sn[2 * j + 1]);
-                    outc[half][g * 4 + j] = pack_bf16x2(cs[2 * j], cs[2 * j + 1]);
+                    for (int j = 0; j < 4; ++j) {
+                      outw[half][g * 4 + j] = pack_bf16x2(sn[2 * j], sn[2 * j + 1]);
+                      outc[half][g * 4 + j] = pack_bf16x2(cs[2 * j], cs[2 * j + 1]);
+                    }
+                  } else {     // inference: h only
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                      outw[half][g * 4 + j] = pack_bf16x2(__sinf(args.w0 * x[2 * j]), __sinf(args.w0 * x[2 * j + 1]));
                   }
                 } else {
 #pragma unroll
@@ -601,7 +617,7 @@ int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
   SNB_CHECK_ARG(a.b_stages * (int)a.b_slot + a.a_stages * GEMM_A_STAGE <= GEMM_OPERAND_BYTES, SNB_ERR_INVALID,
                 "gemm: rings %d/%d exceed the operand smem", a.a_stages, a.b_stages);
   const double macs = (double)a.m_tiles * GEMM_BLOCK_M * a.cta_group * (double)a.n_tiles * a.block_n * (double)a.kb_total * GEMM_BLOCK_K;
-  const bool timed = profile_gemm_begin(st, macs);
+  const bool timed = profile_gemm_begin(st, macs, epi, a.M, a.N, a.kb_total * GEMM_BLOCK_K, a.cta_group, a.splits);
   int rc;
   const bool two = a.cta_group == 2;
   switch (epi) {

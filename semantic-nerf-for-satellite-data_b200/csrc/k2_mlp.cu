@@ -46,7 +46,7 @@ struct PackJob {
 
 struct snb_model {
   int kind, n_classes, sem_sigmoid;
-  int k0, enc_ld, hhw, n_out, tau;
+  int k0, enc_ld, w0_ld, hhw, n_out, tau;   // enc_ld: K1 row width; w0_ld: packed K of the first layer
   int hh_rgb, hh_beta, hh_sem, hh_sun;
   int kho;  // K of the head-output layer: 512 + 256 + hhw
   std::vector<snb::TensorInfo> tensors;
@@ -223,7 +223,7 @@ static void build_layout(snb_model* m) {
   const int kh1 = F + 64;       // packed K of the fused head first layers: [f(512) | aux(64)]
   const int ktf = F + 64;       // packed K of the feats dgrad: [dF(512) | dPre16(64)]
   m->kho = F + FL + hhw;        // [h7 | s3 | hh]
-  for (int i = 0; i < LAYERS; ++i) m->wl[i] = take(cur, (long long)F * (i == 0 ? m->enc_ld : (i == 4 ? kl4 : F)));
+  for (int i = 0; i < LAYERS; ++i) m->wl[i] = take(cur, (long long)F * (i == 0 ? m->w0_ld : (i == 4 ? kl4 : F)));
   m->wf = take(cur, (long long)F * F);
   m->wh1 = take(cur, (long long)hhw * kh1);
   m->ws2 = take(cur, (long long)FL * FL);
@@ -250,10 +250,17 @@ static void build_layout(snb_model* m) {
   auto job = [&](long long dst, int ldd, long long src, int lds, int rows, int cols, int tr, int mode) {
     J.push_back({dst, src, ldd, lds, rows, cols, tr, mode});
   };
-  // layer 0: [hi | lo | hi] against the input row [hi | hi | lo]
-  job(m->wl[0], m->enc_ld, fcw(0), k0, F, k0, 0, 0);
-  job(m->wl[0] + k0, m->enc_ld, fcw(0), k0, F, k0, 0, 1);
-  job(m->wl[0] + 2 * k0, m->enc_ld, fcw(0), k0, F, k0, 0, 0);
+  if (sem) {
+    // layer 0, semantic: K-segments [enc cols 0..127 = hi | lo | 0] x [W_hi | W_hi | 0] and [enc cols 0..63 = hi | lo(0:4)] x [W_lo | 0]
+    job(m->wl[0], m->w0_ld, fcw(0), k0, F, k0, 0, 0);
+    job(m->wl[0] + k0, m->w0_ld, fcw(0), k0, F, k0, 0, 0);
+    job(m->wl[0] + 128, m->w0_ld, fcw(0), k0, F, k0, 0, 1);
+  } else {
+    // layer 0, satnerf: [hi | lo | hi] against the input row [hi | hi | lo]
+    job(m->wl[0], m->w0_ld, fcw(0), k0, F, k0, 0, 0);
+    job(m->wl[0] + k0, m->w0_ld, fcw(0), k0, F, k0, 0, 1);
+    job(m->wl[0] + 2 * k0, m->w0_ld, fcw(0), k0, F, k0, 0, 0);
+  }
   for (int i = 1; i < LAYERS; ++i) {
     if (i == 4) {
       job(m->wl[4], kl4, fcw(4), F + k0, F, k0, 0, 0);            // enc columns (first k0 of the 64-wide segment)
@@ -544,7 +551,8 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   m->sem_sigmoid = semantic_sigmoid;
   m->tau = 4;  // t_embedding_tau (configs/pipelines/*.toml)
   m->k0 = model_kind == SNB_MODEL_SEMANTIC ? 60 : 3;
-  m->enc_ld = model_kind == SNB_MODEL_SEMANTIC ? 192 : 64;
+  m->enc_ld = model_kind == SNB_MODEL_SEMANTIC ? 128 : 64;
+  m->w0_ld = model_kind == SNB_MODEL_SEMANTIC ? 192 : 64;
   m->n_out = 9 + n_classes;
   // hidden block order of the fused head first layers: [rgb | beta | (sem) | sun]
   m->hh_rgb = 0;
@@ -610,8 +618,10 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
   Plan p;
   // trunk ----------------------------------------------------------------------------------------
   {
-    Seg s0[1] = {{enc, m->enc_ld, m->enc_ld, m->enc_ld / 64}};
-    add_kmajor(p, EPI_SIN, P, F, s0, 1, pk + m->wl[0], m->enc_ld, m->enc_ld, H(0), Cs(0), F, nullptr, 0, pb + m->bl[0], 30.0f);
+    // semantic: the 128-column row is read twice ([hi|lo|0] then its first 64 columns again, against W_lo)
+    Seg s0[2] = {{enc, m->enc_ld, m->enc_ld, m->enc_ld / 64}, {enc, m->enc_ld, 64, 1}};
+    add_kmajor(p, EPI_SIN, P, F, s0, m->kind == SNB_MODEL_SEMANTIC ? 2 : 1, pk + m->wl[0], m->w0_ld, m->w0_ld, H(0), Cs(0), F,
+               nullptr, 0, pb + m->bl[0], 30.0f);
   }
   for (int i = 1; i < LAYERS; ++i) {
     if (i == 4) {

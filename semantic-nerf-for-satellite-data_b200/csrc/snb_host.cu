@@ -1,5 +1,6 @@
 // Host-side plumbing shared by every entry point: error strings, device query.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -54,10 +55,17 @@ static size_t g_ev_used = 0;
 
 void count_launch() { ++g_launches; }
 
-bool profile_gemm_begin(cudaStream_t st, double macs) {
+struct GemmRecord {
+  int epi, M, N, K, cg, splits;
+  double macs;
+};
+static std::vector<GemmRecord> g_records;
+
+bool profile_gemm_begin(cudaStream_t st, double macs, int epi, int M, int N, int K, int cg, int splits) {
   ++g_gemm_launches;
   g_gemm_macs += macs;
   if (!g_prof_time) return false;
+  g_records.push_back({epi, M, N, K, cg, splits, macs});
   if (g_ev_used + 2 > g_ev_pool.size()) {
     for (int i = 0; i < 256; ++i) {
       cudaEvent_t e;
@@ -80,17 +88,28 @@ extern "C" void snb_profile_begin(int time_gemms) {
   snb::g_launches = snb::g_gemm_launches = 0;
   snb::g_gemm_macs = 0.0;
   snb::g_ev_used = 0;
+  snb::g_records.clear();
 }
 
 extern "C" int snb_profile_end(double* gemm_ms, int64_t* gemm_launches, int64_t* total_launches, double* gemm_macs) {
   using namespace snb;
   SNB_CUDA(cudaDeviceSynchronize());
   double ms = 0.0;
+  // SNB_PROF_DUMP=<file>: per-launch list (epilogue, shape, SM-pair mode, split count, device time) for tools/
+  FILE* dump = nullptr;
+  if (const char* path = getenv("SNB_PROF_DUMP")) dump = fopen(path, "a");
+  if (dump) fprintf(dump, "# idx epi M N K cta_group splits us tflops_executed\n");
   for (size_t i = 0; i + 1 < g_ev_used; i += 2) {
     float t = 0.f;
     SNB_CUDA(cudaEventElapsedTime(&t, g_ev_pool[i], g_ev_pool[i + 1]));
     ms += t;
+    if (dump && i / 2 < g_records.size()) {
+      const GemmRecord& r = g_records[i / 2];
+      fprintf(dump, "%zu %d %d %d %d %d %d %.2f %.1f\n", i / 2, r.epi, r.M, r.N, r.K, r.cg, r.splits, t * 1e3,
+              2.0 * r.macs / (t * 1e-3) / 1e12);
+    }
   }
+  if (dump) fclose(dump);
   if (gemm_ms) *gemm_ms = ms;
   if (gemm_launches) *gemm_launches = g_gemm_launches;
   if (total_launches) *total_launches = g_launches;

@@ -35,7 +35,7 @@ class SnbMLP(torch.nn.Module):
         self.semantic_n_classes = n_classes          # read by the reference's inference(), rs_semantic.py:95
         self.number_of_outputs = 9 + n_classes       # satnerf.py:120
         self.t_embedding_dims = tau
-        self.enc_ld = 192 if kind == MODEL_SEMANTIC else 64
+        self.enc_ld = 128 if kind == MODEL_SEMANTIC else 64
         n = lib.snb_model_param_count(h)
         self.table: List[Tuple[str, int, Tuple[int, ...]]] = []
         for i in range(lib.snb_model_num_tensors(h)):

@@ -118,8 +118,13 @@ def test_k1_sampling_bit_exact_and_encoding(kind, S):
         xyz = O.sample_points(rays[:, :3], dirs, z_ref).reshape(-1, 3)
         ref = O.posenc(xyz, 10) if kind == "semantic" else xyz
         e = e.float().cpu()
-        assert (e[:, :k0] + e[:, 2 * k0:3 * k0] - ref).abs().max() <= 2 ** -16   # two-term bf16 split: 16 mantissa bits
-        assert torch.equal(e[:, k0:2 * k0], e[:, :k0]) and (e[:, 3 * k0:] == 0).all()
+        if kind == "semantic":    # row = [hi(60) | lo(60) | 0(8)]
+            hi, lo, pad = e[:, :k0], e[:, k0:2 * k0], e[:, 2 * k0:]
+        else:                     # row = [hi(3) | hi(3) | lo(3) | 0]
+            hi, lo, pad = e[:, :k0], e[:, 2 * k0:3 * k0], e[:, 3 * k0:]
+            assert torch.equal(e[:, k0:2 * k0], hi)
+        assert (hi + lo - ref).abs().max() <= 2 ** -16   # two-term bf16 split: 16 mantissa bits
+        assert (pad == 0).all()
     a = aux.float().cpu().view(n, S, 16)
     ref_aux = torch.cat([torch.ones(n, 1), extras[:, :3], emb[extras[:, 3].long()], torch.zeros(n, 8)], 1)
     assert torch.equal(a[:, 0], ref_aux.bfloat16().float()) and torch.equal(a[:, -1], a[:, 0])

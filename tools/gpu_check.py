@@ -132,9 +132,9 @@ def group_k1():
                 ref = O.posenc(xyz, 10) if kind == "semantic" else xyz
                 k0 = spec.k0
                 e = e.float().cpu()
-                stats(nm + " hi+lo", e[:, :k0] + e[:, 2 * k0:3 * k0], ref, 3e-5)
-                stats(nm + " hi copy", e[:, k0:2 * k0], e[:, :k0], 0.0)
-                print("   pad zero:", bool((e[:, 3 * k0:] == 0).all()))
+                lo0 = k0 if kind == "semantic" else 2 * k0
+                stats(nm + " hi+lo", e[:, :k0] + e[:, lo0:lo0 + k0], ref, 3e-5)
+                print("   pad zero:", bool((e[:, lo0 + k0:] == 0).all()))
             a = aux.float().cpu().view(n, S, 16)
             t = emb[extras[:, 3].long()]
             ref_aux = torch.cat([torch.ones(n, 1), extras[:, :3], t, torch.zeros(n, 8)], 1)
