@@ -157,6 +157,11 @@ int snb_composite_backward(const float* out, const float* z_vals, int n_rays, in
 int snb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
 
+/* tuning / test hook: run the MLP as ONE chained persistent kernel per pass (1, the default; inter-layer
+ * activations are read back from L2) or as one GEMM launch per layer (0).  Both give the same results; the
+ * parity tests compare them at sizes where every SM pair carries several row blocks.  Returns the old value. */
+int snb_set_chained_mlp(int on);
+
 /* ------------------------------------------------------------------------------------------------
  * measurement hooks (bench.py): count kernel launches made by this library and time every GEMM
  * launch with CUDA events on the launching stream.  snb_profile_end synchronises the device and

@@ -2,12 +2,12 @@
 // or the backward dgrad chain) instead of one launch per layer.
 //
 // Every SM pair (cta_group::2) owns 256-row blocks of the sample matrix and carries CHAIN_SLOTS of them,
-// interleaved, through all layers of the chain: tile order (slot0,l,n0) (slot0,l,n1) (slot1,l,n0) ... then
-// layer l+1.  A layer's input rows were written by the same CTA one layer-step earlier, so they are read
-// back from L2 instead of HBM (the write-once streams - saved derivatives - carry evict_first hints),
-// there is no per-layer launch / pipeline fill / drain, and the epilogue of one slot overlaps the MMAs of
-// the other.  A per-slot, per-layer completion counter in shared memory (bumped by the epilogue leaders
-// once their TMA stores have completed, polled by the A-producer) orders producer and consumer.
+// interleaved, through all layers of the chain: tile order (l, slot0, n0) (l, slot0, n1) (l, slot1, n0) ...
+// then layer l+1.  A layer's input rows were written by the SAME CTA one layer-step earlier, so they are
+// read back from L2 instead of HBM; inference keeps the inter-layer activations in a small per-pair scratch
+// that never leaves L2 at all.  There is no per-layer launch / pipeline fill / drain, and the epilogue of
+// one slot overlaps the MMAs of the other.  A per-slot mbarrier (arrived by the epilogue group leaders once
+// the TMA stores of a layer have completed, waited by the A-producer) orders producer and consumer.
 #pragma once
 #include "k2_gemm.cuh"
 
@@ -15,27 +15,32 @@ namespace snb {
 
 constexpr int CHAIN_SLOTS = 2;
 constexpr int CHAIN_MAX_LAYERS = 16;
-constexpr int CHAIN_MAX_COLSUM = 12;   // layers whose bias gradient (column sums) is accumulated in smem
-constexpr int CHAIN_A_STAGES = 5;      // 16 KB slots
-constexpr int CHAIN_B_STAGES = 3;      // 16 KB slots (weights: L2-resident, evict_last)
-constexpr int CHAIN_SMEM_BYTES = (CHAIN_A_STAGES + CHAIN_B_STAGES) * 16384 + GEMM_NUM_STAGING * GEMM_STAGING +
-                                 CHAIN_MAX_COLSUM * 512 * 4 + 1024 + 1024;
+constexpr int CHAIN_MAX_COLSUM = 11;   // layers whose bias gradient (column sums) is accumulated in smem
+constexpr int CHAIN_COLSUM_W = 512;    // widest layer with a column sum
+constexpr int CHAIN_A_STAGES = 5;      // 16 KB slots (128 rows x 64 k)
+constexpr int CHAIN_B_STAGES = 3;      // 16 KB slots (this CTA's 128 of the 256 weight rows x 64 k; weights are L2-resident)
+constexpr int CHAIN_EPI_WARPS = 16;    // two groups of 8 warps; warps w and w+4 of a group split a 64-column chunk
+constexpr int CHAIN_THREADS = 96 + CHAIN_EPI_WARPS * 32;
+constexpr int CHAIN_RING_BYTES = (CHAIN_A_STAGES + CHAIN_B_STAGES) * 16384;
+constexpr int CHAIN_SMEM_BYTES = CHAIN_RING_BYTES + GEMM_NUM_STAGING * GEMM_STAGING +
+                                 CHAIN_MAX_COLSUM * CHAIN_COLSUM_W * 4 + 1024 /*barriers*/ + 1024 /*alignment*/;
 
 struct alignas(64) ChainLayer {
-  CUtensorMap tmA[2];   // A K-segments, box {64, 128}
-  CUtensorMap tmB;      // weights [N, K], box {64, 128} (each CTA of the pair loads half of the 256-wide N tile)
+  CUtensorMap tmA[3];   // A K-segments, box {64 k, 128 rows}
+  CUtensorMap tmB;      // weights [N, K], box {64 k, block_n / 2 rows}
   CUtensorMap tmO0, tmO1, tmMul;
-  int seg_kb[2];
+  int seg_kb[3];
+  int a_scratch[3];     // segment lives in the per-pair scratch (row = (pair*SLOTS + slot)*256) instead of at the block's rows
   int nseg;
   int kb_total;
   int n_tiles;          // N / 256
   int epi;              // EPI_SIN / EPI_LINEAR / EPI_MUL
-  int two_out;
-  int cs_slot;          // >= 0: accumulate column sums of the bf16 output into colsum (bias gradient)
-  int dep[2];           // chain layers whose output rows (same block) feed this layer's A; -1 = none
+  int two_out;          // EPI_SIN: also store the derivative w0*cos(.)
+  int o_scratch;        // outputs go to the per-pair scratch
+  int cs_slot;          // >= 0: accumulate column sums of the bf16 output (bias gradient) in smem slot cs_slot
   float w0;
   const float* bias;
-  float* colsum;
+  float* colsum;        // global destination of the column sums (N floats), flushed once per CTA at the end
 };
 
 struct ChainArgs {
@@ -45,6 +50,8 @@ struct ChainArgs {
   int n_blocks;         // ceil(M / 256)
 };
 
+// rows of per-pair scratch a chain launch may address: (SMs/2) * CHAIN_SLOTS * 256
+int chain_scratch_rows();
 int chain_launch(const ChainArgs& a, cudaStream_t st);
 
 }  // namespace snb

@@ -19,6 +19,9 @@
 #include <string>
 #include <vector>
 
+#include <stdlib.h>
+
+#include "k2_chain.cuh"
 #include "k2_gemm.cuh"
 
 namespace snb {
@@ -390,10 +393,20 @@ static int run_jobs(const std::vector<PackJob>& jobs, bool unpack, const float* 
 struct Workspace {
   // all offsets in bytes from the workspace base; 0-sized members are absent
   size_t h[8], c[8], f, hh, chh, s2, cs2, s3, cs3;  // forward (c*: saved SIREN derivatives, train only)
-  size_t dpre, dy[2], df, dyhh, dys3, dys2;         // backward
+  size_t dpre, dy[8], df, dyhh, dys3, dys2;         // backward (dy[i] = gradient w.r.t. the pre-activation of trunk layer i)
+  size_t scr_h[2], scr_f, scr_s2;                   // inference: per-SM-pair scratch of the chained kernel (L2-resident)
   size_t gscratch;                                  // fp32 packed gradients
   size_t total;
 };
+
+static int g_chain = -1;   // -1: from the environment (SNB_CHAIN, default on)
+static bool use_chain() {
+  if (g_chain < 0) {
+    const char* e = getenv("SNB_CHAIN");
+    g_chain = e ? (atoi(e) != 0) : 1;
+  }
+  return g_chain != 0;
+}
 
 static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
   Workspace w;
@@ -411,6 +424,13 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
   } else {
     size_t a = take_b(rowF), b = take_b(rowF);
     for (int i = 0; i < 8; ++i) w.h[i] = (i & 1) ? b : a;  // ping-pong (layer 4 reads h3, writes h4: distinct)
+    // chained kernel: layers 0..6, f and s2 live in a per-pair scratch instead (h7 / hh / s3 stay per-point:
+    // the head-output kernel reads them)
+    const size_t R = (size_t)chain_scratch_rows();
+    w.scr_h[0] = take_b(R * F * 2);
+    w.scr_h[1] = take_b(R * F * 2);
+    w.scr_f = take_b(R * F * 2);
+    w.scr_s2 = take_b(R * FL * 2);
   }
   w.f = take_b(rowF);
   w.hh = take_b(rowHH);
@@ -421,8 +441,7 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
     w.cs2 = take_b(rowFL);
     w.cs3 = take_b(rowFL);
     w.dpre = take_b((size_t)P * 16 * 2);
-    w.dy[0] = take_b(rowF);
-    w.dy[1] = take_b(rowF);
+    for (int i = 0; i < 8; ++i) w.dy[i] = take_b(rowF);
     w.df = take_b(rowF);
     w.dyhh = take_b(rowHH);
     w.dys3 = take_b(rowFL);
@@ -527,6 +546,66 @@ static int run_plan(const Plan& p, cudaStream_t st) {
   return 0;
 }
 
+// ---- chained-kernel plan ------------------------------------------------------------------------------
+struct CSeg {
+  const void* ptr;   // bf16, row-major, first column of the segment
+  long long ld;
+  int cols;          // readable columns (TMA zero-fills beyond)
+  int kb;
+  long long rows;    // rows of the tensor (P, or the scratch rows)
+  int scratch;
+};
+
+struct ChainPlan {
+  ChainArgs a;
+  int rc = 0;
+  int n_cs = 0;
+  ChainPlan(long long P) {
+    memset(&a, 0, sizeof(a));
+    a.M = (int)P;
+    a.n_blocks = (int)((P + 255) / 256);
+  }
+  void chk(int r) {
+    if (r && !rc) rc = r;
+  }
+  // D[rows, N] = epilogue(sum_seg A_seg * B[N, Kp]^T); N % 256 == 0
+  void add(int epi, int N, const CSeg* segs, int nseg, const void* B, long long ldb, int b_cols, void* out0, void* out1,
+           long long ldo, long long o_rows, int o_scratch, const void* mul, long long ldmul, const float* bias, float w0,
+           float* colsum) {
+    if (a.n_layers >= CHAIN_MAX_LAYERS || N % 256 != 0 || nseg > 3) {
+      set_error("chain plan: layer %d unsupported (N %d, %d segments)", a.n_layers, N, nseg);
+      chk(SNB_ERR_UNSUPPORTED);
+      return;
+    }
+    ChainLayer& ly = a.layers[a.n_layers++];
+    ly.epi = epi;
+    ly.n_tiles = N / 256;
+    ly.nseg = nseg;
+    ly.kb_total = 0;
+    for (int s = 0; s < nseg; ++s) {
+      ly.seg_kb[s] = segs[s].kb;
+      ly.a_scratch[s] = segs[s].scratch;
+      ly.kb_total += segs[s].kb;
+      chk(make_tmap_2d(&ly.tmA[s], segs[s].ptr, 2, (uint64_t)segs[s].cols, (uint64_t)segs[s].rows, (uint64_t)segs[s].ld * 2, 64,
+                       GEMM_BLOCK_M));
+    }
+    chk(make_tmap_2d(&ly.tmB, B, 2, (uint64_t)b_cols, (uint64_t)N, (uint64_t)ldb * 2, 64, 128));
+    chk(make_tmap_2d(&ly.tmO0, out0, 2, (uint64_t)N, (uint64_t)o_rows, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
+    if (out1) chk(make_tmap_2d(&ly.tmO1, out1, 2, (uint64_t)N, (uint64_t)o_rows, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
+    if (epi == EPI_MUL) chk(make_tmap_2d(&ly.tmMul, mul, 2, (uint64_t)N, (uint64_t)a.M, (uint64_t)ldmul * 2, 64, GEMM_BLOCK_M));
+    ly.two_out = out1 != nullptr;
+    ly.o_scratch = o_scratch;
+    ly.bias = bias;
+    ly.w0 = w0;
+    ly.colsum = colsum;
+    ly.cs_slot = colsum ? n_cs++ : -1;
+  }
+  int run(cudaStream_t st) {
+    if (rc) return rc;
+    return chain_launch(a, st);
+  }
+};
+
 static bool mask_supported(int head_mask) {
   return head_mask == SNB_HEADS_ALL || head_mask == SNB_HEADS_SOLAR || head_mask == SNB_HEADS_DEPTH;
 }
@@ -566,6 +645,11 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
 }
 
 extern "C" void snb_model_destroy(snb_model* m) { delete m; }
+extern "C" int snb_set_chained_mlp(int on) {
+  const int prev = use_chain() ? 1 : 0;
+  g_chain = on ? 1 : 0;
+  return prev;
+}
 extern "C" int64_t snb_model_param_count(const snb_model* m) { return m ? m->n_params : -1; }
 extern "C" int snb_model_num_tensors(const snb_model* m) { return m ? (int)m->tensors.size() : -1; }
 extern "C" int snb_model_tensor_info(const snb_model* m, int i, const char** name, int64_t* offset, int* rows,
@@ -615,7 +699,53 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
   auto H = [&](int i) { return (void*)(ws + w.h[i]); };
   auto Cs = [&](int i) { return train ? (void*)(ws + w.c[i]) : (void*)nullptr; };
   const int hhw = m->hhw;
+  const bool need_f = head_mask != SNB_HEADS_DEPTH;
+  const bool all = head_mask == SNB_HEADS_ALL;
   Plan p;
+  if (use_chain()) {
+    // one persistent launch: trunk + feats + head first layers + sun layers; inter-layer activations stay in L2
+    ChainPlan cp(P);
+    const long long R = chain_scratch_rows();
+    const bool scr = !train;   // inference: layers 0..6, f, s2 in the per-pair scratch
+    auto hbuf = [&](int i) { return scr && i < 7 ? (void*)(ws + w.scr_h[i & 1]) : H(i); };
+    auto hrows = [&](int i) { return scr && i < 7 ? R : P; };
+    auto hscr = [&](int i) { return scr && i < 7 ? 1 : 0; };
+    {
+      CSeg s0[2] = {{enc, m->enc_ld, m->enc_ld, m->enc_ld / 64, P, 0}, {enc, m->enc_ld, 64, 1, P, 0}};
+      cp.add(EPI_SIN, F, s0, m->kind == SNB_MODEL_SEMANTIC ? 2 : 1, pk + m->wl[0], m->w0_ld, m->w0_ld, hbuf(0), Cs(0), F,
+             hrows(0), hscr(0), nullptr, 0, pb + m->bl[0], 30.0f, nullptr);
+    }
+    for (int i = 1; i < LAYERS; ++i) {
+      if (i == 4) {
+        CSeg s[2] = {{enc, m->enc_ld, 64, 1, P, 0}, {hbuf(3), F, F, F / 64, hrows(3), hscr(3)}};
+        cp.add(EPI_SIN, F, s, 2, pk + m->wl[4], 64 + F, 64 + F, hbuf(4), Cs(4), F, hrows(4), hscr(4), nullptr, 0, pb + m->bl[4],
+               1.0f, nullptr);
+      } else {
+        CSeg s[1] = {{hbuf(i - 1), F, F, F / 64, hrows(i - 1), hscr(i - 1)}};
+        cp.add(EPI_SIN, F, s, 1, pk + m->wl[i], F, F, hbuf(i), Cs(i), F, hrows(i), hscr(i), nullptr, 0, pb + m->bl[i], 1.0f,
+               nullptr);
+      }
+    }
+    if (need_f) {
+      void* fbuf = scr ? (void*)(ws + w.scr_f) : (void*)(ws + w.f);
+      void* s2buf = scr ? (void*)(ws + w.scr_s2) : (void*)(ws + w.s2);
+      const long long srows = scr ? R : P;
+      const int sflag = scr ? 1 : 0;
+      CSeg s[1] = {{H(7), F, F, F / 64, P, 0}};
+      cp.add(EPI_LINEAR, F, s, 1, pk + m->wf, F, F, fbuf, nullptr, F, srows, sflag, nullptr, 0, pb + m->bfe, 1.0f, nullptr);
+      const int r0 = all ? 0 : m->hh_sun, n = all ? hhw : FL;
+      CSeg s1[2] = {{fbuf, F, F, F / 64, srows, sflag}, {aux, 16, 16, 1, P, 0}};
+      cp.add(EPI_SIN, n, s1, 2, pk + m->wh1 + (long long)r0 * (F + 64), F + 64, F + 64, ws + w.hh + (size_t)r0 * 2,
+             train ? ws + w.chh + (size_t)r0 * 2 : nullptr, hhw, P, 0, nullptr, 0, nullptr, 1.0f, nullptr);
+      CSeg s2[1] = {{ws + w.hh + (size_t)m->hh_sun * 2, hhw, FL, FL / 64, P, 0}};
+      cp.add(EPI_SIN, FL, s2, 1, pk + m->ws2, FL, FL, s2buf, train ? ws + w.cs2 : nullptr, FL, srows, sflag, nullptr, 0,
+             pb + m->bs2, 1.0f, nullptr);
+      CSeg s3[1] = {{s2buf, FL, FL, FL / 64, srows, sflag}};
+      cp.add(EPI_SIN, FL, s3, 1, pk + m->ws4, FL, FL, ws + w.s3, train ? ws + w.cs3 : nullptr, FL, P, 0, nullptr, 0, pb + m->bs4,
+             1.0f, nullptr);
+    }
+    if (int r = cp.run((cudaStream_t)stream)) return r;
+  } else {
   // trunk ----------------------------------------------------------------------------------------
   {
     // semantic: the 128-column row is read twice ([hi|lo|0] then its first 64 columns again, against W_lo)
@@ -632,8 +762,6 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
       add_kmajor(p, EPI_SIN, P, F, s, 1, pk + m->wl[i], F, F, H(i), Cs(i), F, nullptr, 0, pb + m->bl[i], 1.0f);
     }
   }
-  const bool need_f = head_mask != SNB_HEADS_DEPTH;
-  const bool all = head_mask == SNB_HEADS_ALL;
   if (need_f) {
     Seg s[1] = {{H(7), F, F, F / 64}};
     add_kmajor(p, EPI_LINEAR, P, F, s, 1, pk + m->wf, F, F, ws + w.f, nullptr, F, nullptr, 0, pb + m->bfe, 1.0f);
@@ -649,6 +777,7 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
     add_kmajor(p, EPI_SIN, P, FL, s3, 1, pk + m->ws4, FL, FL, ws + w.s3, train ? ws + w.cs3 : nullptr, FL, nullptr, 0,
                pb + m->bs4, 1.0f);
   }
+  }   // per-layer launches
   {
     Seg s[3] = {{H(7), F, F, F / 64}, {ws + w.s3, FL, FL, FL / 64}, {ws + w.hh, hhw, hhw, hhw / 64}};
     const int nseg = head_mask == SNB_HEADS_DEPTH ? 1 : (all ? 3 : 2);
@@ -698,32 +827,78 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
                                                   (__nv_bfloat16*)dpre, gs + m->gbho);
     if (int r = launch_status("head_grad_kernel")) return r;
   }
+  auto DY = [&](int i) { return (void*)(ws + w.dy[i]); };
   Plan p;
-  // head output layer: weight gradients (transposed scratch [features, 16]) -----------------------------
+  const int r0 = all ? 0 : m->hh_sun, nh = all ? hhw : FL;
+  const char* dyhh_r0 = ws + w.dyhh + (size_t)r0 * 2;
+  Seg sdpre[1] = {{dpre, 16, 16, 1}};
+  // ---- dgrad: the gradient w.r.t. every pre-activation, from the heads back to trunk layer 0 ---------------
+  if (use_chain()) {
+    // one persistent launch; each dY is read back from L2 by the next step of the same SM pair
+    ChainPlan cp(P);
+    CSeg cdpre[1] = {{dpre, 16, 16, 1, P, 0}};
+    if (!depth) {
+      // sun head: s3 <- head output, then back through sun.4, sun.2 into the sun block of hh
+      cp.add(EPI_MUL, FL, cdpre, 1, pk + m->tho, 16, 16, ws + w.dys3, nullptr, FL, P, 0, ws + w.cs3, FL, nullptr, 1.0f, gs + m->gbs4);
+      if (all)  // rgb / beta / sem blocks of hh (columns [0, hhw-256))
+        cp.add(EPI_MUL, hhw - FL, cdpre, 1, pk + m->tho + (long long)FL * 16, 16, 16, ws + w.dyhh, nullptr, hhw, P, 0, ws + w.chh,
+               hhw, nullptr, 1.0f, nullptr);
+      CSeg c3[1] = {{ws + w.dys3, FL, FL, FL / 64, P, 0}};
+      cp.add(EPI_MUL, FL, c3, 1, pk + m->ts4, FL, FL, ws + w.dys2, nullptr, FL, P, 0, ws + w.cs2, FL, nullptr, 1.0f, gs + m->gbs2);
+      CSeg c2[1] = {{ws + w.dys2, FL, FL, FL / 64, P, 0}};
+      cp.add(EPI_MUL, FL, c2, 1, pk + m->ts2, FL, FL, ws + w.dyhh + (size_t)m->hh_sun * 2, nullptr, hhw, P, 0,
+             ws + w.chh + (size_t)m->hh_sun * 2, hhw, nullptr, 1.0f, nullptr);
+      CSeg ch[1] = {{dyhh_r0, hhw, nh, nh / 64, P, 0}};
+      cp.add(EPI_LINEAR, F, ch, 1, pk + m->th1 + r0, hhw, nh, ws + w.df, nullptr, F, P, 0, nullptr, 0, nullptr, 1.0f, gs + m->gbf);
+      CSeg c7[2] = {{ws + w.df, F, F, F / 64, P, 0}, {dpre, 16, 16, 1, P, 0}};
+      cp.add(EPI_MUL, F, c7, 2, pk + m->tf, F + 64, F + 64, DY(7), nullptr, F, P, 0, Cs(7), F, nullptr, 1.0f, gs + m->gbl[7]);
+    } else {
+      cp.add(EPI_MUL, F, cdpre, 1, pk + m->tf + F, F + 64, 64, DY(7), nullptr, F, P, 0, Cs(7), F, nullptr, 1.0f, gs + m->gbl[7]);
+    }
+    for (int i = LAYERS - 1; i > 0; --i) {
+      // dY_{i-1} = (dY_i W_i) * c_{i-1}; its column sums are the bias gradient of layer i-1
+      CSeg c[1] = {{DY(i), F, F, F / 64, P, 0}};
+      cp.add(EPI_MUL, F, c, 1, pk + m->tl[i], F, F, DY(i - 1), nullptr, F, P, 0, Cs(i - 1), F, nullptr, 1.0f, gs + m->gbl[i - 1]);
+    }
+    if (int r = cp.run(st)) return r;
+  } else {
+    if (!depth) {
+      add_kmajor(p, EPI_MUL, P, FL, sdpre, 1, pk + m->tho, 16, 16, ws + w.dys3, nullptr, FL, ws + w.cs3, FL, nullptr, 1.0f,
+                 gs + m->gbs4);
+      if (all)
+        add_kmajor(p, EPI_MUL, P, hhw - FL, sdpre, 1, pk + m->tho + (long long)FL * 16, 16, 16, ws + w.dyhh, nullptr, hhw,
+                   ws + w.chh, hhw, nullptr, 1.0f);
+      Seg s3[1] = {{ws + w.dys3, FL, FL, FL / 64}};
+      add_kmajor(p, EPI_MUL, P, FL, s3, 1, pk + m->ts4, FL, FL, ws + w.dys2, nullptr, FL, ws + w.cs2, FL, nullptr, 1.0f,
+                 gs + m->gbs2);
+      Seg s2[1] = {{ws + w.dys2, FL, FL, FL / 64}};
+      add_kmajor(p, EPI_MUL, P, FL, s2, 1, pk + m->ts2, FL, FL, ws + w.dyhh + (size_t)m->hh_sun * 2, nullptr, hhw,
+                 ws + w.chh + (size_t)m->hh_sun * 2, hhw, nullptr, 1.0f);
+      Seg sh[1] = {{dyhh_r0, hhw, nh, nh / 64}};
+      add_kmajor(p, EPI_LINEAR, P, F, sh, 1, pk + m->th1 + r0, hhw, nh, ws + w.df, nullptr, F, nullptr, 0, nullptr, 1.0f,
+                 gs + m->gbf);
+      Seg s[2] = {{ws + w.df, F, F, F / 64}, {dpre, 16, 16, 1}};
+      add_kmajor(p, EPI_MUL, P, F, s, 2, pk + m->tf, F + 64, F + 64, DY(7), nullptr, F, Cs(7), F, nullptr, 1.0f, gs + m->gbl[7]);
+    } else {
+      add_kmajor(p, EPI_MUL, P, F, sdpre, 1, pk + m->tf + F, F + 64, 64, DY(7), nullptr, F, Cs(7), F, nullptr, 1.0f,
+                 gs + m->gbl[7]);
+    }
+    for (int i = LAYERS - 1; i > 0; --i) {
+      Seg s[1] = {{DY(i), F, F, F / 64}};
+      add_kmajor(p, EPI_MUL, P, F, s, 1, pk + m->tl[i], F, F, DY(i - 1), nullptr, F, Cs(i - 1), F, nullptr, 1.0f,
+                 gs + m->gbl[i - 1]);
+    }
+  }
+  // ---- wgrad: every weight gradient is dY^T x (layer input), split-K over the samples -----------------------
   add_wgrad(p, F, 16, H(7), F, dpre, 16, P, gs + m->ghot, 16, sms);
   if (!depth) add_wgrad(p, FL, 16, ws + w.s3, FL, dpre, 16, P, gs + m->ghot + (long long)F * 16, 16, sms);
   if (all) add_wgrad(p, hhw, 16, ws + w.hh, hhw, dpre, 16, P, gs + m->ghot + (long long)(F + FL) * 16, 16, sms);
-  Seg sdpre[1] = {{dpre, 16, 16, 1}};
   if (!depth) {
-    // sun head: s3 <- head output, then back through sun.4, sun.2 into the sun block of hh
-    add_kmajor(p, EPI_MUL, P, FL, sdpre, 1, pk + m->tho, 16, 16, ws + w.dys3, nullptr, FL, ws + w.cs3, FL, nullptr, 1.0f,
-               gs + m->gbs4);
-    if (all)  // rgb / beta / sem blocks of hh (columns [0, hhw-256))
-      add_kmajor(p, EPI_MUL, P, hhw - FL, sdpre, 1, pk + m->tho + (long long)FL * 16, 16, 16, ws + w.dyhh, nullptr, hhw,
-                 ws + w.chh, hhw, nullptr, 1.0f);
     add_wgrad(p, FL, FL, ws + w.dys3, FL, ws + w.s2, FL, P, gs + m->gs4, FL, sms);
-    Seg s3[1] = {{ws + w.dys3, FL, FL, FL / 64}};
-    add_kmajor(p, EPI_MUL, P, FL, s3, 1, pk + m->ts4, FL, FL, ws + w.dys2, nullptr, FL, ws + w.cs2, FL, nullptr, 1.0f,
-               gs + m->gbs2);
     add_wgrad(p, FL, FL, ws + w.dys2, FL, ws + w.hh + (size_t)m->hh_sun * 2, hhw, P, gs + m->gs2, FL, sms);
-    Seg s2[1] = {{ws + w.dys2, FL, FL, FL / 64}};
-    add_kmajor(p, EPI_MUL, P, FL, s2, 1, pk + m->ts2, FL, FL, ws + w.dyhh + (size_t)m->hh_sun * 2, nullptr, hhw,
-               ws + w.chh + (size_t)m->hh_sun * 2, hhw, nullptr, 1.0f);
-    // fused head first layers: weight / bias / per-ray-column gradients, then dF
-    const int r0 = all ? 0 : m->hh_sun, n = all ? hhw : FL;
-    const char* dyhh = ws + w.dyhh + (size_t)r0 * 2;
-    add_wgrad(p, n, F, dyhh, hhw, ws + w.f, F, P, gs + m->gh1 + (long long)r0 * F, F, sms);
-    add_wgrad(p, n, 16, dyhh, hhw, aux, 16, P, gs + m->gh1aux + (long long)r0 * 16, 16, sms);
+    // fused head first layers: weight / bias / per-ray-column gradients
+    add_wgrad(p, nh, F, dyhh_r0, hhw, ws + w.f, F, P, gs + m->gh1 + (long long)r0 * F, F, sms);
+    add_wgrad(p, nh, 16, dyhh_r0, hhw, aux, 16, P, gs + m->gh1aux + (long long)r0 * 16, 16, sms);
     if (all && g_aux) {
       // d aux = dY_beta * W_beta0[:, 512:]  -> embedding gradient (summed per ray by the caller-side kernel)
       Seg sb[1] = {{ws + w.dyhh + (size_t)m->hh_beta * 2, hhw, FL, FL / 64}};
@@ -731,36 +906,14 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
       a.f32out = g_aux;
       a.ldo = 16;
     }
-    Seg sh[1] = {{dyhh, hhw, n, n / 64}};
-    add_kmajor(p, EPI_LINEAR, P, F, sh, 1, pk + m->th1 + r0, hhw, n, ws + w.df, nullptr, F, nullptr, 0, nullptr, 1.0f,
-               gs + m->gbf);
     add_wgrad(p, F, F, ws + w.df, F, H(7), F, P, gs + m->gf, F, sms);
   }
-  // dY7 = ([dF | dPre16] * [Wf ; w_sigma]) * c7 ------------------------------------------------------------
-  int cur = 0;
-  if (!depth) {
-    Seg s[2] = {{ws + w.df, F, F, F / 64}, {dpre, 16, 16, 1}};
-    add_kmajor(p, EPI_MUL, P, F, s, 2, pk + m->tf, F + 64, F + 64, ws + w.dy[cur], nullptr, F, Cs(7), F, nullptr, 1.0f,
-               gs + m->gbl[7]);
-  } else {
-    add_kmajor(p, EPI_MUL, P, F, sdpre, 1, pk + m->tf + F, F + 64, 64, ws + w.dy[cur], nullptr, F, Cs(7), F, nullptr, 1.0f,
-               gs + m->gbl[7]);
-  }
   for (int i = LAYERS - 1; i >= 0; --i) {
-    const void* dy = ws + w.dy[cur];
-    // weight / bias gradients of layer i
     if (i == 0) {
-      add_wgrad(p, F, 64, dy, F, enc, m->enc_ld, P, gs + m->gl[0], 64, sms);
+      add_wgrad(p, F, 64, DY(0), F, enc, m->enc_ld, P, gs + m->gl[0], 64, sms);
     } else {
-      add_wgrad(p, F, F, dy, F, H(i - 1), F, P, gs + m->gl[i], F, sms);
-      if (i == 4) add_wgrad(p, F, 64, dy, F, enc, m->enc_ld, P, gs + m->gl4e, 64, sms);
-    }
-    if (i > 0) {
-      // dY_{i-1} = (dY_i W_i) * c_{i-1}; its column sums are the bias gradient of layer i-1
-      Seg s[1] = {{dy, F, F, F / 64}};
-      add_kmajor(p, EPI_MUL, P, F, s, 1, pk + m->tl[i], F, F, ws + w.dy[cur ^ 1], nullptr, F, Cs(i - 1), F, nullptr, 1.0f,
-                 gs + m->gbl[i - 1]);
-      cur ^= 1;
+      add_wgrad(p, F, F, DY(i), F, H(i - 1), F, P, gs + m->gl[i], F, sms);
+      if (i == 4) add_wgrad(p, F, 64, DY(4), F, enc, m->enc_ld, P, gs + m->gl4e, 64, sms);
     }
   }
   if (int r = run_plan(p, st)) return r;

@@ -72,19 +72,38 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
                     const float* __restrict__ g_weights, const float* __restrict__ g_transp,
                     const float* __restrict__ g_sem, const float* __restrict__ g_direct,
                     float* __restrict__ g_out) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_words = S * n_out;
-  // per warp: packed rows [S*n_out] (+ gradient rows in BWD) + z [S]
-  const int per_warp = (BWD ? 2 : 1) * row_words + S;
+  // per warp: packed rows [S*n_out] (+ gradient rows in BWD) + z [S], each region 16-byte aligned
+  const int rw4 = (row_words + 3) & ~3, s4 = (S + 3) & ~3;
+  const int per_warp = (BWD ? 2 : 1) * rw4 + s4;
   float* rows = smem + warp * per_warp;
-  float* grow = rows + row_words;  // BWD only
-  float* zs = rows + (BWD ? 2 : 1) * row_words;
+  float* grow = rows + rw4;  // BWD only
+  float* zs = rows + (BWD ? 2 : 1) * rw4;
+  // 16-byte global accesses when every ray's rows start on a 16-byte boundary (S*n_out % 4 == 0: true for
+  // the even sample counts the pipelines use); 4x the bytes in flight per load instruction
+  const bool vec_rows = (row_words & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                        (!BWD || (((reinterpret_cast<uintptr_t>(g_out) | reinterpret_cast<uintptr_t>(g_direct)) & 15) == 0));
+  const bool vec_z = (S & 3) == 0 && ((reinterpret_cast<uintptr_t>(z_vals) & 15) == 0);
 
   for (int ray = blockIdx.x * K3_WARPS + warp; ray < n_rays; ray += gridDim.x * K3_WARPS) {
     const float* src = out + (size_t)ray * row_words;
-    for (int i = lane; i < row_words; i += 32) rows[i] = __ldg(src + i);
-    for (int i = lane; i < S; i += 32) zs[i] = __ldg(z_vals + (size_t)ray * S + i);
+    if (vec_rows) {
+      const float4* s4p = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(rows);
+#pragma unroll 8
+      for (int i = lane; i < row_words / 4; i += 32) d4[i] = __ldg(s4p + i);
+    } else {
+      for (int i = lane; i < row_words; i += 32) rows[i] = __ldg(src + i);
+    }
+    if (vec_z) {
+      if (lane < S / 4) reinterpret_cast<float4*>(zs)[lane] = __ldg(reinterpret_cast<const float4*>(z_vals + (size_t)ray * S) + lane);
+      for (int i = lane + 32; i < S / 4; i += 32)
+        reinterpret_cast<float4*>(zs)[i] = __ldg(reinterpret_cast<const float4*>(z_vals + (size_t)ray * S) + i);
+    } else {
+      for (int i = lane; i < S; i += 32) zs[i] = __ldg(z_vals + (size_t)ray * S + i);
+    }
     __syncwarp();
 
     // ---- forward pass over this lane's SPL consecutive samples --------------------------------
@@ -228,7 +247,21 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
       }
       __syncwarp();
       float* dst = g_out + (size_t)ray * row_words;
-      if (g_direct) {
+      if (vec_rows) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        const float4* g4 = reinterpret_cast<const float4*>(grow);
+        if (g_direct) {
+          const float4* gd4 = reinterpret_cast<const float4*>(g_direct + (size_t)ray * row_words);
+#pragma unroll 8
+          for (int i = lane; i < row_words / 4; i += 32) {
+            const float4 a = g4[i], b = __ldg(gd4 + i);
+            d4[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+          }
+        } else {
+#pragma unroll 8
+          for (int i = lane; i < row_words / 4; i += 32) d4[i] = g4[i];
+        }
+      } else if (g_direct) {
         const float* gdir = g_direct + (size_t)ray * row_words;
         for (int i = lane; i < row_words; i += 32) dst[i] = grow[i] + __ldg(gdir + i);
       } else {
@@ -245,7 +278,7 @@ static int launch_k3(const float* out, const float* z, int n_rays, int S, int n_
                      const float* g_rgb, const float* g_depth, const float* g_w, const float* g_t,
                      const float* g_sem, const float* g_direct, float* g_out, cudaStream_t st) {
   const int spl = (S + 31) / 32;
-  const size_t smem = (size_t)K3_WARPS * ((BWD ? 2 : 1) * S * n_out + S) * sizeof(float);
+  const size_t smem = (size_t)K3_WARPS * ((BWD ? 2 : 1) * ((S * n_out + 3) & ~3) + ((S + 3) & ~3)) * sizeof(float);
   int sms = num_sms();
   if (sms <= 0) return SNB_ERR_NO_DEVICE;
   int blocks = (n_rays + K3_WARPS - 1) / K3_WARPS;

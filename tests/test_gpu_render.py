@@ -159,3 +159,38 @@ def test_state_dict_interchange_changes_results():
         model.load_state_dict(params)
         c = r.render_rays({"coarse": model, "t": t}, rays.to(DEV), extras.to(DEV), render_options={"u": u})["rgb_coarse"]
     assert not torch.equal(a, b) and torch.equal(a, c)
+
+
+@pytest.mark.parametrize("kind,C,P", [("semantic", 6, 148 * 256 * 3 + 77), ("satnerf", 0, 148 * 256 + 256 * 30), ("semantic", 5, 256 * 74 + 1)])
+def test_chained_mlp_equals_per_layer_mlp(kind, C, P):
+    """The chained persistent kernel (one launch per pass, several 256-row blocks per SM pair, two slots in
+    flight, ragged tail) against the per-layer GEMM launches: same tile arithmetic, so the forward outputs are
+    bit-identical and the gradients agree up to the fp32 split-K accumulation order."""
+    from semnerf_b200 import _lib
+    lib = _lib_or_fail()
+    spec, params, emb, cfgs, model, t = _model(kind, C, seed=3)
+    g = torch.Generator().manual_seed(5)
+    xyz = (torch.rand(P, 3, generator=g) * 2 - 1).to(DEV)
+    sun = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=1).to(DEV)
+    tt = torch.randn(P, 4, generator=g).to(DEV)
+    w = torch.randn(P, 9 + C, generator=g).to(DEV)
+    res = {}
+    prev = lib.snb_set_chained_mlp(1)
+    try:
+        for mode in (1, 0):
+            lib.snb_set_chained_mlp(mode)
+            model.flat.grad = None
+            tg = tt.clone().requires_grad_(True)
+            out = model(xyz, input_sun_dir=sun, input_t=tg)
+            (out * w).sum().backward()
+            with torch.no_grad():
+                inf = model(xyz, input_sun_dir=sun, input_t=tt)   # inference path (per-pair scratch when chained)
+            torch.cuda.synchronize()
+            res[mode] = (out.detach().clone(), model.flat.grad.detach().clone(), tg.grad.detach().clone(), inf.clone())
+    finally:
+        lib.snb_set_chained_mlp(prev)
+    assert torch.equal(res[1][0], res[0][0])
+    assert torch.equal(res[1][3], res[0][3]) and torch.equal(res[1][3], res[1][0])
+    ga, gb = res[1][1].double(), res[0][1].double()
+    assert (ga - gb).abs().max() <= 1e-3 * gb.abs().max() and _cos(ga, gb) >= 0.999999
+    assert _cos(res[1][2], res[0][2]) >= 0.999999
