@@ -173,7 +173,9 @@ int snb_profile_end(double* gemm_ms, int64_t* gemm_launches, int64_t* total_laun
 /* ------------------------------------------------------------------------------------------------
  * test hook: one bf16 GEMM through the tcgen05 kernel.  D = A (M,K) x B (N,K)^T (+ epilogue).
  * a_mn / b_mn = 1: operand stored (K,M) / (K,N) row-major (the wgrad form).
- * epi: 0 sin(w0*(acc+bias)) -> out0 bf16 [+ out1 = w0*cos(..)], 1 acc+bias -> bf16, 2 acc*mul -> bf16,
+ * epi: 0 sin(w0*(acc+bias)) -> out0 bf16 [+ out1 = (M, N/32) u32 sign mask: bit c of row r = cos(..) < 0],
+ *      1 acc+bias -> bf16, 2 acc*mul -> bf16 [out1 = sign mask: acc * w0 * (+-)sqrt(1 - mul^2), the SIREN
+ *      derivative rebuilt from the saved activation mul = sin(..)]  (0-2: N % 256 == 0, K-major operands),
  *      4 f32 rows (N==16), 5 f32 += acc (split-K reduce).
  * ---------------------------------------------------------------------------------------------- */
 int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int N, int K,

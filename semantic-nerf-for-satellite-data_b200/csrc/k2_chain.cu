@@ -51,6 +51,73 @@ __device__ __forceinline__ void cur_next(Cursor& c, const Seq& q, const ChainArg
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+
+// ---- epilogue math, specialised per mode so the inner loops are branch-free ---------------------------------
+enum ChunkMode { CM_LINEAR = 0, CM_SIN = 1, CM_SIN_MASK = 2 };
+
+// 32 accumulator columns of one row -> 16 packed bf16x2 words (+ the sign bits of the SIREN derivative).
+// bsm: shared-memory address of this thread's 32 bias values, pre-multiplied by w0.
+// Sign-mask layout (one 32-bit word per row and 32 columns): bit k = column 2k, bit 16 + k = column 2k + 1, so that
+// the backward epilogue flips the signs of a packed bf16x2 pair with one shift and one logic op.
+template <int MODE>
+__device__ __forceinline__ void chunk_math(const uint32_t (&v)[32], uint32_t bsm, float w0, uint32_t (&outw)[16],
+                                           uint32_t& mbits) {
+  uint32_t me = 0, mo = 0;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    uint32_t b0, b1, b2, b3;
+    ld_shared_v4(bsm + g * 16, b0, b1, b2, b3);
+    float y[4];
+    y[0] = fmaf(__uint_as_float(v[g * 4 + 0]), w0, __uint_as_float(b0));
+    y[1] = fmaf(__uint_as_float(v[g * 4 + 1]), w0, __uint_as_float(b1));
+    y[2] = fmaf(__uint_as_float(v[g * 4 + 2]), w0, __uint_as_float(b2));
+    y[3] = fmaf(__uint_as_float(v[g * 4 + 3]), w0, __uint_as_float(b3));
+    if (MODE == CM_SIN_MASK) {
+      // y = n*pi + r, |r| <= pi/2: cos(y) = (-1)^n cos(r), so its sign is the parity of n = rint(y/pi), read off the
+      // mantissa after adding 1.5 * 2^23; bits enter at the top of me / mo (even / odd columns) in column order
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t u = __float_as_uint(fmaf(y[j], 0.318309886183790672f, 12582912.0f));
+        if (j & 1) mo = __funnelshift_r(mo, u, 1);
+        else me = __funnelshift_r(me, u, 1);
+      }
+    }
+    if (MODE != CM_LINEAR) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = __sinf(y[j]);
+    }
+    outw[g * 2] = pack_bf16x2(y[0], y[1]);
+    outw[g * 2 + 1] = pack_bf16x2(y[2], y[3]);
+  }
+  mbits = (me >> 16) | (mo & 0xffff0000u);
+}
+
+// dgrad: accumulator * multiplicand, in place in the staged multiplicand tile (this thread's 4 x 16 bytes of a row).
+// SIREN: the multiplicand is the derivative w0 cos(.) rebuilt from the saved activation h = sin(.) (|h| <= 1 in bf16,
+// so 1 - h^2 >= 0 exactly) and its sign bit: |cos| = sqrt(1 - h^2); the signs are applied to the packed bf16x2 pairs.
+template <bool SIREN, bool W0ONE>
+__device__ __forceinline__ void chunk_mul(const uint32_t (&v)[32], uint32_t buf, uint32_t row_off, uint32_t sw, int half,
+                                          float w0, uint32_t mw) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint32_t off = row_off + ((((uint32_t)(half * 4 + g)) ^ sw) << 4);
+    uint32_t q[4], o[4];
+    ld_shared_v4(buf + off, q[0], q[1], q[2], q[3]);
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float f0 = bf16_lo(q[p]), f1 = bf16_hi(q[p]);
+      if (SIREN) {
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f0) : "f"(fmaf(-f0, f0, 1.0f)));
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f1) : "f"(fmaf(-f1, f1, 1.0f)));
+        if (!W0ONE) { f0 *= w0; f1 *= w0; }
+      }
+      o[p] = pack_bf16x2(__uint_as_float(v[g * 8 + 2 * p]) * f0, __uint_as_float(v[g * 8 + 2 * p + 1]) * f1);
+      if (SIREN) o[p] ^= (mw << (15 - (g * 4 + p))) & 0x80008000u;
+    }
+    st_shared_v4(buf + off, o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace
 
 __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __grid_constant__ ChainArgs args) {
@@ -59,8 +126,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
   uint8_t* sA = smem;
   uint8_t* sB = sA + CHAIN_A_STAGES * 16384;
   uint8_t* sStg = smem + CHAIN_RING_BYTES;
-  float* cs_smem = reinterpret_cast<float*>(sStg + GEMM_NUM_STAGING * GEMM_STAGING);
-  uint64_t* fullA = reinterpret_cast<uint64_t*>(cs_smem + CHAIN_MAX_COLSUM * CHAIN_COLSUM_W);
+  float* bias_smem = reinterpret_cast<float*>(sStg + GEMM_NUM_STAGING * GEMM_STAGING);   // [group][buffer][128]: the bias of a group's two chunks
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(bias_smem + 512);
   uint64_t* emptyA = fullA + 8;
   uint64_t* fullB = emptyA + 8;
   uint64_t* emptyB = fullB + 8;
@@ -81,7 +148,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
   seq.n_my = pair < args.n_blocks ? (args.n_blocks - pair + n_pairs - 1) / n_pairs : 0;
   seq.n_layers = args.n_layers;
 
-  for (int i = threadIdx.x; i < CHAIN_MAX_COLSUM * CHAIN_COLSUM_W; i += CHAIN_THREADS) cs_smem[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < 8; ++s) {
       mbar_init(&fullA[s], 2);   // the leader's expect_tx arrive + the peer's remote arrive
@@ -213,12 +279,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
     const uint32_t sw = (uint32_t)(row & 7);
     const int bar_id = 1 + grp;
     auto gbar = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory"); };
-    const int cs_col = gtid & 63, cs_rq = gtid >> 6;   // column-sum ownership: column x 32-row quarter
 
     uint32_t it = 0;
-    uint32_t cn = 0;          // chunks this group has committed (one bulk group per chunk)
+    uint32_t cn = 0;          // chunks this group has committed (one bulk group per chunk); chunk cn stages in buffer cn & 1
     uint32_t mpar = 0;        // phase bits of the two mul-operand barriers
-    bool prev_single = false; // the previous chunk used one staging buffer (the other one than this chunk)
     bool cur_prefetched = false;
     // completion signals owed to the A producer: slot + the commit count that must have completed (leader only)
     int npend = 0, pend_slot0 = 0, pend_slot1 = 0;
@@ -233,11 +297,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         --npend;
       }
     };
-    // staging-buffer reuse: at most `allow` of this leader's bulk stores may still be reading shared memory
-    auto wait_staging = [&](int allow) {   // leader only
-      if (allow == 0) bulk_wait_read<0>();
-      else bulk_wait_read<1>();
-    };
     // a tile-set's rows must be in L2 / HBM before the A producer may read them back: checked right before this
     // leader issues its next store, i.e. one chunk of compute after the stores in question were issued
     auto confirm_pending = [&]() {   // leader only
@@ -246,18 +305,29 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         confirm(cn);
       }
     };
+    // bias of this group's two chunks of a tile: column (grp + 2 * (i >> 6)) * 64 + (i & 63) for i < 128
+    float* gbias = bias_smem + grp * 256;
+    auto bias_fetch = [&](const Cursor& t) -> float {
+      const float* bp = args.layers[t.l].bias;   // staged pre-multiplied by w0: the epilogue computes fma(acc, w0, w0 * bias)
+      return (gtid < 128 && bp != nullptr) ? args.layers[t.l].w0 * __ldg(bp + t.j * 256 + (grp + 2 * (gtid >> 6)) * 64 + (gtid & 63)) : 0.f;
+    };
 
     Cursor c, nx;
     cur_init(c, seq);
     nx = c;
     if (!nx.done) cur_next(nx, seq, args);
+    if (!c.done) {
+      const float b0 = bias_fetch(c);
+      if (gtid < 128) gbias[gtid] = b0;
+      gbar();
+    }
     for (; !c.done; c = nx, cur_next(nx, seq, args), ++it) {
       const ChainLayer& ly = args.layers[c.l];
       const int epi = ly.epi;
-      const bool two = ly.two_out != 0;
       const float w0 = ly.w0;
-      const float* bias = ly.bias;
-      const int cs_slot = ly.cs_slot;
+      const uint32_t* mask = ly.mask;
+      const int mask_ld = ly.mask_ld;
+      const bool siren = ly.mul_siren != 0;
       const bool next_mul = !nx.done && args.layers[nx.l].epi == EPI_MUL;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int blk = (c.g * CHAIN_SLOTS + c.s) * n_pairs + pair;
@@ -265,6 +335,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       const int m_scr = (pair * CHAIN_SLOTS + c.s) * 256 + (int)cta_rank * GEMM_BLOCK_M;
       const int m_out = ly.o_scratch ? m_scr : m_real;
       const int n0 = c.j * 256;
+      const bool row_ok = m_real + row < args.M;
+      const float* tbias = gbias + (it & 1) * 128;
+      float nbias = 0.f;   // next tile's bias value staged by threads 0..127 of the group
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -273,15 +346,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
 #pragma unroll 1
       for (int ci = 0; ci < 2; ++ci) {
         const int ch = grp + 2 * ci;                 // 64-column chunk of the tile
-        const uint32_t b = cn & 1;                   // staging buffer of a single-output chunk
-        const uint32_t buf0 = two ? stg0 : stg0 + b * GEMM_STAGING;
-        const uint32_t buf1 = stg0 + GEMM_STAGING;
+        const uint32_t b = cn & 1;                   // staging buffer of this chunk
+        const uint32_t buf0 = stg0 + b * GEMM_STAGING;
         // the chunk after this one (same tile, or the first chunk of the next tile)
         const bool nmul = (ci == 0) ? (epi == EPI_MUL) : next_mul;
         if (leader && (epi == EPI_MUL || nmul)) {
           // a mul-operand tile is TMA-loaded into the staging buffer its chunk will be multiplied in: the
           // store that last used that buffer must have drained first
-          wait_staging(0);
+          bulk_wait_read<0>();
           if (epi == EPI_MUL && !cur_prefetched) {
             mbar_expect_tx(&gmfull[b], GEMM_STAGING);
             tma_load_2d_hint(stg_ptr + b * GEMM_STAGING, &ly.tmMul, &gmfull[b], n0 + ch * 64, m_real, L2_EVICT_FIRST);
@@ -299,89 +371,49 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
           }
         }
         cur_prefetched = nmul;
+        if (ci == 1 && !nx.done) nbias = bias_fetch(nx);   // in flight during this chunk
+        const int colbase = n0 + ch * 64 + half * 32;
+        uint32_t mw = 0;
+        if (epi == EPI_MUL && siren && row_ok) mw = __ldg(mask + (size_t)(m_real + row) * mask_ld + (colbase >> 5));
 
         uint32_t v[32];
         tmem_ld32(taddr + ch * 64 + half * 32, v);
         tc_wait_ld();
-        const int colbase = n0 + ch * 64 + half * 32;
 
         if (epi == EPI_MUL) {
           mbar_wait(&gmfull[b], (mpar >> b) & 1u);
           mpar ^= 1u << b;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t off = row_off + ((((uint32_t)(half * 4 + g)) ^ sw) << 4);
-            uint32_t q0, q1, q2, q3;
-            ld_shared_v4(buf0 + off, q0, q1, q2, q3);
-            const float x0 = __uint_as_float(v[g * 8 + 0]) * bf16_lo(q0), x1 = __uint_as_float(v[g * 8 + 1]) * bf16_hi(q0);
-            const float x2 = __uint_as_float(v[g * 8 + 2]) * bf16_lo(q1), x3 = __uint_as_float(v[g * 8 + 3]) * bf16_hi(q1);
-            const float x4 = __uint_as_float(v[g * 8 + 4]) * bf16_lo(q2), x5 = __uint_as_float(v[g * 8 + 5]) * bf16_hi(q2);
-            const float x6 = __uint_as_float(v[g * 8 + 6]) * bf16_lo(q3), x7 = __uint_as_float(v[g * 8 + 7]) * bf16_hi(q3);
-            st_shared_v4(buf0 + off, pack_bf16x2(x0, x1), pack_bf16x2(x2, x3), pack_bf16x2(x4, x5), pack_bf16x2(x6, x7));
-          }
+          if (!siren) chunk_mul<false, true>(v, buf0, row_off, sw, half, w0, mw);
+          else if (w0 == 1.0f) chunk_mul<true, true>(v, buf0, row_off, sw, half, w0, mw);
+          else chunk_mul<true, false>(v, buf0, row_off, sw, half, w0, mw);
         } else {
-          uint32_t outw[16], outc[16];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float x[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
-            if (bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + colbase + g * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + colbase + g * 8 + 4));
-              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-            }
-            if (epi == EPI_SIN) {
-              if (two) {   // training: h and the derivative w0*cos(.)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float y0 = w0 * x[2 * j], y1 = w0 * x[2 * j + 1];
-                  outw[g * 4 + j] = pack_bf16x2(__sinf(y0), __sinf(y1));
-                  outc[g * 4 + j] = pack_bf16x2(w0 * __cosf(y0), w0 * __cosf(y1));
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) outw[g * 4 + j] = pack_bf16x2(__sinf(w0 * x[2 * j]), __sinf(w0 * x[2 * j + 1]));
-              }
-            } else {   // EPI_LINEAR
-#pragma unroll
-              for (int j = 0; j < 4; ++j) outw[g * 4 + j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-            }
-          }
-          // results are in registers: the previous TMA store(s) of the buffer(s) about to be overwritten had
-          // the whole compute phase above to drain
-          if (leader) wait_staging((!two && prev_single) ? 1 : 0);
+          uint32_t outw[16];
+          uint32_t mbits = 0;
+          const uint32_t bsm = smem_u32(tbias + ci * 64 + half * 32);
+          if (epi == EPI_LINEAR) chunk_math<CM_LINEAR>(v, bsm, w0, outw, mbits);
+          else if (mask == nullptr) chunk_math<CM_SIN>(v, bsm, w0, outw, mbits);
+          else chunk_math<CM_SIN_MASK>(v, bsm, w0, outw, mbits);
+          if (epi == EPI_SIN && mask != nullptr && row_ok)
+            const_cast<uint32_t*>(mask)[(size_t)(m_real + row) * mask_ld + (colbase >> 5)] = mbits;
+          // results are in registers: the store that last used this buffer (two chunks ago) had the whole compute
+          // phase above to drain; the previous chunk's store (other buffer) may still be in flight
+          if (leader) bulk_wait_read<1>();
           gbar();
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint32_t off = row_off + ((((uint32_t)(half * 4 + g)) ^ sw) << 4);
             st_shared_v4(buf0 + off, outw[g * 4], outw[g * 4 + 1], outw[g * 4 + 2], outw[g * 4 + 3]);
-            if (two) st_shared_v4(buf1 + off, outc[g * 4], outc[g * 4 + 1], outc[g * 4 + 2], outc[g * 4 + 3]);
           }
         }
-        if (cs_slot >= 0) {
-          gbar();   // every row of the chunk is in the staging buffer
-          float sum = 0.f;
-          const uint32_t cbase = buf0 + (uint32_t)(cs_col & 7) * 2u;
-#pragma unroll 8
-          for (int r = cs_rq * 32; r < cs_rq * 32 + 32; ++r) {
-            uint16_t hv;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(cbase + (uint32_t)r * 128u + ((((uint32_t)cs_col >> 3) ^ ((uint32_t)r & 7u)) << 4)));
-            sum += __uint_as_float(((uint32_t)hv) << 16);
-          }
-          atomicAdd(&cs_smem[cs_slot * CHAIN_COLSUM_W + n0 + ch * 64 + cs_col], sum);
-        }
+        if (ci == 1 && gtid < 128) gbias[((it + 1) & 1) * 128 + gtid] = nbias;   // visible after the barrier below
         fence_proxy_async();
         gbar();
         if (leader) {
           confirm_pending();
           tma_store_2d(&ly.tmO0, buf0, n0 + ch * 64, m_out);
-          if (two) tma_store_2d_hint(&ly.tmO1, buf1, n0 + ch * 64, m_out, L2_EVICT_FIRST);   // read again only by the backward pass
           bulk_commit();
         }
         ++cn;
-        prev_single = !two;
       }
       tc_fence_before();
       if (lead_cta) mbar_arrive(&tempty[acc]);
@@ -389,8 +421,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
 
       if (leader && c.j == ly.n_tiles - 1) {
         // this group's part of the tile-set (layer, slot) is committed; tell the A producer once it has landed.
-        // Normally that is noticed at the staging waits of the following tiles (other slot); when the very next
-        // tile-set belongs to the same slot (single-slot tail) or nothing follows, wait here.
+        // Normally that is noticed before the next store (a tile of the other slot); when the very next tile-set
+        // belongs to the same slot (single-slot tail) or nothing follows, wait here.
         if (npend == 0) { pend_cn0 = cn; pend_slot0 = c.s; }
         else { pend_cn1 = cn; pend_slot1 = c.s; }
         ++npend;
@@ -405,17 +437,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
 
   tc_fence_before();
   __syncthreads();
-  // bias gradients: one atomic per column per CTA
-  for (int l = 0; l < args.n_layers; ++l) {
-    const ChainLayer& ly = args.layers[l];
-    if (ly.cs_slot >= 0 && ly.colsum != nullptr && seq.n_my > 0) {
-      const int n = ly.n_tiles * 256;
-      for (int i = threadIdx.x; i < n; i += CHAIN_THREADS) {
-        const float v = cs_smem[ly.cs_slot * CHAIN_COLSUM_W + i];
-        if (v != 0.f) atomicAdd(ly.colsum + i, v);
-      }
-    }
-  }
   cluster_sync_all();   // neither CTA may exit while its peer can still signal it
   if (warp == 1) {
     tc_fence_after();
@@ -434,19 +455,15 @@ int chain_scratch_rows() {
 int chain_launch(const ChainArgs& a, cudaStream_t st) {
   SNB_CHECK_ARG(a.n_layers >= 1 && a.n_layers <= CHAIN_MAX_LAYERS, SNB_ERR_INVALID, "chain: %d layers", a.n_layers);
   SNB_CHECK_ARG(a.M >= 1 && a.n_blocks == (a.M + 255) / 256, SNB_ERR_INVALID, "chain: bad row count");
-  bool any_two = false, any_mul = false;
   double macs = 0.0;
   for (int l = 0; l < a.n_layers; ++l) {
     const ChainLayer& ly = a.layers[l];
     SNB_CHECK_ARG(ly.n_tiles >= 1 && ly.kb_total >= 1 && ly.nseg >= 1 && ly.nseg <= 3, SNB_ERR_INVALID, "chain: layer %d shape", l);
     SNB_CHECK_ARG(ly.epi == EPI_SIN || ly.epi == EPI_LINEAR || ly.epi == EPI_MUL, SNB_ERR_UNSUPPORTED, "chain: layer %d epilogue %d", l, ly.epi);
-    SNB_CHECK_ARG(ly.cs_slot < CHAIN_MAX_COLSUM && (ly.cs_slot < 0 || ly.n_tiles * 256 <= CHAIN_COLSUM_W), SNB_ERR_UNSUPPORTED,
-                  "chain: layer %d column-sum slot", l);
-    any_two |= ly.two_out != 0;
-    any_mul |= ly.epi == EPI_MUL;
+    SNB_CHECK_ARG(!(ly.epi == EPI_MUL && ly.mul_siren) || (ly.mask != nullptr && ly.mask_ld > 0), SNB_ERR_INVALID,
+                  "chain: layer %d needs the sign mask of the saved activation", l);
     macs += (double)a.n_blocks * 256.0 * ly.n_tiles * 256.0 * ly.kb_total * GEMM_BLOCK_K;
   }
-  SNB_CHECK_ARG(!(any_two && any_mul), SNB_ERR_UNSUPPORTED, "chain: two-output and mul layers cannot share a chain");
   const int sms = num_sms();
   if (sms <= 0) return SNB_ERR_NO_DEVICE;
   static bool attr_set = false;

@@ -15,32 +15,33 @@ namespace snb {
 
 constexpr int CHAIN_SLOTS = 2;
 constexpr int CHAIN_MAX_LAYERS = 16;
-constexpr int CHAIN_MAX_COLSUM = 11;   // layers whose bias gradient (column sums) is accumulated in smem
-constexpr int CHAIN_COLSUM_W = 512;    // widest layer with a column sum
 constexpr int CHAIN_A_STAGES = 5;      // 16 KB slots (128 rows x 64 k)
-constexpr int CHAIN_B_STAGES = 3;      // 16 KB slots (this CTA's 128 of the 256 weight rows x 64 k; weights are L2-resident)
+constexpr int CHAIN_B_STAGES = 4;      // 16 KB slots (this CTA's 128 of the 256 weight rows x 64 k; weights are L2-resident)
 constexpr int CHAIN_EPI_WARPS = 16;    // two groups of 8 warps; warps w and w+4 of a group split a 64-column chunk
 constexpr int CHAIN_THREADS = 96 + CHAIN_EPI_WARPS * 32;
 constexpr int CHAIN_RING_BYTES = (CHAIN_A_STAGES + CHAIN_B_STAGES) * 16384;
 constexpr int CHAIN_SMEM_BYTES = CHAIN_RING_BYTES + GEMM_NUM_STAGING * GEMM_STAGING +
-                                 CHAIN_MAX_COLSUM * CHAIN_COLSUM_W * 4 + 1024 /*barriers*/ + 1024 /*alignment*/;
+                                 2048 /*bias tiles*/ + 1024 /*barriers*/ + 1024 /*alignment*/;
 
 struct alignas(64) ChainLayer {
   CUtensorMap tmA[3];   // A K-segments, box {64 k, 128 rows}
   CUtensorMap tmB;      // weights [N, K], box {64 k, block_n / 2 rows}
-  CUtensorMap tmO0, tmO1, tmMul;
+  CUtensorMap tmO0, tmMul;
   int seg_kb[3];
   int a_scratch[3];     // segment lives in the per-pair scratch (row = (pair*SLOTS + slot)*256) instead of at the block's rows
   int nseg;
   int kb_total;
   int n_tiles;          // N / 256
   int epi;              // EPI_SIN / EPI_LINEAR / EPI_MUL
-  int two_out;          // EPI_SIN: also store the derivative w0*cos(.)
+  int mul_siren;        // EPI_MUL: the multiplicand is the SIREN derivative rebuilt from the saved activation h = sin(y)
+                        // (tmMul) and the sign mask: w0 * (-1)^bit * sqrt(1 - h^2); 0: multiply by the tmMul tensor itself
   int o_scratch;        // outputs go to the per-pair scratch
-  int cs_slot;          // >= 0: accumulate column sums of the bf16 output (bias gradient) in smem slot cs_slot
+  int mask_ld;          // 32-bit words per row of `mask`
+  uint32_t* mask;       // EPI_SIN: written (NULL = inference), bit c of row r = [cos(w0*(acc+bias)) < 0]: with h it is all the
+                        // backward pass needs of the derivative (1 bit instead of 16 per element of HBM write traffic);
+                        // EPI_MUL + mul_siren: read
   float w0;
   const float* bias;
-  float* colsum;        // global destination of the column sums (N floats), flushed once per CTA at the end
 };
 
 struct ChainArgs {

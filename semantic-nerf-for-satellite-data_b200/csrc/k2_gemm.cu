@@ -1,4 +1,5 @@
 // K2 GEMM kernel - see k2_gemm.cuh for the design.  sm_100a only (tcgen05 / TMEM / TMA).
+#include "k2_chain.cuh"
 #include "k2_gemm.cuh"
 #include "k2_ptx.cuh"
 
@@ -32,12 +33,17 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& a, int tile) {
 // each CTA holds its 128 rows of A and HALF of the B tile, the leader CTA issues cta_group::2 MMAs.
 template <int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_constant__ GemmArgs args) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  if ((smem - smem_raw) + GEMM_LAYOUT_BYTES > GEMM_SMEM_BYTES) {
+    if (threadIdx.x == 0) printf("snb gemm: dynamic shared memory base misaligned by %d bytes\n", (int)(smem - smem_raw));
+    __trap();
+  }
   uint8_t* sA = smem;
   uint8_t* sB = sA + args.a_stages * GEMM_A_STAGE;
   uint8_t* sStg = smem + GEMM_OPERAND_BYTES;
-  uint64_t* fullA = reinterpret_cast<uint64_t*>(sStg + GEMM_NUM_STAGING * GEMM_STAGING);
+  uint8_t* sOnes = sStg + GEMM_NUM_STAGING * GEMM_STAGING;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(sOnes + GEMM_ONES_BYTES);
   uint64_t* emptyA = fullA + GEMM_MAX_RING;
   uint64_t* fullB = emptyA + GEMM_MAX_RING;
   uint64_t* emptyB = fullB + GEMM_MAX_RING;
@@ -71,6 +77,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
     }
     for (int s = 0; s < GEMM_NUM_STAGING; ++s) mbar_init(&mfull[s], 1);
     fence_barrier_init();
+  }
+  if constexpr (EPI == EPI_WGRAD) {
+    // the all-ones operand of the bias-gradient MMA (read by the tensor core: async proxy)
+    for (int i = threadIdx.x; i < GEMM_ONES_BYTES / 4; i += GEMM_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+    fence_proxy_async();
   }
   if (warp == 1) {
     if constexpr (CG == 2) {
@@ -162,6 +173,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
       const uint64_t adesc0 = umma_desc(0, a_lbo, 1024u), bdesc0 = umma_desc(0, b_lbo, 1024u);
       const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4;
       const uint32_t b_slot16 = b_slot >> 4;
+      // bias gradient: D2[M, 16] += A[M, k] * ones[16, k]^T into the last 16 TMEM columns (every unit runs at most one
+      // tile when colsum is set, so the second accumulator's columns are free)
+      const uint32_t idesc_cs = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)args.a_mn << 15) | ((16u >> 3) << 17) |
+                                ((uint32_t)((GEMM_BLOCK_M * CG) >> 4) << 24);
+      const uint64_t odesc = umma_desc(smem_u32(sOnes), 16u, 1024u);
+      const uint32_t d_cs = tmem_base + 2 * GEMM_MAX_BLOCK_N - 16;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
         const TileCoord t = decode_tile(args, tile);
@@ -169,6 +186,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * GEMM_MAX_BLOCK_N;
+        const bool do_cs = EPI == EPI_WGRAD && args.colsum != nullptr && t.n_blk == 0;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&fullA[sa], pa);
           mbar_wait(&fullB[sb], pb);
@@ -180,6 +198,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
             for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
               if constexpr (CG == 2) tc_mma_bf16_2sm(d_tmem, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
               else tc_mma_bf16(d_tmem, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+            }
+            if (do_cs) {
+#pragma unroll
+              for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+                if constexpr (CG == 2) tc_mma_bf16_2sm(d_cs, ad + k * a_kstep, odesc + k * 2, idesc_cs, (kb > t.kb0 || k > 0) ? 1u : 0u);
+                else tc_mma_bf16(d_cs, ad + k * a_kstep, odesc + k * 2, idesc_cs, (kb > t.kb0 || k > 0) ? 1u : 0u);
+              }
             }
             // frees the smem slots (in both CTAs of a pair) once these MMAs have read them
             if constexpr (CG == 2) { tc_commit_2sm(&emptyA[sa]); tc_commit_2sm(&emptyB[sb]); }
@@ -207,43 +232,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
     const int gtid = (ewarp & 3) * 32 + lane;  // 0..127 within the group
     const bool leader = (gtid == 0);
     const uint32_t stg0 = smem_u32(sStg) + grp * 2 * GEMM_STAGING;   // this group's two staging buffers
-    uint8_t* stg_ptr = sStg + grp * 2 * GEMM_STAGING;
-    uint64_t* gmfull = mfull + grp * 2;
     const uint32_t row_off = (uint32_t)row * 128u;
     const uint32_t sw = (uint32_t)(row & 7);
     const int bar_id = 1 + grp;
     auto gbar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory"); };
     uint32_t it = 0;
     uint32_t cn = 0;  // this group's running chunk counter (position in its staging ring)
-
-    // EPI_MUL: this group's chunk n+1 of the saved SIREN derivative is prefetched while chunk n is processed
-    const uint32_t grp_chunks = (uint32_t)(args.block_n / 128);   // chunks per tile per group (64-wide chunks)
-    auto mul_issue = [&](uint32_t n) {
-      const uint32_t tl = n / grp_chunks, c = (n % grp_chunks) * 2 + grp;
-      const long long tile = (long long)unit + (long long)tl * n_units;
-      if (tile >= total_tiles) return;
-      const TileCoord t = decode_tile(args, (int)tile);
-      mbar_expect_tx(&gmfull[n & 1], GEMM_STAGING);
-      tma_load_2d(stg_ptr + (n & 1) * GEMM_STAGING, &args.tmMul, &gmfull[n & 1], t.n_blk * args.block_n + (int)c * 64,
-                  t.m_blk * (GEMM_BLOCK_M * CG) + (int)cta_rank * GEMM_BLOCK_M);
-    };
-    if (EPI == EPI_MUL && leader && grp_chunks > 0) mul_issue(0);
-    // bias-gradient column sums (EPI_MUL / EPI_LINEAR with args.colsum): thread (cj, half) owns column cj of
-    // this group's chunks over 64 of the 128 rows; sums live in registers across tiles and are flushed
-    // with one atomicAdd per column whenever the CTA moves to another n-block (and at the end).
-    const int cs_col = gtid & 63, cs_half = gtid >> 6;
-    float cs_acc[2] = {0.f, 0.f};
-    int cs_nblk = -1;
-    auto cs_flush = [&]() {
-      if (cs_nblk >= 0) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int col = cs_nblk * args.block_n + (2 * q + grp) * 64 + cs_col;
-          if ((2 * q + grp) * 64 < args.block_n && col < args.N && cs_acc[q] != 0.f) atomicAdd(args.colsum + col, cs_acc[q]);
-          cs_acc[q] = 0.f;
-        }
-      }
-    };
 
     for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
       const TileCoord t = decode_tile(args, tile);
@@ -254,121 +248,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
       const int m0 = t.m_blk * (GEMM_BLOCK_M * CG) + (int)cta_rank * GEMM_BLOCK_M;
       const int n0 = t.n_blk * args.block_n;
 
-      if constexpr (EPI == EPI_SIN || EPI == EPI_LINEAR || EPI == EPI_MUL) {
-        // ---- bf16 outputs, 64-column chunks through swizzled staging + TMA store ---------------------
-        const bool two = (EPI == EPI_SIN) && args.two_out;
-        const bool do_cs = (EPI != EPI_SIN) && args.colsum != nullptr;
-        if (do_cs && t.n_blk != cs_nblk) {
-          cs_flush();
-          cs_nblk = t.n_blk;
-        }
-        const int chunks = args.block_n / 64;
-        for (int c = grp; c < chunks; c += 2, ++cn) {
-          // two outputs: both buffers per chunk; one output: the buffers alternate
-          const uint32_t buf0 = two ? stg0 : stg0 + (cn & 1) * GEMM_STAGING;
-          const uint32_t buf1 = stg0 + GEMM_STAGING;
-          if constexpr (EPI == EPI_MUL) {
-            if (leader) {
-              bulk_wait_read<0>();   // store of chunk cn-1 has drained its buffer ...
-              mul_issue(cn + 1);     // ... which now receives the derivative chunk after this one
-            }
-            mbar_wait(&gmfull[cn & 1], (cn >> 1) & 1);
-          }
-          uint32_t outw[2][16], outc[2][16];  // packed bf16x2 results of the two 32-column halves
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c * 64 + half * 32, v);
-            tc_wait_ld();
-            const int colbase = n0 + c * 64 + half * 32;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t off = row_off + ((((uint32_t)(half * 4 + g)) ^ sw) << 4);
-              float x[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g * 8 + j]);
-              if constexpr (EPI == EPI_MUL) {
-                uint32_t q0, q1, q2, q3;
-                ld_shared_v4(buf0 + off, q0, q1, q2, q3);
-                x[0] *= bf16_lo(q0); x[1] *= bf16_hi(q0); x[2] *= bf16_lo(q1); x[3] *= bf16_hi(q1);
-                x[4] *= bf16_lo(q2); x[5] *= bf16_hi(q2); x[6] *= bf16_lo(q3); x[7] *= bf16_hi(q3);
-                st_shared_v4(buf0 + off, pack_bf16x2(x[0], x[1]), pack_bf16x2(x[2], x[3]),
-                             pack_bf16x2(x[4], x[5]), pack_bf16x2(x[6], x[7]));
-              } else {
-                if (args.bias) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(args.bias + colbase + g * 8));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(args.bias + colbase + g * 8 + 4));
-                  x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                  x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-                }
-                if constexpr (EPI == EPI_SIN) {
-                  if (two) {   // training: h and the derivative w0*cos(.) (2 MUFU ops per element)
-                    float sn[8], cs[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                      const float y = args.w0 * x[j];
-                      sn[j] = __sinf(y);
-                      cs[j] = args.w0 * __cosf(y);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      outw[half][g * 4 + j] = pack_bf16x2(sn[2 * j], sn[2 * j + 1]);
-                      outc[half][g * 4 + j] = pack_bf16x2(cs[2 * j], cs[2 * j + 1]);
-                    }
-                  } else {     // inference: h only
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                      outw[half][g * 4 + j] = pack_bf16x2(__sinf(args.w0 * x[2 * j]), __sinf(args.w0 * x[2 * j + 1]));
-                  }
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) outw[half][g * 4 + j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-                }
-              }
-            }
-          }
-          if constexpr (EPI != EPI_MUL) {
-            // results are in registers: now make sure the previous TMA store(s) of the buffer(s) about
-            // to be overwritten have drained (they had the whole compute phase above to do so)
-            if (leader) {
-              if (two) bulk_wait_read<0>();
-              else bulk_wait_read<1>();
-            }
-            gbar();
-#pragma unroll
-            for (int half = 0; half < 2; ++half)
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint32_t off = row_off + ((((uint32_t)(half * 4 + g)) ^ sw) << 4);
-                st_shared_v4(buf0 + off, outw[half][g * 4], outw[half][g * 4 + 1], outw[half][g * 4 + 2],
-                             outw[half][g * 4 + 3]);
-                if (two)
-                  st_shared_v4(buf1 + off, outc[half][g * 4], outc[half][g * 4 + 1], outc[half][g * 4 + 2],
-                               outc[half][g * 4 + 3]);
-              }
-          }
-          if (do_cs) {
-            gbar();   // every row of the chunk is in the staging buffer
-            float sum = 0.f;
-            const uint32_t cbase = buf0 + (uint32_t)(cs_col & 7) * 2u;
-#pragma unroll 8
-            for (int r = cs_half * 64; r < cs_half * 64 + 64; ++r) {
-              uint16_t hv;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(cbase + (uint32_t)r * 128u + ((((uint32_t)cs_col >> 3) ^ ((uint32_t)r & 7u)) << 4)));
-              sum += __uint_as_float(((uint32_t)hv) << 16);
-            }
-            if (c < 2) cs_acc[0] += sum;
-            else cs_acc[1] += sum;
-          }
-          fence_proxy_async();
-          gbar();
-          if (leader) {
-            tma_store_2d(&args.tmO0, buf0, n0 + c * 64, m0);
-            if (two) tma_store_2d(&args.tmO1, buf1, n0 + c * 64, m0);
-            bulk_commit();
-          }
-        }
-      } else if constexpr (EPI == EPI_HEADOUT) {
+      if constexpr (EPI == EPI_HEADOUT) {
         // ---- N=16 head pre-activations -> packed (P, n_out) fp32 rows (group 0 only) -----------------
         if (grp == 0) {
           uint32_t v[16];
@@ -463,12 +343,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
           }
         }
       }
+      if constexpr (EPI == EPI_WGRAD) {
+        if (args.colsum != nullptr && t.n_blk == 0 && grp == 0) {
+          // bias gradient of this tile's 128 rows: column 0 of the all-ones product
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + 2 * GEMM_MAX_BLOCK_N - 16, v);
+          tc_wait_ld();
+          if (m0 + row < args.M) atomicAdd(args.colsum + m0 + row, __uint_as_float(v[0]));
+        }
+      }
       tc_fence_before();
       if (lead_cta) mbar_arrive(&tempty[acc]);
       else mbar_arrive_remote(&tempty[acc], 0);   // the leader CTA's MMA warp owns the accumulator hand-shake
-    }
-    if constexpr (EPI == EPI_MUL || EPI == EPI_LINEAR) {
-      if (args.colsum != nullptr) cs_flush();
     }
     if (leader) bulk_wait_all();
   }
@@ -605,8 +491,8 @@ int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
                     a.a_stages * GEMM_A_STAGE + a.b_stages * (int)a.b_slot <= GEMM_OPERAND_BYTES,
                 SNB_ERR_INVALID, "gemm: ring depths %d/%d exceed the operand smem", a.a_stages, a.b_stages);
   SNB_CHECK_ARG(a.splits == 1 || epi == EPI_WGRAD, SNB_ERR_INVALID, "gemm: split-K only for the accumulate epilogue");
-  if (epi == EPI_SIN || epi == EPI_LINEAR || epi == EPI_MUL)
-    SNB_CHECK_ARG(a.block_n % 64 == 0, SNB_ERR_UNSUPPORTED, "gemm: bf16 epilogues need block_n %% 64 == 0");
+  SNB_CHECK_ARG(epi == EPI_HEADOUT || epi == EPI_F32ROWS || epi == EPI_WGRAD, SNB_ERR_UNSUPPORTED,
+                "gemm: epilogue %d is served by the chained kernel (k2_chain.cu)", epi);
   if (epi == EPI_HEADOUT || epi == EPI_F32ROWS)
     SNB_CHECK_ARG(a.block_n == 16 && a.n_tiles == 1, SNB_ERR_UNSUPPORTED, "gemm: row epilogues need N == 16");
   const int sms = num_sms();
@@ -614,6 +500,8 @@ int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
   const long long tiles = (long long)a.m_tiles * a.n_tiles * a.splits;
   const int max_units = a.cta_group == 2 ? sms / 2 : sms;
   const int grid = (int)(tiles < max_units ? tiles : max_units);
+  SNB_CHECK_ARG(a.colsum == nullptr || (epi == EPI_WGRAD && tiles <= max_units && a.a_mn), SNB_ERR_UNSUPPORTED,
+                "gemm: the fused column sum needs the wgrad form and at most one tile per scheduling unit");
   SNB_CHECK_ARG(a.b_stages * (int)a.b_slot + a.a_stages * GEMM_A_STAGE <= GEMM_OPERAND_BYTES, SNB_ERR_INVALID,
                 "gemm: rings %d/%d exceed the operand smem", a.a_stages, a.b_stages);
   const double macs = (double)a.m_tiles * GEMM_BLOCK_M * a.cta_group * (double)a.n_tiles * a.block_n * (double)a.kb_total * GEMM_BLOCK_K;
@@ -621,9 +509,6 @@ int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
   int rc;
   const bool two = a.cta_group == 2;
   switch (epi) {
-    case EPI_SIN: rc = two ? launch_epi<EPI_SIN, 2>(a, grid, st) : launch_epi<EPI_SIN, 1>(a, grid, st); break;
-    case EPI_LINEAR: rc = two ? launch_epi<EPI_LINEAR, 2>(a, grid, st) : launch_epi<EPI_LINEAR, 1>(a, grid, st); break;
-    case EPI_MUL: rc = two ? launch_epi<EPI_MUL, 2>(a, grid, st) : launch_epi<EPI_MUL, 1>(a, grid, st); break;
     case EPI_HEADOUT: rc = launch_epi<EPI_HEADOUT, 1>(a, grid, st); break;
     case EPI_F32ROWS: rc = launch_epi<EPI_F32ROWS, 1>(a, grid, st); break;
     case EPI_WGRAD: rc = two ? launch_epi<EPI_WGRAD, 2>(a, grid, st) : launch_epi<EPI_WGRAD, 1>(a, grid, st); break;
@@ -642,6 +527,34 @@ extern "C" int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t 
   using namespace snb;
   SNB_CHECK_ARG(A && B && out0, SNB_ERR_INVALID, "gemm_bf16: null operand");
   SNB_CHECK_ARG(M > 0 && N > 0 && K > 0 && M < (1ll << 31), SNB_ERR_INVALID, "gemm_bf16: bad shape");
+  if (epi == EPI_SIN || epi == EPI_LINEAR || epi == EPI_MUL) {
+    // bf16-output epilogues: a one-layer chain (out1 = the sign mask: written by EPI_SIN, read by EPI_MUL)
+    SNB_CHECK_ARG(splits == 1, SNB_ERR_INVALID, "gemm_bf16: split-K only for the accumulate epilogue");
+    SNB_CHECK_ARG(!a_mn && !b_mn && N % 256 == 0, SNB_ERR_UNSUPPORTED, "gemm_bf16: bf16 epilogues need K-major operands and N %% 256 == 0");
+    SNB_CHECK_ARG(epi != EPI_MUL || mul != nullptr, SNB_ERR_INVALID, "gemm_bf16: mul operand required");
+    ChainArgs* ca = new ChainArgs();
+    memset(ca, 0, sizeof(*ca));
+    ca->M = (int)M;
+    ca->n_blocks = (int)((M + 255) / 256);
+    ca->n_layers = 1;
+    ChainLayer& ly = ca->layers[0];
+    ly.epi = epi;
+    ly.n_tiles = N / 256;
+    ly.nseg = 1;
+    ly.kb_total = ly.seg_kb[0] = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    int r = make_tmap_2d(&ly.tmA[0], A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, GEMM_BLOCK_M);
+    if (!r) r = make_tmap_2d(&ly.tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, 128);
+    if (!r) r = make_tmap_2d(&ly.tmO0, out0, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M);
+    if (!r && epi == EPI_MUL) r = make_tmap_2d(&ly.tmMul, mul, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M);
+    ly.mul_siren = (epi == EPI_MUL && out1 != nullptr) ? 1 : 0;
+    ly.mask = epi == EPI_LINEAR ? nullptr : reinterpret_cast<uint32_t*>(out1);
+    ly.mask_ld = N / 32;
+    ly.bias = bias;
+    ly.w0 = w0;
+    if (!r) r = chain_launch(*ca, (cudaStream_t)stream);
+    delete ca;
+    return r;
+  }
   GemmArgs a;
   memset(&a, 0, sizeof(a));
   a.M = (int)M;
@@ -657,7 +570,6 @@ extern "C" int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t 
   a.splits = splits;
   a.bias = bias;
   a.w0 = w0;
-  a.two_out = (out1 != nullptr);
   a.ldo = ldo;
   int r;
   // K-major operand: [rows, K] box {64 k, rows};  MN-major: [K, rows] box {64 rows, 64 k}
@@ -667,14 +579,7 @@ extern "C" int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t 
   if (!b_mn) r = make_tmap_2d(&a.tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, b_rows);
   else r = make_tmap_2d(&a.tmB, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, 64);
   if (r) return r;
-  if (epi == EPI_SIN || epi == EPI_LINEAR || epi == EPI_MUL) {
-    if ((r = make_tmap_2d(&a.tmO0, out0, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M))) return r;
-    if (out1 && (r = make_tmap_2d(&a.tmO1, out1, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M))) return r;
-    if (epi == EPI_MUL) {
-      SNB_CHECK_ARG(mul != nullptr, SNB_ERR_INVALID, "gemm_bf16: mul operand required");
-      if ((r = make_tmap_2d(&a.tmMul, mul, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M))) return r;
-    }
-  } else if (epi == EPI_F32ROWS) {
+  if (epi == EPI_F32ROWS) {
     a.f32out = (float*)out0;
   } else if (epi == EPI_WGRAD) {
     if (a.block_n >= 32 && N % 32 == 0) {

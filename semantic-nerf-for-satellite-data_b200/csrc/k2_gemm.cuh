@@ -19,9 +19,11 @@
 namespace snb {
 
 enum GemmEpi {
-  EPI_SIN = 0,      // h = sin(w0*(acc+bias)) -> out0 bf16 ; optional out1 = w0*cos(w0*(acc+bias)) bf16
-  EPI_LINEAR = 1,   // acc + bias -> out0 bf16
-  EPI_MUL = 2,      // acc * mul[m,n] -> out0 bf16           (dgrad through the saved SIREN derivative)
+  // bf16-output epilogues: served by the chained kernel (k2_chain.cu), also for single layers
+  EPI_SIN = 0,      // h = sin(w0*(acc+bias)) -> bf16 ; optional sign mask of the derivative w0*cos(w0*(acc+bias))
+  EPI_LINEAR = 1,   // acc + bias -> bf16
+  EPI_MUL = 2,      // acc * mul[m,n] -> bf16, or acc * (SIREN derivative rebuilt from the saved activation + sign mask)
+  // this kernel:
   EPI_HEADOUT = 3,  // N=16 head pre-activations -> packed (P, n_out) fp32 with the reference activations
   EPI_F32ROWS = 4,  // N=16 raw fp32 rows -> f32rows[M,16]
   EPI_WGRAD = 5     // fp32 += acc (split-K): TMA reduce-add (block_n % 32 == 0, >= 32) or red.global
@@ -41,13 +43,16 @@ constexpr int GEMM_STAGING = 16384;                                // one 128 x 
 constexpr int GEMM_NUM_STAGING = 4;
 constexpr int GEMM_EPI_THREADS = 256;  // two epilogue warpgroups
 constexpr int GEMM_THREADS = 96 + GEMM_EPI_THREADS;  // warp 0: A producer, 1: MMA, 2: B producer, 3-10: epilogue
-constexpr int GEMM_SMEM_BYTES = GEMM_OPERAND_BYTES + GEMM_NUM_STAGING * GEMM_STAGING + 512 + 1024;
+constexpr int GEMM_ONES_BYTES = 2048;   // constant all-ones B tile (16 x 64 bf16) of the bias-gradient MMA
+constexpr int GEMM_LAYOUT_BYTES = GEMM_OPERAND_BYTES + GEMM_NUM_STAGING * GEMM_STAGING + GEMM_ONES_BYTES + 512;
+// the dynamic shared memory is declared 1024-byte aligned; the kernel still rounds its base up and traps if the
+// layout would not fit (512 bytes of slack are left below the 227 KB limit)
+constexpr int GEMM_SMEM_BYTES = GEMM_LAYOUT_BYTES + 512;
 
 struct GemmArgs {
   CUtensorMap tmA[3];
   CUtensorMap tmB;
-  CUtensorMap tmO0, tmO1;
-  CUtensorMap tmMul;
+  CUtensorMap tmO0;
   int seg_kb[3];
   int nseg;
   int kb_total;
@@ -59,14 +64,15 @@ struct GemmArgs {
   int a_stages, b_stages;  // ring depths: a_stages*16 KB + b_stages*b_slot <= GEMM_OPERAND_BYTES
   int cta_group;           // 1, or 2 = SM pair per 256 x block_n tile (set before building tmB: its box is block_n/cta_group rows)
   unsigned b_slot;         // bytes per B ring slot
-  int two_out;
   const float* bias;
   float w0;
-  float* colsum;  // EPI_MUL / EPI_LINEAR: if set, colsum[n] += sum over rows of the bf16 output (bias gradient)
   // EPI_HEADOUT
   float* out_packed;
   const float* sky;
   int n_out, rows_per_ray, n_classes, sem_sigmoid, head_mask;
+  // EPI_WGRAD: if set, colsum[m] += sum over the K (sample) dimension of A[:, m] - the bias gradient rides the weight
+  // gradient GEMM as one extra N = 16 MMA per k-block against a constant all-ones tile (n-block 0 tiles only)
+  float* colsum;
   // EPI_F32ROWS / small-N EPI_WGRAD
   float* f32out;
   long long ldo;

@@ -392,7 +392,7 @@ static int run_jobs(const std::vector<PackJob>& jobs, bool unpack, const float* 
 // ---- workspace layout -----------------------------------------------------------------------------
 struct Workspace {
   // all offsets in bytes from the workspace base; 0-sized members are absent
-  size_t h[8], c[8], f, hh, chh, s2, cs2, s3, cs3;  // forward (c*: saved SIREN derivatives, train only)
+  size_t h[8], sg[8], f, hh, sghh, s2, sgs2, s3, sgs3;  // forward (sg*: sign masks of the SIREN derivatives, train only)
   size_t dpre, dy[8], df, dyhh, dys3, dys2;         // backward (dy[i] = gradient w.r.t. the pre-activation of trunk layer i)
   size_t scr_h[2], scr_f, scr_s2;                   // inference: per-SM-pair scratch of the chained kernel (L2-resident)
   size_t gscratch;                                  // fp32 packed gradients
@@ -420,7 +420,7 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
   const size_t rowF = (size_t)P * F * 2, rowFL = (size_t)P * FL * 2, rowHH = (size_t)P * m->hhw * 2;
   if (train) {
     for (int i = 0; i < 8; ++i) w.h[i] = take_b(rowF);
-    for (int i = 0; i < 8; ++i) w.c[i] = take_b(rowF);
+    for (int i = 0; i < 8; ++i) w.sg[i] = take_b((size_t)P * (F / 8));   // 1 bit per element
   } else {
     size_t a = take_b(rowF), b = take_b(rowF);
     for (int i = 0; i < 8; ++i) w.h[i] = (i & 1) ? b : a;  // ping-pong (layer 4 reads h3, writes h4: distinct)
@@ -437,9 +437,9 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
   w.s2 = take_b(rowFL);
   w.s3 = take_b(rowFL);
   if (train) {
-    w.chh = take_b(rowHH);
-    w.cs2 = take_b(rowFL);
-    w.cs3 = take_b(rowFL);
+    w.sghh = take_b((size_t)P * (m->hhw / 8));
+    w.sgs2 = take_b((size_t)P * (FL / 8));
+    w.sgs3 = take_b((size_t)P * (FL / 8));
     w.dpre = take_b((size_t)P * 16 * 2);
     for (int i = 0; i < 8; ++i) w.dy[i] = take_b(rowF);
     w.df = take_b(rowF);
@@ -475,15 +475,14 @@ struct Plan {
   }
 };
 
-// D[M,N] = sum_seg A_seg[M,K] * B[N,Kp]^T  (K-major operands)
-static GemmArgs& add_kmajor(Plan& p, int epi, long long M, int N, const Seg* segs, int nseg, const void* B, long long ldb,
-                            int b_cols, void* out0, void* out1, long long ldo, const void* mul, long long ldmul,
-                            const float* bias, float w0, float* colsum = nullptr) {
+// D[M,16] = sum_seg A_seg[M,K] * B[16,Kp]^T  (K-major operands; the N = 16 row epilogues HEADOUT / F32ROWS)
+static GemmArgs& add_rows16(Plan& p, int epi, long long M, const Seg* segs, int nseg, const void* B, long long ldb, int b_cols,
+                            const float* bias) {
   GemmArgs& a = p.add(epi);
   a.M = (int)M;
-  a.N = N;
-  a.block_n = N >= 256 ? 256 : N;
-  a.cta_group = gemm_pick_cta_group(epi, M, N, a.block_n);
+  a.N = 16;
+  a.block_n = 16;
+  a.cta_group = 1;
   a.nseg = nseg;
   a.kb_total = 0;
   for (int s = 0; s < nseg; ++s) {
@@ -492,25 +491,18 @@ static GemmArgs& add_kmajor(Plan& p, int epi, long long M, int N, const Seg* seg
     p.chk(make_tmap_2d(&a.tmA[s], segs[s].ptr, 2, (uint64_t)segs[s].cols, (uint64_t)M, (uint64_t)segs[s].ld * 2, 64,
                        GEMM_BLOCK_M));
   }
-  p.chk(make_tmap_2d(&a.tmB, B, 2, (uint64_t)b_cols, (uint64_t)N, (uint64_t)ldb * 2, 64, (uint32_t)(a.block_n / a.cta_group)));
-  if (epi == EPI_SIN || epi == EPI_LINEAR || epi == EPI_MUL) {
-    p.chk(make_tmap_2d(&a.tmO0, out0, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
-    if (out1) p.chk(make_tmap_2d(&a.tmO1, out1, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
-    if (epi == EPI_MUL)
-      p.chk(make_tmap_2d(&a.tmMul, mul, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldmul * 2, 64, GEMM_BLOCK_M));
-  }
-  a.two_out = out1 != nullptr;
+  p.chk(make_tmap_2d(&a.tmB, B, 2, (uint64_t)b_cols, (uint64_t)16, (uint64_t)ldb * 2, 64, 16));
   a.bias = bias;
-  a.w0 = w0;
-  a.colsum = colsum;
+  a.w0 = 1.0f;
   a.splits = 1;
   gemm_finalize(a);
   return a;
 }
 
 // G[Mf,Nf] += dY[P,Mf]^T * X[P,Nf]   (reduction over the P samples; MN-major operands; split-K)
+// colsum (optional): [Mf] += column sums of dY over the samples = the bias gradient, computed by the same launch
 static void add_wgrad(Plan& p, int Mf, int Nf, const void* dY, long long ld_dy, const void* X, long long ld_x,
-                      long long P, float* G, long long ldg, int sms) {
+                      long long P, float* G, long long ldg, int sms, float* colsum = nullptr) {
   GemmArgs& a = p.add(EPI_WGRAD);
   a.M = Mf;
   a.N = Nf;
@@ -536,6 +528,7 @@ static void add_wgrad(Plan& p, int Mf, int Nf, const void* dY, long long ld_dy, 
   // keep at least 4 k-blocks per split so the accumulate traffic stays small against the operand reads
   const int max_splits = a.kb_total / 4 > 0 ? a.kb_total / 4 : 1;
   a.splits = splits < max_splits ? splits : max_splits;
+  a.colsum = colsum;
   gemm_finalize(a);
 }
 
@@ -559,8 +552,9 @@ struct CSeg {
 struct ChainPlan {
   ChainArgs a;
   int rc = 0;
-  int n_cs = 0;
-  ChainPlan(long long P) {
+  bool per_layer;     // one launch per layer (snb_set_chained_mlp(0)) instead of one per pass
+  cudaStream_t st;
+  ChainPlan(long long P, bool chained, cudaStream_t stream) : per_layer(!chained), st(stream) {
     memset(&a, 0, sizeof(a));
     a.M = (int)P;
     a.n_blocks = (int)((P + 255) / 256);
@@ -568,10 +562,12 @@ struct ChainPlan {
   void chk(int r) {
     if (r && !rc) rc = r;
   }
-  // D[rows, N] = epilogue(sum_seg A_seg * B[N, Kp]^T); N % 256 == 0
-  void add(int epi, int N, const CSeg* segs, int nseg, const void* B, long long ldb, int b_cols, void* out0, void* out1,
-           long long ldo, long long o_rows, int o_scratch, const void* mul, long long ldmul, const float* bias, float w0,
-           float* colsum) {
+  // D[rows, N] = epilogue(sum_seg A_seg * B[N, Kp]^T); N % 256 == 0.
+  //   EPI_SIN:  out0 = sin(w0 (acc + bias)); mask (optional) receives the sign bits of the derivative
+  //   EPI_MUL:  out0 = acc * mul, or (mask != NULL) acc * w0 * (+-)sqrt(1 - mul^2): `mul` is then the saved activation
+  void add(int epi, int N, const CSeg* segs, int nseg, const void* B, long long ldb, int b_cols, void* out0, long long ldo,
+           long long o_rows, int o_scratch, const void* mul, long long ldmul, uint32_t* mask, int mask_ld, const float* bias,
+           float w0) {
     if (a.n_layers >= CHAIN_MAX_LAYERS || N % 256 != 0 || nseg > 3) {
       set_error("chain plan: layer %d unsupported (N %d, %d segments)", a.n_layers, N, nseg);
       chk(SNB_ERR_UNSUPPORTED);
@@ -584,25 +580,29 @@ struct ChainPlan {
     ly.kb_total = 0;
     for (int s = 0; s < nseg; ++s) {
       ly.seg_kb[s] = segs[s].kb;
-      ly.a_scratch[s] = segs[s].scratch;
+      ly.a_scratch[s] = per_layer ? 0 : segs[s].scratch;
       ly.kb_total += segs[s].kb;
       chk(make_tmap_2d(&ly.tmA[s], segs[s].ptr, 2, (uint64_t)segs[s].cols, (uint64_t)segs[s].rows, (uint64_t)segs[s].ld * 2, 64,
                        GEMM_BLOCK_M));
     }
     chk(make_tmap_2d(&ly.tmB, B, 2, (uint64_t)b_cols, (uint64_t)N, (uint64_t)ldb * 2, 64, 128));
     chk(make_tmap_2d(&ly.tmO0, out0, 2, (uint64_t)N, (uint64_t)o_rows, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
-    if (out1) chk(make_tmap_2d(&ly.tmO1, out1, 2, (uint64_t)N, (uint64_t)o_rows, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
     if (epi == EPI_MUL) chk(make_tmap_2d(&ly.tmMul, mul, 2, (uint64_t)N, (uint64_t)a.M, (uint64_t)ldmul * 2, 64, GEMM_BLOCK_M));
-    ly.two_out = out1 != nullptr;
+    ly.mul_siren = (epi == EPI_MUL && mask != nullptr) ? 1 : 0;
+    ly.mask = mask;
+    ly.mask_ld = mask_ld;
     ly.o_scratch = o_scratch;
     ly.bias = bias;
     ly.w0 = w0;
-    ly.colsum = colsum;
-    ly.cs_slot = colsum ? n_cs++ : -1;
+    if (per_layer) flush();
   }
-  int run(cudaStream_t st) {
-    if (rc) return rc;
-    return chain_launch(a, st);
+  void flush() {
+    if (!rc && a.n_layers > 0) chk(chain_launch(a, st));
+    a.n_layers = 0;
+  }
+  int run() {
+    flush();
+    return rc;
   }
 };
 
@@ -697,33 +697,35 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
   const __nv_bfloat16* pk = reinterpret_cast<const __nv_bfloat16*>(packed);
   const float* pb = reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + (size_t)m->packed_bf16_elems * 2);
   auto H = [&](int i) { return (void*)(ws + w.h[i]); };
-  auto Cs = [&](int i) { return train ? (void*)(ws + w.c[i]) : (void*)nullptr; };
   const int hhw = m->hhw;
   const bool need_f = head_mask != SNB_HEADS_DEPTH;
   const bool all = head_mask == SNB_HEADS_ALL;
   Plan p;
-  if (use_chain()) {
-    // one persistent launch: trunk + feats + head first layers + sun layers; inter-layer activations stay in L2
-    ChainPlan cp(P);
+  {
+    // trunk + feats + head first layers + sun layers.  Chained (default): one persistent launch, inter-layer
+    // activations are read back from L2 and, in inference, live in a per-SM-pair scratch that never reaches HBM.
+    const bool chained = use_chain();
+    ChainPlan cp(P, chained, (cudaStream_t)stream);
     const long long R = chain_scratch_rows();
-    const bool scr = !train;   // inference: layers 0..6, f, s2 in the per-pair scratch
+    const bool scr = !train && chained;   // inference: layers 0..6, f, s2 in the per-pair scratch
     auto hbuf = [&](int i) { return scr && i < 7 ? (void*)(ws + w.scr_h[i & 1]) : H(i); };
     auto hrows = [&](int i) { return scr && i < 7 ? R : P; };
     auto hscr = [&](int i) { return scr && i < 7 ? 1 : 0; };
+    auto SG = [&](int i) { return train ? reinterpret_cast<uint32_t*>(ws + w.sg[i]) : (uint32_t*)nullptr; };
     {
+      // semantic: the 128-column row is read twice ([hi|lo|0] then its first 64 columns again, against W_lo)
       CSeg s0[2] = {{enc, m->enc_ld, m->enc_ld, m->enc_ld / 64, P, 0}, {enc, m->enc_ld, 64, 1, P, 0}};
-      cp.add(EPI_SIN, F, s0, m->kind == SNB_MODEL_SEMANTIC ? 2 : 1, pk + m->wl[0], m->w0_ld, m->w0_ld, hbuf(0), Cs(0), F,
-             hrows(0), hscr(0), nullptr, 0, pb + m->bl[0], 30.0f, nullptr);
+      cp.add(EPI_SIN, F, s0, m->kind == SNB_MODEL_SEMANTIC ? 2 : 1, pk + m->wl[0], m->w0_ld, m->w0_ld, hbuf(0), F, hrows(0), hscr(0),
+             nullptr, 0, SG(0), F / 32, pb + m->bl[0], 30.0f);
     }
     for (int i = 1; i < LAYERS; ++i) {
-      if (i == 4) {
+      if (i == 4) {   // skip connection cat(enc, h3) as two K-segments
         CSeg s[2] = {{enc, m->enc_ld, 64, 1, P, 0}, {hbuf(3), F, F, F / 64, hrows(3), hscr(3)}};
-        cp.add(EPI_SIN, F, s, 2, pk + m->wl[4], 64 + F, 64 + F, hbuf(4), Cs(4), F, hrows(4), hscr(4), nullptr, 0, pb + m->bl[4],
-               1.0f, nullptr);
+        cp.add(EPI_SIN, F, s, 2, pk + m->wl[4], 64 + F, 64 + F, hbuf(4), F, hrows(4), hscr(4), nullptr, 0, SG(4), F / 32,
+               pb + m->bl[4], 1.0f);
       } else {
         CSeg s[1] = {{hbuf(i - 1), F, F, F / 64, hrows(i - 1), hscr(i - 1)}};
-        cp.add(EPI_SIN, F, s, 1, pk + m->wl[i], F, F, hbuf(i), Cs(i), F, hrows(i), hscr(i), nullptr, 0, pb + m->bl[i], 1.0f,
-               nullptr);
+        cp.add(EPI_SIN, F, s, 1, pk + m->wl[i], F, F, hbuf(i), F, hrows(i), hscr(i), nullptr, 0, SG(i), F / 32, pb + m->bl[i], 1.0f);
       }
     }
     if (need_f) {
@@ -732,57 +734,25 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
       const long long srows = scr ? R : P;
       const int sflag = scr ? 1 : 0;
       CSeg s[1] = {{H(7), F, F, F / 64, P, 0}};
-      cp.add(EPI_LINEAR, F, s, 1, pk + m->wf, F, F, fbuf, nullptr, F, srows, sflag, nullptr, 0, pb + m->bfe, 1.0f, nullptr);
+      cp.add(EPI_LINEAR, F, s, 1, pk + m->wf, F, F, fbuf, F, srows, sflag, nullptr, 0, nullptr, 0, pb + m->bfe, 1.0f);
+      // fused head first layers (all blocks, or only the sun block for the solar pass)
       const int r0 = all ? 0 : m->hh_sun, n = all ? hhw : FL;
       CSeg s1[2] = {{fbuf, F, F, F / 64, srows, sflag}, {aux, 16, 16, 1, P, 0}};
-      cp.add(EPI_SIN, n, s1, 2, pk + m->wh1 + (long long)r0 * (F + 64), F + 64, F + 64, ws + w.hh + (size_t)r0 * 2,
-             train ? ws + w.chh + (size_t)r0 * 2 : nullptr, hhw, P, 0, nullptr, 0, nullptr, 1.0f, nullptr);
+      cp.add(EPI_SIN, n, s1, 2, pk + m->wh1 + (long long)r0 * (F + 64), F + 64, F + 64, ws + w.hh + (size_t)r0 * 2, hhw, P, 0,
+             nullptr, 0, train ? reinterpret_cast<uint32_t*>(ws + w.sghh) + r0 / 32 : nullptr, hhw / 32, nullptr, 1.0f);
       CSeg s2[1] = {{ws + w.hh + (size_t)m->hh_sun * 2, hhw, FL, FL / 64, P, 0}};
-      cp.add(EPI_SIN, FL, s2, 1, pk + m->ws2, FL, FL, s2buf, train ? ws + w.cs2 : nullptr, FL, srows, sflag, nullptr, 0,
-             pb + m->bs2, 1.0f, nullptr);
+      cp.add(EPI_SIN, FL, s2, 1, pk + m->ws2, FL, FL, s2buf, FL, srows, sflag, nullptr, 0,
+             train ? reinterpret_cast<uint32_t*>(ws + w.sgs2) : nullptr, FL / 32, pb + m->bs2, 1.0f);
       CSeg s3[1] = {{s2buf, FL, FL, FL / 64, srows, sflag}};
-      cp.add(EPI_SIN, FL, s3, 1, pk + m->ws4, FL, FL, ws + w.s3, train ? ws + w.cs3 : nullptr, FL, P, 0, nullptr, 0, pb + m->bs4,
-             1.0f, nullptr);
+      cp.add(EPI_SIN, FL, s3, 1, pk + m->ws4, FL, FL, ws + w.s3, FL, P, 0, nullptr, 0,
+             train ? reinterpret_cast<uint32_t*>(ws + w.sgs3) : nullptr, FL / 32, pb + m->bs4, 1.0f);
     }
-    if (int r = cp.run((cudaStream_t)stream)) return r;
-  } else {
-  // trunk ----------------------------------------------------------------------------------------
-  {
-    // semantic: the 128-column row is read twice ([hi|lo|0] then its first 64 columns again, against W_lo)
-    Seg s0[2] = {{enc, m->enc_ld, m->enc_ld, m->enc_ld / 64}, {enc, m->enc_ld, 64, 1}};
-    add_kmajor(p, EPI_SIN, P, F, s0, m->kind == SNB_MODEL_SEMANTIC ? 2 : 1, pk + m->wl[0], m->w0_ld, m->w0_ld, H(0), Cs(0), F,
-               nullptr, 0, pb + m->bl[0], 30.0f);
+    if (int r = cp.run()) return r;
   }
-  for (int i = 1; i < LAYERS; ++i) {
-    if (i == 4) {
-      Seg s[2] = {{enc, m->enc_ld, 64, 1}, {H(3), F, F, F / 64}};
-      add_kmajor(p, EPI_SIN, P, F, s, 2, pk + m->wl[4], 64 + F, 64 + F, H(4), Cs(4), F, nullptr, 0, pb + m->bl[4], 1.0f);
-    } else {
-      Seg s[1] = {{H(i - 1), F, F, F / 64}};
-      add_kmajor(p, EPI_SIN, P, F, s, 1, pk + m->wl[i], F, F, H(i), Cs(i), F, nullptr, 0, pb + m->bl[i], 1.0f);
-    }
-  }
-  if (need_f) {
-    Seg s[1] = {{H(7), F, F, F / 64}};
-    add_kmajor(p, EPI_LINEAR, P, F, s, 1, pk + m->wf, F, F, ws + w.f, nullptr, F, nullptr, 0, pb + m->bfe, 1.0f);
-    // fused head first layers (all blocks, or only the sun block for the solar pass)
-    const int r0 = all ? 0 : m->hh_sun, n = all ? hhw : FL;
-    Seg s1[2] = {{ws + w.f, F, F, F / 64}, {aux, 16, 16, 1}};
-    add_kmajor(p, EPI_SIN, P, n, s1, 2, pk + m->wh1 + (long long)r0 * (F + 64), F + 64, F + 64,
-               ws + w.hh + (size_t)r0 * 2, train ? ws + w.chh + (size_t)r0 * 2 : nullptr, hhw, nullptr, 0, nullptr, 1.0f);
-    Seg s2[1] = {{ws + w.hh + (size_t)m->hh_sun * 2, hhw, FL, FL / 64}};
-    add_kmajor(p, EPI_SIN, P, FL, s2, 1, pk + m->ws2, FL, FL, ws + w.s2, train ? ws + w.cs2 : nullptr, FL, nullptr, 0,
-               pb + m->bs2, 1.0f);
-    Seg s3[1] = {{ws + w.s2, FL, FL, FL / 64}};
-    add_kmajor(p, EPI_SIN, P, FL, s3, 1, pk + m->ws4, FL, FL, ws + w.s3, train ? ws + w.cs3 : nullptr, FL, nullptr, 0,
-               pb + m->bs4, 1.0f);
-  }
-  }   // per-layer launches
   {
     Seg s[3] = {{H(7), F, F, F / 64}, {ws + w.s3, FL, FL, FL / 64}, {ws + w.hh, hhw, hhw, hhw / 64}};
     const int nseg = head_mask == SNB_HEADS_DEPTH ? 1 : (all ? 3 : 2);
-    GemmArgs& a = add_kmajor(p, EPI_HEADOUT, P, 16, s, nseg, pk + m->who, m->kho, m->kho, nullptr, nullptr, 0, nullptr, 0,
-                             pb + m->bho, 1.0f);
+    GemmArgs& a = add_rows16(p, EPI_HEADOUT, P, s, nseg, pk + m->who, m->kho, m->kho, pb + m->bho);
     a.out_packed = out;
     a.sky = sky;
     a.n_out = m->n_out;
@@ -812,7 +782,6 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
   const __nv_bfloat16* pk = reinterpret_cast<const __nv_bfloat16*>(packed);
   float* gs = reinterpret_cast<float*>(ws + w.gscratch);
   auto H = [&](int i) { return (void*)(ws + w.h[i]); };
-  auto Cs = [&](int i) { return (void*)(ws + w.c[i]); };
   const int hhw = m->hhw;
   const bool all = head_mask == SNB_HEADS_ALL;
   const bool solar = head_mask == SNB_HEADS_SOLAR;
@@ -831,88 +800,67 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
   Plan p;
   const int r0 = all ? 0 : m->hh_sun, nh = all ? hhw : FL;
   const char* dyhh_r0 = ws + w.dyhh + (size_t)r0 * 2;
-  Seg sdpre[1] = {{dpre, 16, 16, 1}};
   // ---- dgrad: the gradient w.r.t. every pre-activation, from the heads back to trunk layer 0 ---------------
-  if (use_chain()) {
-    // one persistent launch; each dY is read back from L2 by the next step of the same SM pair
-    ChainPlan cp(P);
+  {
+    // chained (default): one persistent launch; each dY is read back from L2 by the next step of the same SM pair.
+    // The SIREN derivative w0 cos(.) is rebuilt in the epilogue from the saved activation and its sign mask.
+    ChainPlan cp(P, use_chain(), st);
+    auto SG = [&](int i) { return reinterpret_cast<uint32_t*>(ws + w.sg[i]); };
+    uint32_t* sghh = reinterpret_cast<uint32_t*>(ws + w.sghh);
     CSeg cdpre[1] = {{dpre, 16, 16, 1, P, 0}};
     if (!depth) {
       // sun head: s3 <- head output, then back through sun.4, sun.2 into the sun block of hh
-      cp.add(EPI_MUL, FL, cdpre, 1, pk + m->tho, 16, 16, ws + w.dys3, nullptr, FL, P, 0, ws + w.cs3, FL, nullptr, 1.0f, gs + m->gbs4);
+      cp.add(EPI_MUL, FL, cdpre, 1, pk + m->tho, 16, 16, ws + w.dys3, FL, P, 0, ws + w.s3, FL,
+             reinterpret_cast<uint32_t*>(ws + w.sgs3), FL / 32, nullptr, 1.0f);
       if (all)  // rgb / beta / sem blocks of hh (columns [0, hhw-256))
-        cp.add(EPI_MUL, hhw - FL, cdpre, 1, pk + m->tho + (long long)FL * 16, 16, 16, ws + w.dyhh, nullptr, hhw, P, 0, ws + w.chh,
-               hhw, nullptr, 1.0f, nullptr);
+        cp.add(EPI_MUL, hhw - FL, cdpre, 1, pk + m->tho + (long long)FL * 16, 16, 16, ws + w.dyhh, hhw, P, 0, ws + w.hh, hhw, sghh,
+               hhw / 32, nullptr, 1.0f);
       CSeg c3[1] = {{ws + w.dys3, FL, FL, FL / 64, P, 0}};
-      cp.add(EPI_MUL, FL, c3, 1, pk + m->ts4, FL, FL, ws + w.dys2, nullptr, FL, P, 0, ws + w.cs2, FL, nullptr, 1.0f, gs + m->gbs2);
+      cp.add(EPI_MUL, FL, c3, 1, pk + m->ts4, FL, FL, ws + w.dys2, FL, P, 0, ws + w.s2, FL,
+             reinterpret_cast<uint32_t*>(ws + w.sgs2), FL / 32, nullptr, 1.0f);
       CSeg c2[1] = {{ws + w.dys2, FL, FL, FL / 64, P, 0}};
-      cp.add(EPI_MUL, FL, c2, 1, pk + m->ts2, FL, FL, ws + w.dyhh + (size_t)m->hh_sun * 2, nullptr, hhw, P, 0,
-             ws + w.chh + (size_t)m->hh_sun * 2, hhw, nullptr, 1.0f, nullptr);
+      cp.add(EPI_MUL, FL, c2, 1, pk + m->ts2, FL, FL, ws + w.dyhh + (size_t)m->hh_sun * 2, hhw, P, 0,
+             ws + w.hh + (size_t)m->hh_sun * 2, hhw, sghh + m->hh_sun / 32, hhw / 32, nullptr, 1.0f);
       CSeg ch[1] = {{dyhh_r0, hhw, nh, nh / 64, P, 0}};
-      cp.add(EPI_LINEAR, F, ch, 1, pk + m->th1 + r0, hhw, nh, ws + w.df, nullptr, F, P, 0, nullptr, 0, nullptr, 1.0f, gs + m->gbf);
+      cp.add(EPI_LINEAR, F, ch, 1, pk + m->th1 + r0, hhw, nh, ws + w.df, F, P, 0, nullptr, 0, nullptr, 0, nullptr, 1.0f);
+      // dY7 = ([dF | dPre16] * [Wf ; w_sigma]) * c7
       CSeg c7[2] = {{ws + w.df, F, F, F / 64, P, 0}, {dpre, 16, 16, 1, P, 0}};
-      cp.add(EPI_MUL, F, c7, 2, pk + m->tf, F + 64, F + 64, DY(7), nullptr, F, P, 0, Cs(7), F, nullptr, 1.0f, gs + m->gbl[7]);
+      cp.add(EPI_MUL, F, c7, 2, pk + m->tf, F + 64, F + 64, DY(7), F, P, 0, H(7), F, SG(7), F / 32, nullptr, 1.0f);
     } else {
-      cp.add(EPI_MUL, F, cdpre, 1, pk + m->tf + F, F + 64, 64, DY(7), nullptr, F, P, 0, Cs(7), F, nullptr, 1.0f, gs + m->gbl[7]);
+      cp.add(EPI_MUL, F, cdpre, 1, pk + m->tf + F, F + 64, 64, DY(7), F, P, 0, H(7), F, SG(7), F / 32, nullptr, 1.0f);
     }
     for (int i = LAYERS - 1; i > 0; --i) {
-      // dY_{i-1} = (dY_i W_i) * c_{i-1}; its column sums are the bias gradient of layer i-1
+      // dY_{i-1} = (dY_i W_i) * c_{i-1}
       CSeg c[1] = {{DY(i), F, F, F / 64, P, 0}};
-      cp.add(EPI_MUL, F, c, 1, pk + m->tl[i], F, F, DY(i - 1), nullptr, F, P, 0, Cs(i - 1), F, nullptr, 1.0f, gs + m->gbl[i - 1]);
+      cp.add(EPI_MUL, F, c, 1, pk + m->tl[i], F, F, DY(i - 1), F, P, 0, H(i - 1), F, SG(i - 1), F / 32, nullptr,
+             i - 1 == 0 ? 30.0f : 1.0f);
     }
-    if (int r = cp.run(st)) return r;
-  } else {
-    if (!depth) {
-      add_kmajor(p, EPI_MUL, P, FL, sdpre, 1, pk + m->tho, 16, 16, ws + w.dys3, nullptr, FL, ws + w.cs3, FL, nullptr, 1.0f,
-                 gs + m->gbs4);
-      if (all)
-        add_kmajor(p, EPI_MUL, P, hhw - FL, sdpre, 1, pk + m->tho + (long long)FL * 16, 16, 16, ws + w.dyhh, nullptr, hhw,
-                   ws + w.chh, hhw, nullptr, 1.0f);
-      Seg s3[1] = {{ws + w.dys3, FL, FL, FL / 64}};
-      add_kmajor(p, EPI_MUL, P, FL, s3, 1, pk + m->ts4, FL, FL, ws + w.dys2, nullptr, FL, ws + w.cs2, FL, nullptr, 1.0f,
-                 gs + m->gbs2);
-      Seg s2[1] = {{ws + w.dys2, FL, FL, FL / 64}};
-      add_kmajor(p, EPI_MUL, P, FL, s2, 1, pk + m->ts2, FL, FL, ws + w.dyhh + (size_t)m->hh_sun * 2, nullptr, hhw,
-                 ws + w.chh + (size_t)m->hh_sun * 2, hhw, nullptr, 1.0f);
-      Seg sh[1] = {{dyhh_r0, hhw, nh, nh / 64}};
-      add_kmajor(p, EPI_LINEAR, P, F, sh, 1, pk + m->th1 + r0, hhw, nh, ws + w.df, nullptr, F, nullptr, 0, nullptr, 1.0f,
-                 gs + m->gbf);
-      Seg s[2] = {{ws + w.df, F, F, F / 64}, {dpre, 16, 16, 1}};
-      add_kmajor(p, EPI_MUL, P, F, s, 2, pk + m->tf, F + 64, F + 64, DY(7), nullptr, F, Cs(7), F, nullptr, 1.0f, gs + m->gbl[7]);
-    } else {
-      add_kmajor(p, EPI_MUL, P, F, sdpre, 1, pk + m->tf + F, F + 64, 64, DY(7), nullptr, F, Cs(7), F, nullptr, 1.0f,
-                 gs + m->gbl[7]);
-    }
-    for (int i = LAYERS - 1; i > 0; --i) {
-      Seg s[1] = {{DY(i), F, F, F / 64}};
-      add_kmajor(p, EPI_MUL, P, F, s, 1, pk + m->tl[i], F, F, DY(i - 1), nullptr, F, Cs(i - 1), F, nullptr, 1.0f,
-                 gs + m->gbl[i - 1]);
-    }
+    if (int r = cp.run()) return r;
   }
   // ---- wgrad: every weight gradient is dY^T x (layer input), split-K over the samples -----------------------
   add_wgrad(p, F, 16, H(7), F, dpre, 16, P, gs + m->ghot, 16, sms);
   if (!depth) add_wgrad(p, FL, 16, ws + w.s3, FL, dpre, 16, P, gs + m->ghot + (long long)F * 16, 16, sms);
   if (all) add_wgrad(p, hhw, 16, ws + w.hh, hhw, dpre, 16, P, gs + m->ghot + (long long)(F + FL) * 16, 16, sms);
   if (!depth) {
-    add_wgrad(p, FL, FL, ws + w.dys3, FL, ws + w.s2, FL, P, gs + m->gs4, FL, sms);
-    add_wgrad(p, FL, FL, ws + w.dys2, FL, ws + w.hh + (size_t)m->hh_sun * 2, hhw, P, gs + m->gs2, FL, sms);
+    add_wgrad(p, FL, FL, ws + w.dys3, FL, ws + w.s2, FL, P, gs + m->gs4, FL, sms, gs + m->gbs4);
+    add_wgrad(p, FL, FL, ws + w.dys2, FL, ws + w.hh + (size_t)m->hh_sun * 2, hhw, P, gs + m->gs2, FL, sms, gs + m->gbs2);
     // fused head first layers: weight / bias / per-ray-column gradients
     add_wgrad(p, nh, F, dyhh_r0, hhw, ws + w.f, F, P, gs + m->gh1 + (long long)r0 * F, F, sms);
     add_wgrad(p, nh, 16, dyhh_r0, hhw, aux, 16, P, gs + m->gh1aux + (long long)r0 * 16, 16, sms);
     if (all && g_aux) {
       // d aux = dY_beta * W_beta0[:, 512:]  -> embedding gradient (summed per ray by the caller-side kernel)
       Seg sb[1] = {{ws + w.dyhh + (size_t)m->hh_beta * 2, hhw, FL, FL / 64}};
-      GemmArgs& a = add_kmajor(p, EPI_F32ROWS, P, 16, sb, 1, pk + m->taux, FL, FL, nullptr, nullptr, 0, nullptr, 0, nullptr, 1.0f);
+      GemmArgs& a = add_rows16(p, EPI_F32ROWS, P, sb, 1, pk + m->taux, FL, FL, nullptr);
       a.f32out = g_aux;
       a.ldo = 16;
     }
-    add_wgrad(p, F, F, ws + w.df, F, H(7), F, P, gs + m->gf, F, sms);
+    add_wgrad(p, F, F, ws + w.df, F, H(7), F, P, gs + m->gf, F, sms, gs + m->gbf);
   }
   for (int i = LAYERS - 1; i >= 0; --i) {
     if (i == 0) {
-      add_wgrad(p, F, 64, DY(0), F, enc, m->enc_ld, P, gs + m->gl[0], 64, sms);
+      add_wgrad(p, F, 64, DY(0), F, enc, m->enc_ld, P, gs + m->gl[0], 64, sms, gs + m->gbl[0]);
     } else {
-      add_wgrad(p, F, F, DY(i), F, H(i - 1), F, P, gs + m->gl[i], F, sms);
+      add_wgrad(p, F, F, DY(i), F, H(i - 1), F, P, gs + m->gl[i], F, sms, gs + m->gbl[i]);
       if (i == 4) add_wgrad(p, F, 64, DY(4), F, enc, m->enc_ld, P, gs + m->gl4e, 64, sms);
     }
   }

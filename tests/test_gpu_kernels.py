@@ -33,18 +33,34 @@ def test_gemm_kmajor_epilogues(M, N, K):
                             1.0, 1, stream()), "linear")
     # fp32 accumulation of exact bf16 products: only the final bf16 rounding (2^-9 relative) differs
     assert (out.float() - (ref + bias)).abs().max() <= 2 ** -8 * (ref + bias).abs().max()
-    o0, o1 = torch.zeros_like(out), torch.zeros_like(out)
-    check(lib.snb_gemm_bf16(ptr(A), K, ptr(B), K, M, N, K, 0, 0, _lib.EPI_SIN, ptr(o0), ptr(o1), N, None, ptr(bias),
+    o0 = torch.zeros_like(out)
+    sgn = torch.zeros(M, N // 32, device=DEV, dtype=torch.int32)
+    check(lib.snb_gemm_bf16(ptr(A), K, ptr(B), K, M, N, K, 0, 0, _lib.EPI_SIN, ptr(o0), ptr(sgn), N, None, ptr(bias),
                             3.0, 1, stream()), "sin")
     y = 3.0 * (ref + bias)
     assert (o0.float() - torch.sin(y)).abs().max() <= 2 ** -8 + 1e-4            # bf16 rounding of |sin| <= 1
-    assert (o1.float() - 3.0 * torch.cos(y)).abs().max() <= 3 * 2 ** -8 + 3e-4
+    # the sign mask of the derivative: [cos(y) < 0], one word per 32 columns, bit k = column 2k, bit 16 + k = column 2k + 1
+    # (checked away from the zero crossings)
+    pos = torch.tensor([(c >> 1) + 16 * (c & 1) for c in range(32)], device=DEV, dtype=torch.int32)
+    bits = ((sgn.view(M, N // 32, 1) >> pos) & 1).reshape(M, N).bool()
+    cy = torch.cos(y)
+    clear = cy.abs() > 1e-3
+    assert torch.equal(bits[clear], (cy < 0)[clear])
     mul = torch.randn(M, N, device=DEV).bfloat16()
     o2 = torch.zeros_like(out)
     check(lib.snb_gemm_bf16(ptr(A), K, ptr(B), K, M, N, K, 0, 0, _lib.EPI_MUL, ptr(o2), None, N, ptr(mul), None, 1.0, 1,
                             stream()), "mul")
     want = ref * mul.float()
     assert (o2.float() - want).abs().max() <= 2 ** -8 * want.abs().max()
+    # SIREN dgrad epilogue: acc * w0 * cos(y), the derivative rebuilt from h = sin(y) (bf16) and its sign mask
+    o3 = torch.zeros_like(out)
+    check(lib.snb_gemm_bf16(ptr(A), K, ptr(B), K, M, N, K, 0, 0, _lib.EPI_MUL, ptr(o3), ptr(sgn), N, ptr(o0), None, 3.0, 1,
+                            stream()), "mul siren")
+    want = ref * 3.0 * cy
+    err = (o3.float() - want).abs()
+    # sqrt(1 - h^2) from a bf16 h: absolute error ~ 2^-9 h^2 / |cos| away from the zero crossings of cos, <= ~0.07 at
+    # them (here w0 = 3 spreads the phase uniformly, the worst case): <= 2.5 % rms, i.e. gradient cosine >= 0.9996
+    assert err.max() <= 0.1 * 3.0 * ref.abs().max() and err.pow(2).mean().sqrt() <= 0.025 * want.pow(2).mean().sqrt()
 
 
 def test_gemm_n16_rows():
@@ -79,8 +95,10 @@ def test_gemm_wgrad_splitk_accumulates(P, Mf, Nf, splits):
 def test_gemm_rejects_bad_arguments():
     lib = _lib_or_fail()
     a = torch.zeros(128, 256, device=DEV, dtype=torch.bfloat16)
-    assert lib.snb_gemm_bf16(ptr(a), 256, ptr(a), 256, 128, 128, 256, 0, 0, _lib.EPI_LINEAR, ptr(a), None, 128, None,
+    assert lib.snb_gemm_bf16(ptr(a), 256, ptr(a), 256, 128, 256, 256, 0, 0, _lib.EPI_LINEAR, ptr(a), None, 256, None,
                              None, 1.0, 4, stream()) == -1    # split-K only with the accumulate epilogue
+    assert lib.snb_gemm_bf16(ptr(a), 256, ptr(a), 256, 128, 128, 256, 0, 0, _lib.EPI_LINEAR, ptr(a), None, 128, None,
+                             None, 1.0, 1, stream()) == -2    # bf16 epilogues: N must be a multiple of 256
     assert lib.snb_gemm_bf16(None, 256, ptr(a), 256, 128, 128, 256, 0, 0, 1, ptr(a), None, 128, None, None, 1.0, 1,
                              stream()) == -1
 

@@ -55,13 +55,16 @@ def group_gemm():
             stats("linear(acc+bias)", out.float(), (ref + bias).bfloat16().float(), 0.05)
             # sin with derivative
             o0 = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-            o1 = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+            o1 = torch.zeros(M, max(N // 32, 1), device=dev, dtype=torch.int32)   # sign mask of the derivative
             check(lib.snb_gemm_bf16(ptr(A), K, ptr(B), K, M, N, K, 0, 0, _lib.EPI_SIN, ptr(o0), ptr(o1), N, None,
                                     ptr(bias), 3.0, 1, stream()), "gemm sin")
             torch.cuda.synchronize()
             y = 3.0 * (ref + bias)
             stats("sin(w0*(acc+b))", o0.float(), torch.sin(y), 0.02)
-            stats("w0*cos(w0*(acc+b))", o1.float(), 3.0 * torch.cos(y), 0.06)
+            pos = torch.tensor([(c >> 1) + 16 * (c & 1) for c in range(32)], device=dev, dtype=torch.int32)
+            bits = ((o1.view(M, -1, 1) >> pos) & 1).reshape(M, -1)[:, :N].bool()
+            cy = torch.cos(y)
+            print("   sign mask == [cos < 0] away from zero crossings:", bool(torch.equal(bits[cy.abs() > 1e-3], (cy < 0)[cy.abs() > 1e-3])))
             # mul
             mul = torch.randn(M, N, device=dev).bfloat16()
             o2 = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
