@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         if (elect_one()) {
           if (lead_cta) mbar_expect_tx(&fullA[stage], 2 * 16384);
           else mbar_arrive_remote(&fullA[stage], 0);
-          tma_load_2d_2sm(sA + stage * 16384, &ly.tmA[sg], &fullA[stage], kk * GEMM_BLOCK_K,
+          tma_load_2d_2sm(sA + stage * 16384, &args.maps[c.l].tmA[sg], &fullA[stage], kk * GEMM_BLOCK_K,
                           ly.a_scratch[sg] ? row_scr : row_real);
         }
         __syncwarp();
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         if (elect_one()) {
           if (lead_cta) mbar_expect_tx(&fullB[stage], 2 * 16384);
           else mbar_arrive_remote(&fullB[stage], 0);
-          tma_load_2d_2sm_hint(sB + stage * 16384, &ly.tmB, &fullB[stage], kb * GEMM_BLOCK_K, n_row, L2_EVICT_LAST);
+          tma_load_2d_2sm_hint(sB + stage * 16384, &args.maps[c.l].tmB, &fullB[stage], kb * GEMM_BLOCK_K, n_row, L2_EVICT_LAST);
         }
         __syncwarp();
         if (++stage == CHAIN_B_STAGES) { stage = 0; phase ^= 1; }
@@ -356,16 +356,16 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
           bulk_wait_read<0>();
           if (epi == EPI_MUL && !cur_prefetched) {
             mbar_expect_tx(&gmfull[b], GEMM_STAGING);
-            tma_load_2d_hint(stg_ptr + b * GEMM_STAGING, &ly.tmMul, &gmfull[b], n0 + ch * 64, m_real, L2_EVICT_FIRST);
+            tma_load_2d_hint(stg_ptr + b * GEMM_STAGING, &args.maps[c.l].tmMul, &gmfull[b], n0 + ch * 64, m_real, L2_EVICT_FIRST);
           }
           if (nmul) {
             const uint32_t nb = b ^ 1;
             mbar_expect_tx(&gmfull[nb], GEMM_STAGING);
             if (ci == 0) {
-              tma_load_2d_hint(stg_ptr + nb * GEMM_STAGING, &ly.tmMul, &gmfull[nb], n0 + (ch + 2) * 64, m_real, L2_EVICT_FIRST);
+              tma_load_2d_hint(stg_ptr + nb * GEMM_STAGING, &args.maps[c.l].tmMul, &gmfull[nb], n0 + (ch + 2) * 64, m_real, L2_EVICT_FIRST);
             } else {
               const int nblk = (nx.g * CHAIN_SLOTS + nx.s) * n_pairs + pair;
-              tma_load_2d_hint(stg_ptr + nb * GEMM_STAGING, &args.layers[nx.l].tmMul, &gmfull[nb], nx.j * 256 + grp * 64,
+              tma_load_2d_hint(stg_ptr + nb * GEMM_STAGING, &args.maps[nx.l].tmMul, &gmfull[nb], nx.j * 256 + grp * 64,
                                nblk * 256 + (int)cta_rank * GEMM_BLOCK_M, L2_EVICT_FIRST);
             }
           }
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         gbar();
         if (leader) {
           confirm_pending();
-          tma_store_2d(&ly.tmO0, buf0, n0 + ch * 64, m_out);
+          tma_store_2d(&args.maps[c.l].tmO0, buf0, n0 + ch * 64, m_out);
           bulk_commit();
         }
         ++cn;

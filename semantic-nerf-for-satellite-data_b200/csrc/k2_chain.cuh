@@ -13,7 +13,7 @@
 
 namespace snb {
 
-constexpr int CHAIN_SLOTS = 2;
+constexpr int CHAIN_SLOTS = 3;
 constexpr int CHAIN_MAX_LAYERS = 16;
 constexpr int CHAIN_A_STAGES = 5;      // 16 KB slots (128 rows x 64 k)
 constexpr int CHAIN_B_STAGES = 4;      // 16 KB slots (this CTA's 128 of the 256 weight rows x 64 k; weights are L2-resident)
@@ -23,10 +23,14 @@ constexpr int CHAIN_RING_BYTES = (CHAIN_A_STAGES + CHAIN_B_STAGES) * 16384;
 constexpr int CHAIN_SMEM_BYTES = CHAIN_RING_BYTES + GEMM_NUM_STAGING * GEMM_STAGING +
                                  2048 /*bias tiles*/ + 1024 /*barriers*/ + 1024 /*alignment*/;
 
-struct alignas(64) ChainLayer {
+struct alignas(64) ChainMaps {   // only touched by the TMA unit
   CUtensorMap tmA[3];   // A K-segments, box {64 k, 128 rows}
-  CUtensorMap tmB;      // weights [N, K], box {64 k, block_n / 2 rows}
-  CUtensorMap tmO0, tmMul;
+  CUtensorMap tmB;      // weights [N, K], box {64 k, 128 rows}
+  CUtensorMap tmO0;     // output, box {64 columns, 128 rows}
+  CUtensorMap tmMul;    // EPI_MUL multiplicand, box {64 columns, 128 rows}
+};
+
+struct ChainLayer {     // scalars every role reads once per tile: kept together so they stay in the constant cache
   int seg_kb[3];
   int a_scratch[3];     // segment lives in the per-pair scratch (row = (pair*SLOTS + slot)*256) instead of at the block's rows
   int nseg;
@@ -37,10 +41,10 @@ struct alignas(64) ChainLayer {
                         // (tmMul) and the sign mask: w0 * (-1)^bit * sqrt(1 - h^2); 0: multiply by the tmMul tensor itself
   int o_scratch;        // outputs go to the per-pair scratch
   int mask_ld;          // 32-bit words per row of `mask`
-  uint32_t* mask;       // EPI_SIN: written (NULL = inference), bit c of row r = [cos(w0*(acc+bias)) < 0]: with h it is all the
-                        // backward pass needs of the derivative (1 bit instead of 16 per element of HBM write traffic);
-                        // EPI_MUL + mul_siren: read
   float w0;
+  uint32_t* mask;       // EPI_SIN: written (NULL = inference), one bit per element = [cos(w0*(acc+bias)) < 0]: with h it is
+                        // all the backward pass needs of the derivative (1 bit instead of 16 per element of HBM write
+                        // traffic); EPI_MUL + mul_siren: read.  Word layout: see chunk_math in k2_chain.cu
   const float* bias;
 };
 
@@ -49,6 +53,7 @@ struct ChainArgs {
   int n_layers;
   int M;
   int n_blocks;         // ceil(M / 256)
+  ChainMaps maps[CHAIN_MAX_LAYERS];
 };
 
 // rows of per-pair scratch a chain launch may address: (SMs/2) * CHAIN_SLOTS * 256

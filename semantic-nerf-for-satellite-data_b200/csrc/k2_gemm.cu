@@ -538,14 +538,15 @@ extern "C" int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t 
     ca->n_blocks = (int)((M + 255) / 256);
     ca->n_layers = 1;
     ChainLayer& ly = ca->layers[0];
+    ChainMaps& mp = ca->maps[0];
     ly.epi = epi;
     ly.n_tiles = N / 256;
     ly.nseg = 1;
     ly.kb_total = ly.seg_kb[0] = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
-    int r = make_tmap_2d(&ly.tmA[0], A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, GEMM_BLOCK_M);
-    if (!r) r = make_tmap_2d(&ly.tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, 128);
-    if (!r) r = make_tmap_2d(&ly.tmO0, out0, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M);
-    if (!r && epi == EPI_MUL) r = make_tmap_2d(&ly.tmMul, mul, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M);
+    int r = make_tmap_2d(&mp.tmA[0], A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, GEMM_BLOCK_M);
+    if (!r) r = make_tmap_2d(&mp.tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, 128);
+    if (!r) r = make_tmap_2d(&mp.tmO0, out0, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M);
+    if (!r && epi == EPI_MUL) r = make_tmap_2d(&mp.tmMul, mul, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M);
     ly.mul_siren = (epi == EPI_MUL && out1 != nullptr) ? 1 : 0;
     ly.mask = epi == EPI_LINEAR ? nullptr : reinterpret_cast<uint32_t*>(out1);
     ly.mask_ld = N / 32;

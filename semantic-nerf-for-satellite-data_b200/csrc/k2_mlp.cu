@@ -573,6 +573,7 @@ struct ChainPlan {
       chk(SNB_ERR_UNSUPPORTED);
       return;
     }
+    ChainMaps& mp = a.maps[a.n_layers];
     ChainLayer& ly = a.layers[a.n_layers++];
     ly.epi = epi;
     ly.n_tiles = N / 256;
@@ -582,12 +583,12 @@ struct ChainPlan {
       ly.seg_kb[s] = segs[s].kb;
       ly.a_scratch[s] = per_layer ? 0 : segs[s].scratch;
       ly.kb_total += segs[s].kb;
-      chk(make_tmap_2d(&ly.tmA[s], segs[s].ptr, 2, (uint64_t)segs[s].cols, (uint64_t)segs[s].rows, (uint64_t)segs[s].ld * 2, 64,
+      chk(make_tmap_2d(&mp.tmA[s], segs[s].ptr, 2, (uint64_t)segs[s].cols, (uint64_t)segs[s].rows, (uint64_t)segs[s].ld * 2, 64,
                        GEMM_BLOCK_M));
     }
-    chk(make_tmap_2d(&ly.tmB, B, 2, (uint64_t)b_cols, (uint64_t)N, (uint64_t)ldb * 2, 64, 128));
-    chk(make_tmap_2d(&ly.tmO0, out0, 2, (uint64_t)N, (uint64_t)o_rows, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
-    if (epi == EPI_MUL) chk(make_tmap_2d(&ly.tmMul, mul, 2, (uint64_t)N, (uint64_t)a.M, (uint64_t)ldmul * 2, 64, GEMM_BLOCK_M));
+    chk(make_tmap_2d(&mp.tmB, B, 2, (uint64_t)b_cols, (uint64_t)N, (uint64_t)ldb * 2, 64, 128));
+    chk(make_tmap_2d(&mp.tmO0, out0, 2, (uint64_t)N, (uint64_t)o_rows, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
+    if (epi == EPI_MUL) chk(make_tmap_2d(&mp.tmMul, mul, 2, (uint64_t)N, (uint64_t)a.M, (uint64_t)ldmul * 2, 64, GEMM_BLOCK_M));
     ly.mul_siren = (epi == EPI_MUL && mask != nullptr) ? 1 : 0;
     ly.mask = mask;
     ly.mask_ld = mask_ld;
