@@ -33,6 +33,9 @@ N_CLASSES, N_SAMPLES, CAR_INDEX = 6, 64, 4
 # (fwd + dgrad + wgrad, no dgrad into the inputs) + solar pass 14.470 MFLOP/sample.
 ALG_FLOP_PER_TRAIN_RAY = 64 * (16_862_208 + 14_470_144)
 ALG_FLOP_PER_RENDER_SAMPLE = 5_641_216 + 4_844_544  # all heads + the solar pass forward
+# dram__bytes_read.sum + dram__bytes_write.sum of the GEMM kernels of one 8192-ray step, from the ncu --set full capture
+# under profiles/ (filled in by tools/ncu_traffic.py; None until a capture of the current kernels exists)
+NCU_TRAFFIC_BYTES_PER_STEP = None
 
 
 def peaks():
@@ -219,26 +222,30 @@ def run_gpu(args):
     e2e_value = world * B * args.steps / t_e2e.item()
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
-    # ---- roofline of the dominant kernel (the tcgen05 GEMM), timed live with CUDA events per launch ------
+    # ---- roofline of the dominant kernels (the tcgen05 GEMMs), timed live with CUDA events per launch ------
+    # every rank runs these steps (they contain the gradient all-reduce); rank 0 reports its own launches
     roof = cpu = render = None
+    nprof = 2
+    snb_dist.barrier()
+    lib.snb_profile_begin(1)
+    for i in range(nprof):
+        step_resident(i)
+    gms, gl2, tl2, macs = C.c_double(), C.c_int64(), C.c_int64(), C.c_double()
+    lib.snb_profile_end(C.byref(gms), C.byref(gl2), C.byref(tl2), C.byref(macs))
+    snb_dist.barrier()
     if rank == 0:
         peak_tf, peak_hbm, which = peaks()
-        nprof = 2
-        lib.snb_profile_begin(1)
-        for i in range(nprof):
-            step_resident(i)
-        gms, gl2, tl2, macs = C.c_double(), C.c_int64(), C.c_int64(), C.c_double()
-        lib.snb_profile_end(C.byref(gms), C.byref(gl2), C.byref(tl2), C.byref(macs))
         gemm_ms_step = gms.value / nprof
         alg = ALG_FLOP_PER_TRAIN_RAY * B
         achieved = alg / (gemm_ms_step * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "snb_gemm_kernel (tcgen05 GEMM, all epilogues)", "achieved": achieved,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
-                "peak_source": which, "per": "step: algorithmic MLP FLOPs of one step / summed GEMM launch time",
+        roof = {"bound": "tensor", "kernel": "snb_chain_kernel + snb_gemm_kernel (tcgen05 GEMMs: chained MLP passes, wgrad, head rows)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": NCU_TRAFFIC_BYTES_PER_STEP,
+                "peak_source": which, "per": "step: algorithmic MLP FLOPs of one step / summed GEMM launch time (one rank)",
                 "gemm_launches_per_step": gl2.value // nprof, "gemm_ms_per_step": gemm_ms_step,
                 "executed_tflops": 2 * macs.value / nprof / (gemm_ms_step * 1e-3) / 1e12,
                 "gemm_share_of_step": gemm_ms_step / (ms_total / args.steps)}
-        # secondary metric: no-grad render throughput (samples/s), chunked like batched_inference
+        # secondary metric: no-grad render throughput (samples/s), chunked like batched_inference (no collectives)
         nr = 4 * 40960
         from semnerf_b200 import synth
         rr, ee = synth.make_rays(nr, seed=7)

@@ -7,7 +7,8 @@
 // (baseline/models/satnerf.py:73-96, semantic/models/rs_semantic.py:81-126,131-136).
 //
 // HBM-bound: forward reads (n_out + 1) floats per sample and writes 2 (weights, transparency);
-// each ray's packed rows are staged through shared memory with fully coalesced 4-byte accesses.
+// each ray's packed rows stream into shared memory with 16-byte cp.async copies, double-buffered so the
+// next ray's loads are in flight while this one is composited.
 #include "snb_common.cuh"
 
 namespace snb {
@@ -75,33 +76,46 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_words = S * n_out;
-  // per warp: packed rows [S*n_out] (+ gradient rows in BWD) + z [S], each region 16-byte aligned
+  // per warp: two input buffers {packed rows [S*n_out], z [S]} (the next ray streams in with cp.async while this
+  // one is composited) + gradient rows in BWD; every region 16-byte aligned
   const int rw4 = (row_words + 3) & ~3, s4 = (S + 3) & ~3;
-  const int per_warp = (BWD ? 2 : 1) * rw4 + s4;
-  float* rows = smem + warp * per_warp;
-  float* grow = rows + rw4;  // BWD only
-  float* zs = rows + (BWD ? 2 : 1) * rw4;
-  // 16-byte global accesses when every ray's rows start on a 16-byte boundary (S*n_out % 4 == 0: true for
-  // the even sample counts the pipelines use); 4x the bytes in flight per load instruction
+  const int in_words = rw4 + s4;
+  const int per_warp = 2 * in_words + (BWD ? rw4 : 0);
+  float* wbase = smem + warp * per_warp;
+  float* grow = wbase + 2 * in_words;  // BWD only
+  // 16-byte accesses when every ray's rows start on a 16-byte boundary (S*n_out % 4 == 0: true for the even sample
+  // counts the pipelines use)
   const bool vec_rows = (row_words & 3) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                         (!BWD || (((reinterpret_cast<uintptr_t>(g_out) | reinterpret_cast<uintptr_t>(g_direct)) & 15) == 0));
   const bool vec_z = (S & 3) == 0 && ((reinterpret_cast<uintptr_t>(z_vals) & 15) == 0);
+  const bool async_in = vec_rows && vec_z;
 
-  for (int ray = blockIdx.x * K3_WARPS + warp; ray < n_rays; ray += gridDim.x * K3_WARPS) {
-    const float* src = out + (size_t)ray * row_words;
-    if (vec_rows) {
-      const float4* s4p = reinterpret_cast<const float4*>(src);
-      float4* d4 = reinterpret_cast<float4*>(rows);
-#pragma unroll 8
-      for (int i = lane; i < row_words / 4; i += 32) d4[i] = __ldg(s4p + i);
-    } else {
-      for (int i = lane; i < row_words; i += 32) rows[i] = __ldg(src + i);
+  // asynchronous global -> shared copy of one ray's inputs (one cp.async group per ray)
+  auto fetch = [&](int ray, float* dst) {
+    if (ray < n_rays) {
+      const float4* s4p = reinterpret_cast<const float4*>(out + (size_t)ray * row_words);
+      const uint32_t d = smem_u32(dst);
+      for (int i = lane; i < row_words / 4; i += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 16), "l"(s4p + i) : "memory");
+      const float4* z4 = reinterpret_cast<const float4*>(z_vals + (size_t)ray * S);
+      for (int i = lane; i < S / 4; i += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (rw4 + i * 4) * 4), "l"(z4 + i) : "memory");
     }
-    if (vec_z) {
-      if (lane < S / 4) reinterpret_cast<float4*>(zs)[lane] = __ldg(reinterpret_cast<const float4*>(z_vals + (size_t)ray * S) + lane);
-      for (int i = lane + 32; i < S / 4; i += 32)
-        reinterpret_cast<float4*>(zs)[i] = __ldg(reinterpret_cast<const float4*>(z_vals + (size_t)ray * S) + i);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int ray0 = blockIdx.x * K3_WARPS + warp, stride = gridDim.x * K3_WARPS;
+  int cur = 0;
+  if (async_in) fetch(ray0, wbase);
+  for (int ray = ray0; ray < n_rays; ray += stride, cur ^= 1) {
+    float* rows = wbase + (async_in ? cur * in_words : 0);
+    float* zs = rows + rw4;
+    if (async_in) {
+      fetch(ray + stride, wbase + (cur ^ 1) * in_words);          // the other buffer was released by the __syncwarp below
+      asm volatile("cp.async.wait_group 1;" ::: "memory");      // this ray's group has landed
     } else {
+      const float* src = out + (size_t)ray * row_words;
+      for (int i = lane; i < row_words; i += 32) rows[i] = __ldg(src + i);
       for (int i = lane; i < S; i += 32) zs[i] = __ldg(z_vals + (size_t)ray * S + i);
     }
     __syncwarp();
@@ -252,10 +266,22 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
         const float4* g4 = reinterpret_cast<const float4*>(grow);
         if (g_direct) {
           const float4* gd4 = reinterpret_cast<const float4*>(g_direct + (size_t)ray * row_words);
-#pragma unroll 8
-          for (int i = lane; i < row_words / 4; i += 32) {
-            const float4 a = g4[i], b = __ldg(gd4 + i);
-            d4[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+          const int n4 = row_words / 4;
+          for (int base = 0; base < n4; base += 256) {
+            float4 t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int i = base + lane + 32 * k;
+              if (i < n4) t[k] = __ldg(gd4 + i);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int i = base + lane + 32 * k;
+              if (i < n4) {
+                const float4 a = g4[i];
+                d4[i] = make_float4(a.x + t[k].x, a.y + t[k].y, a.z + t[k].z, a.w + t[k].w);
+              }
+            }
           }
         } else {
 #pragma unroll 8
@@ -278,16 +304,20 @@ static int launch_k3(const float* out, const float* z, int n_rays, int S, int n_
                      const float* g_rgb, const float* g_depth, const float* g_w, const float* g_t,
                      const float* g_sem, const float* g_direct, float* g_out, cudaStream_t st) {
   const int spl = (S + 31) / 32;
-  const size_t smem = (size_t)K3_WARPS * ((BWD ? 2 : 1) * ((S * n_out + 3) & ~3) + ((S + 3) & ~3)) * sizeof(float);
+  const size_t rw4 = (size_t)((S * n_out + 3) & ~3), s4 = (size_t)((S + 3) & ~3);
+  const size_t smem = (size_t)K3_WARPS * (2 * (rw4 + s4) + (BWD ? rw4 : 0)) * sizeof(float);
   int sms = num_sms();
   if (sms <= 0) return SNB_ERR_NO_DEVICE;
   int blocks = (n_rays + K3_WARPS - 1) / K3_WARPS;
-  const int max_blocks = sms * 16;
-  if (blocks > max_blocks) blocks = max_blocks;
 #define K3_LAUNCH(SPL_)                                                                               \
   do {                                                                                                \
     auto kfn = k3_composite_kernel<SPL_, BWD>;                                                        \
     if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    /* one full wave of resident blocks, each looping over rays: a partial second wave would idle most SMs */ \
+    int resident = 0;                                                                                 \
+    SNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, K3_WARPS * 32, smem));     \
+    if (resident < 1) resident = 1;                                                                   \
+    if (blocks > sms * resident) blocks = sms * resident;                                             \
     kfn<<<blocks, K3_WARPS * 32, smem, st>>>(out, z, n_rays, S, n_out, C, rgb, depth, weights, transp, sem, label, \
                                              g_rgb, g_depth, g_w, g_t, g_sem, g_direct, g_out);       \
   } while (0)

@@ -25,7 +25,13 @@ def init_from_env(backend: str | None = None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        import datetime
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local)
+        # a mismatched collective must fail in minutes, not hold the GPUs for the default 10
+        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("SNB_DIST_TIMEOUT_S", "180"))), **kw)
     return rank, local, world
 
 
