@@ -143,7 +143,7 @@ def run_reference(args):
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, cpu=False):
@@ -273,11 +273,27 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "clocks": clocks, "render": render, "loss": loss_host,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     snb_dist.barrier()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner, build
+    chatter) was redirected to stderr at start-up"""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
