@@ -214,12 +214,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
     Cursor c;
     for (cur_init(c, seq); !c.done; cur_next(c, seq, args)) {
       const ChainLayer& ly = args.layers[c.l];
-      const int n_row = c.j * 256 + (int)cta_rank * 128;
+      const bool rows16 = ly.epi == EPI_HEADOUT;   // N = 16: this CTA holds 8 of the 16 weight rows
+      const int n_row = rows16 ? (int)cta_rank * 8 : c.j * 256 + (int)cta_rank * 128;
+      const uint32_t b_bytes = rows16 ? 2u * 1024u : 2u * 16384u;
       const int kb_total = ly.kb_total;
       for (int kb = 0; kb < kb_total; ++kb) {
         mbar_wait(&emptyB[stage], phase ^ 1);
         if (elect_one()) {
-          if (lead_cta) mbar_expect_tx(&fullB[stage], 2 * 16384);
+          if (lead_cta) mbar_expect_tx(&fullB[stage], b_bytes);
           else mbar_arrive_remote(&fullB[stage], 0);
           tma_load_2d_2sm_hint(sB + stage * 16384, &args.maps[c.l].tmB, &fullB[stage], kb * GEMM_BLOCK_K, n_row, L2_EVICT_LAST);
         }
@@ -231,13 +233,15 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
     // ===================================== MMA issuer (leader CTA) ===========================
     if (lead_cta) {
       // cute::UMMA::InstrDescriptor: f32 accumulate, bf16 x bf16, both K-major, N = 256, M = 256 (SM pair)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t idesc256 = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((16u >> 3) << 17) | ((256u >> 4) << 24);
       const uint64_t desc0 = umma_desc(0, 16u, 1024u);   // K-major SW128: 8-row groups 1024 B apart
       const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       Cursor c;
       for (cur_init(c, seq); !c.done; cur_next(c, seq, args), ++it) {
         const int kb_total = args.layers[c.l].kb_total;
+        const uint32_t idesc = args.layers[c.l].epi == EPI_HEADOUT ? idesc16 : idesc256;
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -308,7 +312,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
     // bias of this group's two chunks of a tile: column (grp + 2 * (i >> 6)) * 64 + (i & 63) for i < 128
     float* gbias = bias_smem + grp * 256;
     auto bias_fetch = [&](const Cursor& t) -> float {
-      const float* bp = args.layers[t.l].bias;   // staged pre-multiplied by w0: the epilogue computes fma(acc, w0, w0 * bias)
+      const float* bp = args.layers[t.l].epi == EPI_HEADOUT ? nullptr : args.layers[t.l].bias;
+      // staged pre-multiplied by w0: the epilogue computes fma(acc, w0, w0 * bias)
       return (gtid < 128 && bp != nullptr) ? args.layers[t.l].w0 * __ldg(bp + t.j * 256 + (grp + 2 * (gtid >> 6)) * 64 + (gtid & 63)) : 0.f;
     };
 
@@ -343,6 +348,65 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256;
 
+      if (epi == EPI_HEADOUT) {
+        // ---- 16 head pre-activations per row: one warp per TMEM lane quadrant, straight from / to global memory ----
+        if (grp == 0 && half == 0) {
+          uint32_t v[16];
+          tmem_ld16(taddr, v);
+          tc_wait_ld();
+          if (row_ok) {
+            const long long grow = (long long)m_real + row;
+            float x[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+            if (ly.part != nullptr && ly.rows_mode >= 1) {
+              const float4* pp = reinterpret_cast<const float4*>(ly.part + grow * 16);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float4 t4 = pp[j];
+                x[4 * j] += t4.x; x[4 * j + 1] += t4.y; x[4 * j + 2] += t4.z; x[4 * j + 3] += t4.w;
+              }
+            }
+            if (ly.rows_mode < 2) {
+              float4* pp = reinterpret_cast<float4*>(ly.part + grow * 16);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pp[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            } else {
+              if (ly.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] += __ldg(ly.bias + j);
+              }
+              float* o = args.out_packed + grow * args.n_out;
+              const int hm = args.head_mask;
+              // rs_semantic.py:282-284: rgb = sigmoid(.) * (1 + 2*0.001) - 0.001
+#pragma unroll
+              for (int j = 0; j < 3; ++j) o[j] = (hm & SNB_HEAD_RGB) ? (1.0f / (1.0f + expf(-x[j]))) * 1.002f - 0.001f : 0.f;
+              o[3] = (hm & SNB_HEAD_SIGMA) ? (x[3] > 20.f ? x[3] : log1pf(expf(x[3]))) : 0.f;
+              o[4] = (hm & SNB_HEAD_SUN) ? 1.0f / (1.0f + expf(-x[4])) : 0.f;
+              if ((hm & SNB_HEAD_SKY) && args.sky != nullptr) {
+                const long long ray = args.rows_per_ray > 0 ? grow / args.rows_per_ray : grow;
+                o[5] = __ldg(args.sky + ray * 3);
+                o[6] = __ldg(args.sky + ray * 3 + 1);
+                o[7] = __ldg(args.sky + ray * 3 + 2);
+              } else {
+                o[5] = o[6] = o[7] = 0.f;
+              }
+              o[8] = (hm & SNB_HEAD_BETA) ? (x[5] > 20.f ? x[5] : log1pf(expf(x[5]))) : 0.f;
+#pragma unroll
+              for (int cc = 0; cc < 10; ++cc) {
+                if (cc < args.n_classes) {
+                  const float sv = x[6 + cc];
+                  o[9 + cc] = (hm & SNB_HEAD_SEM) ? (args.sem_sigmoid ? 1.0f / (1.0f + expf(-sv)) : sv) : 0.f;
+                }
+              }
+            }
+          }
+        }
+        // the next tile's bias still has to be staged (done inside the chunk loop otherwise)
+        if (!nx.done) nbias = bias_fetch(nx);
+        if (gtid < 128) gbias[((it + 1) & 1) * 128 + gtid] = nbias;
+        gbar();
+      } else {
 #pragma unroll 1
       for (int ci = 0; ci < 2; ++ci) {
         const int ch = grp + 2 * ci;                 // 64-column chunk of the tile
@@ -415,6 +479,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         }
         ++cn;
       }
+      }
       tc_fence_before();
       if (lead_cta) mbar_arrive(&tempty[acc]);
       else mbar_arrive_remote(&tempty[acc], 0);   // the leader CTA's MMA warp owns the accumulator hand-shake
@@ -426,7 +491,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         if (npend == 0) { pend_cn0 = cn; pend_slot0 = c.s; }
         else { pend_cn1 = cn; pend_slot1 = c.s; }
         ++npend;
-        if (nx.done || nx.s == c.s) {
+        // (a head-output tile-set issues no store of its own, so nothing later would notice it: release it now)
+        if (nx.done || nx.s == c.s || epi == EPI_HEADOUT) {
           bulk_wait_done<0>();
           confirm(cn);
         }
@@ -459,10 +525,14 @@ int chain_launch(const ChainArgs& a, cudaStream_t st) {
   for (int l = 0; l < a.n_layers; ++l) {
     const ChainLayer& ly = a.layers[l];
     SNB_CHECK_ARG(ly.n_tiles >= 1 && ly.kb_total >= 1 && ly.nseg >= 1 && ly.nseg <= 3, SNB_ERR_INVALID, "chain: layer %d shape", l);
-    SNB_CHECK_ARG(ly.epi == EPI_SIN || ly.epi == EPI_LINEAR || ly.epi == EPI_MUL, SNB_ERR_UNSUPPORTED, "chain: layer %d epilogue %d", l, ly.epi);
+    SNB_CHECK_ARG(ly.epi == EPI_SIN || ly.epi == EPI_LINEAR || ly.epi == EPI_MUL || ly.epi == EPI_HEADOUT, SNB_ERR_UNSUPPORTED,
+                  "chain: layer %d epilogue %d", l, ly.epi);
+    if (ly.epi == EPI_HEADOUT)
+      SNB_CHECK_ARG(ly.n_tiles == 1 && (ly.rows_mode == 2 ? a.out_packed != nullptr : ly.part != nullptr), SNB_ERR_INVALID,
+                    "chain: head-output layer %d needs its destination", l);
     SNB_CHECK_ARG(!(ly.epi == EPI_MUL && ly.mul_siren) || (ly.mask != nullptr && ly.mask_ld > 0), SNB_ERR_INVALID,
                   "chain: layer %d needs the sign mask of the saved activation", l);
-    macs += (double)a.n_blocks * 256.0 * ly.n_tiles * 256.0 * ly.kb_total * GEMM_BLOCK_K;
+    macs += (double)a.n_blocks * 256.0 * (ly.epi == EPI_HEADOUT ? 16.0 : ly.n_tiles * 256.0) * ly.kb_total * GEMM_BLOCK_K;
   }
   const int sms = num_sms();
   if (sms <= 0) return SNB_ERR_NO_DEVICE;

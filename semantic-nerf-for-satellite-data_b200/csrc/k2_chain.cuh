@@ -36,12 +36,17 @@ struct ChainLayer {     // scalars every role reads once per tile: kept together
   int nseg;
   int kb_total;
   int n_tiles;          // N / 256
-  int epi;              // EPI_SIN / EPI_LINEAR / EPI_MUL
+  int epi;              // EPI_SIN / EPI_LINEAR / EPI_MUL (256-column tiles) or EPI_HEADOUT (one 16-column tile, see `rows`)
   int mul_siren;        // EPI_MUL: the multiplicand is the SIREN derivative rebuilt from the saved activation h = sin(y)
                         // (tmMul) and the sign mask: w0 * (-1)^bit * sqrt(1 - h^2); 0: multiply by the tmMul tensor itself
   int o_scratch;        // outputs go to the per-pair scratch
   int mask_ld;          // 32-bit words per row of `mask`
   float w0;
+  int rows_mode;        // EPI_HEADOUT: the 16 head pre-activations are the sum of up to three of these layers, each placed
+                        // right after the layer that produced its input (still in L2): 0 = store the partial sums to
+                        // `part`, 1 = add to `part`, 2 = add `part` (if set) + bias, apply the head activations, write the
+                        // packed (P, n_out) fp32 rows
+  float* part;          // EPI_HEADOUT: (M, 16) fp32 partial sums
   uint32_t* mask;       // EPI_SIN: written (NULL = inference), one bit per element = [cos(w0*(acc+bias)) < 0]: with h it is
                         // all the backward pass needs of the derivative (1 bit instead of 16 per element of HBM write
                         // traffic); EPI_MUL + mul_siren: read.  Word layout: see chunk_math in k2_chain.cu
@@ -53,6 +58,10 @@ struct ChainArgs {
   int n_layers;
   int M;
   int n_blocks;         // ceil(M / 256)
+  // head output (EPI_HEADOUT, rows_mode 2): packed (M, n_out) fp32 [rgb 0:3 | sigma 3 | sun 4 | sky 5:8 | beta 8 | sem 9:]
+  float* out_packed;
+  const float* sky;     // (rays or points, 3) per-ray sky colour from K1
+  int n_out, rows_per_ray, n_classes, sem_sigmoid, head_mask;
   ChainMaps maps[CHAIN_MAX_LAYERS];
 };
 

@@ -248,49 +248,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
       const int m0 = t.m_blk * (GEMM_BLOCK_M * CG) + (int)cta_rank * GEMM_BLOCK_M;
       const int n0 = t.n_blk * args.block_n;
 
-      if constexpr (EPI == EPI_HEADOUT) {
-        // ---- N=16 head pre-activations -> packed (P, n_out) fp32 rows (group 0 only) -----------------
-        if (grp == 0) {
-          uint32_t v[16];
-          tmem_ld16(taddr, v);
-          tc_wait_ld();
-          float* stg = reinterpret_cast<float*>(sStg);
-          const int n_out = args.n_out;
-          const long long grow = (long long)m0 + row;
-          float x[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + (args.bias ? __ldg(args.bias + j) : 0.f);
-          float* o = stg + row * n_out;
-          const int hm = args.head_mask;
-          // rs_semantic.py:282-284: rgb = sigmoid(.) * (1 + 2*0.001) - 0.001
-#pragma unroll
-          for (int j = 0; j < 3; ++j) o[j] = (hm & SNB_HEAD_RGB) ? (1.0f / (1.0f + expf(-x[j]))) * 1.002f - 0.001f : 0.f;
-          o[3] = (hm & SNB_HEAD_SIGMA) ? (x[3] > 20.f ? x[3] : log1pf(expf(x[3]))) : 0.f;
-          o[4] = (hm & SNB_HEAD_SUN) ? 1.0f / (1.0f + expf(-x[4])) : 0.f;
-          if ((hm & SNB_HEAD_SKY) && args.sky && grow < args.M) {
-            const long long ray = args.rows_per_ray > 0 ? grow / args.rows_per_ray : grow;
-            o[5] = __ldg(args.sky + ray * 3);
-            o[6] = __ldg(args.sky + ray * 3 + 1);
-            o[7] = __ldg(args.sky + ray * 3 + 2);
-          } else {
-            o[5] = o[6] = o[7] = 0.f;
-          }
-          o[8] = (hm & SNB_HEAD_BETA) ? (x[5] > 20.f ? x[5] : log1pf(expf(x[5]))) : 0.f;
-#pragma unroll
-          for (int c = 0; c < 10; ++c) {
-            if (c < args.n_classes) {
-              const float sv = x[6 + c];
-              o[9 + c] = (hm & SNB_HEAD_SEM) ? (args.sem_sigmoid ? 1.0f / (1.0f + expf(-sv)) : sv) : 0.f;
-            }
-          }
-          gbar();
-          const int valid = min(GEMM_BLOCK_M, args.M - m0);
-          const int total = valid * n_out;
-          float* dst = args.out_packed + (size_t)m0 * n_out;
-          for (int i = gtid; i < total; i += 128) dst[i] = stg[i];
-          gbar();
-        }
-      } else if constexpr (EPI == EPI_F32ROWS) {
+      if constexpr (EPI == EPI_F32ROWS) {
         if (grp == 0) {
           uint32_t v[16];
           tmem_ld16(taddr, v);
@@ -491,10 +449,10 @@ int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
                     a.a_stages * GEMM_A_STAGE + a.b_stages * (int)a.b_slot <= GEMM_OPERAND_BYTES,
                 SNB_ERR_INVALID, "gemm: ring depths %d/%d exceed the operand smem", a.a_stages, a.b_stages);
   SNB_CHECK_ARG(a.splits == 1 || epi == EPI_WGRAD, SNB_ERR_INVALID, "gemm: split-K only for the accumulate epilogue");
-  SNB_CHECK_ARG(epi == EPI_HEADOUT || epi == EPI_F32ROWS || epi == EPI_WGRAD, SNB_ERR_UNSUPPORTED,
+  SNB_CHECK_ARG(epi == EPI_F32ROWS || epi == EPI_WGRAD, SNB_ERR_UNSUPPORTED,
                 "gemm: epilogue %d is served by the chained kernel (k2_chain.cu)", epi);
-  if (epi == EPI_HEADOUT || epi == EPI_F32ROWS)
-    SNB_CHECK_ARG(a.block_n == 16 && a.n_tiles == 1, SNB_ERR_UNSUPPORTED, "gemm: row epilogues need N == 16");
+  if (epi == EPI_F32ROWS)
+    SNB_CHECK_ARG(a.block_n == 16 && a.n_tiles == 1, SNB_ERR_UNSUPPORTED, "gemm: the row epilogue needs N == 16");
   const int sms = num_sms();
   if (sms <= 0) return SNB_ERR_NO_DEVICE;
   const long long tiles = (long long)a.m_tiles * a.n_tiles * a.splits;
@@ -509,7 +467,6 @@ int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
   int rc;
   const bool two = a.cta_group == 2;
   switch (epi) {
-    case EPI_HEADOUT: rc = launch_epi<EPI_HEADOUT, 1>(a, grid, st); break;
     case EPI_F32ROWS: rc = launch_epi<EPI_F32ROWS, 1>(a, grid, st); break;
     case EPI_WGRAD: rc = two ? launch_epi<EPI_WGRAD, 2>(a, grid, st) : launch_epi<EPI_WGRAD, 1>(a, grid, st); break;
     default: set_error("gemm: unknown epilogue %d", epi); rc = SNB_ERR_INVALID;

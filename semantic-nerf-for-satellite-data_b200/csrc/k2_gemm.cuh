@@ -23,8 +23,8 @@ enum GemmEpi {
   EPI_SIN = 0,      // h = sin(w0*(acc+bias)) -> bf16 ; optional sign mask of the derivative w0*cos(w0*(acc+bias))
   EPI_LINEAR = 1,   // acc + bias -> bf16
   EPI_MUL = 2,      // acc * mul[m,n] -> bf16, or acc * (SIREN derivative rebuilt from the saved activation + sign mask)
+  EPI_HEADOUT = 3,  // N=16 head pre-activations -> packed (P, n_out) fp32 with the reference activations (chained kernel)
   // this kernel:
-  EPI_HEADOUT = 3,  // N=16 head pre-activations -> packed (P, n_out) fp32 with the reference activations
   EPI_F32ROWS = 4,  // N=16 raw fp32 rows -> f32rows[M,16]
   EPI_WGRAD = 5     // fp32 += acc (split-K): TMA reduce-add (block_n % 32 == 0, >= 32) or red.global
 };
@@ -66,10 +66,6 @@ struct GemmArgs {
   unsigned b_slot;         // bytes per B ring slot
   const float* bias;
   float w0;
-  // EPI_HEADOUT
-  float* out_packed;
-  const float* sky;
-  int n_out, rows_per_ray, n_classes, sem_sigmoid, head_mask;
   // EPI_WGRAD: if set, colsum[m] += sum over the K (sample) dimension of A[:, m] - the bias gradient rides the weight
   // gradient GEMM as one extra N = 16 MMA per k-block against a constant all-ones tile (n-block 0 tiles only)
   float* colsum;

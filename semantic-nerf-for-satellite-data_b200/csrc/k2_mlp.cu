@@ -395,6 +395,7 @@ struct Workspace {
   size_t h[8], sg[8], f, hh, sghh, s2, sgs2, s3, sgs3;  // forward (sg*: sign masks of the SIREN derivatives, train only)
   size_t dpre, dy[8], df, dyhh, dys3, dys2;         // backward (dy[i] = gradient w.r.t. the pre-activation of trunk layer i)
   size_t scr_h[2], scr_f, scr_s2;                   // inference: per-SM-pair scratch of the chained kernel (L2-resident)
+  size_t hpart;                                     // (P, 16) fp32 partial sums of the head pre-activations
   size_t gscratch;                                  // fp32 packed gradients
   size_t total;
 };
@@ -433,6 +434,7 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
     w.scr_s2 = take_b(R * FL * 2);
   }
   w.f = take_b(rowF);
+  w.hpart = take_b((size_t)P * 16 * 4);
   w.hh = take_b(rowHH);
   w.s2 = take_b(rowFL);
   w.s3 = take_b(rowFL);
@@ -475,7 +477,7 @@ struct Plan {
   }
 };
 
-// D[M,16] = sum_seg A_seg[M,K] * B[16,Kp]^T  (K-major operands; the N = 16 row epilogues HEADOUT / F32ROWS)
+// D[M,16] = sum_seg A_seg[M,K] * B[16,Kp]^T  (K-major operands; the N = 16 fp32-row epilogue F32ROWS)
 static GemmArgs& add_rows16(Plan& p, int epi, long long M, const Seg* segs, int nseg, const void* B, long long ldb, int b_cols,
                             const float* bias) {
   GemmArgs& a = p.add(epi);
@@ -597,6 +599,27 @@ struct ChainPlan {
     ly.w0 = w0;
     if (per_layer) flush();
   }
+  // 16 head pre-activations: part (+)= A_seg * B[16, Kp]^T (mode 0 / 1), or (mode 2) the packed head outputs
+  void add_rows16(const CSeg& seg, const void* B, long long ldb, int b_cols, int mode, float* part, const float* bias) {
+    if (a.n_layers >= CHAIN_MAX_LAYERS) {
+      chk(SNB_ERR_UNSUPPORTED);
+      return;
+    }
+    ChainMaps& mp = a.maps[a.n_layers];
+    ChainLayer& ly = a.layers[a.n_layers++];
+    ly.epi = EPI_HEADOUT;
+    ly.n_tiles = 1;
+    ly.nseg = 1;
+    ly.kb_total = ly.seg_kb[0] = seg.kb;
+    ly.a_scratch[0] = per_layer ? 0 : seg.scratch;
+    chk(make_tmap_2d(&mp.tmA[0], seg.ptr, 2, (uint64_t)seg.cols, (uint64_t)seg.rows, (uint64_t)seg.ld * 2, 64, GEMM_BLOCK_M));
+    chk(make_tmap_2d(&mp.tmB, B, 2, (uint64_t)b_cols, (uint64_t)16, (uint64_t)ldb * 2, 64, 8));
+    ly.rows_mode = mode;
+    ly.part = part;
+    ly.bias = bias;
+    ly.w0 = 1.0f;
+    if (per_layer) flush();
+  }
   void flush() {
     if (!rc && a.n_layers > 0) chk(chain_launch(a, st));
     a.n_layers = 0;
@@ -701,7 +724,6 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
   const int hhw = m->hhw;
   const bool need_f = head_mask != SNB_HEADS_DEPTH;
   const bool all = head_mask == SNB_HEADS_ALL;
-  Plan p;
   {
     // trunk + feats + head first layers + sun layers.  Chained (default): one persistent launch, inter-layer
     // activations are read back from L2 and, in inference, live in a per-SM-pair scratch that never reaches HBM.
@@ -729,6 +751,20 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
         cp.add(EPI_SIN, F, s, 1, pk + m->wl[i], F, F, hbuf(i), F, hrows(i), hscr(i), nullptr, 0, SG(i), F / 32, pb + m->bl[i], 1.0f);
       }
     }
+    // head outputs: three N = 16 layers ([h7 | s3 | hh] x W_out^T split by K-segment), each right after the layer that
+    // produced its input so it is read from L2; the last one applies the head activations and writes `out`
+    cp.a.out_packed = out;
+    cp.a.sky = sky;
+    cp.a.n_out = m->n_out;
+    cp.a.rows_per_ray = rows_per_ray;
+    cp.a.n_classes = m->n_classes;
+    cp.a.sem_sigmoid = m->sem_sigmoid;
+    cp.a.head_mask = head_mask;
+    float* hpart = reinterpret_cast<float*>(ws + w.hpart);
+    {
+      CSeg s7 = {H(7), F, F, F / 64, P, 0};
+      cp.add_rows16(s7, pk + m->who, m->kho, F, need_f ? 0 : 2, need_f ? hpart : nullptr, need_f ? nullptr : pb + m->bho);
+    }
     if (need_f) {
       void* fbuf = scr ? (void*)(ws + w.scr_f) : (void*)(ws + w.f);
       void* s2buf = scr ? (void*)(ws + w.scr_s2) : (void*)(ws + w.s2);
@@ -741,28 +777,21 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
       CSeg s1[2] = {{fbuf, F, F, F / 64, srows, sflag}, {aux, 16, 16, 1, P, 0}};
       cp.add(EPI_SIN, n, s1, 2, pk + m->wh1 + (long long)r0 * (F + 64), F + 64, F + 64, ws + w.hh + (size_t)r0 * 2, hhw, P, 0,
              nullptr, 0, train ? reinterpret_cast<uint32_t*>(ws + w.sghh) + r0 / 32 : nullptr, hhw / 32, nullptr, 1.0f);
+      if (all) {
+        CSeg shh = {ws + w.hh, hhw, hhw, hhw / 64, P, 0};
+        cp.add_rows16(shh, pk + m->who + F + FL, m->kho, hhw, 1, hpart, nullptr);
+      }
       CSeg s2[1] = {{ws + w.hh + (size_t)m->hh_sun * 2, hhw, FL, FL / 64, P, 0}};
       cp.add(EPI_SIN, FL, s2, 1, pk + m->ws2, FL, FL, s2buf, FL, srows, sflag, nullptr, 0,
              train ? reinterpret_cast<uint32_t*>(ws + w.sgs2) : nullptr, FL / 32, pb + m->bs2, 1.0f);
       CSeg s3[1] = {{s2buf, FL, FL, FL / 64, srows, sflag}};
       cp.add(EPI_SIN, FL, s3, 1, pk + m->ws4, FL, FL, ws + w.s3, FL, P, 0, nullptr, 0,
              train ? reinterpret_cast<uint32_t*>(ws + w.sgs3) : nullptr, FL / 32, pb + m->bs4, 1.0f);
+      CSeg ss3 = {ws + w.s3, FL, FL, FL / 64, P, 0};
+      cp.add_rows16(ss3, pk + m->who + F, m->kho, FL, 2, hpart, pb + m->bho);
     }
-    if (int r = cp.run()) return r;
+    return cp.run();
   }
-  {
-    Seg s[3] = {{H(7), F, F, F / 64}, {ws + w.s3, FL, FL, FL / 64}, {ws + w.hh, hhw, hhw, hhw / 64}};
-    const int nseg = head_mask == SNB_HEADS_DEPTH ? 1 : (all ? 3 : 2);
-    GemmArgs& a = add_rows16(p, EPI_HEADOUT, P, s, nseg, pk + m->who, m->kho, m->kho, pb + m->bho);
-    a.out_packed = out;
-    a.sky = sky;
-    a.n_out = m->n_out;
-    a.rows_per_ray = rows_per_ray;
-    a.n_classes = m->n_classes;
-    a.sem_sigmoid = m->sem_sigmoid;
-    a.head_mask = head_mask;
-  }
-  return run_plan(p, (cudaStream_t)stream);
 }
 
 extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
