@@ -186,7 +186,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * GEMM_MAX_BLOCK_N;
-        const bool do_cs = EPI == EPI_WGRAD && args.colsum != nullptr && t.n_blk == 0;
+        // the n-tiles of an m-block share the column-sum work: k-block kb belongs to n-tile kb % n_tiles (every tile of a
+        // split owns the same k range, so together they cover it exactly once) - one tile doing all of it ran ~10 % longer
+        const bool cs_tile = EPI == EPI_WGRAD && args.colsum != nullptr;
+        bool cs_started = false;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&fullA[sa], pa);
           mbar_wait(&fullB[sb], pb);
@@ -199,11 +202,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
               if constexpr (CG == 2) tc_mma_bf16_2sm(d_tmem, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
               else tc_mma_bf16(d_tmem, ad + k * a_kstep, bd + k * b_kstep, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
             }
-            if (do_cs) {
+            if (cs_tile && (kb % args.n_tiles) == t.n_blk) {
 #pragma unroll
               for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-                if constexpr (CG == 2) tc_mma_bf16_2sm(d_cs, ad + k * a_kstep, odesc + k * 2, idesc_cs, (kb > t.kb0 || k > 0) ? 1u : 0u);
-                else tc_mma_bf16(d_cs, ad + k * a_kstep, odesc + k * 2, idesc_cs, (kb > t.kb0 || k > 0) ? 1u : 0u);
+                if constexpr (CG == 2) tc_mma_bf16_2sm(d_cs, ad + k * a_kstep, odesc + k * 2, idesc_cs, (cs_started || k > 0) ? 1u : 0u);
+                else tc_mma_bf16(d_cs, ad + k * a_kstep, odesc + k * 2, idesc_cs, (cs_started || k > 0) ? 1u : 0u);
               }
             }
             // frees the smem slots (in both CTAs of a pair) once these MMAs have read them
@@ -211,6 +214,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
             else { tc_commit(&emptyA[sa]); tc_commit(&emptyB[sb]); }
           }
           __syncwarp();
+          if (cs_tile && (kb % args.n_tiles) == t.n_blk) cs_started = true;
           if (++sa == a_stages) { sa = 0; pa ^= 1; }
           if (++sb == b_stages) { sb = 0; pb ^= 1; }
         }
@@ -302,8 +306,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
         }
       }
       if constexpr (EPI == EPI_WGRAD) {
-        if (args.colsum != nullptr && t.n_blk == 0 && grp == 0) {
-          // bias gradient of this tile's 128 rows: column 0 of the all-ones product
+        // (this tile issued column-sum MMAs iff its k range holds a k-block with kb % n_tiles == n_blk)
+        if (args.colsum != nullptr && grp == 0 &&
+            t.kb0 + ((t.n_blk - t.kb0 % args.n_tiles + args.n_tiles) % args.n_tiles) < t.kb1) {
+          // bias gradient of this tile's 128 rows over its share of the k-blocks: column 0 of the all-ones product
           uint32_t v[16];
           tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + 2 * GEMM_MAX_BLOCK_N - 16, v);
           tc_wait_ld();
