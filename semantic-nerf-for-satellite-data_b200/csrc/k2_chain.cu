@@ -1,13 +1,17 @@
 // K2 chained MLP kernel - see k2_chain.cuh for the design.  sm_100a only (tcgen05 / TMEM / TMA).
 //
-// Roles (19 warps, one CTA per SM, clusters of 2 = SM pairs, cta_group::2 MMAs over 256 x 256 x 64):
+// Roles (20 warps, one CTA per SM, clusters of 2 = SM pairs, cta_group::2 MMAs over 256 x 256 x 64):
 //   warp 0      TMA producer for A (activations; waits for the producing layer of the same slot)
 //   warp 1      tcgen05.mma issuer of the leader CTA (+ TMEM owner)
 //   warp 2      TMA producer for B (weights)
-//   warps 3-18  epilogue: two groups of 8 warps.  Group g takes the 64-column chunks {g, g+2} of every
+//   warps 3-18  epilogue math: two groups of 8 warps.  Group g takes the 64-column chunks {g, g+2} of every
 //               256-column tile; inside a group, warp w and warp w+4 read the same TMEM lane quadrant and
 //               split the chunk's columns 0-31 / 32-63, so every SM sub-partition has 4 epilogue warps to
-//               hide the TMEM-load / MUFU / shared-memory latencies behind each other.
+//               hide the TMEM-load / MUFU / shared-memory latencies behind each other.  They never wait for
+//               each other: a chunk is handed over through mbarriers to
+//   warp 19     the store warp: TMA-stores every staged chunk, re-arms the staging buffer once the store has
+//               drained (for dgrad layers by TMA-loading the next multiplicand tile into it), and tells the
+//               A producer when a layer's rows have landed.
 #include "k2_chain.cuh"
 #include "k2_ptx.cuh"
 
@@ -126,15 +130,16 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
   uint8_t* sA = smem;
   uint8_t* sB = sA + CHAIN_A_STAGES * 16384;
   uint8_t* sStg = smem + CHAIN_RING_BYTES;
-  float* bias_smem = reinterpret_cast<float*>(sStg + GEMM_NUM_STAGING * GEMM_STAGING);   // [group][buffer][128]: the bias of a group's two chunks
-  uint64_t* fullA = reinterpret_cast<uint64_t*>(bias_smem + 512);
+  float* bias_smem = reinterpret_cast<float*>(sStg + GEMM_NUM_STAGING * GEMM_STAGING);   // [warp][tile parity][chunk][32]
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(bias_smem + 2048);
   uint64_t* emptyA = fullA + 8;
   uint64_t* fullB = emptyA + 8;
   uint64_t* emptyB = fullB + 8;
   uint64_t* tfull = emptyB + 8;
   uint64_t* tempty = tfull + 2;
-  uint64_t* mfull = tempty + 2;
-  uint64_t* ready = mfull + GEMM_NUM_STAGING;
+  uint64_t* rdy = tempty + 2;                 // [group][chunk]: staging buffer free / multiplicand tile landed
+  uint64_t* stg = rdy + GEMM_NUM_STAGING;     // [group][chunk]: chunk staged by the group's 8 warps
+  uint64_t* ready = stg + GEMM_NUM_STAGING;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + CHAIN_SLOTS);
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
@@ -159,8 +164,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], 2 * CHAIN_EPI_WARPS * 32);
     }
-    for (int s = 0; s < GEMM_NUM_STAGING; ++s) mbar_init(&mfull[s], 1);
-    for (int s = 0; s < CHAIN_SLOTS; ++s) mbar_init(&ready[s], 2);   // the two epilogue group leaders
+    for (int s = 0; s < GEMM_NUM_STAGING; ++s) {
+      mbar_init(&rdy[s], 1);
+      mbar_init(&stg[s], 8);   // one arrival per warp of the group
+    }
+    for (int s = 0; s < CHAIN_SLOTS; ++s) mbar_init(&ready[s], 1);   // the store warp
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -180,9 +188,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
     Cursor c;
     for (cur_init(c, seq); !c.done; cur_next(c, seq, args)) {
       const ChainLayer& ly = args.layers[c.l];
-      if (c.j == 0 && !(c.g == 0 && c.l == 0)) {
+      if (c.j == 0 && !(c.g == 0 && c.l == 0) &&
+          args.layers[c.l > 0 ? c.l - 1 : seq.n_layers - 1].epi != EPI_HEADOUT) {
         // the previous tile-set of this slot (the layer that produced this layer's input rows) has been
-        // stored completely; one barrier phase per tile-set keeps producer and epilogue in lock step
+        // stored completely; one barrier phase per stored tile-set keeps producer and store warp in lock step.
+        // (A head-output tile-set stores nothing through TMA and feeds no later layer: no phase for it.)
         mbar_wait(&ready[c.s], (rbits >> c.s) & 1u);
         rbits ^= 1u << c.s;
         fence_proxy_async_all();
@@ -267,32 +277,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         __syncwarp();
       }
     }
-  } else {
-    // ===================================== epilogue (2 groups x 256 threads) =================
-    const int ewarp = warp - 3;               // 0..15
-    const int grp = ewarp >> 3;               // epilogue group
-    const int half = (ewarp >> 2) & 1;        // which 32 columns of a 64-column chunk
-    const int quad = warp & 3;                // TMEM lane quadrant this warp may read (warp id % 4)
-    const int row = quad * 32 + lane;         // row of the 128-row tile == TMEM lane
-    const int gtid = (ewarp & 7) * 32 + lane; // 0..255 within the group
-    const bool leader = (gtid == 0);
-    const uint32_t stg0 = smem_u32(sStg) + grp * 2 * GEMM_STAGING;   // this group's two staging buffers
-    uint8_t* stg_ptr = sStg + grp * 2 * GEMM_STAGING;
-    uint64_t* gmfull = mfull + grp * 2;
-    const uint32_t row_off = (uint32_t)row * 128u;
-    const uint32_t sw = (uint32_t)(row & 7);
-    const int bar_id = 1 + grp;
-    auto gbar = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory"); };
-
-    uint32_t it = 0;
-    uint32_t cn = 0;          // chunks this group has committed (one bulk group per chunk); chunk cn stages in buffer cn & 1
-    uint32_t mpar = 0;        // phase bits of the two mul-operand barriers
-    bool cur_prefetched = false;
-    // completion signals owed to the A producer: slot + the commit count that must have completed (leader only)
+  } else if (warp == 3 + CHAIN_EPI_WARPS) {
+    // ===================================== store warp =========================================
+    // Staging buffer (group g, chunk ci of a tile) = sStg + (g * 2 + ci) * 16 KB; every chunked tile uses all four.
+    uint32_t itc = 0;        // chunked tiles seen
+    uint32_t cn = 0;         // stores committed
     int npend = 0, pend_slot0 = 0, pend_slot1 = 0;
     uint32_t pend_cn0 = 0, pend_cn1 = 0;
-
-    auto confirm = [&](uint32_t completed) {   // leader only
+    auto confirm = [&](uint32_t completed) {   // elected lane only
       while (npend > 0 && pend_cn0 <= completed) {
         fence_proxy_async_all();
         mbar_arrive(&ready[pend_slot0]);
@@ -301,20 +293,103 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         --npend;
       }
     };
-    // a tile-set's rows must be in L2 / HBM before the A producer may read them back: checked right before this
-    // leader issues its next store, i.e. one chunk of compute after the stores in question were issued
-    auto confirm_pending = [&]() {   // leader only
-      if (npend > 0) {
-        bulk_wait_done<0>();
-        confirm(cn);
+    // make buffer (g, ci) ready for tile t: dgrad layers get their multiplicand tile TMA-loaded into it
+    auto arm = [&](const Cursor& t, int g, int ci) {   // elected lane only
+      const ChainLayer& tl = args.layers[t.l];
+      uint64_t* bar = &rdy[g * 2 + ci];
+      if (tl.epi == EPI_MUL) {
+        const int tblk = (t.g * CHAIN_SLOTS + t.s) * n_pairs + pair;
+        mbar_expect_tx(bar, GEMM_STAGING);
+        tma_load_2d_hint(sStg + (g * 2 + ci) * GEMM_STAGING, &args.maps[t.l].tmMul, bar, t.j * 256 + (g + 2 * ci) * 64,
+                         tblk * 256 + (int)cta_rank * GEMM_BLOCK_M, L2_EVICT_FIRST);
+      } else {
+        mbar_arrive(bar);
       }
     };
-    // bias of this group's two chunks of a tile: column (grp + 2 * (i >> 6)) * 64 + (i & 63) for i < 128
-    float* gbias = bias_smem + grp * 256;
-    auto bias_fetch = [&](const Cursor& t) -> float {
-      const float* bp = args.layers[t.l].epi == EPI_HEADOUT ? nullptr : args.layers[t.l].bias;
-      // staged pre-multiplied by w0: the epilogue computes fma(acc, w0, w0 * bias)
-      return (gtid < 128 && bp != nullptr) ? args.layers[t.l].w0 * __ldg(bp + t.j * 256 + (grp + 2 * (gtid >> 6)) * 64 + (gtid & 63)) : 0.f;
+    const bool el = elect_one();
+    Cursor c, nx;
+    cur_init(c, seq);
+    // skip to the first / next tile that stages chunks (head-output tiles write straight to global memory)
+    auto next_chunked = [&](Cursor t) {
+      do { cur_next(t, seq, args); } while (!t.done && args.layers[t.l].epi == EPI_HEADOUT);
+      return t;
+    };
+    if (!c.done && el)
+      for (int k = 0; k < 4; ++k) arm(c, k >> 1, k & 1);
+    int prev_g = -1, prev_ci = -1;   // the store issued before the current one: its buffer is re-armed once it has drained
+    for (; !c.done;) {
+      const ChainLayer& ly = args.layers[c.l];
+      Cursor nx = c;
+      cur_next(nx, seq, args);
+      if (ly.epi != EPI_HEADOUT) {
+        const Cursor nc = next_chunked(c);
+        const int blk = (c.g * CHAIN_SLOTS + c.s) * n_pairs + pair;
+        const int m_out = ly.o_scratch ? (pair * CHAIN_SLOTS + c.s) * 256 + (int)cta_rank * GEMM_BLOCK_M
+                                       : blk * 256 + (int)cta_rank * GEMM_BLOCK_M;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+          const int ci = k >> 1, g = k & 1;
+          mbar_wait(&stg[g * 2 + ci], itc & 1);
+          if (el) {
+            if (npend > 0) {
+              // a tile-set's rows must be in L2 / HBM before the A producer may read them back
+              bulk_wait_done<0>();
+              confirm(cn);
+            }
+            tma_store_2d(&args.maps[c.l].tmO0, smem_u32(sStg) + (g * 2 + ci) * GEMM_STAGING, c.j * 256 + (g + 2 * ci) * 64, m_out);
+            bulk_commit();
+            ++cn;
+            if (prev_g >= 0 && !nc.done) {
+              // every store but the one just issued has drained: hand the previous chunk's buffer to the next tile
+              bulk_wait_read<1>();
+              arm(nc, prev_g, prev_ci);
+            }
+            prev_g = g;
+            prev_ci = ci;
+          }
+          __syncwarp();
+        }
+        // the buffer of the tile's last store: wait for its drain here rather than at the next tile's first store, so the
+        // next tile's math never waits for it longer than the drain takes
+        if (el && !nc.done) {
+          bulk_wait_read<0>();
+          arm(nc, 1, 1);
+        }
+        prev_g = -1;
+        ++itc;
+      }
+      if (el && c.j == ly.n_tiles - 1 && ly.epi != EPI_HEADOUT) {
+        // the tile-set (layer, slot) is committed; tell the A producer once it has landed.  Normally that is noticed before
+        // the next store; when the next tile-set is the same slot's (single-slot tail), nothing follows, or the next tiles
+        // issue no store (head outputs: this warp does not take part in them, so nothing would notice in time), wait here.
+        if (npend == 0) { pend_cn0 = cn; pend_slot0 = c.s; }
+        else { pend_cn1 = cn; pend_slot1 = c.s; }
+        ++npend;
+        if (nx.done || nx.s == c.s || args.layers[nx.l].epi == EPI_HEADOUT) {
+          bulk_wait_done<0>();
+          confirm(cn);
+        }
+      }
+      c = nx;
+    }
+    if (el) bulk_wait_all();
+  } else {
+    // ===================================== epilogue math (2 groups x 8 warps) =================
+    const int ewarp = warp - 3;               // 0..15
+    const int grp = ewarp >> 3;               // epilogue group
+    const int half = (ewarp >> 2) & 1;        // which 32 columns of a 64-column chunk
+    const int quad = warp & 3;                // TMEM lane quadrant this warp may read (warp id % 4)
+    const int row = quad * 32 + lane;         // row of the 128-row tile == TMEM lane
+    const uint32_t stg0 = smem_u32(sStg) + grp * 2 * GEMM_STAGING;   // this group's two staging buffers (chunk 0 / 1 of a tile)
+    const uint32_t row_off = (uint32_t)row * 128u;
+    const uint32_t sw = (uint32_t)(row & 7);
+    float* wbias = bias_smem + ewarp * 128;   // [tile parity][chunk][32]: this warp's bias values (x w0)
+
+    uint32_t it = 0, itc = 0;
+    auto bias_fetch = [&](const Cursor& t, int ci) -> float {   // staged pre-multiplied by w0: y = fma(acc, w0, w0 * bias)
+      const ChainLayer& tl = args.layers[t.l];
+      return (tl.epi != EPI_HEADOUT && tl.bias != nullptr)
+                 ? tl.w0 * __ldg(tl.bias + t.j * 256 + (grp + 2 * ci) * 64 + half * 32 + lane) : 0.f;
     };
 
     Cursor c, nx;
@@ -322,9 +397,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
     nx = c;
     if (!nx.done) cur_next(nx, seq, args);
     if (!c.done) {
-      const float b0 = bias_fetch(c);
-      if (gtid < 128) gbias[gtid] = b0;
-      gbar();
+      wbias[lane] = bias_fetch(c, 0);
+      wbias[32 + lane] = bias_fetch(c, 1);
+      __syncwarp();
     }
     for (; !c.done; c = nx, cur_next(nx, seq, args), ++it) {
       const ChainLayer& ly = args.layers[c.l];
@@ -333,16 +408,15 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       const uint32_t* mask = ly.mask;
       const int mask_ld = ly.mask_ld;
       const bool siren = ly.mul_siren != 0;
-      const bool next_mul = !nx.done && args.layers[nx.l].epi == EPI_MUL;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int blk = (c.g * CHAIN_SLOTS + c.s) * n_pairs + pair;
       const int m_real = blk * 256 + (int)cta_rank * GEMM_BLOCK_M;
-      const int m_scr = (pair * CHAIN_SLOTS + c.s) * 256 + (int)cta_rank * GEMM_BLOCK_M;
-      const int m_out = ly.o_scratch ? m_scr : m_real;
       const int n0 = c.j * 256;
       const bool row_ok = m_real + row < args.M;
-      const float* tbias = gbias + (it & 1) * 128;
-      float nbias = 0.f;   // next tile's bias value staged by threads 0..127 of the group
+      const uint32_t bsm = smem_u32(wbias + (it & 1) * 64);
+      // in flight while this warp waits for the accumulator: the next tile's bias slice
+      float nb0 = 0.f, nb1 = 0.f;
+      if (!nx.done) { nb0 = bias_fetch(nx, 0); nb1 = bias_fetch(nx, 1); }
 
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -402,103 +476,54 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
             }
           }
         }
-        // the next tile's bias still has to be staged (done inside the chunk loop otherwise)
-        if (!nx.done) nbias = bias_fetch(nx);
-        if (gtid < 128) gbias[((it + 1) & 1) * 128 + gtid] = nbias;
-        gbar();
       } else {
 #pragma unroll 1
-      for (int ci = 0; ci < 2; ++ci) {
-        const int ch = grp + 2 * ci;                 // 64-column chunk of the tile
-        const uint32_t b = cn & 1;                   // staging buffer of this chunk
-        const uint32_t buf0 = stg0 + b * GEMM_STAGING;
-        // the chunk after this one (same tile, or the first chunk of the next tile)
-        const bool nmul = (ci == 0) ? (epi == EPI_MUL) : next_mul;
-        if (leader && (epi == EPI_MUL || nmul)) {
-          // a mul-operand tile is TMA-loaded into the staging buffer its chunk will be multiplied in: the
-          // store that last used that buffer must have drained first
-          bulk_wait_read<0>();
-          if (epi == EPI_MUL && !cur_prefetched) {
-            mbar_expect_tx(&gmfull[b], GEMM_STAGING);
-            tma_load_2d_hint(stg_ptr + b * GEMM_STAGING, &args.maps[c.l].tmMul, &gmfull[b], n0 + ch * 64, m_real, L2_EVICT_FIRST);
-          }
-          if (nmul) {
-            const uint32_t nb = b ^ 1;
-            mbar_expect_tx(&gmfull[nb], GEMM_STAGING);
-            if (ci == 0) {
-              tma_load_2d_hint(stg_ptr + nb * GEMM_STAGING, &args.maps[c.l].tmMul, &gmfull[nb], n0 + (ch + 2) * 64, m_real, L2_EVICT_FIRST);
-            } else {
-              const int nblk = (nx.g * CHAIN_SLOTS + nx.s) * n_pairs + pair;
-              tma_load_2d_hint(stg_ptr + nb * GEMM_STAGING, &args.maps[nx.l].tmMul, &gmfull[nb], nx.j * 256 + grp * 64,
-                               nblk * 256 + (int)cta_rank * GEMM_BLOCK_M, L2_EVICT_FIRST);
+        for (int ci = 0; ci < 2; ++ci) {
+          const int ch = grp + 2 * ci;                 // 64-column chunk of the tile
+          const uint32_t buf0 = stg0 + ci * GEMM_STAGING;
+          uint64_t* brdy = &rdy[grp * 2 + ci];
+          const int colbase = n0 + ch * 64 + half * 32;
+          uint32_t mw = 0;
+          if (epi == EPI_MUL && siren && row_ok) mw = __ldg(mask + (size_t)(m_real + row) * mask_ld + (colbase >> 5));
+
+          uint32_t v[32];
+          tmem_ld32(taddr + ch * 64 + half * 32, v);
+          tc_wait_ld();
+
+          if (epi == EPI_MUL) {
+            mbar_wait(brdy, itc & 1);   // the multiplicand tile has landed in the staging buffer
+            if (!siren) chunk_mul<false, true>(v, buf0, row_off, sw, half, w0, mw);
+            else if (w0 == 1.0f) chunk_mul<true, true>(v, buf0, row_off, sw, half, w0, mw);
+            else chunk_mul<true, false>(v, buf0, row_off, sw, half, w0, mw);
+          } else {
+            uint32_t outw[16];
+            uint32_t mbits = 0;
+            const uint32_t bs = bsm + ci * 128;
+            if (epi == EPI_LINEAR) chunk_math<CM_LINEAR>(v, bs, w0, outw, mbits);
+            else if (mask == nullptr) chunk_math<CM_SIN>(v, bs, w0, outw, mbits);
+            else chunk_math<CM_SIN_MASK>(v, bs, w0, outw, mbits);
+            if (epi == EPI_SIN && mask != nullptr && row_ok)
+              const_cast<uint32_t*>(mask)[(size_t)(m_real + row) * mask_ld + (colbase >> 5)] = mbits;
+            mbar_wait(brdy, itc & 1);   // the store that last used this buffer (previous tile) has drained
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t off = row_off + ((((uint32_t)(half * 4 + g)) ^ sw) << 4);
+              st_shared_v4(buf0 + off, outw[g * 4], outw[g * 4 + 1], outw[g * 4 + 2], outw[g * 4 + 3]);
             }
           }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&stg[grp * 2 + ci]);   // 8 arrivals = chunk staged -> store warp
         }
-        cur_prefetched = nmul;
-        if (ci == 1 && !nx.done) nbias = bias_fetch(nx);   // in flight during this chunk
-        const int colbase = n0 + ch * 64 + half * 32;
-        uint32_t mw = 0;
-        if (epi == EPI_MUL && siren && row_ok) mw = __ldg(mask + (size_t)(m_real + row) * mask_ld + (colbase >> 5));
-
-        uint32_t v[32];
-        tmem_ld32(taddr + ch * 64 + half * 32, v);
-        tc_wait_ld();
-
-        if (epi == EPI_MUL) {
-          mbar_wait(&gmfull[b], (mpar >> b) & 1u);
-          mpar ^= 1u << b;
-          if (!siren) chunk_mul<false, true>(v, buf0, row_off, sw, half, w0, mw);
-          else if (w0 == 1.0f) chunk_mul<true, true>(v, buf0, row_off, sw, half, w0, mw);
-          else chunk_mul<true, false>(v, buf0, row_off, sw, half, w0, mw);
-        } else {
-          uint32_t outw[16];
-          uint32_t mbits = 0;
-          const uint32_t bsm = smem_u32(tbias + ci * 64 + half * 32);
-          if (epi == EPI_LINEAR) chunk_math<CM_LINEAR>(v, bsm, w0, outw, mbits);
-          else if (mask == nullptr) chunk_math<CM_SIN>(v, bsm, w0, outw, mbits);
-          else chunk_math<CM_SIN_MASK>(v, bsm, w0, outw, mbits);
-          if (epi == EPI_SIN && mask != nullptr && row_ok)
-            const_cast<uint32_t*>(mask)[(size_t)(m_real + row) * mask_ld + (colbase >> 5)] = mbits;
-          // results are in registers: the store that last used this buffer (two chunks ago) had the whole compute
-          // phase above to drain; the previous chunk's store (other buffer) may still be in flight
-          if (leader) bulk_wait_read<1>();
-          gbar();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint32_t off = row_off + ((((uint32_t)(half * 4 + g)) ^ sw) << 4);
-            st_shared_v4(buf0 + off, outw[g * 4], outw[g * 4 + 1], outw[g * 4 + 2], outw[g * 4 + 3]);
-          }
-        }
-        if (ci == 1 && gtid < 128) gbias[((it + 1) & 1) * 128 + gtid] = nbias;   // visible after the barrier below
-        fence_proxy_async();
-        gbar();
-        if (leader) {
-          confirm_pending();
-          tma_store_2d(&args.maps[c.l].tmO0, buf0, n0 + ch * 64, m_out);
-          bulk_commit();
-        }
-        ++cn;
-      }
+        ++itc;
       }
       tc_fence_before();
       if (lead_cta) mbar_arrive(&tempty[acc]);
       else mbar_arrive_remote(&tempty[acc], 0);   // the leader CTA's MMA warp owns the accumulator hand-shake
-
-      if (leader && c.j == ly.n_tiles - 1) {
-        // this group's part of the tile-set (layer, slot) is committed; tell the A producer once it has landed.
-        // Normally that is noticed before the next store (a tile of the other slot); when the very next tile-set
-        // belongs to the same slot (single-slot tail) or nothing follows, wait here.
-        if (npend == 0) { pend_cn0 = cn; pend_slot0 = c.s; }
-        else { pend_cn1 = cn; pend_slot1 = c.s; }
-        ++npend;
-        // (a head-output tile-set issues no store of its own, so nothing later would notice it: release it now)
-        if (nx.done || nx.s == c.s || epi == EPI_HEADOUT) {
-          bulk_wait_done<0>();
-          confirm(cn);
-        }
-      }
+      wbias[((it + 1) & 1) * 64 + lane] = nb0;
+      wbias[((it + 1) & 1) * 64 + 32 + lane] = nb1;
+      __syncwarp();
     }
-    if (leader) bulk_wait_all();
   }
 
   tc_fence_before();

@@ -18,10 +18,10 @@ constexpr int CHAIN_MAX_LAYERS = 16;
 constexpr int CHAIN_A_STAGES = 5;      // 16 KB slots (128 rows x 64 k)
 constexpr int CHAIN_B_STAGES = 4;      // 16 KB slots (this CTA's 128 of the 256 weight rows x 64 k; weights are L2-resident)
 constexpr int CHAIN_EPI_WARPS = 16;    // two groups of 8 warps; warps w and w+4 of a group split a 64-column chunk
-constexpr int CHAIN_THREADS = 96 + CHAIN_EPI_WARPS * 32;
+constexpr int CHAIN_THREADS = 96 + CHAIN_EPI_WARPS * 32 + 32;   // + the store warp
 constexpr int CHAIN_RING_BYTES = (CHAIN_A_STAGES + CHAIN_B_STAGES) * 16384;
 constexpr int CHAIN_SMEM_BYTES = CHAIN_RING_BYTES + GEMM_NUM_STAGING * GEMM_STAGING +
-                                 2048 /*bias tiles*/ + 1024 /*barriers*/ + 1024 /*alignment*/;
+                                 8192 /*per-warp bias slices*/ + 1024 /*barriers*/ + 1024 /*alignment*/;
 
 struct alignas(64) ChainMaps {   // only touched by the TMA unit
   CUtensorMap tmA[3];   // A K-segments, box {64 k, 128 rows}
