@@ -35,7 +35,7 @@ ALG_FLOP_PER_TRAIN_RAY = 64 * (16_862_208 + 14_470_144)
 ALG_FLOP_PER_RENDER_SAMPLE = 5_641_216 + 4_844_544  # all heads + the solar pass forward
 # dram__bytes_read.sum + dram__bytes_write.sum of the GEMM kernels of one 8192-ray step, from the ncu --set full capture
 # under profiles/ (filled in by tools/ncu_traffic.py; None until a capture of the current kernels exists)
-NCU_TRAFFIC_BYTES_PER_STEP = None
+NCU_TRAFFIC_BYTES_PER_STEP = 76.137e9   # profiles/r01c_ncu_step_gemms.csv (38 launches of one step)
 
 
 def peaks():
@@ -158,6 +158,77 @@ def workload_config(args, cpu=False):
 
 
 # ------------------------------------------------------------------------------------------------------
+# HBM-bound kernels of the path (K1 sample + encode, K3 composite) timed alone against the measured copy peak
+# ------------------------------------------------------------------------------------------------------
+def hbm_kernel_rooflines(lib, dev, peak_hbm, n=40960):
+    """Algorithmic bytes (DESIGN.md 4 / SURVEY 8d) / CUDA-event time, L2 flushed between repetitions."""
+    import types
+    from semnerf_b200 import synth
+    from semnerf_b200._lib import check, ptr, stream
+    from semnerf_b200.autograd import t_steps
+    from semnerf_b200.model import RSSemanticNeRFB200
+    from semnerf_b200.trainer import default_cfgs
+    S, C = N_SAMPLES, N_CLASSES
+    n_out, P = 9 + C, n * N_SAMPLES
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def timed(fn, reps=5):
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2] * 1e-3
+
+    cfgs = default_cfgs("semantic", n_samples=S, sc_lambda=0.05)
+    model = RSSemanticNeRFB200(cfgs, types.SimpleNamespace(semantic_n_classes=C)).to(dev)
+    emb = torch.nn.Embedding(50, 4).to(dev)
+    rays, extras = synth.make_rays(n, seed=1)
+    rays, extras = rays.to(dev), extras.to(dev)
+    zv = torch.empty(n, S, device=dev)
+    enc = torch.empty(P, model.enc_ld, dtype=torch.bfloat16, device=dev)
+    enc_sc = torch.empty_like(enc)
+    aux = torch.empty(P, 16, dtype=torch.bfloat16, device=dev)
+    ts, ew = t_steps(S, dev), emb.weight.detach().contiguous()
+    k1_args = (ptr(rays), ptr(extras), None, 3, 0, ptr(ts), ptr(ew), 50, 4, None, None, None, None, 0, n, S, model.kind, 0,
+               ptr(zv), ptr(enc), ptr(enc_sc), ptr(aux), None, stream())
+
+    def k1x4():
+        for _ in range(4):
+            check(lib.snb_sample_encode(*k1_args), "k1")
+    res = {}
+    t = timed(k1x4) / 4
+    b = n * 48 + P * (4 + 2 * model.enc_ld * 2 + 32)
+    res["k1_sample_encode"] = {"bound": "hbm", "achieved": b / t / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                               "frac": b / t / 1e9 / peak_hbm, "bytes": b, "us": t * 1e6,
+                               "note": "write-only kernel (main + solar rows); the measured write-only peak is ~3.9 TB/s"}
+    out = torch.rand(P, n_out, device=dev)
+    z = torch.sort(torch.rand(n, S, device=dev), dim=1).values
+    rgb, depth = torch.empty(n, 3, device=dev), torch.empty(n, device=dev)
+    w, T = torch.empty(n, S, device=dev), torch.empty(n, S, device=dev)
+    sem, lab = torch.empty(n, C, device=dev), torch.empty(n, dtype=torch.int64, device=dev)
+    t = timed(lambda: check(lib.snb_composite_forward(ptr(out), ptr(z), n, S, n_out, C, ptr(rgb), ptr(depth), ptr(w), ptr(T),
+                                                      ptr(sem), ptr(lab), stream()), "k3f"))
+    b = n * (S * (4 * n_out + 4 + 8) + 12 + 4 + 4 * C + 8)
+    res["k3_composite_forward"] = {"bound": "hbm", "achieved": b / t / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                                   "frac": b / t / 1e9 / peak_hbm, "bytes": b, "us": t * 1e6}
+    g_rgb, g_d, g_w = torch.rand(n, 3, device=dev), torch.rand(n, device=dev), torch.rand(n, S, device=dev)
+    g_sem, g_dir, g_out = torch.rand(n, C, device=dev), torch.rand(P, n_out, device=dev), torch.empty(P, n_out, device=dev)
+    t = timed(lambda: check(lib.snb_composite_backward(ptr(out), ptr(z), n, S, n_out, C, ptr(g_rgb), ptr(g_d), ptr(g_w), None,
+                                                       ptr(g_sem), ptr(g_dir), ptr(g_out), stream()), "k3b"))
+    b = n * (S * (4 * n_out + 4 + 4 + 4 * n_out + 4 * n_out) + 12 + 4 + 4 * C)
+    res["k3_composite_backward"] = {"bound": "hbm", "achieved": b / t / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                                    "frac": b / t / 1e9 / peak_hbm, "bytes": b, "us": t * 1e6}
+    res["rays"] = n
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
 def run_gpu(args):
@@ -224,8 +295,8 @@ def run_gpu(args):
 
     # ---- roofline of the dominant kernels (the tcgen05 GEMMs), timed live with CUDA events per launch ------
     # every rank runs these steps (they contain the gradient all-reduce); rank 0 reports its own launches
-    roof = cpu = render = None
-    nprof = 2
+    roof = cpu = render = hbm = None
+    nprof = 4
     snb_dist.barrier()
     lib.snb_profile_begin(1)
     for i in range(nprof):
@@ -260,6 +331,10 @@ def run_gpu(args):
         rs = nr * N_SAMPLES / (r0.elapsed_time(r1) * 1e-3)
         render = {"samples_per_s": rs, "rays": nr, "chunk_rays": 40960, "passes": "main + solar-correction",
                   "tensor_frac": rs * ALG_FLOP_PER_RENDER_SAMPLE / 1e12 / peak_tf}
+        try:
+            hbm = hbm_kernel_rooflines(lib, dev, peak_hbm)
+        except Exception as e:   # secondary numbers must not take the headline line down
+            hbm = {"error": str(e)[:200]}
         if world == 1 and not args.no_cpu:
             rps, cores, _ = cpu_training_steps(args.cpu_rays, 2, 1)
             cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
@@ -271,7 +346,7 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": clocks, "render": render, "loss": loss_host,
+            "gpu_launches": launches, "clocks": clocks, "render": render, "hbm_kernels": hbm, "loss": loss_host,
         }
         emit(line)
     snb_dist.barrier()

@@ -131,7 +131,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
   uint8_t* sB = sA + CHAIN_A_STAGES * 16384;
   uint8_t* sStg = smem + CHAIN_RING_BYTES;
   float* bias_smem = reinterpret_cast<float*>(sStg + GEMM_NUM_STAGING * GEMM_STAGING);   // [warp][tile parity][chunk][32]
-  uint64_t* fullA = reinterpret_cast<uint64_t*>(bias_smem + 2048);
+  // [tile parity][128 rows][8 words]: the sign-mask words of a tile travel as ONE 4 KB TMA tile (full 32-byte sectors) instead
+  // of one 4-byte access per thread and chunk, which cost a whole L2 sector operation each (ncu: a third of the write sectors)
+  uint32_t* mask_smem = reinterpret_cast<uint32_t*>(bias_smem + 2048);
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(mask_smem + 2048);
   uint64_t* emptyA = fullA + 8;
   uint64_t* fullB = emptyA + 8;
   uint64_t* emptyB = fullB + 8;
@@ -140,7 +143,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
   uint64_t* rdy = tempty + 2;                 // [group][chunk]: staging buffer free / multiplicand tile landed
   uint64_t* stg = rdy + GEMM_NUM_STAGING;     // [group][chunk]: chunk staged by the group's 8 warps
   uint64_t* ready = stg + GEMM_NUM_STAGING;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + CHAIN_SLOTS);
+  uint64_t* mrdy = ready + CHAIN_SLOTS;       // sign-mask tile of a dgrad tile landed (one phase per chunked tile)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mrdy + 1);
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
@@ -169,6 +173,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       mbar_init(&stg[s], 8);   // one arrival per warp of the group
     }
     for (int s = 0; s < CHAIN_SLOTS; ++s) mbar_init(&ready[s], 1);   // the store warp
+    mbar_init(mrdy, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -294,16 +299,24 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       }
     };
     // make buffer (g, ci) ready for tile t: dgrad layers get their multiplicand tile TMA-loaded into it
-    auto arm = [&](const Cursor& t, int g, int ci) {   // elected lane only
+    auto arm = [&](const Cursor& t, int g, int ci, uint32_t par) {   // elected lane only; par = parity of the tile's index
       const ChainLayer& tl = args.layers[t.l];
       uint64_t* bar = &rdy[g * 2 + ci];
+      const int trow = ((t.g * CHAIN_SLOTS + t.s) * n_pairs + pair) * 256 + (int)cta_rank * GEMM_BLOCK_M;
       if (tl.epi == EPI_MUL) {
-        const int tblk = (t.g * CHAIN_SLOTS + t.s) * n_pairs + pair;
         mbar_expect_tx(bar, GEMM_STAGING);
-        tma_load_2d_hint(sStg + (g * 2 + ci) * GEMM_STAGING, &args.maps[t.l].tmMul, bar, t.j * 256 + (g + 2 * ci) * 64,
-                         tblk * 256 + (int)cta_rank * GEMM_BLOCK_M, L2_EVICT_FIRST);
+        tma_load_2d_hint(sStg + (g * 2 + ci) * GEMM_STAGING, &args.maps[t.l].tmMul, bar, t.j * 256 + (g + 2 * ci) * 64, trow,
+                         L2_EVICT_FIRST);
       } else {
         mbar_arrive(bar);
+      }
+      if (g == 0 && ci == 0) {   // once per tile: its sign-mask words
+        if (tl.epi == EPI_MUL && tl.mul_siren) {
+          mbar_expect_tx(mrdy, 4096);
+          tma_load_2d_hint(mask_smem + par * 1024, &args.maps[t.l].tmMask, mrdy, t.j * 8, trow, L2_EVICT_FIRST);
+        } else {
+          mbar_arrive(mrdy);
+        }
       }
     };
     const bool el = elect_one();
@@ -315,7 +328,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       return t;
     };
     if (!c.done && el)
-      for (int k = 0; k < 4; ++k) arm(c, k >> 1, k & 1);
+      for (int k = 0; k < 4; ++k) arm(c, k >> 1, k & 1, 0);
     int prev_g = -1, prev_ci = -1;   // the store issued before the current one: its buffer is re-armed once it has drained
     for (; !c.done;) {
       const ChainLayer& ly = args.layers[c.l];
@@ -337,12 +350,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
               confirm(cn);
             }
             tma_store_2d(&args.maps[c.l].tmO0, smem_u32(sStg) + (g * 2 + ci) * GEMM_STAGING, c.j * 256 + (g + 2 * ci) * 64, m_out);
+            if (k == 3 && ly.epi == EPI_SIN && ly.mask != nullptr)   // all 16 warps have staged their words of the tile
+              tma_store_2d(&args.maps[c.l].tmMask, smem_u32(mask_smem) + (itc & 1) * 4096, c.j * 8, blk * 256 + (int)cta_rank * GEMM_BLOCK_M);
             bulk_commit();
             ++cn;
             if (prev_g >= 0 && !nc.done) {
               // every store but the one just issued has drained: hand the previous chunk's buffer to the next tile
               bulk_wait_read<1>();
-              arm(nc, prev_g, prev_ci);
+              arm(nc, prev_g, prev_ci, (itc + 1) & 1);
             }
             prev_g = g;
             prev_ci = ci;
@@ -353,7 +368,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         // next tile's math never waits for it longer than the drain takes
         if (el && !nc.done) {
           bulk_wait_read<0>();
-          arm(nc, 1, 1);
+          arm(nc, 1, 1, (itc + 1) & 1);
         }
         prev_g = -1;
         ++itc;
@@ -422,6 +437,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256;
 
+      uint32_t* mtile = mask_smem + (itc & 1) * 1024 + row * 8 + grp * 2 + half;   // + 4 * ci: this thread's word of chunk ci
+      uint32_t mw0 = 0, mw1 = 0;
+      if (epi == EPI_MUL && siren) {
+        mbar_wait(mrdy, itc & 1);   // the tile's sign-mask words have landed
+        mw0 = mtile[0];
+        mw1 = mtile[4];
+      }
+
       if (epi == EPI_HEADOUT) {
         // ---- 16 head pre-activations per row: one warp per TMEM lane quadrant, straight from / to global memory ----
         if (grp == 0 && half == 0) {
@@ -483,8 +506,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
           const uint32_t buf0 = stg0 + ci * GEMM_STAGING;
           uint64_t* brdy = &rdy[grp * 2 + ci];
           const int colbase = n0 + ch * 64 + half * 32;
-          uint32_t mw = 0;
-          if (epi == EPI_MUL && siren && row_ok) mw = __ldg(mask + (size_t)(m_real + row) * mask_ld + (colbase >> 5));
+          const uint32_t mw = ci ? mw1 : mw0;
 
           uint32_t v[32];
           tmem_ld32(taddr + ch * 64 + half * 32, v);
@@ -502,9 +524,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
             if (epi == EPI_LINEAR) chunk_math<CM_LINEAR>(v, bs, w0, outw, mbits);
             else if (mask == nullptr) chunk_math<CM_SIN>(v, bs, w0, outw, mbits);
             else chunk_math<CM_SIN_MASK>(v, bs, w0, outw, mbits);
-            if (epi == EPI_SIN && mask != nullptr && row_ok)
-              const_cast<uint32_t*>(mask)[(size_t)(m_real + row) * mask_ld + (colbase >> 5)] = mbits;
             mbar_wait(brdy, itc & 1);   // the store that last used this buffer (previous tile) has drained
+            if (epi == EPI_SIN && mask != nullptr) mtile[4 * ci] = mbits;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const uint32_t off = row_off + ((((uint32_t)(half * 4 + g)) ^ sw) << 4);

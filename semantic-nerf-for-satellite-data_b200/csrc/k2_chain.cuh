@@ -21,13 +21,15 @@ constexpr int CHAIN_EPI_WARPS = 16;    // two groups of 8 warps; warps w and w+4
 constexpr int CHAIN_THREADS = 96 + CHAIN_EPI_WARPS * 32 + 32;   // + the store warp
 constexpr int CHAIN_RING_BYTES = (CHAIN_A_STAGES + CHAIN_B_STAGES) * 16384;
 constexpr int CHAIN_SMEM_BYTES = CHAIN_RING_BYTES + GEMM_NUM_STAGING * GEMM_STAGING +
-                                 8192 /*per-warp bias slices*/ + 1024 /*barriers*/ + 1024 /*alignment*/;
+                                 8192 /*per-warp bias slices*/ + 8192 /*sign-mask tiles*/ + 1024 /*barriers*/ + 1024 /*alignment*/;
+static_assert(CHAIN_SMEM_BYTES <= 227 * 1024, "chained kernel: shared memory");
 
 struct alignas(64) ChainMaps {   // only touched by the TMA unit
   CUtensorMap tmA[3];   // A K-segments, box {64 k, 128 rows}
   CUtensorMap tmB;      // weights [N, K], box {64 k, 128 rows}
   CUtensorMap tmO0;     // output, box {64 columns, 128 rows}
   CUtensorMap tmMul;    // EPI_MUL multiplicand, box {64 columns, 128 rows}
+  CUtensorMap tmMask;   // sign mask (u32 words, not swizzled), box {8 words = the 256 columns of a tile, 128 rows}
 };
 
 struct ChainLayer {     // scalars every role reads once per tile: kept together so they stay in the constant cache

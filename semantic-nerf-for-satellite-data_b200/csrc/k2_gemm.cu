@@ -379,6 +379,24 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t inn
   return 0;
 }
 
+int make_tmap_mask(CUtensorMap* map, const void* ptr, uint64_t words, uint64_t rows, uint64_t row_stride_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  SNB_CHECK_ARG(fn != nullptr, SNB_ERR_NO_DEVICE, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  SNB_CHECK_ARG(ptr != nullptr && ((uintptr_t)ptr & 15) == 0 && (row_stride_bytes & 15) == 0 && words % 8 == 0, SNB_ERR_INVALID,
+                "mask tensor map: base %p / stride %llu / %llu words not 16-byte granular", ptr,
+                (unsigned long long)row_stride_bytes, (unsigned long long)words);
+  cuuint64_t dims[2] = {words, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {8, GEMM_BLOCK_M};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SNB_CHECK_ARG(r == CUDA_SUCCESS, SNB_ERR_INVALID, "cuTensorMapEncodeTiled (mask) failed (%d): %llu words x %llu rows, stride %llu",
+                (int)r, (unsigned long long)words, (unsigned long long)rows, (unsigned long long)row_stride_bytes);
+  return 0;
+}
+
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -513,6 +531,7 @@ extern "C" int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t 
     ly.mul_siren = (epi == EPI_MUL && out1 != nullptr) ? 1 : 0;
     ly.mask = epi == EPI_LINEAR ? nullptr : reinterpret_cast<uint32_t*>(out1);
     ly.mask_ld = N / 32;
+    if (!r && ly.mask) r = make_tmap_mask(&mp.tmMask, ly.mask, (uint64_t)(N / 32), (uint64_t)M, (uint64_t)(N / 32) * 4);
     ly.bias = bias;
     ly.w0 = w0;
     if (!r) r = chain_launch(*ca, (cudaStream_t)stream);

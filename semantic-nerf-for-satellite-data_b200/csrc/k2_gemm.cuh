@@ -78,6 +78,8 @@ struct GemmArgs {
 // 2-D tensor map over a row-major [outer, inner] array, 128B swizzle, zero OOB fill.
 int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t inner, uint64_t outer,
                  uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+// sign-mask tiles of the chained kernel: u32 words, [rows, words] row-major, box {8 words, 128 rows}, no swizzle
+int make_tmap_mask(CUtensorMap* map, const void* ptr, uint64_t words, uint64_t rows, uint64_t row_stride_bytes);
 
 // fills tile counts / byte counts from M, N, block_n, kb_total, splits, a_mn, b_mn
 int gemm_pick_cta_group(int epi, long long M, int N, int block_n);

@@ -592,8 +592,10 @@ struct ChainPlan {
     chk(make_tmap_2d(&mp.tmO0, out0, 2, (uint64_t)N, (uint64_t)o_rows, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
     if (epi == EPI_MUL) chk(make_tmap_2d(&mp.tmMul, mul, 2, (uint64_t)N, (uint64_t)a.M, (uint64_t)ldmul * 2, 64, GEMM_BLOCK_M));
     ly.mul_siren = (epi == EPI_MUL && mask != nullptr) ? 1 : 0;
+    if (epi == EPI_LINEAR) mask = nullptr;
     ly.mask = mask;
     ly.mask_ld = mask_ld;
+    if (mask) chk(make_tmap_mask(&mp.tmMask, mask, (uint64_t)(N / 32), (uint64_t)a.M, (uint64_t)mask_ld * 4));
     ly.o_scratch = o_scratch;
     ly.bias = bias;
     ly.w0 = w0;
