@@ -123,6 +123,19 @@ int snb_mlp_backward(const snb_model* m, const void* packed, void* workspace, si
                      int64_t n_points, const void* enc, const void* aux, const float* out,
                      const float* g_out, int head_mask, float* grads, float* g_aux, void* stream);
 
+/* fp32 verification mode ("fp32 mode" of the parity contract: rgb / depth within 1e-3 of the reference's fp32 CPU path
+ * for ANY weights, not only at the initialisers).  Same forward as snb_mlp_forward - Model.forward of
+ * satnerf.py:208-255 / rs_semantic.py:260-340 - with fp32 inputs, the fp32 weights straight from the flat parameter buffer
+ * and fp32 FMA accumulation on the CUDA cores (no bf16 anywhere, no tensor cores: B200 has no fp32 MMA).  Inference only.
+ *   xyz   (P,3) f32 sample positions (o + d*z, or o + sun_d*z for the solar-correction pass)
+ *   sun_d (R,3), t (R,tau), sky (R,3) f32: R = P / rows_per_ray rows when rows_per_ray > 1 (one per ray, broadcast over
+ *         the ray's samples like repeat_interleave in rs_semantic.py:42-61), else one row per point
+ *   out   (P, n_out) f32, packed like snb_mlp_forward; heads outside head_mask are written as 0 */
+size_t snb_mlp_fp32_workspace_bytes(const snb_model* m, int64_t n_points);
+int snb_mlp_forward_fp32(const snb_model* m, const float* params, void* workspace, size_t workspace_bytes,
+                         int64_t n_points, const float* xyz, const float* sun_d, const float* t, const float* sky,
+                         int rows_per_ray, int head_mask, float* out, void* stream);
+
 /* sky_color / embedding parameter gradients (tiny per-ray kernel).
  *   sky   (N,3) f32 from K1 (NULL: skip the sky_color gradients)
  *   g_out (P, n_out) f32 - columns 5:8 (sky) are summed per ray

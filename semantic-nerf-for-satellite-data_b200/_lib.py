@@ -37,6 +37,8 @@ SIGNATURES = {
     "snb_mlp_workspace_bytes": (_sz, [_vp, _i64, _i]),
     "snb_mlp_forward": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "snb_mlp_backward": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "snb_mlp_fp32_workspace_bytes": (_sz, [_vp, _i64]),
+    "snb_mlp_forward_fp32": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "snb_ray_param_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "snb_composite_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "snb_composite_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

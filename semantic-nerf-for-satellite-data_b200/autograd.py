@@ -162,6 +162,28 @@ def mlp_points(model, xyz, sun_d, t):
     return MLPPoints.apply(model.flat, t, model, xyz, sun_d)
 
 
+def mlp_fp32(model, xyz, sun_d, t, sky, rows_per_ray: int, head_mask: int = HEADS_ALL):
+    """fp32 verification mode of K2 (snb_mlp_forward_fp32): fp32 weights straight from the flat parameter, fp32 FMA
+    accumulation, no bf16 anywhere.  Inference only - there is no backward for this mode.
+    xyz (P,3); sun_d / t / sky one row per ray when rows_per_ray > 1, else per point."""
+    lib = _lib.load()
+    if torch.is_grad_enabled() and model.flat.requires_grad:
+        raise _lib.SnbError("fp32 mode is an inference / verification mode: call it under torch.no_grad()")
+    xyz, sun_d, t, sky = _f32c(xyz), _f32c(sun_d), _f32c(t), _f32c(sky)
+    P = xyz.shape[0]
+    cache = model.__dict__.setdefault("_ws_fp32", {})
+    nbytes = lib.snb_mlp_fp32_workspace_bytes(model._h, P)
+    key = (nbytes, str(xyz.device))
+    if key not in cache:
+        cache.clear()
+        cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device)
+    ws = cache[key]
+    out = torch.empty(P, model.number_of_outputs, dtype=torch.float32, device=xyz.device)
+    check(lib.snb_mlp_forward_fp32(model._h, ptr(model.flat.detach()), ptr(ws), ws.numel(), P, ptr(xyz), ptr(sun_d), ptr(t),
+                                   ptr(sky), rows_per_ray, head_mask, ptr(out), stream()), "snb_mlp_forward_fp32")
+    return out
+
+
 class Composite(torch.autograd.Function):
     """K3: packed head outputs (N,S,n_out) + z_vals (N,S) -> rgb, depth, weights, transparency,
     semantic scores, label  (framework/util/rendering.py:4-34 + the tail of `inference`)."""

@@ -13,7 +13,7 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libsnb.so")
-SOURCES = ["snb_host.cu", "k1_sample_encode.cu", "k2_gemm.cu", "k2_chain.cu", "k2_mlp.cu", "k3_composite.cu", "k_aux.cu"]
+SOURCES = ["snb_host.cu", "k1_sample_encode.cu", "k2_gemm.cu", "k2_chain.cu", "k2_mlp.cu", "k3_composite.cu", "k_aux.cu", "k_fp32.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
 

@@ -899,3 +899,116 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
   if (int r = run_plan(p, st)) return r;
   return run_jobs(m->unpack_jobs, true, gs, nullptr, grads, st);
 }
+
+// =====================================================================================================
+// fp32 verification mode (k_fp32.cuh): the same forward on the CUDA cores, fp32 end to end
+// =====================================================================================================
+#include "k_fp32.cuh"
+
+namespace {
+constexpr long long F32_CHUNK = 65536;   // points per pass over the layers (bounds the fp32 activation scratch)
+constexpr int F32_ENC_LD = 64;
+// per-point scratch floats: enc | hA | hB | f | g1 | g2
+constexpr long long F32_ROW_FLOATS = F32_ENC_LD + 3 * snb::F + 2 * snb::FL;
+}  // namespace
+
+extern "C" size_t snb_mlp_fp32_workspace_bytes(const snb_model* m, int64_t n_points) {
+  if (!m || n_points <= 0) return 0;
+  const long long rows = n_points < F32_CHUNK ? n_points : F32_CHUNK;
+  return (size_t)rows * F32_ROW_FLOATS * sizeof(float);
+}
+
+extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, void* workspace, size_t workspace_bytes,
+                                    int64_t n_points, const float* xyz, const float* sun_d, const float* t, const float* sky,
+                                    int rows_per_ray, int head_mask, float* out, void* stream) {
+  SNB_CHECK_ARG(m && params && workspace && xyz && out, SNB_ERR_INVALID, "mlp_forward_fp32: null argument");
+  SNB_CHECK_ARG(n_points > 0 && n_points < (1ll << 31) && rows_per_ray >= 0, SNB_ERR_INVALID, "mlp_forward_fp32: bad sizes");
+  SNB_CHECK_ARG(mask_supported(head_mask), SNB_ERR_UNSUPPORTED,
+                "mlp_forward_fp32: head_mask %d (supported: ALL=63, SOLAR=5, DEPTH=1)", head_mask);
+  const bool all = head_mask == SNB_HEADS_ALL, depth = head_mask == SNB_HEADS_DEPTH;
+  SNB_CHECK_ARG(depth || sun_d != nullptr, SNB_ERR_INVALID, "mlp_forward_fp32: sun_d required");
+  SNB_CHECK_ARG(!all || (t != nullptr && sky != nullptr), SNB_ERR_INVALID, "mlp_forward_fp32: t and sky required for all heads");
+  SNB_CHECK_ARG(workspace_bytes >= snb_mlp_fp32_workspace_bytes(m, n_points), SNB_ERR_WORKSPACE,
+                "mlp_forward_fp32: workspace %zu too small", workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool sem = m->kind == SNB_MODEL_SEMANTIC;
+  const int k0 = m->k0, tau = m->tau, n_out = m->n_out, C = m->n_classes;
+  const bool by_ray = rows_per_ray > 1;   // per-ray sun_d / t / sky rows, broadcast over the ray's samples
+  const int div = by_ray ? rows_per_ray : 1;
+  auto W = [&](const char* name) { return params + m->find((std::string(name) + ".weight").c_str()); };
+  auto B = [&](const char* name) { return params + m->find((std::string(name) + ".bias").c_str()); };
+  SNB_CUDA(cudaMemsetAsync(out, 0, (size_t)n_points * n_out * sizeof(float), st));   // heads outside head_mask read as 0
+  float* base = reinterpret_cast<float*>(workspace);
+  for (long long r0 = 0; r0 < n_points; r0 += F32_CHUNK) {
+    const int M = (int)(n_points - r0 < F32_CHUNK ? n_points - r0 : F32_CHUNK);
+    float* enc = base;
+    float* hA = enc + (long long)M * F32_ENC_LD;
+    float* hB = hA + (long long)M * F;
+    float* f = hB + (long long)M * F;
+    float* g1 = f + (long long)M * F;
+    float* g2 = g1 + (long long)M * FL;
+    float* o = out + r0 * n_out;
+    if (int r = f32_posenc_launch(xyz + r0 * 3, M, sem ? 10 : 0, enc, F32_ENC_LD, st)) return r;
+    auto gemm = [&](F32Seg s0, const F32Seg* s1, const float* w, int ldw, const float* bias, int N, int act, float w0, float* c,
+                    long long ldc) {
+      F32Gemm g;
+      memset(&g, 0, sizeof(g));
+      g.seg[0] = s0;
+      g.nseg = 1;
+      if (s1) {
+        g.seg[1] = *s1;
+        g.nseg = 2;
+      }
+      g.w = w; g.ldw = ldw; g.bias = bias; g.M = M; g.N = N; g.w0 = w0; g.act = act; g.c = c; g.ldc = ldc;
+      return f32_gemm_launch(g, st);
+    };
+    auto rows = [&](const float* a, long long lda, int k) { return F32Seg{a, lda, k, 1, 0}; };
+    auto per_ray = [&](const float* a, int k) {   // (rays, k) broadcast by row index, or (points, k)
+      return by_ray ? F32Seg{a, (long long)k, k, div, r0} : F32Seg{a + r0 * k, (long long)k, k, 1, 0};
+    };
+    const F32Seg senc = rows(enc, F32_ENC_LD, k0);
+    // trunk (satnerf.py:220-229): layer i reads cur, writes the other buffer; the skip layer reads cat(enc, h)
+    float* cur = hA;
+    float* nxt = hB;
+    for (int i = 0; i < LAYERS; ++i) {
+      const std::string nm = "fc_net." + std::to_string(2 * i);
+      int rc;
+      if (i == 0) {
+        rc = gemm(senc, nullptr, W(nm.c_str()), k0, B(nm.c_str()), F, F32_SIN, 30.0f, cur, F);
+      } else {
+        const F32Seg sh = rows(cur, F, F);
+        if (i == 4) rc = gemm(senc, &sh, W(nm.c_str()), k0 + F, B(nm.c_str()), F, F32_SIN, 1.0f, nxt, F);
+        else rc = gemm(sh, nullptr, W(nm.c_str()), F, B(nm.c_str()), F, F32_SIN, 1.0f, nxt, F);
+        float* tmp = cur; cur = nxt; nxt = tmp;
+      }
+      if (rc) return rc;
+    }
+    const F32Seg sh7 = rows(cur, F, F);
+    if (int r = gemm(sh7, nullptr, W("sigma_from_xyz.0"), F, B("sigma_from_xyz.0"), 1, F32_SOFTPLUS, 1.0f, o + 3, n_out)) return r;
+    if (depth) continue;
+    if (int r = gemm(sh7, nullptr, W("feats_from_xyz"), F, B("feats_from_xyz"), F, F32_NONE, 1.0f, f, F)) return r;
+    const F32Seg sf = rows(f, F, F);
+    {   // sun visibility: cat(f, sun_d) -> 3 x sin -> sigmoid  (satnerf.py:236-243)
+      const F32Seg ss = per_ray(sun_d, 3);
+      if (int r = gemm(sf, &ss, W("sun_v_net.0"), F + 3, B("sun_v_net.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
+      if (int r = gemm(rows(g1, FL, FL), nullptr, W("sun_v_net.2"), FL, B("sun_v_net.2"), FL, F32_SIN, 1.0f, g2, FL)) return r;
+      if (int r = gemm(rows(g2, FL, FL), nullptr, W("sun_v_net.4"), FL, B("sun_v_net.4"), FL, F32_SIN, 1.0f, g1, FL)) return r;
+      if (int r = gemm(rows(g1, FL, FL), nullptr, W("sun_v_net.6"), FL, B("sun_v_net.6"), 1, F32_SIGMOID, 1.0f, o + 4, n_out)) return r;
+    }
+    if (!all) continue;
+    if (int r = gemm(sf, nullptr, W("rgb_from_xyzdir.0"), F, B("rgb_from_xyzdir.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
+    if (int r = gemm(rows(g1, FL, FL), nullptr, W("rgb_from_xyzdir.2"), FL, B("rgb_from_xyzdir.2"), 3, F32_RGB, 1.0f, o, n_out)) return r;
+    {
+      const F32Seg st_ = per_ray(t, tau);
+      if (int r = gemm(sf, &st_, W("beta_from_xyz.0"), F + tau, B("beta_from_xyz.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
+      if (int r = gemm(rows(g1, FL, FL), nullptr, W("beta_from_xyz.2"), FL, B("beta_from_xyz.2"), 1, F32_SOFTPLUS, 1.0f, o + 8, n_out)) return r;
+    }
+    if (sem) {
+      if (int r = gemm(sf, nullptr, W("semantic_prediction.0"), F, B("semantic_prediction.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
+      if (int r = gemm(rows(g1, FL, FL), nullptr, W("semantic_prediction.2"), FL, B("semantic_prediction.2"), C,
+                       m->sem_sigmoid ? F32_SIGMOID : F32_NONE, 1.0f, o + 9, n_out)) return r;
+    }
+    if (int r = f32_sky_launch(sky, M, div, r0, o, n_out, st)) return r;
+  }
+  return 0;
+}

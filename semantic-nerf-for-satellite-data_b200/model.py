@@ -150,7 +150,20 @@ class SnbMLP(torch.nn.Module):
     def forward(self, input_xyz, input_dir=None, input_sun_dir=None, input_t=None, input_t_s=None, epoch=None):
         """(B,3),(B,3),(B,tau) -> (B, 9[+C]) packed exactly like the reference's forward
         (satnerf.py:208-255, rs_semantic.py:260-313)."""
-        from .autograd import mlp_points
+        from .autograd import mlp_fp32, mlp_points
+        if getattr(self, "precision", "bf16") == "fp32":   # verification mode: fp32 end to end, inference only
+            lib = _lib.load()
+            xyz = input_xyz.float().contiguous()
+            sun, tt = input_sun_dir.float().contiguous(), input_t.detach().float().contiguous()
+            P, dev = xyz.shape[0], xyz.device
+            # K1's point encoder supplies the per-point sky colour (fp32); its bf16 encodings are not used in this mode
+            enc = torch.empty(P, self.enc_ld, dtype=torch.bfloat16, device=dev)
+            aux = torch.empty(P, 16, dtype=torch.bfloat16, device=dev)
+            sky = torch.empty(P, 3, dtype=torch.float32, device=dev)
+            w1, b1, w2, b2 = self.sky_params()
+            check(lib.snb_encode_points(ptr(xyz), ptr(sun), ptr(tt), tt.shape[1], ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+                                        w1.shape[0], P, self.kind, ptr(enc), ptr(aux), ptr(sky), stream()), "snb_encode_points")
+            return mlp_fp32(self, xyz, sun, tt, sky, 0, HEADS_ALL)
         return mlp_points(self, input_xyz, input_sun_dir, input_t)
 
 

@@ -12,14 +12,16 @@ render_options (all optional, default = reference behaviour):
   "u" (N,S) / "z_vals" (N,S): replace the random jitter (parity tests; the reference's
       ``given_z_vals`` hook, rendering.py:91-92);  "seed", "ray_offset": Philox key / global ray index;
   "heads": "all" | "depth" - "depth" evaluates only trunk + sigma (what the depth-supervision
-      batch consumes, semantic/components/training_step.py:32-46) and skips the solar pass.
+      batch consumes, semantic/components/training_step.py:32-46) and skips the solar pass;
+  "precision": "bf16" (default: the tcgen05 path) | "fp32" - the fp32 verification mode (fp32 weights and
+      accumulation on the CUDA cores, inference only; also selected by cfgs.pipeline.precision = "fp32").
 """
 from __future__ import annotations
 
 import torch
 
 from ._lib import HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, MODEL_SEMANTIC
-from .autograd import Composite, MLPRays, encode_rays
+from .autograd import Composite, MLPRays, encode_rays, mlp_fp32
 
 
 class B200Renderer:
@@ -49,7 +51,16 @@ class B200Renderer:
                                                ray_offset=int(opts.get("ray_offset", 0)), want_sc=sc)
         C = model.semantic_n_classes
         mask = HEADS_DEPTH if depth_only else HEADS_ALL
-        out = MLPRays.apply(model.flat, emb, model, enc, aux, sky, extras, n, S, mask).view(n, S, -1)
+        fp32 = opts.get("precision", getattr(cfgs.pipeline, "precision", "bf16")) == "fp32"
+        if fp32:
+            # sample positions exactly as the reference forms them (framework/components/rendering.py:113-115) and the
+            # per-ray inputs in fp32; K1 above still supplies z_vals (bit-exact) and the per-ray sky colour (fp32)
+            o, d, sun_d = rays[:, 0:3].float(), rays[:, 3:6].float(), extras[:, 0:3].float()
+            t_ray = emb[extras[:, 3].long()].float() if emb is not None else None
+            xyz_main = (o.unsqueeze(1) + d.unsqueeze(1) * z.unsqueeze(2)).reshape(-1, 3)
+            out = mlp_fp32(model, xyz_main, sun_d, t_ray, sky, S, mask).view(n, S, -1)
+        else:
+            out = MLPRays.apply(model.flat, emb, model, enc, aux, sky, extras, n, S, mask).view(n, S, -1)
         rgb, depth, weights, transp, sem, label = Composite.apply(out, z, C)
         result = {
             "rgb": rgb, "depth": depth, "weights": weights, "transparency": transp,
@@ -61,7 +72,11 @@ class B200Renderer:
             result["semantic_label"] = label
         if sc:
             # solar correction: second pass on o + sun_d*z, keeping weights / transparency / sun
-            out_sc = MLPRays.apply(model.flat, emb, model, enc_sc, aux, None, extras, n, S, HEADS_SOLAR).view(n, S, -1)
+            if fp32:
+                xyz_sc = (o.unsqueeze(1) + sun_d.unsqueeze(1) * z.unsqueeze(2)).reshape(-1, 3)
+                out_sc = mlp_fp32(model, xyz_sc, sun_d, None, None, S, HEADS_SOLAR).view(n, S, -1)
+            else:
+                out_sc = MLPRays.apply(model.flat, emb, model, enc_sc, aux, None, extras, n, S, HEADS_SOLAR).view(n, S, -1)
             _, _, w_sc, t_sc, _, _ = Composite.apply(out_sc, z, 0)  # no semantic columns to composite
             result["weights_sc"] = w_sc
             result["transparency_sc"] = t_sc

@@ -194,3 +194,63 @@ def test_chained_mlp_equals_per_layer_mlp(kind, C, P):
     ga, gb = res[1][1].double(), res[0][1].double()
     assert (ga - gb).abs().max() <= 1e-3 * gb.abs().max() and _cos(ga, gb) >= 0.999999
     assert _cos(res[1][2], res[0][2]) >= 0.999999
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fp32 verification mode (snb_mlp_forward_fp32): the parity contract's "fp32 mode" - rgb / depth within 1e-3 abs of
+# the reference's fp32 path for ANY weights (the trained-like case included), here held to 2e-5
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c[0] for c in GOLDEN_CASES])
+def test_fp32_mode_render_rays_against_reference_golden(case):
+    from semnerf_b200.renderer import B200Renderer
+    _lib_or_fail()
+    name, kind, C, feat, n, s, sc, seed = case
+    spec, params, emb, rays, extras, u, gold = golden_inputs(case)
+    _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"))
+    renderer = B200Renderer(cfgs)
+    with torch.no_grad():
+        res = renderer.render_rays({"coarse": model, "t": t}, rays.to(DEV), extras.to(DEV),
+                                   render_options={"u": u.to(DEV), "precision": "fp32"})
+    worst = {}
+    for k, g in gold.items():
+        if k in ("loss_satnerf", "model_forward", "grad_norms"):
+            continue
+        got = res[k].cpu().numpy()
+        assert got.shape == g.shape and got.dtype == g.dtype, k
+        if k == "semantic_label_coarse":
+            # fp32 against fp32: labels agree wherever the top-2 margin is above the fp32 noise floor
+            lg = gold["semantic_logits_coarse"]
+            top2 = np.sort(lg, axis=1)[:, -2:]
+            sure = (top2[:, 1] - top2[:, 0]) > 1e-4
+            assert (got[sure] == g[sure]).all()
+            continue
+        worst[k] = float(np.abs(got - g).max())
+        # sigma / beta are unbounded softplus outputs: relative tolerance on their scale
+        scale = max(1.0, float(np.abs(g).max())) if k in ("sigmas_coarse", "beta_coarse") else 1.0
+        assert worst[k] <= 2e-5 * scale, (k, worst[k])
+    assert worst["rgb_coarse"] <= 1e-3 and worst["depth_coarse"] <= 1e-3   # the contract's bar, met with margin
+
+
+@pytest.mark.parametrize("kind,C", [("semantic", 6), ("satnerf", 0)])
+def test_fp32_mode_model_forward_matches_fp64_oracle(kind, C):
+    """Model.forward in fp32 mode vs the oracle in fp64 on the same points, incl. a ragged multi-chunk point count."""
+    _lib_or_fail()
+    spec, params, emb, cfgs, model, t = _model(kind, C, seed=2, trained_like=True)
+    P = 65536 + 777   # two passes of the chunked fp32 evaluation, ragged tail
+    g = torch.Generator().manual_seed(1)
+    xyz = torch.rand(P, 3, generator=g) * 2 - 1
+    sun = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=1)
+    tt = torch.randn(P, 4, generator=g)
+    p64 = {k: v.double() for k, v in params.items()}
+    ref = O.mlp_forward(p64, spec, xyz.double(), sun.double(), tt.double())
+    model.precision = "fp32"
+    try:
+        with torch.no_grad():
+            out = model(xyz.to(DEV), input_sun_dir=sun.to(DEV), input_t=tt.to(DEV))
+        with pytest.raises(Exception):
+            model(xyz[:8].to(DEV), input_sun_dir=sun[:8].to(DEV), input_t=tt[:8].to(DEV))   # grad mode: refused
+    finally:
+        model.precision = "bf16"
+    d = (out.cpu().double() - ref).abs()
+    rel = d / ref.abs().clamp(min=1.0)
+    assert rel.max() <= 5e-5, float(rel.max())
