@@ -73,10 +73,11 @@ class MLPRays(torch.autograd.Function):
     """K2 on ray samples: (flat params, embedding table) -> packed (P, n_out) head outputs."""
 
     @staticmethod
-    def forward(ctx, flat, emb_weight, model, enc, aux, sky, extras, n_rays, n_samples, head_mask):
+    def forward(ctx, flat, emb_weight, model, enc, aux, sky, extras, n_rays, n_samples, head_mask, train):
+        # `train` comes from the caller (mlp_rays): grad mode is always off inside forward(), and needs_input_grad is
+        # True for a parameter even under torch.no_grad(), which would make every render save its activations
         lib = _lib.load()
         P = n_rays * n_samples
-        train = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])  # grad mode is off inside forward()
         ws = _workspace(model, P, train, enc.device)
         out = torch.empty(P, model.number_of_outputs, dtype=torch.float32, device=enc.device)
         packed = model.packed()
@@ -109,19 +110,18 @@ class MLPRays(torch.autograd.Function):
             check(lib.snb_ray_param_backward(model._h, ptr(flat.detach()), ptr(extras), ptr(sky_arg), ptr(g_out),
                                              ptr(g_aux), n_rays, S, model.number_of_outputs, tau, vocab,
                                              ptr(g_flat), ptr(g_emb), stream()), "snb_ray_param_backward")
-        return g_flat, g_emb, None, None, None, None, None, None, None, None
+        return g_flat, g_emb, None, None, None, None, None, None, None, None, None
 
 
 class MLPPoints(torch.autograd.Function):
     """K2 on caller-supplied points: the reference's Model.forward (satnerf.py:208, rs_semantic.py:260)."""
 
     @staticmethod
-    def forward(ctx, flat, t, model, xyz, sun_d):
+    def forward(ctx, flat, t, model, xyz, sun_d, train):
         lib = _lib.load()
         xyz, sun_d, tt = _f32c(xyz), _f32c(sun_d), _f32c(t.detach())
         P = xyz.shape[0]
         dev = xyz.device
-        train = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])  # grad mode is off inside forward()
         enc = torch.empty(P, model.enc_ld, dtype=torch.bfloat16, device=dev)
         aux = torch.empty(P, 16, dtype=torch.bfloat16, device=dev)
         sky = torch.empty(P, 3, dtype=torch.float32, device=dev)
@@ -155,11 +155,22 @@ class MLPPoints(torch.autograd.Function):
         check(lib.snb_ray_param_backward(model._h, ptr(flat.detach()), ptr(extras), ptr(sky), ptr(g_out), None, P, 1,
                                          model.number_of_outputs, 0, 1, ptr(g_flat), None, stream()),
               "snb_ray_param_backward")
-        return g_flat, g_aux[:, 4:4 + ctx.tau].contiguous(), None, None, None
+        return g_flat, g_aux[:, 4:4 + ctx.tau].contiguous(), None, None, None, None
+
+
+def _wants_grad(*tensors) -> bool:
+    """Does this call have to save activations for a backward pass?  (decided OUTSIDE the autograd.Function)"""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
 def mlp_points(model, xyz, sun_d, t):
-    return MLPPoints.apply(model.flat, t, model, xyz, sun_d)
+    return MLPPoints.apply(model.flat, t, model, xyz, sun_d, _wants_grad(model.flat, t))
+
+
+def mlp_rays(model, emb_weight, enc, aux, sky, extras, n_rays, n_samples, head_mask):
+    """K2 on ray samples; inference (no saved activations, per-SM-pair L2 scratch) unless a gradient is required."""
+    return MLPRays.apply(model.flat, emb_weight, model, enc, aux, sky, extras, n_rays, n_samples, head_mask,
+                         _wants_grad(model.flat, emb_weight))
 
 
 def mlp_fp32(model, xyz, sun_d, t, sky, rows_per_ray: int, head_mask: int = HEADS_ALL):

@@ -21,7 +21,7 @@ from __future__ import annotations
 import torch
 
 from ._lib import HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, MODEL_SEMANTIC
-from .autograd import Composite, MLPRays, encode_rays, mlp_fp32
+from .autograd import Composite, encode_rays, mlp_fp32, mlp_rays
 
 
 class B200Renderer:
@@ -60,7 +60,7 @@ class B200Renderer:
             xyz_main = (o.unsqueeze(1) + d.unsqueeze(1) * z.unsqueeze(2)).reshape(-1, 3)
             out = mlp_fp32(model, xyz_main, sun_d, t_ray, sky, S, mask).view(n, S, -1)
         else:
-            out = MLPRays.apply(model.flat, emb, model, enc, aux, sky, extras, n, S, mask).view(n, S, -1)
+            out = mlp_rays(model, emb, enc, aux, sky, extras, n, S, mask).view(n, S, -1)
         rgb, depth, weights, transp, sem, label = Composite.apply(out, z, C)
         result = {
             "rgb": rgb, "depth": depth, "weights": weights, "transparency": transp,
@@ -76,7 +76,7 @@ class B200Renderer:
                 xyz_sc = (o.unsqueeze(1) + sun_d.unsqueeze(1) * z.unsqueeze(2)).reshape(-1, 3)
                 out_sc = mlp_fp32(model, xyz_sc, sun_d, None, None, S, HEADS_SOLAR).view(n, S, -1)
             else:
-                out_sc = MLPRays.apply(model.flat, emb, model, enc_sc, aux, None, extras, n, S, HEADS_SOLAR).view(n, S, -1)
+                out_sc = mlp_rays(model, emb, enc_sc, aux, None, extras, n, S, HEADS_SOLAR).view(n, S, -1)
             _, _, w_sc, t_sc, _, _ = Composite.apply(out_sc, z, 0)  # no semantic columns to composite
             result["weights_sc"] = w_sc
             result["transparency_sc"] = t_sc

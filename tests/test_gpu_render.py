@@ -136,9 +136,14 @@ def test_render_depth_only_heads_and_no_grad_path():
         dep = r.render_rays(models, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV), "heads": "depth"})
     assert torch.equal(full["depth_coarse"], dep["depth_coarse"]) and torch.equal(full["weights_coarse"], dep["weights_coarse"])
     assert "weights_sc_coarse" not in dep
+    # under no_grad the MLP ran in inference mode (cached inference workspace: L2 scratch, no saved activations) although
+    # the parameters require grad; with grad enabled it does not touch that cache
+    assert len(model.__dict__.get("_ws_infer", {})) == 1
+    model.__dict__["_ws_infer"].clear()
     # depth-only backward touches trunk + sigma only
     dep = r.render_rays(models, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV), "heads": "depth"})
     dep["depth_coarse"].sum().backward()
+    assert len(model.__dict__["_ws_infer"]) == 0
     g = model.named_grads()
     assert g["fc_net.0.weight"].abs().sum() > 0 and g["sigma_from_xyz.0.weight"].abs().sum() > 0
     assert g["rgb_from_xyzdir.0.weight"].abs().sum() == 0 and g["feats_from_xyz.weight"].abs().sum() == 0
