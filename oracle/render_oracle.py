@@ -50,6 +50,8 @@ class ModelSpec:
     kind = "satnerf":  baseline/models/satnerf.py:101-206 (mapping=False: raw xyz input,
                        baseline/pipelines/satnerf.py:53-59 never overrides the default)
     kind = "semantic": semantic/models/rs_semantic.py:139-258 (positional Mapping always on)
+    kind = "snerf":    baseline/models/snerf.py:104-188 (ShadowNeRF as baseline/pipelines/snerf.py:24-32 builds it:
+                       SIREN, raw xyz): SatNeRF without the transient-uncertainty head and embedding, 8 outputs
     """
 
     kind: str = "semantic"
@@ -73,6 +75,8 @@ class ModelSpec:
 
     @property
     def n_out(self) -> int:
+        if self.kind == "snerf":
+            return 8
         return 9 + (self.n_classes if self.kind == "semantic" else 0)
 
 
@@ -114,6 +118,8 @@ def param_shapes(spec: ModelSpec) -> Dict[str, tuple]:
     s["sky_color.0.bias"] = (fl,)
     s["sky_color.2.weight"] = (3, fl)
     s["sky_color.2.bias"] = (3,)
+    if spec.kind == "snerf":   # snerf.py:161-186: no beta head
+        return s
     s["beta_from_xyz.0.weight"] = (fl, f + spec.tau)
     s["beta_from_xyz.0.bias"] = (fl,)
     s["beta_from_xyz.2.weight"] = (1, fl)
@@ -226,6 +232,9 @@ def mlp_forward(p: Dict[str, torch.Tensor], spec: ModelSpec, xyz: torch.Tensor,
     s = torch.sin(_lin(p, "sun_v_net.4", s))
     sun_v = torch.sigmoid(_lin(p, "sun_v_net.6", s))
     sky = torch.sigmoid(_lin(p, "sky_color.2", torch.relu(_lin(p, "sky_color.0", sun_d))))
+    if spec.kind == "snerf":   # snerf.py:226-242: [rgb | sigma | sun_v | sky]
+        out = torch.cat([rgb, sigma, sun_v, sky], 1)
+        return (out, hidden, f) if return_hidden else out
     beta = F.softplus(_lin(p, "beta_from_xyz.2", torch.sin(_lin(p, "beta_from_xyz.0", torch.cat([f, t], -1)))))
     cols = [rgb, sigma, sun_v, sky, beta]
     if spec.kind == "semantic":
@@ -260,14 +269,17 @@ def convert_sigmas(sigmas: torch.Tensor, z: torch.Tensor):
 def composite(out: torch.Tensor, z: torch.Tensor, n_classes: int = 0) -> Dict[str, torch.Tensor]:
     """Tail of ``inference``: satnerf.py:73-96 / rs_semantic.py:81-126.  ``out`` is (N,S,9[+C])."""
     rgbs, sigmas = out[..., :3], out[..., 3]
-    sun_v, sky, beta = out[..., 4:5], out[..., 5:8], out[..., 8:9]
+    sun_v, sky = out[..., 4:5], out[..., 5:8]
     weights, depth, transparency, _ = convert_sigmas(sigmas, z)
     irradiance = sun_v + (1 - sun_v) * sky
     rgb = torch.clamp(torch.sum(weights.unsqueeze(-1) * rgbs * irradiance, -2), min=0.0, max=1.0)
     res = {
         "rgb": rgb, "depth": depth, "weights": weights, "transparency": transparency,
-        "albedo": rgbs, "sun": sun_v, "sky": sky, "beta": beta, "sigmas": sigmas,
+        "albedo": rgbs, "sun": sun_v, "sky": sky,
     }
+    if out.shape[-1] > 8:   # SatNeRF / semantic (satnerf.py:73-96); S-NeRF's inference returns neither (snerf.py:86-96)
+        res["beta"] = out[..., 8:9]
+        res["sigmas"] = sigmas
     if n_classes > 0:
         sem = out[..., 9:9 + n_classes]
         logits = torch.sum(weights.unsqueeze(-1) * sem, -2)
@@ -282,8 +294,8 @@ def inference(p, spec: ModelSpec, xyz: torch.Tensor, z: torch.Tensor, sun_d: tor
     """satnerf.py:8-98 / rs_semantic.py:8-128 (per-ray inputs broadcast over samples,
     model evaluated on all points, then composited)."""
     n, s = z.shape
-    out = mlp_forward(p, spec, xyz.reshape(-1, 3),
-                      torch.repeat_interleave(sun_d, s, 0), torch.repeat_interleave(t, s, 0))
+    out = mlp_forward(p, spec, xyz.reshape(-1, 3), torch.repeat_interleave(sun_d, s, 0),
+                      torch.repeat_interleave(t, s, 0) if t is not None else None)
     return composite(out.view(n, s, -1), z, spec.n_classes if spec.kind == "semantic" else 0)
 
 
@@ -299,7 +311,7 @@ def render_rays(p, emb: torch.Tensor, spec: ModelSpec, rays: torch.Tensor, extra
     o, d = rays[:, 0:3], rays[:, 3:6]
     sun_d = extras[:, 0:3]
     ts = extras[:, 3].long()
-    t = emb[ts]
+    t = emb[ts] if spec.kind != "snerf" else None   # S-NeRF has no embedding (baseline/components/rendering.py:70-100)
     res = inference(p, spec, sample_points(o, d, z), z, sun_d, t)
     if sc_lambda > 0:
         tmp = inference(p, spec, sample_points(o, sun_d, z), z, sun_d, t)

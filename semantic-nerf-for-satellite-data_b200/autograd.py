@@ -79,7 +79,7 @@ class MLPRays(torch.autograd.Function):
         lib = _lib.load()
         P = n_rays * n_samples
         ws = _workspace(model, P, train, enc.device)
-        out = torch.empty(P, model.number_of_outputs, dtype=torch.float32, device=enc.device)
+        out = torch.empty(P, model.n_out_kernel, dtype=torch.float32, device=enc.device)
         packed = model.packed()
         check(lib.snb_mlp_forward(model._h, ptr(packed), ptr(ws), ws.numel(), P, ptr(enc), ptr(aux), ptr(sky),
                                   n_samples, head_mask, 1 if train else 0, ptr(out), stream()), "snb_mlp_forward")
@@ -108,7 +108,7 @@ class MLPRays(torch.autograd.Function):
         if sky_arg is not None or g_aux is not None:
             vocab, tau = (emb_weight.shape if want_emb else (1, 0))
             check(lib.snb_ray_param_backward(model._h, ptr(flat.detach()), ptr(extras), ptr(sky_arg), ptr(g_out),
-                                             ptr(g_aux), n_rays, S, model.number_of_outputs, tau, vocab,
+                                             ptr(g_aux), n_rays, S, model.n_out_kernel, tau, vocab,
                                              ptr(g_flat), ptr(g_emb), stream()), "snb_ray_param_backward")
         return g_flat, g_emb, None, None, None, None, None, None, None, None, None
 
@@ -130,7 +130,7 @@ class MLPPoints(torch.autograd.Function):
                                     w1.shape[0], P, model.kind, ptr(enc), ptr(aux), ptr(sky), stream()),
               "snb_encode_points")
         ws = _workspace(model, P, train, dev)
-        out = torch.empty(P, model.number_of_outputs, dtype=torch.float32, device=dev)
+        out = torch.empty(P, model.n_out_kernel, dtype=torch.float32, device=dev)
         packed = model.packed()
         check(lib.snb_mlp_forward(model._h, ptr(packed), ptr(ws), ws.numel(), P, ptr(enc), ptr(aux), ptr(sky), 0,
                                   HEADS_ALL, 1 if train else 0, ptr(out), stream()), "snb_mlp_forward")
@@ -153,7 +153,7 @@ class MLPPoints(torch.autograd.Function):
                                    ptr(g_out), HEADS_ALL, ptr(g_flat), ptr(g_aux), stream()), "snb_mlp_backward")
         extras = torch.cat([sun_d, torch.zeros(P, 1, device=sun_d.device)], 1).contiguous()
         check(lib.snb_ray_param_backward(model._h, ptr(flat.detach()), ptr(extras), ptr(sky), ptr(g_out), None, P, 1,
-                                         model.number_of_outputs, 0, 1, ptr(g_flat), None, stream()),
+                                         model.n_out_kernel, 0, 1, ptr(g_flat), None, stream()),
               "snb_ray_param_backward")
         return g_flat, g_aux[:, 4:4 + ctx.tau].contiguous(), None, None, None, None
 
@@ -189,7 +189,7 @@ def mlp_fp32(model, xyz, sun_d, t, sky, rows_per_ray: int, head_mask: int = HEAD
         cache.clear()
         cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device)
     ws = cache[key]
-    out = torch.empty(P, model.number_of_outputs, dtype=torch.float32, device=xyz.device)
+    out = torch.empty(P, model.n_out_kernel, dtype=torch.float32, device=xyz.device)
     check(lib.snb_mlp_forward_fp32(model._h, ptr(model.flat.detach()), ptr(ws), ws.numel(), P, ptr(xyz), ptr(sun_d), ptr(t),
                                    ptr(sky), rows_per_ray, head_mask, ptr(out), stream()), "snb_mlp_forward_fp32")
     return out

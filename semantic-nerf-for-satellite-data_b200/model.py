@@ -34,6 +34,8 @@ class SnbMLP(torch.nn.Module):
         self.kind = kind
         self.semantic_n_classes = n_classes          # read by the reference's inference(), rs_semantic.py:95
         self.number_of_outputs = 9 + n_classes       # satnerf.py:120
+        self.n_out_kernel = 9 + n_classes            # columns of the packed tensor the kernels write
+        self.hidden_prefixes: Tuple[str, ...] = ()   # tensors of the flat buffer a model variant does not own (S-NeRF)
         self.t_embedding_dims = tau
         self.enc_ld = 128 if kind == MODEL_SEMANTIC else 64
         n = lib.snb_model_param_count(h)
@@ -72,6 +74,8 @@ class SnbMLP(torch.nn.Module):
         """Reference-named views into the flat parameter."""
         out = OrderedDict()
         for name, off, shape in self.table:
+            if name.startswith(self.hidden_prefixes) and self.hidden_prefixes:
+                continue
             n = int(torch.tensor(shape).prod())
             out[name] = self.flat.detach()[off:off + n].view(shape)  # detach(): shares the version counter
         return out
@@ -80,6 +84,8 @@ class SnbMLP(torch.nn.Module):
         g = self.flat.grad
         out = {}
         for name, off, shape in self.table:
+            if name.startswith(self.hidden_prefixes) and self.hidden_prefixes:
+                continue
             n = int(torch.tensor(shape).prod())
             out[name] = None if g is None else g[off:off + n].view(shape)
         return out
@@ -195,3 +201,34 @@ class RSSemanticNeRFB200(SnbMLP):
         super().__init__(MODEL_SEMANTIC, int(dataset_semantic.semantic_n_classes), sig, p.t_embedding_tau, cfgs)
         self.cfg = p
         self.layers, self.skips = p.fc_layers, list(p.fc_skips)
+
+
+class ShadowNeRFB200(SnbMLP):
+    """Drop-in for baseline.models.snerf.ShadowNeRF as the S-NeRF pipeline builds it (baseline/pipelines/snerf.py:24-32:
+    8x512 SIREN, raw xyz, skip [4]; constructor signature snerf.py:104-112).
+
+    S-NeRF is SatNeRF without the transient-uncertainty head and its embedding (snerf.py:161-186 vs satnerf.py:143-206):
+    same trunk, sigma, feats, albedo, sun-visibility and sky heads, outputs [rgb | sigma | sun_v | sky] (8 columns).  It
+    runs on the SatNeRF kernel plan; the beta block of the fused head layer is held at zero weights, is not part of
+    ``state_dict()`` / ``named_tensors()`` and receives no gradient (nothing downstream reads column 8), so checkpoints
+    interchange with the reference's ShadowNeRF."""
+
+    def __init__(self, layers=8, feat=512, mapping=False, mapping_sizes=(10, 4), skips=(4,), siren=True):
+        if layers != 8 or feat != 512 or list(skips) != [4] or mapping or not siren:
+            raise _lib.SnbError("libsnb implements the shipped S-NeRF configuration: 8x512 SIREN, skip [4], raw-xyz input "
+                                "(configs/pipelines/snerf.toml, baseline/pipelines/snerf.py:24-32)")
+        super().__init__(MODEL_SATNERF, 0, True, 4, None)
+        self.variant = "snerf"
+        self.number_of_outputs = 8                   # snerf.py:117-119
+        self.layers, self.skips = layers, list(skips)
+        with torch.no_grad():
+            for name, off, shape in self.table:
+                if name.startswith("beta_from_xyz."):
+                    self.flat[off:off + int(torch.tensor(shape).prod())] = 0
+        self.hidden_prefixes = ("beta_from_xyz.",)
+
+    def forward(self, input_xyz, input_dir=None, input_sun_dir=None, sigma_only=False):
+        """(B,3), -, (B,3) -> (B,8) [rgb | sigma | sun_v | sky]  (snerf.py:190-243); sigma_only -> (B,1)."""
+        t = torch.zeros(input_xyz.shape[0], self.t_embedding_dims, dtype=torch.float32, device=input_xyz.device)
+        out = super().forward(input_xyz, input_sun_dir=input_sun_dir, input_t=t)
+        return out[:, 3:4] if sigma_only else out[:, :8]

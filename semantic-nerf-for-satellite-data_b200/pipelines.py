@@ -3,7 +3,7 @@
 The reference selects a pipeline by dotted class path in the pipeline TOML
 (`pipeline = "semantic.pipelines.rs_semantic.RSSemanticPipeline"`, configs/pipelines/rs_semantic.toml:5;
 resolved by framework/pipelines.py:341-352).  Pointing that line at
-`semnerf_b200.pipelines.RSSemanticB200Pipeline` / `SatNeRFB200Pipeline` swaps the B200 model and
+`semnerf_b200.pipelines.RSSemanticB200Pipeline` / `SatNeRFB200Pipeline` / `SNeRFB200Pipeline` swaps the B200 model and
 renderer in; datasets, losses, training step, visualisers and checkpoints are the reference's own.
 Only `_init_models` and `_init_renderer` are overridden (semantic/pipelines/rs_semantic.py:61-79,
 baseline/pipelines/satnerf.py:51-69).
@@ -15,8 +15,8 @@ from __future__ import annotations
 
 import torch
 
-from .model import RSSemanticNeRFB200, SatNeRFB200
-from .renderer import RSSemanticB200Rendering, SatNeRFB200Rendering
+from .model import RSSemanticNeRFB200, SatNeRFB200, ShadowNeRFB200
+from .renderer import RSSemanticB200Rendering, SatNeRFB200Rendering, SNeRFB200Rendering
 
 _CACHE = {}
 
@@ -25,7 +25,16 @@ def get_pipeline_classes():
     if _CACHE:
         return _CACHE
     from baseline.pipelines.satnerf import SatNeRFPipeline          # reference checkout on sys.path
+    from baseline.pipelines.snerf import SNerfPipeline
     from semantic.pipelines.rs_semantic import RSSemanticPipeline
+
+    class SNeRFB200Pipeline(SNerfPipeline):
+        def _init_models(self) -> dict:   # baseline/pipelines/snerf.py:24-32
+            p = self.cfgs.pipeline
+            return {"coarse": ShadowNeRFB200(layers=p.fc_layers, feat=p.fc_units, skips=p.fc_skips)}
+
+        def _init_renderer(self):         # baseline/pipelines/snerf.py:34-35
+            return SNeRFB200Rendering(self.cfgs)
 
     class SatNeRFB200Pipeline(SatNeRFPipeline):
         def _init_models(self) -> dict:
@@ -46,11 +55,12 @@ def get_pipeline_classes():
         def _init_renderer(self):
             return RSSemanticB200Rendering(self.cfgs)
 
-    _CACHE.update(SatNeRFB200Pipeline=SatNeRFB200Pipeline, RSSemanticB200Pipeline=RSSemanticB200Pipeline)
+    _CACHE.update(SatNeRFB200Pipeline=SatNeRFB200Pipeline, RSSemanticB200Pipeline=RSSemanticB200Pipeline,
+                  SNeRFB200Pipeline=SNeRFB200Pipeline)
     return _CACHE
 
 
 def __getattr__(name):  # `semnerf_b200.pipelines.RSSemanticB200Pipeline` resolves through importlib
-    if name in ("SatNeRFB200Pipeline", "RSSemanticB200Pipeline"):
+    if name in ("SatNeRFB200Pipeline", "RSSemanticB200Pipeline", "SNeRFB200Pipeline"):
         return get_pipeline_classes()[name]
     raise AttributeError(name)

@@ -56,7 +56,7 @@ class B200Renderer:
             # sample positions exactly as the reference forms them (framework/components/rendering.py:113-115) and the
             # per-ray inputs in fp32; K1 above still supplies z_vals (bit-exact) and the per-ray sky colour (fp32)
             o, d, sun_d = rays[:, 0:3].float(), rays[:, 3:6].float(), extras[:, 0:3].float()
-            t_ray = emb[extras[:, 3].long()].float() if emb is not None else None
+            t_ray = emb[extras[:, 3].long()].float() if emb is not None else torch.zeros(n, 4, device=rays.device)
             xyz_main = (o.unsqueeze(1) + d.unsqueeze(1) * z.unsqueeze(2)).reshape(-1, 3)
             out = mlp_fp32(model, xyz_main, sun_d, t_ray, sky, S, mask).view(n, S, -1)
         else:
@@ -70,6 +70,8 @@ class B200Renderer:
         if model.kind == MODEL_SEMANTIC:
             result["semantic_logits"] = sem
             result["semantic_label"] = label
+        if getattr(model, "variant", None) == "snerf":   # snerf.py:86-96 returns neither beta nor sigmas
+            del result["beta"], result["sigmas"]
         if sc:
             # solar correction: second pass on o + sun_d*z, keeping weights / transparency / sun
             if fp32:
@@ -88,6 +90,10 @@ class B200Renderer:
 # the reference's two renderer class names, for configs / code that instantiate them by name
 class SatNeRFB200Rendering(B200Renderer):
     pass
+
+
+class SNeRFB200Rendering(B200Renderer):
+    """≙ baseline.components.rendering.SNeRFRendering (rendering.py:70-100): models = {"coarse": ShadowNeRFB200}."""
 
 
 class RSSemanticB200Rendering(B200Renderer):

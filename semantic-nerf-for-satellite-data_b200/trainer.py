@@ -19,7 +19,7 @@ import torch
 from . import _lib, dist as snb_dist
 from ._lib import check, ptr, stream
 from .losses import DepthLoss, SatNerfLoss, SemanticCarRegLoss, SemanticLoss, SNerfLoss
-from .model import RSSemanticNeRFB200, SatNeRFB200
+from .model import RSSemanticNeRFB200, SatNeRFB200, ShadowNeRFB200
 from .renderer import B200Renderer
 
 
@@ -45,11 +45,14 @@ class Trainer:
         torch.manual_seed(seed)  # identical initial replicas on every rank
         if kind == "semantic":
             model = RSSemanticNeRFB200(cfgs, types.SimpleNamespace(semantic_n_classes=n_classes))
+        elif kind == "snerf":   # baseline/pipelines/snerf.py:21-38: SNerfLoss, NeRFTrainingStep, no embedding, no depth batch
+            model = ShadowNeRFB200(layers=p.fc_layers, feat=p.fc_units, skips=p.fc_skips)
         else:
             model = SatNeRFB200(cfgs, layers=p.fc_layers, feat=p.fc_units, skips=p.fc_skips,
                                 t_embedding_dims=p.t_embedding_tau)
-        self.models = {"coarse": model.to(self.device),
-                       "t": torch.nn.Embedding(p.t_embedding_vocab, p.t_embedding_tau).to(self.device)}
+        self.models = {"coarse": model.to(self.device)}
+        if kind != "snerf":
+            self.models["t"] = torch.nn.Embedding(p.t_embedding_vocab, p.t_embedding_tau).to(self.device)
         self.renderer = B200Renderer(cfgs)
         self.loss = SatNerfLoss(lambda_sc=p.sc_lambda)
         self.loss_without_beta = SNerfLoss(lambda_sc=p.sc_lambda)
@@ -62,7 +65,7 @@ class Trainer:
         flat = model.flat
         self.exp_avg = torch.zeros_like(flat.data)
         self.exp_avg_sq = torch.zeros_like(flat.data)
-        self.emb_opt = torch.optim.Adam(self.models["t"].parameters(), lr=self.lr)
+        self.emb_opt = torch.optim.Adam(self.models["t"].parameters(), lr=self.lr) if "t" in self.models else None
         self.step_idx = 0
         self.reducer = snb_dist.GradAllReducer(snb_dist.bucket_ranges(model.table, flat.numel(), 3))
 
@@ -70,11 +73,11 @@ class Trainer:
     def training_step(self, batch: Dict[str, torch.Tensor], epoch: int = 2, depth_batch: Optional[dict] = None,
                       ray_offset: int = 0) -> torch.Tensor:
         p = self.cfgs.pipeline
-        model, emb = self.models["coarse"], self.models["t"]
+        model, emb = self.models["coarse"], self.models.get("t")
         self.step_idx += 1
         opts = {"seed": self.step_idx, "ray_offset": ray_offset}
         results = self.renderer.render_rays(self.models, batch["rays"], batch["extras"], epoch=epoch, render_options=opts)
-        if epoch < p.first_beta_epoch:
+        if epoch < p.first_beta_epoch or self.kind == "snerf":
             loss, loss_dict = self.loss_without_beta(results, batch["rgbs"])
         else:
             loss, loss_dict = self.loss(results, batch["rgbs"])
@@ -94,26 +97,29 @@ class Trainer:
                 loss = loss + l_c
                 loss_dict.update(d)
         model.flat.grad = None
-        emb.weight.grad = None
+        if emb is not None:
+            emb.weight.grad = None
         loss.backward()
         self.optimizer_step()
         self.last_loss_dict = loss_dict
         return loss.detach()
 
     def optimizer_step(self):
-        model, emb = self.models["coarse"], self.models["t"]
+        model, emb = self.models["coarse"], self.models.get("t")
         g = model.flat.grad
         if self.world > 1:
             self.reducer.launch(g)
-            torch.distributed.all_reduce(emb.weight.grad)
-            emb.weight.grad.mul_(1.0 / self.world)
+            if emb is not None:
+                torch.distributed.all_reduce(emb.weight.grad)
+                emb.weight.grad.mul_(1.0 / self.world)
             self.reducer.wait()
         lib = _lib.load()
         check(lib.snb_adam_step(ptr(model.flat.data), ptr(g), ptr(self.exp_avg), ptr(self.exp_avg_sq), g.numel(),
                                 self.lr, self.betas[0], self.betas[1], self.eps, self.step_idx, 1.0 / self.world,
                                 stream()), "snb_adam_step")
         model.mark_dirty()
-        self.emb_opt.step()
+        if self.emb_opt is not None:
+            self.emb_opt.step()
 
     # -- chunked no-grad render of a whole image (BaseRayPipeline.forward / batched_inference) ---------------
     @torch.no_grad()

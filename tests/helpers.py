@@ -34,6 +34,8 @@ GOLDEN_CASES = [
     ("sat_s64", "satnerf", 0, 512, 24, 64, 0.05, 5),
     ("sat_s8_nosc", "satnerf", 0, 512, 16, 8, 0.0, 6),
     ("sem_c6_s64_trained", "semantic", 6, 512, 24, 64, 0.05, 7),
+    ("snerf_s64", "snerf", 0, 512, 24, 64, 0.05, 8),
+    ("snerf_s8_nosc", "snerf", 0, 512, 16, 8, 0.0, 9),
 ]
 
 

@@ -111,8 +111,12 @@ def _model(kind, C, seed=3, S=64, sc=0.05, trained_like=False):
     spec = O.ModelSpec(kind=kind, n_classes=C)
     params, emb = O.make_params(spec, seed=seed, trained_like=trained_like)
     cfgs = make_cfgs(spec, S, sc)
-    model = (RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": C})()) if kind == "semantic"
-             else SatNeRFB200(cfgs)).to(DEV)
+    if kind == "snerf":
+        from semnerf_b200.model import ShadowNeRFB200
+        model = ShadowNeRFB200().to(DEV)
+    else:
+        model = (RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": C})()) if kind == "semantic"
+                 else SatNeRFB200(cfgs)).to(DEV)
     model.load_state_dict(params)
     t = torch.nn.Embedding(spec.vocab, spec.tau).to(DEV)
     t.weight.data.copy_(emb)

@@ -61,8 +61,11 @@ def test_render_rays_against_reference_golden(case):
     _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"))
     renderer = B200Renderer(cfgs)
     with torch.no_grad():
-        res = renderer.render_rays({"coarse": model, "t": t}, rays.to(DEV), extras.to(DEV),
-                                   render_options={"u": u.to(DEV)})
+        models = {"coarse": model} if kind == "snerf" else {"coarse": model, "t": t}
+        res = renderer.render_rays(models, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV)})
+        assert set(gold) - {"loss_satnerf", "model_forward", "grad_norms"} <= set(res)
+        if kind == "snerf":   # snerf.py:86-96: no beta / sigmas entries
+            assert "beta_coarse" not in res and "sigmas_coarse" not in res
     trained = name.endswith("trained")
     for k, g in gold.items():
         if k in ("loss_satnerf", "model_forward", "grad_norms"):
@@ -214,7 +217,8 @@ def test_fp32_mode_render_rays_against_reference_golden(case):
     _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"))
     renderer = B200Renderer(cfgs)
     with torch.no_grad():
-        res = renderer.render_rays({"coarse": model, "t": t}, rays.to(DEV), extras.to(DEV),
+        models = {"coarse": model} if kind == "snerf" else {"coarse": model, "t": t}
+        res = renderer.render_rays(models, rays.to(DEV), extras.to(DEV),
                                    render_options={"u": u.to(DEV), "precision": "fp32"})
     worst = {}
     for k, g in gold.items():
@@ -259,3 +263,61 @@ def test_fp32_mode_model_forward_matches_fp64_oracle(kind, C):
     d = (out.cpu().double() - ref).abs()
     rel = d / ref.abs().clamp(min=1.0)
     assert rel.max() <= 5e-5, float(rel.max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# S-NeRF (baseline/models/snerf.py): SatNeRF's kernel plan without the uncertainty head
+# ---------------------------------------------------------------------------------------------------------
+def test_snerf_model_and_render_gradients_match_oracle():
+    from semnerf_b200.renderer import SNeRFB200Rendering
+    _lib_or_fail()
+    S, n = 64, 192
+    spec, params, emb, cfgs, model, _ = _model("snerf", 0, seed=4, S=S)
+    assert list(model.state_dict().keys()) == list(O.param_shapes(spec).keys())       # the reference ShadowNeRF's names
+    assert model.number_of_outputs == 8
+    # Model.forward: (B,8) [rgb | sigma | sun_v | sky], sigma_only -> (B,1)
+    g = torch.Generator().manual_seed(0)
+    P = 700
+    xyz = torch.rand(P, 3, generator=g) * 2 - 1
+    sun = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=1)
+    ref = O.mlp_forward({k: v.double() for k, v in params.items()}, spec, xyz.double(), sun.double(), None)
+    with torch.no_grad():
+        out = model(xyz.to(DEV), input_sun_dir=sun.to(DEV))
+        sig = model(xyz.to(DEV), input_sun_dir=sun.to(DEV), sigma_only=True)
+    assert out.shape == (P, 8) and sig.shape == (P, 1) and torch.equal(sig[:, 0], out[:, 3])
+    d = (out.cpu().double() - ref).abs()
+    assert d[:, [0, 1, 2, 4]].max() <= 2e-3 and d[:, 5:8].max() <= 1e-6 and d[:, 3].max() <= 1e-2
+    # render + SNerfLoss gradients (baseline/pipelines/snerf.py:21-22)
+    rays, extras = O.synthetic_rays(n, seed=6)
+    u = torch.rand(n, S, generator=torch.Generator().manual_seed(2))
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(3))
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    r_ref = O.render_rays(p, None, spec, rays, extras, S, u=u, sc_lambda=0.05)
+    O.snerf_loss(r_ref, gt).backward()
+    res = SNeRFB200Rendering(cfgs).render_rays({"coarse": model}, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV)})
+    for k in ("rgb_coarse", "depth_coarse"):
+        assert (res[k].detach().cpu() - r_ref[k].detach()).abs().max() <= 1e-3, k
+    O.snerf_loss(res, gt.to(DEV)).backward()
+    grads = model.named_grads()
+    assert set(grads) == set(p)
+    for k in p:
+        assert _cos(grads[k].cpu(), p[k].grad) >= 0.999, k
+    # the hidden beta block stays at zero and receives no gradient
+    for name, off, shape in model.table:
+        if name.startswith("beta_from_xyz."):
+            nel = int(torch.tensor(shape).prod())
+            assert model.flat.grad[off:off + nel].abs().max() == 0 and model.flat.data[off:off + nel].abs().max() == 0
+
+
+def test_snerf_training_step_runs_and_learns():
+    from semnerf_b200 import synth
+    from semnerf_b200.trainer import Trainer, default_cfgs
+    _lib_or_fail()
+    cfgs = default_cfgs("snerf", n_samples=64, sc_lambda=0.05)
+    tr = Trainer(cfgs, "snerf", 0, device=DEV, seed=0)
+    assert "t" not in tr.models
+    rays, extras = synth.make_rays(1024, seed=0)
+    rgbs, _, _ = synth.make_targets(rays, 0, seed=0)
+    batch = {"rays": rays.to(DEV), "extras": extras.to(DEV), "rgbs": rgbs.to(DEV)}
+    losses = [tr.training_step(batch, epoch=3).item() for _ in range(12)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
