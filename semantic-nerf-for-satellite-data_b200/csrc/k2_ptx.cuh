@@ -23,25 +23,36 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a protocol bug must surface as a trap (CUDA error), never as a hung GPU.
+// The retry loop is kept to try_wait + counter + branch: the waiting roles share their SM sub-partition's issue slots with
+// the epilogue math warps (ncu: the old loop - clock read, 64-bit subtract and compare every iteration - was 17 % of all
+// instructions the chained kernel executed), and every attempt may suspend in hardware for up to ~1 us before it returns.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity), "r"(1000u)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_timeout(uint32_t addr, uint32_t parity) {
+  printf("snb gemm: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, addr, parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t ok = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (clock64() - t0 > 8000000000LL) {  // ~4 s
-      printf("snb gemm: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-             threadIdx.x, addr, parity);
-      __trap();
+  if (mbar_try_wait(addr, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(addr, parity)) {
+    if ((++spins & 0x3fffu) == 0) {   // look at the clock every 16384 failed attempts only
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) mbar_timeout(addr, parity);   // ~4 s
     }
   }
 }
