@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
   if (threadIdx.x == 0) {
     for (int s = 0; s < args.nseg; ++s) tma_prefetch_desc(&args.tmA[s]);
     tma_prefetch_desc(&args.tmB);
+    if (EPI == EPI_WGRAD && args.side_n > 0) tma_prefetch_desc(&args.tmB2);
     for (int s = 0; s < GEMM_MAX_RING; ++s) {
       mbar_init(&fullA[s], CG);   // CG == 2: the leader's expect_tx arrive + the peer's remote arrive
       mbar_init(&emptyA[s], 1);
@@ -142,8 +143,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
         const int n_row = t.n_blk * args.block_n + (int)cta_rank * n_half;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&emptyB[stage], phase ^ 1);
-          if (lead_cta) mbar_expect_tx(&fullB[stage], args.b_bytes * CG);
+          // side operand: only on the k-blocks whose side MMAs this n-tile issues (see the MMA warp)
+          const bool side_kb = EPI == EPI_WGRAD && CG == 2 && args.side_n > 0 && (kb % args.n_tiles) == t.n_blk;
+          const uint32_t side_bytes = side_kb ? (uint32_t)(args.side_n / CG) * (GEMM_BLOCK_K * 2) : 0u;
+          if (lead_cta) mbar_expect_tx(&fullB[stage], (args.b_bytes + side_bytes) * CG);
           else mbar_arrive_remote(&fullB[stage], 0);
+          if (side_kb)
+            tma_load_op<CG>(sStg + stage * GEMM_SIDE_STAGE, &args.tmB2, &fullB[stage], kb * GEMM_BLOCK_K,
+                            (int)cta_rank * (args.side_n / CG));
           uint8_t* b_dst = sB + stage * b_slot;
           if (!args.b_mn) {
             tma_load_op<CG>(b_dst, &args.tmB, &fullB[stage], kb * GEMM_BLOCK_K, n_row);
@@ -171,6 +178,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
       const uint32_t a_kstep = (args.a_mn ? 2048u : 32u) >> 4, b_kstep = (args.b_mn ? 2048u : 32u) >> 4;
       // descriptor = constant high part | (smem address >> 4): only the low word changes per k-step
       const uint64_t adesc0 = umma_desc(0, a_lbo, 1024u), bdesc0 = umma_desc(0, b_lbo, 1024u);
+      const uint64_t bdesc_k0 = umma_desc(0, 16u, 1024u);   // K-major tile (side operand)
       const uint32_t a_base = smem_u32(sA) >> 4, b_base = smem_u32(sB) >> 4;
       const uint32_t b_slot16 = b_slot >> 4;
       // bias gradient: D2[M, 16] += A[M, k] * ones[16, k]^T into the last 16 TMEM columns (every unit runs at most one
@@ -179,6 +187,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
                                 ((uint32_t)((GEMM_BLOCK_M * CG) >> 4) << 24);
       const uint64_t odesc = umma_desc(smem_u32(sOnes), 16u, 1024u);
       const uint32_t d_cs = tmem_base + 2 * GEMM_MAX_BLOCK_N - 16;
+      // side operand (K-major [side_n / CG rows, 64 k] per CTA in the staging area): D3[M, side_n] in the columns below d_cs
+      const uint32_t idesc_side = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)args.a_mn << 15) |
+                                  ((uint32_t)(args.side_n >> 3) << 17) | ((uint32_t)((GEMM_BLOCK_M * CG) >> 4) << 24);
+      const uint32_t side_base = smem_u32(sStg) >> 4;
+      const uint32_t d_side = tmem_base + 2 * GEMM_MAX_BLOCK_N - 16 - 64;
+      const bool has_side = EPI == EPI_WGRAD && CG == 2 && args.side_n > 0;
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       for (int tile = unit; tile < total_tiles; tile += n_units, ++it) {
         const TileCoord t = decode_tile(args, tile);
@@ -209,12 +223,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
                 else tc_mma_bf16(d_cs, ad + k * a_kstep, odesc + k * 2, idesc_cs, (cs_started || k > 0) ? 1u : 0u);
               }
             }
+            if constexpr (CG == 2) {
+              if (has_side && (kb % args.n_tiles) == t.n_blk) {
+                const uint64_t sd = bdesc_k0 + (uint64_t)(side_base + sb * (GEMM_SIDE_STAGE >> 4));
+#pragma unroll
+                for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+                  tc_mma_bf16_2sm(d_side, ad + k * a_kstep, sd + k * 2, idesc_side, (cs_started || k > 0) ? 1u : 0u);
+              }
+            }
             // frees the smem slots (in both CTAs of a pair) once these MMAs have read them
             if constexpr (CG == 2) { tc_commit_2sm(&emptyA[sa]); tc_commit_2sm(&emptyB[sb]); }
             else { tc_commit(&emptyA[sa]); tc_commit(&emptyB[sb]); }
           }
           __syncwarp();
-          if (cs_tile && (kb % args.n_tiles) == t.n_blk) cs_started = true;
+          if ((cs_tile || has_side) && (kb % args.n_tiles) == t.n_blk) cs_started = true;
           if (++sa == a_stages) { sa = 0; pa ^= 1; }
           if (++sb == b_stages) { sb = 0; pb ^= 1; }
         }
@@ -314,6 +336,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) snb_gemm_kernel(const __grid_
           tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + 2 * GEMM_MAX_BLOCK_N - 16, v);
           tc_wait_ld();
           if (m0 + row < args.M) atomicAdd(args.colsum + m0 + row, __uint_as_float(v[0]));
+        }
+        if (CG == 2 && args.side_n > 0 && grp == 0 &&
+            t.kb0 + ((t.n_blk - t.kb0 % args.n_tiles + args.n_tiles) % args.n_tiles) < t.kb1) {
+          // this tile's share of side_out[M, side_n] = A^T x X2 (fp32 partial sums over its k-blocks)
+          const long long grow = (long long)m0 + row;
+          for (int c0 = 0; c0 < args.side_n; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + 2 * GEMM_MAX_BLOCK_N - 16 - 64 + c0, v);
+            tc_wait_ld();
+            if (grow < args.M) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) atomicAdd(args.side_out + grow * args.ld_side + c0 + j, __uint_as_float(v[j]));
+            }
+          }
         }
       }
       tc_fence_before();
@@ -486,6 +522,10 @@ int gemm_launch(const GemmArgs& a, int epi, cudaStream_t st) {
                 "gemm: the fused column sum needs the wgrad form and at most one tile per scheduling unit");
   SNB_CHECK_ARG(a.b_stages * (int)a.b_slot + a.a_stages * GEMM_A_STAGE <= GEMM_OPERAND_BYTES, SNB_ERR_INVALID,
                 "gemm: rings %d/%d exceed the operand smem", a.a_stages, a.b_stages);
+  SNB_CHECK_ARG(a.side_n == 0 || (epi == EPI_WGRAD && a.cta_group == 2 && tiles <= max_units && a.a_mn && a.side_out != nullptr &&
+                                  (a.side_n == 16 || a.side_n == 64) &&
+                                  a.b_stages * GEMM_SIDE_STAGE <= GEMM_NUM_STAGING * GEMM_STAGING),
+                SNB_ERR_UNSUPPORTED, "gemm: the side operand needs the SM-pair wgrad form, one tile per unit and 16 or 64 columns");
   const double macs = (double)a.m_tiles * GEMM_BLOCK_M * a.cta_group * (double)a.n_tiles * a.block_n * (double)a.kb_total * GEMM_BLOCK_K;
   const bool timed = profile_gemm_begin(st, macs, epi, a.M, a.N, a.kb_total * GEMM_BLOCK_K, a.cta_group, a.splits);
   int rc;

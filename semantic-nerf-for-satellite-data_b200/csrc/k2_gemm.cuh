@@ -44,6 +44,7 @@ constexpr int GEMM_NUM_STAGING = 4;
 constexpr int GEMM_EPI_THREADS = 256;  // two epilogue warpgroups
 constexpr int GEMM_THREADS = 96 + GEMM_EPI_THREADS;  // warp 0: A producer, 1: MMA, 2: B producer, 3-10: epilogue
 constexpr int GEMM_ONES_BYTES = 2048;   // constant all-ones B tile (16 x 64 bf16) of the bias-gradient MMA
+constexpr int GEMM_SIDE_STAGE = 4096;   // side operand: up to 32 rows x 64 k bf16 per CTA and k-block
 constexpr int GEMM_LAYOUT_BYTES = GEMM_OPERAND_BYTES + GEMM_NUM_STAGING * GEMM_STAGING + GEMM_ONES_BYTES + 512;
 // the dynamic shared memory is declared 1024-byte aligned; the kernel still rounds its base up and traps if the
 // layout would not fit (512 bytes of slack are left below the 227 KB limit)
@@ -69,6 +70,16 @@ struct GemmArgs {
   // EPI_WGRAD: if set, colsum[m] += sum over the K (sample) dimension of A[:, m] - the bias gradient rides the weight
   // gradient GEMM as one extra N = 16 MMA per k-block against a constant all-ones tile (n-block 0 tiles only)
   float* colsum;
+  // EPI_WGRAD, SM-pair mode: optional SIDE operand riding the same launch - side_out[M, side_n] += A^T x X2 for a narrow
+  // second right-hand side X2 (the per-ray `aux` columns of the fused head layer, the encoding block of the skip layer),
+  // given TRANSPOSED ([side_n, K] K-major, like a weight matrix) so each CTA of the pair loads side_n / 2 rows x 64 k per
+  // k-block.  One extra N = side_n MMA per k-block into spare TMEM columns, shared between the n-tiles like the column
+  // sums; replaces a separate launch that re-read the whole dY from HBM.  The side ring lives in the epilogue's staging
+  // buffers (idle during the k-loop: a unit runs one tile when colsum / side are set).
+  CUtensorMap tmB2;
+  int side_n;              // 0, 16 or 64
+  float* side_out;
+  long long ld_side;
   // EPI_F32ROWS / small-N EPI_WGRAD
   float* f32out;
   long long ldo;

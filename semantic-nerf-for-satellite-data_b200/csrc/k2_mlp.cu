@@ -396,6 +396,7 @@ struct Workspace {
   size_t dpre, dy[8], df, dyhh, dys3, dys2;         // backward (dy[i] = gradient w.r.t. the pre-activation of trunk layer i)
   size_t scr_h[2], scr_f, scr_s2;                   // inference: per-SM-pair scratch of the chained kernel (L2-resident)
   size_t hpart;                                     // (P, 16) fp32 partial sums of the head pre-activations
+  size_t auxT, encT;                                // [16, ldt] / [64, ldt] K-major copies of aux / enc[:, :64] (wgrad side operands)
   size_t gscratch;                                  // fp32 packed gradients
   size_t total;
 };
@@ -448,6 +449,9 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
     w.dyhh = take_b(rowHH);
     w.dys3 = take_b(rowFL);
     w.dys2 = take_b(rowFL);
+    const size_t ldt = ((size_t)P + 63) & ~(size_t)63;
+    w.auxT = take_b(16 * ldt * 2);
+    w.encT = take_b(64 * ldt * 2);
     w.gscratch = take_b((size_t)m->gscratch_elems * 4);
   }
   w.total = cur;
@@ -503,8 +507,18 @@ static GemmArgs& add_rows16(Plan& p, int epi, long long M, const Seg* segs, int 
 
 // G[Mf,Nf] += dY[P,Mf]^T * X[P,Nf]   (reduction over the P samples; MN-major operands; split-K)
 // colsum (optional): [Mf] += column sums of dY over the samples = the bias gradient, computed by the same launch
+// side (optional, SM-pair launches only): side_out[Mf, side_n] += dY^T * X2, X2 given transposed as XT[side_n, ldt] (bf16)
+struct WgradSide {
+  const void* xt;
+  long long ldt;
+  int n;
+  float* out;
+  long long ld;
+};
+
 static void add_wgrad(Plan& p, int Mf, int Nf, const void* dY, long long ld_dy, const void* X, long long ld_x,
-                      long long P, float* G, long long ldg, int sms, float* colsum = nullptr) {
+                      long long P, float* G, long long ldg, int sms, float* colsum = nullptr,
+                      const WgradSide* side = nullptr) {
   GemmArgs& a = p.add(EPI_WGRAD);
   a.M = Mf;
   a.N = Nf;
@@ -531,7 +545,39 @@ static void add_wgrad(Plan& p, int Mf, int Nf, const void* dY, long long ld_dy, 
   const int max_splits = a.kb_total / 4 > 0 ? a.kb_total / 4 : 1;
   a.splits = splits < max_splits ? splits : max_splits;
   a.colsum = colsum;
+  if (side != nullptr) {
+    if (a.cta_group != 2) {
+      set_error("wgrad: a side operand needs the SM-pair form (M %d, N %d)", Mf, Nf);
+      p.chk(SNB_ERR_UNSUPPORTED);
+    }
+    a.side_n = side->n;
+    a.side_out = side->out;
+    a.ld_side = side->ld;
+    p.chk(make_tmap_2d(&a.tmB2, side->xt, 2, (uint64_t)P, (uint64_t)side->n, (uint64_t)side->ldt * 2, 64, (uint32_t)(side->n / 2)));
+  }
   gemm_finalize(a);
+}
+
+// dst[c, p] = src[p, c] for c < cols (bf16): the K-major copies of the narrow wgrad side operands
+__global__ void __launch_bounds__(256) transpose_cols_kernel(const __nv_bfloat16* __restrict__ src, long long ld_src, int cols,
+                                                             long long P, __nv_bfloat16* __restrict__ dst, long long ldt) {
+  __shared__ __nv_bfloat16 tile[64][64 + 2];
+  const long long p0 = (long long)blockIdx.x * 64;
+  for (int i = threadIdx.x; i < 64 * cols; i += 256) {
+    const int r = i / cols, c = i - r * cols;
+    tile[r][c] = p0 + r < P ? src[(p0 + r) * ld_src + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * cols; i += 256) {
+    const int c = i >> 6, r = i & 63;
+    if (p0 + r < ldt) dst[(long long)c * ldt + p0 + r] = tile[r][c];
+  }
+}
+
+static int transpose_cols(const void* src, long long ld_src, int cols, long long P, void* dst, long long ldt, cudaStream_t st) {
+  transpose_cols_kernel<<<(unsigned)((ldt + 63) / 64), 256, 0, st>>>((const __nv_bfloat16*)src, ld_src, cols, P,
+                                                                     (__nv_bfloat16*)dst, ldt);
+  return launch_status("transpose_cols_kernel");
 }
 
 static int run_plan(const Plan& p, cudaStream_t st) {
@@ -870,6 +916,10 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     if (int r = cp.run()) return r;
   }
   // ---- wgrad: every weight gradient is dY^T x (layer input), split-K over the samples -----------------------
+  const long long ldt = (P + 63) & ~63ll;
+  if (!depth)
+    if (int r = transpose_cols(aux, 16, 16, P, ws + w.auxT, ldt, st)) return r;
+  if (int r = transpose_cols(enc, m->enc_ld, 64, P, ws + w.encT, ldt, st)) return r;
   add_wgrad(p, F, 16, H(7), F, dpre, 16, P, gs + m->ghot, 16, sms);
   if (!depth) add_wgrad(p, FL, 16, ws + w.s3, FL, dpre, 16, P, gs + m->ghot + (long long)F * 16, 16, sms);
   if (all) add_wgrad(p, hhw, 16, ws + w.hh, hhw, dpre, 16, P, gs + m->ghot + (long long)(F + FL) * 16, 16, sms);
@@ -877,8 +927,9 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     add_wgrad(p, FL, FL, ws + w.dys3, FL, ws + w.s2, FL, P, gs + m->gs4, FL, sms, gs + m->gbs4);
     add_wgrad(p, FL, FL, ws + w.dys2, FL, ws + w.hh + (size_t)m->hh_sun * 2, hhw, P, gs + m->gs2, FL, sms, gs + m->gbs2);
     // fused head first layers: weight / bias / per-ray-column gradients
-    add_wgrad(p, nh, F, dyhh_r0, hhw, ws + w.f, F, P, gs + m->gh1 + (long long)r0 * F, F, sms);
-    add_wgrad(p, nh, 16, dyhh_r0, hhw, aux, 16, P, gs + m->gh1aux + (long long)r0 * 16, 16, sms);
+    // ... the bias / per-ray-column gradients dY^T x aux ride the same launch as a 16-column side operand
+    const WgradSide s_aux = {ws + w.auxT, ldt, 16, gs + m->gh1aux + (long long)r0 * 16, 16};
+    add_wgrad(p, nh, F, dyhh_r0, hhw, ws + w.f, F, P, gs + m->gh1 + (long long)r0 * F, F, sms, nullptr, &s_aux);
     if (all && g_aux) {
       // d aux = dY_beta * W_beta0[:, 512:]  -> embedding gradient (summed per ray by the caller-side kernel)
       Seg sb[1] = {{ws + w.dyhh + (size_t)m->hh_beta * 2, hhw, FL, FL / 64}};
@@ -892,8 +943,9 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     if (i == 0) {
       add_wgrad(p, F, 64, DY(0), F, enc, m->enc_ld, P, gs + m->gl[0], 64, sms, gs + m->gbl[0]);
     } else {
-      add_wgrad(p, F, F, DY(i), F, H(i - 1), F, P, gs + m->gl[i], F, sms, gs + m->gbl[i]);
-      if (i == 4) add_wgrad(p, F, 64, DY(4), F, enc, m->enc_ld, P, gs + m->gl4e, 64, sms);
+      // skip layer: its encoding block dY4^T x enc[:, :64] is a 64-column side operand of the same launch
+      const WgradSide s_enc = {ws + w.encT, ldt, 64, gs + m->gl4e, 64};
+      add_wgrad(p, F, F, DY(i), F, H(i - 1), F, P, gs + m->gl[i], F, sms, gs + m->gbl[i], i == 4 ? &s_enc : nullptr);
     }
   }
   if (int r = run_plan(p, st)) return r;
