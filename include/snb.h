@@ -163,6 +163,31 @@ int snb_composite_backward(const float* out, const float* z_vals, int n_rays, in
                            const float* g_transparency, const float* g_sem_logits,
                            const float* g_out_direct, float* g_out, void* stream);
 
+/* K3 + losses fused: composite forward, the loss terms that sit directly on its outputs and the
+ * composite backward in one pass per ray; the per-sample weights / transparency / beta / sun_sc tensors are never
+ * materialised.  Replaces, for the training step, snb_composite_forward + the loss modules + snb_composite_backward:
+ *   mode 0 (main pass)   SNerfLoss colour term (color = 0, baseline/components/loss.py:71-94) or SatNerfLoss's
+ *                        uncertainty_aware_loss (color = 1, loss.py:16-27) + SemanticLoss (cross-entropy with
+ *                        ignore_index, semantic/components/loss.py:35-65) + SemanticCarRegLoss (loss.py:117-157)
+ *   mode 1 (solar pass)  solar_correction terms 2 and 3 (baseline/components/loss.py:4-13)
+ *   mode 2 (depth batch) DepthLoss (baseline/components/loss.py:30-47)
+ * gt_rgb (N,3) f32; labels (N) i64 or NULL; depth_gt / depth_w (N) f32 (depth_w NULL = 1);
+ * counts: device float[2] = {rays whose label != ignore_index, rays whose label == car_label} (NULL without labels);
+ * g_out (P, n_out) f32 = d(sum of the terms)/d(out); loss_terms: device float[8], ACCUMULATED:
+ * [0] colour [1] log-beta without its constant 3/2 [2] cross-entropy [3] car reg [4] sc term 2 [5] sc term 3 [6] depth. */
+typedef struct snb_loss_params {
+  int mode, color;
+  float beta_min, inv_n;     /* inv_n = 1 / (rays of the batch): the means of the reference losses */
+  float lambda_s;
+  int ignore_index;
+  float lambda_c;
+  int car_label;
+  float lambda_sc, lambda_ds;
+} snb_loss_params;
+int snb_composite_loss(const float* out, const float* z_vals, int n_rays, int n_samples, int n_out, int n_classes,
+                       const float* gt_rgb, const int64_t* labels, const float* depth_gt, const float* depth_w,
+                       const float* counts, const snb_loss_params* p, float* g_out, float* loss_terms, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * optimiser step on the flat buffers (Adam, torch.optim.Adam semantics, weight_decay = 0:
  * baseline/pipelines/base_ray_pipeline.py:246-269).  grad_scale multiplies the gradient first

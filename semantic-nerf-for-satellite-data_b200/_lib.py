@@ -42,12 +42,21 @@ SIGNATURES = {
     "snb_ray_param_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "snb_composite_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "snb_composite_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "snb_composite_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "snb_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _vp]),
     "snb_set_chained_mlp": (_i, [_i]),
     "snb_profile_begin": (None, [_i]),
     "snb_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(C.c_double)]),
     "snb_gemm_bf16": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp, _vp, _f, _i, _vp]),
 }
+
+
+
+class LossParams(C.Structure):
+    """snb_loss_params (include/snb.h)"""
+    _fields_ = [("mode", _i), ("color", _i), ("beta_min", _f), ("inv_n", _f), ("lambda_s", _f), ("ignore_index", _i),
+                ("lambda_c", _f), ("car_label", _i), ("lambda_sc", _f), ("lambda_ds", _f)]
+
 
 _lib = None
 

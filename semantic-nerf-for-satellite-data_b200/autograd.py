@@ -5,6 +5,7 @@ These replace the autograd graph PyTorch would build for the reference's eager i
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional
 
 import torch
@@ -230,3 +231,35 @@ class Composite(torch.autograd.Function):
                                          ptr(_f32c(g_sem)) if ctx.n_classes else None, None, ptr(g_out), stream()),
               "snb_composite_backward")
         return g_out, None, None
+
+
+LOSS_TERMS = ("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3", "ds")
+
+
+class CompositeLoss(torch.autograd.Function):
+    """K3 + losses fused (snb_composite_loss): packed head outputs (N,S,n_out) + z_vals -> the scalar sum of the loss
+    terms of one pass; the gradient of the packed rows is produced by the same kernel and handed to the MLP backward.
+    `terms` (8,) is accumulated in place (logging; not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, out, z_vals, n_classes, params, gt_rgb, labels, depth_gt, depth_w, counts, terms):
+        lib = _lib.load()
+        out, z_vals = _f32c(out), _f32c(z_vals)
+        n, s, n_out = out.shape
+        g_out = torch.empty_like(out)
+        mine = torch.zeros(8, dtype=torch.float32, device=out.device)
+        check(lib.snb_composite_loss(ptr(out), ptr(z_vals), n, s, n_out, n_classes, ptr(_f32c(gt_rgb)), ptr(labels),
+                                     ptr(_f32c(depth_gt)), ptr(_f32c(depth_w)), ptr(counts), C.addressof(params),
+                                     ptr(g_out), ptr(mine), stream()), "snb_composite_loss")
+        ctx.save_for_backward(g_out)
+        if terms is not None:
+            terms.add_(mine)
+        loss = mine.sum()
+        if params.mode == 0 and params.color == 1:
+            loss = loss + 1.5      # (3 + mean log beta) / 2: the constant of the log-beta term (loss.py:26)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (g_out,) = ctx.saved_tensors
+        return g_out * g_loss, None, None, None, None, None, None, None, None, None

@@ -341,7 +341,338 @@ static int check_k3(const float* out, const float* z, int n_rays, int S, int n_o
   return 0;
 }
 
+// =====================================================================================================================
+// K3 + losses fused: composite forward, the training losses that sit directly on its outputs and the
+// composite backward in ONE pass per ray - the per-sample weights / transparency / beta / sun_sc tensors and the ~40
+// small PyTorch launches of the loss modules never exist.  Per ray the kernel forms the loss terms, their gradients
+// w.r.t. the composited values analytically, and pushes them straight through the compositing backward into
+// g_out (P, n_out), the gradient of the packed head outputs.
+//   mode 0 (main pass):   colour loss - MSE (SNerfLoss, baseline/components/loss.py:71-94) or uncertainty-aware
+//                         (SatNerfLoss, loss.py:16-27,50-68) - + semantic cross-entropy with ignore_index
+//                         (semantic/components/loss.py:35-65) + car regularisation (loss.py:117-157)
+//   mode 1 (solar pass):  solar-correction terms 2 and 3 (baseline/components/loss.py:4-13); transparency_sc / weights_sc
+//                         are detached there, so only the sun column receives a gradient
+//   mode 2 (depth batch): DepthLoss (baseline/components/loss.py:30-47)
+// Means are over n_rays (inv_n), the CE mean over the non-ignored rays and the car term over the car rays: their counts
+// come from a device buffer (counts[0], counts[1]) so no host synchronisation is needed.
+// loss_terms (device float[8], accumulated): 0 colour, 1 log-beta (without the constant 3/2), 2 CE, 3 car, 4 sc term 2,
+// 5 sc term 3, 6 depth.
+// =====================================================================================================================
+struct LossParams {
+  int mode, color;
+  float beta_min, inv_n;
+  float lambda_s;
+  int ignore_index;
+  float lambda_c;
+  int car_label;
+  float lambda_sc, lambda_ds;
+};
+
+template <int SPL>
+__global__ void __launch_bounds__(K3_WARPS * 32)
+k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, int n_rays, int S, int n_out, int C,
+               const float* __restrict__ gt_rgb, const long long* __restrict__ labels, const float* __restrict__ depth_gt,
+               const float* __restrict__ depth_w, const float* __restrict__ counts, const LossParams lp,
+               float* __restrict__ g_out, float* __restrict__ loss_terms) {
+  extern __shared__ __align__(16) float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_words = S * n_out;
+  const int rw4 = (row_words + 3) & ~3, s4 = (S + 3) & ~3;
+  const int in_words = rw4 + s4;
+  const int per_warp = 2 * in_words + rw4;
+  float* wbase = smem + warp * per_warp;
+  float* grow = wbase + 2 * in_words;
+  const bool vec_rows = (row_words & 3) == 0 && (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(g_out)) & 15) == 0);
+  const bool async_in = vec_rows && (S & 3) == 0 && ((reinterpret_cast<uintptr_t>(z_vals) & 15) == 0);
+  auto fetch = [&](int ray, float* dst) {
+    if (ray < n_rays) {
+      const float4* s4p = reinterpret_cast<const float4*>(out + (size_t)ray * row_words);
+      const uint32_t d = smem_u32(dst);
+      for (int i = lane; i < row_words / 4; i += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + i * 16), "l"(s4p + i) : "memory");
+      const float4* z4 = reinterpret_cast<const float4*>(z_vals + (size_t)ray * S);
+      for (int i = lane; i < S / 4; i += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + (rw4 + i * 4) * 4), "l"(z4 + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const float inv_valid = counts ? 1.0f / fmaxf(counts[0], 1.0f) : 0.f;
+  const float inv_car = counts ? 1.0f / fmaxf(counts[1], 1.0f) : 0.f;
+  float lsum[7];
+#pragma unroll
+  for (int i = 0; i < 7; ++i) lsum[i] = 0.f;
+
+  const int ray0 = blockIdx.x * K3_WARPS + warp, stride = gridDim.x * K3_WARPS;
+  int cur = 0;
+  if (async_in) fetch(ray0, wbase);
+  for (int ray = ray0; ray < n_rays; ray += stride, cur ^= 1) {
+    float* rows = wbase + (async_in ? cur * in_words : 0);
+    float* zs = rows + rw4;
+    if (async_in) {
+      fetch(ray + stride, wbase + (cur ^ 1) * in_words);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      const float* src = out + (size_t)ray * row_words;
+      for (int i = lane; i < row_words; i += 32) rows[i] = __ldg(src + i);
+      for (int i = lane; i < S; i += 32) zs[i] = __ldg(z_vals + (size_t)ray * S + i);
+    }
+    __syncwarp();
+
+    // ---- composite forward (same arithmetic as k3_composite_kernel) ----------------------------------------
+    float alpha[SPL], tloc[SPL], qv[SPL];
+    float Q = 1.0f;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      int s = lane * SPL + j;
+      tloc[j] = Q;
+      if (s < S) {
+        SampleVals v = sample_alpha(zs, rows + s * n_out, s, S);
+        alpha[j] = v.alpha;
+        qv[j] = v.q;
+        Q *= v.q;
+      } else {
+        alpha[j] = 0.0f;
+        qv[j] = 1.0f;
+      }
+    }
+    const float prefix = warp_excl_prod(Q, lane);
+    float acc_d = 0.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_beta = 0.f, acc_t2 = 0.f, acc_t3 = 0.f;
+    float acc_s[10];
+#pragma unroll
+    for (int c = 0; c < 10; ++c) acc_s[c] = 0.f;
+    float T[SPL], w[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      int s = lane * SPL + j;
+      T[j] = prefix * tloc[j];
+      w[j] = alpha[j] * T[j];
+      if (s < S) {
+        const float* r = rows + s * n_out;
+        const float v = r[4];
+        acc_d += w[j] * zs[s];
+        if (lp.mode == 0) {
+          acc_r += w[j] * r[0] * (v + (1.0f - v) * r[5]);
+          acc_g += w[j] * r[1] * (v + (1.0f - v) * r[6]);
+          acc_b += w[j] * r[2] * (v + (1.0f - v) * r[7]);
+          acc_beta += w[j] * r[8];
+#pragma unroll
+          for (int c = 0; c < 10; ++c)
+            if (c < C) acc_s[c] += w[j] * r[9 + c];
+        } else if (lp.mode == 1) {
+          acc_t2 += (T[j] - v) * (T[j] - v);
+          acc_t3 += w[j] * v;
+        }
+      }
+    }
+    float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, gB = 0.f;
+    float gs[10];
+#pragma unroll
+    for (int c = 0; c < 10; ++c) gs[c] = 0.f;
+    if (lp.mode == 0) {
+      acc_r = warp_sum(acc_r);
+      acc_g = warp_sum(acc_g);
+      acc_b = warp_sum(acc_b);
+      acc_beta = warp_sum(acc_beta);
+#pragma unroll
+      for (int c = 0; c < 10; ++c)
+        if (c < C) acc_s[c] = warp_sum(acc_s[c]);
+      // colour loss on the clamped colour (rs_semantic.py:103); the clamp passes gradient inside [0, 1] only
+      const float d0 = fminf(fmaxf(acc_r, 0.f), 1.f) - gt_rgb[ray * 3 + 0];
+      const float d1 = fminf(fmaxf(acc_g, 0.f), 1.f) - gt_rgb[ray * 3 + 1];
+      const float d2 = fminf(fmaxf(acc_b, 0.f), 1.f) - gt_rgb[ray * 3 + 2];
+      const float sq = d0 * d0 + d1 * d1 + d2 * d2;
+      const float k3n = lp.inv_n * (1.0f / 3.0f);
+      if (lp.color == 1) {   // ((rgb - gt)^2 / (2 beta^2)).mean() + (3 + log(beta).mean()) / 2
+        const float Bt = acc_beta + lp.beta_min;
+        const float i2 = 1.0f / (Bt * Bt);
+        lsum[0] += 0.5f * sq * i2 * k3n;
+        lsum[1] += 0.5f * logf(Bt) * lp.inv_n;
+        gr = d0 * i2 * k3n;
+        gg = d1 * i2 * k3n;
+        gb = d2 * i2 * k3n;
+        gB = -sq * i2 / Bt * k3n + 0.5f * lp.inv_n / Bt;
+      } else {               // mse_loss(rgb, gt)
+        lsum[0] += sq * k3n;
+        gr = 2.0f * d0 * k3n;
+        gg = 2.0f * d1 * k3n;
+        gb = 2.0f * d2 * k3n;
+      }
+      if (!(acc_r >= 0.f && acc_r <= 1.f)) gr = 0.f;
+      if (!(acc_g >= 0.f && acc_g <= 1.f)) gg = 0.f;
+      if (!(acc_b >= 0.f && acc_b <= 1.f)) gb = 0.f;
+      if (labels != nullptr && C > 0) {
+        const int y = (int)labels[ray];
+        if (lp.lambda_s != 0.f && y != lp.ignore_index && y >= 0 && y < C) {
+          float mx = acc_s[0];
+#pragma unroll
+          for (int c = 1; c < 10; ++c)
+            if (c < C) mx = fmaxf(mx, acc_s[c]);
+          float se = 0.f, ly = 0.f;
+#pragma unroll
+          for (int c = 0; c < 10; ++c)
+            if (c < C) {
+              se += expf(acc_s[c] - mx);
+              if (c == y) ly = acc_s[c];
+            }
+          const float lse = mx + logf(se);
+          lsum[2] += lp.lambda_s * (lse - ly) * inv_valid;
+#pragma unroll
+          for (int c = 0; c < 10; ++c)
+            if (c < C) gs[c] = lp.lambda_s * (expf(acc_s[c] - lse) - (c == y ? 1.0f : 0.0f)) * inv_valid;
+        }
+        if (lp.lambda_c != 0.f && y == lp.car_label) {   // mse(1, sum w beta) over the car rays
+          const float e = 1.0f - acc_beta;
+          lsum[3] += lp.lambda_c * e * e * inv_car;
+          gB += -2.0f * lp.lambda_c * e * inv_car;
+        }
+      }
+    } else if (lp.mode == 1) {
+      acc_t2 = warp_sum(acc_t2);
+      acc_t3 = warp_sum(acc_t3);
+      const float k = lp.lambda_sc * (1.0f / 3.0f) * lp.inv_n;
+      lsum[4] += k * acc_t2;
+      lsum[5] += k * (1.0f - acc_t3);
+    } else {
+      acc_d = warp_sum(acc_d);
+      const float wt = depth_w ? depth_w[ray] : 1.0f;
+      const float e = acc_d - depth_gt[ray];
+      const float k = lp.lambda_ds * (1.0f / 3.0f) * lp.inv_n;
+      lsum[6] += k * wt * e * e;
+      gd = 2.0f * k * wt * e;
+    }
+
+    // ---- gradient of the packed rows ------------------------------------------------------------------------
+    if (lp.mode == 1) {
+      const float k = lp.lambda_sc * (1.0f / 3.0f) * lp.inv_n;
+#pragma unroll
+      for (int j = 0; j < SPL; ++j) {
+        int s = lane * SPL + j;
+        if (s < S) {
+          float* go = grow + s * n_out;
+          for (int c = 0; c < n_out; ++c) go[c] = 0.f;
+          go[4] = k * (-2.0f * (T[j] - rows[s * n_out + 4]) - w[j]);   // T, w detached (loss.py:9-10)
+        }
+      }
+    } else {
+      float Gw[SPL], Bv[SPL];
+      float Bsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < SPL; ++j) {
+        int s = lane * SPL + j;
+        Gw[j] = 0.f;
+        Bv[j] = 0.f;
+        if (s < S) {
+          const float* r = rows + s * n_out;
+          const float v = r[4];
+          float g = gB * r[8] + gd * zs[s];
+          g += gr * r[0] * (v + (1.0f - v) * r[5]) + gg * r[1] * (v + (1.0f - v) * r[6]) + gb * r[2] * (v + (1.0f - v) * r[7]);
+#pragma unroll
+          for (int c = 0; c < 10; ++c)
+            if (c < C) g += gs[c] * r[9 + c];
+          Gw[j] = g;
+          Bv[j] = g * alpha[j] * T[j];
+          Bsum += Bv[j];
+        }
+      }
+      float R = warp_excl_suffix_sum(Bsum, lane);
+#pragma unroll
+      for (int j = SPL - 1; j >= 0; --j) {
+        int s = lane * SPL + j;
+        if (s < S) {
+          const float* r = rows + s * n_out;
+          float* go = grow + s * n_out;
+          const float dq = R / qv[j];
+          const float dalpha = Gw[j] * T[j] - dq;
+          SampleVals sv = sample_alpha(zs, r, s, S);
+          const float v = r[4], wj = w[j];
+          go[0] = gr * wj * (v + (1.0f - v) * r[5]);
+          go[1] = gg * wj * (v + (1.0f - v) * r[6]);
+          go[2] = gb * wj * (v + (1.0f - v) * r[7]);
+          go[3] = (sv.sigma > 0.f) ? dalpha * sv.e * sv.delta : 0.f;
+          go[4] = wj * (gr * r[0] * (1.0f - r[5]) + gg * r[1] * (1.0f - r[6]) + gb * r[2] * (1.0f - r[7]));
+          go[5] = gr * wj * r[0] * (1.0f - v);
+          go[6] = gg * wj * r[1] * (1.0f - v);
+          go[7] = gb * wj * r[2] * (1.0f - v);
+          go[8] = gB * wj;
+#pragma unroll
+          for (int c = 0; c < 10; ++c)
+            if (c < C) go[9 + c] = gs[c] * wj;
+          for (int c = 9 + C; c < n_out; ++c) go[c] = 0.f;
+        }
+        R += Bv[j];
+      }
+    }
+    __syncwarp();
+    float* dst = g_out + (size_t)ray * row_words;
+    if (vec_rows) {
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      const float4* g4 = reinterpret_cast<const float4*>(grow);
+#pragma unroll 8
+      for (int i = lane; i < row_words / 4; i += 32) d4[i] = g4[i];
+    } else {
+      for (int i = lane; i < row_words; i += 32) dst[i] = grow[i];
+    }
+    __syncwarp();
+  }
+  // every lane of a warp holds the same per-ray sums: one atomic per warp and term
+  if (lane < 7) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+      if (lane == i) v = lsum[i];
+    if (v != 0.f) atomicAdd(loss_terms + lane, v);
+  }
+}
+
+static int launch_k3_loss(const float* out, const float* z, int n_rays, int S, int n_out, int C, const float* gt_rgb,
+                          const long long* labels, const float* depth_gt, const float* depth_w, const float* counts,
+                          const LossParams& lp, float* g_out, float* loss_terms, cudaStream_t st) {
+  const int spl = (S + 31) / 32;
+  const size_t rw4 = (size_t)((S * n_out + 3) & ~3), s4 = (size_t)((S + 3) & ~3);
+  const size_t smem = (size_t)K3_WARPS * (2 * (rw4 + s4) + rw4) * sizeof(float);
+  int sms = num_sms();
+  if (sms <= 0) return SNB_ERR_NO_DEVICE;
+  int blocks = (n_rays + K3_WARPS - 1) / K3_WARPS;
+#define K3L_LAUNCH(SPL_)                                                                              \
+  do {                                                                                                \
+    auto kfn = k3_loss_kernel<SPL_>;                                                                  \
+    if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    int resident = 0;                                                                                 \
+    SNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, K3_WARPS * 32, smem));     \
+    if (resident < 1) resident = 1;                                                                   \
+    if (blocks > sms * resident) blocks = sms * resident;                                             \
+    kfn<<<blocks, K3_WARPS * 32, smem, st>>>(out, z, n_rays, S, n_out, C, gt_rgb, labels, depth_gt, depth_w, counts, lp, \
+                                             g_out, loss_terms);                                      \
+  } while (0)
+  if (spl <= 1) K3L_LAUNCH(1);
+  else if (spl <= 2) K3L_LAUNCH(2);
+  else if (spl <= 4) K3L_LAUNCH(4);
+  else K3L_LAUNCH(8);
+#undef K3L_LAUNCH
+  return launch_status("k3_loss_kernel");
+}
+
 }  // namespace snb
+
+extern "C" int snb_composite_loss(const float* out, const float* z_vals, int n_rays, int n_samples, int n_out, int n_classes,
+                                  const float* gt_rgb, const int64_t* labels, const float* depth_gt, const float* depth_w,
+                                  const float* counts, const snb_loss_params* p, float* g_out, float* loss_terms,
+                                  void* stream) {
+  if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes)) return r;
+  SNB_CHECK_ARG(p && g_out && loss_terms, SNB_ERR_INVALID, "composite_loss: null argument");
+  SNB_CHECK_ARG(p->mode >= 0 && p->mode <= 2, SNB_ERR_INVALID, "composite_loss: mode %d", p->mode);
+  SNB_CHECK_ARG(p->mode != 0 || gt_rgb != nullptr, SNB_ERR_INVALID, "composite_loss: the colour loss needs gt_rgb");
+  SNB_CHECK_ARG(p->mode != 2 || depth_gt != nullptr, SNB_ERR_INVALID, "composite_loss: the depth loss needs depth_gt");
+  SNB_CHECK_ARG(labels == nullptr || counts != nullptr || p->mode != 0, SNB_ERR_INVALID,
+                "composite_loss: labels need the device counts [n_valid, n_car]");
+  if (n_rays == 0) return 0;
+  snb::LossParams lp;
+  lp.mode = p->mode; lp.color = p->color; lp.beta_min = p->beta_min; lp.inv_n = p->inv_n; lp.lambda_s = p->lambda_s;
+  lp.ignore_index = p->ignore_index; lp.lambda_c = p->lambda_c; lp.car_label = p->car_label; lp.lambda_sc = p->lambda_sc;
+  lp.lambda_ds = p->lambda_ds;
+  return snb::launch_k3_loss(out, z_vals, n_rays, n_samples, n_out, n_classes, gt_rgb, reinterpret_cast<const long long*>(labels),
+                             depth_gt, depth_w, counts, lp, g_out, loss_terms, (cudaStream_t)stream);
+}
 
 extern "C" int snb_composite_forward(const float* out, const float* z_vals, int n_rays, int n_samples,
                                      int n_out, int n_classes, float* rgb, float* depth, float* weights,

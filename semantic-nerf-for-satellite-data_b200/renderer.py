@@ -21,7 +21,8 @@ from __future__ import annotations
 import torch
 
 from ._lib import HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, MODEL_SEMANTIC
-from .autograd import Composite, encode_rays, mlp_fp32, mlp_rays
+from . import _lib
+from .autograd import Composite, CompositeLoss, encode_rays, mlp_fp32, mlp_rays
 
 
 class B200Renderer:
@@ -45,6 +46,8 @@ class B200Renderer:
             z_vals = opts.get("z_vals")
         depth_only = opts.get("heads", "all") == "depth"
         sc = cfgs.pipeline.sc_lambda > 0 and not depth_only
+        if n == 0:   # an empty ray batch renders to empty tensors, as the reference's eager code does
+            return self._empty_result(model, rays, S, sc)
         self._calls += 1
         z, enc, enc_sc, aux, sky = encode_rays(model, emb, rays, extras, S, u=opts.get("u"), z=z_vals,
                                                seed=int(opts.get("seed", self._calls)),
@@ -85,6 +88,61 @@ class B200Renderer:
             result["sun_sc"] = out_sc[..., 4:5]
         result["_z_vals"] = z
         return result
+
+
+    def render_loss(self, models: dict, rays, extras, rgbs, semantic=None, *, color: str = "satnerf", lambda_s: float = 0.0,
+                    ignore_index: int = -100, lambda_c: float = 0.0, car_label: int = -1, beta_min: float = 0.05,
+                    depth=None, depth_weights=None, lambda_ds: float = 0.0, render_options=None):
+        """Training fast path: render + the losses that sit on the render outputs + their gradients
+        with the compositing fused (snb_composite_loss), without materialising any per-sample output tensor.
+        Equivalent to render_rays() followed by SNerfLoss / SatNerfLoss (color = "snerf" / "satnerf", with the solar
+        correction when cfgs.pipeline.sc_lambda > 0) [+ SemanticLoss + SemanticCarRegLoss when `semantic` labels are
+        given], or - with `depth` targets - to the depth-supervision pass + DepthLoss.  Returns (loss, terms) where
+        terms is a (8,) tensor in the order of autograd.LOSS_TERMS (the log-beta entry without its constant 3/2)."""
+        opts = render_options or {}
+        model = models["coarse"]
+        emb = models["t"].weight if "t" in models else None
+        n, S = rays.shape[0], self.N_samples
+        depth_pass = depth is not None
+        sc = self.cfgs.pipeline.sc_lambda > 0 and not depth_pass
+        self._calls += 1
+        z, enc, enc_sc, aux, sky = encode_rays(model, emb, rays, extras, S, u=opts.get("u"), z=opts.get("z_vals"),
+                                               seed=int(opts.get("seed", self._calls)),
+                                               ray_offset=int(opts.get("ray_offset", 0)), want_sc=sc)
+        C = model.semantic_n_classes
+        terms = torch.zeros(8, dtype=torch.float32, device=rays.device)
+        p = _lib.LossParams(mode=2 if depth_pass else 0, color=1 if color == "satnerf" else 0, beta_min=beta_min,
+                            inv_n=1.0 / max(n, 1), lambda_s=lambda_s, ignore_index=ignore_index, lambda_c=lambda_c,
+                            car_label=car_label, lambda_sc=self.cfgs.pipeline.sc_lambda, lambda_ds=lambda_ds)
+        counts = None
+        if semantic is not None and not depth_pass:
+            lab = semantic.reshape(-1)
+            counts = torch.stack([(lab != ignore_index).sum(), (lab == car_label).sum()]).float()
+            semantic = lab.contiguous()
+        out = mlp_rays(model, emb, enc, aux, sky, extras, n, S, HEADS_DEPTH if depth_pass else HEADS_ALL).view(n, S, -1)
+        loss = CompositeLoss.apply(out, z, 0 if depth_pass else C, p, rgbs, None if depth_pass else semantic, depth,
+                                   depth_weights, counts, terms)
+        if sc:
+            p_sc = _lib.LossParams(mode=1, color=0, beta_min=beta_min, inv_n=1.0 / max(n, 1), lambda_s=0.0, ignore_index=-100,
+                                   lambda_c=0.0, car_label=-1, lambda_sc=self.cfgs.pipeline.sc_lambda, lambda_ds=0.0)
+            out_sc = mlp_rays(model, emb, enc_sc, aux, None, extras, n, S, HEADS_SOLAR).view(n, S, -1)
+            loss = loss + CompositeLoss.apply(out_sc, z, 0, p_sc, None, None, None, None, None, terms)
+        return loss, terms
+
+    @staticmethod
+    def _empty_result(model, rays, S, sc):
+        f = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=rays.device)
+        res = {"rgb": f(0, 3), "depth": f(0), "weights": f(0, S), "transparency": f(0, S), "albedo": f(0, S, 3),
+               "sun": f(0, S, 1), "sky": f(0, S, 3), "beta": f(0, S, 1), "sigmas": f(0, S)}
+        if model.kind == MODEL_SEMANTIC:
+            res["semantic_logits"] = f(0, model.semantic_n_classes)
+            res["semantic_label"] = torch.empty(0, dtype=torch.int64, device=rays.device)
+        if getattr(model, "variant", None) == "snerf":
+            del res["beta"], res["sigmas"]
+        if sc:
+            res.update(weights_sc=f(0, S), transparency_sc=f(0, S), sun_sc=f(0, S, 1))
+        res["_z_vals"] = f(0, S)
+        return res
 
 
 # the reference's two renderer class names, for configs / code that instantiate them by name

@@ -39,7 +39,7 @@ def default_cfgs(kind: str = "semantic", n_samples: int = 64, sc_lambda: float =
 
 class Trainer:
     def __init__(self, cfgs, kind: str = "semantic", n_classes: int = 6, device="cuda", car_index: int = 4,
-                 world: int = 1, rank: int = 0, seed: int = 0):
+                 world: int = 1, rank: int = 0, seed: int = 0, fused_loss: bool = True):
         p = cfgs.pipeline
         self.cfgs, self.kind, self.device, self.world, self.rank = cfgs, kind, torch.device(device), world, rank
         torch.manual_seed(seed)  # identical initial replicas on every rank
@@ -67,6 +67,9 @@ class Trainer:
         self.exp_avg_sq = torch.zeros_like(flat.data)
         self.emb_opt = torch.optim.Adam(self.models["t"].parameters(), lr=self.lr) if "t" in self.models else None
         self.step_idx = 0
+        # fused_loss: compositing + the loss modules + their backward in one kernel per pass (renderer.render_loss,
+        # SURVEY 8f rank 1); False runs render_rays() + the reference-shaped loss modules (what a Lightning pipeline does)
+        self.fused_loss = fused_loss
         self.reducer = snb_dist.GradAllReducer(snb_dist.bucket_ranges(model.table, flat.numel(), 3))
 
     # -- one step ---------------------------------------------------------------------------------------
@@ -76,6 +79,8 @@ class Trainer:
         model, emb = self.models["coarse"], self.models.get("t")
         self.step_idx += 1
         opts = {"seed": self.step_idx, "ray_offset": ray_offset}
+        if self.fused_loss:
+            return self._fused_step(batch, epoch, depth_batch, opts)
         results = self.renderer.render_rays(self.models, batch["rays"], batch["extras"], epoch=epoch, render_options=opts)
         if epoch < p.first_beta_epoch or self.kind == "snerf":
             loss, loss_dict = self.loss_without_beta(results, batch["rgbs"])
@@ -102,6 +107,31 @@ class Trainer:
         loss.backward()
         self.optimizer_step()
         self.last_loss_dict = loss_dict
+        return loss.detach()
+
+    def _fused_step(self, batch, epoch, depth_batch, opts):
+        """the same step through renderer.render_loss: same loss value and gradients, no per-sample output tensors"""
+        p = self.cfgs.pipeline
+        model, emb = self.models["coarse"], self.models.get("t")
+        sem = self.kind == "semantic"
+        car = sem and self.car_reg_loss is not None and epoch >= p.car_reg_loss_start
+        loss, terms = self.renderer.render_loss(
+            self.models, batch["rays"], batch["extras"], batch["rgbs"], batch["semantic"] if sem else None,
+            color="snerf" if (epoch < p.first_beta_epoch or self.kind == "snerf") else "satnerf",
+            lambda_s=p.lambda_s if sem else 0.0, ignore_index=self.car_index if (sem and p.ignore_car_index) else -100,
+            lambda_c=p.lambda_c if car else 0.0, car_label=self.car_index, render_options=opts)
+        if depth_batch is not None:
+            w = None if p.ds_noweights else depth_batch["weights"].flatten()
+            l_d, t_d = self.renderer.render_loss(self.models, depth_batch["rays"], depth_batch["extras"], None,
+                                                 depth=depth_batch["depths"].flatten(), depth_weights=w, lambda_ds=p.ds_lambda,
+                                                 render_options={"seed": self.step_idx + (1 << 20)})
+            loss, terms = loss + l_d, terms + t_d
+        model.flat.grad = None
+        if emb is not None:
+            emb.weight.grad = None
+        loss.backward()
+        self.optimizer_step()
+        self.last_loss_terms = terms          # device tensor, order of autograd.LOSS_TERMS (no host sync here)
         return loss.detach()
 
     def optimizer_step(self):

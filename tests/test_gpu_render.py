@@ -321,3 +321,68 @@ def test_snerf_training_step_runs_and_learns():
     batch = {"rays": rays.to(DEV), "extras": extras.to(DEV), "rgbs": rgbs.to(DEV)}
     losses = [tr.training_step(batch, epoch=3).item() for _ in range(12)]
     assert all(l == l for l in losses) and losses[-1] < losses[0]
+
+
+def test_empty_and_single_ray_batches():
+    """edge sizes: an empty batch gives empty tensors under every key; one ray (a 64-row tail of one 256-row block) renders"""
+    from semnerf_b200.renderer import B200Renderer
+    _lib_or_fail()
+    S = 64
+    spec, params, emb, cfgs, model, t = _model("semantic", 6, seed=2, S=S)
+    models = {"coarse": model, "t": t}
+    r = B200Renderer(cfgs)
+    rays, extras = O.synthetic_rays(3, seed=1)
+    with torch.no_grad():
+        full = r.render_rays(models, rays.to(DEV), extras.to(DEV), render_options={"u": torch.full((3, S), 0.5, device=DEV)})
+        none = r.render_rays(models, rays[:0].to(DEV), extras[:0].to(DEV))
+        one = r.render_rays(models, rays[:1].to(DEV), extras[:1].to(DEV), render_options={"u": torch.full((1, S), 0.5, device=DEV)})
+    assert set(none) == set(full)
+    for k in full:
+        assert none[k].shape == (0,) + tuple(full[k].shape[1:]) and none[k].dtype == full[k].dtype, k
+        assert torch.equal(one[k], full[k][:1]), k          # a ray's result does not depend on its batch
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K3 + losses fused (snb_composite_loss, SURVEY 8f rank 1) against render_rays() + the reference-shaped loss modules
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,epoch,with_depth", [("semantic", 3, False), ("semantic", 1, True), ("satnerf", 3, True),
+                                                   ("snerf", 3, False)])
+def test_fused_loss_step_equals_module_losses(kind, epoch, with_depth):
+    from semnerf_b200 import synth
+    from semnerf_b200.trainer import Trainer, default_cfgs
+    _lib_or_fail()
+    C = 6 if kind == "semantic" else 0
+    n = 777   # ragged: not a multiple of the warps per block
+    cfgs = default_cfgs(kind, n_samples=64, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=0)
+    rays, extras = synth.make_rays(n, seed=3)
+    rgbs, labels, depths = synth.make_targets(rays, C, seed=3)
+    batch = {"rays": rays.to(DEV), "extras": extras.to(DEV), "rgbs": rgbs.to(DEV), "semantic": labels.to(DEV)}
+    dbatch = None
+    if with_depth:
+        dr, de = synth.make_rays(300, seed=4)
+        dbatch = {"rays": dr.to(DEV), "extras": de.to(DEV), "depths": depths[:300].to(DEV).view(-1, 1),
+                  "weights": torch.rand(300, generator=torch.Generator().manual_seed(1)).to(DEV)}
+    res = {}
+    for fused in (True, False):
+        tr = Trainer(cfgs, kind, C, device=DEV, car_index=4, seed=0, fused_loss=fused)
+        loss = tr.training_step(batch, epoch=epoch, depth_batch=dbatch)
+        res[fused] = (loss.item(), tr.models["coarse"].flat.grad.clone(),
+                      tr.models["t"].weight.grad.clone() if "t" in tr.models else None,
+                      tr.last_loss_terms.cpu() if fused else {k: v.detach() for k, v in tr.last_loss_dict.items()})
+    lf, gf, ef, terms = res[True]
+    lu, gu, eu, ldict = res[False]
+    assert abs(lf - lu) <= 2e-5 * max(1.0, abs(lu)), (lf, lu)
+    assert _cos(gf, gu) >= 0.99999 and (gf - gu).abs().max() <= 1e-4 * gu.abs().max()
+    if ef is not None:
+        assert _cos(ef, eu) >= 0.9999
+    # the individual terms match the loss modules' dictionary
+    t = dict(zip(("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3", "ds"), terms.tolist()))
+    assert abs(t["color"] - float(ldict["coarse_color"])) <= 2e-5 * max(1.0, float(ldict["coarse_color"]))
+    if "coarse_logbeta" in ldict:
+        assert abs(t["logbeta"] + 1.5 - float(ldict["coarse_logbeta"])) <= 2e-5
+    assert abs(t["sc_term2"] - float(ldict["coarse_sc_term2"])) <= 1e-6 and abs(t["sc_term3"] - float(ldict["coarse_sc_term3"])) <= 1e-6
+    if kind == "semantic":
+        assert abs(t["semantic"] - float(ldict["coarse_semantic"])) <= 1e-6
+        assert abs(t["car_reg"] - float(ldict["coarse_car_reg_loss"])) <= 1e-6
+    if with_depth:
+        assert abs(t["ds"] - float(ldict["coarse_ds"])) <= 2e-5 * max(1.0, float(ldict["coarse_ds"]))
