@@ -153,6 +153,7 @@ def workload_config(args, cpu=False):
                     "SemanticCarRegLoss, Adam; steady-state step (after the depth-supervision drop)",
         "rays_per_gpu_per_step": args.cpu_rays if cpu else args.batch, "samples_per_ray": N_SAMPLES,
         "n_classes": N_CLASSES, "parallelism": f"dp{args.gpus}",
+        "losses": "loss modules on render_rays()" if getattr(args, "module_losses", False) else "fused into the compositing kernel",
         "l2": "per-step activation working set (~30 GB at 8192 rays) >> 126 MB L2; no flush needed",
     }
 
@@ -245,7 +246,8 @@ def run_gpu(args):
     lib = _lib.load()
     B = args.batch
     cfgs = default_cfgs("semantic", n_samples=N_SAMPLES, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=0)
-    tr = Trainer(cfgs, "semantic", N_CLASSES, device=dev, car_index=CAR_INDEX, world=world, rank=rank, seed=0)
+    tr = Trainer(cfgs, "semantic", N_CLASSES, device=dev, car_index=CAR_INDEX, world=world, rank=rank, seed=0,
+                 fused_loss=not args.module_losses)
     host = [make_batch(B, seed=100 * rank + i, pinned=True) for i in range(4)]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
 
@@ -377,6 +379,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--module-losses", action="store_true",
+                    help="render_rays() + the reference-shaped loss modules instead of the fused K3 + loss kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
