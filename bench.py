@@ -334,7 +334,9 @@ def run_gpu(args):
         render = {"samples_per_s": rs, "rays": nr, "chunk_rays": 40960, "passes": "main + solar-correction",
                   "tensor_frac": rs * ALG_FLOP_PER_RENDER_SAMPLE / 1e12 / peak_tf}
         try:
-            hbm = hbm_kernel_rooflines(lib, dev, peak_hbm)
+            # at the reference's render chunk (40 960 rays: 43-350 us launches, ramp and tail included) and at 4 chunks
+            hbm = {"chunk_40960": hbm_kernel_rooflines(lib, dev, peak_hbm, 40960),
+                   "rays_163840": hbm_kernel_rooflines(lib, dev, peak_hbm, 163840)}
         except Exception as e:   # secondary numbers must not take the headline line down
             hbm = {"error": str(e)[:200]}
         if world == 1 and not args.no_cpu:

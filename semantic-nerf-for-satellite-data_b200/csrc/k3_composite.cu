@@ -160,10 +160,24 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
 #pragma unroll
         for (int c = 0; c < 10; ++c)
           if (c < C) acc_s[c] += w[j] * r[9 + c];
-        if (!BWD) {
-          weights[(size_t)ray * S + s] = w[j];
-          transparency[(size_t)ray * S + s] = T[j];
-        }
+      }
+    }
+    if (!BWD) {
+      // this lane's SPL consecutive samples: one 8 / 16-byte store per tensor when the row allows it
+      const size_t o = (size_t)ray * S + (size_t)lane * SPL;
+      if (SPL == 2 && (S & 1) == 0 && lane * SPL + 1 < S) {
+        *reinterpret_cast<float2*>(weights + o) = make_float2(w[0], w[1 % SPL]);
+        *reinterpret_cast<float2*>(transparency + o) = make_float2(T[0], T[1 % SPL]);
+      } else if (SPL == 4 && (S & 3) == 0 && lane * SPL + 3 < S) {
+        *reinterpret_cast<float4*>(weights + o) = make_float4(w[0], w[1 % SPL], w[2 % SPL], w[3 % SPL]);
+        *reinterpret_cast<float4*>(transparency + o) = make_float4(T[0], T[1 % SPL], T[2 % SPL], T[3 % SPL]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < SPL; ++j)
+          if (lane * SPL + j < S) {
+            weights[o + j] = w[j];
+            transparency[o + j] = T[j];
+          }
       }
     }
     acc_d = warp_sum(acc_d);
