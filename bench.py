@@ -323,11 +323,12 @@ def run_gpu(args):
         from semnerf_b200 import synth
         rr, ee = synth.make_rays(nr, seed=7)
         rr, ee = rr.to(dev), ee.to(dev)
-        tr.render_image(rr[:40960], ee[:40960])
+        rkeys = ("rgb_coarse", "depth_coarse", "semantic_label_coarse", "sun_sc_coarse")   # sun_sc: keeps the solar pass in
+        tr.render_image(rr[:40960], ee[:40960], keys=rkeys)
         torch.cuda.synchronize()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         r0.record()
-        tr.render_image(rr, ee)
+        tr.render_image(rr, ee, keys=rkeys)
         r1.record()
         torch.cuda.synchronize()
         rs = nr * N_SAMPLES / (r0.elapsed_time(r1) * 1e-3)

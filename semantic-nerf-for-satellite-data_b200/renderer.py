@@ -14,7 +14,8 @@ render_options (all optional, default = reference behaviour):
   "heads": "all" | "depth" - "depth" evaluates only trunk + sigma (what the depth-supervision
       batch consumes, semantic/components/training_step.py:32-46) and skips the solar pass;
   "precision": "bf16" (default: the tcgen05 path) | "fp32" - the fp32 verification mode (fp32 weights and
-      accumulation on the CUDA cores, inference only; also selected by cfgs.pipeline.precision = "fp32").
+      accumulation on the CUDA cores, inference only; also selected by cfgs.pipeline.precision = "fp32");
+  "solar_pass": False - skip the solar-correction pass (its `*_sc` outputs feed only the training loss).
 """
 from __future__ import annotations
 
@@ -45,7 +46,9 @@ class B200Renderer:
         if z_vals is None:
             z_vals = opts.get("z_vals")
         depth_only = opts.get("heads", "all") == "depth"
-        sc = cfgs.pipeline.sc_lambda > 0 and not depth_only
+        # "solar_pass": False skips the solar-correction pass (its outputs feed only the training loss; an evaluation render
+        # that wants rgb / depth / labels need not pay for it - the reference always runs it when sc_lambda > 0)
+        sc = cfgs.pipeline.sc_lambda > 0 and not depth_only and bool(opts.get("solar_pass", True))
         if n == 0:   # an empty ray batch renders to empty tensors, as the reference's eager code does
             return self._empty_result(model, rays, S, sc)
         self._calls += 1

@@ -160,9 +160,11 @@ class Trainer:
         chunk = chunk or self.cfgs.pipeline.render_chunk_size
         n = rays.shape[0]
         out: Dict[str, torch.Tensor] = {}
+        want_sc = any("_sc_" in k for k in keys)   # the solar-correction pass only produces the *_sc keys
         for i in range(0, n, chunk):
             res = self.renderer.render_rays(self.models, rays[i:i + chunk], extras[i:i + chunk],
-                                            render_options={"seed": 1, "ray_offset": i, "heads": heads})
+                                            render_options={"seed": 1, "ray_offset": i, "heads": heads,
+                                                            "solar_pass": want_sc})
             for k in keys:
                 if k not in res:
                     continue

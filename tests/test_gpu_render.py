@@ -139,6 +139,10 @@ def test_render_depth_only_heads_and_no_grad_path():
         dep = r.render_rays(models, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV), "heads": "depth"})
     assert torch.equal(full["depth_coarse"], dep["depth_coarse"]) and torch.equal(full["weights_coarse"], dep["weights_coarse"])
     assert "weights_sc_coarse" not in dep
+    with torch.no_grad():   # an evaluation render may skip the solar-correction pass: same main outputs, no *_sc keys
+        nosc = r.render_rays(models, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV), "solar_pass": False})
+    assert set(full) - set(nosc) == {"weights_sc_coarse", "transparency_sc_coarse", "sun_sc_coarse"}
+    assert all(torch.equal(nosc[k], full[k]) for k in nosc)
     # under no_grad the MLP ran in inference mode (cached inference workspace: L2 scratch, no saved activations) although
     # the parameters require grad; with grad enabled it does not touch that cache
     assert len(model.__dict__.get("_ws_infer", {})) == 1
