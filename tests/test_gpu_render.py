@@ -390,3 +390,38 @@ def test_fused_loss_step_equals_module_losses(kind, epoch, with_depth):
         assert abs(t["car_reg"] - float(ldict["coarse_car_reg_loss"])) <= 1e-6
     if with_depth:
         assert abs(t["ds"] - float(ldict["coarse_ds"])) <= 2e-5 * max(1.0, float(ldict["coarse_ds"]))
+
+
+def test_bf16_mode_statistical_parity_on_a_trained_model():
+    """The bf16-mode criteria of the parity contract on weights with real class margins: train a few hundred steps on the
+    procedural scene with the B200 trainer, then render held-out rays with the tcgen05 path and with the fp32 oracle from
+    the SAME state_dict: PSNR against the targets within 0.05 dB, semantic argmax agreement >= 99.9 %."""
+    from semnerf_b200 import synth
+    from semnerf_b200.trainer import Trainer, default_cfgs
+    _lib_or_fail()
+    C, S = 6, 64
+    cfgs = default_cfgs("semantic", n_samples=S, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=0)
+    tr = Trainer(cfgs, "semantic", C, device=DEV, car_index=4, seed=0)
+    rays, extras = synth.make_rays(4096, seed=21)
+    rgbs, labels, _ = synth.make_targets(rays, C, seed=21)
+    for i in range(250):
+        sl = slice((i % 2) * 2048, (i % 2 + 1) * 2048)
+        tr.training_step({"rays": rays[sl].to(DEV), "extras": extras[sl].to(DEV), "rgbs": rgbs[sl].to(DEV),
+                          "semantic": labels[sl].to(DEV)}, epoch=3)
+    n = 3072
+    vr, ve = synth.make_rays(n, seed=22)
+    vrgb, vlab, _ = synth.make_targets(vr, C, seed=22)
+    u = torch.rand(n, S, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ours = tr.renderer.render_rays(tr.models, vr.to(DEV), ve.to(DEV), render_options={"u": u.to(DEV), "solar_pass": False})
+        spec = O.ModelSpec(kind="semantic", n_classes=C)
+        params = {k: v.cpu() for k, v in tr.models["coarse"].state_dict().items()}
+        ref = O.render_rays(params, tr.models["t"].weight.detach().cpu(), spec, vr, ve, S, u=u, sc_lambda=0.0)
+    p_ours, p_ref = O.psnr(ours["rgb_coarse"].cpu(), vrgb), O.psnr(ref["rgb_coarse"], vrgb)
+    agree = (ours["semantic_label_coarse"].cpu() == ref["semantic_label_coarse"]).float().mean().item()
+    acc = (ref["semantic_label_coarse"] == vlab).float().mean().item()
+    print(f"trained model: PSNR ours {p_ours:.3f} dB, oracle {p_ref:.3f} dB; argmax agreement {agree:.5f}; label accuracy {acc:.3f}; "
+          f"max |rgb diff| {(ours['rgb_coarse'].cpu() - ref['rgb_coarse']).abs().max():.2e}")
+    assert p_ref > 15.0 and acc > 0.5            # the model has actually learnt the scene
+    assert abs(p_ours - p_ref) <= 0.05
+    assert agree >= 0.999
