@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libsnb.so")
 SOURCES = ["snb_host.cu", "k1_sample_encode.cu", "k2_gemm.cu", "k2_chain.cu", "k2_mlp.cu", "k3_composite.cu", "k_aux.cu", "k_fp32.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"] + (["-DSNB_EXPERIMENT_HALF_B"] if __import__("os").environ.get("SNB_EXPERIMENT_HALF_B") else [])
+         "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
 
 
 def _source_hash() -> str:

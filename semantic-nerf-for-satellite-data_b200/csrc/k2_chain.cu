@@ -236,16 +236,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       for (int kb = 0; kb < kb_total; ++kb) {
         mbar_wait(&emptyB[stage], phase ^ 1);
         if (elect_one()) {
-#ifdef SNB_EXPERIMENT_HALF_B
-          // EXPERIMENT ONLY (wrong results): every second k-block skips its B load - the L2 traffic of a 2-pair B multicast
-          const bool skip = (kb & 1) && !(c.g == 0 && c.l == 0 && c.s == 0 && c.j == 0);
-          if (lead_cta) { if (skip) mbar_arrive(&fullB[stage]); else mbar_expect_tx(&fullB[stage], b_bytes); }
-          else mbar_arrive_remote(&fullB[stage], 0);
-          if (!skip)
-#else
           if (lead_cta) mbar_expect_tx(&fullB[stage], b_bytes);
           else mbar_arrive_remote(&fullB[stage], 0);
-#endif
           tma_load_2d_2sm_hint(sB + stage * 16384, &args.maps[c.l].tmB, &fullB[stage], kb * GEMM_BLOCK_K, n_row, L2_EVICT_LAST);
         }
         __syncwarp();
