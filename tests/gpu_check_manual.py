@@ -1,7 +1,7 @@
 """GPU diagnostics: run each kernel family against its reference and print error statistics.
 
-    python tools/gpu_check.py            # every group, each in its own subprocess
-    python tools/gpu_check.py gemm k3    # selected groups (in-process)
+    python tests/gpu_check_manual.py            # every group, each in its own subprocess
+    python tests/gpu_check_manual.py gemm k3    # selected groups (in-process)
 
 Used during bring-up through `gpurun`; the pytest `-m gpu` suite asserts the same comparisons.
 Test infrastructure: imports oracle/.
