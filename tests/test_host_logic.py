@@ -94,3 +94,51 @@ def test_no_cpu_fallback():
     _, m = build("satnerf", 0)
     with pytest.raises(_lib.SnbError):
         m(torch.zeros(4, 3), input_sun_dir=torch.zeros(4, 3), input_t=torch.zeros(4, 4))
+
+
+def test_snerf_state_dict_is_the_reference_shadow_nerf():
+    """ShadowNeRFB200 runs on the SatNeRF kernel plan but exposes exactly ShadowNeRF's tensors (snerf.py:104-188): the
+    uncertainty block exists only in the flat buffer, at zero."""
+    from semnerf_b200.model import ShadowNeRFB200
+    spec = O.ModelSpec(kind="snerf", n_classes=0)
+    m = ShadowNeRFB200(layers=8, feat=512, skips=[4])
+    want = O.param_shapes(spec)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(want.keys()) and not any(k.startswith("beta_from_xyz") for k in sd)
+    assert all(tuple(sd[k].shape) == tuple(want[k]) for k in want)
+    assert m.number_of_outputs == 8 and m.n_out_kernel == 9
+    hidden = [(off, int(torch.tensor(shape).prod())) for name, off, shape in m.table if name.startswith("beta_from_xyz.")]
+    assert hidden and all(m.flat.data[o:o + n].abs().max() == 0 for o, n in hidden)
+    params, _ = O.make_params(spec, seed=3)
+    res = m.load_state_dict(params, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert all(m.flat.data[o:o + n].abs().max() == 0 for o, n in hidden)          # loading does not touch the hidden block
+    with pytest.raises(_lib.SnbError):
+        ShadowNeRFB200(layers=8, feat=256)                                        # only the shipped 8x512 configuration
+
+
+def test_loss_params_struct_matches_the_header():
+    """ctypes mirror of snb_loss_params: same field order and types as include/snb.h (10 x 4 bytes)."""
+    import ctypes
+    import os
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "snb.h")).read()
+    body = re.search(r"typedef struct snb_loss_params \{(.*?)\} snb_loss_params;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            typ, names = decl.split(None, 1)
+            fields += [(n.strip(), typ) for n in names.split(",")]
+    got = [(n, "int" if t is ctypes.c_int else "float") for n, t in _lib.LossParams._fields_]
+    assert got == fields and ctypes.sizeof(_lib.LossParams) == 4 * len(fields) == 40
+
+
+def test_render_loss_signature_and_term_order():
+    from semnerf_b200.autograd import LOSS_TERMS
+    sig = inspect.signature(B200Renderer.render_loss)
+    for name in ("models", "rays", "extras", "rgbs", "semantic", "color", "lambda_s", "ignore_index", "lambda_c", "car_label",
+                 "depth", "depth_weights", "lambda_ds", "render_options"):
+        assert name in sig.parameters, name
+    assert LOSS_TERMS == ("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3", "ds")
