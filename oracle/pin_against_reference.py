@@ -44,6 +44,11 @@ def build_reference(spec: O.ModelSpec, params, emb, n_samples, sc_lambda):
         from semantic.components.rendering import RSSemanticRendering
         model = RSSemanticNeRF(cfgs, types.SimpleNamespace(semantic_n_classes=spec.n_classes))
         renderer = RSSemanticRendering(cfgs)
+    elif spec.kind == "nerf":
+        from baseline.models.nerf import NeRF
+        from baseline.components.rendering import NeRFRendering
+        model = NeRF(layers=spec.layers, feat=spec.feat, skips=list(spec.skips))   # baseline/pipelines/nerf.py:26-34
+        renderer = NeRFRendering(cfgs)
     elif spec.kind == "snerf":
         from baseline.models.snerf import ShadowNeRF
         from baseline.components.rendering import SNeRFRendering
@@ -81,6 +86,8 @@ CASES = [
     ("sem_c6_s64_trained", "semantic", 6, 512, 24, 64, 0.05, 7),
     ("snerf_s64", "snerf", 0, 512, 24, 64, 0.05, 8),
     ("snerf_s8_nosc", "snerf", 0, 512, 16, 8, 0.0, 9),
+    ("nerf_s64", "nerf", 0, 512, 24, 64, 0.0, 10),
+    ("nerf_s8", "nerf", 0, 512, 16, 8, 0.0, 11),
 ]
 
 GOLDEN_KEYS = ["rgb_coarse", "depth_coarse", "weights_coarse", "transparency_coarse",
@@ -148,22 +155,28 @@ def main(write=True):
         sd = extras[:1, :3].expand(P, 3).contiguous()
         tt = emb[:1].expand(P, spec.tau).contiguous()
         with torch.no_grad():
-            a = model(xyz, input_sun_dir=sd) if spec.kind == "snerf" else model(xyz, input_sun_dir=sd, input_t=tt)
+            if spec.kind == "nerf":
+                a = model(xyz, input_dir=sd)
+            else:
+                a = model(xyz, input_sun_dir=sd) if spec.kind == "snerf" else model(xyz, input_sun_dir=sd, input_t=tt)
             b = O.mlp_forward(params, spec, xyz, sd, tt)
         assert (a - b).abs().max().item() <= 2e-6
         # gradient parity through the reference's own loss modules
-        from baseline.components.loss import SatNerfLoss, SNerfLoss
-        snerf = spec.kind == "snerf"
+        from baseline.components.loss import NerfLoss, SatNerfLoss, SNerfLoss
+        snerf = spec.kind in ("snerf", "nerf")
         gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(seed))
         for prm in model.parameters():
             prm.grad = None
         ref2 = ref_render(renderer, models, cfgs, rays, extras, z)
-        loss_ref, _ = (SNerfLoss if snerf else SatNerfLoss)(lambda_sc=sc)(ref2, gt)   # baseline/pipelines/snerf.py:21-22
+        if spec.kind == "nerf":
+            loss_ref, _ = NerfLoss()(ref2, gt)                                        # baseline/pipelines/nerf.py:23-24
+        else:
+            loss_ref, _ = (SNerfLoss if snerf else SatNerfLoss)(lambda_sc=sc)(ref2, gt)   # baseline/pipelines/snerf.py:21-22
         loss_ref.backward()
         p2 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
         e2 = emb.clone().requires_grad_(True)
         res2 = O.render_rays(p2, e2, spec, rays, extras, s, z=z, sc_lambda=sc)
-        loss = (O.snerf_loss if snerf else O.satnerf_loss)(res2, gt, lambda_sc=sc)
+        loss = (O.nerf_loss if spec.kind == "nerf" else O.snerf_loss if snerf else O.satnerf_loss)(res2, gt, lambda_sc=sc)
         loss.backward()
         assert abs(loss.item() - loss_ref.item()) <= 1e-5 * max(1, abs(loss_ref.item()))
         num = den_a = den_b = 0.0

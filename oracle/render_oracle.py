@@ -50,6 +50,9 @@ class ModelSpec:
     kind = "satnerf":  baseline/models/satnerf.py:101-206 (mapping=False: raw xyz input,
                        baseline/pipelines/satnerf.py:53-59 never overrides the default)
     kind = "semantic": semantic/models/rs_semantic.py:139-258 (positional Mapping always on)
+    kind = "nerf":     baseline/models/nerf.py:98-212 (NeRF as baseline/pipelines/nerf.py:26-34 builds it: the
+                       constructor defaults mapping=True, siren=False -> positional encoding of xyz (10 freqs) and of the
+                       view direction (4 freqs), ReLU activations, outputs [rgb | sigma])
     kind = "snerf":    baseline/models/snerf.py:104-188 (ShadowNeRF as baseline/pipelines/snerf.py:24-32 builds it:
                        SIREN, raw xyz): SatNeRF without the transient-uncertainty head and embedding, 8 outputs
     """
@@ -67,7 +70,11 @@ class ModelSpec:
 
     @property
     def k0(self) -> int:
-        return 2 * self.n_freq * 3 if self.kind == "semantic" else 3
+        return 2 * self.n_freq * 3 if self.kind in ("semantic", "nerf") else 3
+
+    @property
+    def kdir(self) -> int:   # encoded view direction (NeRF only): mapping_sizes[1] = 4 frequencies (nerf.py:104)
+        return 2 * 4 * 3
 
     @property
     def feat_last(self) -> int:
@@ -75,6 +82,8 @@ class ModelSpec:
 
     @property
     def n_out(self) -> int:
+        if self.kind == "nerf":
+            return 4
         if self.kind == "snerf":
             return 8
         return 9 + (self.n_classes if self.kind == "semantic" else 0)
@@ -98,10 +107,12 @@ def param_shapes(spec: ModelSpec) -> Dict[str, tuple]:
     s["sigma_from_xyz.0.bias"] = (1,)
     s["feats_from_xyz.weight"] = (f, f)
     s["feats_from_xyz.bias"] = (f,)
-    s["rgb_from_xyzdir.0.weight"] = (fl, f)
+    s["rgb_from_xyzdir.0.weight"] = (fl, f + (spec.kdir if spec.kind == "nerf" else 0))
     s["rgb_from_xyzdir.0.bias"] = (fl,)
     s["rgb_from_xyzdir.2.weight"] = (3, fl)
     s["rgb_from_xyzdir.2.bias"] = (3,)
+    if spec.kind == "nerf":   # nerf.py:140-160: no further heads
+        return s
     if spec.kind == "semantic":
         s["semantic_prediction.0.weight"] = (fl, f)
         s["semantic_prediction.0.bias"] = (fl,)
@@ -145,7 +156,8 @@ def make_params(spec: ModelSpec, seed: int = 0, dtype=torch.float32, trained_lik
             bound = 1.0 / math.sqrt(wshape[1])
         else:
             fan_in = shape[1]
-            siren_net = name.startswith("fc_net.") or name.startswith("sun_v_net.")
+            # NeRF is built with siren=False (baseline/pipelines/nerf.py:28-32): nn.Linear default init everywhere
+            siren_net = (name.startswith("fc_net.") or name.startswith("sun_v_net.")) and spec.kind != "nerf"
             if siren_net:
                 first = name in ("fc_net.0.weight", "sun_v_net.0.weight")
                 bound = 1.0 / fan_in if first else math.sqrt(6.0 / fan_in)
@@ -213,6 +225,8 @@ def mlp_forward(p: Dict[str, torch.Tensor], spec: ModelSpec, xyz: torch.Tensor,
     """(B,3),(B,3),(B,tau) -> (B, 9[+C]) packed [rgb 0:3 | sigma 3 | sun 4 | sky 5:8 | beta 8 | sem 9:].
     satnerf.py:208-255 / rs_semantic.py:260-340; Siren: commons.py:27-38 (w0=30 on the
     first trunk layer only, satnerf.py:146)."""
+    if spec.kind == "nerf":
+        return _nerf_forward(p, spec, xyz, sun_d, return_hidden)   # `sun_d` carries the view direction here
     enc = posenc(xyz, spec.n_freq) if spec.kind == "semantic" else xyz
     h = enc
     hidden = []
@@ -248,6 +262,25 @@ def mlp_forward(p: Dict[str, torch.Tensor], spec: ModelSpec, xyz: torch.Tensor,
     return out
 
 
+def _nerf_forward(p, spec: ModelSpec, xyz: torch.Tensor, view_d: torch.Tensor, return_hidden: bool = False):
+    """NeRF.forward, baseline/models/nerf.py:164-212 (mapping on, ReLU): (B,3),(B,3) -> (B,4) [rgb | sigma]."""
+    enc = posenc(xyz, spec.n_freq)
+    h = enc
+    hidden = []
+    for i in range(spec.layers):
+        if i in spec.skips:
+            h = torch.cat([enc, h], -1)
+        h = torch.relu(_lin(p, f"fc_net.{2 * i}", h))
+        hidden.append(h)
+    sigma = F.softplus(_lin(p, "sigma_from_xyz.0", h))
+    f = _lin(p, "feats_from_xyz", h)
+    x = torch.cat([f, posenc(view_d, 4)], -1)
+    rgb = torch.sigmoid(_lin(p, "rgb_from_xyzdir.2", torch.relu(_lin(p, "rgb_from_xyzdir.0", x))))
+    rgb = rgb * (1 + 2 * 0.001) - 0.001
+    out = torch.cat([rgb, sigma], 1)
+    return (out, hidden, f) if return_hidden else out
+
+
 # --------------------------------------------------------------------------------------
 # K3: compositing
 # --------------------------------------------------------------------------------------
@@ -269,8 +302,11 @@ def convert_sigmas(sigmas: torch.Tensor, z: torch.Tensor):
 def composite(out: torch.Tensor, z: torch.Tensor, n_classes: int = 0) -> Dict[str, torch.Tensor]:
     """Tail of ``inference``: satnerf.py:73-96 / rs_semantic.py:81-126.  ``out`` is (N,S,9[+C])."""
     rgbs, sigmas = out[..., :3], out[..., 3]
-    sun_v, sky = out[..., 4:5], out[..., 5:8]
     weights, depth, transparency, _ = convert_sigmas(sigmas, z)
+    if out.shape[-1] == 4:   # NeRF's inference (nerf.py:73-86): plain emission-absorption, no lighting model, no clamp
+        return {"rgb": torch.sum(weights.unsqueeze(-1) * rgbs, -2), "depth": depth, "weights": weights,
+                "transparency": transparency}
+    sun_v, sky = out[..., 4:5], out[..., 5:8]
     irradiance = sun_v + (1 - sun_v) * sky
     rgb = torch.clamp(torch.sum(weights.unsqueeze(-1) * rgbs * irradiance, -2), min=0.0, max=1.0)
     res = {
@@ -311,7 +347,12 @@ def render_rays(p, emb: torch.Tensor, spec: ModelSpec, rays: torch.Tensor, extra
     o, d = rays[:, 0:3], rays[:, 3:6]
     sun_d = extras[:, 0:3]
     ts = extras[:, 3].long()
-    t = emb[ts] if spec.kind != "snerf" else None   # S-NeRF has no embedding (baseline/components/rendering.py:70-100)
+    t = emb[ts] if spec.kind not in ("snerf", "nerf") else None   # no embedding (baseline/components/rendering.py:70-118)
+    if spec.kind == "nerf":   # NeRFRendering (rendering.py:103-118): view direction instead of sun direction, one pass
+        res = inference(p, spec, sample_points(o, d, z), z, d, None)
+        out = {f"{k}_coarse": v for k, v in res.items()}
+        out["_z_vals"] = z
+        return out
     res = inference(p, spec, sample_points(o, d, z), z, sun_d, t)
     if sc_lambda > 0:
         tmp = inference(p, spec, sample_points(o, sun_d, z), z, sun_d, t)
@@ -353,6 +394,11 @@ def _solar_correction(res, lambda_sc):
     term2 = torch.sum(torch.square(res["transparency_sc_coarse"].detach() - sun_sc), -1)
     term3 = 1 - torch.sum(res["weights_sc_coarse"].detach() * sun_sc, -1)
     return lambda_sc / 3.0 * torch.mean(term2) + lambda_sc / 3.0 * torch.mean(term3)
+
+
+def nerf_loss(res, gt_rgb, lambda_sc=0.0):
+    """NerfLoss, baseline/components/loss.py:97-110 (coarse network only)."""
+    return F.mse_loss(res["rgb_coarse"], gt_rgb)
 
 
 def snerf_loss(res, gt_rgb, lambda_sc=0.05):
