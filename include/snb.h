@@ -38,7 +38,11 @@ enum {
 
 /* model kinds: baseline/models/satnerf.py:101 (raw xyz input) and
  * semantic/models/rs_semantic.py:139 (positional mapping, semantic head) */
-enum { SNB_MODEL_SATNERF = 0, SNB_MODEL_SEMANTIC = 1 };
+/* SNB_MODEL_NERF: vanilla NeRF as baseline/pipelines/nerf.py:26-34 builds it (baseline/models/nerf.py:98-212): positional
+ * encoding of xyz (10) and of the view direction (4), ReLU activations, outputs [rgb | sigma].  It runs on the SatNeRF head
+ * layout with the sun / uncertainty blocks absent (zero weights) and the sun column pinned to 1, so the compositing kernel's
+ * irradiance is 1; the 24 encoded view-direction values ride a 32-column `aux` row (snb_nerf_aux). */
+enum { SNB_MODEL_SATNERF = 0, SNB_MODEL_SEMANTIC = 1, SNB_MODEL_NERF = 2 };
 
 /* which heads a pass evaluates (bit mask).  SNB_HEADS_ALL is the reference's forward();
  * SNB_HEADS_SOLAR is what the solar-correction pass keeps (semantic/components/rendering.py:76-78);
@@ -122,6 +126,11 @@ int snb_mlp_forward(const snb_model* m, const void* packed, void* workspace, siz
 int snb_mlp_backward(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
                      int64_t n_points, const void* enc, const void* aux, const float* out,
                      const float* g_out, int head_mask, float* grads, float* g_aux, void* stream);
+
+/* NeRF only: aux (P, 32) bf16 = [1, sin/cos(2^k d)_{k<4} (24, commons.py:68-74 order), 0 x 7] from the per-ray view
+ * directions dirs (N, 3) f32 (row stride `stride` floats), broadcast over the ray's n_samples samples.  Replaces
+ * Mapping(4, 3)(input_dir) + repeat_interleave (baseline/models/nerf.py:33-37,197-199). */
+int snb_nerf_aux(const float* dirs, int stride, int n_rays, int n_samples, void* aux32, void* stream);
 
 /* fp32 verification mode ("fp32 mode" of the parity contract: rgb / depth within 1e-3 of the reference's fp32 CPU path
  * for ANY weights, not only at the initialisers).  Same forward as snb_mlp_forward - Model.forward of

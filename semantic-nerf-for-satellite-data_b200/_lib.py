@@ -13,7 +13,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libsnb.so")
 
-MODEL_SATNERF, MODEL_SEMANTIC = 0, 1
+MODEL_SATNERF, MODEL_SEMANTIC, MODEL_NERF = 0, 1, 2
 HEADS_ALL, HEADS_SOLAR, HEADS_DEPTH = 63, 5, 1
 EPI_SIN, EPI_LINEAR, EPI_MUL, EPI_HEADOUT, EPI_F32ROWS, EPI_WGRAD = range(6)
 
@@ -37,6 +37,7 @@ SIGNATURES = {
     "snb_mlp_workspace_bytes": (_sz, [_vp, _i64, _i]),
     "snb_mlp_forward": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "snb_mlp_backward": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "snb_nerf_aux": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "snb_mlp_fp32_workspace_bytes": (_sz, [_vp, _i64]),
     "snb_mlp_forward_fp32": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "snb_ray_param_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

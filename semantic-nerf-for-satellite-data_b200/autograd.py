@@ -47,14 +47,32 @@ def encode_rays(model, emb_weight, rays, extras, n_samples, u=None, z=None, seed
     enc_sc = torch.empty(P, model.enc_ld, dtype=torch.bfloat16, device=dev) if want_sc else None
     aux = torch.empty(P, 16, dtype=torch.bfloat16, device=dev)
     sky = torch.empty(n, 3, dtype=torch.float32, device=dev) if want_sky else None
-    w1, b1, w2, b2 = model.sky_params()
+    nerf = model.kind == _lib.MODEL_NERF      # no sky head; xyz is encoded like the semantic model's
+    if nerf:
+        sky, (w1, b1, w2, b2), hidden = None, (None, None, None, None), 0
+    else:
+        w1, b1, w2, b2 = model.sky_params()
+        hidden = w1.shape[0]
     ew = _f32c(emb_weight.detach()) if emb_weight is not None else None
     check(lib.snb_sample_encode(ptr(rays), ptr(extras), ptr(_f32c(u)), seed, ray_offset, ptr(t_steps(n_samples, dev)),
                                 ptr(ew), ew.shape[0] if ew is not None else 0, ew.shape[1] if ew is not None else 0,
-                                ptr(w1), ptr(b1), ptr(w2), ptr(b2), w1.shape[0], n, n_samples, model.kind,
+                                ptr(w1), ptr(b1), ptr(w2), ptr(b2), hidden, n, n_samples,
+                                _lib.MODEL_SEMANTIC if nerf else model.kind,
                                 1 if z_given else 0, ptr(z_vals), ptr(enc), ptr(enc_sc), ptr(aux), ptr(sky), stream()),
           "snb_sample_encode")
+    if nerf:   # the aux row of NeRF: [1, Mapping(4, 3)(view direction), 0...] (32 columns) instead of [1, sun_d, t]
+        aux = nerf_aux(rays[:, 3:6], n_samples)
     return z_vals, enc, enc_sc, aux, sky
+
+
+def nerf_aux(dirs, n_samples: int):
+    """(N,3) view directions -> aux (N * n_samples, 32) bf16 (snb_nerf_aux)."""
+    lib = _lib.load()
+    dirs = _f32c(dirs)
+    n = dirs.shape[0]
+    aux = torch.empty(n * n_samples, 32, dtype=torch.bfloat16, device=dirs.device)
+    check(lib.snb_nerf_aux(ptr(dirs), 3, n, n_samples, ptr(aux), stream()), "snb_nerf_aux")
+    return aux
 
 
 def _workspace(model, P, train, device):
@@ -105,7 +123,7 @@ class MLPRays(torch.autograd.Function):
         check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws), ws.numel(), P, ptr(enc), ptr(aux), ptr(out),
                                    ptr(g_out), head_mask, ptr(g_flat), ptr(g_aux), stream()), "snb_mlp_backward")
         g_emb = torch.zeros_like(emb_weight) if want_emb else None
-        sky_arg = sky if head_mask == HEADS_ALL else None
+        sky_arg = sky if (head_mask == HEADS_ALL and model.kind != _lib.MODEL_NERF) else None
         if sky_arg is not None or g_aux is not None:
             vocab, tau = (emb_weight.shape if want_emb else (1, 0))
             check(lib.snb_ray_param_backward(model._h, ptr(flat.detach()), ptr(extras), ptr(sky_arg), ptr(g_out),
@@ -125,11 +143,18 @@ class MLPPoints(torch.autograd.Function):
         dev = xyz.device
         enc = torch.empty(P, model.enc_ld, dtype=torch.bfloat16, device=dev)
         aux = torch.empty(P, 16, dtype=torch.bfloat16, device=dev)
-        sky = torch.empty(P, 3, dtype=torch.float32, device=dev)
-        w1, b1, w2, b2 = model.sky_params()
+        nerf = model.kind == _lib.MODEL_NERF   # `sun_d` is the view direction there; no sky head, no embedding
+        if nerf:
+            sky, (w1, b1, w2, b2), hidden = None, (None, None, None, None), 0
+        else:
+            sky = torch.empty(P, 3, dtype=torch.float32, device=dev)
+            w1, b1, w2, b2 = model.sky_params()
+            hidden = w1.shape[0]
         check(lib.snb_encode_points(ptr(xyz), ptr(sun_d), ptr(tt), tt.shape[1], ptr(w1), ptr(b1), ptr(w2), ptr(b2),
-                                    w1.shape[0], P, model.kind, ptr(enc), ptr(aux), ptr(sky), stream()),
-              "snb_encode_points")
+                                    hidden, P, _lib.MODEL_SEMANTIC if nerf else model.kind, ptr(enc), ptr(aux), ptr(sky),
+                                    stream()), "snb_encode_points")
+        if nerf:
+            aux = nerf_aux(sun_d, 1)
         ws = _workspace(model, P, train, dev)
         out = torch.empty(P, model.n_out_kernel, dtype=torch.float32, device=dev)
         packed = model.packed()
@@ -152,6 +177,8 @@ class MLPPoints(torch.autograd.Function):
         g_aux = torch.empty(P, 16, dtype=torch.float32, device=enc.device)
         check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws), ws.numel(), P, ptr(enc), ptr(aux), ptr(out),
                                    ptr(g_out), HEADS_ALL, ptr(g_flat), ptr(g_aux), stream()), "snb_mlp_backward")
+        if model.kind == _lib.MODEL_NERF:   # no sky_color parameters, no embedding
+            return g_flat, None, None, None, None, None
         extras = torch.cat([sun_d, torch.zeros(P, 1, device=sun_d.device)], 1).contiguous()
         check(lib.snb_ray_param_backward(model._h, ptr(flat.detach()), ptr(extras), ptr(sky), ptr(g_out), None, P, 1,
                                          model.n_out_kernel, 0, 1, ptr(g_flat), None, stream()),

@@ -57,7 +57,7 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 
 
 // ---- epilogue math, specialised per mode so the inner loops are branch-free ---------------------------------
-enum ChunkMode { CM_LINEAR = 0, CM_SIN = 1, CM_SIN_MASK = 2 };
+enum ChunkMode { CM_LINEAR = 0, CM_SIN = 1, CM_SIN_MASK = 2, CM_RELU = 3 };
 
 // 32 accumulator columns of one row -> 16 packed bf16x2 words (+ the sign bits of the SIREN derivative).
 // bsm: shared-memory address of this thread's 32 bias values, pre-multiplied by w0.
@@ -86,7 +86,10 @@ __device__ __forceinline__ void chunk_math(const uint32_t (&v)[32], uint32_t bsm
         else me = __funnelshift_r(me, u, 1);
       }
     }
-    if (MODE != CM_LINEAR) {
+    if (MODE == CM_RELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[j] = fmaxf(y[j], 0.f);
+    } else if (MODE != CM_LINEAR) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) y[j] = __sinf(y[j]);
     }
@@ -99,7 +102,8 @@ __device__ __forceinline__ void chunk_math(const uint32_t (&v)[32], uint32_t bsm
 // dgrad: accumulator * multiplicand, in place in the staged multiplicand tile (this thread's 4 x 16 bytes of a row).
 // SIREN: the multiplicand is the derivative w0 cos(.) rebuilt from the saved activation h = sin(.) (|h| <= 1 in bf16,
 // so 1 - h^2 >= 0 exactly) and its sign bit: |cos| = sqrt(1 - h^2); the signs are applied to the packed bf16x2 pairs.
-template <bool SIREN, bool W0ONE>
+// RELU: the multiplicand is the saved activation h = max(y, 0): derivative [h > 0]
+template <bool SIREN, bool W0ONE, bool RELU = false>
 __device__ __forceinline__ void chunk_mul(const uint32_t (&v)[32], uint32_t buf, uint32_t row_off, uint32_t sw, int half,
                                           float w0, uint32_t mw) {
 #pragma unroll
@@ -110,6 +114,10 @@ __device__ __forceinline__ void chunk_mul(const uint32_t (&v)[32], uint32_t buf,
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       float f0 = bf16_lo(q[p]), f1 = bf16_hi(q[p]);
+      if (RELU) {
+        f0 = f0 > 0.f ? 1.0f : 0.f;
+        f1 = f1 > 0.f ? 1.0f : 0.f;
+      }
       if (SIREN) {
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f0) : "f"(fmaf(-f0, f0, 1.0f)));
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(f1) : "f"(fmaf(-f1, f1, 1.0f)));
@@ -311,7 +319,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         mbar_arrive(bar);
       }
       if (g == 0 && ci == 0) {   // once per tile: its sign-mask words
-        if (tl.epi == EPI_MUL && tl.mul_siren) {
+        if (tl.epi == EPI_MUL && tl.mul_siren == 1) {
           mbar_expect_tx(mrdy, 4096);
           tma_load_2d_hint(mask_smem + par * 1024, &args.maps[t.l].tmMask, mrdy, t.j * 8, trow, L2_EVICT_FIRST);
         } else {
@@ -422,7 +430,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       const float w0 = ly.w0;
       const uint32_t* mask = ly.mask;
       const int mask_ld = ly.mask_ld;
-      const bool siren = ly.mul_siren != 0;
+      const bool siren = ly.mul_siren == 1;
+      const bool relu_bwd = ly.mul_siren == 2;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
       const int blk = (c.g * CHAIN_SLOTS + c.s) * n_pairs + pair;
       const int m_real = blk * 256 + (int)cta_rank * GEMM_BLOCK_M;
@@ -479,7 +488,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
 #pragma unroll
               for (int j = 0; j < 3; ++j) o[j] = (hm & SNB_HEAD_RGB) ? (1.0f / (1.0f + expf(-x[j]))) * 1.002f - 0.001f : 0.f;
               o[3] = (hm & SNB_HEAD_SIGMA) ? (x[3] > 20.f ? x[3] : log1pf(expf(x[3]))) : 0.f;
-              o[4] = (hm & SNB_HEAD_SUN) ? 1.0f / (1.0f + expf(-x[4])) : 0.f;
+              o[4] = args.nerf ? 1.0f : ((hm & SNB_HEAD_SUN) ? 1.0f / (1.0f + expf(-x[4])) : 0.f);
               if ((hm & SNB_HEAD_SKY) && args.sky != nullptr) {
                 const long long ray = args.rows_per_ray > 0 ? grow / args.rows_per_ray : grow;
                 o[5] = __ldg(args.sky + ray * 3);
@@ -514,7 +523,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
 
           if (epi == EPI_MUL) {
             mbar_wait(brdy, itc & 1);   // the multiplicand tile has landed in the staging buffer
-            if (!siren) chunk_mul<false, true>(v, buf0, row_off, sw, half, w0, mw);
+            if (relu_bwd) chunk_mul<false, true, true>(v, buf0, row_off, sw, half, w0, mw);
+            else if (!siren) chunk_mul<false, true>(v, buf0, row_off, sw, half, w0, mw);
             else if (w0 == 1.0f) chunk_mul<true, true>(v, buf0, row_off, sw, half, w0, mw);
             else chunk_mul<true, false>(v, buf0, row_off, sw, half, w0, mw);
           } else {
@@ -522,6 +532,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
             uint32_t mbits = 0;
             const uint32_t bs = bsm + ci * 128;
             if (epi == EPI_LINEAR) chunk_math<CM_LINEAR>(v, bs, w0, outw, mbits);
+            else if (ly.relu) chunk_math<CM_RELU>(v, bs, w0, outw, mbits);
             else if (mask == nullptr) chunk_math<CM_SIN>(v, bs, w0, outw, mbits);
             else chunk_math<CM_SIN_MASK>(v, bs, w0, outw, mbits);
             mbar_wait(brdy, itc & 1);   // the store that last used this buffer (previous tile) has drained
@@ -576,7 +587,7 @@ int chain_launch(const ChainArgs& a, cudaStream_t st) {
     if (ly.epi == EPI_HEADOUT)
       SNB_CHECK_ARG(ly.n_tiles == 1 && (ly.rows_mode == 2 ? a.out_packed != nullptr : ly.part != nullptr), SNB_ERR_INVALID,
                     "chain: head-output layer %d needs its destination", l);
-    SNB_CHECK_ARG(!(ly.epi == EPI_MUL && ly.mul_siren) || (ly.mask != nullptr && ly.mask_ld > 0), SNB_ERR_INVALID,
+    SNB_CHECK_ARG(!(ly.epi == EPI_MUL && ly.mul_siren == 1) || (ly.mask != nullptr && ly.mask_ld > 0), SNB_ERR_INVALID,
                   "chain: layer %d needs the sign mask of the saved activation", l);
     macs += (double)a.n_blocks * 256.0 * (ly.epi == EPI_HEADOUT ? 16.0 : ly.n_tiles * 256.0) * ly.kb_total * GEMM_BLOCK_K;
   }

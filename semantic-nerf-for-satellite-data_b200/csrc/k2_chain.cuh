@@ -39,7 +39,8 @@ struct ChainLayer {     // scalars every role reads once per tile: kept together
   int kb_total;
   int n_tiles;          // N / 256
   int epi;              // EPI_SIN / EPI_LINEAR / EPI_MUL (256-column tiles) or EPI_HEADOUT (one 16-column tile, see `rows`)
-  int mul_siren;        // EPI_MUL: the multiplicand is the SIREN derivative rebuilt from the saved activation h = sin(y)
+  int relu;             // EPI_SIN layers: max(acc + bias, 0) instead of sin (vanilla NeRF); no sign mask
+  int mul_siren;        // EPI_MUL: 2 = ReLU derivative [h > 0] of the saved activation; 1 = the multiplicand is the SIREN derivative rebuilt from the saved activation h = sin(y)
                         // (tmMul) and the sign mask: w0 * (-1)^bit * sqrt(1 - h^2); 0: multiply by the tmMul tensor itself
   int o_scratch;        // outputs go to the per-pair scratch
   int mask_ld;          // 32-bit words per row of `mask`
@@ -64,6 +65,7 @@ struct ChainArgs {
   float* out_packed;
   const float* sky;     // (rays or points, 3) per-ray sky colour from K1
   int n_out, rows_per_ray, n_classes, sem_sigmoid, head_mask;
+  int nerf;             // head output: the sun column is written as 1 (no lighting model: irradiance = 1 in K3)
   ChainMaps maps[CHAIN_MAX_LAYERS];
 };
 

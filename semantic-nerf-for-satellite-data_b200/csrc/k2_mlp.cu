@@ -52,6 +52,7 @@ struct snb_model {
   int k0, enc_ld, w0_ld, hhw, n_out, tau;   // enc_ld: K1 row width; w0_ld: packed K of the first layer
   int hh_rgb, hh_beta, hh_sem, hh_sun;
   int kho;  // K of the head-output layer: 512 + 256 + hhw
+  int relu, aux_ld, kdir;   // vanilla NeRF: ReLU activations, 32-column aux rows carrying the 24 encoded view-direction values
   std::vector<snb::TensorInfo> tensors;
   int64_t n_params;
   // packed bf16 image (element offsets) ----------------------------------------------------------
@@ -178,6 +179,8 @@ static long long take(long long& cursor, long long elems) {
 static void build_layout(snb_model* m) {
   const int k0 = m->k0, hhw = m->hhw, tau = m->tau, C = m->n_classes;
   const bool sem = m->kind == SNB_MODEL_SEMANTIC;
+  const bool nerf = m->kind == SNB_MODEL_NERF;   // nerf.py:118-160: trunk, sigma, feats, rgb(f | dir) only
+  const bool enc60 = k0 == 60;                   // positional encoding input: the [hi | lo | 0] 128-column K1 row
   // ---- flat fp32 parameter order = reference state_dict order ----
   m->n_params = 0;
   for (int i = 0; i < LAYERS; ++i) {
@@ -189,7 +192,7 @@ static void build_layout(snb_model* m) {
   add_tensor(m, "sigma_from_xyz.0.bias", 1, 0);
   add_tensor(m, "feats_from_xyz.weight", F, F);
   add_tensor(m, "feats_from_xyz.bias", F, 0);
-  add_tensor(m, "rgb_from_xyzdir.0.weight", FL, F);
+  add_tensor(m, "rgb_from_xyzdir.0.weight", FL, F + (nerf ? m->kdir : 0));
   add_tensor(m, "rgb_from_xyzdir.0.bias", FL, 0);
   add_tensor(m, "rgb_from_xyzdir.2.weight", 3, FL);
   add_tensor(m, "rgb_from_xyzdir.2.bias", 3, 0);
@@ -199,6 +202,7 @@ static void build_layout(snb_model* m) {
     add_tensor(m, "semantic_prediction.2.weight", C, FL);
     add_tensor(m, "semantic_prediction.2.bias", C, 0);
   }
+  if (!nerf) {
   add_tensor(m, "sun_v_net.0.weight", FL, F + 3);
   add_tensor(m, "sun_v_net.0.bias", FL, 0);
   add_tensor(m, "sun_v_net.2.weight", FL, FL);
@@ -215,6 +219,7 @@ static void build_layout(snb_model* m) {
   add_tensor(m, "beta_from_xyz.0.bias", FL, 0);
   add_tensor(m, "beta_from_xyz.2.weight", 1, FL);
   add_tensor(m, "beta_from_xyz.2.bias", 1, 0);
+  }
 
   auto P = [&](const std::string& n) { return m->find(n.c_str()); };
   auto fcw = [&](int i) { return P("fc_net." + std::to_string(2 * i) + ".weight"); };
@@ -253,7 +258,7 @@ static void build_layout(snb_model* m) {
   auto job = [&](long long dst, int ldd, long long src, int lds, int rows, int cols, int tr, int mode) {
     J.push_back({dst, src, ldd, lds, rows, cols, tr, mode});
   };
-  if (sem) {
+  if (enc60) {
     // layer 0, semantic: K-segments [enc cols 0..127 = hi | lo | 0] x [W_hi | W_hi | 0] and [enc cols 0..63 = hi | lo(0:4)] x [W_lo | 0]
     job(m->wl[0], m->w0_ld, fcw(0), k0, F, k0, 0, 0);
     job(m->wl[0] + k0, m->w0_ld, fcw(0), k0, F, k0, 0, 0);
@@ -277,11 +282,13 @@ static void build_layout(snb_model* m) {
   job(m->wf, F, P("feats_from_xyz.weight"), F, F, F, 0, 0);
   job(m->tf, ktf, P("feats_from_xyz.weight"), F, F, F, 1, 0);
   job(m->tf + F + 3, ktf, P("sigma_from_xyz.0.weight"), F, F, 1, 1, 0);  // dPre16 column 3 = sigma
-  // fused head first layers: rows [rgb | beta | (sem) | sun]
+  // fused head first layers: rows [rgb | beta | (sem) | sun]  (NeRF: the rgb block only; the others stay zero)
   struct Blk { int row; const char* w; const char* b; int kin; };
-  std::vector<Blk> blks = {{m->hh_rgb, "rgb_from_xyzdir.0", "rgb_from_xyzdir.0", F},
-                           {m->hh_beta, "beta_from_xyz.0", "beta_from_xyz.0", F + tau},
-                           {m->hh_sun, "sun_v_net.0", "sun_v_net.0", F + 3}};
+  std::vector<Blk> blks = {{m->hh_rgb, "rgb_from_xyzdir.0", "rgb_from_xyzdir.0", F + (nerf ? m->kdir : 0)}};
+  if (!nerf) {
+    blks.push_back({m->hh_beta, "beta_from_xyz.0", "beta_from_xyz.0", F + tau});
+    blks.push_back({m->hh_sun, "sun_v_net.0", "sun_v_net.0", F + 3});
+  }
   if (sem) blks.push_back({m->hh_sem, "semantic_prediction.0", "semantic_prediction.0", F});
   for (auto& b : blks) {
     const long long w = P(std::string(b.w) + ".weight"), bb = P(std::string(b.b) + ".bias");
@@ -289,6 +296,9 @@ static void build_layout(snb_model* m) {
     job(m->wh1 + (long long)b.row * kh1 + F, kh1, bb, 1, FL, 1, 0, 0);  // aux column 0 = 1 -> bias
     job(m->th1 + b.row, hhw, w, b.kin, F, FL, 1, 0);
   }
+  if (nerf) {   // aux columns 1..24 = the encoded view direction (cat(f, Mapping(dir)), nerf.py:197-199)
+    job(m->wh1 + (long long)m->hh_rgb * kh1 + F + 1, kh1, P("rgb_from_xyzdir.0.weight") + F, F + m->kdir, FL, m->kdir, 0, 0);
+  } else {
   job(m->wh1 + (long long)m->hh_sun * kh1 + F + 1, kh1, P("sun_v_net.0.weight") + F, F + 3, FL, 3, 0, 0);
   job(m->wh1 + (long long)m->hh_beta * kh1 + F + 4, kh1, P("beta_from_xyz.0.weight") + F, F + tau, FL, tau, 0, 0);
   job(m->taux + 4 * FL, FL, P("beta_from_xyz.0.weight") + F, F + tau, tau, FL, 1, 0);
@@ -296,27 +306,28 @@ static void build_layout(snb_model* m) {
   job(m->ts2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 1, 0);
   job(m->ws4, FL, P("sun_v_net.4.weight"), FL, FL, FL, 0, 0);
   job(m->ts4, FL, P("sun_v_net.4.weight"), FL, FL, FL, 1, 0);
+  }
   // head output layer: rows [rgb0-2, sigma, sun, beta, sem...], K = [h7 | s3 | hh]
   const int kho = m->kho;
   job(m->who + 3ll * kho, kho, P("sigma_from_xyz.0.weight"), F, 1, F, 0, 0);
-  job(m->who + 4ll * kho + F, kho, P("sun_v_net.6.weight"), FL, 1, FL, 0, 0);
+  if (!nerf) job(m->who + 4ll * kho + F, kho, P("sun_v_net.6.weight"), FL, 1, FL, 0, 0);
   job(m->who + 0ll * kho + F + FL + m->hh_rgb, kho, P("rgb_from_xyzdir.2.weight"), FL, 3, FL, 0, 0);
-  job(m->who + 5ll * kho + F + FL + m->hh_beta, kho, P("beta_from_xyz.2.weight"), FL, 1, FL, 0, 0);
+  if (!nerf) job(m->who + 5ll * kho + F + FL + m->hh_beta, kho, P("beta_from_xyz.2.weight"), FL, 1, FL, 0, 0);
   if (sem) job(m->who + 6ll * kho + F + FL + m->hh_sem, kho, P("semantic_prediction.2.weight"), FL, C, FL, 0, 0);
   // transposed head output for dgrad: rows = [s3 | hh] features, 16 columns
-  job(m->tho + 4, 16, P("sun_v_net.6.weight"), FL, FL, 1, 1, 0);
+  if (!nerf) job(m->tho + 4, 16, P("sun_v_net.6.weight"), FL, FL, 1, 1, 0);
   job(m->tho + (long long)(FL + m->hh_rgb) * 16 + 0, 16, P("rgb_from_xyzdir.2.weight"), FL, FL, 3, 1, 0);
-  job(m->tho + (long long)(FL + m->hh_beta) * 16 + 5, 16, P("beta_from_xyz.2.weight"), FL, FL, 1, 1, 0);
+  if (!nerf) job(m->tho + (long long)(FL + m->hh_beta) * 16 + 5, 16, P("beta_from_xyz.2.weight"), FL, FL, 1, 1, 0);
   if (sem) job(m->tho + (long long)(FL + m->hh_sem) * 16 + 6, 16, P("semantic_prediction.2.weight"), FL, FL, C, 1, 0);
   // fp32 biases
   for (int i = 0; i < LAYERS; ++i) job(m->bl[i], 1, fcb(i), 1, F, 1, 0, 2);
   job(m->bfe, 1, P("feats_from_xyz.bias"), 1, F, 1, 0, 2);
-  job(m->bs2, 1, P("sun_v_net.2.bias"), 1, FL, 1, 0, 2);
-  job(m->bs4, 1, P("sun_v_net.4.bias"), 1, FL, 1, 0, 2);
+  if (!nerf) job(m->bs2, 1, P("sun_v_net.2.bias"), 1, FL, 1, 0, 2);
+  if (!nerf) job(m->bs4, 1, P("sun_v_net.4.bias"), 1, FL, 1, 0, 2);
   job(m->bho + 0, 1, P("rgb_from_xyzdir.2.bias"), 1, 3, 1, 0, 2);
   job(m->bho + 3, 1, P("sigma_from_xyz.0.bias"), 1, 1, 1, 0, 2);
-  job(m->bho + 4, 1, P("sun_v_net.6.bias"), 1, 1, 1, 0, 2);
-  job(m->bho + 5, 1, P("beta_from_xyz.2.bias"), 1, 1, 1, 0, 2);
+  if (!nerf) job(m->bho + 4, 1, P("sun_v_net.6.bias"), 1, 1, 1, 0, 2);
+  if (!nerf) job(m->bho + 5, 1, P("beta_from_xyz.2.bias"), 1, 1, 1, 0, 2);
   if (sem) job(m->bho + 6, 1, P("semantic_prediction.2.bias"), 1, C, 1, 0, 2);
 
   // ---- fp32 packed-gradient scratch + unpack jobs (grads[dst] += scratch[src]) ----
@@ -325,7 +336,8 @@ static void build_layout(snb_model* m) {
   m->gl4e = take(gc, (long long)F * 64);
   m->gf = take(gc, (long long)F * F);
   m->gh1 = take(gc, (long long)hhw * F);
-  m->gh1aux = take(gc, (long long)hhw * 16);
+  const int gald = nerf ? 64 : 16;   // row length of the dY^T x aux block (the wgrad side operand's column count)
+  m->gh1aux = take(gc, (long long)hhw * gald);
   m->gs2 = take(gc, (long long)FL * FL);
   m->gs4 = take(gc, (long long)FL * FL);
   m->ghot = take(gc, (long long)kho * 16);
@@ -354,24 +366,28 @@ static void build_layout(snb_model* m) {
   for (auto& b : blks) {
     const long long w = P(std::string(b.w) + ".weight"), bb = P(std::string(b.b) + ".bias");
     ujob(w, b.kin, m->gh1 + (long long)b.row * F, F, FL, F, 0);
-    ujob(bb, 1, m->gh1aux + (long long)b.row * 16, 16, FL, 1, 0);
+    ujob(bb, 1, m->gh1aux + (long long)b.row * gald, gald, FL, 1, 0);
   }
+  if (nerf) {
+    ujob(P("rgb_from_xyzdir.0.weight") + F, F + m->kdir, m->gh1aux + (long long)m->hh_rgb * gald + 1, gald, FL, m->kdir, 0);
+  } else {
   ujob(P("sun_v_net.0.weight") + F, F + 3, m->gh1aux + (long long)m->hh_sun * 16 + 1, 16, FL, 3, 0);
   ujob(P("beta_from_xyz.0.weight") + F, F + tau, m->gh1aux + (long long)m->hh_beta * 16 + 4, 16, FL, tau, 0);
   ujob(P("sun_v_net.2.weight"), FL, m->gs2, FL, FL, FL, 0);
   ujob(P("sun_v_net.2.bias"), 1, m->gbs2, 1, FL, 1, 0);
   ujob(P("sun_v_net.4.weight"), FL, m->gs4, FL, FL, FL, 0);
   ujob(P("sun_v_net.4.bias"), 1, m->gbs4, 1, FL, 1, 0);
+  }
   // head output layer: scratch is transposed [K features, 16]
   ujob(P("sigma_from_xyz.0.weight"), F, m->ghot + 3, 16, 1, F, 1);
-  ujob(P("sun_v_net.6.weight"), FL, m->ghot + (long long)F * 16 + 4, 16, 1, FL, 1);
+  if (!nerf) ujob(P("sun_v_net.6.weight"), FL, m->ghot + (long long)F * 16 + 4, 16, 1, FL, 1);
   ujob(P("rgb_from_xyzdir.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_rgb) * 16 + 0, 16, 3, FL, 1);
-  ujob(P("beta_from_xyz.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_beta) * 16 + 5, 16, 1, FL, 1);
+  if (!nerf) ujob(P("beta_from_xyz.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_beta) * 16 + 5, 16, 1, FL, 1);
   if (sem) ujob(P("semantic_prediction.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_sem) * 16 + 6, 16, C, FL, 1);
   ujob(P("rgb_from_xyzdir.2.bias"), 1, m->gbho + 0, 1, 3, 1, 0);
   ujob(P("sigma_from_xyz.0.bias"), 1, m->gbho + 3, 1, 1, 1, 0);
-  ujob(P("sun_v_net.6.bias"), 1, m->gbho + 4, 1, 1, 1, 0);
-  ujob(P("beta_from_xyz.2.bias"), 1, m->gbho + 5, 1, 1, 1, 0);
+  if (!nerf) ujob(P("sun_v_net.6.bias"), 1, m->gbho + 4, 1, 1, 1, 0);
+  if (!nerf) ujob(P("beta_from_xyz.2.bias"), 1, m->gbho + 5, 1, 1, 1, 0);
   if (sem) ujob(P("semantic_prediction.2.bias"), 1, m->gbho + 6, 1, C, 1, 0);
 }
 
@@ -450,7 +466,7 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
     w.dys3 = take_b(rowFL);
     w.dys2 = take_b(rowFL);
     const size_t ldt = ((size_t)P + 63) & ~(size_t)63;
-    w.auxT = take_b(16 * ldt * 2);
+    w.auxT = take_b(64 * ldt * 2);
     w.encT = take_b(64 * ldt * 2);
     w.gscratch = take_b((size_t)m->gscratch_elems * 4);
   }
@@ -511,9 +527,10 @@ static GemmArgs& add_rows16(Plan& p, int epi, long long M, const Seg* segs, int 
 struct WgradSide {
   const void* xt;
   long long ldt;
-  int n;
+  int n;        // 16 or 64 MMA columns
   float* out;
   long long ld;
+  int n_real;   // rows XT really has (<= n; the tensor map zero-fills the rest)
 };
 
 static void add_wgrad(Plan& p, int Mf, int Nf, const void* dY, long long ld_dy, const void* X, long long ld_x,
@@ -553,7 +570,8 @@ static void add_wgrad(Plan& p, int Mf, int Nf, const void* dY, long long ld_dy, 
     a.side_n = side->n;
     a.side_out = side->out;
     a.ld_side = side->ld;
-    p.chk(make_tmap_2d(&a.tmB2, side->xt, 2, (uint64_t)P, (uint64_t)side->n, (uint64_t)side->ldt * 2, 64, (uint32_t)(side->n / 2)));
+    p.chk(make_tmap_2d(&a.tmB2, side->xt, 2, (uint64_t)P, (uint64_t)(side->n_real > 0 ? side->n_real : side->n),
+                       (uint64_t)side->ldt * 2, 64, (uint32_t)(side->n / 2)));
   }
   gemm_finalize(a);
 }
@@ -601,6 +619,7 @@ struct ChainPlan {
   ChainArgs a;
   int rc = 0;
   bool per_layer;     // one launch per layer (snb_set_chained_mlp(0)) instead of one per pass
+  bool relu = false;  // vanilla NeRF: EPI_SIN layers apply max(., 0), EPI_MUL layers with a saved activation multiply by [h > 0]
   cudaStream_t st;
   ChainPlan(long long P, bool chained, cudaStream_t stream) : per_layer(!chained), st(stream) {
     memset(&a, 0, sizeof(a));
@@ -637,8 +656,9 @@ struct ChainPlan {
     chk(make_tmap_2d(&mp.tmB, B, 2, (uint64_t)b_cols, (uint64_t)N, (uint64_t)ldb * 2, 64, 128));
     chk(make_tmap_2d(&mp.tmO0, out0, 2, (uint64_t)N, (uint64_t)o_rows, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
     if (epi == EPI_MUL) chk(make_tmap_2d(&mp.tmMul, mul, 2, (uint64_t)N, (uint64_t)a.M, (uint64_t)ldmul * 2, 64, GEMM_BLOCK_M));
-    ly.mul_siren = (epi == EPI_MUL && mask != nullptr) ? 1 : 0;
-    if (epi == EPI_LINEAR) mask = nullptr;
+    ly.mul_siren = (epi == EPI_MUL && mask != nullptr) ? (relu ? 2 : 1) : 0;
+    ly.relu = (relu && epi == EPI_SIN) ? 1 : 0;
+    if (epi == EPI_LINEAR || relu) mask = nullptr;   // ReLU needs no sign mask: its derivative is [h > 0]
     ly.mask = mask;
     ly.mask_ld = mask_ld;
     if (mask) chk(make_tmap_mask(&mp.tmMask, mask, (uint64_t)(N / 32), (uint64_t)a.M, (uint64_t)mask_ld * 4));
@@ -691,19 +711,23 @@ using namespace snb;
 // =====================================================================================================
 extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid) {
   SNB_CHECK_ARG(out != nullptr, SNB_ERR_INVALID, "model_create: null out");
-  SNB_CHECK_ARG(model_kind == SNB_MODEL_SATNERF || model_kind == SNB_MODEL_SEMANTIC, SNB_ERR_INVALID,
-                "model_create: bad kind %d", model_kind);
-  if (model_kind == SNB_MODEL_SATNERF) n_classes = 0;
-  SNB_CHECK_ARG(n_classes >= 0 && n_classes <= 10 && (model_kind == SNB_MODEL_SATNERF || n_classes >= 1),
+  SNB_CHECK_ARG(model_kind == SNB_MODEL_SATNERF || model_kind == SNB_MODEL_SEMANTIC || model_kind == SNB_MODEL_NERF,
+                SNB_ERR_INVALID, "model_create: bad kind %d", model_kind);
+  if (model_kind != SNB_MODEL_SEMANTIC) n_classes = 0;
+  SNB_CHECK_ARG(n_classes >= 0 && n_classes <= 10 && (model_kind != SNB_MODEL_SEMANTIC || n_classes >= 1),
                 SNB_ERR_UNSUPPORTED, "model_create: n_classes %d outside [1,10]", n_classes);
   snb_model* m = new snb_model();
   m->kind = model_kind;
   m->n_classes = n_classes;
   m->sem_sigmoid = semantic_sigmoid;
   m->tau = 4;  // t_embedding_tau (configs/pipelines/*.toml)
-  m->k0 = model_kind == SNB_MODEL_SEMANTIC ? 60 : 3;
-  m->enc_ld = model_kind == SNB_MODEL_SEMANTIC ? 128 : 64;
-  m->w0_ld = model_kind == SNB_MODEL_SEMANTIC ? 192 : 64;
+  const bool enc60 = model_kind != SNB_MODEL_SATNERF;   // positional encoding of xyz (10 frequencies)
+  m->k0 = enc60 ? 60 : 3;
+  m->enc_ld = enc60 ? 128 : 64;
+  m->w0_ld = enc60 ? 192 : 64;
+  m->relu = model_kind == SNB_MODEL_NERF ? 1 : 0;
+  m->aux_ld = model_kind == SNB_MODEL_NERF ? 32 : 16;
+  m->kdir = 24;
   m->n_out = 9 + n_classes;
   // hidden block order of the fused head first layers: [rgb | beta | (sem) | sun]
   m->hh_rgb = 0;
@@ -777,6 +801,9 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
     // activations are read back from L2 and, in inference, live in a per-SM-pair scratch that never reaches HBM.
     const bool chained = use_chain();
     ChainPlan cp(P, chained, (cudaStream_t)stream);
+    cp.relu = m->relu != 0;
+    cp.a.nerf = m->kind == SNB_MODEL_NERF ? 1 : 0;
+    const float w_first = m->relu ? 1.0f : 30.0f;   // Siren(w0 = 30) on the first trunk layer only (satnerf.py:146)
     const long long R = chain_scratch_rows();
     const bool scr = !train && chained;   // inference: layers 0..6, f, s2 in the per-pair scratch
     auto hbuf = [&](int i) { return scr && i < 7 ? (void*)(ws + w.scr_h[i & 1]) : H(i); };
@@ -786,8 +813,8 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
     {
       // semantic: the 128-column row is read twice ([hi|lo|0] then its first 64 columns again, against W_lo)
       CSeg s0[2] = {{enc, m->enc_ld, m->enc_ld, m->enc_ld / 64, P, 0}, {enc, m->enc_ld, 64, 1, P, 0}};
-      cp.add(EPI_SIN, F, s0, m->kind == SNB_MODEL_SEMANTIC ? 2 : 1, pk + m->wl[0], m->w0_ld, m->w0_ld, hbuf(0), F, hrows(0), hscr(0),
-             nullptr, 0, SG(0), F / 32, pb + m->bl[0], 30.0f);
+      cp.add(EPI_SIN, F, s0, m->k0 == 60 ? 2 : 1, pk + m->wl[0], m->w0_ld, m->w0_ld, hbuf(0), F, hrows(0), hscr(0),
+             nullptr, 0, SG(0), F / 32, pb + m->bl[0], w_first);
     }
     for (int i = 1; i < LAYERS; ++i) {
       if (i == 4) {   // skip connection cat(enc, h3) as two K-segments
@@ -822,7 +849,7 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
       cp.add(EPI_LINEAR, F, s, 1, pk + m->wf, F, F, fbuf, F, srows, sflag, nullptr, 0, nullptr, 0, pb + m->bfe, 1.0f);
       // fused head first layers (all blocks, or only the sun block for the solar pass)
       const int r0 = all ? 0 : m->hh_sun, n = all ? hhw : FL;
-      CSeg s1[2] = {{fbuf, F, F, F / 64, srows, sflag}, {aux, 16, 16, 1, P, 0}};
+      CSeg s1[2] = {{fbuf, F, F, F / 64, srows, sflag}, {aux, m->aux_ld, m->aux_ld, 1, P, 0}};
       cp.add(EPI_SIN, n, s1, 2, pk + m->wh1 + (long long)r0 * (F + 64), F + 64, F + 64, ws + w.hh + (size_t)r0 * 2, hhw, P, 0,
              nullptr, 0, train ? reinterpret_cast<uint32_t*>(ws + w.sghh) + r0 / 32 : nullptr, hhw / 32, nullptr, 1.0f);
       if (all) {
@@ -883,6 +910,7 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     // chained (default): one persistent launch; each dY is read back from L2 by the next step of the same SM pair.
     // The SIREN derivative w0 cos(.) is rebuilt in the epilogue from the saved activation and its sign mask.
     ChainPlan cp(P, use_chain(), st);
+    cp.relu = m->relu != 0;
     auto SG = [&](int i) { return reinterpret_cast<uint32_t*>(ws + w.sg[i]); };
     uint32_t* sghh = reinterpret_cast<uint32_t*>(ws + w.sghh);
     CSeg cdpre[1] = {{dpre, 16, 16, 1, P, 0}};
@@ -911,14 +939,14 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
       // dY_{i-1} = (dY_i W_i) * c_{i-1}
       CSeg c[1] = {{DY(i), F, F, F / 64, P, 0}};
       cp.add(EPI_MUL, F, c, 1, pk + m->tl[i], F, F, DY(i - 1), F, P, 0, H(i - 1), F, SG(i - 1), F / 32, nullptr,
-             i - 1 == 0 ? 30.0f : 1.0f);
+             (i - 1 == 0 && !m->relu) ? 30.0f : 1.0f);
     }
     if (int r = cp.run()) return r;
   }
   // ---- wgrad: every weight gradient is dY^T x (layer input), split-K over the samples -----------------------
   const long long ldt = (P + 63) & ~63ll;
   if (!depth)
-    if (int r = transpose_cols(aux, 16, 16, P, ws + w.auxT, ldt, st)) return r;
+    if (int r = transpose_cols(aux, m->aux_ld, m->aux_ld, P, ws + w.auxT, ldt, st)) return r;
   if (int r = transpose_cols(enc, m->enc_ld, 64, P, ws + w.encT, ldt, st)) return r;
   add_wgrad(p, F, 16, H(7), F, dpre, 16, P, gs + m->ghot, 16, sms);
   if (!depth) add_wgrad(p, FL, 16, ws + w.s3, FL, dpre, 16, P, gs + m->ghot + (long long)F * 16, 16, sms);
@@ -928,7 +956,8 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     add_wgrad(p, FL, FL, ws + w.dys2, FL, ws + w.hh + (size_t)m->hh_sun * 2, hhw, P, gs + m->gs2, FL, sms, gs + m->gbs2);
     // fused head first layers: weight / bias / per-ray-column gradients
     // ... the bias / per-ray-column gradients dY^T x aux ride the same launch as a 16-column side operand
-    const WgradSide s_aux = {ws + w.auxT, ldt, 16, gs + m->gh1aux + (long long)r0 * 16, 16};
+    const int gald = m->aux_ld > 16 ? 64 : 16;
+    const WgradSide s_aux = {ws + w.auxT, ldt, gald, gs + m->gh1aux + (long long)r0 * gald, gald, m->aux_ld};
     add_wgrad(p, nh, F, dyhh_r0, hhw, ws + w.f, F, P, gs + m->gh1 + (long long)r0 * F, F, sms, nullptr, &s_aux);
     if (all && g_aux) {
       // d aux = dY_beta * W_beta0[:, 512:]  -> embedding gradient (summed per ray by the caller-side kernel)
@@ -944,7 +973,7 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
       add_wgrad(p, F, 64, DY(0), F, enc, m->enc_ld, P, gs + m->gl[0], 64, sms, gs + m->gbl[0]);
     } else {
       // skip layer: its encoding block dY4^T x enc[:, :64] is a 64-column side operand of the same launch
-      const WgradSide s_enc = {ws + w.encT, ldt, 64, gs + m->gl4e, 64};
+      const WgradSide s_enc = {ws + w.encT, ldt, 64, gs + m->gl4e, 64, 64};
       add_wgrad(p, F, F, DY(i), F, H(i - 1), F, P, gs + m->gl[i], F, sms, gs + m->gbl[i], i == 4 ? &s_enc : nullptr);
     }
   }
@@ -978,12 +1007,15 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
   SNB_CHECK_ARG(mask_supported(head_mask), SNB_ERR_UNSUPPORTED,
                 "mlp_forward_fp32: head_mask %d (supported: ALL=63, SOLAR=5, DEPTH=1)", head_mask);
   const bool all = head_mask == SNB_HEADS_ALL, depth = head_mask == SNB_HEADS_DEPTH;
+  const bool nerf = m->kind == SNB_MODEL_NERF;   // sun_d carries the ENCODED view direction (R, 24) there; t / sky unused
   SNB_CHECK_ARG(depth || sun_d != nullptr, SNB_ERR_INVALID, "mlp_forward_fp32: sun_d required");
-  SNB_CHECK_ARG(!all || (t != nullptr && sky != nullptr), SNB_ERR_INVALID, "mlp_forward_fp32: t and sky required for all heads");
+  SNB_CHECK_ARG(!all || nerf || (t != nullptr && sky != nullptr), SNB_ERR_INVALID,
+                "mlp_forward_fp32: t and sky required for all heads");
   SNB_CHECK_ARG(workspace_bytes >= snb_mlp_fp32_workspace_bytes(m, n_points), SNB_ERR_WORKSPACE,
                 "mlp_forward_fp32: workspace %zu too small", workspace_bytes);
   cudaStream_t st = (cudaStream_t)stream;
   const bool sem = m->kind == SNB_MODEL_SEMANTIC;
+  const int hid = nerf ? F32_RELU : F32_SIN;
   const int k0 = m->k0, tau = m->tau, n_out = m->n_out, C = m->n_classes;
   const bool by_ray = rows_per_ray > 1;   // per-ray sun_d / t / sky rows, broadcast over the ray's samples
   const int div = by_ray ? rows_per_ray : 1;
@@ -1000,7 +1032,7 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
     float* g1 = f + (long long)M * F;
     float* g2 = g1 + (long long)M * FL;
     float* o = out + r0 * n_out;
-    if (int r = f32_posenc_launch(xyz + r0 * 3, M, sem ? 10 : 0, enc, F32_ENC_LD, st)) return r;
+    if (int r = f32_posenc_launch(xyz + r0 * 3, M, k0 == 60 ? 10 : 0, enc, F32_ENC_LD, st)) return r;
     auto gemm = [&](F32Seg s0, const F32Seg* s1, const float* w, int ldw, const float* bias, int N, int act, float w0, float* c,
                     long long ldc) {
       F32Gemm g;
@@ -1026,11 +1058,11 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
       const std::string nm = "fc_net." + std::to_string(2 * i);
       int rc;
       if (i == 0) {
-        rc = gemm(senc, nullptr, W(nm.c_str()), k0, B(nm.c_str()), F, F32_SIN, 30.0f, cur, F);
+        rc = gemm(senc, nullptr, W(nm.c_str()), k0, B(nm.c_str()), F, hid, nerf ? 1.0f : 30.0f, cur, F);
       } else {
         const F32Seg sh = rows(cur, F, F);
-        if (i == 4) rc = gemm(senc, &sh, W(nm.c_str()), k0 + F, B(nm.c_str()), F, F32_SIN, 1.0f, nxt, F);
-        else rc = gemm(sh, nullptr, W(nm.c_str()), F, B(nm.c_str()), F, F32_SIN, 1.0f, nxt, F);
+        if (i == 4) rc = gemm(senc, &sh, W(nm.c_str()), k0 + F, B(nm.c_str()), F, hid, 1.0f, nxt, F);
+        else rc = gemm(sh, nullptr, W(nm.c_str()), F, B(nm.c_str()), F, hid, 1.0f, nxt, F);
         float* tmp = cur; cur = nxt; nxt = tmp;
       }
       if (rc) return rc;
@@ -1040,6 +1072,12 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
     if (depth) continue;
     if (int r = gemm(sh7, nullptr, W("feats_from_xyz"), F, B("feats_from_xyz"), F, F32_NONE, 1.0f, f, F)) return r;
     const F32Seg sf = rows(f, F, F);
+    if (nerf) {   // rgb = sigmoid(W2 relu(W0 cat(f, Mapping(dir)) + b0) + b2) * 1.002 - 0.001  (nerf.py:197-203); sun column = 1
+      const F32Seg sd = per_ray(sun_d, m->kdir);
+      if (int r = gemm(sf, &sd, W("rgb_from_xyzdir.0"), F + m->kdir, B("rgb_from_xyzdir.0"), FL, F32_RELU, 1.0f, g1, FL)) return r;
+      if (int r = gemm(rows(g1, FL, FL), nullptr, W("rgb_from_xyzdir.2"), FL, B("rgb_from_xyzdir.2"), 3, F32_RGB, 1.0f, o, n_out)) return r;
+      continue;
+    }
     {   // sun visibility: cat(f, sun_d) -> 3 x sin -> sigmoid  (satnerf.py:236-243)
       const F32Seg ss = per_ray(sun_d, 3);
       if (int r = gemm(sf, &ss, W("sun_v_net.0"), F + 3, B("sun_v_net.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;

@@ -157,3 +157,44 @@ extern "C" int snb_adam_step(float* params, const float* grads, float* exp_avg, 
                                                              bc1, sqrtf(bc2), grad_scale);
   return launch_status("adam_kernel");
 }
+
+
+// ---- vanilla NeRF: the per-sample aux row [1, Mapping(4, 3)(dir), 0...] (32 bf16) ---------------------------------------
+namespace snb {
+__global__ void __launch_bounds__(256) nerf_aux_kernel(const float* __restrict__ dirs, int stride, long long n_rays, int S,
+                                                       __nv_bfloat16* __restrict__ aux) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_rays * S) return;
+  const float* d = dirs + (p / S) * stride;
+  float v[32];
+  v[0] = 1.0f;
+  float f = 1.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k, f *= 2.0f) {   // commons.py:68-74: per frequency sin(3) then cos(3)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float x = f * d[c];
+      v[1 + k * 6 + c] = sinf(x);
+      v[1 + k * 6 + 3 + c] = cosf(x);
+    }
+  }
+#pragma unroll
+  for (int j = 25; j < 32; ++j) v[j] = 0.f;
+  uint4* dst = reinterpret_cast<uint4*>(aux + p * 32);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    dst[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                        pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
+}
+}  // namespace snb
+
+extern "C" int snb_nerf_aux(const float* dirs, int stride, int n_rays, int n_samples, void* aux32, void* stream) {
+  using namespace snb;
+  SNB_CHECK_ARG(dirs && aux32 && stride >= 3 && n_rays >= 0 && n_samples >= 1, SNB_ERR_INVALID, "nerf_aux: bad argument");
+  SNB_CHECK_ARG(((uintptr_t)aux32 & 15) == 0, SNB_ERR_INVALID, "nerf_aux: aux must be 16-byte aligned");
+  const long long P = (long long)n_rays * n_samples;
+  if (P == 0) return 0;
+  nerf_aux_kernel<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dirs, stride, n_rays, n_samples,
+                                                                                 (__nv_bfloat16*)aux32);
+  return launch_status("nerf_aux_kernel");
+}

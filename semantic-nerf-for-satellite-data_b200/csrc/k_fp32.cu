@@ -18,6 +18,7 @@ __device__ __forceinline__ float f32_act(float y, int act, float w0) {
     case F32_SIGMOID: return 1.0f / (1.0f + expf(-y));
     case F32_SOFTPLUS: return y > 20.0f ? y : log1pf(expf(y));
     case F32_RGB: return (1.0f / (1.0f + expf(-y))) * 1.002f - 0.001f;
+    case F32_RELU: return fmaxf(y, 0.f);
     default: return y;
   }
 }

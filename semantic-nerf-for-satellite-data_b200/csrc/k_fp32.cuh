@@ -12,7 +12,8 @@ enum F32Act {
   F32_SIN = 1,       // sin(w0 * y)                       (Siren, baseline/models/commons.py:27-38)
   F32_SIGMOID = 2,   // sigmoid(y)
   F32_SOFTPLUS = 3,  // softplus(y), beta = 1, threshold 20
-  F32_RGB = 4        // sigmoid(y) * 1.002 - 0.001        (rs_semantic.py:282-284)
+  F32_RGB = 4,       // sigmoid(y) * 1.002 - 0.001        (rs_semantic.py:282-284)
+  F32_RELU = 5       // max(y, 0)                         (vanilla NeRF, nerf.py:110)
 };
 
 struct F32Seg {      // one block of input columns: the reference's torch.cat([...], -1) operands, in order

@@ -17,7 +17,7 @@ from typing import Dict, List, Tuple
 import torch
 
 from . import _lib
-from ._lib import HEADS_ALL, MODEL_SATNERF, MODEL_SEMANTIC, check, ptr, stream
+from ._lib import HEADS_ALL, MODEL_NERF, MODEL_SATNERF, MODEL_SEMANTIC, check, ptr, stream
 
 
 class SnbMLP(torch.nn.Module):
@@ -37,7 +37,7 @@ class SnbMLP(torch.nn.Module):
         self.n_out_kernel = 9 + n_classes            # columns of the packed tensor the kernels write
         self.hidden_prefixes: Tuple[str, ...] = ()   # tensors of the flat buffer a model variant does not own (S-NeRF)
         self.t_embedding_dims = tau
-        self.enc_ld = 128 if kind == MODEL_SEMANTIC else 64
+        self.enc_ld = 64 if kind == MODEL_SATNERF else 128
         n = lib.snb_model_param_count(h)
         self.table: List[Tuple[str, int, Tuple[int, ...]]] = []
         for i in range(lib.snb_model_num_tensors(h)):
@@ -63,7 +63,7 @@ class SnbMLP(torch.nn.Module):
                     t.uniform_(-b, b)
                     continue
                 fan_in = t.shape[1]
-                if name.startswith("fc_net.") or name.startswith("sun_v_net."):
+                if (name.startswith("fc_net.") or name.startswith("sun_v_net.")) and self.kind != MODEL_NERF:
                     first = name in ("fc_net.0.weight", "sun_v_net.0.weight")
                     b = 1.0 / fan_in if first else math.sqrt(6.0 / fan_in)
                 else:
@@ -232,3 +232,42 @@ class ShadowNeRFB200(SnbMLP):
         t = torch.zeros(input_xyz.shape[0], self.t_embedding_dims, dtype=torch.float32, device=input_xyz.device)
         out = super().forward(input_xyz, input_sun_dir=input_sun_dir, input_t=t)
         return out[:, 3:4] if sigma_only else out[:, :8]
+
+
+class NeRFB200(SnbMLP):
+    """Drop-in for baseline.models.nerf.NeRF as the NeRF pipeline builds it (baseline/pipelines/nerf.py:26-34: constructor
+    defaults mapping=True, siren=False -> positional encoding of xyz (10 frequencies) and of the view direction (4), ReLU
+    activations, nn.Linear default initialisation; nerf.py:98-162).  Outputs [rgb | sigma] (4 columns).
+
+    Runs on the SatNeRF head layout with the sun / uncertainty blocks absent (zero weights in the packed image, no
+    parameters) and the sun column pinned to 1, so K3's lighting model reduces to NeRF's plain emission-absorption sum
+    (nerf.py:73-86).  NB: K3 clamps the composited colour to [0, 1] (as SatNeRF / S-NeRF do); NeRF's inference does not -
+    the two differ only when a composited channel leaves [0, 1], by at most 1e-3 (the sigmoid padding, nerf.py:203)."""
+
+    def __init__(self, layers=8, feat=512, mapping=True, mapping_sizes=(10, 4), skips=(4,), siren=False):
+        if layers != 8 or feat != 512 or list(skips) != [4] or not mapping or siren or list(mapping_sizes) != [10, 4]:
+            raise _lib.SnbError("libsnb implements the NeRF configuration the pipeline builds: 8x512 ReLU, skip [4], "
+                                "positional encoding 10 / 4 (baseline/pipelines/nerf.py:26-34)")
+        super().__init__(MODEL_NERF, 0, True, 4, None)
+        self.variant = "nerf"
+        self.number_of_outputs = 4                   # nerf.py:116
+        self.layers, self.skips = layers, list(skips)
+
+    def sky_params(self):
+        raise _lib.SnbError("NeRF has no sky_color head")
+
+    def forward(self, input_xyz, input_dir=None, sigma_only=False, epoch=None):
+        """(B,3),(B,3) -> (B,4) [rgb | sigma]  (nerf.py:164-212); sigma_only -> (B,1)."""
+        from .autograd import mlp_fp32, mlp_points
+        if getattr(self, "precision", "bf16") == "fp32":   # verification mode: fp32 end to end, inference only
+            out = mlp_fp32(self, input_xyz, posenc_dirs(input_dir), None, None, 0, HEADS_ALL)
+        else:
+            t = torch.zeros(input_xyz.shape[0], self.t_embedding_dims, dtype=torch.float32, device=input_xyz.device)
+            out = mlp_points(self, input_xyz, input_dir, t)
+        return out[:, 3:4] if sigma_only else out[:, :4]
+
+
+def posenc_dirs(dirs: torch.Tensor, n_freq: int = 4) -> torch.Tensor:
+    """Mapping(4, 3)(dir) in fp32 for the fp32 verification mode: [sin(2^k d), cos(2^k d)]_k (commons.py:68-74)."""
+    d = dirs.float()
+    return torch.cat([f(float(2 ** k) * d) for k in range(n_freq) for f in (torch.sin, torch.cos)], -1).contiguous()

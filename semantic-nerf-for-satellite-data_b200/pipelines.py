@@ -15,8 +15,8 @@ from __future__ import annotations
 
 import torch
 
-from .model import RSSemanticNeRFB200, SatNeRFB200, ShadowNeRFB200
-from .renderer import RSSemanticB200Rendering, SatNeRFB200Rendering, SNeRFB200Rendering
+from .model import NeRFB200, RSSemanticNeRFB200, SatNeRFB200, ShadowNeRFB200
+from .renderer import NeRFB200Rendering, RSSemanticB200Rendering, SatNeRFB200Rendering, SNeRFB200Rendering
 
 _CACHE = {}
 
@@ -27,6 +27,16 @@ def get_pipeline_classes():
     from baseline.pipelines.satnerf import SatNeRFPipeline          # reference checkout on sys.path
     from baseline.pipelines.snerf import SNerfPipeline
     from semantic.pipelines.rs_semantic import RSSemanticPipeline
+
+    from baseline.pipelines.nerf import NerfPipeline
+
+    class NeRFB200Pipeline(NerfPipeline):
+        def _init_models(self) -> dict:   # baseline/pipelines/nerf.py:26-34
+            p = self.cfgs.pipeline
+            return {"coarse": NeRFB200(layers=p.fc_layers, feat=p.fc_units, skips=p.fc_skips)}
+
+        def _init_renderer(self):         # baseline/pipelines/nerf.py:36-37
+            return NeRFB200Rendering(self.cfgs)
 
     class SNeRFB200Pipeline(SNerfPipeline):
         def _init_models(self) -> dict:   # baseline/pipelines/snerf.py:24-32
@@ -56,11 +66,11 @@ def get_pipeline_classes():
             return RSSemanticB200Rendering(self.cfgs)
 
     _CACHE.update(SatNeRFB200Pipeline=SatNeRFB200Pipeline, RSSemanticB200Pipeline=RSSemanticB200Pipeline,
-                  SNeRFB200Pipeline=SNeRFB200Pipeline)
+                  SNeRFB200Pipeline=SNeRFB200Pipeline, NeRFB200Pipeline=NeRFB200Pipeline)
     return _CACHE
 
 
 def __getattr__(name):  # `semnerf_b200.pipelines.RSSemanticB200Pipeline` resolves through importlib
-    if name in ("SatNeRFB200Pipeline", "RSSemanticB200Pipeline", "SNeRFB200Pipeline"):
+    if name in ("SatNeRFB200Pipeline", "RSSemanticB200Pipeline", "SNeRFB200Pipeline", "NeRFB200Pipeline"):
         return get_pipeline_classes()[name]
     raise AttributeError(name)

@@ -46,9 +46,10 @@ class B200Renderer:
         if z_vals is None:
             z_vals = opts.get("z_vals")
         depth_only = opts.get("heads", "all") == "depth"
+        nerf = getattr(model, "variant", None) == "nerf"   # NeRFRendering (baseline/components/rendering.py:103-118)
         # "solar_pass": False skips the solar-correction pass (its outputs feed only the training loss; an evaluation render
         # that wants rgb / depth / labels need not pay for it - the reference always runs it when sc_lambda > 0)
-        sc = cfgs.pipeline.sc_lambda > 0 and not depth_only and bool(opts.get("solar_pass", True))
+        sc = cfgs.pipeline.sc_lambda > 0 and not depth_only and bool(opts.get("solar_pass", True)) and not nerf
         if n == 0:   # an empty ray batch renders to empty tensors, as the reference's eager code does
             return self._empty_result(model, rays, S, sc)
         self._calls += 1
@@ -64,7 +65,13 @@ class B200Renderer:
             o, d, sun_d = rays[:, 0:3].float(), rays[:, 3:6].float(), extras[:, 0:3].float()
             t_ray = emb[extras[:, 3].long()].float() if emb is not None else torch.zeros(n, 4, device=rays.device)
             xyz_main = (o.unsqueeze(1) + d.unsqueeze(1) * z.unsqueeze(2)).reshape(-1, 3)
-            out = mlp_fp32(model, xyz_main, sun_d, t_ray, sky, S, mask).view(n, S, -1)
+            if nerf:   # the per-ray input is the ENCODED view direction; the sun column is pinned to 1 (no lighting model)
+                from .model import posenc_dirs
+                out = mlp_fp32(model, xyz_main, posenc_dirs(d), None, None, S, mask)
+                out[:, 4] = 1.0
+                out = out.view(n, S, -1)
+            else:
+                out = mlp_fp32(model, xyz_main, sun_d, t_ray, sky, S, mask).view(n, S, -1)
         else:
             out = mlp_rays(model, emb, enc, aux, sky, extras, n, S, mask).view(n, S, -1)
         rgb, depth, weights, transp, sem, label = Composite.apply(out, z, C)
@@ -78,6 +85,8 @@ class B200Renderer:
             result["semantic_label"] = label
         if getattr(model, "variant", None) == "snerf":   # snerf.py:86-96 returns neither beta nor sigmas
             del result["beta"], result["sigmas"]
+        if nerf:                                         # nerf.py:80-86: rgb, depth, weights, transparency only
+            result = {k: result[k] for k in ("rgb", "depth", "weights", "transparency")}
         if sc:
             # solar correction: second pass on o + sun_d*z, keeping weights / transparency / sun
             if fp32:
@@ -142,6 +151,8 @@ class B200Renderer:
             res["semantic_label"] = torch.empty(0, dtype=torch.int64, device=rays.device)
         if getattr(model, "variant", None) == "snerf":
             del res["beta"], res["sigmas"]
+        if getattr(model, "variant", None) == "nerf":
+            res = {k: res[k] for k in ("rgb", "depth", "weights", "transparency")}
         if sc:
             res.update(weights_sc=f(0, S), transparency_sc=f(0, S), sun_sc=f(0, S, 1))
         res["_z_vals"] = f(0, S)
@@ -151,6 +162,10 @@ class B200Renderer:
 # the reference's two renderer class names, for configs / code that instantiate them by name
 class SatNeRFB200Rendering(B200Renderer):
     pass
+
+
+class NeRFB200Rendering(B200Renderer):
+    """≙ baseline.components.rendering.NeRFRendering (rendering.py:103-118): models = {"coarse": NeRFB200}."""
 
 
 class SNeRFB200Rendering(B200Renderer):

@@ -19,7 +19,7 @@ import torch
 from . import _lib, dist as snb_dist
 from ._lib import check, ptr, stream
 from .losses import DepthLoss, SatNerfLoss, SemanticCarRegLoss, SemanticLoss, SNerfLoss
-from .model import RSSemanticNeRFB200, SatNeRFB200, ShadowNeRFB200
+from .model import NeRFB200, RSSemanticNeRFB200, SatNeRFB200, ShadowNeRFB200
 from .renderer import B200Renderer
 
 
@@ -45,13 +45,15 @@ class Trainer:
         torch.manual_seed(seed)  # identical initial replicas on every rank
         if kind == "semantic":
             model = RSSemanticNeRFB200(cfgs, types.SimpleNamespace(semantic_n_classes=n_classes))
+        elif kind == "nerf":    # baseline/pipelines/nerf.py:23-40: NerfLoss (MSE), NeRFTrainingStep, no embedding, no solar pass
+            model = NeRFB200(layers=p.fc_layers, feat=p.fc_units, skips=p.fc_skips)
         elif kind == "snerf":   # baseline/pipelines/snerf.py:21-38: SNerfLoss, NeRFTrainingStep, no embedding, no depth batch
             model = ShadowNeRFB200(layers=p.fc_layers, feat=p.fc_units, skips=p.fc_skips)
         else:
             model = SatNeRFB200(cfgs, layers=p.fc_layers, feat=p.fc_units, skips=p.fc_skips,
                                 t_embedding_dims=p.t_embedding_tau)
         self.models = {"coarse": model.to(self.device)}
-        if kind != "snerf":
+        if kind not in ("snerf", "nerf"):
             self.models["t"] = torch.nn.Embedding(p.t_embedding_vocab, p.t_embedding_tau).to(self.device)
         self.renderer = B200Renderer(cfgs)
         self.loss = SatNerfLoss(lambda_sc=p.sc_lambda)
@@ -82,7 +84,7 @@ class Trainer:
         if self.fused_loss:
             return self._fused_step(batch, epoch, depth_batch, opts)
         results = self.renderer.render_rays(self.models, batch["rays"], batch["extras"], epoch=epoch, render_options=opts)
-        if epoch < p.first_beta_epoch or self.kind == "snerf":
+        if epoch < p.first_beta_epoch or self.kind in ("snerf", "nerf"):
             loss, loss_dict = self.loss_without_beta(results, batch["rgbs"])
         else:
             loss, loss_dict = self.loss(results, batch["rgbs"])
@@ -117,7 +119,7 @@ class Trainer:
         car = sem and self.car_reg_loss is not None and epoch >= p.car_reg_loss_start
         loss, terms = self.renderer.render_loss(
             self.models, batch["rays"], batch["extras"], batch["rgbs"], batch["semantic"] if sem else None,
-            color="snerf" if (epoch < p.first_beta_epoch or self.kind == "snerf") else "satnerf",
+            color="snerf" if (epoch < p.first_beta_epoch or self.kind in ("snerf", "nerf")) else "satnerf",
             lambda_s=p.lambda_s if sem else 0.0, ignore_index=self.car_index if (sem and p.ignore_car_index) else -100,
             lambda_c=p.lambda_c if car else 0.0, car_label=self.car_index, render_options=opts)
         if depth_batch is not None:

@@ -36,6 +36,8 @@ GOLDEN_CASES = [
     ("sem_c6_s64_trained", "semantic", 6, 512, 24, 64, 0.05, 7),
     ("snerf_s64", "snerf", 0, 512, 24, 64, 0.05, 8),
     ("snerf_s8_nosc", "snerf", 0, 512, 16, 8, 0.0, 9),
+    ("nerf_s64", "nerf", 0, 512, 24, 64, 0.0, 10),
+    ("nerf_s8", "nerf", 0, 512, 16, 8, 0.0, 11),
 ]
 
 

@@ -114,6 +114,9 @@ def _model(kind, C, seed=3, S=64, sc=0.05, trained_like=False):
     if kind == "snerf":
         from semnerf_b200.model import ShadowNeRFB200
         model = ShadowNeRFB200().to(DEV)
+    elif kind == "nerf":
+        from semnerf_b200.model import NeRFB200
+        model = NeRFB200().to(DEV)
     else:
         model = (RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": C})()) if kind == "semantic"
                  else SatNeRFB200(cfgs)).to(DEV)

@@ -61,7 +61,7 @@ def test_render_rays_against_reference_golden(case):
     _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"))
     renderer = B200Renderer(cfgs)
     with torch.no_grad():
-        models = {"coarse": model} if kind == "snerf" else {"coarse": model, "t": t}
+        models = {"coarse": model} if kind in ("snerf", "nerf") else {"coarse": model, "t": t}
         res = renderer.render_rays(models, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV)})
         assert set(gold) - {"loss_satnerf", "model_forward", "grad_norms"} <= set(res)
         if kind == "snerf":   # snerf.py:86-96: no beta / sigmas entries
@@ -221,7 +221,7 @@ def test_fp32_mode_render_rays_against_reference_golden(case):
     _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"))
     renderer = B200Renderer(cfgs)
     with torch.no_grad():
-        models = {"coarse": model} if kind == "snerf" else {"coarse": model, "t": t}
+        models = {"coarse": model} if kind in ("snerf", "nerf") else {"coarse": model, "t": t}
         res = renderer.render_rays(models, rays.to(DEV), extras.to(DEV),
                                    render_options={"u": u.to(DEV), "precision": "fp32"})
     worst = {}
@@ -425,3 +425,63 @@ def test_bf16_mode_statistical_parity_on_a_trained_model():
     assert p_ref > 15.0 and acc > 0.5            # the model has actually learnt the scene
     assert abs(p_ours - p_ref) <= 0.05
     assert agree >= 0.999
+
+
+# ---------------------------------------------------------------------------------------------------------
+# vanilla NeRF (baseline/models/nerf.py): ReLU trunk, encoded view direction, [rgb | sigma]
+# ---------------------------------------------------------------------------------------------------------
+def test_nerf_model_and_render_gradients_match_oracle():
+    from semnerf_b200.renderer import NeRFB200Rendering
+    _lib_or_fail()
+    S, n = 64, 192
+    spec, params, emb, cfgs, model, _ = _model("nerf", 0, seed=4, S=S, sc=0.0)
+    assert list(model.state_dict().keys()) == list(O.param_shapes(spec).keys()) and model.number_of_outputs == 4
+    g = torch.Generator().manual_seed(0)
+    P = 700
+    xyz = torch.rand(P, 3, generator=g) * 2 - 1
+    dirs = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=1)
+    ref = O.mlp_forward({k: v.double() for k, v in params.items()}, spec, xyz.double(), dirs.double(), None)
+    with torch.no_grad():
+        out = model(xyz.to(DEV), input_dir=dirs.to(DEV))
+        sig = model(xyz.to(DEV), input_dir=dirs.to(DEV), sigma_only=True)
+        model.precision = "fp32"
+        out32 = model(xyz.to(DEV), input_dir=dirs.to(DEV))
+        model.precision = "bf16"
+    assert out.shape == (P, 4) and sig.shape == (P, 1) and torch.equal(sig[:, 0], out[:, 3])
+    d = (out.cpu().double() - ref).abs()
+    assert d[:, :3].max() <= 2e-3 and d[:, 3].max() <= 1e-2, (float(d[:, :3].max()), float(d[:, 3].max()))
+    assert (out32.cpu().double() - ref).abs().max() <= 2e-5
+    rays, extras = O.synthetic_rays(n, seed=6)
+    u = torch.rand(n, S, generator=torch.Generator().manual_seed(2))
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(3))
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    r_ref = O.render_rays(p, None, spec, rays, extras, S, u=u, sc_lambda=0.0)
+    O.nerf_loss(r_ref, gt).backward()
+    res = NeRFB200Rendering(cfgs).render_rays({"coarse": model}, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV)})
+    assert set(k for k in res if not k.startswith("_")) == {"rgb_coarse", "depth_coarse", "weights_coarse", "transparency_coarse"}
+    for k in ("rgb_coarse", "depth_coarse"):
+        assert (res[k].detach().cpu() - r_ref[k].detach()).abs().max() <= 1e-3, k
+    O.nerf_loss(res, gt.to(DEV)).backward()
+    grads = model.named_grads()
+    assert set(grads) == set(p)
+    # the contract's bar is on the whole gradient (measured 0.99996).  Per tensor a ReLU net at nn.Linear's default
+    # initialisation is noisier in bf16 than the SIREN models (0.999 each): its gradients are ~1e-8 sums of cancelling terms,
+    # and the rounding of dY accumulates down the trunk (layer 7: 0.9999 ... layer 0: 0.995; sigma row: 0.993)
+    assert _cos(model.flat.grad.cpu(), torch.cat([p[k].grad.flatten() for k in p])) >= 0.9995
+    for k in p:
+        assert _cos(grads[k].cpu(), p[k].grad) >= 0.99, k
+
+
+def test_nerf_training_step_runs_and_learns():
+    from semnerf_b200 import synth
+    from semnerf_b200.trainer import Trainer, default_cfgs
+    _lib_or_fail()
+    cfgs = default_cfgs("nerf", n_samples=64, sc_lambda=0.0)
+    rays, extras = synth.make_rays(1024, seed=0)
+    rgbs, _, _ = synth.make_targets(rays, 0, seed=0)
+    batch = {"rays": rays.to(DEV), "extras": extras.to(DEV), "rgbs": rgbs.to(DEV)}
+    for fused in (True, False):
+        tr = Trainer(cfgs, "nerf", 0, device=DEV, seed=0, fused_loss=fused)
+        assert "t" not in tr.models
+        losses = [tr.training_step(batch, epoch=3).item() for _ in range(15)]
+        assert all(l == l for l in losses) and losses[-1] < losses[0], losses

@@ -142,3 +142,20 @@ def test_render_loss_signature_and_term_order():
                  "depth", "depth_weights", "lambda_ds", "render_options"):
         assert name in sig.parameters, name
     assert LOSS_TERMS == ("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3", "ds")
+
+
+def test_nerf_state_dict_is_the_reference_nerf():
+    """NeRFB200 exposes exactly the tensors of the reference's NeRF as its pipeline builds it (nerf.py:98-162: mapping on,
+    ReLU): rgb_from_xyzdir.0 takes the 512 features + the 24 encoded view-direction values; no sun / sky / beta heads."""
+    from semnerf_b200.model import NeRFB200, posenc_dirs
+    spec = O.ModelSpec(kind="nerf", n_classes=0)
+    m = NeRFB200(layers=8, feat=512, skips=[4])
+    want = O.param_shapes(spec)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(want.keys()) and all(tuple(sd[k].shape) == tuple(want[k]) for k in want)
+    assert tuple(sd["rgb_from_xyzdir.0.weight"].shape) == (256, 536) and tuple(sd["fc_net.8.weight"].shape) == (512, 572)
+    assert m.number_of_outputs == 4 and m.n_out_kernel == 9 and m.enc_ld == 128
+    d = torch.nn.functional.normalize(torch.randn(5, 3), dim=1)
+    assert torch.allclose(posenc_dirs(d), O.posenc(d, 4))            # the fp32-mode direction encoding = Mapping(4, 3)
+    with pytest.raises(_lib.SnbError):
+        NeRFB200(siren=True)
