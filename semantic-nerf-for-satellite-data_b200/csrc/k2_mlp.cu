@@ -203,22 +203,22 @@ static void build_layout(snb_model* m) {
     add_tensor(m, "semantic_prediction.2.bias", C, 0);
   }
   if (!nerf) {
-  add_tensor(m, "sun_v_net.0.weight", FL, F + 3);
-  add_tensor(m, "sun_v_net.0.bias", FL, 0);
-  add_tensor(m, "sun_v_net.2.weight", FL, FL);
-  add_tensor(m, "sun_v_net.2.bias", FL, 0);
-  add_tensor(m, "sun_v_net.4.weight", FL, FL);
-  add_tensor(m, "sun_v_net.4.bias", FL, 0);
-  add_tensor(m, "sun_v_net.6.weight", 1, FL);
-  add_tensor(m, "sun_v_net.6.bias", 1, 0);
-  add_tensor(m, "sky_color.0.weight", FL, 3);
-  add_tensor(m, "sky_color.0.bias", FL, 0);
-  add_tensor(m, "sky_color.2.weight", 3, FL);
-  add_tensor(m, "sky_color.2.bias", 3, 0);
-  add_tensor(m, "beta_from_xyz.0.weight", FL, F + tau);
-  add_tensor(m, "beta_from_xyz.0.bias", FL, 0);
-  add_tensor(m, "beta_from_xyz.2.weight", 1, FL);
-  add_tensor(m, "beta_from_xyz.2.bias", 1, 0);
+    add_tensor(m, "sun_v_net.0.weight", FL, F + 3);
+    add_tensor(m, "sun_v_net.0.bias", FL, 0);
+    add_tensor(m, "sun_v_net.2.weight", FL, FL);
+    add_tensor(m, "sun_v_net.2.bias", FL, 0);
+    add_tensor(m, "sun_v_net.4.weight", FL, FL);
+    add_tensor(m, "sun_v_net.4.bias", FL, 0);
+    add_tensor(m, "sun_v_net.6.weight", 1, FL);
+    add_tensor(m, "sun_v_net.6.bias", 1, 0);
+    add_tensor(m, "sky_color.0.weight", FL, 3);
+    add_tensor(m, "sky_color.0.bias", FL, 0);
+    add_tensor(m, "sky_color.2.weight", 3, FL);
+    add_tensor(m, "sky_color.2.bias", 3, 0);
+    add_tensor(m, "beta_from_xyz.0.weight", FL, F + tau);
+    add_tensor(m, "beta_from_xyz.0.bias", FL, 0);
+    add_tensor(m, "beta_from_xyz.2.weight", 1, FL);
+    add_tensor(m, "beta_from_xyz.2.bias", 1, 0);
   }
 
   auto P = [&](const std::string& n) { return m->find(n.c_str()); };
@@ -299,13 +299,13 @@ static void build_layout(snb_model* m) {
   if (nerf) {   // aux columns 1..24 = the encoded view direction (cat(f, Mapping(dir)), nerf.py:197-199)
     job(m->wh1 + (long long)m->hh_rgb * kh1 + F + 1, kh1, P("rgb_from_xyzdir.0.weight") + F, F + m->kdir, FL, m->kdir, 0, 0);
   } else {
-  job(m->wh1 + (long long)m->hh_sun * kh1 + F + 1, kh1, P("sun_v_net.0.weight") + F, F + 3, FL, 3, 0, 0);
-  job(m->wh1 + (long long)m->hh_beta * kh1 + F + 4, kh1, P("beta_from_xyz.0.weight") + F, F + tau, FL, tau, 0, 0);
-  job(m->taux + 4 * FL, FL, P("beta_from_xyz.0.weight") + F, F + tau, tau, FL, 1, 0);
-  job(m->ws2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 0, 0);
-  job(m->ts2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 1, 0);
-  job(m->ws4, FL, P("sun_v_net.4.weight"), FL, FL, FL, 0, 0);
-  job(m->ts4, FL, P("sun_v_net.4.weight"), FL, FL, FL, 1, 0);
+    job(m->wh1 + (long long)m->hh_sun * kh1 + F + 1, kh1, P("sun_v_net.0.weight") + F, F + 3, FL, 3, 0, 0);
+    job(m->wh1 + (long long)m->hh_beta * kh1 + F + 4, kh1, P("beta_from_xyz.0.weight") + F, F + tau, FL, tau, 0, 0);
+    job(m->taux + 4 * FL, FL, P("beta_from_xyz.0.weight") + F, F + tau, tau, FL, 1, 0);
+    job(m->ws2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 0, 0);
+    job(m->ts2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 1, 0);
+    job(m->ws4, FL, P("sun_v_net.4.weight"), FL, FL, FL, 0, 0);
+    job(m->ts4, FL, P("sun_v_net.4.weight"), FL, FL, FL, 1, 0);
   }
   // head output layer: rows [rgb0-2, sigma, sun, beta, sem...], K = [h7 | s3 | hh]
   const int kho = m->kho;
@@ -371,12 +371,12 @@ static void build_layout(snb_model* m) {
   if (nerf) {
     ujob(P("rgb_from_xyzdir.0.weight") + F, F + m->kdir, m->gh1aux + (long long)m->hh_rgb * gald + 1, gald, FL, m->kdir, 0);
   } else {
-  ujob(P("sun_v_net.0.weight") + F, F + 3, m->gh1aux + (long long)m->hh_sun * 16 + 1, 16, FL, 3, 0);
-  ujob(P("beta_from_xyz.0.weight") + F, F + tau, m->gh1aux + (long long)m->hh_beta * 16 + 4, 16, FL, tau, 0);
-  ujob(P("sun_v_net.2.weight"), FL, m->gs2, FL, FL, FL, 0);
-  ujob(P("sun_v_net.2.bias"), 1, m->gbs2, 1, FL, 1, 0);
-  ujob(P("sun_v_net.4.weight"), FL, m->gs4, FL, FL, FL, 0);
-  ujob(P("sun_v_net.4.bias"), 1, m->gbs4, 1, FL, 1, 0);
+    ujob(P("sun_v_net.0.weight") + F, F + 3, m->gh1aux + (long long)m->hh_sun * 16 + 1, 16, FL, 3, 0);
+    ujob(P("beta_from_xyz.0.weight") + F, F + tau, m->gh1aux + (long long)m->hh_beta * 16 + 4, 16, FL, tau, 0);
+    ujob(P("sun_v_net.2.weight"), FL, m->gs2, FL, FL, FL, 0);
+    ujob(P("sun_v_net.2.bias"), 1, m->gbs2, 1, FL, 1, 0);
+    ujob(P("sun_v_net.4.weight"), FL, m->gs4, FL, FL, FL, 0);
+    ujob(P("sun_v_net.4.bias"), 1, m->gbs4, 1, FL, 1, 0);
   }
   // head output layer: scratch is transposed [K features, 16]
   ujob(P("sigma_from_xyz.0.weight"), F, m->ghot + 3, 16, 1, F, 1);
