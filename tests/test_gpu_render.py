@@ -349,15 +349,17 @@ def test_empty_and_single_ray_batches():
 # ---------------------------------------------------------------------------------------------------------
 # K3 + losses fused (snb_composite_loss) against render_rays() + the reference-shaped loss modules
 # ---------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kind,epoch,with_depth", [("semantic", 3, False), ("semantic", 1, True), ("satnerf", 3, True),
-                                                   ("snerf", 3, False)])
-def test_fused_loss_step_equals_module_losses(kind, epoch, with_depth):
+@pytest.mark.parametrize("kind,epoch,with_depth,S", [("semantic", 3, False, 64), ("semantic", 1, True, 64), ("satnerf", 3, True, 64),
+                                                     ("snerf", 3, False, 64), ("semantic", 3, True, 8), ("semantic", 3, True, 128),
+                                                     ("semantic", 3, False, 6)])
+def test_fused_loss_step_equals_module_losses(kind, epoch, with_depth, S):
+    """S = 8 / 64 / 128: one, two and four samples per lane; S = 6: rows that are not 16-byte multiples (scalar path)"""
     from semnerf_b200 import synth
     from semnerf_b200.trainer import Trainer, default_cfgs
     _lib_or_fail()
     C = 6 if kind == "semantic" else 0
     n = 777   # ragged: not a multiple of the warps per block
-    cfgs = default_cfgs(kind, n_samples=64, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=0)
+    cfgs = default_cfgs(kind, n_samples=S, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=0)
     rays, extras = synth.make_rays(n, seed=3)
     rgbs, labels, depths = synth.make_targets(rays, C, seed=3)
     batch = {"rays": rays.to(DEV), "extras": extras.to(DEV), "rgbs": rgbs.to(DEV), "semantic": labels.to(DEV)}
