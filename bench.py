@@ -341,9 +341,9 @@ def run_gpu(args):
         except Exception as e:   # secondary numbers must not take the headline line down
             hbm = {"error": str(e)[:200]}
         if world == 1 and not args.no_cpu:
-            rps, cores, _ = cpu_training_steps(args.cpu_rays, 2, 1)
+            rps, cores, _ = cpu_training_steps(args.cpu_rays, 10, 1)   # ~10-15 s of CPU work
             cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                   "sample": f"{args.cpu_rays} rays x {N_SAMPLES} samples, 2 timed steps of the same training step"}
+                   "sample": f"{args.cpu_rays} rays x {N_SAMPLES} samples, 10 timed steps of the same training step"}
     if rank == 0:
         line = {
             "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
