@@ -487,3 +487,26 @@ def test_nerf_training_step_runs_and_learns():
         assert "t" not in tr.models
         losses = [tr.training_step(batch, epoch=3).item() for _ in range(15)]
         assert all(l == l for l in losses) and losses[-1] < losses[0], losses
+
+
+@pytest.mark.parametrize("C,S", [(10, 16), (1, 200)])
+def test_class_count_and_sample_count_limits(C, S):
+    """the widest and the narrowest semantic head (10 classes fill the 16 head pre-activations exactly; 1 class) and a
+    sample count that needs 7 samples per lane: render + losses + gradients vs the oracle"""
+    from semnerf_b200.renderer import B200Renderer
+    _lib_or_fail()
+    n = 96
+    spec, params, emb, cfgs, model, t = _model("semantic", C, seed=6, S=S, sc=0.05)
+    rays, extras = O.synthetic_rays(n, seed=12)
+    u = torch.rand(n, S, generator=torch.Generator().manual_seed(4))
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ref = O.render_rays(p, emb, spec, rays, extras, S, u=u, sc_lambda=0.05)
+    res = B200Renderer(cfgs).render_rays({"coarse": model, "t": t}, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV)})
+    assert res["semantic_logits_coarse"].shape == (n, C) and res["albedo_coarse"].shape == (n, S, 3)
+    for k in ("rgb_coarse", "depth_coarse", "semantic_logits_coarse"):
+        assert (res[k].detach().cpu() - ref[k].detach()).abs().max() <= 2e-3, k
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(9))
+    lab = torch.randint(0, C, (n,), generator=torch.Generator().manual_seed(4))
+    (O.satnerf_loss(ref, gt) + O.semantic_loss(ref, lab)).backward()
+    (O.satnerf_loss(res, gt.to(DEV)) + O.semantic_loss(res, lab.to(DEV))).backward()
+    assert _cos(model.flat.grad.cpu(), torch.cat([p[k].grad.flatten() for k in p])) >= 0.999
