@@ -35,7 +35,7 @@ ALG_FLOP_PER_TRAIN_RAY = 64 * (16_862_208 + 14_470_144)
 ALG_FLOP_PER_RENDER_SAMPLE = 5_641_216 + 4_844_544  # all heads + the solar pass forward
 # dram__bytes_read.sum + dram__bytes_write.sum of the GEMM kernels of one 8192-ray step, from the ncu --set full capture
 # under profiles/ (filled in by tools/ncu_traffic.py; None until a capture of the current kernels exists)
-NCU_TRAFFIC_BYTES_PER_STEP = 72.607e9   # profiles/r01d_ncu_step_gemms.csv (34 launches of one step)
+NCU_TRAFFIC_BYTES_PER_STEP = 67.932e9   # profiles/r01g_ncu_step_gemms.csv (34 launches of one step)
 
 
 def peaks():

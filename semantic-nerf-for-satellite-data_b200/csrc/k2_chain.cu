@@ -224,8 +224,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         if (elect_one()) {
           if (lead_cta) mbar_expect_tx(&fullA[stage], 2 * 16384);
           else mbar_arrive_remote(&fullA[stage], 0);
-          tma_load_2d_2sm(sA + stage * 16384, &args.maps[c.l].tmA[sg], &fullA[stage], kk * GEMM_BLOCK_K,
-                          ly.a_scratch[sg] ? row_scr : row_real);
+          // rows written by this pair one layer-step ago are kept in L2 (stores: evict-last) until their last read here
+          tma_load_2d_2sm_hint(sA + stage * 16384, &args.maps[c.l].tmA[sg], &fullA[stage], kk * GEMM_BLOCK_K,
+                               ly.a_scratch[sg] ? row_scr : row_real, c.j == ly.n_tiles - 1 ? L2_EVICT_FIRST : L2_EVICT_LAST);
         }
         __syncwarp();
         if (++stage == CHAIN_A_STAGES) { stage = 0; phase ^= 1; }
@@ -357,7 +358,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
               bulk_wait_done<0>();
               confirm(cn);
             }
-            tma_store_2d(&args.maps[c.l].tmO0, smem_u32(sStg) + (g * 2 + ci) * GEMM_STAGING, c.j * 256 + (g + 2 * ci) * 64, m_out);
+            tma_store_2d_hint(&args.maps[c.l].tmO0, smem_u32(sStg) + (g * 2 + ci) * GEMM_STAGING, c.j * 256 + (g + 2 * ci) * 64, m_out,
+                              L2_EVICT_LAST);
             if (k == 3 && ly.epi == EPI_SIN && ly.mask != nullptr)   // all 16 warps have staged their words of the tile
               tma_store_2d(&args.maps[c.l].tmMask, smem_u32(mask_smem) + (itc & 1) * 4096, c.j * 8, blk * 256 + (int)cta_rank * GEMM_BLOCK_M);
             bulk_commit();
