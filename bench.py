@@ -34,7 +34,7 @@ N_CLASSES, N_SAMPLES, CAR_INDEX = 6, 64, 4
 ALG_FLOP_PER_TRAIN_RAY = 64 * (16_862_208 + 14_470_144)
 ALG_FLOP_PER_RENDER_SAMPLE = 5_641_216 + 4_844_544  # all heads + the solar pass forward
 # dram__bytes_read.sum + dram__bytes_write.sum of the GEMM kernels of one 8192-ray step, from the ncu --set full capture
-# under profiles/ (filled in by tools/ncu_traffic.py; None until a capture of the current kernels exists)
+# under profiles/ (total printed by tools/ncu_summary.py on the capture tools/round_profile.sh takes)
 NCU_TRAFFIC_BYTES_PER_STEP = 67.932e9   # profiles/r01g_ncu_step_gemms.csv (34 launches of one step)
 
 
