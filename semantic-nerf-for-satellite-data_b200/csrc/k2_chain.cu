@@ -226,7 +226,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
           else mbar_arrive_remote(&fullA[stage], 0);
           // rows written by this pair one layer-step ago are kept in L2 (stores: evict-last) until their last read here
           tma_load_2d_2sm_hint(sA + stage * 16384, &args.maps[c.l].tmA[sg], &fullA[stage], kk * GEMM_BLOCK_K,
-                               ly.a_scratch[sg] ? row_scr : row_real, c.j == ly.n_tiles - 1 ? L2_EVICT_FIRST : L2_EVICT_LAST);
+                               ly.a_scratch[sg] ? row_scr : row_real,
+                               // (a head-output layer reads its rows BEFORE the wide layer that shares them: never the last use)
+                               (c.j == ly.n_tiles - 1 && ly.epi != EPI_HEADOUT) ? L2_EVICT_FIRST : L2_EVICT_LAST);
         }
         __syncwarp();
         if (++stage == CHAIN_A_STAGES) { stage = 0; phase ^= 1; }
