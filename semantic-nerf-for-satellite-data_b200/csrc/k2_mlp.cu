@@ -733,7 +733,8 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   m->hh_rgb = 0;
   m->hh_beta = FL;
   m->hh_sem = 2 * FL;
-  m->hhw = model_kind == SNB_MODEL_SEMANTIC ? 4 * FL : 3 * FL;
+  // NeRF: the rgb block only (no sun / uncertainty heads: their layers are not part of its plans)
+  m->hhw = model_kind == SNB_MODEL_SEMANTIC ? 4 * FL : (model_kind == SNB_MODEL_NERF ? FL : 3 * FL);
   m->hh_sun = m->hhw - FL;
   build_layout(m);
   *out = m;
@@ -852,10 +853,12 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
       CSeg s1[2] = {{fbuf, F, F, F / 64, srows, sflag}, {aux, m->aux_ld, m->aux_ld, 1, P, 0}};
       cp.add(EPI_SIN, n, s1, 2, pk + m->wh1 + (long long)r0 * (F + 64), F + 64, F + 64, ws + w.hh + (size_t)r0 * 2, hhw, P, 0,
              nullptr, 0, train ? reinterpret_cast<uint32_t*>(ws + w.sghh) + r0 / 32 : nullptr, hhw / 32, nullptr, 1.0f);
+      const bool nerf = m->kind == SNB_MODEL_NERF;   // no sun head: the hh rows are the last head-output layer
       if (all) {
         CSeg shh = {ws + w.hh, hhw, hhw, hhw / 64, P, 0};
-        cp.add_rows16(shh, pk + m->who + F + FL, m->kho, hhw, 1, hpart, nullptr);
+        cp.add_rows16(shh, pk + m->who + F + FL, m->kho, hhw, nerf ? 2 : 1, hpart, nerf ? pb + m->bho : nullptr);
       }
+      if (nerf) return cp.run();
       CSeg s2[1] = {{ws + w.hh + (size_t)m->hh_sun * 2, hhw, FL, FL / 64, P, 0}};
       cp.add(EPI_SIN, FL, s2, 1, pk + m->ws2, FL, FL, s2buf, FL, srows, sflag, nullptr, 0,
              train ? reinterpret_cast<uint32_t*>(ws + w.sgs2) : nullptr, FL / 32, pb + m->bs2, 1.0f);
@@ -891,6 +894,7 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
   const bool all = head_mask == SNB_HEADS_ALL;
   const bool solar = head_mask == SNB_HEADS_SOLAR;
   const bool depth = head_mask == SNB_HEADS_DEPTH;
+  const bool nerf = m->kind == SNB_MODEL_NERF;
   void* dpre = ws + w.dpre;
 
   SNB_CUDA(cudaMemsetAsync(gs, 0, (size_t)m->gscratch_elems * 4, st));
@@ -915,18 +919,21 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     uint32_t* sghh = reinterpret_cast<uint32_t*>(ws + w.sghh);
     CSeg cdpre[1] = {{dpre, 16, 16, 1, P, 0}};
     if (!depth) {
-      // sun head: s3 <- head output, then back through sun.4, sun.2 into the sun block of hh
-      cp.add(EPI_MUL, FL, cdpre, 1, pk + m->tho, 16, 16, ws + w.dys3, FL, P, 0, ws + w.s3, FL,
-             reinterpret_cast<uint32_t*>(ws + w.sgs3), FL / 32, nullptr, 1.0f);
-      if (all)  // rgb / beta / sem blocks of hh (columns [0, hhw-256))
-        cp.add(EPI_MUL, hhw - FL, cdpre, 1, pk + m->tho + (long long)FL * 16, 16, 16, ws + w.dyhh, hhw, P, 0, ws + w.hh, hhw, sghh,
-               hhw / 32, nullptr, 1.0f);
-      CSeg c3[1] = {{ws + w.dys3, FL, FL, FL / 64, P, 0}};
-      cp.add(EPI_MUL, FL, c3, 1, pk + m->ts4, FL, FL, ws + w.dys2, FL, P, 0, ws + w.s2, FL,
-             reinterpret_cast<uint32_t*>(ws + w.sgs2), FL / 32, nullptr, 1.0f);
-      CSeg c2[1] = {{ws + w.dys2, FL, FL, FL / 64, P, 0}};
-      cp.add(EPI_MUL, FL, c2, 1, pk + m->ts2, FL, FL, ws + w.dyhh + (size_t)m->hh_sun * 2, hhw, P, 0,
-             ws + w.hh + (size_t)m->hh_sun * 2, hhw, sghh + m->hh_sun / 32, hhw / 32, nullptr, 1.0f);
+      // sun head: s3 <- head output, then back through sun.4, sun.2 into the sun block of hh  (NeRF has no sun head)
+      if (!nerf)
+        cp.add(EPI_MUL, FL, cdpre, 1, pk + m->tho, 16, 16, ws + w.dys3, FL, P, 0, ws + w.s3, FL,
+               reinterpret_cast<uint32_t*>(ws + w.sgs3), FL / 32, nullptr, 1.0f);
+      if (all)  // rgb / beta / sem blocks of hh (columns [0, hhw-256); NeRF: its single rgb block)
+        cp.add(EPI_MUL, nerf ? hhw : hhw - FL, cdpre, 1, pk + m->tho + (long long)FL * 16, 16, 16, ws + w.dyhh, hhw, P, 0, ws + w.hh,
+               hhw, sghh, hhw / 32, nullptr, 1.0f);
+      if (!nerf) {
+        CSeg c3[1] = {{ws + w.dys3, FL, FL, FL / 64, P, 0}};
+        cp.add(EPI_MUL, FL, c3, 1, pk + m->ts4, FL, FL, ws + w.dys2, FL, P, 0, ws + w.s2, FL,
+               reinterpret_cast<uint32_t*>(ws + w.sgs2), FL / 32, nullptr, 1.0f);
+        CSeg c2[1] = {{ws + w.dys2, FL, FL, FL / 64, P, 0}};
+        cp.add(EPI_MUL, FL, c2, 1, pk + m->ts2, FL, FL, ws + w.dyhh + (size_t)m->hh_sun * 2, hhw, P, 0,
+               ws + w.hh + (size_t)m->hh_sun * 2, hhw, sghh + m->hh_sun / 32, hhw / 32, nullptr, 1.0f);
+      }
       CSeg ch[1] = {{dyhh_r0, hhw, nh, nh / 64, P, 0}};
       cp.add(EPI_LINEAR, F, ch, 1, pk + m->th1 + r0, hhw, nh, ws + w.df, F, P, 0, nullptr, 0, nullptr, 0, nullptr, 1.0f);
       // dY7 = ([dF | dPre16] * [Wf ; w_sigma]) * c7
@@ -949,11 +956,13 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     if (int r = transpose_cols(aux, m->aux_ld, m->aux_ld, P, ws + w.auxT, ldt, st)) return r;
   if (int r = transpose_cols(enc, m->enc_ld, 64, P, ws + w.encT, ldt, st)) return r;
   add_wgrad(p, F, 16, H(7), F, dpre, 16, P, gs + m->ghot, 16, sms);
-  if (!depth) add_wgrad(p, FL, 16, ws + w.s3, FL, dpre, 16, P, gs + m->ghot + (long long)F * 16, 16, sms);
+  if (!depth && !nerf) add_wgrad(p, FL, 16, ws + w.s3, FL, dpre, 16, P, gs + m->ghot + (long long)F * 16, 16, sms);
   if (all) add_wgrad(p, hhw, 16, ws + w.hh, hhw, dpre, 16, P, gs + m->ghot + (long long)(F + FL) * 16, 16, sms);
   if (!depth) {
-    add_wgrad(p, FL, FL, ws + w.dys3, FL, ws + w.s2, FL, P, gs + m->gs4, FL, sms, gs + m->gbs4);
-    add_wgrad(p, FL, FL, ws + w.dys2, FL, ws + w.hh + (size_t)m->hh_sun * 2, hhw, P, gs + m->gs2, FL, sms, gs + m->gbs2);
+    if (!nerf) {
+      add_wgrad(p, FL, FL, ws + w.dys3, FL, ws + w.s2, FL, P, gs + m->gs4, FL, sms, gs + m->gbs4);
+      add_wgrad(p, FL, FL, ws + w.dys2, FL, ws + w.hh + (size_t)m->hh_sun * 2, hhw, P, gs + m->gs2, FL, sms, gs + m->gbs2);
+    }
     // fused head first layers: weight / bias / per-ray-column gradients
     // ... the bias / per-ray-column gradients dY^T x aux ride the same launch as a 16-column side operand
     const int gald = m->aux_ld > 16 ? 64 : 16;

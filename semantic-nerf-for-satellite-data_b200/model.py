@@ -239,9 +239,8 @@ class NeRFB200(SnbMLP):
     defaults mapping=True, siren=False -> positional encoding of xyz (10 frequencies) and of the view direction (4), ReLU
     activations, nn.Linear default initialisation; nerf.py:98-162).  Outputs [rgb | sigma] (4 columns).
 
-    Runs on the SatNeRF head layout with the sun / uncertainty blocks absent (zero weights in the packed image, no
-    parameters) and the sun column pinned to 1, so K3's lighting model reduces to NeRF's plain emission-absorption sum
-    (nerf.py:73-86).  NB: K3 clamps the composited colour to [0, 1] (as SatNeRF / S-NeRF do); NeRF's inference does not -
+    Its kernel plans hold the trunk, sigma, feats and the rgb head only; the packed sun column is pinned to 1, so K3's
+    lighting model reduces to NeRF's plain emission-absorption sum (nerf.py:73-86).  NB: K3 clamps the composited colour to [0, 1] (as SatNeRF / S-NeRF do); NeRF's inference does not -
     the two differ only when a composited channel leaves [0, 1], by at most 1e-3 (the sigmoid padding, nerf.py:203)."""
 
     def __init__(self, layers=8, feat=512, mapping=True, mapping_sizes=(10, 4), skips=(4,), siren=False):
