@@ -41,7 +41,8 @@ enum {
 /* SNB_MODEL_NERF: vanilla NeRF as baseline/pipelines/nerf.py:26-34 builds it (baseline/models/nerf.py:98-212): positional
  * encoding of xyz (10) and of the view direction (4), ReLU activations, outputs [rgb | sigma].  Its plans hold the trunk, sigma,
  * feats and the rgb head only; the packed sun column is pinned to 1, so the compositing kernel's irradiance is 1; the 24 encoded view-direction values ride a 32-column `aux` row (snb_nerf_aux). */
-enum { SNB_MODEL_SATNERF = 0, SNB_MODEL_SEMANTIC = 1, SNB_MODEL_NERF = 2 };
+enum { SNB_MODEL_SATNERF = 0, SNB_MODEL_SEMANTIC = 1, SNB_MODEL_NERF = 2,
+       SNB_MODEL_SNERF = 3 /* S-NeRF (baseline/models/snerf.py:104-243): SatNeRF without the uncertainty head and embedding */ };
 
 /* which heads a pass evaluates (bit mask).  SNB_HEADS_ALL is the reference's forward();
  * SNB_HEADS_SOLAR is what the solar-correction pass keeps (semantic/components/rendering.py:76-78);

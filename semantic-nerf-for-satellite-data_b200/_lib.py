@@ -13,7 +13,9 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libsnb.so")
 
-MODEL_SATNERF, MODEL_SEMANTIC, MODEL_NERF = 0, 1, 2
+MODEL_SATNERF, MODEL_SEMANTIC, MODEL_NERF, MODEL_SNERF = 0, 1, 2, 3
+# the kind K1 (sample + encode) sees: raw xyz (SatNeRF, S-NeRF) or the 10-frequency positional encoding (semantic, NeRF)
+K1_KIND = {0: 0, 1: 1, 2: 1, 3: 0}
 HEADS_ALL, HEADS_SOLAR, HEADS_DEPTH = 63, 5, 1
 EPI_SIN, EPI_LINEAR, EPI_MUL, EPI_HEADOUT, EPI_F32ROWS, EPI_WGRAD = range(6)
 

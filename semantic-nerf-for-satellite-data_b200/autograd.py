@@ -57,7 +57,7 @@ def encode_rays(model, emb_weight, rays, extras, n_samples, u=None, z=None, seed
     check(lib.snb_sample_encode(ptr(rays), ptr(extras), ptr(_f32c(u)), seed, ray_offset, ptr(t_steps(n_samples, dev)),
                                 ptr(ew), ew.shape[0] if ew is not None else 0, ew.shape[1] if ew is not None else 0,
                                 ptr(w1), ptr(b1), ptr(w2), ptr(b2), hidden, n, n_samples,
-                                _lib.MODEL_SEMANTIC if nerf else model.kind,
+                                _lib.K1_KIND[model.kind],
                                 1 if z_given else 0, ptr(z_vals), ptr(enc), ptr(enc_sc), ptr(aux), ptr(sky), stream()),
           "snb_sample_encode")
     if nerf:   # the aux row of NeRF: [1, Mapping(4, 3)(view direction), 0...] (32 columns) instead of [1, sun_d, t]
@@ -151,7 +151,7 @@ class MLPPoints(torch.autograd.Function):
             w1, b1, w2, b2 = model.sky_params()
             hidden = w1.shape[0]
         check(lib.snb_encode_points(ptr(xyz), ptr(sun_d), ptr(tt), tt.shape[1], ptr(w1), ptr(b1), ptr(w2), ptr(b2),
-                                    hidden, P, _lib.MODEL_SEMANTIC if nerf else model.kind, ptr(enc), ptr(aux), ptr(sky),
+                                    hidden, P, _lib.K1_KIND[model.kind], ptr(enc), ptr(aux), ptr(sky),
                                     stream()), "snb_encode_points")
         if nerf:
             aux = nerf_aux(sun_d, 1)

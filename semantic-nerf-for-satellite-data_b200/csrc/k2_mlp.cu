@@ -180,6 +180,7 @@ static void build_layout(snb_model* m) {
   const int k0 = m->k0, hhw = m->hhw, tau = m->tau, C = m->n_classes;
   const bool sem = m->kind == SNB_MODEL_SEMANTIC;
   const bool nerf = m->kind == SNB_MODEL_NERF;   // nerf.py:118-160: trunk, sigma, feats, rgb(f | dir) only
+  const bool has_beta = m->kind == SNB_MODEL_SATNERF || sem;   // S-NeRF (snerf.py:161-186) and NeRF have no uncertainty head
   const bool enc60 = k0 == 60;                   // positional encoding input: the [hi | lo | 0] 128-column K1 row
   // ---- flat fp32 parameter order = reference state_dict order ----
   m->n_params = 0;
@@ -215,6 +216,8 @@ static void build_layout(snb_model* m) {
     add_tensor(m, "sky_color.0.bias", FL, 0);
     add_tensor(m, "sky_color.2.weight", 3, FL);
     add_tensor(m, "sky_color.2.bias", 3, 0);
+  }
+  if (has_beta) {
     add_tensor(m, "beta_from_xyz.0.weight", FL, F + tau);
     add_tensor(m, "beta_from_xyz.0.bias", FL, 0);
     add_tensor(m, "beta_from_xyz.2.weight", 1, FL);
@@ -285,10 +288,8 @@ static void build_layout(snb_model* m) {
   // fused head first layers: rows [rgb | beta | (sem) | sun]  (NeRF: the rgb block only; the others stay zero)
   struct Blk { int row; const char* w; const char* b; int kin; };
   std::vector<Blk> blks = {{m->hh_rgb, "rgb_from_xyzdir.0", "rgb_from_xyzdir.0", F + (nerf ? m->kdir : 0)}};
-  if (!nerf) {
-    blks.push_back({m->hh_beta, "beta_from_xyz.0", "beta_from_xyz.0", F + tau});
-    blks.push_back({m->hh_sun, "sun_v_net.0", "sun_v_net.0", F + 3});
-  }
+  if (has_beta) blks.push_back({m->hh_beta, "beta_from_xyz.0", "beta_from_xyz.0", F + tau});
+  if (!nerf) blks.push_back({m->hh_sun, "sun_v_net.0", "sun_v_net.0", F + 3});
   if (sem) blks.push_back({m->hh_sem, "semantic_prediction.0", "semantic_prediction.0", F});
   for (auto& b : blks) {
     const long long w = P(std::string(b.w) + ".weight"), bb = P(std::string(b.b) + ".bias");
@@ -300,8 +301,10 @@ static void build_layout(snb_model* m) {
     job(m->wh1 + (long long)m->hh_rgb * kh1 + F + 1, kh1, P("rgb_from_xyzdir.0.weight") + F, F + m->kdir, FL, m->kdir, 0, 0);
   } else {
     job(m->wh1 + (long long)m->hh_sun * kh1 + F + 1, kh1, P("sun_v_net.0.weight") + F, F + 3, FL, 3, 0, 0);
-    job(m->wh1 + (long long)m->hh_beta * kh1 + F + 4, kh1, P("beta_from_xyz.0.weight") + F, F + tau, FL, tau, 0, 0);
-    job(m->taux + 4 * FL, FL, P("beta_from_xyz.0.weight") + F, F + tau, tau, FL, 1, 0);
+    if (has_beta) {
+      job(m->wh1 + (long long)m->hh_beta * kh1 + F + 4, kh1, P("beta_from_xyz.0.weight") + F, F + tau, FL, tau, 0, 0);
+      job(m->taux + 4 * FL, FL, P("beta_from_xyz.0.weight") + F, F + tau, tau, FL, 1, 0);
+    }
     job(m->ws2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 0, 0);
     job(m->ts2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 1, 0);
     job(m->ws4, FL, P("sun_v_net.4.weight"), FL, FL, FL, 0, 0);
@@ -312,12 +315,12 @@ static void build_layout(snb_model* m) {
   job(m->who + 3ll * kho, kho, P("sigma_from_xyz.0.weight"), F, 1, F, 0, 0);
   if (!nerf) job(m->who + 4ll * kho + F, kho, P("sun_v_net.6.weight"), FL, 1, FL, 0, 0);
   job(m->who + 0ll * kho + F + FL + m->hh_rgb, kho, P("rgb_from_xyzdir.2.weight"), FL, 3, FL, 0, 0);
-  if (!nerf) job(m->who + 5ll * kho + F + FL + m->hh_beta, kho, P("beta_from_xyz.2.weight"), FL, 1, FL, 0, 0);
+  if (has_beta) job(m->who + 5ll * kho + F + FL + m->hh_beta, kho, P("beta_from_xyz.2.weight"), FL, 1, FL, 0, 0);
   if (sem) job(m->who + 6ll * kho + F + FL + m->hh_sem, kho, P("semantic_prediction.2.weight"), FL, C, FL, 0, 0);
   // transposed head output for dgrad: rows = [s3 | hh] features, 16 columns
   if (!nerf) job(m->tho + 4, 16, P("sun_v_net.6.weight"), FL, FL, 1, 1, 0);
   job(m->tho + (long long)(FL + m->hh_rgb) * 16 + 0, 16, P("rgb_from_xyzdir.2.weight"), FL, FL, 3, 1, 0);
-  if (!nerf) job(m->tho + (long long)(FL + m->hh_beta) * 16 + 5, 16, P("beta_from_xyz.2.weight"), FL, FL, 1, 1, 0);
+  if (has_beta) job(m->tho + (long long)(FL + m->hh_beta) * 16 + 5, 16, P("beta_from_xyz.2.weight"), FL, FL, 1, 1, 0);
   if (sem) job(m->tho + (long long)(FL + m->hh_sem) * 16 + 6, 16, P("semantic_prediction.2.weight"), FL, FL, C, 1, 0);
   // fp32 biases
   for (int i = 0; i < LAYERS; ++i) job(m->bl[i], 1, fcb(i), 1, F, 1, 0, 2);
@@ -327,7 +330,7 @@ static void build_layout(snb_model* m) {
   job(m->bho + 0, 1, P("rgb_from_xyzdir.2.bias"), 1, 3, 1, 0, 2);
   job(m->bho + 3, 1, P("sigma_from_xyz.0.bias"), 1, 1, 1, 0, 2);
   if (!nerf) job(m->bho + 4, 1, P("sun_v_net.6.bias"), 1, 1, 1, 0, 2);
-  if (!nerf) job(m->bho + 5, 1, P("beta_from_xyz.2.bias"), 1, 1, 1, 0, 2);
+  if (has_beta) job(m->bho + 5, 1, P("beta_from_xyz.2.bias"), 1, 1, 1, 0, 2);
   if (sem) job(m->bho + 6, 1, P("semantic_prediction.2.bias"), 1, C, 1, 0, 2);
 
   // ---- fp32 packed-gradient scratch + unpack jobs (grads[dst] += scratch[src]) ----
@@ -372,7 +375,7 @@ static void build_layout(snb_model* m) {
     ujob(P("rgb_from_xyzdir.0.weight") + F, F + m->kdir, m->gh1aux + (long long)m->hh_rgb * gald + 1, gald, FL, m->kdir, 0);
   } else {
     ujob(P("sun_v_net.0.weight") + F, F + 3, m->gh1aux + (long long)m->hh_sun * 16 + 1, 16, FL, 3, 0);
-    ujob(P("beta_from_xyz.0.weight") + F, F + tau, m->gh1aux + (long long)m->hh_beta * 16 + 4, 16, FL, tau, 0);
+    if (has_beta) ujob(P("beta_from_xyz.0.weight") + F, F + tau, m->gh1aux + (long long)m->hh_beta * 16 + 4, 16, FL, tau, 0);
     ujob(P("sun_v_net.2.weight"), FL, m->gs2, FL, FL, FL, 0);
     ujob(P("sun_v_net.2.bias"), 1, m->gbs2, 1, FL, 1, 0);
     ujob(P("sun_v_net.4.weight"), FL, m->gs4, FL, FL, FL, 0);
@@ -382,12 +385,12 @@ static void build_layout(snb_model* m) {
   ujob(P("sigma_from_xyz.0.weight"), F, m->ghot + 3, 16, 1, F, 1);
   if (!nerf) ujob(P("sun_v_net.6.weight"), FL, m->ghot + (long long)F * 16 + 4, 16, 1, FL, 1);
   ujob(P("rgb_from_xyzdir.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_rgb) * 16 + 0, 16, 3, FL, 1);
-  if (!nerf) ujob(P("beta_from_xyz.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_beta) * 16 + 5, 16, 1, FL, 1);
+  if (has_beta) ujob(P("beta_from_xyz.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_beta) * 16 + 5, 16, 1, FL, 1);
   if (sem) ujob(P("semantic_prediction.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_sem) * 16 + 6, 16, C, FL, 1);
   ujob(P("rgb_from_xyzdir.2.bias"), 1, m->gbho + 0, 1, 3, 1, 0);
   ujob(P("sigma_from_xyz.0.bias"), 1, m->gbho + 3, 1, 1, 1, 0);
   if (!nerf) ujob(P("sun_v_net.6.bias"), 1, m->gbho + 4, 1, 1, 1, 0);
-  if (!nerf) ujob(P("beta_from_xyz.2.bias"), 1, m->gbho + 5, 1, 1, 1, 0);
+  if (has_beta) ujob(P("beta_from_xyz.2.bias"), 1, m->gbho + 5, 1, 1, 1, 0);
   if (sem) ujob(P("semantic_prediction.2.bias"), 1, m->gbho + 6, 1, C, 1, 0);
 }
 
@@ -711,8 +714,8 @@ using namespace snb;
 // =====================================================================================================
 extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid) {
   SNB_CHECK_ARG(out != nullptr, SNB_ERR_INVALID, "model_create: null out");
-  SNB_CHECK_ARG(model_kind == SNB_MODEL_SATNERF || model_kind == SNB_MODEL_SEMANTIC || model_kind == SNB_MODEL_NERF,
-                SNB_ERR_INVALID, "model_create: bad kind %d", model_kind);
+  SNB_CHECK_ARG(model_kind >= SNB_MODEL_SATNERF && model_kind <= SNB_MODEL_SNERF, SNB_ERR_INVALID, "model_create: bad kind %d",
+                model_kind);
   if (model_kind != SNB_MODEL_SEMANTIC) n_classes = 0;
   SNB_CHECK_ARG(n_classes >= 0 && n_classes <= 10 && (model_kind != SNB_MODEL_SEMANTIC || n_classes >= 1),
                 SNB_ERR_UNSUPPORTED, "model_create: n_classes %d outside [1,10]", n_classes);
@@ -721,7 +724,7 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   m->n_classes = n_classes;
   m->sem_sigmoid = semantic_sigmoid;
   m->tau = 4;  // t_embedding_tau (configs/pipelines/*.toml)
-  const bool enc60 = model_kind != SNB_MODEL_SATNERF;   // positional encoding of xyz (10 frequencies)
+  const bool enc60 = model_kind == SNB_MODEL_SEMANTIC || model_kind == SNB_MODEL_NERF;   // positional encoding of xyz (10 frequencies)
   m->k0 = enc60 ? 60 : 3;
   m->enc_ld = enc60 ? 128 : 64;
   m->w0_ld = enc60 ? 192 : 64;
@@ -734,8 +737,11 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   m->hh_beta = FL;
   m->hh_sem = 2 * FL;
   // NeRF: the rgb block only (no sun / uncertainty heads: their layers are not part of its plans)
-  m->hhw = model_kind == SNB_MODEL_SEMANTIC ? 4 * FL : (model_kind == SNB_MODEL_NERF ? FL : 3 * FL);
+  // S-NeRF: [rgb | sun] (no uncertainty block)
+  m->hhw = model_kind == SNB_MODEL_SEMANTIC ? 4 * FL
+                                            : (model_kind == SNB_MODEL_NERF ? FL : (model_kind == SNB_MODEL_SNERF ? 2 * FL : 3 * FL));
   m->hh_sun = m->hhw - FL;
+  if (model_kind == SNB_MODEL_SNERF || model_kind == SNB_MODEL_NERF) m->hh_beta = m->hh_sem = 0;   // absent blocks: never addressed
   build_layout(m);
   *out = m;
   return 0;
@@ -968,7 +974,9 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     const int gald = m->aux_ld > 16 ? 64 : 16;
     const WgradSide s_aux = {ws + w.auxT, ldt, gald, gs + m->gh1aux + (long long)r0 * gald, gald, m->aux_ld};
     add_wgrad(p, nh, F, dyhh_r0, hhw, ws + w.f, F, P, gs + m->gh1 + (long long)r0 * F, F, sms, nullptr, &s_aux);
-    if (all && g_aux) {
+    if (g_aux && m->find("beta_from_xyz.0.weight") < 0) {
+      SNB_CUDA(cudaMemsetAsync(g_aux, 0, (size_t)P * 16 * sizeof(float), st));   // no embedding-dependent head in this model
+    } else if (all && g_aux) {
       // d aux = dY_beta * W_beta0[:, 512:]  -> embedding gradient (summed per ray by the caller-side kernel)
       Seg sb[1] = {{ws + w.dyhh + (size_t)m->hh_beta * 2, hhw, FL, FL / 64}};
       GemmArgs& a = add_rows16(p, EPI_F32ROWS, P, sb, 1, pk + m->taux, FL, FL, nullptr);
@@ -1018,7 +1026,7 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
   const bool all = head_mask == SNB_HEADS_ALL, depth = head_mask == SNB_HEADS_DEPTH;
   const bool nerf = m->kind == SNB_MODEL_NERF;   // sun_d carries the ENCODED view direction (R, 24) there; t / sky unused
   SNB_CHECK_ARG(depth || sun_d != nullptr, SNB_ERR_INVALID, "mlp_forward_fp32: sun_d required");
-  SNB_CHECK_ARG(!all || nerf || (t != nullptr && sky != nullptr), SNB_ERR_INVALID,
+  SNB_CHECK_ARG(!all || nerf || ((t != nullptr || m->find("beta_from_xyz.0.weight") < 0) && sky != nullptr), SNB_ERR_INVALID,
                 "mlp_forward_fp32: t and sky required for all heads");
   SNB_CHECK_ARG(workspace_bytes >= snb_mlp_fp32_workspace_bytes(m, n_points), SNB_ERR_WORKSPACE,
                 "mlp_forward_fp32: workspace %zu too small", workspace_bytes);
@@ -1097,7 +1105,7 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
     if (!all) continue;
     if (int r = gemm(sf, nullptr, W("rgb_from_xyzdir.0"), F, B("rgb_from_xyzdir.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
     if (int r = gemm(rows(g1, FL, FL), nullptr, W("rgb_from_xyzdir.2"), FL, B("rgb_from_xyzdir.2"), 3, F32_RGB, 1.0f, o, n_out)) return r;
-    {
+    if (m->find("beta_from_xyz.0.weight") >= 0) {
       const F32Seg st_ = per_ray(t, tau);
       if (int r = gemm(sf, &st_, W("beta_from_xyz.0"), F + tau, B("beta_from_xyz.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("beta_from_xyz.2"), FL, B("beta_from_xyz.2"), 1, F32_SOFTPLUS, 1.0f, o + 8, n_out)) return r;

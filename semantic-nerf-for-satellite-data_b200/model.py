@@ -17,7 +17,7 @@ from typing import Dict, List, Tuple
 import torch
 
 from . import _lib
-from ._lib import HEADS_ALL, MODEL_NERF, MODEL_SATNERF, MODEL_SEMANTIC, check, ptr, stream
+from ._lib import HEADS_ALL, MODEL_NERF, MODEL_SATNERF, MODEL_SEMANTIC, MODEL_SNERF, check, ptr, stream
 
 
 class SnbMLP(torch.nn.Module):
@@ -37,7 +37,7 @@ class SnbMLP(torch.nn.Module):
         self.n_out_kernel = 9 + n_classes            # columns of the packed tensor the kernels write
         self.hidden_prefixes: Tuple[str, ...] = ()   # tensors of the flat buffer a model variant does not own (S-NeRF)
         self.t_embedding_dims = tau
-        self.enc_ld = 64 if kind == MODEL_SATNERF else 128
+        self.enc_ld = 64 if kind in (MODEL_SATNERF, MODEL_SNERF) else 128
         n = lib.snb_model_param_count(h)
         self.table: List[Tuple[str, int, Tuple[int, ...]]] = []
         for i in range(lib.snb_model_num_tensors(h)):
@@ -208,24 +208,18 @@ class ShadowNeRFB200(SnbMLP):
     8x512 SIREN, raw xyz, skip [4]; constructor signature snerf.py:104-112).
 
     S-NeRF is SatNeRF without the transient-uncertainty head and its embedding (snerf.py:161-186 vs satnerf.py:143-206):
-    same trunk, sigma, feats, albedo, sun-visibility and sky heads, outputs [rgb | sigma | sun_v | sky] (8 columns).  It
-    runs on the SatNeRF kernel plan; the beta block of the fused head layer is held at zero weights, is not part of
-    ``state_dict()`` / ``named_tensors()`` and receives no gradient (nothing downstream reads column 8), so checkpoints
-    interchange with the reference's ShadowNeRF."""
+    same trunk, sigma, feats, albedo, sun-visibility and sky heads, outputs [rgb | sigma | sun_v | sky] (8 columns).  The
+    library model kind SNB_MODEL_SNERF holds exactly these tensors (fused head layer = [rgb | sun] blocks); the kernels'
+    packed rows keep 9 columns, the ninth is unused."""
 
     def __init__(self, layers=8, feat=512, mapping=False, mapping_sizes=(10, 4), skips=(4,), siren=True):
         if layers != 8 or feat != 512 or list(skips) != [4] or mapping or not siren:
             raise _lib.SnbError("libsnb implements the shipped S-NeRF configuration: 8x512 SIREN, skip [4], raw-xyz input "
                                 "(configs/pipelines/snerf.toml, baseline/pipelines/snerf.py:24-32)")
-        super().__init__(MODEL_SATNERF, 0, True, 4, None)
+        super().__init__(MODEL_SNERF, 0, True, 4, None)
         self.variant = "snerf"
         self.number_of_outputs = 8                   # snerf.py:117-119
         self.layers, self.skips = layers, list(skips)
-        with torch.no_grad():
-            for name, off, shape in self.table:
-                if name.startswith("beta_from_xyz."):
-                    self.flat[off:off + int(torch.tensor(shape).prod())] = 0
-        self.hidden_prefixes = ("beta_from_xyz.",)
 
     def forward(self, input_xyz, input_dir=None, input_sun_dir=None, sigma_only=False):
         """(B,3), -, (B,3) -> (B,8) [rgb | sigma | sun_v | sky]  (snerf.py:190-243); sigma_only -> (B,1)."""
