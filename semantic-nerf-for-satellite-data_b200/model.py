@@ -35,7 +35,6 @@ class SnbMLP(torch.nn.Module):
         self.semantic_n_classes = n_classes          # read by the reference's inference(), rs_semantic.py:95
         self.number_of_outputs = 9 + n_classes       # satnerf.py:120
         self.n_out_kernel = 9 + n_classes            # columns of the packed tensor the kernels write
-        self.hidden_prefixes: Tuple[str, ...] = ()   # tensors of the flat buffer a model variant does not own (S-NeRF)
         self.t_embedding_dims = tau
         self.enc_ld = 64 if kind in (MODEL_SATNERF, MODEL_SNERF) else 128
         n = lib.snb_model_param_count(h)
@@ -74,8 +73,6 @@ class SnbMLP(torch.nn.Module):
         """Reference-named views into the flat parameter."""
         out = OrderedDict()
         for name, off, shape in self.table:
-            if name.startswith(self.hidden_prefixes) and self.hidden_prefixes:
-                continue
             n = int(torch.tensor(shape).prod())
             out[name] = self.flat.detach()[off:off + n].view(shape)  # detach(): shares the version counter
         return out
@@ -84,8 +81,6 @@ class SnbMLP(torch.nn.Module):
         g = self.flat.grad
         out = {}
         for name, off, shape in self.table:
-            if name.startswith(self.hidden_prefixes) and self.hidden_prefixes:
-                continue
             n = int(torch.tensor(shape).prod())
             out[name] = None if g is None else g[off:off + n].view(shape)
         return out
