@@ -196,7 +196,7 @@ def hbm_kernel_rooflines(lib, dev, peak_hbm, n=40960):
     enc_sc = torch.empty_like(enc)
     aux = torch.empty(P, 16, dtype=torch.bfloat16, device=dev)
     ts, ew = t_steps(S, dev), emb.weight.detach().contiguous()
-    k1_args = (ptr(rays), ptr(extras), None, 3, 0, ptr(ts), ptr(ew), 50, 4, None, None, None, None, 0, n, S, model.kind, 0,
+    k1_args = (ptr(rays), ptr(extras), None, 3, None, 0, ptr(ts), ptr(ew), 50, 4, None, None, None, None, 0, n, S, model.kind, 0,
                ptr(zv), ptr(enc), ptr(enc_sc), ptr(aux), None, stream())
 
     def k1x4():
@@ -213,14 +213,14 @@ def hbm_kernel_rooflines(lib, dev, peak_hbm, n=40960):
     rgb, depth = torch.empty(n, 3, device=dev), torch.empty(n, device=dev)
     w, T = torch.empty(n, S, device=dev), torch.empty(n, S, device=dev)
     sem, lab = torch.empty(n, C, device=dev), torch.empty(n, dtype=torch.int64, device=dev)
-    t = timed(lambda: check(lib.snb_composite_forward(ptr(out), ptr(z), n, S, n_out, C, ptr(rgb), ptr(depth), ptr(w), ptr(T),
+    t = timed(lambda: check(lib.snb_composite_forward(ptr(out), ptr(z), n, S, n_out, C, 0, ptr(rgb), ptr(depth), ptr(w), ptr(T),
                                                       ptr(sem), ptr(lab), stream()), "k3f"))
     b = n * (S * (4 * n_out + 4 + 8) + 12 + 4 + 4 * C + 8)
     res["k3_composite_forward"] = {"bound": "hbm", "achieved": b / t / 1e9, "peak": peak_hbm, "unit": "GB/s",
                                    "frac": b / t / 1e9 / peak_hbm, "bytes": b, "us": t * 1e6}
     g_rgb, g_d, g_w = torch.rand(n, 3, device=dev), torch.rand(n, device=dev), torch.rand(n, S, device=dev)
     g_sem, g_dir, g_out = torch.rand(n, C, device=dev), torch.rand(P, n_out, device=dev), torch.empty(P, n_out, device=dev)
-    t = timed(lambda: check(lib.snb_composite_backward(ptr(out), ptr(z), n, S, n_out, C, ptr(g_rgb), ptr(g_d), ptr(g_w), None,
+    t = timed(lambda: check(lib.snb_composite_backward(ptr(out), ptr(z), n, S, n_out, C, 0, ptr(g_rgb), ptr(g_d), ptr(g_w), None,
                                                        ptr(g_sem), ptr(g_dir), ptr(g_out), stream()), "k3b"))
     b = n * (S * (4 * n_out + 4 + 4 + 4 * n_out + 4 * n_out) + 12 + 4 + 4 * C)
     res["k3_composite_backward"] = {"bound": "hbm", "achieved": b / t / 1e9, "peak": peak_hbm, "unit": "GB/s",

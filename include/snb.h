@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SNB_VERSION 100
+#define SNB_VERSION 200
 
 enum {
   SNB_OK = 0,
@@ -77,8 +77,10 @@ int snb_device_sms(void);
  * ---------------------------------------------------------------------------------------------- */
 /*   t_steps (S) f32  linspace(0,1,S) exactly as the reference's host computes it (rendering.py:95);
  *          passed in so the stratification bins are bit-identical to the reference's. */
+/*   seed_dev: optional DEVICE uint64; when non-NULL the Philox key is read from it instead of `seed`, so a captured CUDA
+ *          graph of the training step draws fresh jitter on every replay. */
 int snb_sample_encode(const float* rays, const float* extras, const float* u, uint64_t seed,
-                      uint64_t ray_offset, const float* t_steps, const float* t_table, int vocab, int tau,
+                      const uint64_t* seed_dev, uint64_t ray_offset, const float* t_steps, const float* t_table, int vocab, int tau,
                       const float* sky_w1, const float* sky_b1, const float* sky_w2, const float* sky_b2,
                       int sky_hidden, int n_rays, int n_samples, int model_kind, int z_given,
                       float* z_vals, void* enc, void* enc_sc, void* aux, float* sky, void* stream);
@@ -123,9 +125,16 @@ int snb_mlp_forward(const snb_model* m, const void* packed, void* workspace, siz
 /* backward: g_out (P, n_out) f32 (gradient w.r.t. `out`) -> accumulates into grads (flat fp32, same
  * layout as params), g_aux (P,16) f32 [.., d t(tau) at cols 4..] (NULL to skip), g_sky (P or N,3) summed
  * by the caller.  Must follow snb_mlp_forward(train=1) on the same workspace. */
+/* bucket_events: NULL, or 3 cudaEvent_t (entries may be NULL).  The weight gradients complete in three buckets - heads,
+ * trunk layers 4-7, trunk layers 0-3 (flat ranges: snb_model_grad_buckets) - and event b is recorded on `stream` as soon
+ * as bucket b of `grads` is final, so a data-parallel caller can start that bucket's all-reduce on a side stream while
+ * the remaining weight-gradient GEMMs still run ("bucketed ... overlapped with K2 backward"). */
 int snb_mlp_backward(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
                      int64_t n_points, const void* enc, const void* aux, const float* out,
-                     const float* g_out, int head_mask, float* grads, float* g_aux, void* stream);
+                     const float* g_out, int head_mask, float* grads, float* g_aux, void* const* bucket_events,
+                     void* stream);
+/* flat element ranges [lo[b], hi[b]) of the three gradient buckets, in completion order */
+int snb_model_grad_buckets(const snb_model* m, int64_t* lo3, int64_t* hi3);
 
 /* NeRF only: aux (P, 32) bf16 = [1, sin/cos(2^k d)_{k<4} (24, commons.py:68-74 order), 0 x 7] from the per-ray view
  * directions dirs (N, 3) f32 (row stride `stride` floats), broadcast over the ray's n_samples samples.  Replaces
@@ -161,14 +170,17 @@ int snb_ray_param_backward(const snb_model* m, const float* params, const float*
  * replaces framework/util/rendering.py:4-34 (convert_sigmas) and the tails of `inference`
  * (satnerf.py:73-96, rs_semantic.py:81-126, _logit_to_label :131-136) and their autograd.
  * ---------------------------------------------------------------------------------------------- */
+/* flags: SNB_COMPOSITE_NO_CLAMP - the composited colour is NOT clamped to [0, 1]: NeRF's inference
+ * (baseline/models/nerf.py:73-86) returns the raw sum, SatNeRF / S-NeRF / semantic clamp (satnerf.py:79, rs_semantic.py:103) */
+enum { SNB_COMPOSITE_NO_CLAMP = 1 };
 int snb_composite_forward(const float* out, const float* z_vals, int n_rays, int n_samples, int n_out,
-                          int n_classes, float* rgb, float* depth, float* weights, float* transparency,
+                          int n_classes, int flags, float* rgb, float* depth, float* weights, float* transparency,
                           float* sem_logits, int64_t* sem_label, void* stream);
 
 /* any g_* may be NULL (treated as zero).  g_out_direct: gradient flowing straight into the
  * per-sample tensors (albedo/sun/sky/beta/sigmas views of `out`).  Writes g_out (P, n_out). */
 int snb_composite_backward(const float* out, const float* z_vals, int n_rays, int n_samples, int n_out,
-                           int n_classes, const float* g_rgb, const float* g_depth, const float* g_weights,
+                           int n_classes, int flags, const float* g_rgb, const float* g_depth, const float* g_weights,
                            const float* g_transparency, const float* g_sem_logits,
                            const float* g_out_direct, float* g_out, void* stream);
 
@@ -181,7 +193,12 @@ int snb_composite_backward(const float* out, const float* z_vals, int n_rays, in
  *   mode 1 (solar pass)  solar_correction terms 2 and 3 (baseline/components/loss.py:4-13)
  *   mode 2 (depth batch) DepthLoss (baseline/components/loss.py:30-47)
  * gt_rgb (N,3) f32; labels (N) i64 or NULL; depth_gt / depth_w (N) f32 (depth_w NULL = 1);
- * counts: device float[2] = {rays whose label != ignore_index, rays whose label == car_label} (NULL without labels);
+ * ray_mask (N) u8 or NULL: the reference's `semantic_sparsity_mask` (semantic/dataset/semantic_dataset.py:65,87, passed to
+ *   all semantic losses by semantic/components/training_step.py:58-88) - rays with mask 0 enter neither the cross-entropy nor
+ *   the car regularisation;
+ * counts: device float[>=2] = {rays in the cross-entropy mean, rays in the car-regularisation mean} as snb_label_counts
+ *   produces them (NULL without labels).  Data parallel: all-reduce (sum) them first and pass inv_n = 1 / GLOBAL rays, so the
+ *   per-rank terms add up to the global-batch loss and the summed gradients are the global-batch gradients;
  * g_out (P, n_out) f32 = d(sum of the terms)/d(out); loss_terms: device float[8], ACCUMULATED:
  * [0] colour [1] log-beta without its constant 3/2 [2] cross-entropy [3] car reg [4] sc term 2 [5] sc term 3 [6] depth. */
 typedef struct snb_loss_params {
@@ -192,17 +209,30 @@ typedef struct snb_loss_params {
   float lambda_c;
   int car_label;
   float lambda_sc, lambda_ds;
+  int flags;                 /* SNB_COMPOSITE_* */
 } snb_loss_params;
 int snb_composite_loss(const float* out, const float* z_vals, int n_rays, int n_samples, int n_out, int n_classes,
-                       const float* gt_rgb, const int64_t* labels, const float* depth_gt, const float* depth_w,
-                       const float* counts, const snb_loss_params* p, float* g_out, float* loss_terms, void* stream);
+                       const float* gt_rgb, const int64_t* labels, const uint8_t* ray_mask, const float* depth_gt,
+                       const float* depth_w, const float* counts, const snb_loss_params* p, float* g_out,
+                       float* loss_terms, void* stream);
+
+/* The masked-mean denominators of the semantic losses, with exactly the predicates snb_composite_loss applies (ACCUMULATED
+ * into counts, device float[3]; zero it first):
+ *   counts[0] += rays with mask != 0, label != ignore_index and 0 <= label < n_classes   (CrossEntropyLoss mean, loss.py:41-55)
+ *   counts[1] += rays with mask != 0 and label == car_label                               (SemanticCarRegLoss, loss.py:131-147)
+ *   counts[2] += labels outside [0, n_classes) that are not ignore_index - torch's CrossEntropyLoss raises for those; the
+ *                caller checks this entry where it can afford a device read (the ray table does it once per table). */
+int snb_label_counts(const int64_t* labels, const uint8_t* ray_mask, int n_rays, int n_classes, int ignore_index,
+                     int car_label, float* counts, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * optimiser step on the flat buffers (Adam, torch.optim.Adam semantics, weight_decay = 0:
  * baseline/pipelines/base_ray_pipeline.py:246-269).  grad_scale multiplies the gradient first
  * (1/world_size after the all-reduce). */
+/* step_dev: optional DEVICE int; when non-NULL the bias corrections use *step_dev instead of `step` (CUDA-graph replay). */
 int snb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
-                  float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+                  float lr, float beta1, float beta2, float eps, int step, const int* step_dev, float grad_scale,
+                  void* stream);
 
 /* tuning / test hook: run the MLP as ONE chained persistent kernel per pass (1, the default; inter-layer
  * activations are read back from L2) or as one GEMM launch per layer (0).  Both give the same results; the

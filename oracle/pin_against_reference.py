@@ -104,6 +104,93 @@ def case_inputs(name, kind, C, feat, n, s, sc, seed):
     return spec, params, emb, rays, extras, u
 
 
+from oracle.step_cases import CAR, STEP_CASES, oracle_step_loss, step_inputs  # noqa: E402
+
+
+def pin_losses_and_steps(write):
+    """SemanticLoss / SemanticUncertaintyLoss / SemanticCarRegLoss / DepthLoss and the whole training-step loss of the oracle
+    against the reference's loss modules driven in the order of RSSemanticTrainingStep.training_step
+    (semantic/components/training_step.py:12-99; that module itself needs torchmetrics, which is absent here)."""
+    from baseline.components.loss import DepthLoss, SatNerfLoss, SNerfLoss
+    from semantic.components.loss import SemanticCarRegLoss, SemanticLoss, SemanticUncertaintyLoss
+    for case in STEP_CASES:
+        name, C, n, s, seed, ignore_car, use_mask, car_reg, use_depth, beta_loss = case
+        spec, params, emb, batch, depth = step_inputs(*case)
+        cfgs, model, models, renderer = build_reference(spec, params, emb, s, 0.05)
+        z = O.sample_z(batch["rays"], s, batch["u"])
+        zd = O.sample_z(depth["rays"], s, depth["u"])
+        for prm in list(model.parameters()) + list(models["t"].parameters()):
+            prm.grad = None
+        res = ref_render(renderer, models, cfgs, batch["rays"], batch["extras"], z)
+        # --- training_step.py:22-28
+        loss, d = (SatNerfLoss if beta_loss else SNerfLoss)(lambda_sc=0.05)(res, batch["rgbs"])
+        ref_terms = {"color": loss.clone()}
+        # --- :31-49
+        if use_depth:
+            tmp = ref_render(renderer, models, cfgs, depth["rays"], depth["extras"], zd)
+            l_d, _ = DepthLoss(lambda_ds=1000.0)(tmp, torch.flatten(depth["depths"][:, 0]), torch.flatten(depth["weights"]))
+            loss = loss + l_d
+            ref_terms["ds"] = l_d
+        # --- :52-75 (use_beta_for_s = false)
+        mask = batch["semantic_sparsity_mask"] if use_mask else None
+        l_s, _ = SemanticLoss(0.04, CAR, ignore_car_index=ignore_car)(res, batch["semantic"], mask)
+        loss = loss + l_s
+        ref_terms["semantic"] = l_s
+        # --- :77-92
+        if car_reg:
+            l_c, _ = SemanticCarRegLoss(0.1, CAR)(res, batch["semantic"], mask)
+            loss = loss + l_c
+            ref_terms["car_reg"] = l_c
+        loss.backward()
+        p2 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        e2 = emb.clone().requires_grad_(True)
+        ours, terms, res2 = oracle_step_loss(O, p2, e2, spec, batch, depth, s, ignore_car, use_mask, car_reg, use_depth,
+                                             beta_loss)
+        ours.backward()
+        for k, v in ref_terms.items():
+            assert abs(terms[k].item() - v.item()) <= 2e-6 * max(1.0, abs(v.item())), (name, k, terms[k].item(), v.item())
+        assert abs(ours.item() - loss.item()) <= 2e-6 * max(1.0, abs(loss.item()))
+        num = da = db = 0.0
+        for k, prm in model.named_parameters():
+            ga, gb = prm.grad.flatten().double(), p2[k].grad.flatten().double()
+            num += float(ga @ gb); da += float(ga @ ga); db += float(gb @ gb)
+            assert (ga - gb).abs().max().item() <= 1e-4 * max(1e-6, ga.abs().max().item()) + 1e-9, (name, k)
+        cos = num / max(1e-300, (da * db) ** 0.5)
+        assert cos > 1 - 1e-9, (name, cos)
+        ge = models["t"].weight.grad
+        assert (ge - e2.grad).abs().max().item() <= 1e-5 * max(1.0, ge.abs().max().item())
+        # the uncertainty-weighted semantic loss (use_beta_for_s; loss.py:6-32,68-114), with and without detaching beta
+        with torch.no_grad():
+            for det in (False, True):
+                l_u, _ = SemanticUncertaintyLoss(0.04, CAR, detach_beta_for_s=det, ignore_car_index=ignore_car)(
+                    res, batch["semantic"], mask)
+                mine = O.semantic_uncertainty_loss(res2, batch["semantic"], 0.04, CAR if ignore_car else -100, mask, detach_beta=det)
+                assert abs(l_u.item() - mine.item()) <= 2e-6 * max(1.0, abs(l_u.item())), (name, det)
+            # every mask / ignore_index combination of the two plain semantic losses
+            for ig in (False, True):
+                for mk in (None, batch["semantic_sparsity_mask"]):
+                    a, _ = SemanticLoss(0.04, CAR, ignore_car_index=ig)(res, batch["semantic"], mk)
+                    b = O.semantic_loss(res2, batch["semantic"], 0.04, CAR if ig else -100, mk)
+                    assert abs(a.item() - b.item()) <= 2e-6, (name, ig, mk is None)
+                    if CAR < C:
+                        a, _ = SemanticCarRegLoss(0.1, CAR)(res, batch["semantic"], mk)
+                        b = O.car_reg_loss(res2, batch["semantic"], CAR, 0.1, mk)
+                        assert abs(a.item() - b.item()) <= 2e-6, (name, "car", mk is None)
+        print(f"{name}: step loss {loss.item():.6f} ({', '.join(f'{k} {v.item():.6f}' for k, v in ref_terms.items())}), "
+              f"grad cosine {cos:.12f}")
+        if write:
+            gold = {f"term_{k}": np.float64(v.item()) for k, v in ref_terms.items()}
+            gold["loss"] = np.float64(loss.item())
+            gold["grad_norms"] = np.array([prm.grad.norm().item() for _, prm in model.named_parameters()])
+            gold["grad_emb"] = ge.numpy()
+            # probes: the gradient of every tensor projected on a fixed random direction (checks direction, not only size)
+            rng = np.random.Generator(np.random.PCG64(99))
+            gold["grad_probes"] = np.array([float((prm.grad.double().flatten() *
+                                                   torch.from_numpy(rng.standard_normal(prm.numel()))).sum())
+                                            for _, prm in model.named_parameters()])
+            np.savez_compressed(os.path.join(REPO, "tests", "golden", f"{name}.npz"), **gold)
+
+
 def main(write=True):
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -195,6 +282,7 @@ def main(write=True):
             gold["model_forward"] = a.numpy()
             gold["grad_norms"] = np.array([prm.grad.norm().item() for _, prm in model.named_parameters()])
             np.savez_compressed(os.path.join(REPO, "tests", "golden", f"{name}.npz"), **gold)
+    pin_losses_and_steps(write)
     print("oracle pinned against reference; golden vectors written" if write else "oracle pinned")
 
 

@@ -36,6 +36,7 @@ __all__ = [
     "depth_loss",
     "semantic_loss",
     "car_reg_loss",
+    "semantic_uncertainty_loss",
     "psnr",
 ]
 
@@ -424,16 +425,48 @@ def depth_loss(res, depths, weights=1.0, lambda_ds=1000.0):
     return lambda_ds / 3.0 * torch.mean(weights * (res["depth_coarse"] - depths) ** 2)
 
 
-def semantic_loss(res, labels, lambda_s=0.04, ignore_index=-100):
-    """SemanticLoss, semantic/components/loss.py:35-65 (CE over the composited class scores)."""
-    return lambda_s * F.cross_entropy(res["semantic_logits_coarse"], labels, ignore_index=ignore_index)
+def _apply_mask(logits, labels, ignore_mask):
+    """`inputs[...][ignore_mask], targets[ignore_mask].squeeze()` of the reference losses (semantic/components/loss.py:52-55)."""
+    labels = labels.reshape(-1).long()
+    if ignore_mask is not None:
+        m = ignore_mask.reshape(-1).bool()
+        logits, labels = logits[m], labels[m]
+    return logits, labels
 
 
-def car_reg_loss(res, labels, car_label, lambda_c=0.1):
-    """SemanticCarRegLoss, semantic/components/loss.py:117-157."""
+def semantic_loss(res, labels, lambda_s=0.04, ignore_index=-100, ignore_mask=None):
+    """SemanticLoss, semantic/components/loss.py:35-65 (CE over the composited class scores; `ignore_mask` is the
+    dataset's semantic_sparsity_mask, semantic/dataset/semantic_dataset.py:65,87)."""
+    logits, labels = _apply_mask(res["semantic_logits_coarse"], labels, ignore_mask)
+    return lambda_s * F.cross_entropy(logits, labels, ignore_index=ignore_index)
+
+
+def car_reg_loss(res, labels, car_label, lambda_c=0.1, ignore_mask=None):
+    """SemanticCarRegLoss, semantic/components/loss.py:117-157.  NB: with no selected ray the reference's MSELoss of an
+    empty tensor is NaN; so is this."""
     unc = torch.sum(res["weights_coarse"].unsqueeze(-1) * res["beta_coarse"], -2)
-    sel = unc[labels == car_label]
+    sel_mask = labels.reshape(-1) == car_label
+    if ignore_mask is not None:
+        sel_mask = torch.logical_and(sel_mask, ignore_mask.reshape(-1).bool())
+    sel = unc[sel_mask]
     return lambda_c * F.mse_loss(torch.ones_like(sel), sel)
+
+
+def semantic_uncertainty_loss(res, labels, lambda_s=0.04, ignore_index=-100, ignore_mask=None, beta_min=0.05,
+                              detach_beta=False):
+    """SemanticUncertaintyLoss + uncertainty_aware_semantic_loss, semantic/components/loss.py:6-32,68-114: the (scalar)
+    cross-entropy mean divided by 2 beta^2 per ray, then averaged; beta is the composited uncertainty - of the separate
+    semantic head when the render returned `beta_semantic_coarse`, which also adds a second log-beta term."""
+    beta_in = res.get("beta_semantic_coarse", res["beta_coarse"])
+    if detach_beta:
+        beta_in = beta_in.detach().clone()
+    beta = torch.sum(res["weights_coarse"].unsqueeze(-1) * beta_in, -2) + beta_min
+    logits, lab = _apply_mask(res["semantic_logits_coarse"], labels, ignore_mask)
+    ce = F.cross_entropy(logits, lab, ignore_index=ignore_index)
+    loss = lambda_s * (ce / (2 * beta ** 2)).mean()
+    if "beta_semantic_coarse" in res:
+        loss = loss + lambda_s * (3 + torch.log(beta).mean()) / 2
+    return loss
 
 
 def psnr(a: torch.Tensor, b: torch.Tensor) -> float:

@@ -17,6 +17,7 @@ MODEL_SATNERF, MODEL_SEMANTIC, MODEL_NERF, MODEL_SNERF = 0, 1, 2, 3
 # the kind K1 (sample + encode) sees: raw xyz (SatNeRF, S-NeRF) or the 10-frequency positional encoding (semantic, NeRF)
 K1_KIND = {0: 0, 1: 1, 2: 1, 3: 0}
 HEADS_ALL, HEADS_SOLAR, HEADS_DEPTH = 63, 5, 1
+COMPOSITE_NO_CLAMP = 1
 EPI_SIN, EPI_LINEAR, EPI_MUL, EPI_HEADOUT, EPI_F32ROWS, EPI_WGRAD = range(6)
 
 _vp, _i, _i64, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
@@ -26,7 +27,7 @@ SIGNATURES = {
     "snb_version": (_i, []),
     "snb_last_error": (C.c_char_p, []),
     "snb_device_sms": (_i, []),
-    "snb_sample_encode": (_i, [_vp, _vp, _vp, _u64, _u64, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
+    "snb_sample_encode": (_i, [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
                                _vp, _vp, _vp, _vp, _vp, _vp]),
     "snb_encode_points": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "snb_model_create": (_i, [C.POINTER(_vp), _i, _i, _i]),
@@ -38,15 +39,17 @@ SIGNATURES = {
     "snb_model_pack": (_i, [_vp, _vp, _vp, _vp]),
     "snb_mlp_workspace_bytes": (_sz, [_vp, _i64, _i]),
     "snb_mlp_forward": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
-    "snb_mlp_backward": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "snb_mlp_backward": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "snb_model_grad_buckets": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "snb_nerf_aux": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "snb_mlp_fp32_workspace_bytes": (_sz, [_vp, _i64]),
     "snb_mlp_forward_fp32": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "snb_ray_param_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "snb_composite_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "snb_composite_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "snb_composite_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "snb_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _f, _vp]),
+    "snb_composite_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "snb_composite_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "snb_composite_loss": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "snb_label_counts": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "snb_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _vp, _f, _vp]),
     "snb_set_chained_mlp": (_i, [_i]),
     "snb_profile_begin": (None, [_i]),
     "snb_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(C.c_double)]),
@@ -58,7 +61,7 @@ SIGNATURES = {
 class LossParams(C.Structure):
     """snb_loss_params (include/snb.h)"""
     _fields_ = [("mode", _i), ("color", _i), ("beta_min", _f), ("inv_n", _f), ("lambda_s", _f), ("ignore_index", _i),
-                ("lambda_c", _f), ("car_label", _i), ("lambda_sc", _f), ("lambda_ds", _f)]
+                ("lambda_c", _f), ("car_label", _i), ("lambda_sc", _f), ("lambda_ds", _f), ("flags", _i)]
 
 
 _lib = None

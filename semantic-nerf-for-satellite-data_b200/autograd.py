@@ -33,7 +33,7 @@ def _f32c(t: Optional[torch.Tensor]):
 
 
 def encode_rays(model, emb_weight, rays, extras, n_samples, u=None, z=None, seed=0, ray_offset=0, want_sc=False,
-                want_sky=True):
+                want_sky=True, seed_dev=None):
     """K1: z_vals (N,S), enc / enc_sc (P, enc_ld) bf16, aux (P,16) bf16, sky (N,3).  No autograd here:
     the embedding gradient comes back through the MLP backward's aux gradient."""
     lib = _lib.load()
@@ -54,7 +54,7 @@ def encode_rays(model, emb_weight, rays, extras, n_samples, u=None, z=None, seed
         w1, b1, w2, b2 = model.sky_params()
         hidden = w1.shape[0]
     ew = _f32c(emb_weight.detach()) if emb_weight is not None else None
-    check(lib.snb_sample_encode(ptr(rays), ptr(extras), ptr(_f32c(u)), seed, ray_offset, ptr(t_steps(n_samples, dev)),
+    check(lib.snb_sample_encode(ptr(rays), ptr(extras), ptr(_f32c(u)), seed, ptr(seed_dev), ray_offset, ptr(t_steps(n_samples, dev)),
                                 ptr(ew), ew.shape[0] if ew is not None else 0, ew.shape[1] if ew is not None else 0,
                                 ptr(w1), ptr(b1), ptr(w2), ptr(b2), hidden, n, n_samples,
                                 _lib.K1_KIND[model.kind],
@@ -121,7 +121,7 @@ class MLPRays(torch.autograd.Function):
         want_emb = ctx.has_emb and head_mask == HEADS_ALL
         g_aux = torch.empty(P, 16, dtype=torch.float32, device=enc.device) if want_emb else None
         check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws), ws.numel(), P, ptr(enc), ptr(aux), ptr(out),
-                                   ptr(g_out), head_mask, ptr(g_flat), ptr(g_aux), stream()), "snb_mlp_backward")
+                                   ptr(g_out), head_mask, ptr(g_flat), ptr(g_aux), None, stream()), "snb_mlp_backward")
         g_emb = torch.zeros_like(emb_weight) if want_emb else None
         sky_arg = sky if (head_mask == HEADS_ALL and model.kind != _lib.MODEL_NERF) else None
         if sky_arg is not None or g_aux is not None:
@@ -176,7 +176,7 @@ class MLPPoints(torch.autograd.Function):
         g_flat = torch.zeros_like(flat)
         g_aux = torch.empty(P, 16, dtype=torch.float32, device=enc.device)
         check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws), ws.numel(), P, ptr(enc), ptr(aux), ptr(out),
-                                   ptr(g_out), HEADS_ALL, ptr(g_flat), ptr(g_aux), stream()), "snb_mlp_backward")
+                                   ptr(g_out), HEADS_ALL, ptr(g_flat), ptr(g_aux), None, stream()), "snb_mlp_backward")
         if model.kind == _lib.MODEL_NERF:   # no sky_color parameters, no embedding
             return g_flat, None, None, None, None, None
         extras = torch.cat([sun_d, torch.zeros(P, 1, device=sun_d.device)], 1).contiguous()
@@ -228,7 +228,7 @@ class Composite(torch.autograd.Function):
     semantic scores, label  (framework/util/rendering.py:4-34 + the tail of `inference`)."""
 
     @staticmethod
-    def forward(ctx, out, z_vals, n_classes):
+    def forward(ctx, out, z_vals, n_classes, flags=0):
         lib = _lib.load()
         out, z_vals = _f32c(out), _f32c(z_vals)
         n, s, n_out = out.shape
@@ -239,11 +239,11 @@ class Composite(torch.autograd.Function):
         transp = torch.empty(n, s, dtype=torch.float32, device=dev)
         sem = torch.empty(n, n_classes, dtype=torch.float32, device=dev)
         label = torch.empty(n, dtype=torch.int64, device=dev)
-        check(lib.snb_composite_forward(ptr(out), ptr(z_vals), n, s, n_out, n_classes, ptr(rgb), ptr(depth),
+        check(lib.snb_composite_forward(ptr(out), ptr(z_vals), n, s, n_out, n_classes, flags, ptr(rgb), ptr(depth),
                                         ptr(weights), ptr(transp), ptr(sem) if n_classes else None,
                                         ptr(label) if n_classes else None, stream()), "snb_composite_forward")
         ctx.save_for_backward(out, z_vals)
-        ctx.n_classes = n_classes
+        ctx.n_classes, ctx.flags = n_classes, flags
         ctx.mark_non_differentiable(label)
         return rgb, depth, weights, transp, sem, label
 
@@ -253,14 +253,42 @@ class Composite(torch.autograd.Function):
         out, z_vals = ctx.saved_tensors
         n, s, n_out = out.shape
         g_out = torch.empty_like(out)
-        check(lib.snb_composite_backward(ptr(out), ptr(z_vals), n, s, n_out, ctx.n_classes, ptr(_f32c(g_rgb)),
+        check(lib.snb_composite_backward(ptr(out), ptr(z_vals), n, s, n_out, ctx.n_classes, ctx.flags, ptr(_f32c(g_rgb)),
                                          ptr(_f32c(g_depth)), ptr(_f32c(g_w)), ptr(_f32c(g_t)),
                                          ptr(_f32c(g_sem)) if ctx.n_classes else None, None, ptr(g_out), stream()),
               "snb_composite_backward")
-        return g_out, None, None
+        return g_out, None, None, None
 
 
 LOSS_TERMS = ("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3", "ds")
+
+
+def label_counts(labels, ray_mask, n_classes: int, ignore_index: int, car_label: int, counts=None):
+    """snb_label_counts: the masked-mean denominators of the semantic losses as a device float[4]
+    [rays in the CE mean, rays in the car term, out-of-range labels, 0] - no host sync.  `labels` int64 (N),
+    `ray_mask` uint8 (N) or None."""
+    lib = _lib.load()
+    if counts is None:
+        counts = torch.zeros(4, dtype=torch.float32, device=labels.device)
+    check(lib.snb_label_counts(ptr(labels), ptr(ray_mask), labels.numel(), n_classes, ignore_index, car_label, ptr(counts),
+                               stream()), "snb_label_counts")
+    return counts
+
+
+def as_labels(semantic) -> torch.Tensor:
+    """labels as the kernels read them: contiguous int64 (N).  The reference's dataset yields uint8
+    (framework/util/img_utils.py::load_tensor_from_cls_geotiff; semantic/components/metrics.py:47)."""
+    lab = semantic.reshape(-1)
+    if lab.dtype != torch.int64:
+        lab = lab.to(torch.int64)
+    return lab.contiguous()
+
+
+def as_ray_mask(mask):
+    """semantic_sparsity_mask (bool, (N,) or (N,1)) -> contiguous uint8 (N), None stays None"""
+    if mask is None:
+        return None
+    return mask.reshape(-1).to(torch.uint8).contiguous()
 
 
 class CompositeLoss(torch.autograd.Function):
@@ -269,14 +297,14 @@ class CompositeLoss(torch.autograd.Function):
     `terms` (8,) is accumulated in place (logging; not differentiable)."""
 
     @staticmethod
-    def forward(ctx, out, z_vals, n_classes, params, gt_rgb, labels, depth_gt, depth_w, counts, terms):
+    def forward(ctx, out, z_vals, n_classes, params, gt_rgb, labels, depth_gt, depth_w, counts, terms, ray_mask=None):
         lib = _lib.load()
         out, z_vals = _f32c(out), _f32c(z_vals)
         n, s, n_out = out.shape
         g_out = torch.empty_like(out)
         mine = torch.zeros(8, dtype=torch.float32, device=out.device)
         check(lib.snb_composite_loss(ptr(out), ptr(z_vals), n, s, n_out, n_classes, ptr(_f32c(gt_rgb)), ptr(labels),
-                                     ptr(_f32c(depth_gt)), ptr(_f32c(depth_w)), ptr(counts), C.addressof(params),
+                                     ptr(ray_mask), ptr(_f32c(depth_gt)), ptr(_f32c(depth_w)), ptr(counts), C.addressof(params),
                                      ptr(g_out), ptr(mine), stream()), "snb_composite_loss")
         ctx.save_for_backward(g_out)
         if terms is not None:
@@ -289,4 +317,4 @@ class CompositeLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss):
         (g_out,) = ctx.saved_tensors
-        return g_out * g_loss, None, None, None, None, None, None, None, None, None
+        return g_out * g_loss, None, None, None, None, None, None, None, None, None, None

@@ -166,8 +166,8 @@ constexpr int K1_THREADS = 128;   // samples per block iteration
 template <int KIND>
 __global__ void __launch_bounds__(K1_THREADS)
 k1_sample_encode_kernel(const float* __restrict__ rays, const float* __restrict__ extras,
-                        const float* __restrict__ u, uint64_t seed, uint64_t ray_offset,
-                        const float* __restrict__ t_steps, const float* __restrict__ t_table, int vocab,
+                        const float* __restrict__ u, uint64_t seed, const uint64_t* __restrict__ seed_dev,
+                        uint64_t ray_offset, const float* __restrict__ t_steps, const float* __restrict__ t_table, int vocab,
                         int tau, int n_rays, int S, int z_given, float* __restrict__ z_vals,
                         __nv_bfloat16* __restrict__ enc, __nv_bfloat16* __restrict__ enc_sc,
                         __nv_bfloat16* __restrict__ aux) {
@@ -176,6 +176,7 @@ k1_sample_encode_kernel(const float* __restrict__ rays, const float* __restrict_
   __shared__ __align__(16) uint8_t stage_aux[K1_THREADS * 32];
   const long long P = (long long)n_rays * S;
   const int tid = threadIdx.x;
+  if (seed_dev != nullptr) seed = *seed_dev;   // a captured CUDA graph replays with a fresh key each step
   for (long long p0 = (long long)blockIdx.x * K1_THREADS; p0 < P; p0 += (long long)gridDim.x * K1_THREADS) {
     const long long p = p0 + tid;
     const int rows = (int)min((long long)K1_THREADS, P - p0);
@@ -304,7 +305,7 @@ static int sky_launch(const float* dirs, int stride, long long n, const float* w
 }  // namespace snb
 
 extern "C" int snb_sample_encode(const float* rays, const float* extras, const float* u, uint64_t seed,
-                                 uint64_t ray_offset, const float* t_steps, const float* t_table, int vocab,
+                                 const uint64_t* seed_dev, uint64_t ray_offset, const float* t_steps, const float* t_table, int vocab,
                                  int tau, const float* sky_w1, const float* sky_b1, const float* sky_w2,
                                  const float* sky_b2, int sky_hidden, int n_rays, int n_samples,
                                  int model_kind, int z_given, float* z_vals, void* enc, void* enc_sc,
@@ -326,11 +327,11 @@ extern "C" int snb_sample_encode(const float* rays, const float* extras, const f
   if (blocks > 148 * 64) blocks = 148 * 64;
   if (model_kind == SNB_MODEL_SEMANTIC)
     k1_sample_encode_kernel<SNB_MODEL_SEMANTIC><<<(int)blocks, K1_THREADS, 0, st>>>(
-        rays, extras, u, seed, ray_offset, t_steps, t_table, vocab, tau, n_rays, n_samples, z_given, z_vals,
+        rays, extras, u, seed, seed_dev, ray_offset, t_steps, t_table, vocab, tau, n_rays, n_samples, z_given, z_vals,
         (__nv_bfloat16*)enc, (__nv_bfloat16*)enc_sc, (__nv_bfloat16*)aux);
   else
     k1_sample_encode_kernel<SNB_MODEL_SATNERF><<<(int)blocks, K1_THREADS, 0, st>>>(
-        rays, extras, u, seed, ray_offset, t_steps, t_table, vocab, tau, n_rays, n_samples, z_given, z_vals,
+        rays, extras, u, seed, seed_dev, ray_offset, t_steps, t_table, vocab, tau, n_rays, n_samples, z_given, z_vals,
         (__nv_bfloat16*)enc, (__nv_bfloat16*)enc_sc, (__nv_bfloat16*)aux);
   if (int r = launch_status("k1_sample_encode_kernel")) return r;
   return sky_launch(extras, 4, n_rays, sky_w1, sky_b1, sky_w2, sky_b2, sky_hidden, sky, st);

@@ -67,6 +67,9 @@ struct snb_model {
   long long gl[8], gl4e, gf, gh1, gh1aux, gs2, gs4, ghot, gbl[8], gbf, gbs2, gbs4, gbho;
   long long gscratch_elems;
   std::vector<snb::PackJob> unpack_jobs;
+  // gradient buckets in the order the backward pass completes them: [0] heads (+ feats, sigma), [1] trunk layers 4-7,
+  // [2] trunk layers 0-3; flat element ranges [bucket_lo[b], bucket_hi[b])
+  int64_t bucket_lo[3], bucket_hi[3];
   int64_t find(const char* name) const {
     for (auto& t : tensors)
       if (t.name == name) return t.offset;
@@ -135,9 +138,10 @@ head_grad_kernel(const float* __restrict__ out, const float* __restrict__ g_out,
         d[j] = g[j] * 1.002f * s * (1.0f - s);
       }
     }
-    if (head_mask & SNB_HEAD_SIGMA) d[3] = g[3] * (1.0f - expf(-o[3]));  // softplus' = sigmoid(x) = 1 - exp(-softplus)
+    // softplus' = sigmoid(x) = 1 - exp(-softplus(x)); expm1 keeps full relative precision for the small outputs of empty space
+    if (head_mask & SNB_HEAD_SIGMA) d[3] = g[3] * -expm1f(-o[3]);
     if (head_mask & SNB_HEAD_SUN) d[4] = g[4] * o[4] * (1.0f - o[4]);
-    if (head_mask & SNB_HEAD_BETA) d[5] = g[8] * (1.0f - expf(-o[8]));
+    if (head_mask & SNB_HEAD_BETA) d[5] = g[8] * -expm1f(-o[8]);
     if (head_mask & SNB_HEAD_SEM) {
 #pragma unroll
       for (int c = 0; c < 10; ++c)
@@ -392,10 +396,21 @@ static void build_layout(snb_model* m) {
   if (!nerf) ujob(P("sun_v_net.6.bias"), 1, m->gbho + 4, 1, 1, 1, 0);
   if (has_beta) ujob(P("beta_from_xyz.2.bias"), 1, m->gbho + 5, 1, 1, 1, 0);
   if (sem) ujob(P("semantic_prediction.2.bias"), 1, m->gbho + 6, 1, C, 1, 0);
+  m->bucket_lo[2] = 0;
+  m->bucket_hi[2] = m->bucket_lo[1] = fcw(4);
+  m->bucket_hi[1] = m->bucket_lo[0] = P("sigma_from_xyz.0.weight");
+  m->bucket_hi[0] = m->n_params;
 }
 
-static int run_jobs(const std::vector<PackJob>& jobs, bool unpack, const float* src, void* dst_bf16, float* dst_f32,
-                    cudaStream_t st) {
+// lo/hi: only the jobs whose flat-parameter offset (unpack: dst) lies in [lo, hi)
+static int run_jobs(const std::vector<PackJob>& all, bool unpack, const float* src, void* dst_bf16, float* dst_f32,
+                    cudaStream_t st, long long lo = 0, long long hi = -1) {
+  std::vector<PackJob> sel;
+  if (hi >= 0) {
+    for (auto& j : all)
+      if (j.dst >= lo && j.dst < hi) sel.push_back(j);
+  }
+  const std::vector<PackJob>& jobs = hi >= 0 ? sel : all;
   for (size_t base = 0; base < jobs.size(); base += MAX_JOBS) {
     JobTable tab;
     tab.n = (int)std::min<size_t>(MAX_JOBS, jobs.size() - base);
@@ -790,6 +805,8 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
   SNB_CHECK_ARG(mask_supported(head_mask), SNB_ERR_UNSUPPORTED,
                 "mlp_forward: head_mask %d (supported: ALL=63, SOLAR=5, DEPTH=1)", head_mask);
   SNB_CHECK_ARG(head_mask == SNB_HEADS_DEPTH || aux != nullptr, SNB_ERR_INVALID, "mlp_forward: aux required");
+  SNB_CHECK_ARG(!(m->kind == SNB_MODEL_NERF && head_mask == SNB_HEADS_SOLAR), SNB_ERR_UNSUPPORTED,
+                "mlp_forward: NeRF has no sun head - there is no solar-correction pass (baseline/components/rendering.py:103-118)");
   SNB_CHECK_ARG((((uintptr_t)workspace | (uintptr_t)packed | (uintptr_t)enc) & 127) == 0, SNB_ERR_INVALID,
                 "mlp_forward: workspace/packed/enc must be 128-byte aligned");
   const Workspace w = layout_workspace(m, n_points, train);
@@ -878,9 +895,19 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
   }
 }
 
+extern "C" int snb_model_grad_buckets(const snb_model* m, int64_t* lo3, int64_t* hi3) {
+  SNB_CHECK_ARG(m && lo3 && hi3, SNB_ERR_INVALID, "grad_buckets: null argument");
+  for (int b = 0; b < 3; ++b) {
+    lo3[b] = m->bucket_lo[b];
+    hi3[b] = m->bucket_hi[b];
+  }
+  return 0;
+}
+
 extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
                                 int64_t n_points, const void* enc, const void* aux, const float* out,
-                                const float* g_out, int head_mask, float* grads, float* g_aux, void* stream) {
+                                const float* g_out, int head_mask, float* grads, float* g_aux, void* const* bucket_events,
+                                void* stream) {
   SNB_CHECK_ARG(m && packed && workspace && enc && aux && out && g_out && grads, SNB_ERR_INVALID,
                 "mlp_backward: null argument");
   SNB_CHECK_ARG(n_points > 0 && n_points < (1ll << 31), SNB_ERR_INVALID, "mlp_backward: n_points out of range");
@@ -961,6 +988,17 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
   if (!depth)
     if (int r = transpose_cols(aux, m->aux_ld, m->aux_ld, P, ws + w.auxT, ldt, st)) return r;
   if (int r = transpose_cols(enc, m->enc_ld, 64, P, ws + w.encT, ldt, st)) return r;
+  // the wgrads run heads first, then trunk layers 7..0; after each of the three gradient buckets (snb_model_grad_buckets)
+  // its packed gradients are added into `grads` and its event (if any) is recorded: a data-parallel caller starts that
+  // bucket's all-reduce on a side stream while the remaining wgrads still run
+  auto finish_bucket = [&](int b) -> int {
+    if (int r = run_plan(p, st)) return r;
+    p.g.clear();
+    p.epi.clear();
+    if (int r = run_jobs(m->unpack_jobs, true, gs, nullptr, grads, st, m->bucket_lo[b], m->bucket_hi[b])) return r;
+    if (bucket_events != nullptr && bucket_events[b] != nullptr) SNB_CUDA(cudaEventRecord((cudaEvent_t)bucket_events[b], st));
+    return 0;
+  };
   add_wgrad(p, F, 16, H(7), F, dpre, 16, P, gs + m->ghot, 16, sms);
   if (!depth && !nerf) add_wgrad(p, FL, 16, ws + w.s3, FL, dpre, 16, P, gs + m->ghot + (long long)F * 16, 16, sms);
   if (all) add_wgrad(p, hhw, 16, ws + w.hh, hhw, dpre, 16, P, gs + m->ghot + (long long)(F + FL) * 16, 16, sms);
@@ -985,6 +1023,7 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     }
     add_wgrad(p, F, F, ws + w.df, F, H(7), F, P, gs + m->gf, F, sms, gs + m->gbf);
   }
+  if (int r = finish_bucket(0)) return r;
   for (int i = LAYERS - 1; i >= 0; --i) {
     if (i == 0) {
       add_wgrad(p, F, 64, DY(0), F, enc, m->enc_ld, P, gs + m->gl[0], 64, sms, gs + m->gbl[0]);
@@ -993,9 +1032,10 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
       const WgradSide s_enc = {ws + w.encT, ldt, 64, gs + m->gl4e, 64, 64};
       add_wgrad(p, F, F, DY(i), F, H(i - 1), F, P, gs + m->gl[i], F, sms, gs + m->gbl[i], i == 4 ? &s_enc : nullptr);
     }
+    if (i == 4)
+      if (int r = finish_bucket(1)) return r;
   }
-  if (int r = run_plan(p, st)) return r;
-  return run_jobs(m->unpack_jobs, true, gs, nullptr, grads, st);
+  return finish_bucket(2);
 }
 
 // =====================================================================================================

@@ -63,7 +63,7 @@ __device__ __forceinline__ SampleVals sample_alpha(const float* zs, const float*
 template <int SPL, bool BWD>
 __global__ void __launch_bounds__(K3_WARPS * 32)
 k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, int n_rays, int S,
-                    int n_out, int C,
+                    int n_out, int C, int flags,
                     // forward outputs
                     float* __restrict__ rgb, float* __restrict__ depth, float* __restrict__ weights,
                     float* __restrict__ transparency, float* __restrict__ sem_logits,
@@ -190,9 +190,11 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
 
     if (!BWD) {
       if (lane == 0) {
-        rgb[ray * 3 + 0] = fminf(fmaxf(acc_r, 0.f), 1.f);  // rs_semantic.py:103
-        rgb[ray * 3 + 1] = fminf(fmaxf(acc_g, 0.f), 1.f);
-        rgb[ray * 3 + 2] = fminf(fmaxf(acc_b, 0.f), 1.f);
+        // rs_semantic.py:103 / satnerf.py:79 clamp the composited colour; NeRF's inference (nerf.py:73-86) does not
+        const bool clamp = !(flags & SNB_COMPOSITE_NO_CLAMP);
+        rgb[ray * 3 + 0] = clamp ? fminf(fmaxf(acc_r, 0.f), 1.f) : acc_r;
+        rgb[ray * 3 + 1] = clamp ? fminf(fmaxf(acc_g, 0.f), 1.f) : acc_g;
+        rgb[ray * 3 + 2] = clamp ? fminf(fmaxf(acc_b, 0.f), 1.f) : acc_b;
         depth[ray] = acc_d;
         if (C > 0) {
           int best = 0;
@@ -212,9 +214,11 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
       // clamp passes gradient where 0 <= raw <= 1
       float gr = g_rgb ? g_rgb[ray * 3 + 0] : 0.f, gg = g_rgb ? g_rgb[ray * 3 + 1] : 0.f,
             gb = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
-      if (!(acc_r >= 0.f && acc_r <= 1.f)) gr = 0.f;
-      if (!(acc_g >= 0.f && acc_g <= 1.f)) gg = 0.f;
-      if (!(acc_b >= 0.f && acc_b <= 1.f)) gb = 0.f;
+      if (!(flags & SNB_COMPOSITE_NO_CLAMP)) {
+        if (!(acc_r >= 0.f && acc_r <= 1.f)) gr = 0.f;
+        if (!(acc_g >= 0.f && acc_g <= 1.f)) gg = 0.f;
+        if (!(acc_b >= 0.f && acc_b <= 1.f)) gb = 0.f;
+      }
       const float gd = g_depth ? g_depth[ray] : 0.f;
       float gs[10];
 #pragma unroll
@@ -313,7 +317,7 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
 }
 
 template <bool BWD>
-static int launch_k3(const float* out, const float* z, int n_rays, int S, int n_out, int C, float* rgb,
+static int launch_k3(const float* out, const float* z, int n_rays, int S, int n_out, int C, int flags, float* rgb,
                      float* depth, float* weights, float* transp, float* sem, long long* label,
                      const float* g_rgb, const float* g_depth, const float* g_w, const float* g_t,
                      const float* g_sem, const float* g_direct, float* g_out, cudaStream_t st) {
@@ -332,7 +336,7 @@ static int launch_k3(const float* out, const float* z, int n_rays, int S, int n_
     SNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, K3_WARPS * 32, smem));     \
     if (resident < 1) resident = 1;                                                                   \
     if (blocks > sms * resident) blocks = sms * resident;                                             \
-    kfn<<<blocks, K3_WARPS * 32, smem, st>>>(out, z, n_rays, S, n_out, C, rgb, depth, weights, transp, sem, label, \
+    kfn<<<blocks, K3_WARPS * 32, smem, st>>>(out, z, n_rays, S, n_out, C, flags, rgb, depth, weights, transp, sem, label, \
                                              g_rgb, g_depth, g_w, g_t, g_sem, g_direct, g_out);       \
   } while (0)
   if (spl <= 1) K3_LAUNCH(1);
@@ -380,12 +384,14 @@ struct LossParams {
   float lambda_c;
   int car_label;
   float lambda_sc, lambda_ds;
+  int flags;
 };
 
 template <int SPL>
 __global__ void __launch_bounds__(K3_WARPS * 32)
 k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, int n_rays, int S, int n_out, int C,
-               const float* __restrict__ gt_rgb, const long long* __restrict__ labels, const float* __restrict__ depth_gt,
+               const float* __restrict__ gt_rgb, const long long* __restrict__ labels,
+               const unsigned char* __restrict__ ray_mask, const float* __restrict__ depth_gt,
                const float* __restrict__ depth_w, const float* __restrict__ counts, const LossParams lp,
                float* __restrict__ g_out, float* __restrict__ loss_terms) {
   extern __shared__ __align__(16) float smem[];
@@ -491,9 +497,11 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
       for (int c = 0; c < 10; ++c)
         if (c < C) acc_s[c] = warp_sum(acc_s[c]);
       // colour loss on the clamped colour (rs_semantic.py:103); the clamp passes gradient inside [0, 1] only
-      const float d0 = fminf(fmaxf(acc_r, 0.f), 1.f) - gt_rgb[ray * 3 + 0];
-      const float d1 = fminf(fmaxf(acc_g, 0.f), 1.f) - gt_rgb[ray * 3 + 1];
-      const float d2 = fminf(fmaxf(acc_b, 0.f), 1.f) - gt_rgb[ray * 3 + 2];
+      // (NeRF's inference does not clamp, nerf.py:73-86: SNB_COMPOSITE_NO_CLAMP)
+      const bool clamp = !(lp.flags & SNB_COMPOSITE_NO_CLAMP);
+      const float d0 = (clamp ? fminf(fmaxf(acc_r, 0.f), 1.f) : acc_r) - gt_rgb[ray * 3 + 0];
+      const float d1 = (clamp ? fminf(fmaxf(acc_g, 0.f), 1.f) : acc_g) - gt_rgb[ray * 3 + 1];
+      const float d2 = (clamp ? fminf(fmaxf(acc_b, 0.f), 1.f) : acc_b) - gt_rgb[ray * 3 + 2];
       const float sq = d0 * d0 + d1 * d1 + d2 * d2;
       const float k3n = lp.inv_n * (1.0f / 3.0f);
       if (lp.color == 1) {   // ((rgb - gt)^2 / (2 beta^2)).mean() + (3 + log(beta).mean()) / 2
@@ -511,10 +519,15 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
         gg = 2.0f * d1 * k3n;
         gb = 2.0f * d2 * k3n;
       }
-      if (!(acc_r >= 0.f && acc_r <= 1.f)) gr = 0.f;
-      if (!(acc_g >= 0.f && acc_g <= 1.f)) gg = 0.f;
-      if (!(acc_b >= 0.f && acc_b <= 1.f)) gb = 0.f;
-      if (labels != nullptr && C > 0) {
+      if (clamp) {
+        if (!(acc_r >= 0.f && acc_r <= 1.f)) gr = 0.f;
+        if (!(acc_g >= 0.f && acc_g <= 1.f)) gg = 0.f;
+        if (!(acc_b >= 0.f && acc_b <= 1.f)) gb = 0.f;
+      }
+      // semantic_sparsity_mask (semantic/components/training_step.py:58-88): rays outside it take part in neither the
+      // cross-entropy nor the car regularisation (loss.py:52-55,131-143); same predicate as snb_label_counts
+      const bool sem_on = labels != nullptr && C > 0 && (ray_mask == nullptr || ray_mask[ray] != 0);
+      if (sem_on) {
         const int y = (int)labels[ray];
         if (lp.lambda_s != 0.f && y != lp.ignore_index && y >= 0 && y < C) {
           float mx = acc_s[0];
@@ -639,7 +652,8 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
 }
 
 static int launch_k3_loss(const float* out, const float* z, int n_rays, int S, int n_out, int C, const float* gt_rgb,
-                          const long long* labels, const float* depth_gt, const float* depth_w, const float* counts,
+                          const long long* labels, const unsigned char* ray_mask, const float* depth_gt,
+                          const float* depth_w, const float* counts,
                           const LossParams& lp, float* g_out, float* loss_terms, cudaStream_t st) {
   const int spl = (S + 31) / 32;
   const size_t rw4 = (size_t)((S * n_out + 3) & ~3), s4 = (size_t)((S + 3) & ~3);
@@ -655,7 +669,7 @@ static int launch_k3_loss(const float* out, const float* z, int n_rays, int S, i
     SNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, K3_WARPS * 32, smem));     \
     if (resident < 1) resident = 1;                                                                   \
     if (blocks > sms * resident) blocks = sms * resident;                                             \
-    kfn<<<blocks, K3_WARPS * 32, smem, st>>>(out, z, n_rays, S, n_out, C, gt_rgb, labels, depth_gt, depth_w, counts, lp, \
+    kfn<<<blocks, K3_WARPS * 32, smem, st>>>(out, z, n_rays, S, n_out, C, gt_rgb, labels, ray_mask, depth_gt, depth_w, counts, lp, \
                                              g_out, loss_terms);                                      \
   } while (0)
   if (spl <= 1) K3L_LAUNCH(1);
@@ -668,10 +682,50 @@ static int launch_k3_loss(const float* out, const float* z, int n_rays, int S, i
 
 }  // namespace snb
 
+// counts[0] += rays that enter the cross-entropy mean, counts[1] += rays that enter the car regularisation,
+// counts[2] += labels outside [0, C) that are not ignore_index (PyTorch's CrossEntropyLoss raises for those; the caller checks)
+namespace snb {
+__global__ void __launch_bounds__(256)
+label_counts_kernel(const long long* __restrict__ labels, const unsigned char* __restrict__ ray_mask, int n, int C,
+                    int ignore_index, int car_label, float* __restrict__ counts) {
+  int valid = 0, car = 0, oor = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const long long y = labels[i];
+    const bool in = ray_mask == nullptr || ray_mask[i] != 0;
+    const bool range = y >= 0 && y < C;
+    if (in && y != ignore_index && range) ++valid;
+    if (in && y == car_label) ++car;
+    if (y != ignore_index && !range) ++oor;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    valid += __shfl_xor_sync(FULL, valid, d);
+    car += __shfl_xor_sync(FULL, car, d);
+    oor += __shfl_xor_sync(FULL, oor, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (valid) atomicAdd(counts + 0, (float)valid);
+    if (car) atomicAdd(counts + 1, (float)car);
+    if (oor) atomicAdd(counts + 2, (float)oor);
+  }
+}
+}  // namespace snb
+
+extern "C" int snb_label_counts(const int64_t* labels, const uint8_t* ray_mask, int n_rays, int n_classes, int ignore_index,
+                                int car_label, float* counts, void* stream) {
+  SNB_CHECK_ARG(labels && counts && n_rays >= 0 && n_classes >= 0, SNB_ERR_INVALID, "label_counts: bad argument");
+  if (n_rays == 0) return 0;
+  int blocks = (n_rays + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  snb::label_counts_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(labels), ray_mask, n_rays,
+                                                                    n_classes, ignore_index, car_label, counts);
+  return snb::launch_status("label_counts_kernel");
+}
+
 extern "C" int snb_composite_loss(const float* out, const float* z_vals, int n_rays, int n_samples, int n_out, int n_classes,
-                                  const float* gt_rgb, const int64_t* labels, const float* depth_gt, const float* depth_w,
-                                  const float* counts, const snb_loss_params* p, float* g_out, float* loss_terms,
-                                  void* stream) {
+                                  const float* gt_rgb, const int64_t* labels, const uint8_t* ray_mask, const float* depth_gt,
+                                  const float* depth_w, const float* counts, const snb_loss_params* p, float* g_out,
+                                  float* loss_terms, void* stream) {
   if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes)) return r;
   SNB_CHECK_ARG(p && g_out && loss_terms, SNB_ERR_INVALID, "composite_loss: null argument");
   SNB_CHECK_ARG(p->mode >= 0 && p->mode <= 2, SNB_ERR_INVALID, "composite_loss: mode %d", p->mode);
@@ -684,12 +738,13 @@ extern "C" int snb_composite_loss(const float* out, const float* z_vals, int n_r
   lp.mode = p->mode; lp.color = p->color; lp.beta_min = p->beta_min; lp.inv_n = p->inv_n; lp.lambda_s = p->lambda_s;
   lp.ignore_index = p->ignore_index; lp.lambda_c = p->lambda_c; lp.car_label = p->car_label; lp.lambda_sc = p->lambda_sc;
   lp.lambda_ds = p->lambda_ds;
+  lp.flags = p->flags;
   return snb::launch_k3_loss(out, z_vals, n_rays, n_samples, n_out, n_classes, gt_rgb, reinterpret_cast<const long long*>(labels),
-                             depth_gt, depth_w, counts, lp, g_out, loss_terms, (cudaStream_t)stream);
+                             ray_mask, depth_gt, depth_w, counts, lp, g_out, loss_terms, (cudaStream_t)stream);
 }
 
 extern "C" int snb_composite_forward(const float* out, const float* z_vals, int n_rays, int n_samples,
-                                     int n_out, int n_classes, float* rgb, float* depth, float* weights,
+                                     int n_out, int n_classes, int flags, float* rgb, float* depth, float* weights,
                                      float* transparency, float* sem_logits, int64_t* sem_label,
                                      void* stream) {
   if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes)) return r;
@@ -697,20 +752,20 @@ extern "C" int snb_composite_forward(const float* out, const float* z_vals, int 
   SNB_CHECK_ARG(n_classes == 0 || (sem_logits && sem_label), SNB_ERR_INVALID,
                 "composite_forward: semantic outputs required when n_classes > 0");
   if (n_rays == 0) return 0;
-  return snb::launch_k3<false>(out, z_vals, n_rays, n_samples, n_out, n_classes, rgb, depth, weights,
+  return snb::launch_k3<false>(out, z_vals, n_rays, n_samples, n_out, n_classes, flags, rgb, depth, weights,
                                transparency, sem_logits, reinterpret_cast<long long*>(sem_label), nullptr,
                                nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int snb_composite_backward(const float* out, const float* z_vals, int n_rays, int n_samples,
-                                      int n_out, int n_classes, const float* g_rgb, const float* g_depth,
+                                      int n_out, int n_classes, int flags, const float* g_rgb, const float* g_depth,
                                       const float* g_weights, const float* g_transparency,
                                       const float* g_sem_logits, const float* g_out_direct, float* g_out,
                                       void* stream) {
   if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes)) return r;
   SNB_CHECK_ARG(g_out, SNB_ERR_INVALID, "composite_backward: null g_out");
   if (n_rays == 0) return 0;
-  return snb::launch_k3<true>(out, z_vals, n_rays, n_samples, n_out, n_classes, nullptr, nullptr, nullptr,
+  return snb::launch_k3<true>(out, z_vals, n_rays, n_samples, n_out, n_classes, flags, nullptr, nullptr, nullptr,
                               nullptr, nullptr, nullptr, g_rgb, g_depth, g_weights, g_transparency,
                               g_sem_logits, g_out_direct, g_out, (cudaStream_t)stream);
 }

@@ -97,7 +97,13 @@ ray_param_bwd_kernel(const float* __restrict__ extras, const float* __restrict__
 // torch.optim.Adam (amsgrad=False, weight_decay=0, maximize=False)
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale) {
+            long long n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale,
+            const int* __restrict__ step_dev) {
+  if (step_dev != nullptr) {   // a captured CUDA graph replays with the step counter read from the device
+    const float t = (float)*step_dev;
+    bc1 = 1.0f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * gscale;
     const float mi = b1 * m[i] + (1.0f - b1) * gi;
@@ -145,16 +151,19 @@ extern "C" int snb_ray_param_backward(const snb_model* m, const float* params, c
 }
 
 extern "C" int snb_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                             float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+                             float beta1, float beta2, float eps, int step, const int* step_dev, float grad_scale,
+                             void* stream) {
   using namespace snb;
-  SNB_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, SNB_ERR_INVALID, "adam_step: bad argument");
+  SNB_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n >= 0 && (step >= 1 || step_dev != nullptr), SNB_ERR_INVALID,
+                "adam_step: bad argument");
+  if (step < 1) step = 1;
   if (n == 0) return 0;
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2 = 1.0f - powf(beta2, (float)step);
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                             bc1, sqrtf(bc2), grad_scale);
+                                                             bc1, sqrtf(bc2), grad_scale, step_dev);
   return launch_status("adam_kernel");
 }
 

@@ -66,6 +66,24 @@ class SNerfLoss(torch.nn.Module):
         return sum(d.values()), d
 
 
+class NerfLoss(torch.nn.Module):
+    """baseline/components/loss.py:97-110 (coarse network only: n_importance = 0)"""
+
+    def forward(self, inputs, targets):
+        d = {"coarse_color": torch.nn.functional.mse_loss(inputs["rgb_coarse"], targets)}
+        return sum(d.values()), d
+
+
+def _masked(logits, targets, ignore_mask):
+    """`inputs[...][ignore_mask], targets[ignore_mask].squeeze()` (semantic/components/loss.py:52-55); labels arrive as the
+    dataset delivers them - uint8, (N,1) (framework/util/img_utils.py::load_tensor_from_cls_geotiff)"""
+    tgt = targets.reshape(-1).long()
+    if ignore_mask is not None:
+        m = ignore_mask.reshape(-1).bool()
+        logits, tgt = logits[m], tgt[m]
+    return logits, tgt
+
+
 class SemanticLoss(torch.nn.Module):
     """semantic/components/loss.py:35-65"""
 
@@ -75,10 +93,30 @@ class SemanticLoss(torch.nn.Module):
         self.loss = torch.nn.CrossEntropyLoss(ignore_index=car_index if ignore_car_index else -100)
 
     def forward(self, inputs, targets, ignore_mask=None):
-        logits, tgt = inputs["semantic_logits_coarse"], targets.reshape(-1)
-        if ignore_mask is not None:
-            logits, tgt = logits[ignore_mask], tgt[ignore_mask]
+        logits, tgt = _masked(inputs["semantic_logits_coarse"], targets, ignore_mask)
         d = {"coarse_semantic": self.lambda_s * self.loss(logits, tgt)}
+        return sum(d.values()), d
+
+
+class SemanticUncertaintyLoss(torch.nn.Module):
+    """semantic/components/loss.py:6-32,68-114 (`use_beta_for_s`): the cross-entropy mean weighted per ray by 1 / (2 beta^2)
+    of the composited uncertainty - of the separate semantic uncertainty head when the render returned
+    `beta_semantic_coarse`, which also adds its own log-beta term."""
+
+    def __init__(self, lambda_s, car_index, detach_beta_for_s=False, ignore_car_index=False, beta_min=0.05):
+        super().__init__()
+        self.lambda_s, self.detach_beta_for_s, self.beta_min = lambda_s, detach_beta_for_s, beta_min
+        self.cross_entropy = torch.nn.CrossEntropyLoss(ignore_index=car_index if ignore_car_index else -100)
+
+    def forward(self, inputs, targets, ignore_mask=None):
+        beta_in = inputs.get("beta_semantic_coarse", inputs["beta_coarse"])
+        if self.detach_beta_for_s:
+            beta_in = beta_in.detach().clone()
+        beta = torch.sum(inputs["weights_coarse"].unsqueeze(-1) * beta_in, -2) + self.beta_min
+        logits, tgt = _masked(inputs["semantic_logits_coarse"], targets, ignore_mask)
+        d = {"coarse_semantic": self.lambda_s * (self.cross_entropy(logits, tgt) / (2 * beta ** 2)).mean()}
+        if "beta_semantic_coarse" in inputs:
+            d["coarse_semantic_logbeta"] = self.lambda_s * (3 + torch.log(beta).mean()) / 2
         return sum(d.values()), d
 
 
@@ -94,8 +132,9 @@ class SemanticCarRegLoss(torch.nn.Module):
         unc = torch.sum(inputs["weights_coarse"].unsqueeze(-1) * inputs["beta_coarse"], -2)
         mask = targets.reshape(-1) == self.car_label
         if ignore_mask is not None:
-            mask = mask & ignore_mask.reshape(-1)
-        # masked mean without a data-dependent shape (no host sync): mean over selected rays
+            mask = mask & ignore_mask.reshape(-1).bool()
+        # masked mean without a data-dependent shape (no host sync): mean over selected rays.  Deviation, on purpose: with NO
+        # selected ray the reference's MSELoss of an empty tensor is NaN (and poisons the step); this term is then 0.
         sq = (1.0 - unc.reshape(-1)) ** 2 * mask
         d = {"coarse_car_reg_loss": self.lambda_c * sq.sum() / mask.sum().clamp_min(1)}
         return sum(d.values()), d

@@ -21,9 +21,10 @@ from __future__ import annotations
 
 import torch
 
-from ._lib import HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, MODEL_SEMANTIC
+from ._lib import COMPOSITE_NO_CLAMP, HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, MODEL_SEMANTIC
 from . import _lib
-from .autograd import Composite, CompositeLoss, encode_rays, mlp_fp32, mlp_rays
+from .autograd import (Composite, CompositeLoss, as_labels, as_ray_mask, encode_rays, label_counts, mlp_fp32,
+                       mlp_rays)
 
 
 class B200Renderer:
@@ -49,7 +50,9 @@ class B200Renderer:
         nerf = getattr(model, "variant", None) == "nerf"   # NeRFRendering (baseline/components/rendering.py:103-118)
         # "solar_pass": False skips the solar-correction pass (its outputs feed only the training loss; an evaluation render
         # that wants rgb / depth / labels need not pay for it - the reference always runs it when sc_lambda > 0)
-        sc = cfgs.pipeline.sc_lambda > 0 and not depth_only and bool(opts.get("solar_pass", True)) and not nerf
+        # (nerf.toml has no sc_lambda at all: NeRF has no sun head and no solar-correction pass)
+        sc = getattr(cfgs.pipeline, "sc_lambda", 0.0) > 0 and not depth_only and bool(opts.get("solar_pass", True)) \
+            and not nerf
         if n == 0:   # an empty ray batch renders to empty tensors, as the reference's eager code does
             return self._empty_result(model, rays, S, sc)
         self._calls += 1
@@ -74,7 +77,8 @@ class B200Renderer:
                 out = mlp_fp32(model, xyz_main, sun_d, t_ray, sky, S, mask).view(n, S, -1)
         else:
             out = mlp_rays(model, emb, enc, aux, sky, extras, n, S, mask).view(n, S, -1)
-        rgb, depth, weights, transp, sem, label = Composite.apply(out, z, C)
+        # NeRF's inference returns the raw composited colour (nerf.py:73-86); the other models clamp it to [0, 1]
+        rgb, depth, weights, transp, sem, label = Composite.apply(out, z, C, COMPOSITE_NO_CLAMP if nerf else 0)
         result = {
             "rgb": rgb, "depth": depth, "weights": weights, "transparency": transp,
             "albedo": out[..., :3], "sun": out[..., 4:5], "sky": out[..., 5:8], "beta": out[..., 8:9],
@@ -104,41 +108,54 @@ class B200Renderer:
 
     def render_loss(self, models: dict, rays, extras, rgbs, semantic=None, *, color: str = "satnerf", lambda_s: float = 0.0,
                     ignore_index: int = -100, lambda_c: float = 0.0, car_label: int = -1, beta_min: float = 0.05,
-                    depth=None, depth_weights=None, lambda_ds: float = 0.0, render_options=None):
+                    depth=None, depth_weights=None, lambda_ds: float = 0.0, ignore_mask=None, global_rays=None,
+                    reduce_counts=None, render_options=None):
         """Training fast path: render + the losses that sit on the render outputs + their gradients
         with the compositing fused (snb_composite_loss), without materialising any per-sample output tensor.
         Equivalent to render_rays() followed by SNerfLoss / SatNerfLoss (color = "snerf" / "satnerf", with the solar
-        correction when cfgs.pipeline.sc_lambda > 0) [+ SemanticLoss + SemanticCarRegLoss when `semantic` labels are
-        given], or - with `depth` targets - to the depth-supervision pass + DepthLoss.  Returns (loss, terms) where
-        terms is a (8,) tensor in the order of autograd.LOSS_TERMS (the log-beta entry without its constant 3/2)."""
+        correction when cfgs.pipeline.sc_lambda > 0; NeRF: NerfLoss = color "snerf" without a solar pass) [+ SemanticLoss +
+        SemanticCarRegLoss when `semantic` labels are given, `ignore_mask` = the reference's semantic_sparsity_mask,
+        semantic/components/training_step.py:58-88], or - with `depth` targets - to the depth-supervision pass + DepthLoss.
+        Data parallel: `global_rays` = rays of the GLOBAL batch (the means of the reference losses run over it) and
+        `reduce_counts` = a callable that sum-all-reduces the masked-mean denominators in place; the per-rank losses then
+        add up to the single-process loss on the concatenated batch, and so do the gradients.
+        Returns (loss, terms) where terms is a (8,) tensor in the order of autograd.LOSS_TERMS (the log-beta entry without
+        its constant 3/2)."""
         opts = render_options or {}
         model = models["coarse"]
         emb = models["t"].weight if "t" in models else None
         n, S = rays.shape[0], self.N_samples
         depth_pass = depth is not None
-        sc = self.cfgs.pipeline.sc_lambda > 0 and not depth_pass
+        nerf = getattr(model, "variant", None) == "nerf"
+        sc_lambda = getattr(self.cfgs.pipeline, "sc_lambda", 0.0)
+        sc = sc_lambda > 0 and not depth_pass and not nerf
         self._calls += 1
         z, enc, enc_sc, aux, sky = encode_rays(model, emb, rays, extras, S, u=opts.get("u"), z=opts.get("z_vals"),
                                                seed=int(opts.get("seed", self._calls)),
                                                ray_offset=int(opts.get("ray_offset", 0)), want_sc=sc)
         C = model.semantic_n_classes
         terms = torch.zeros(8, dtype=torch.float32, device=rays.device)
+        inv_n = 1.0 / max(int(global_rays) if global_rays is not None else n, 1)
+        flags = COMPOSITE_NO_CLAMP if nerf else 0
         p = _lib.LossParams(mode=2 if depth_pass else 0, color=1 if color == "satnerf" else 0, beta_min=beta_min,
-                            inv_n=1.0 / max(n, 1), lambda_s=lambda_s, ignore_index=ignore_index, lambda_c=lambda_c,
-                            car_label=car_label, lambda_sc=self.cfgs.pipeline.sc_lambda, lambda_ds=lambda_ds)
-        counts = None
+                            inv_n=inv_n, lambda_s=lambda_s, ignore_index=ignore_index, lambda_c=lambda_c,
+                            car_label=car_label, lambda_sc=sc_lambda, lambda_ds=lambda_ds, flags=flags)
+        counts = mask = None
         if semantic is not None and not depth_pass:
-            lab = semantic.reshape(-1)
-            counts = torch.stack([(lab != ignore_index).sum(), (lab == car_label).sum()]).float()
-            semantic = lab.contiguous()
+            semantic = as_labels(semantic)          # the reference's dataset yields uint8 labels; the kernel reads int64
+            mask = as_ray_mask(ignore_mask)
+            counts = label_counts(semantic, mask, C, ignore_index, car_label)   # same predicates as the loss kernel
+            if reduce_counts is not None:
+                reduce_counts(counts)
         out = mlp_rays(model, emb, enc, aux, sky, extras, n, S, HEADS_DEPTH if depth_pass else HEADS_ALL).view(n, S, -1)
         loss = CompositeLoss.apply(out, z, 0 if depth_pass else C, p, rgbs, None if depth_pass else semantic, depth,
-                                   depth_weights, counts, terms)
+                                   depth_weights, counts, terms, mask)
         if sc:
-            p_sc = _lib.LossParams(mode=1, color=0, beta_min=beta_min, inv_n=1.0 / max(n, 1), lambda_s=0.0, ignore_index=-100,
-                                   lambda_c=0.0, car_label=-1, lambda_sc=self.cfgs.pipeline.sc_lambda, lambda_ds=0.0)
+            p_sc = _lib.LossParams(mode=1, color=0, beta_min=beta_min, inv_n=inv_n, lambda_s=0.0, ignore_index=-100,
+                                   lambda_c=0.0, car_label=-1, lambda_sc=sc_lambda, lambda_ds=0.0, flags=0)
             out_sc = mlp_rays(model, emb, enc_sc, aux, None, extras, n, S, HEADS_SOLAR).view(n, S, -1)
             loss = loss + CompositeLoss.apply(out_sc, z, 0, p_sc, None, None, None, None, None, terms)
+        self.last_counts = counts
         return loss, terms
 
     @staticmethod
@@ -173,5 +190,13 @@ class SNeRFB200Rendering(B200Renderer):
 
 
 class RSSemanticB200Rendering(B200Renderer):
+    """≙ semantic.components.rendering.RSSemanticRendering (rendering.py:14-16).  The reference's constructor takes a
+    replacement `inference` callable; here sampling, the MLP and the compositing are fused CUDA kernels, so there is no
+    per-stage hook to inject into - a non-None `inference` is refused instead of being silently ignored."""
+
     def __init__(self, cfgs, inference=None):
+        if inference is not None:
+            raise _lib.SnbError("RSSemanticB200Rendering does not accept a replacement `inference` callable: the B200 "
+                                "path runs sampling, MLP and compositing as fused kernels (use the reference's "
+                                "RSSemanticRendering for a custom inference function)")
         super().__init__(cfgs)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     lib = _lib.load()
-    assert lib.snb_version() == 100
+    assert lib.snb_version() == 200
     assert isinstance(lib.snb_last_error(), bytes)
 
 
@@ -53,12 +53,12 @@ def test_argument_validation_error_codes():
     assert lib.snb_model_create(C.byref(h), 1, 11, 1) == -2               # SNB_ERR_UNSUPPORTED (C > 10)
     assert b"n_classes" in lib.snb_last_error()
     # null pointers / S < 2 are rejected before any launch
-    assert lib.snb_composite_forward(None, None, 4, 64, 15, 6, None, None, None, None, None, None, None) == -1
+    assert lib.snb_composite_forward(None, None, 4, 64, 15, 6, 0, None, None, None, None, None, None, None) == -1
     one = C.c_void_p(16)
-    assert lib.snb_composite_forward(one, one, 4, 1, 15, 6, one, one, one, one, one, one, None) == -2
-    assert lib.snb_sample_encode(None, None, None, 0, 0, None, None, 0, 0, None, None, None, None, 0, 4, 64, 1, 0,
+    assert lib.snb_composite_forward(one, one, 4, 1, 15, 6, 0, one, one, one, one, one, one, None) == -2
+    assert lib.snb_sample_encode(None, None, None, 0, None, 0, None, None, 0, 0, None, None, None, None, 0, 4, 64, 1, 0,
                                  None, None, None, None, None, None) == -1
-    assert lib.snb_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
+    assert lib.snb_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 1, None, 1.0, None) == -1
 
 
 def test_python_wrappers_refuse_cpu_tensors():

@@ -225,7 +225,7 @@ def test_k3_rejects_degenerate_sample_counts():
     lib = _lib_or_fail()
     x = torch.zeros(64, device=DEV)
     # S = 1: the reference itself collapses to empty per-sample tensors (framework/util/rendering.py:13)
-    assert lib.snb_composite_forward(ptr(x), ptr(x), 4, 1, 15, 6, ptr(x), ptr(x), ptr(x), ptr(x), ptr(x), ptr(x),
+    assert lib.snb_composite_forward(ptr(x), ptr(x), 4, 1, 15, 6, 0, ptr(x), ptr(x), ptr(x), ptr(x), ptr(x), ptr(x),
                                      stream()) == -2
-    assert lib.snb_composite_forward(ptr(x), ptr(x), 0, 64, 15, 6, ptr(x), ptr(x), ptr(x), ptr(x), ptr(x), ptr(x),
+    assert lib.snb_composite_forward(ptr(x), ptr(x), 0, 64, 15, 6, 0, ptr(x), ptr(x), ptr(x), ptr(x), ptr(x), ptr(x),
                                      stream()) == 0     # empty batch is a no-op

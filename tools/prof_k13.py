@@ -58,7 +58,7 @@ for n in sizes:
     zv = torch.empty(n, S, device=dev); enc = torch.empty(P, model.enc_ld, dtype=torch.bfloat16, device=dev)
     enc_sc = torch.empty_like(enc); aux = torch.empty(P, 16, dtype=torch.bfloat16, device=dev)
     ts = t_steps(S, dev); ew = emb.weight.detach().contiguous()
-    k1_args = (ptr(rays), ptr(extras), None, 3, 0, ptr(ts), ptr(ew), 50, 4, None, None, None, None, 0, n, S, model.kind, 0,
+    k1_args = (ptr(rays), ptr(extras), None, 3, None, 0, ptr(ts), ptr(ew), 50, 4, None, None, None, None, 0, n, S, model.kind, 0,
                ptr(zv), ptr(enc), ptr(enc_sc), ptr(aux), None, stream())
 
     def k1x4():
@@ -73,14 +73,14 @@ for n in sizes:
     rgb = torch.empty(n, 3, device=dev); depth = torch.empty(n, device=dev)
     w = torch.empty(n, S, device=dev); T = torch.empty(n, S, device=dev)
     sem = torch.empty(n, C, device=dev); lab = torch.empty(n, dtype=torch.int64, device=dev)
-    t = timed(lambda: check(lib.snb_composite_forward(ptr(out), ptr(z), n, S, n_out, C, ptr(rgb), ptr(depth), ptr(w), ptr(T),
+    t = timed(lambda: check(lib.snb_composite_forward(ptr(out), ptr(z), n, S, n_out, C, 0, ptr(rgb), ptr(depth), ptr(w), ptr(T),
                                                       ptr(sem), ptr(lab), stream()), "k3f"))
     k3f = n * (S * (4 * n_out + 4 + 8) + 12 + 4 + 4 * C + 8)
     print(f"K3 composite forward n={n}:              {t * 1e6:8.1f} us  {k3f / t / 1e9:8.1f} GB/s  = {k3f / t / 1e9 / HBM:.3f} "
           f"of measured HBM peak ({k3f / 1e6:.1f} MB)")
     g_rgb = torch.rand(n, 3, device=dev); g_d = torch.rand(n, device=dev); g_w = torch.rand(n, S, device=dev)
     g_sem = torch.rand(n, C, device=dev); g_dir = torch.rand(P, n_out, device=dev); g_out = torch.empty(P, n_out, device=dev)
-    t = timed(lambda: check(lib.snb_composite_backward(ptr(out), ptr(z), n, S, n_out, C, ptr(g_rgb), ptr(g_d), ptr(g_w), None,
+    t = timed(lambda: check(lib.snb_composite_backward(ptr(out), ptr(z), n, S, n_out, C, 0, ptr(g_rgb), ptr(g_d), ptr(g_w), None,
                                                        ptr(g_sem), ptr(g_dir), ptr(g_out), stream()), "k3b"))
     k3b = n * (S * (4 * n_out + 4 + 4 + 4 * n_out + 4 * n_out) + 12 + 4 + 4 * C)
     print(f"K3 composite backward n={n}:             {t * 1e6:8.1f} us  {k3b / t / 1e9:8.1f} GB/s  = {k3b / t / 1e9 / HBM:.3f} "
