@@ -247,7 +247,7 @@ def run_gpu(args):
     B = args.batch
     cfgs = default_cfgs("semantic", n_samples=N_SAMPLES, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=0)
     tr = Trainer(cfgs, "semantic", N_CLASSES, device=dev, car_index=CAR_INDEX, world=world, rank=rank, seed=0,
-                 fused_loss=not args.module_losses)
+                 fused_loss=not args.module_losses, graph=args.graph)
     host = [make_batch(B, seed=100 * rank + i, pinned=True) for i in range(4)]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
 
@@ -301,8 +301,10 @@ def run_gpu(args):
     nprof = 4
     snb_dist.barrier()
     lib.snb_profile_begin(1)
+    use_graph, tr.use_graph = tr.use_graph, False     # per-launch event timing needs the launches to go through the host
     for i in range(nprof):
         step_resident(i)
+    tr.use_graph = use_graph
     gms, gl2, tl2, macs = C.c_double(), C.c_int64(), C.c_int64(), C.c_double()
     lib.snb_profile_end(C.byref(gms), C.byref(gl2), C.byref(tl2), C.byref(macs))
     snb_dist.barrier()
@@ -382,6 +384,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (single GPU)")
     ap.add_argument("--module-losses", action="store_true",
                     help="render_rays() + the reference-shaped loss modules instead of the fused K3 + loss kernel")
     args = ap.parse_args()

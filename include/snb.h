@@ -245,6 +245,10 @@ int snb_set_chained_mlp(int on);
  * returns the summed GEMM device time (ms), the number of GEMM launches, all launches, and the MACs
  * the GEMM launches executed (padded tile work, for reference next to the algorithmic count). */
 void snb_profile_begin(int time_gemms);
+/* the running launch counter, and a way to credit launches that did not pass through the host entry points: a step captured
+ * into a CUDA graph launches its kernels on every replay without calling them (the caller adds the captured count). */
+int64_t snb_profile_launch_count(void);
+void snb_profile_add_launches(int64_t n);
 int snb_profile_end(double* gemm_ms, int64_t* gemm_launches, int64_t* total_launches, double* gemm_macs);
 
 /* ------------------------------------------------------------------------------------------------

@@ -104,7 +104,7 @@ def case_inputs(name, kind, C, feat, n, s, sc, seed):
     return spec, params, emb, rays, extras, u
 
 
-from oracle.step_cases import CAR, STEP_CASES, oracle_step_loss, step_inputs  # noqa: E402
+from oracle.step_cases import BATCHED_CASE, BATCHED_CHUNK, CAR, STEP_CASES, oracle_step_loss, step_inputs  # noqa: E402
 
 
 def pin_losses_and_steps(write):
@@ -189,6 +189,65 @@ def pin_losses_and_steps(write):
                                                    torch.from_numpy(rng.standard_normal(prm.numel()))).sum())
                                             for _, prm in model.named_parameters()])
             np.savez_compressed(os.path.join(REPO, "tests", "golden", f"{name}.npz"), **gold)
+
+
+def _reference_method(path, cls, name):
+    """a method of a reference class whose MODULE does not import here (missing geo dependencies), compiled from the
+    reference's own source text - the function body that runs is the reference's, not a restatement"""
+    import ast
+    src = open(os.path.join(REF, path)).read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for fn in node.body:
+                if isinstance(fn, ast.FunctionDef) and fn.name == name:
+                    mod = ast.Module(body=[fn], type_ignores=[])
+                    ns = {"torch": torch, "np": np}
+                    exec(compile(mod, os.path.join(REF, path), "exec"), ns)
+                    return ns[name]
+    raise KeyError((path, cls, name))
+
+
+NORM = {"X_offset": 3.1e5, "Y_offset": 3.3e6, "Z_offset": -12.5, "X_scale": 310.0, "Y_scale": 287.5, "Z_scale": 64.0}
+
+
+def pin_batched_and_pointcloud(write):
+    """a11 / 8f rank 3: the reference's own `batched_inference` (eval/utils/util.py:13-42) over 2.5 chunks, then the
+    point-cloud chain of eval/extract_pointcloud.py:66-94 - get_xyz_from_nerf_prediction (satnerf_dataset.py:156-171) and
+    StandardNormalization.denormalize (normalization.py:50-79) - against the oracle's restatements."""
+    from eval.utils.util import batched_inference
+    from baseline.components.normalization import StandardNormalization
+    name, kind, C, feat, n, s, sc, seed = BATCHED_CASE
+    spec, params, emb, rays, extras, _ = case_inputs(*BATCHED_CASE)
+    cfgs, model, models, renderer = build_reference(spec, params, emb, s, sc)
+    cfgs.pipeline.render_chunk_size = BATCHED_CHUNK
+    torch.manual_seed(seed)
+    ref = batched_inference(cfgs, renderer, models, rays, extras)
+    torch.manual_seed(seed)   # the jitter the reference drew, chunk by chunk (rendering.py:109: torch.rand_like(z_vals))
+    u = torch.cat([torch.rand(min(BATCHED_CHUNK, n - i), s) for i in range(0, n, BATCHED_CHUNK)], 0)
+    with torch.no_grad():
+        ours = O.batched_inference(params, emb, spec, rays, extras, s, BATCHED_CHUNK, u=u, sc_lambda=sc)
+    for k, v in ref.items():
+        assert tuple(ours[k].shape) == tuple(v.shape), (k, ours[k].shape, v.shape)
+        if v.dtype.is_floating_point:
+            assert (ours[k] - v).abs().max().item() <= 2e-6, k
+        else:
+            assert torch.equal(ours[k], v), k
+    get_xyz = _reference_method("baseline/dataset/satnerf_dataset.py", "SatNeRFDataset", "get_xyz_from_nerf_prediction")
+    depth = ref["depth_coarse"]
+    xyz_n = get_xyz(None, rays, depth)
+    assert torch.equal(O.xyz_from_depth(rays, depth), xyz_n)
+    norm = object.__new__(StandardNormalization)
+    norm.norm_params = dict(NORM)
+    center, rng = norm.calculate_center_range()
+    xyz = norm.denormalize({"xyz": xyz_n.clone()})
+    assert torch.equal(O.denormalize(xyz_n.clone(), center.tolist(), float(rng)), xyz)
+    print(f"{name}: batched_inference over {n} rays in chunks of {BATCHED_CHUNK}: {len(ref)} keys ok; point cloud bit-exact")
+    if write:
+        gold = {k: ref[k].numpy() for k in ("rgb_coarse", "depth_coarse", "semantic_label_coarse", "weights_coarse",
+                                             "sun_sc_coarse")}
+        gold.update(u=u.numpy(), xyz_n=xyz_n.numpy(), xyz=xyz.numpy(), center=center.numpy(), scale=np.float64(float(rng)))
+        np.savez_compressed(os.path.join(REPO, "tests", "golden", f"{name}.npz"), **gold)
 
 
 def main(write=True):
@@ -283,6 +342,7 @@ def main(write=True):
             gold["grad_norms"] = np.array([prm.grad.norm().item() for _, prm in model.named_parameters()])
             np.savez_compressed(os.path.join(REPO, "tests", "golden", f"{name}.npz"), **gold)
     pin_losses_and_steps(write)
+    pin_batched_and_pointcloud(write)
     print("oracle pinned against reference; golden vectors written" if write else "oracle pinned")
 
 

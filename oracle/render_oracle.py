@@ -37,6 +37,9 @@ __all__ = [
     "semantic_loss",
     "car_reg_loss",
     "semantic_uncertainty_loss",
+    "batched_inference",
+    "xyz_from_depth",
+    "denormalize",
     "psnr",
 ]
 
@@ -467,6 +470,38 @@ def semantic_uncertainty_loss(res, labels, lambda_s=0.04, ignore_index=-100, ign
     if "beta_semantic_coarse" in res:
         loss = loss + lambda_s * (3 + torch.log(beta).mean()) / 2
     return loss
+
+
+# --------------------------------------------------------------------------------------
+# callers of the path: chunked whole-image inference and point-cloud extraction
+# --------------------------------------------------------------------------------------
+def batched_inference(p, emb, spec: ModelSpec, rays, extras, n_samples: int, chunk: int, u=None, sc_lambda: float = 0.05):
+    """eval/utils/util.py:13-42 (and BaseRayPipeline.forward, baseline/pipelines/base_ray_pipeline.py:34-54): render_rays on
+    consecutive chunks of `chunk` rays, every key concatenated along dim 0.  `u` (N,S) is the jitter the reference draws chunk
+    by chunk with torch.rand_like."""
+    res: Dict[str, list] = {}
+    for i in range(0, rays.shape[0], chunk):
+        r = render_rays(p, emb, spec, rays[i:i + chunk], extras[i:i + chunk], n_samples,
+                        u=None if u is None else u[i:i + chunk], sc_lambda=sc_lambda)
+        for k, v in r.items():
+            res.setdefault(k, []).append(v)
+    return {k: torch.cat(v, 0) for k, v in res.items()}
+
+
+def xyz_from_depth(rays: torch.Tensor, depth: torch.Tensor) -> torch.Tensor:
+    """SatNeRFDataset.get_xyz_from_nerf_prediction, baseline/dataset/satnerf_dataset.py:156-171: the ray end points at the
+    predicted depth, in float64 and normalised scene coordinates."""
+    rays, depth = rays.double(), depth.double()
+    return rays[:, 0:3] + rays[:, 3:6] * depth.view(-1, 1)
+
+
+def denormalize(xyz_n: torch.Tensor, center, scale: float) -> torch.Tensor:
+    """StandardNormalization.denormalize, baseline/components/normalization.py:50-58 (`range` = the largest of the three
+    scales, :60-79): xyz * range + center."""
+    out = xyz_n * scale
+    for c in range(3):
+        out[:, c] += center[c]
+    return out
 
 
 def psnr(a: torch.Tensor, b: torch.Tensor) -> float:

@@ -15,6 +15,9 @@ STEP_CASES = [
     ("step_sem_c5_early", 5, 32, 8, 22, False, False, False, True, False),
 ]
 CAR = 4
+# a11: the reference's batched_inference over 25 rays in chunks of 10 (2.5 chunks) - (name, kind, C, feat, n, S, sc_lambda, seed)
+BATCHED_CASE = ("batched_sem_c6_s8", "semantic", 6, 512, 25, 8, 0.05, 31)
+BATCHED_CHUNK = 10
 
 
 def step_inputs(name, C, n, s, seed, *_):
@@ -48,13 +51,17 @@ def step_inputs(name, C, n, s, seed, *_):
 def oracle_step_loss(O_, params, emb, spec, batch, depth, s, ignore_car, use_mask, car_reg, use_depth, beta_loss,
                      lambda_s=0.04, lambda_c=0.1, ds_lambda=1000.0, sc_lambda=0.05):
     """the oracle's restatement of RSSemanticTrainingStep.training_step (semantic/components/training_step.py:12-99)"""
-    res = O_.render_rays(params, emb, spec, batch["rays"], batch["extras"], s, u=batch["u"], sc_lambda=sc_lambda)
+    res = O_.render_rays(params, emb, spec, batch["rays"], batch["extras"], s, u=batch.get("u"), z=batch.get("z"),
+                         sc_lambda=sc_lambda)
     terms = {}
     terms["color"] = (O_.satnerf_loss if beta_loss else O_.snerf_loss)(res, batch["rgbs"], lambda_sc=sc_lambda)
     if use_depth:
-        tmp = O_.render_rays(params, emb, spec, depth["rays"], depth["extras"], s, u=depth["u"], sc_lambda=sc_lambda)
+        tmp = O_.render_rays(params, emb, spec, depth["rays"], depth["extras"], s, u=depth.get("u"), z=depth.get("z"),
+                             sc_lambda=sc_lambda)
         terms["ds"] = O_.depth_loss(tmp, torch.flatten(depth["depths"][:, 0]), torch.flatten(depth["weights"]), ds_lambda)
     mask = batch["semantic_sparsity_mask"] if use_mask else None
+    if spec.kind != "semantic":     # the baseline pipelines' step: colour (+ depth) only (baseline/components/training_step.py)
+        return sum(terms.values()), terms, res
     terms["semantic"] = O_.semantic_loss(res, batch["semantic"], lambda_s, CAR if ignore_car else -100, mask)
     if car_reg:
         terms["car_reg"] = O_.car_reg_loss(res, batch["semantic"], CAR, lambda_c, mask)

@@ -52,6 +52,8 @@ SIGNATURES = {
     "snb_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _vp, _f, _vp]),
     "snb_set_chained_mlp": (_i, [_i]),
     "snb_profile_begin": (None, [_i]),
+    "snb_profile_launch_count": (_i64, []),
+    "snb_profile_add_launches": (None, [_i64]),
     "snb_profile_end": (_i, [C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(C.c_double)]),
     "snb_gemm_bf16": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _vp, _vp, _i64, _vp, _vp, _f, _i, _vp]),
 }

@@ -119,6 +119,9 @@ extern "C" int snb_profile_end(double* gemm_ms, int64_t* gemm_launches, int64_t*
   return 0;
 }
 
+extern "C" int64_t snb_profile_launch_count(void) { return snb::g_launches; }
+extern "C" void snb_profile_add_launches(int64_t n) { snb::g_launches += n; }
+
 extern "C" int snb_version(void) { return SNB_VERSION; }
 extern "C" const char* snb_last_error(void) { return snb::g_err; }
 extern "C" int snb_device_sms(void) { return snb::num_sms(); }

@@ -17,15 +17,18 @@ import torch
 
 @torch.no_grad()
 def render_depth_rgb(renderer, models, rays: torch.Tensor, extras: torch.Tensor, chunk: int = 40960,
-                     want_rgb: bool = True, seed: int = 1, ray_offset: int = 0) -> Dict[str, torch.Tensor]:
-    """depth (N,) [and rgb (N,3)] of a whole view, chunked; `want_rgb=False` evaluates trunk + sigma only."""
+                     want_rgb: bool = True, seed: int = 1, ray_offset: int = 0, u=None) -> Dict[str, torch.Tensor]:
+    """depth (N,) [and rgb (N,3)] of a whole view, chunked; `want_rgb=False` evaluates trunk + sigma only.
+    The jitter is keyed on (seed, global ray index) - independent of the chunking; `u` (N,S) replaces it (parity tests)."""
     n = rays.shape[0]
     depth = torch.empty(n, dtype=torch.float32, device=rays.device)
     rgb = torch.empty(n, 3, dtype=torch.float32, device=rays.device) if want_rgb else None
     for i in range(0, n, chunk):
+        opts = {"seed": seed, "ray_offset": ray_offset + i, "heads": "all" if want_rgb else "depth", "solar_pass": False}
+        if u is not None:
+            opts["u"] = u[i:i + chunk]
         res = renderer.render_rays(models, rays[i:i + chunk], extras[i:i + chunk] if extras is not None else None,
-                                   render_options={"seed": seed, "ray_offset": ray_offset + i,
-                                                   "heads": "all" if want_rgb else "depth"})
+                                   render_options=opts)
         depth[i:i + chunk] = res["depth_coarse"]
         if want_rgb:
             rgb[i:i + chunk] = res["rgb_coarse"]
@@ -49,9 +52,9 @@ def denormalize(xyz_n: torch.Tensor, center: Sequence[float], scale: float) -> t
 
 @torch.no_grad()
 def extract_pointcloud(renderer, models, rays, extras, center: Optional[Sequence[float]] = None, scale: float = 1.0,
-                       chunk: int = 40960, want_rgb: bool = True) -> Dict[str, torch.Tensor]:
+                       chunk: int = 40960, want_rgb: bool = True, u=None) -> Dict[str, torch.Tensor]:
     """One view -> {"xyz_n" (N,3) f64 normalised, "xyz" (N,3) f64 scene coordinates, "depth", ["rgb"]}."""
-    res = render_depth_rgb(renderer, models, rays, extras, chunk, want_rgb)
+    res = render_depth_rgb(renderer, models, rays, extras, chunk, want_rgb, u=u)
     xyz_n = xyz_from_depth(rays, res["depth"])
     res["xyz_n"] = xyz_n
     res["xyz"] = denormalize(xyz_n, center, scale) if center is not None else xyz_n

@@ -63,7 +63,22 @@ class DeviceRayTable:
             if drop_last and hi - lo < batch_size:
                 return
             a, b = shard_range(hi - lo, rank, world)
-            yield self.gather(perm[lo + a:lo + b])
+            out = self.gather(perm[lo + a:lo + b])
+            # what a data-parallel step needs besides its shard: the size of the global batch (the loss means run over
+            # it) and the shard's position in it (the Philox key of a ray is its index in the global batch)
+            out["_global_rays"] = hi - lo
+            out["_ray_offset"] = a
+            yield out
+
+    def validate_labels(self, n_classes: int, key: str = "semantic", ignore_index: int = -100):
+        """Every label must be a class index in [0, n_classes) (or ignore_index): torch's CrossEntropyLoss raises for
+        anything else, the fused loss kernel would silently skip such rays.  One device read, once per table."""
+        from .autograd import as_labels, label_counts
+        c = label_counts(as_labels(self.tensors[key]), None, n_classes, ignore_index, -1)
+        bad = int(c[2].item())
+        if bad:
+            raise ValueError(f"{bad} labels of '{key}' lie outside [0, {n_classes}): class-count mismatch between the "
+                             f"dataset and the model's semantic_n_classes?")
 
     def steps_per_epoch(self, batch_size: int, drop_last: bool = False) -> int:
         return self.n_rays // batch_size if drop_last else -(-self.n_rays // batch_size)

@@ -3,24 +3,42 @@
 Mirrors the control flow of the reference's training steps
 (baseline/components/training_step.py:19-59, semantic/components/training_step.py:10-99):
 rgb batch -> render (main + solar-correction pass) -> colour loss (SNerfLoss before
-``first_beta_epoch``, SatNerfLoss after) -> optional depth-supervision batch -> semantic CE ->
-optional car regularisation -> backward -> Adam (lr 5e-4, base_ray_pipeline.py:246-269).
-Lightning is not part of the path (and not installed here): this is the plain loop the benchmark
-and the smoke test drive.  Data parallel: each rank renders its shard of the global batch; one
-bucketed gradient all-reduce per step (dist.py).
+``first_beta_epoch``, SatNerfLoss after) -> optional depth-supervision batch -> semantic CE (with the
+dataset's ``semantic_sparsity_mask``) -> optional car regularisation -> backward -> Adam (lr 5e-4,
+base_ray_pipeline.py:246-269).  Lightning is not part of the path (and not installed here): this is the
+plain loop the benchmark and the smoke test drive.
+
+Three ways to run the same step (same loss, same gradients - tests/test_gpu_step.py):
+  fused_loss=False            render_rays() + the reference-shaped loss modules under autograd (what a
+                              Lightning pipeline does with the plug-in renderer);
+  fused_loss=True, direct=False   renderer.render_loss() under autograd (K3 + losses fused);
+  fused_loss=True, direct=True    (default) the kernels of the step called back to back on persistent
+                              buffers - no autograd graph, no per-step allocation, one flat gradient
+                              buffer - optionally replayed as ONE CUDA graph (graph=True, single GPU).
+
+Data parallel: each rank renders its shard of the global batch; the loss means run over the
+GLOBAL batch (global ray count, all-reduced masked-mean denominators), so the per-rank gradients SUM to
+the single-process gradient of the concatenated batch; the flat gradient is all-reduced in three buckets
+(heads, late trunk, early trunk + embedding), each started on NCCL's stream as soon as the backward
+pass has finished it (events recorded inside snb_mlp_backward) while the remaining weight-gradient
+GEMMs still run.
 """
 from __future__ import annotations
 
+import ctypes as C
 import types
 from typing import Dict, Optional
 
 import torch
 
 from . import _lib, dist as snb_dist
-from ._lib import check, ptr, stream
-from .losses import DepthLoss, SatNerfLoss, SemanticCarRegLoss, SemanticLoss, SNerfLoss
+from ._lib import COMPOSITE_NO_CLAMP, HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, check, ptr, stream
+from .autograd import as_labels, as_ray_mask, t_steps
+from .losses import DepthLoss, NerfLoss, SatNerfLoss, SemanticCarRegLoss, SemanticLoss, SNerfLoss
 from .model import NeRFB200, RSSemanticNeRFB200, SatNeRFB200, ShadowNeRFB200
 from .renderer import B200Renderer
+
+EMB_PAD = 256   # floats reserved in front of the model parameters for the embedding table (vocab * tau <= 256)
 
 
 def default_cfgs(kind: str = "semantic", n_samples: int = 64, sc_lambda: float = 0.05, **over):
@@ -37,9 +55,46 @@ def default_cfgs(kind: str = "semantic", n_samples: int = 64, sc_lambda: float =
     return types.SimpleNamespace(pipeline=types.SimpleNamespace(**p))
 
 
+class _PassBuffers:
+    """Persistent device buffers of one ray batch size for the direct step (K1 outputs, the MLP training workspaces of the
+    main and the solar-correction pass, packed head outputs and their gradients).  ~25 KB per sample and pass."""
+
+    def __init__(self, model, n: int, S: int, dev, want_sc: bool, has_emb: bool, depth_only: bool):
+        lib = _lib.load()
+        P = n * S
+        f32 = dict(dtype=torch.float32, device=dev)
+        bf16 = dict(dtype=torch.bfloat16, device=dev)
+        nerf = model.kind == _lib.MODEL_NERF
+        self.n, self.P = n, P
+        self.rays = torch.empty(n, 8, **f32)
+        self.extras = torch.empty(n, 4, **f32)
+        self.z = torch.empty(n, S, **f32)
+        self.enc = torch.empty(P, model.enc_ld, **bf16)
+        self.enc_sc = torch.empty(P, model.enc_ld, **bf16) if want_sc else None
+        self.aux = torch.empty(P, 16, **bf16)
+        self.aux32 = torch.empty(P, 32, **bf16) if nerf else None
+        self.sky = None if (nerf or depth_only) else torch.empty(n, 3, **f32)
+        nbytes = lib.snb_mlp_workspace_bytes(model._h, P, 1)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.ws_sc = torch.empty(nbytes, dtype=torch.uint8, device=dev) if want_sc else None
+        n_out = model.n_out_kernel
+        self.out = torch.empty(P, n_out, **f32)
+        self.g_out = torch.empty(P, n_out, **f32)
+        self.out_sc = torch.empty(P, n_out, **f32) if want_sc else None
+        self.g_out_sc = torch.empty(P, n_out, **f32) if want_sc else None
+        self.g_aux = torch.empty(P, 16, **f32) if (has_emb and not depth_only) else None
+        # targets (static addresses, so the step can be replayed as a CUDA graph)
+        self.rgbs = torch.empty(n, 3, **f32)
+        self.labels = torch.empty(n, dtype=torch.int64, device=dev)
+        self.mask = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.depths = torch.empty(n, **f32)
+        self.dweights = torch.empty(n, **f32)
+
+
 class Trainer:
     def __init__(self, cfgs, kind: str = "semantic", n_classes: int = 6, device="cuda", car_index: int = 4,
-                 world: int = 1, rank: int = 0, seed: int = 0, fused_loss: bool = True):
+                 world: int = 1, rank: int = 0, seed: int = 0, fused_loss: bool = True, direct: bool = True,
+                 graph: bool = False):
         p = cfgs.pipeline
         self.cfgs, self.kind, self.device, self.world, self.rank = cfgs, kind, torch.device(device), world, rank
         torch.manual_seed(seed)  # identical initial replicas on every rank
@@ -55,118 +110,386 @@ class Trainer:
         self.models = {"coarse": model.to(self.device)}
         if kind not in ("snerf", "nerf"):
             self.models["t"] = torch.nn.Embedding(p.t_embedding_vocab, p.t_embedding_tau).to(self.device)
+        emb = self.models.get("t")
+        # ONE flat buffer [embedding table (padded) | model parameters] for parameters, gradients and Adam moments: the
+        # optimiser is one launch, and the embedding gradient rides the last all-reduce bucket instead of its own collective
+        self.n_emb = emb.weight.numel() if emb is not None else 0
+        if self.n_emb > EMB_PAD:
+            raise _lib.SnbError(f"embedding table of {self.n_emb} floats exceeds the {EMB_PAD} reserved")
+        n_params = model.flat.numel()
+        self.pbuf = torch.zeros(EMB_PAD + n_params, dtype=torch.float32, device=self.device)
+        self.pbuf[EMB_PAD:].copy_(model.flat.data)
+        model.flat.data = self.pbuf[EMB_PAD:]
+        if emb is not None:
+            self.pbuf[:self.n_emb].copy_(emb.weight.data.reshape(-1))
+            emb.weight.data = self.pbuf[:self.n_emb].view_as(emb.weight)
+        self.gbuf = torch.zeros_like(self.pbuf)
+        self.exp_avg = torch.zeros_like(self.pbuf)
+        self.exp_avg_sq = torch.zeros_like(self.pbuf)
         self.renderer = B200Renderer(cfgs)
-        self.loss = SatNerfLoss(lambda_sc=p.sc_lambda)
-        self.loss_without_beta = SNerfLoss(lambda_sc=p.sc_lambda)
+        nerf = kind == "nerf"
+        sc_lambda = 0.0 if nerf else getattr(p, "sc_lambda", 0.0)
+        self.loss = SatNerfLoss(lambda_sc=sc_lambda)
+        # NeRF: NerfLoss = plain MSE, no solar term (baseline/pipelines/nerf.py:23-24; nerf.toml has no sc_lambda)
+        self.loss_without_beta = NerfLoss() if nerf else SNerfLoss(lambda_sc=sc_lambda)
         self.depth_loss = DepthLoss(lambda_ds=p.ds_lambda)
         self.car_index = car_index
         if kind == "semantic":
             self.semantic_loss = SemanticLoss(p.lambda_s, car_index, ignore_car_index=p.ignore_car_index)
             self.car_reg_loss = SemanticCarRegLoss(p.lambda_c, car_index) if p.use_car_reg_loss else None
         self.lr, self.betas, self.eps = p.learnrate, (0.9, 0.999), 1e-8
-        flat = model.flat
-        self.exp_avg = torch.zeros_like(flat.data)
-        self.exp_avg_sq = torch.zeros_like(flat.data)
-        self.emb_opt = torch.optim.Adam(self.models["t"].parameters(), lr=self.lr) if "t" in self.models else None
         self.step_idx = 0
-        # fused_loss: compositing + the loss modules + their backward in one kernel per pass (renderer.render_loss,
-        # SURVEY 8f rank 1); False runs render_rays() + the reference-shaped loss modules (what a Lightning pipeline does)
+        # fused_loss: compositing + the loss modules + their backward in one kernel per pass; False runs
+        # render_rays() + the reference-shaped loss modules (what a Lightning pipeline does)
         self.fused_loss = fused_loss
-        self.reducer = snb_dist.GradAllReducer(snb_dist.bucket_ranges(model.table, flat.numel(), 3))
+        self.direct = direct and fused_loss
+        self.use_graph = bool(graph) and self.direct and world == 1
+        # gradient buckets in completion order (snb_model_grad_buckets), as ranges of gbuf; the last one also carries the
+        # embedding gradient
+        lo, hi = (C.c_int64 * 3)(), (C.c_int64 * 3)()
+        check(_lib.load().snb_model_grad_buckets(model._h, lo, hi), "snb_model_grad_buckets")
+        self.buckets = [(EMB_PAD + lo[b], EMB_PAD + hi[b]) for b in range(3)]
+        self.buckets[2] = (0, self.buckets[2][1])
+        self._bufs: Dict[tuple, _PassBuffers] = {}
+        self._graphs: Dict[tuple, tuple] = {}
+        self._events = None
+        self._side = None
+        self._counts = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._terms = torch.zeros(8, dtype=torch.float32, device=self.device)
+        self._seed_dev = torch.zeros(2, dtype=torch.int64, device=self.device)    # [rgb batch key, depth batch key]
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.last_loss_terms = self._terms
+        self.last_loss_dict = {}
+
+    # -- gradient views for code that reads .grad (tests, a user's own optimiser) -----------------------------
+    def _bind_grads(self):
+        model, emb = self.models["coarse"], self.models.get("t")
+        model.flat.grad = self.gbuf[EMB_PAD:]
+        if emb is not None:
+            emb.weight.grad = self.gbuf[:self.n_emb].view_as(emb.weight)
 
     # -- one step ---------------------------------------------------------------------------------------
     def training_step(self, batch: Dict[str, torch.Tensor], epoch: int = 2, depth_batch: Optional[dict] = None,
-                      ray_offset: int = 0) -> torch.Tensor:
-        p = self.cfgs.pipeline
-        model, emb = self.models["coarse"], self.models.get("t")
+                      ray_offset: Optional[int] = None, global_rays: Optional[int] = None,
+                      global_depth_rays: Optional[int] = None, depth_ray_offset: Optional[int] = None) -> torch.Tensor:
+        """`batch`: rays (n,8), extras (n,4), rgbs (n,3) [, semantic (n,) or (n,1) any integer dtype,
+        semantic_sparsity_mask (n,) bool].  Data parallel: `batch` is this rank's shard, `global_rays` the size of the
+        global batch (default world * n) and `ray_offset` the shard's first ray index in it (the Philox key of a ray is its
+        index in the global batch; default rank * n); likewise `global_depth_rays` / `depth_ray_offset` for the depth batch."""
         self.step_idx += 1
-        opts = {"seed": self.step_idx, "ray_offset": ray_offset}
-        if self.fused_loss:
-            return self._fused_step(batch, epoch, depth_batch, opts)
-        results = self.renderer.render_rays(self.models, batch["rays"], batch["extras"], epoch=epoch, render_options=opts)
-        if epoch < p.first_beta_epoch or self.kind in ("snerf", "nerf"):
-            loss, loss_dict = self.loss_without_beta(results, batch["rgbs"])
-        else:
-            loss, loss_dict = self.loss(results, batch["rgbs"])
+        n = batch["rays"].shape[0]
+        if ray_offset is None:
+            ray_offset = batch.get("_ray_offset", self.rank * n)
+        if global_rays is None:
+            global_rays = batch.get("_global_rays", self.world * n)
         if depth_batch is not None:
-            tmp = self.renderer.render_rays(self.models, depth_batch["rays"], depth_batch["extras"], epoch=epoch,
-                                            render_options={"seed": self.step_idx + (1 << 20), "heads": "depth"})
-            w = 1.0 if p.ds_noweights else depth_batch["weights"].flatten()
-            l_d, d = self.depth_loss(tmp, depth_batch["depths"].flatten(), w)
-            loss = loss + l_d
-            loss_dict.update(d)
-        if self.kind == "semantic":
-            l_s, d = self.semantic_loss(results, batch["semantic"])
-            loss = loss + l_s
-            loss_dict.update(d)
-            if self.car_reg_loss is not None and epoch >= p.car_reg_loss_start:
-                l_c, d = self.car_reg_loss(results, batch["semantic"])
-                loss = loss + l_c
-                loss_dict.update(d)
-        model.flat.grad = None
-        if emb is not None:
-            emb.weight.grad = None
-        loss.backward()
-        self.optimizer_step()
-        self.last_loss_dict = loss_dict
-        return loss.detach()
+            nd = depth_batch["rays"].shape[0]
+            if global_depth_rays is None:
+                global_depth_rays = depth_batch.get("_global_rays", self.world * nd)
+            if depth_ray_offset is None:
+                depth_ray_offset = depth_batch.get("_ray_offset", self.rank * nd)
+        offs = (int(ray_offset), int(depth_ray_offset or 0))
+        if self.direct:
+            return self._direct_step(batch, epoch, depth_batch, offs, int(global_rays), global_depth_rays)
+        return self._autograd_step(batch, epoch, depth_batch, offs, int(global_rays), global_depth_rays)
 
-    def _fused_step(self, batch, epoch, depth_batch, opts):
-        """the same step through renderer.render_loss: same loss value and gradients, no per-sample output tensors"""
+    @staticmethod
+    def _depths(depth_batch):
+        dd = depth_batch["depths"]            # semantic/components/training_step.py:39: torch.flatten(depths[:, 0])
+        return (dd[:, 0] if dd.dim() == 2 else dd).flatten()
+
+    def _loss_config(self, epoch):
         p = self.cfgs.pipeline
-        model, emb = self.models["coarse"], self.models.get("t")
         sem = self.kind == "semantic"
         car = sem and self.car_reg_loss is not None and epoch >= p.car_reg_loss_start
-        loss, terms = self.renderer.render_loss(
-            self.models, batch["rays"], batch["extras"], batch["rgbs"], batch["semantic"] if sem else None,
-            color="snerf" if (epoch < p.first_beta_epoch or self.kind in ("snerf", "nerf")) else "satnerf",
-            lambda_s=p.lambda_s if sem else 0.0, ignore_index=self.car_index if (sem and p.ignore_car_index) else -100,
-            lambda_c=p.lambda_c if car else 0.0, car_label=self.car_index, render_options=opts)
-        if depth_batch is not None:
-            w = None if p.ds_noweights else depth_batch["weights"].flatten()
-            l_d, t_d = self.renderer.render_loss(self.models, depth_batch["rays"], depth_batch["extras"], None,
-                                                 depth=depth_batch["depths"].flatten(), depth_weights=w, lambda_ds=p.ds_lambda,
-                                                 render_options={"seed": self.step_idx + (1 << 20)})
-            loss, terms = loss + l_d, terms + t_d
-        model.flat.grad = None
-        if emb is not None:
-            emb.weight.grad = None
-        loss.backward()
-        self.optimizer_step()
-        self.last_loss_terms = terms          # device tensor, order of autograd.LOSS_TERMS (no host sync here)
+        color = "snerf" if (epoch < p.first_beta_epoch or self.kind in ("snerf", "nerf")) else "satnerf"
+        return sem, car, color
+
+    def _reduce_counts(self, counts):
+        if self.world > 1:
+            torch.distributed.all_reduce(counts)
+
+    def _autograd_step(self, batch, epoch, depth_batch, offs, global_rays, global_depth_rays):
+        p = self.cfgs.pipeline
+        sem, car, color = self._loss_config(epoch)
+        opts = {"seed": self.step_idx, "ray_offset": offs[0]}
+        mask = batch.get("semantic_sparsity_mask")
+        self.gbuf.zero_()
+        self._bind_grads()
+        if self.fused_loss:
+            loss, terms = self.renderer.render_loss(
+                self.models, batch["rays"], batch["extras"], batch["rgbs"], batch["semantic"] if sem else None,
+                color=color, lambda_s=p.lambda_s if sem else 0.0,
+                ignore_index=self.car_index if (sem and p.ignore_car_index) else -100,
+                lambda_c=p.lambda_c if car else 0.0, car_label=self.car_index, ignore_mask=mask, global_rays=global_rays,
+                reduce_counts=self._reduce_counts, render_options=opts)
+            if depth_batch is not None:
+                w = None if p.ds_noweights else depth_batch["weights"].flatten()
+                l_d, t_d = self.renderer.render_loss(self.models, depth_batch["rays"], depth_batch["extras"], None,
+                                                     depth=self._depths(depth_batch), depth_weights=w,
+                                                     lambda_ds=p.ds_lambda, global_rays=global_depth_rays,
+                                                     render_options={"seed": self.step_idx + (1 << 20),
+                                                                     "ray_offset": offs[1]})
+                loss, terms = loss + l_d, terms + t_d
+            self.last_loss_terms = terms          # device tensor, order of autograd.LOSS_TERMS (no host sync here)
+        else:
+            if self.world > 1:
+                raise _lib.SnbError("the module-loss path takes per-rank means; data-parallel training uses fused_loss=True "
+                                    "(global-batch means)")
+            results = self.renderer.render_rays(self.models, batch["rays"], batch["extras"], epoch=epoch, render_options=opts)
+            loss, loss_dict = (self.loss_without_beta if color == "snerf" else self.loss)(results, batch["rgbs"])
+            if depth_batch is not None:
+                tmp = self.renderer.render_rays(self.models, depth_batch["rays"], depth_batch["extras"], epoch=epoch,
+                                                render_options={"seed": self.step_idx + (1 << 20), "heads": "depth",
+                                                                "ray_offset": offs[1]})
+                w = 1.0 if p.ds_noweights else depth_batch["weights"].flatten()
+                l_d, d = self.depth_loss(tmp, self._depths(depth_batch), w)
+                loss = loss + l_d
+                loss_dict.update(d)
+            if sem:
+                l_s, d = self.semantic_loss(results, batch["semantic"], mask)
+                loss = loss + l_s
+                loss_dict.update(d)
+                if car:
+                    l_c, d = self.car_reg_loss(results, batch["semantic"], mask)
+                    loss = loss + l_c
+                    loss_dict.update(d)
+            self.last_loss_dict = loss_dict
+        loss.backward()    # accumulates in place into the bound views of gbuf
+        self._all_reduce_and_step(None)
         return loss.detach()
 
-    def optimizer_step(self):
-        model, emb = self.models["coarse"], self.models.get("t")
-        g = model.flat.grad
-        if self.world > 1:
-            self.reducer.launch(g)
-            if emb is not None:
-                torch.distributed.all_reduce(emb.weight.grad)
-                emb.weight.grad.mul_(1.0 / self.world)
-            self.reducer.wait()
+    # -- the direct step: the kernels of the step back to back on persistent buffers ----------------------------
+    def _buffers(self, tag: str, n: int, depth_only: bool) -> _PassBuffers:
+        key = (tag, n)
+        if key not in self._bufs:
+            for k in [k for k in self._bufs if k[0] == tag]:
+                del self._bufs[k]                 # one live batch size per role: a changed size replaces its buffers
+                self._graphs.clear()
+            model = self.models["coarse"]
+            sc = (not depth_only) and self.kind != "nerf" and getattr(self.cfgs.pipeline, "sc_lambda", 0.0) > 0
+            self._bufs[key] = _PassBuffers(model, n, self.cfgs.pipeline.n_samples, self.device, sc, "t" in self.models,
+                                           depth_only)
+        return self._bufs[key]
+
+    @staticmethod
+    def _stage(dst: torch.Tensor, src: torch.Tensor):
+        dst.copy_(src.reshape(dst.shape), non_blocking=True)
+
+    def _direct_step(self, batch, epoch, depth_batch, ray_offset, global_rays, global_depth_rays):
+        # ray_offset: (rgb batch, depth batch)
+        p = self.cfgs.pipeline
+        sem, car, color = self._loss_config(epoch)
+        n = batch["rays"].shape[0]
+        b = self._buffers("rgb", n, False)
+        self._stage(b.rays, batch["rays"])
+        self._stage(b.extras, batch["extras"])
+        self._stage(b.rgbs, batch["rgbs"])
+        has_mask = False
+        if sem:
+            self._stage(b.labels, batch["semantic"])          # any integer dtype (the dataset's uint8) -> int64
+            m = batch.get("semantic_sparsity_mask")
+            has_mask = m is not None
+            if has_mask:
+                self._stage(b.mask, m)
+        d = None
+        if depth_batch is not None:
+            d = self._buffers("depth", depth_batch["rays"].shape[0], True)
+            self._stage(d.rays, depth_batch["rays"])
+            self._stage(d.extras, depth_batch["extras"])
+            dd = depth_batch["depths"]
+            self._stage(d.depths, dd[:, 0] if dd.dim() == 2 else dd)     # training_step.py:39: depths[:, 0]
+            if not p.ds_noweights:
+                self._stage(d.dweights, depth_batch["weights"])
+        self._seed_dev[0].fill_(self.step_idx)
+        self._seed_dev[1].fill_(self.step_idx + (1 << 20))
+        self._step_dev.fill_(self.step_idx)
+        cfg = (n, d.n if d is not None else 0, color, car, has_mask, ray_offset, global_rays, global_depth_rays)
+        if self.use_graph:
+            entry = self._graphs.get(cfg)
+            if entry is None:
+                # first call of a configuration runs eagerly (lazy one-time CUDA attribute calls, allocator warm-up) ...
+                self._graphs[cfg] = ("warm",)
+                self._run_direct(b, d, sem, car, color, has_mask, ray_offset, global_rays, global_depth_rays)
+            elif entry[0] == "warm":
+                # ... the second is captured (and the capture replayed, since capturing does not execute)
+                lib = _lib.load()
+                g = torch.cuda.CUDAGraph()
+                l0 = lib.snb_profile_launch_count()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._run_direct(b, d, sem, car, color, has_mask, ray_offset, global_rays, global_depth_rays)
+                captured = lib.snb_profile_launch_count() - l0
+                lib.snb_profile_add_launches(-captured)            # captured, not yet executed
+                self._graphs[cfg] = entry = ("graph", g, captured, self._loss_out)
+            if entry is not None and entry[0] == "graph":
+                entry[1].replay()
+                _lib.load().snb_profile_add_launches(entry[2])
+                self._loss_out = entry[3]
+        else:
+            self._run_direct(b, d, sem, car, color, has_mask, ray_offset, global_rays, global_depth_rays)
+        self._bind_grads()
+        self.last_loss_terms = self._terms
+        return self._loss_out
+
+    def _run_direct(self, b, d, sem, car, color, has_mask, ray_offset, global_rays, global_depth_rays):
+        """K1 -> MLP forward (main, solar) -> K3 + losses (gradients of the packed rows) -> MLP backward (solar, main) ->
+        ray-parameter gradients -> [depth batch the same way] -> all-reduce -> Adam -> re-pack.  Every buffer is persistent."""
         lib = _lib.load()
-        check(lib.snb_adam_step(ptr(model.flat.data), ptr(g), ptr(self.exp_avg), ptr(self.exp_avg_sq), g.numel(),
-                                self.lr, self.betas[0], self.betas[1], self.eps, self.step_idx, 1.0 / self.world,
+        p = self.cfgs.pipeline
+        model, emb = self.models["coarse"], self.models.get("t")
+        S = p.n_samples
+        st = stream()
+        nerf = model.kind == _lib.MODEL_NERF
+        sc_lambda = 0.0 if nerf else getattr(p, "sc_lambda", 0.0)
+        Cn = model.semantic_n_classes
+        n_out = model.n_out_kernel
+        ew = emb.weight.detach() if emb is not None else None
+        vocab, tau = (ew.shape if ew is not None else (0, 0))
+        if nerf:
+            sw = (None, None, None, None)
+            hidden = 0
+        else:
+            sw = model.sky_params()
+            hidden = sw[0].shape[0]
+        gflat = self.gbuf[EMB_PAD:]
+        g_emb = self.gbuf[:self.n_emb] if emb is not None else None
+        ts = t_steps(S, self.device)
+        self._terms.zero_()
+        self.gbuf.zero_()
+        packed = model.packed()
+        if self._events is None and self.world > 1:
+            self._events = [torch.cuda.Event() for _ in range(3)]
+            for e in self._events:
+                e.record()                      # creates the underlying cudaEvent_t
+            self._side = torch.cuda.Stream(device=self.device)
+        ev_arr = None
+
+        def encode(buf, seed_slot, want_sc, want_sky):
+            check(lib.snb_sample_encode(ptr(buf.rays), ptr(buf.extras), None, 0, self._seed_dev[seed_slot:].data_ptr(),
+                                        ray_offset[seed_slot],
+                                        ptr(ts), ptr(ew), vocab, tau, ptr(sw[0]), ptr(sw[1]), ptr(sw[2]), ptr(sw[3]),
+                                        hidden, buf.n, S, _lib.K1_KIND[model.kind], 0, ptr(buf.z), ptr(buf.enc),
+                                        ptr(buf.enc_sc) if want_sc else None, ptr(buf.aux),
+                                        ptr(buf.sky) if want_sky else None, st), "snb_sample_encode")
+            if nerf:
+                check(lib.snb_nerf_aux(buf.rays[:, 3:6].data_ptr(), 8, buf.n, S, ptr(buf.aux32), st), "snb_nerf_aux")
+
+        def forward(buf, ws, enc, sky, mask, out):
+            aux = buf.aux32 if nerf else buf.aux
+            check(lib.snb_mlp_forward(model._h, ptr(packed), ptr(ws), ws.numel(), buf.P, ptr(enc), ptr(aux), ptr(sky), S, mask, 1,
+                                      ptr(out), st), "snb_mlp_forward")
+
+        def backward(buf, ws, enc, out, g_out, mask, g_aux, events):
+            aux = buf.aux32 if nerf else buf.aux
+            check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws), ws.numel(), buf.P, ptr(enc), ptr(aux), ptr(out),
+                                       ptr(g_out), mask, ptr(gflat), ptr(g_aux), events, st), "snb_mlp_backward")
+
+        # ---- rgb batch ---------------------------------------------------------------------------------------
+        sc = sc_lambda > 0
+        encode(b, 0, sc, not nerf)
+        counts = None
+        work = None
+        if sem:
+            counts = self._counts
+            counts.zero_()
+            check(lib.snb_label_counts(ptr(b.labels), ptr(b.mask) if has_mask else None, b.n, Cn,
+                                       self.car_index if p.ignore_car_index else -100, self.car_index, ptr(counts), st),
+                  "snb_label_counts")
+            if self.world > 1:   # global masked-mean denominators; overlaps the forward passes
+                work = torch.distributed.all_reduce(counts, async_op=True)
+        forward(b, b.ws, b.enc, b.sky, HEADS_ALL, b.out)
+        if sc:
+            forward(b, b.ws_sc, b.enc_sc, None, HEADS_SOLAR, b.out_sc)
+        if work is not None:
+            work.wait()
+        inv_n = 1.0 / max(global_rays, 1)
+        lp = _lib.LossParams(mode=0, color=1 if color == "satnerf" else 0, beta_min=0.05, inv_n=inv_n,
+                             lambda_s=p.lambda_s if sem else 0.0,
+                             ignore_index=self.car_index if (sem and p.ignore_car_index) else -100,
+                             lambda_c=p.lambda_c if car else 0.0, car_label=self.car_index, lambda_sc=sc_lambda,
+                             lambda_ds=0.0, flags=COMPOSITE_NO_CLAMP if nerf else 0)
+        check(lib.snb_composite_loss(ptr(b.out), ptr(b.z), b.n, S, n_out, Cn, ptr(b.rgbs), ptr(b.labels) if sem else None,
+                                     ptr(b.mask) if (sem and has_mask) else None, None, None, ptr(counts), C.byref(lp),
+                                     ptr(b.g_out), ptr(self._terms), st), "snb_composite_loss")
+        if sc:
+            lp_sc = _lib.LossParams(mode=1, color=0, beta_min=0.05, inv_n=inv_n, lambda_s=0.0, ignore_index=-100, lambda_c=0.0,
+                                    car_label=-1, lambda_sc=sc_lambda, lambda_ds=0.0, flags=0)
+            check(lib.snb_composite_loss(ptr(b.out_sc), ptr(b.z), b.n, S, n_out, 0, None, None, None, None, None, None,
+                                         C.byref(lp_sc), ptr(b.g_out_sc), ptr(self._terms), st), "snb_composite_loss")
+        # ---- depth-supervision batch (semantic/components/training_step.py:31-49): trunk + sigma only ---------------
+        if d is not None:
+            encode(d, 1, False, False)
+            forward(d, d.ws, d.enc, None, HEADS_DEPTH, d.out)
+            lp_d = _lib.LossParams(mode=2, color=0, beta_min=0.05, inv_n=1.0 / max(int(global_depth_rays), 1), lambda_s=0.0,
+                                   ignore_index=-100, lambda_c=0.0, car_label=-1, lambda_sc=0.0, lambda_ds=p.ds_lambda, flags=0)
+            check(lib.snb_composite_loss(ptr(d.out), ptr(d.z), d.n, S, n_out, 0, None, None, None, ptr(d.depths),
+                                         None if p.ds_noweights else ptr(d.dweights), None, C.byref(lp_d), ptr(d.g_out),
+                                         ptr(self._terms), st), "snb_composite_loss")
+            backward(d, d.ws, d.enc, d.out, d.g_out, HEADS_DEPTH, None, None)
+        # ---- backward of the rgb batch: sky_color gradients first (they belong to the first bucket), solar pass, main pass
+        if not nerf:
+            check(lib.snb_ray_param_backward(model._h, ptr(model.flat.detach()), ptr(b.extras), ptr(b.sky), ptr(b.g_out), None,
+                                             b.n, S, n_out, 0, 1, ptr(gflat), None, st), "snb_ray_param_backward")
+        if sc:
+            backward(b, b.ws_sc, b.enc_sc, b.out_sc, b.g_out_sc, HEADS_SOLAR, None, None)
+        if self.world > 1:
+            ev_arr = (C.c_void_p * 3)(*[e.cuda_event for e in self._events])
+        backward(b, b.ws, b.enc, b.out, b.g_out, HEADS_ALL, b.g_aux, ev_arr)
+        if b.g_aux is not None:   # embedding gradient: per-ray sums of the aux-column gradients, scattered by ts
+            check(lib.snb_ray_param_backward(model._h, ptr(model.flat.detach()), ptr(b.extras), None, None, ptr(b.g_aux), b.n, S,
+                                             n_out, tau, vocab, ptr(gflat), ptr(g_emb), st), "snb_ray_param_backward")
+        # loss value: the terms' sum (+ the constant 3/2 of the log-beta term, baseline/components/loss.py:26)
+        self._loss_out = self._terms.sum() + (1.5 if color == "satnerf" else 0.0)
+        self._all_reduce_and_step(self._events if self.world > 1 else None)
+
+    # -- gradient all-reduce (sum: the losses are already normalised by the global batch) + Adam + re-pack -------------
+    def _all_reduce_and_step(self, events):
+        model = self.models["coarse"]
+        lib = _lib.load()
+        if self.world > 1:
+            cur = torch.cuda.current_stream()
+            works = []
+            if events is not None:
+                # buckets 0 and 1 start as soon as the backward pass has finished them; the last bucket (early trunk +
+                # embedding) is final once everything launched so far has run
+                last = torch.cuda.Event()
+                last.record(cur)
+                for bkt, ev in zip(self.buckets, (events[0], events[1], last)):
+                    self._side.wait_event(ev)
+                    with torch.cuda.stream(self._side):
+                        works.append(torch.distributed.all_reduce(self.gbuf[bkt[0]:bkt[1]], async_op=True))
+            else:
+                for bkt in self.buckets:
+                    works.append(torch.distributed.all_reduce(self.gbuf[bkt[0]:bkt[1]], async_op=True))
+            for w in works:
+                w.wait()                        # the current stream waits; the host does not
+            if events is not None:
+                cur.wait_stream(self._side)
+        check(lib.snb_adam_step(ptr(self.pbuf), ptr(self.gbuf), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.pbuf.numel(),
+                                self.lr, self.betas[0], self.betas[1], self.eps, self.step_idx, ptr(self._step_dev), 1.0,
                                 stream()), "snb_adam_step")
         model.mark_dirty()
-        if self.emb_opt is not None:
-            self.emb_opt.step()
+        if self.direct:
+            model.packed()                      # re-pack inside the step (and inside its CUDA graph)
 
     # -- chunked no-grad render of a whole image (BaseRayPipeline.forward / batched_inference) ---------------
     @torch.no_grad()
     def render_image(self, rays, extras, chunk: Optional[int] = None, keys=("rgb_coarse", "depth_coarse",
                                                                            "semantic_label_coarse"),
-                     heads: str = "all"):
-        """eval/utils/util.py:13-42 with preallocated outputs instead of the quadratic torch.cat."""
+                     heads: str = "all", seed: int = 1, ray_offset: int = 0, u=None):
+        """eval/utils/util.py:13-42 (`batched_inference`) / baseline/pipelines/base_ray_pipeline.py:34-54 with preallocated
+        outputs instead of the quadratic torch.cat.  The jitter is keyed on (seed, global ray index): the result does not
+        depend on the chunk size or on how an image is split across ranks (`ray_offset` = first global ray of `rays`).
+        `u` (N,S) replaces the jitter (parity tests)."""
         chunk = chunk or self.cfgs.pipeline.render_chunk_size
         n = rays.shape[0]
         out: Dict[str, torch.Tensor] = {}
         want_sc = any("_sc_" in k for k in keys)   # the solar-correction pass only produces the *_sc keys
         for i in range(0, n, chunk):
-            res = self.renderer.render_rays(self.models, rays[i:i + chunk], extras[i:i + chunk],
-                                            render_options={"seed": 1, "ray_offset": i, "heads": heads,
-                                                            "solar_pass": want_sc})
+            opts = {"seed": seed, "ray_offset": ray_offset + i, "heads": heads, "solar_pass": want_sc}
+            if u is not None:
+                opts["u"] = u[i:i + chunk]
+            res = self.renderer.render_rays(self.models, rays[i:i + chunk], extras[i:i + chunk], render_options=opts)
             for k in keys:
                 if k not in res:
                     continue

@@ -1,6 +1,7 @@
 """Data-parallel host logic on CPU with the gloo backend, world_size 2: ray sharding covers every ray
-exactly once, the bucketed all-reduce equals the single-process sum, and a sharded step with the
-1/world scale reproduces the full-batch gradient (linearity of the mean loss)."""
+exactly once, the bucketed all-reduce equals the single-process sum, and a sharded step whose means use
+the GLOBAL counts (ray count, all-reduced masked-mean denominator) reproduces the full-batch gradient by a
+plain sum - also when one rank holds every member of the masked mean."""
 import os
 import socket
 
@@ -65,16 +66,22 @@ def _worker(rank, world, port, n_params, tmp):
     x = torch.randn(10, n_params)
     wgt = torch.randn(n_params, requires_grad=True)
     lo, hi = snb_dist.shard_range(10, rank, world)
-    loss_local = ((x[lo:hi] @ wgt) ** 2).sum() / 10 * world      # local sum / global count * world
+    # the trainer's convention: every rank normalises by the GLOBAL counts (global ray count, all-reduced masked-mean
+    # denominators), so the per-rank losses are shares of the global loss and the gradients simply SUM
+    mask = torch.arange(10) < 3                                   # a masked mean whose members all sit in rank 0's shard
+    cnt_local = mask[lo:hi].sum().float().view(1)
+    cnt = snb_dist.all_reduce_scalar_sum(cnt_local.clone())
+    per_ray = (x[lo:hi] @ wgt) ** 2
+    loss_local = per_ray.sum() / 10 + (per_ray * mask[lo:hi]).sum() / cnt.clamp_min(1)
     loss_local.backward()
     g = wgt.grad.clone()
     red = snb_dist.GradAllReducer([(0, n_params // 3), (n_params // 3, n_params)][::-1])
     red.launch(g)
     red.wait()
-    g.mul_(1.0 / world)                                           # the scale snb_adam_step applies
     wfull = wgt.detach().clone().requires_grad_(True)
-    ((x @ wfull) ** 2).mean().backward()
-    ok = torch.allclose(g, wfull.grad, rtol=1e-5, atol=1e-6)
+    pr = (x @ wfull) ** 2
+    (pr.mean() + pr[mask].mean()).backward()
+    ok = torch.allclose(g, wfull.grad, rtol=1e-5, atol=1e-6) and cnt.item() == 3
     cnt = snb_dist.all_reduce_scalar_sum(torch.tensor([float(hi - lo)]))
     ok = ok and cnt.item() == 10
     snb_dist.barrier()

@@ -364,14 +364,18 @@ def test_fused_loss_step_equals_module_losses(kind, epoch, with_depth, S):
         dbatch = {"rays": dr.to(DEV), "extras": de.to(DEV), "depths": depths[:300].to(DEV).view(-1, 1),
                   "weights": torch.rand(300, generator=torch.Generator().manual_seed(1)).to(DEV)}
     res = {}
-    for fused in (True, False):
-        tr = Trainer(cfgs, kind, C, device=DEV, car_index=4, seed=0, fused_loss=fused)
+    # the three ways to run the step (trainer.py): direct kernel sequence, render_loss under autograd, loss modules on render_rays
+    for mode, kw in (("direct", dict(fused_loss=True, direct=True)), ("autograd", dict(fused_loss=True, direct=False)),
+                     ("module", dict(fused_loss=False))):
+        tr = Trainer(cfgs, kind, C, device=DEV, car_index=4, seed=0, **kw)
         loss = tr.training_step(batch, epoch=epoch, depth_batch=dbatch)
-        res[fused] = (loss.item(), tr.models["coarse"].flat.grad.clone(),
-                      tr.models["t"].weight.grad.clone() if "t" in tr.models else None,
-                      tr.last_loss_terms.cpu() if fused else {k: v.detach() for k, v in tr.last_loss_dict.items()})
-    lf, gf, ef, terms = res[True]
-    lu, gu, eu, ldict = res[False]
+        res[mode] = (loss.item(), tr.models["coarse"].flat.grad.clone(),
+                     tr.models["t"].weight.grad.clone() if "t" in tr.models else None,
+                     tr.last_loss_terms.cpu() if mode != "module" else {k: v.detach() for k, v in tr.last_loss_dict.items()})
+    la, ga, ea, _ = res["autograd"]
+    lf, gf, ef, terms = res["direct"]
+    lu, gu, eu, ldict = res["module"]
+    assert abs(la - lu) <= 2e-5 * max(1.0, abs(lu)) and _cos(ga, gu) >= 0.99999
     assert abs(lf - lu) <= 2e-5 * max(1.0, abs(lu)), (lf, lu)
     assert _cos(gf, gu) >= 0.99999 and (gf - gu).abs().max() <= 1e-4 * gu.abs().max()
     if ef is not None:
