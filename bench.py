@@ -146,16 +146,26 @@ def run_reference(args):
     emit(line)
 
 
-def workload_config(args, cpu=False):
-    return {
+def workload_config(args, cpu=False, graph=False):
+    c = {
         "workload": "Semantic-NeRF training step (BASELINE configs[1]): semantic 8x512 SIREN MLP, C=6, S=64, "
                     "solar-correction pass (sc_lambda=0.05), SatNerfLoss + SemanticLoss(ignore car) + "
                     "SemanticCarRegLoss, Adam; steady-state step (after the depth-supervision drop)",
         "rays_per_gpu_per_step": args.cpu_rays if cpu else args.batch, "samples_per_ray": N_SAMPLES,
         "n_classes": N_CLASSES, "parallelism": f"dp{args.gpus}",
-        "losses": "loss modules on render_rays()" if getattr(args, "module_losses", False) else "fused into the compositing kernel",
-        "l2": "per-step activation working set (~30 GB at 8192 rays) >> 126 MB L2; no flush needed",
     }
+    if cpu:
+        c["losses"] = "plain PyTorch on the host: the oracle's SatNerfLoss + SemanticLoss + SemanticCarRegLoss (autograd, torch Adam)"
+        c["l2"] = "n/a (host cores)"
+        c["note"] = ("bounded sample: the CPU arm steps fewer rays per step than the GPU arm (the metric is rays/s; "
+                     "CPU rays/s is flat in the batch size)")
+    else:
+        c["losses"] = ("loss modules on render_rays()" if getattr(args, "module_losses", False)
+                       else "fused into the compositing kernel")
+        c["l2"] = "per-step activation working set (~30 GB at 8192 rays) >> 126 MB L2; no flush needed"
+        c["step"] = ("direct kernel sequence on persistent buffers" + (", replayed as one CUDA graph" if graph else "")
+                     if not getattr(args, "module_losses", False) else "autograd")
+    return c
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -207,7 +217,7 @@ def hbm_kernel_rooflines(lib, dev, peak_hbm, n=40960):
     b = n * 48 + P * (4 + 2 * model.enc_ld * 2 + 32)
     res["k1_sample_encode"] = {"bound": "hbm", "achieved": b / t / 1e9, "peak": peak_hbm, "unit": "GB/s",
                                "frac": b / t / 1e9 / peak_hbm, "bytes": b, "us": t * 1e6,
-                               "note": "write-only kernel (main + solar rows); the measured write-only peak is ~3.9 TB/s"}
+                               "note": "write-only kernel (main + solar rows)"}
     out = torch.rand(P, n_out, device=dev)
     z = torch.sort(torch.rand(n, S, device=dev), dim=1).values
     rgb, depth = torch.empty(n, 3, device=dev), torch.empty(n, device=dev)
@@ -230,8 +240,116 @@ def hbm_kernel_rooflines(lib, dev, peak_hbm, n=40960):
 
 
 # ------------------------------------------------------------------------------------------------------
+# the same step as eager cuBLAS + ATen on the SAME GPU (SURVEY 2.3 / 8d "kernel to beat"): the oracle's restatement of
+# the reference path run on CUDA tensors - what the reference's own modules execute on a GPU, launch for launch
+# ------------------------------------------------------------------------------------------------------
+def gpu_eager_steps(dev, n_rays: int, mode: str, steps: int = 4, warmup: int = 2):
+    """mode "tf32": torch.set_float32_matmul_precision("high") as in the reference's run template (run/run_template.toml:15);
+    mode "bf16": the same under torch.autocast(bfloat16).  Returns rays/s (CUDA events)."""
+    from oracle import render_oracle as O
+    prev = torch.get_float32_matmul_precision()
+    torch.set_float32_matmul_precision("high")
+    try:
+        spec = O.ModelSpec(kind="semantic", n_classes=N_CLASSES)
+        params, emb = O.make_params(spec, seed=0)
+        params = {k: v.to(dev).requires_grad_(True) for k, v in params.items()}
+        emb = emb.to(dev).requires_grad_(True)
+        opt = torch.optim.Adam(list(params.values()) + [emb], lr=5e-4)
+        b = {k: v.to(dev) for k, v in make_batch(n_rays, seed=0).items()}
+
+        def step():
+            u = torch.rand(n_rays, N_SAMPLES, device=dev)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16")):
+                res = O.render_rays(params, emb, spec, b["rays"], b["extras"], N_SAMPLES, u=u, sc_lambda=0.05)
+            res = {k: (v.float() if v.is_floating_point() else v) for k, v in res.items()}
+            loss = O.satnerf_loss(res, b["rgbs"]) + O.semantic_loss(res, b["semantic"], ignore_index=CAR_INDEX) + \
+                O.car_reg_loss(res, b["semantic"], CAR_INDEX)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return n_rays * steps / (e0.elapsed_time(e1) * 1e-3)
+    finally:
+        torch.set_float32_matmul_precision(prev)
+        del params, emb
+        torch.cuda.empty_cache()
+
+
+def cpu_config1(n_rays: int = 1024):
+    """BASELINE configs[0] exactly (SURVEY 8d "Config 1"): SatNeRF render_rays + (rgb.sum() + depth.sum()).backward(), 1024 rays,
+    64 samples, no semantic head, on the host cores; sc_lambda 0 and 0.05; 1 warm-up + best of 3."""
+    from oracle import render_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = O.ModelSpec(kind="satnerf", n_classes=0)
+    params, emb = O.make_params(spec, seed=0)
+    params = {k: v.requires_grad_(True) for k, v in params.items()}
+    rays, extras = O.synthetic_rays(n_rays, seed=0)
+    out = {}
+    for sc in (0.0, 0.05):
+        best = None
+        for i in range(4):
+            t0 = time.perf_counter()
+            u = torch.rand(n_rays, N_SAMPLES)
+            res = O.render_rays(params, emb, spec, rays, extras, N_SAMPLES, u=u, sc_lambda=sc)
+            loss = res["rgb_coarse"].sum() + res["depth_coarse"].sum()
+            if sc > 0:   # the solar pass enters the graph through its outputs
+                loss = loss + res["sun_sc_coarse"].sum()
+            for v in params.values():
+                v.grad = None
+            loss.backward()
+            dt = time.perf_counter() - t0
+            if i > 0:
+                best = dt if best is None else min(best, dt)
+        out[f"sc_lambda_{sc}"] = {"rays_per_s": n_rays / best, "s_per_step": best}
+    return {"workload": f"SatNeRF render_rays fwd+bwd, {n_rays} rays x {N_SAMPLES} samples, 8x512 SIREN, no semantic head, fp32",
+            "cores": torch.get_num_threads(), "kind": "port", "timing": "1 warm-up + best of 3", **out}
+
+
+def newest_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one step's GEMM kernels from the newest per-launch ncu capture under
+    profiles/ (tools/ncu_summary.py writes the '# total' row)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_step_gemms.csv")))
+    for f in reversed(files):
+        for line in open(f):
+            if line.startswith("# total"):
+                parts = line.strip().split(",")
+                try:
+                    return float(parts[5]), os.path.relpath(f, ROOT)
+                except (IndexError, ValueError):
+                    break
+    return None, None
+
+
+# ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+def timed_steps(fn, steps, dev, world):
+    """device time of `steps` calls of fn(i), barrier + synchronize on both sides, max over ranks (ms)"""
+    from semnerf_b200 import dist as snb_dist
+    snb_dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        out = fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    snb_dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    return ms.item(), out
+
+
 def run_gpu(args):
     from semnerf_b200 import _lib, build, dist as snb_dist
     from semnerf_b200.trainer import Trainer, default_cfgs
@@ -245,34 +363,23 @@ def run_gpu(args):
     snb_dist.barrier()
     lib = _lib.load()
     B = args.batch
+    graph = world == 1 and not args.no_graph and not args.module_losses
     cfgs = default_cfgs("semantic", n_samples=N_SAMPLES, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=0)
     tr = Trainer(cfgs, "semantic", N_CLASSES, device=dev, car_index=CAR_INDEX, world=world, rank=rank, seed=0,
-                 fused_loss=not args.module_losses, graph=args.graph)
+                 fused_loss=not args.module_losses, graph=graph, micro_batch=8192)
     host = [make_batch(B, seed=100 * rank + i, pinned=True) for i in range(4)]
     resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
 
     def step_resident(i):
         return tr.training_step(resident[i % len(resident)], epoch=3, ray_offset=rank * B)
 
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 3)):
         step_resident(i)
     torch.cuda.synchronize()
     # ---- timed region 1: inputs resident in HBM, device-timed ----------------------------------------
     sampler = ClockSampler(local) if rank == 0 else None
     lib.snb_profile_begin(0)
-    snb_dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        loss = step_resident(i)
-    e1.record()
-    torch.cuda.synchronize()
-    snb_dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-    ms_total = ms.item()
+    ms_total, loss = timed_steps(step_resident, args.steps, dev, world)
     clocks = sampler.stop() if sampler else None
     gl, tl = C.c_int64(), C.c_int64()
     lib.snb_profile_end(None, C.byref(gl), C.byref(tl), None)
@@ -280,13 +387,13 @@ def run_gpu(args):
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---- timed region 2: end to end through the public API, host buffers ------------------------------
+    # every step copies its inputs from pinned host memory (inside training_step: the staging copies of the direct step)
+    # and reads the loss back
     snb_dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        hb = host[i % len(host)]
-        b = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-        loss = tr.training_step(b, epoch=3, ray_offset=rank * B)
+        loss = tr.training_step(host[i % len(host)], epoch=3, ray_offset=rank * B)
         loss_host = loss.item()          # device -> host read of the step's result
     torch.cuda.synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
@@ -295,9 +402,23 @@ def run_gpu(args):
     e2e_value = world * B * args.steps / t_e2e.item()
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
+    # ---- strong scaling (BASELINE configs[3]): a fixed 65 536-ray GLOBAL batch, 65 536 / N rays per GPU in 8192-ray
+    # micro-batches that accumulate into one gradient, ONE all-reduce + optimiser step per global batch ------------
+    strong = None
+    if not args.no_extras:
+        G = 65536
+        Bs = G // world
+        sb = {k: v.to(dev) for k, v in make_batch(Bs, seed=900 + rank).items()}
+        tr.training_step(sb, epoch=3, ray_offset=rank * Bs, global_rays=G)
+        nst = 3
+        ms_s, _ = timed_steps(lambda i: tr.training_step(sb, epoch=3, ray_offset=rank * Bs, global_rays=G), nst, dev, world)
+        strong = {"scaling": "strong", "global_rays_per_step": G, "rays_per_gpu_per_step": Bs, "micro_batch_rays": 8192,
+                  "value": G * nst / (ms_s * 1e-3), "unit": "rays/s", "ms_per_step": ms_s / nst, "steps": nst}
+        del sb
+
     # ---- roofline of the dominant kernels (the tcgen05 GEMMs), timed live with CUDA events per launch ------
     # every rank runs these steps (they contain the gradient all-reduce); rank 0 reports its own launches
-    roof = cpu = render = hbm = None
+    roof = cpu = render = hbm = small = early = eager = cfg1 = None
     nprof = 4
     snb_dist.barrier()
     lib.snb_profile_begin(1)
@@ -309,51 +430,104 @@ def run_gpu(args):
     lib.snb_profile_end(C.byref(gms), C.byref(gl2), C.byref(tl2), C.byref(macs))
     snb_dist.barrier()
     if rank == 0:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         peak_tf, peak_hbm, which = peaks()
         gemm_ms_step = gms.value / nprof
         alg = ALG_FLOP_PER_TRAIN_RAY * B
         achieved = alg / (gemm_ms_step * 1e-3) / 1e12
+        traffic, traffic_src = newest_ncu_traffic()
         roof = {"bound": "tensor", "kernel": "snb_chain_kernel + snb_gemm_kernel (tcgen05 GEMMs: chained MLP passes, wgrad, head rows)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": NCU_TRAFFIC_BYTES_PER_STEP,
-                "peak_source": which, "per": "step: algorithmic MLP FLOPs of one step / summed GEMM launch time (one rank)",
+                "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": which, "frac_of_burst_peak": achieved / d["bf16_tflops"] if "bf16_tflops" in d else None,
+                "per": "step: algorithmic MLP FLOPs of one step / summed GEMM launch time (one rank)",
+                "note": "the GEMM time comes from 4 separately event-timed steps (launch-serialised): +-4 % against the timed region",
                 "gemm_launches_per_step": gl2.value // nprof, "gemm_ms_per_step": gemm_ms_step,
                 "executed_tflops": 2 * macs.value / nprof / (gemm_ms_step * 1e-3) / 1e12,
+                "step_basis_tflops": alg / (ms_total / args.steps * 1e-3) / 1e12,
                 "gemm_share_of_step": gemm_ms_step / (ms_total / args.steps)}
+    if rank == 0 and not args.no_extras:
         # secondary metric: no-grad render throughput (samples/s), chunked like batched_inference (no collectives)
         nr = 4 * 40960
         from semnerf_b200 import synth
         rr, ee = synth.make_rays(nr, seed=7)
         rr, ee = rr.to(dev), ee.to(dev)
-        rkeys = ("rgb_coarse", "depth_coarse", "semantic_label_coarse", "sun_sc_coarse")   # sun_sc: keeps the solar pass in
-        tr.render_image(rr[:40960], ee[:40960], keys=rkeys)
-        torch.cuda.synchronize()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        tr.render_image(rr, ee, keys=rkeys)
-        r1.record()
-        torch.cuda.synchronize()
-        rs = nr * N_SAMPLES / (r0.elapsed_time(r1) * 1e-3)
-        render = {"samples_per_s": rs, "rays": nr, "chunk_rays": 40960, "passes": "main + solar-correction",
-                  "tensor_frac": rs * ALG_FLOP_PER_RENDER_SAMPLE / 1e12 / peak_tf}
+        render = {}
+        for name, rkeys, flop in (("main_and_solar_pass", ("rgb_coarse", "depth_coarse", "semantic_label_coarse", "sun_sc_coarse"),
+                                   ALG_FLOP_PER_RENDER_SAMPLE),
+                                  ("main_pass", ("rgb_coarse", "depth_coarse", "semantic_label_coarse"), 5_641_216)):
+            tr.render_image(rr[:40960], ee[:40960], keys=rkeys)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            tr.render_image(rr, ee, keys=rkeys)
+            r1.record()
+            torch.cuda.synchronize()
+            rs = nr * N_SAMPLES / (r0.elapsed_time(r1) * 1e-3)
+            render[name] = {"samples_per_s": rs, "rays": nr, "chunk_rays": 40960, "tensor_frac": rs * flop / 1e12 / peak_tf}
+        del rr, ee
         try:
-            # at the reference's render chunk (40 960 rays: 43-350 us launches, ramp and tail included) and at 4 chunks
-            hbm = {"chunk_40960": hbm_kernel_rooflines(lib, dev, peak_hbm, 40960),
-                   "rays_163840": hbm_kernel_rooflines(lib, dev, peak_hbm, 163840)}
+            # at the training batch (8192 rays), the reference's render chunk (40 960 rays) and at 4 chunks
+            hbm = {f"rays_{n}": hbm_kernel_rooflines(lib, dev, peak_hbm, n) for n in (8192, 40960, 163840)}
         except Exception as e:   # secondary numbers must not take the headline line down
             hbm = {"error": str(e)[:200]}
-        if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_extras:
+        # ---- the reference's default batch (1024 rays / step, configs/pipelines/rs_semantic.toml) ----------------------
+        sb = {k: v.to(dev) for k, v in make_batch(1024, seed=5).items()}
+        for i in range(3):
+            tr.training_step(sb, epoch=3)
+        ms_b, _ = timed_steps(lambda i: tr.training_step(sb, epoch=3), 50, dev, world)
+        small = {"rays_per_step": 1024, "value": 1024 * 50 / (ms_b * 1e-3), "unit": "rays/s", "ms_per_step": ms_b / 50,
+                 "cuda_graph": tr.use_graph, "frac_of_headline": 1024 * 50 / (ms_b * 1e-3) / value}
+        # ---- the early-training step: the depth-supervision batch of the first 25 % of the steps rides along
+        # (semantic/components/training_step.py:31-49; its batch size is the rgb batch's: framework/pipelines.py:107-118)
+        from semnerf_b200 import synth
+        dr, de = synth.make_rays(B, seed=77)
+        _, _, dd = synth.make_targets(dr, N_CLASSES, seed=77)
+        db = {"rays": dr.to(dev), "extras": de.to(dev), "depths": dd.view(-1, 1).to(dev), "weights": torch.ones(B, 1, device=dev)}
+        for i in range(3):
+            tr.training_step(resident[0], epoch=3, depth_batch=db)
+        ms_d, _ = timed_steps(lambda i: tr.training_step(resident[i % 4], epoch=3, depth_batch=db), 5, dev, world)
+        early = {"workload": "the same step + the depth-supervision batch (trunk + sigma, DepthLoss) of the first 25 % of training",
+                 "rgb_rays_per_step": B, "depth_rays_per_step": B, "value": B * 5 / (ms_d * 1e-3), "unit": "rgb rays/s",
+                 "ms_per_step": ms_d / 5, "alg_tflops": (ALG_FLOP_PER_TRAIN_RAY + 64 * 11_320_320) * B * 5 / (ms_d * 1e-3) / 1e12}
+        del db, sb
+        tr._bufs.clear()
+        tr._graphs.clear()
+        torch.cuda.empty_cache()
+        # ---- the "kernel to beat": the same step as eager cuBLAS + ATen on this GPU ------------------------------------
+        eager = {"what": "the oracle's restatement of the reference path on CUDA tensors (eager cuBLAS + ATen, autograd, torch Adam): "
+                         "TF32 'high' as in run/run_template.toml:15, and under torch.autocast(bfloat16)"}
+        for n_e in (B, 1024):
+            for mode in ("tf32", "bf16"):
+                try:
+                    eager[f"rays_{n_e}_{mode}"] = gpu_eager_steps(dev, n_e, mode)
+                except Exception as e:
+                    eager[f"rays_{n_e}_{mode}"] = None
+                    eager[f"rays_{n_e}_{mode}_error"] = str(e)[:160]
+                    torch.cuda.empty_cache()
+        if eager.get(f"rays_{B}_tf32"):
+            eager["speedup_vs_tf32"] = value / eager[f"rays_{B}_tf32"]
+        if eager.get(f"rays_{B}_bf16"):
+            eager["speedup_vs_bf16_autocast"] = value / eager[f"rays_{B}_bf16"]
+        if eager.get("rays_1024_tf32") and small:
+            eager["speedup_vs_tf32_at_1024"] = small["value"] / eager["rays_1024_tf32"]
+        if not args.no_cpu:
             rps, cores, _ = cpu_training_steps(args.cpu_rays, 10, 1)   # ~10-15 s of CPU work
             cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                   "sample": f"{args.cpu_rays} rays x {N_SAMPLES} samples, 10 timed steps of the same training step"}
+                   "sample": f"{args.cpu_rays} rays x {N_SAMPLES} samples per step (the GPU arm steps {B}; the metric is rays/s), "
+                             "10 timed steps of the same training step"}
+            cfg1 = cpu_config1()
     if rank == 0:
         line = {
             "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, graph=graph),
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": launches, "clocks": clocks, "render": render, "hbm_kernels": hbm, "loss": loss_host,
+            "gpu_launches": launches, "clocks": clocks, "strong_scaling": strong, "batch_1024": small, "early_training_step": early,
+            "gpu_eager_baseline": eager, "cpu_baseline_config1": cfg1, "render": render, "hbm_kernels": hbm,
+            "loss": loss_host,
         }
         emit(line)
     snb_dist.barrier()
@@ -384,7 +558,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays per step of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--graph", action="store_true", help="replay the step as one CUDA graph (single GPU)")
+    ap.add_argument("--no-graph", action="store_true", help="do not replay the step as one CUDA graph (single GPU default: on)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline + e2e + roofline only (skip the strong-scaling, 1024-ray, early-step, eager, render, HBM legs)")
     ap.add_argument("--module-losses", action="store_true",
                     help="render_rays() + the reference-shaped loss modules instead of the fused K3 + loss kernel")
     args = ap.parse_args()

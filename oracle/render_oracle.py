@@ -179,12 +179,12 @@ def make_params(spec: ModelSpec, seed: int = 0, dtype=torch.float32, trained_lik
 # --------------------------------------------------------------------------------------
 # K1: sampling + encoding
 # --------------------------------------------------------------------------------------
-def linspace01(n: int, dtype=torch.float32) -> torch.Tensor:
+def linspace01(n: int, dtype=torch.float32, device=None) -> torch.Tensor:
     """torch.linspace(0, 1, n) as the reference calls it
     (framework/components/rendering.py:95).  Kept as a separate function so the
     CUDA kernel's closed form (i*step for the lower half, 1-(n-1-i)*step for the
     upper half) can be pinned against it."""
-    return torch.linspace(0, 1, n, dtype=dtype)
+    return torch.linspace(0, 1, n, dtype=dtype, device=device)   # on the rays' device, as the reference does
 
 
 def sample_z(rays: torch.Tensor, n_samples: int, u: Optional[torch.Tensor]) -> torch.Tensor:
@@ -192,7 +192,7 @@ def sample_z(rays: torch.Tensor, n_samples: int, u: Optional[torch.Tensor]) -> t
     with ``use_disp=False, perturb=1.0``; ``u`` is the U[0,1) jitter the reference
     draws with ``torch.rand_like`` (u=None -> no perturbation, the perturb=0 branch)."""
     near, far = rays[:, 6:7], rays[:, 7:8]
-    t = linspace01(n_samples, rays.dtype)
+    t = linspace01(n_samples, rays.dtype, rays.device)
     z = near * (1 - t) + far * t
     if u is not None:
         mid = 0.5 * (z[:, :-1] + z[:, 1:])

@@ -311,7 +311,8 @@ class CompositeLoss(torch.autograd.Function):
             terms.add_(mine)
         loss = mine.sum()
         if params.mode == 0 and params.color == 1:
-            loss = loss + 1.5      # (3 + mean log beta) / 2: the constant of the log-beta term (loss.py:26)
+            # (3 + mean log beta) / 2: the constant of the log-beta term (loss.py:26); a data-parallel shard carries its share
+            loss = loss + 1.5 * n * params.inv_n
         return loss
 
     @staticmethod

@@ -32,10 +32,19 @@ struct Cursor {   // position in this SM pair's tile sequence: group, layer, slo
 struct Seq {
   int n_my;       // row blocks this pair owns: pair, pair + n_pairs, ...
   int n_layers;
-  __device__ __forceinline__ int nslots(int g) const {
-    const int r = n_my - g * CHAIN_SLOTS;
-    return r < CHAIN_SLOTS ? r : CHAIN_SLOTS;
+  // The blocks are carried through the layers in groups of up to CHAIN_SLOTS interleaved slots.  The groups are BALANCED
+  // (28 blocks = 8 x 3 + 2 x 2, 4 blocks = 2 + 2, never ... + 1): a single-slot group has nothing to interleave with, so
+  // every layer of it would wait for its own store -> load round trip through L2.
+  int groups, base, rem;
+  __device__ __forceinline__ void init(int n_my_, int n_layers_) {
+    n_my = n_my_;
+    n_layers = n_layers_;
+    groups = (n_my + CHAIN_SLOTS - 1) / CHAIN_SLOTS;
+    base = groups > 0 ? n_my / groups : 0;
+    rem = groups > 0 ? n_my - base * groups : 0;
   }
+  __device__ __forceinline__ int nslots(int g) const { return base + (g < rem ? 1 : 0); }
+  __device__ __forceinline__ int first(int g) const { return g * base + (g < rem ? g : rem); }   // first own block of group g
 };
 
 __device__ __forceinline__ void cur_init(Cursor& c, const Seq& q) {
@@ -50,7 +59,7 @@ __device__ __forceinline__ void cur_next(Cursor& c, const Seq& q, const ChainArg
   if (++c.l < q.n_layers) return;
   c.l = 0;
   ++c.g;
-  if (c.g * CHAIN_SLOTS >= q.n_my) c.done = true;
+  if (c.g >= q.groups) c.done = true;
 }
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -162,8 +171,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
   const int pair = (int)(blockIdx.x >> 1);
   const int n_pairs = (int)(gridDim.x >> 1);
   Seq seq;
-  seq.n_my = pair < args.n_blocks ? (args.n_blocks - pair + n_pairs - 1) / n_pairs : 0;
-  seq.n_layers = args.n_layers;
+  seq.init(pair < args.n_blocks ? (args.n_blocks - pair + n_pairs - 1) / n_pairs : 0, args.n_layers);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 8; ++s) {
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
         rbits ^= 1u << c.s;
         fence_proxy_async_all();
       }
-      const int blk = (c.g * CHAIN_SLOTS + c.s) * n_pairs + pair;
+      const int blk = (seq.first(c.g) + c.s) * n_pairs + pair;
       const int row_real = blk * 256 + (int)cta_rank * GEMM_BLOCK_M;
       const int row_scr = (pair * CHAIN_SLOTS + c.s) * 256 + (int)cta_rank * GEMM_BLOCK_M;
       const int kb_total = ly.kb_total;
@@ -313,7 +321,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
     auto arm = [&](const Cursor& t, int g, int ci, uint32_t par) {   // elected lane only; par = parity of the tile's index
       const ChainLayer& tl = args.layers[t.l];
       uint64_t* bar = &rdy[g * 2 + ci];
-      const int trow = ((t.g * CHAIN_SLOTS + t.s) * n_pairs + pair) * 256 + (int)cta_rank * GEMM_BLOCK_M;
+      const int trow = ((seq.first(t.g) + t.s) * n_pairs + pair) * 256 + (int)cta_rank * GEMM_BLOCK_M;
       if (tl.epi == EPI_MUL) {
         mbar_expect_tx(bar, GEMM_STAGING);
         tma_load_2d_hint(sStg + (g * 2 + ci) * GEMM_STAGING, &args.maps[t.l].tmMul, bar, t.j * 256 + (g + 2 * ci) * 64, trow,
@@ -347,7 +355,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       cur_next(nx, seq, args);
       if (ly.epi != EPI_HEADOUT) {
         const Cursor nc = next_chunked(c);
-        const int blk = (c.g * CHAIN_SLOTS + c.s) * n_pairs + pair;
+        const int blk = (seq.first(c.g) + c.s) * n_pairs + pair;
         const int m_out = ly.o_scratch ? (pair * CHAIN_SLOTS + c.s) * 256 + (int)cta_rank * GEMM_BLOCK_M
                                        : blk * 256 + (int)cta_rank * GEMM_BLOCK_M;
 #pragma unroll 1
@@ -437,7 +445,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       const bool siren = ly.mul_siren == 1;
       const bool relu_bwd = ly.mul_siren == 2;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int blk = (c.g * CHAIN_SLOTS + c.s) * n_pairs + pair;
+      const int blk = (seq.first(c.g) + c.s) * n_pairs + pair;
       const int m_real = blk * 256 + (int)cta_rank * GEMM_BLOCK_M;
       const int n0 = c.j * 256;
       const bool row_ok = m_real + row < args.M;

@@ -94,7 +94,7 @@ class _PassBuffers:
 class Trainer:
     def __init__(self, cfgs, kind: str = "semantic", n_classes: int = 6, device="cuda", car_index: int = 4,
                  world: int = 1, rank: int = 0, seed: int = 0, fused_loss: bool = True, direct: bool = True,
-                 graph: bool = False):
+                 graph: bool = False, micro_batch: Optional[int] = None):
         p = cfgs.pipeline
         self.cfgs, self.kind, self.device, self.world, self.rank = cfgs, kind, torch.device(device), world, rank
         torch.manual_seed(seed)  # identical initial replicas on every rank
@@ -144,6 +144,10 @@ class Trainer:
         self.fused_loss = fused_loss
         self.direct = direct and fused_loss
         self.use_graph = bool(graph) and self.direct and world == 1
+        # micro_batch: the direct step runs batches larger than this many rays as several forward / backward passes that
+        # accumulate into the one gradient buffer before the single optimiser step (the saved activations cost ~25 KB per
+        # sample and pass: 8192 rays x 64 samples = 26 GB; a 65 536-ray global batch does not fit one GPU in one piece)
+        self.micro_batch = micro_batch
         # gradient buckets in completion order (snb_model_grad_buckets), as ranges of gbuf; the last one also carries the
         # embedding gradient
         lo, hi = (C.c_int64 * 3)(), (C.c_int64 * 3)()
@@ -281,17 +285,10 @@ class Trainer:
         p = self.cfgs.pipeline
         sem, car, color = self._loss_config(epoch)
         n = batch["rays"].shape[0]
-        b = self._buffers("rgb", n, False)
-        self._stage(b.rays, batch["rays"])
-        self._stage(b.extras, batch["extras"])
-        self._stage(b.rgbs, batch["rgbs"])
-        has_mask = False
-        if sem:
-            self._stage(b.labels, batch["semantic"])          # any integer dtype (the dataset's uint8) -> int64
-            m = batch.get("semantic_sparsity_mask")
-            has_mask = m is not None
-            if has_mask:
-                self._stage(b.mask, m)
+        micro = self.micro_batch if (self.micro_batch and n > self.micro_batch) else n
+        pieces = [(lo, min(lo + micro, n)) for lo in range(0, n, micro)]
+        m = batch.get("semantic_sparsity_mask") if sem else None
+        has_mask = m is not None
         d = None
         if depth_batch is not None:
             d = self._buffers("depth", depth_batch["rays"].shape[0], True)
@@ -304,36 +301,64 @@ class Trainer:
         self._seed_dev[0].fill_(self.step_idx)
         self._seed_dev[1].fill_(self.step_idx + (1 << 20))
         self._step_dev.fill_(self.step_idx)
-        cfg = (n, d.n if d is not None else 0, color, car, has_mask, ray_offset, global_rays, global_depth_rays)
-        if self.use_graph:
-            entry = self._graphs.get(cfg)
-            if entry is None:
-                # first call of a configuration runs eagerly (lazy one-time CUDA attribute calls, allocator warm-up) ...
-                self._graphs[cfg] = ("warm",)
-                self._run_direct(b, d, sem, car, color, has_mask, ray_offset, global_rays, global_depth_rays)
-            elif entry[0] == "warm":
-                # ... the second is captured (and the capture replayed, since capturing does not execute)
-                lib = _lib.load()
-                g = torch.cuda.CUDAGraph()
-                l0 = lib.snb_profile_launch_count()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                    self._run_direct(b, d, sem, car, color, has_mask, ray_offset, global_rays, global_depth_rays)
-                captured = lib.snb_profile_launch_count() - l0
-                lib.snb_profile_add_launches(-captured)            # captured, not yet executed
-                self._graphs[cfg] = entry = ("graph", g, captured, self._loss_out)
-            if entry is not None and entry[0] == "graph":
-                entry[1].replay()
-                _lib.load().snb_profile_add_launches(entry[2])
-                self._loss_out = entry[3]
-        else:
-            self._run_direct(b, d, sem, car, color, has_mask, ray_offset, global_rays, global_depth_rays)
+        counts_done = False
+        if len(pieces) > 1 and sem:
+            # the masked-mean denominators run over the WHOLE batch (and, data parallel, over every rank's)
+            self._counts.zero_()
+            lab_all = as_labels(batch["semantic"].to(self.device, non_blocking=True))
+            mask_all = as_ray_mask(m.to(self.device, non_blocking=True)) if has_mask else None
+            check(_lib.load().snb_label_counts(ptr(lab_all), ptr(mask_all), n,
+                                               self.models["coarse"].semantic_n_classes,
+                                               self.car_index if p.ignore_car_index else -100, self.car_index,
+                                               ptr(self._counts), stream()), "snb_label_counts")
+            self._reduce_counts(self._counts)
+            counts_done = True
+        for i, (lo, hi) in enumerate(pieces):
+            b = self._buffers("rgb", hi - lo, False)
+            self._stage(b.rays, batch["rays"][lo:hi])
+            self._stage(b.extras, batch["extras"][lo:hi])
+            self._stage(b.rgbs, batch["rgbs"][lo:hi])
+            if sem:
+                self._stage(b.labels, batch["semantic"][lo:hi])   # any integer dtype (the dataset's uint8) -> int64
+                if has_mask:
+                    self._stage(b.mask, m[lo:hi])
+            first, last = i == 0, i == len(pieces) - 1
+            offs = (ray_offset[0] + lo, ray_offset[1])
+            args = (b, d if first else None, sem, car, color, has_mask, offs, global_rays, global_depth_rays, first, last,
+                    counts_done, n / max(global_rays, 1))
+            cfg = (hi - lo, d.n if d is not None else 0, color, car, has_mask, offs, global_rays, global_depth_rays)
+            if self.use_graph and len(pieces) == 1:
+                entry = self._graphs.get(cfg)
+                if entry is None:
+                    # first call of a configuration runs eagerly (lazy one-time CUDA attribute calls, allocator warm-up) ...
+                    self._graphs[cfg] = ("warm",)
+                    self._run_direct(*args)
+                elif entry[0] == "warm":
+                    # ... the second is captured (and the capture replayed, since capturing does not execute)
+                    lib = _lib.load()
+                    g = torch.cuda.CUDAGraph()
+                    l0 = lib.snb_profile_launch_count()
+                    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                        self._run_direct(*args)
+                    captured = lib.snb_profile_launch_count() - l0
+                    lib.snb_profile_add_launches(-captured)            # captured, not yet executed
+                    self._graphs[cfg] = entry = ("graph", g, captured, self._loss_out)
+                if entry is not None and entry[0] == "graph":
+                    entry[1].replay()
+                    _lib.load().snb_profile_add_launches(entry[2])
+                    self._loss_out = entry[3]
+            else:
+                self._run_direct(*args)
         self._bind_grads()
         self.last_loss_terms = self._terms
         return self._loss_out
 
-    def _run_direct(self, b, d, sem, car, color, has_mask, ray_offset, global_rays, global_depth_rays):
+    def _run_direct(self, b, d, sem, car, color, has_mask, ray_offset, global_rays, global_depth_rays, first=True, last=True,
+                    counts_done=False, share=1.0):
         """K1 -> MLP forward (main, solar) -> K3 + losses (gradients of the packed rows) -> MLP backward (solar, main) ->
-        ray-parameter gradients -> [depth batch the same way] -> all-reduce -> Adam -> re-pack.  Every buffer is persistent."""
+        ray-parameter gradients -> [depth batch the same way] -> all-reduce -> Adam -> re-pack.  Every buffer is persistent.
+        first / last: this is the first / last micro-batch of the step (zero the accumulators / reduce and step);
+        share: this rank's fraction of the global batch (its share of the constant of the log-beta term)."""
         lib = _lib.load()
         p = self.cfgs.pipeline
         model, emb = self.models["coarse"], self.models.get("t")
@@ -354,8 +379,9 @@ class Trainer:
         gflat = self.gbuf[EMB_PAD:]
         g_emb = self.gbuf[:self.n_emb] if emb is not None else None
         ts = t_steps(S, self.device)
-        self._terms.zero_()
-        self.gbuf.zero_()
+        if first:
+            self._terms.zero_()
+            self.gbuf.zero_()
         packed = model.packed()
         if self._events is None and self.world > 1:
             self._events = [torch.cuda.Event() for _ in range(3)]
@@ -391,12 +417,13 @@ class Trainer:
         work = None
         if sem:
             counts = self._counts
-            counts.zero_()
-            check(lib.snb_label_counts(ptr(b.labels), ptr(b.mask) if has_mask else None, b.n, Cn,
-                                       self.car_index if p.ignore_car_index else -100, self.car_index, ptr(counts), st),
-                  "snb_label_counts")
-            if self.world > 1:   # global masked-mean denominators; overlaps the forward passes
-                work = torch.distributed.all_reduce(counts, async_op=True)
+            if not counts_done:
+                counts.zero_()
+                check(lib.snb_label_counts(ptr(b.labels), ptr(b.mask) if has_mask else None, b.n, Cn,
+                                           self.car_index if p.ignore_car_index else -100, self.car_index, ptr(counts), st),
+                      "snb_label_counts")
+                if self.world > 1:   # global masked-mean denominators; overlaps the forward passes
+                    work = torch.distributed.all_reduce(counts, async_op=True)
         forward(b, b.ws, b.enc, b.sky, HEADS_ALL, b.out)
         if sc:
             forward(b, b.ws_sc, b.enc_sc, None, HEADS_SOLAR, b.out_sc)
@@ -432,18 +459,23 @@ class Trainer:
                                              b.n, S, n_out, 0, 1, ptr(gflat), None, st), "snb_ray_param_backward")
         if sc:
             backward(b, b.ws_sc, b.enc_sc, b.out_sc, b.g_out_sc, HEADS_SOLAR, None, None)
-        if self.world > 1:
+        if self.world > 1 and last:
             ev_arr = (C.c_void_p * 3)(*[e.cuda_event for e in self._events])
         backward(b, b.ws, b.enc, b.out, b.g_out, HEADS_ALL, b.g_aux, ev_arr)
         if b.g_aux is not None:   # embedding gradient: per-ray sums of the aux-column gradients, scattered by ts
             check(lib.snb_ray_param_backward(model._h, ptr(model.flat.detach()), ptr(b.extras), None, None, ptr(b.g_aux), b.n, S,
                                              n_out, tau, vocab, ptr(gflat), ptr(g_emb), st), "snb_ray_param_backward")
         # loss value: the terms' sum (+ the constant 3/2 of the log-beta term, baseline/components/loss.py:26)
-        self._loss_out = self._terms.sum() + (1.5 if color == "satnerf" else 0.0)
-        self._all_reduce_and_step(self._events if self.world > 1 else None)
+        if last:
+            # loss value: the terms' sum (+ the constant 3/2 of the log-beta term, baseline/components/loss.py:26); data
+            # parallel, the per-rank values are shares that add up to the global-batch loss
+            self._loss_out = self._terms.sum() + (1.5 * share if color == "satnerf" else 0.0)
+            self._all_reduce_and_step(self._events if self.world > 1 else None, self._step_dev)
 
     # -- gradient all-reduce (sum: the losses are already normalised by the global batch) + Adam + re-pack -------------
-    def _all_reduce_and_step(self, events):
+    def _all_reduce_and_step(self, events, step_dev=None):
+        """step_dev: device int holding the step number (the direct step keeps it current so that a captured CUDA graph
+        replays with the right Adam bias corrections); None = use the host counter"""
         model = self.models["coarse"]
         lib = _lib.load()
         if self.world > 1:
@@ -466,7 +498,7 @@ class Trainer:
             if events is not None:
                 cur.wait_stream(self._side)
         check(lib.snb_adam_step(ptr(self.pbuf), ptr(self.gbuf), ptr(self.exp_avg), ptr(self.exp_avg_sq), self.pbuf.numel(),
-                                self.lr, self.betas[0], self.betas[1], self.eps, self.step_idx, ptr(self._step_dev), 1.0,
+                                self.lr, self.betas[0], self.betas[1], self.eps, self.step_idx, ptr(step_dev), 1.0,
                                 stream()), "snb_adam_step")
         model.mark_dirty()
         if self.direct:
