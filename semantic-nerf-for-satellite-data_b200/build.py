@@ -16,6 +16,8 @@ LIB = os.path.join(PKG, "lib", "libsnb.so")
 SOURCES = ["snb_host.cu", "k1_sample_encode.cu", "k2_gemm.cu", "k2_chain.cu", "k2_mlp.cu", "k3_composite.cu", "k_aux.cu", "k_fp32.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177"]
+if os.environ.get("SNB_EXPERIMENTS"):   # tools/exp_chain.py: deliberately wrong kernels that locate a bottleneck (never shipped)
+    FLAGS = FLAGS + ["-DSNB_EXPERIMENTS"]
 
 
 def _source_hash() -> str:

@@ -15,6 +15,7 @@
 #include "k2_chain.cuh"
 #include "k2_ptx.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace snb {
@@ -160,8 +161,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
   uint64_t* rdy = tempty + 2;                 // [group][chunk]: staging buffer free / multiplicand tile landed
   uint64_t* stg = rdy + GEMM_NUM_STAGING;     // [group][chunk]: chunk staged by the group's 8 warps
   uint64_t* ready = stg + GEMM_NUM_STAGING;
-  uint64_t* mrdy = ready + CHAIN_SLOTS;       // sign-mask tile of a dgrad tile landed (one phase per chunked tile)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mrdy + 1);
+  // sign-mask tile of a dgrad tile landed: one barrier per tile parity (= per mask buffer), one phase per chunked tile of
+  // that parity - two barriers so that a tile's mask can be requested TWO tiles ahead without lapping a waiter
+  uint64_t* mrdy = ready + CHAIN_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mrdy + 2);
 
   const int warp = threadIdx.x >> 5;  // warp-uniform
   const int lane = threadIdx.x & 31;
@@ -189,7 +192,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       mbar_init(&stg[s], 8);   // one arrival per warp of the group
     }
     for (int s = 0; s < CHAIN_SLOTS; ++s) mbar_init(&ready[s], 1);   // the store warp
-    mbar_init(mrdy, 1);
+    mbar_init(&mrdy[0], 1);
+    mbar_init(&mrdy[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -229,6 +233,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
           ++sg;
         }
         mbar_wait(&emptyA[stage], phase ^ 1);
+#ifdef SNB_EXPERIMENTS
+        if ((args.exp & 2) && (kb & 1)) {   // operand feed experiment: no load, the MMA reads whatever the stage holds
+          if (elect_one()) {
+            if (lead_cta) mbar_arrive(&fullA[stage]);
+            else mbar_arrive_remote(&fullA[stage], 0);
+          }
+        } else
+#endif
         if (elect_one()) {
           if (lead_cta) mbar_expect_tx(&fullA[stage], 2 * 16384);
           else mbar_arrive_remote(&fullA[stage], 0);
@@ -254,6 +266,14 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       const int kb_total = ly.kb_total;
       for (int kb = 0; kb < kb_total; ++kb) {
         mbar_wait(&emptyB[stage], phase ^ 1);
+#ifdef SNB_EXPERIMENTS
+        if ((args.exp & 1) && (kb & 1)) {
+          if (elect_one()) {
+            if (lead_cta) mbar_arrive(&fullB[stage]);
+            else mbar_arrive_remote(&fullB[stage], 0);
+          }
+        } else
+#endif
         if (elect_one()) {
           if (lead_cta) mbar_expect_tx(&fullB[stage], b_bytes);
           else mbar_arrive_remote(&fullB[stage], 0);
@@ -322,6 +342,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       const ChainLayer& tl = args.layers[t.l];
       uint64_t* bar = &rdy[g * 2 + ci];
       const int trow = ((seq.first(t.g) + t.s) * n_pairs + pair) * 256 + (int)cta_rank * GEMM_BLOCK_M;
+#ifdef SNB_EXPERIMENTS
+      if (tl.epi == EPI_MUL && (args.exp & 16)) {
+        mbar_arrive(bar);
+      } else
+#endif
       if (tl.epi == EPI_MUL) {
         mbar_expect_tx(bar, GEMM_STAGING);
         tma_load_2d_hint(sStg + (g * 2 + ci) * GEMM_STAGING, &args.maps[t.l].tmMul, bar, t.j * 256 + (g + 2 * ci) * 64, trow,
@@ -329,13 +354,19 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       } else {
         mbar_arrive(bar);
       }
-      if (g == 0 && ci == 0) {   // once per tile: its sign-mask words
-        if (tl.epi == EPI_MUL && tl.mul_siren == 1) {
-          mbar_expect_tx(mrdy, 4096);
-          tma_load_2d_hint(mask_smem + par * 1024, &args.maps[t.l].tmMask, mrdy, t.j * 8, trow, L2_EVICT_FIRST);
-        } else {
-          mbar_arrive(mrdy);
-        }
+    };
+    // the sign-mask words of tile t (the par-th chunked tile, parity par & 1) into mask buffer par & 1.  They come from HBM
+    // (written by the forward pass) and are the first thing a dgrad tile's epilogue needs, so they are requested two tiles
+    // ahead: ncu showed the 16 math warps waiting 12 % of their time for a request made half a tile ahead.
+    auto arm_mask = [&](const Cursor& t, uint32_t par) {   // elected lane only
+      const ChainLayer& tl = args.layers[t.l];
+      uint64_t* bar = &mrdy[par & 1];
+      if (tl.epi == EPI_MUL && tl.mul_siren == 1) {
+        const int trow = ((seq.first(t.g) + t.s) * n_pairs + pair) * 256 + (int)cta_rank * GEMM_BLOCK_M;
+        mbar_expect_tx(bar, 4096);
+        tma_load_2d_hint(mask_smem + (par & 1) * 1024, &args.maps[t.l].tmMask, bar, t.j * 8, trow, L2_EVICT_FIRST);
+      } else {
+        mbar_arrive(bar);
       }
     };
     const bool el = elect_one();
@@ -346,8 +377,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       do { cur_next(t, seq, args); } while (!t.done && args.layers[t.l].epi == EPI_HEADOUT);
       return t;
     };
-    if (!c.done && el)
+    if (!c.done && el) {
+      // NB: c may be a head-output tile only if the chain starts with one, which no plan does
       for (int k = 0; k < 4; ++k) arm(c, k >> 1, k & 1, 0);
+      arm_mask(c, 0);
+      const Cursor c1 = next_chunked(c);
+      if (!c1.done) arm_mask(c1, 1);
+    }
     int prev_g = -1, prev_ci = -1;   // the store issued before the current one: its buffer is re-armed once it has drained
     for (; !c.done;) {
       const ChainLayer& ly = args.layers[c.l];
@@ -355,6 +391,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       cur_next(nx, seq, args);
       if (ly.epi != EPI_HEADOUT) {
         const Cursor nc = next_chunked(c);
+        const Cursor nc2 = nc.done ? nc : next_chunked(nc);
         const int blk = (seq.first(c.g) + c.s) * n_pairs + pair;
         const int m_out = ly.o_scratch ? (pair * CHAIN_SLOTS + c.s) * 256 + (int)cta_rank * GEMM_BLOCK_M
                                        : blk * 256 + (int)cta_rank * GEMM_BLOCK_M;
@@ -368,6 +405,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
               bulk_wait_done<0>();
               confirm(cn);
             }
+#ifdef SNB_EXPERIMENTS
+            if (!(args.exp & 8))
+#endif
             tma_store_2d_hint(&args.maps[c.l].tmO0, smem_u32(sStg) + (g * 2 + ci) * GEMM_STAGING, c.j * 256 + (g + 2 * ci) * 64, m_out,
                               L2_EVICT_LAST);
             if (k == 3 && ly.epi == EPI_SIN && ly.mask != nullptr)   // all 16 warps have staged their words of the tile
@@ -379,6 +419,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
               bulk_wait_read<1>();
               arm(nc, prev_g, prev_ci, (itc + 1) & 1);
             }
+            // both groups have staged their first chunk of this tile, so all 16 math warps hold its mask words in
+            // registers: its mask buffer is free for the tile after next (forward tiles: only after the mask store below)
+            if (k == 1 && !nc2.done && !(ly.epi == EPI_SIN && ly.mask != nullptr)) arm_mask(nc2, itc + 2);
             prev_g = g;
             prev_ci = ci;
           }
@@ -390,6 +433,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
           bulk_wait_read<0>();
           arm(nc, 1, 1, (itc + 1) & 1);
         }
+        if (el && !nc2.done && ly.epi == EPI_SIN && ly.mask != nullptr) arm_mask(nc2, itc + 2);   // (keeps the phases in step)
         prev_g = -1;
         ++itc;
       }
@@ -461,7 +505,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       uint32_t* mtile = mask_smem + (itc & 1) * 1024 + row * 8 + grp * 2 + half;   // + 4 * ci: this thread's word of chunk ci
       uint32_t mw0 = 0, mw1 = 0;
       if (epi == EPI_MUL && siren) {
-        mbar_wait(mrdy, itc & 1);   // the tile's sign-mask words have landed
+        mbar_wait(&mrdy[itc & 1], (itc >> 1) & 1);   // the tile's sign-mask words have landed
         mw0 = mtile[0];
         mw1 = mtile[4];
       }
@@ -533,6 +577,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
           tmem_ld32(taddr + ch * 64 + half * 32, v);
           tc_wait_ld();
 
+#ifdef SNB_EXPERIMENTS
+          if (args.exp & 4) {
+            mbar_wait(brdy, itc & 1);
+          } else
+#endif
           if (epi == EPI_MUL) {
             mbar_wait(brdy, itc & 1);   // the multiplicand tile has landed in the staging buffer
             if (relu_bwd) chunk_mul<false, true, true>(v, buf0, row_off, sw, half, w0, mw);
@@ -625,7 +674,16 @@ int chain_launch(const ChainArgs& a, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const bool timed = profile_gemm_begin(st, macs, 100 + a.n_layers, a.M, 0, 0, 2, 1);
+#ifdef SNB_EXPERIMENTS
+  {
+    ChainArgs b = a;
+    const char* e = getenv("SNB_EXP");
+    b.exp = e ? atoi(e) : 0;
+    SNB_CUDA(cudaLaunchKernelEx(&cfg, snb_chain_kernel, b));
+  }
+#else
   SNB_CUDA(cudaLaunchKernelEx(&cfg, snb_chain_kernel, a));
+#endif
   if (timed) profile_gemm_end(st);
   return launch_status("snb_chain_kernel");
 }
