@@ -98,17 +98,32 @@ __device__ __forceinline__ void stage_enc_row(uint8_t* stage, int row, float x, 
   for (int i = 0; i < R::LD / 2; ++i) w[i] = 0u;
   const float xyz[3] = {x, y, z};
   if (KIND == SNB_MODEL_SEMANTIC) {
-    // commons.py:68-74: for k: [sin(2^k x)(3), cos(2^k x)(3)], no identity term
+    // commons.py:68-74: for k: [sin(2^k x)(3), cos(2^k x)(3)], no identity term.
+    // sin / cos are evaluated to ~1 ulp at the frequencies k = 0, 3, 6, 9 and carried to k + 1, k + 2 by the double-angle
+    // formulas (sin 2a = 2 sin a cos a, cos 2a = 1 - 2 sin^2 a): two doublings grow the absolute error to <= ~10 ulp = 6e-7,
+    // an order of magnitude below the 2^-17 the two-term bf16 split keeps.  This halves the kernel's instruction count: with
+    // 30 full sincos evaluations per row it was issue-bound (~1100 instructions per 256-byte row), not HBM-bound.
+    float sn[10][3], cs[10][3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+#pragma unroll
+      for (int k0 = 0; k0 < 10; k0 += 3) {
+        sincos_reduced((float)(1 << k0) * xyz[ch], sn[k0][ch], cs[k0][ch]);  // power-of-two factor: the product is exact
+#pragma unroll
+        for (int k = k0 + 1; k < k0 + 3 && k < 10; ++k) {
+          const float s = sn[k - 1][ch], c = cs[k - 1][ch];
+          sn[k][ch] = (s + s) * c;
+          cs[k][ch] = fmaf(-(s + s), s, 1.0f);
+        }
+      }
+    }
 #pragma unroll
     for (int k = 0; k < 10; ++k) {
-      const float f = (float)(1 << k);
       uint32_t hi[6], lo[6];
 #pragma unroll
       for (int ch = 0; ch < 3; ++ch) {
-        float sn, cs;
-        sincos_reduced(f * xyz[ch], sn, cs);  // f is a power of two: the product is exact
-        split_bits(sn, hi[ch], lo[ch]);
-        split_bits(cs, hi[3 + ch], lo[3 + ch]);
+        split_bits(sn[k][ch], hi[ch], lo[ch]);
+        split_bits(cs[k][ch], hi[3 + ch], lo[3 + ch]);
       }
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -164,7 +179,7 @@ __device__ __forceinline__ void stage_aux_row(uint8_t* stage, int row, float sx,
 constexpr int K1_THREADS = 128;   // samples per block iteration
 
 template <int KIND>
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, 6)   // <= 80 registers: six 36 KB blocks (24 warps) per SM
 k1_sample_encode_kernel(const float* __restrict__ rays, const float* __restrict__ extras,
                         const float* __restrict__ u, uint64_t seed, const uint64_t* __restrict__ seed_dev,
                         uint64_t ray_offset, const float* __restrict__ t_steps, const float* __restrict__ t_table, int vocab,
@@ -239,7 +254,7 @@ k1_sample_encode_kernel(const float* __restrict__ rays, const float* __restrict_
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, 6)   // <= 80 registers: six 36 KB blocks (24 warps) per SM
 k1_encode_points_kernel(const float* __restrict__ xyz, const float* __restrict__ sun_d,
                         const float* __restrict__ t, int tau, long long P, __nv_bfloat16* __restrict__ enc,
                         __nv_bfloat16* __restrict__ aux) {

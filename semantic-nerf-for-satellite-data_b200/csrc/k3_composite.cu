@@ -60,8 +60,11 @@ __device__ __forceinline__ SampleVals sample_alpha(const float* zs, const float*
   return v;
 }
 
-template <int SPL, bool BWD>
-__global__ void __launch_bounds__(K3_WARPS * 32)
+// CMAX: compile-time bound of the class loops (0: no semantic columns - SatNeRF / S-NeRF / NeRF and the solar pass; 6: the
+// usual 5-6 classes; 10: the widest head).  With a single 10-wide predicated loop the kernels spent a third of their
+// instructions on classes that do not exist (ncu: 600 - 1400 warp instructions per ray, issue-bound at 55 % of the HBM peak).
+template <int SPL, bool BWD, int CMAX>
+__global__ void __launch_bounds__(K3_WARPS * 32, SPL >= 8 ? 1 : (BWD ? 5 : 6))
 k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, int n_rays, int S,
                     int n_out, int C, int flags,
                     // forward outputs
@@ -140,9 +143,9 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
     const float prefix = warp_excl_prod(Q, lane);
 
     float acc_d = 0.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f;
-    float acc_s[10];
+    float acc_s[CMAX > 0 ? CMAX : 1];
 #pragma unroll
-    for (int c = 0; c < 10; ++c) acc_s[c] = 0.f;
+    for (int c = 0; c < CMAX; ++c) acc_s[c] = 0.f;
     float T[SPL], w[SPL];
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
@@ -158,7 +161,7 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
         acc_g += w[j] * r[1] * (v + (1.0f - v) * r[6]);
         acc_b += w[j] * r[2] * (v + (1.0f - v) * r[7]);
 #pragma unroll
-        for (int c = 0; c < 10; ++c)
+        for (int c = 0; c < CMAX; ++c)
           if (c < C) acc_s[c] += w[j] * r[9 + c];
       }
     }
@@ -185,7 +188,7 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
     acc_g = warp_sum(acc_g);
     acc_b = warp_sum(acc_b);
 #pragma unroll
-    for (int c = 0; c < 10; ++c)
+    for (int c = 0; c < CMAX; ++c)
       if (c < C) acc_s[c] = warp_sum(acc_s[c]);
 
     if (!BWD) {
@@ -200,7 +203,7 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
           int best = 0;
           float bv = acc_s[0];
 #pragma unroll
-          for (int c = 0; c < 10; ++c) {
+          for (int c = 0; c < CMAX; ++c) {
             if (c < C) {
               sem_logits[(size_t)ray * C + c] = acc_s[c];
               if (acc_s[c] > bv) { bv = acc_s[c]; best = c; }
@@ -220,9 +223,9 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
         if (!(acc_b >= 0.f && acc_b <= 1.f)) gb = 0.f;
       }
       const float gd = g_depth ? g_depth[ray] : 0.f;
-      float gs[10];
+      float gs[CMAX > 0 ? CMAX : 1];
 #pragma unroll
-      for (int c = 0; c < 10; ++c) gs[c] = (g_sem && c < C) ? g_sem[(size_t)ray * C + c] : 0.f;
+      for (int c = 0; c < CMAX; ++c) gs[c] = (g_sem && c < C) ? g_sem[(size_t)ray * C + c] : 0.f;
 
       float Gw[SPL], B[SPL];
       float Bsum = 0.f;
@@ -239,7 +242,7 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
           g += gr * r[0] * (v + (1.0f - v) * r[5]) + gg * r[1] * (v + (1.0f - v) * r[6]) +
                gb * r[2] * (v + (1.0f - v) * r[7]);
 #pragma unroll
-          for (int c = 0; c < 10; ++c)
+          for (int c = 0; c < CMAX; ++c)
             if (c < C) g += gs[c] * r[9 + c];
           Gw[j] = g;
           float dT = (g_transp ? g_transp[(size_t)ray * S + s] : 0.f) + g * alpha[j];
@@ -271,7 +274,7 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
           go[7] = gb * wj * r[2] * (1.0f - v);
           go[8] = 0.f;
 #pragma unroll
-          for (int c = 0; c < 10; ++c)
+          for (int c = 0; c < CMAX; ++c)
             if (c < C) go[9 + c] = gs[c] * wj;
           for (int c = 9 + C; c < n_out; ++c) go[c] = 0.f;
         }
@@ -329,11 +332,23 @@ static int launch_k3(const float* out, const float* z, int n_rays, int S, int n_
   int blocks = (n_rays + K3_WARPS - 1) / K3_WARPS;
 #define K3_LAUNCH(SPL_)                                                                               \
   do {                                                                                                \
-    auto kfn = k3_composite_kernel<SPL_, BWD>;                                                        \
-    if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    /* one full wave of resident blocks, each looping over rays: a partial second wave would idle most SMs */ \
-    int resident = 0;                                                                                 \
-    SNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, K3_WARPS * 32, smem));     \
+    if (C == 0) K3_LAUNCH_C(SPL_, 0);                                                                 \
+    else if (C <= 6) K3_LAUNCH_C(SPL_, 6);                                                            \
+    else K3_LAUNCH_C(SPL_, 10);                                                                       \
+  } while (0)
+#define K3_LAUNCH_C(SPL_, CMAX_)                                                                      \
+  do {                                                                                                \
+    auto kfn = k3_composite_kernel<SPL_, BWD, CMAX_>;                                                 \
+    /* one full wave of resident blocks, each looping over rays: a partial second wave would idle most SMs. */ \
+    /* The attribute / occupancy queries cost several microseconds of host time each: once per shared-memory size. */ \
+    static size_t cached_smem = ~(size_t)0;                                                           \
+    static int cached_resident = 0;                                                                   \
+    if (cached_smem != smem) {                                                                        \
+      if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      SNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_resident, kfn, K3_WARPS * 32, smem)); \
+      cached_smem = smem;                                                                             \
+    }                                                                                                 \
+    int resident = cached_resident;                                                                   \
     if (resident < 1) resident = 1;                                                                   \
     if (blocks > sms * resident) blocks = sms * resident;                                             \
     kfn<<<blocks, K3_WARPS * 32, smem, st>>>(out, z, n_rays, S, n_out, C, flags, rgb, depth, weights, transp, sem, label, \
@@ -344,6 +359,7 @@ static int launch_k3(const float* out, const float* z, int n_rays, int S, int n_
   else if (spl <= 4) K3_LAUNCH(4);
   else K3_LAUNCH(8);
 #undef K3_LAUNCH
+#undef K3_LAUNCH_C
   return launch_status("k3_composite_kernel");
 }
 
@@ -387,8 +403,8 @@ struct LossParams {
   int flags;
 };
 
-template <int SPL>
-__global__ void __launch_bounds__(K3_WARPS * 32)
+template <int SPL, int CMAX>
+__global__ void __launch_bounds__(K3_WARPS * 32, SPL >= 8 ? 1 : 5)
 k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, int n_rays, int S, int n_out, int C,
                const float* __restrict__ gt_rgb, const long long* __restrict__ labels,
                const unsigned char* __restrict__ ray_mask, const float* __restrict__ depth_gt,
@@ -457,9 +473,9 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
     }
     const float prefix = warp_excl_prod(Q, lane);
     float acc_d = 0.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_beta = 0.f, acc_t2 = 0.f, acc_t3 = 0.f;
-    float acc_s[10];
+    float acc_s[CMAX > 0 ? CMAX : 1];
 #pragma unroll
-    for (int c = 0; c < 10; ++c) acc_s[c] = 0.f;
+    for (int c = 0; c < CMAX; ++c) acc_s[c] = 0.f;
     float T[SPL], w[SPL];
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
@@ -476,7 +492,7 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
           acc_b += w[j] * r[2] * (v + (1.0f - v) * r[7]);
           acc_beta += w[j] * r[8];
 #pragma unroll
-          for (int c = 0; c < 10; ++c)
+          for (int c = 0; c < CMAX; ++c)
             if (c < C) acc_s[c] += w[j] * r[9 + c];
         } else if (lp.mode == 1) {
           acc_t2 += (T[j] - v) * (T[j] - v);
@@ -485,16 +501,16 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
       }
     }
     float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, gB = 0.f;
-    float gs[10];
+    float gs[CMAX > 0 ? CMAX : 1];
 #pragma unroll
-    for (int c = 0; c < 10; ++c) gs[c] = 0.f;
+    for (int c = 0; c < CMAX; ++c) gs[c] = 0.f;
     if (lp.mode == 0) {
       acc_r = warp_sum(acc_r);
       acc_g = warp_sum(acc_g);
       acc_b = warp_sum(acc_b);
       acc_beta = warp_sum(acc_beta);
 #pragma unroll
-      for (int c = 0; c < 10; ++c)
+      for (int c = 0; c < CMAX; ++c)
         if (c < C) acc_s[c] = warp_sum(acc_s[c]);
       // colour loss on the clamped colour (rs_semantic.py:103); the clamp passes gradient inside [0, 1] only
       // (NeRF's inference does not clamp, nerf.py:73-86: SNB_COMPOSITE_NO_CLAMP)
@@ -532,11 +548,11 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
         if (lp.lambda_s != 0.f && y != lp.ignore_index && y >= 0 && y < C) {
           float mx = acc_s[0];
 #pragma unroll
-          for (int c = 1; c < 10; ++c)
+          for (int c = 1; c < CMAX; ++c)
             if (c < C) mx = fmaxf(mx, acc_s[c]);
           float se = 0.f, ly = 0.f;
 #pragma unroll
-          for (int c = 0; c < 10; ++c)
+          for (int c = 0; c < CMAX; ++c)
             if (c < C) {
               se += expf(acc_s[c] - mx);
               if (c == y) ly = acc_s[c];
@@ -544,7 +560,7 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
           const float lse = mx + logf(se);
           lsum[2] += lp.lambda_s * (lse - ly) * inv_valid;
 #pragma unroll
-          for (int c = 0; c < 10; ++c)
+          for (int c = 0; c < CMAX; ++c)
             if (c < C) gs[c] = lp.lambda_s * (expf(acc_s[c] - lse) - (c == y ? 1.0f : 0.0f)) * inv_valid;
         }
         if (lp.lambda_c != 0.f && y == lp.car_label) {   // mse(1, sum w beta) over the car rays
@@ -594,7 +610,7 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
           float g = gB * r[8] + gd * zs[s];
           g += gr * r[0] * (v + (1.0f - v) * r[5]) + gg * r[1] * (v + (1.0f - v) * r[6]) + gb * r[2] * (v + (1.0f - v) * r[7]);
 #pragma unroll
-          for (int c = 0; c < 10; ++c)
+          for (int c = 0; c < CMAX; ++c)
             if (c < C) g += gs[c] * r[9 + c];
           Gw[j] = g;
           Bv[j] = g * alpha[j] * T[j];
@@ -622,7 +638,7 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
           go[7] = gb * wj * r[2] * (1.0f - v);
           go[8] = gB * wj;
 #pragma unroll
-          for (int c = 0; c < 10; ++c)
+          for (int c = 0; c < CMAX; ++c)
             if (c < C) go[9 + c] = gs[c] * wj;
           for (int c = 9 + C; c < n_out; ++c) go[c] = 0.f;
         }
@@ -663,10 +679,21 @@ static int launch_k3_loss(const float* out, const float* z, int n_rays, int S, i
   int blocks = (n_rays + K3_WARPS - 1) / K3_WARPS;
 #define K3L_LAUNCH(SPL_)                                                                              \
   do {                                                                                                \
-    auto kfn = k3_loss_kernel<SPL_>;                                                                  \
-    if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    int resident = 0;                                                                                 \
-    SNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kfn, K3_WARPS * 32, smem));     \
+    if (C == 0) K3L_LAUNCH_C(SPL_, 0);                                                                \
+    else if (C <= 6) K3L_LAUNCH_C(SPL_, 6);                                                           \
+    else K3L_LAUNCH_C(SPL_, 10);                                                                      \
+  } while (0)
+#define K3L_LAUNCH_C(SPL_, CMAX_)                                                                     \
+  do {                                                                                                \
+    auto kfn = k3_loss_kernel<SPL_, CMAX_>;                                                           \
+    static size_t cached_smem = ~(size_t)0;                                                           \
+    static int cached_resident = 0;                                                                   \
+    if (cached_smem != smem) {                                                                        \
+      if (smem > 48 * 1024) SNB_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      SNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_resident, kfn, K3_WARPS * 32, smem)); \
+      cached_smem = smem;                                                                             \
+    }                                                                                                 \
+    int resident = cached_resident;                                                                   \
     if (resident < 1) resident = 1;                                                                   \
     if (blocks > sms * resident) blocks = sms * resident;                                             \
     kfn<<<blocks, K3_WARPS * 32, smem, st>>>(out, z, n_rays, S, n_out, C, gt_rgb, labels, ray_mask, depth_gt, depth_w, counts, lp, \
@@ -677,6 +704,7 @@ static int launch_k3_loss(const float* out, const float* z, int n_rays, int S, i
   else if (spl <= 4) K3L_LAUNCH(4);
   else K3L_LAUNCH(8);
 #undef K3L_LAUNCH
+#undef K3L_LAUNCH_C
   return launch_status("k3_loss_kernel");
 }
 
