@@ -192,6 +192,10 @@ int snb_composite_backward(const float* out, const float* z_vals, int n_rays, in
  *                        ignore_index, semantic/components/loss.py:35-65) + SemanticCarRegLoss (loss.py:117-157)
  *   mode 1 (solar pass)  solar_correction terms 2 and 3 (baseline/components/loss.py:4-13)
  *   mode 2 (depth batch) DepthLoss (baseline/components/loss.py:30-47)
+ *   mode 3 (statistics)  pre-pass of the uncertainty-weighted semantic loss: loss_terms[0] += sum of the per-ray
+ *                        cross-entropies, loss_terms[1] += sum_r 1 / (2 beta_r^2); g_out may be NULL (nothing is written).
+ *                        Pass `counts + 4` as loss_terms, then run mode 0 with sem_unc != 0 and the same `counts`
+ *                        (float[6]; data parallel: all-reduce entries 4-5 with the rest).
  * gt_rgb (N,3) f32; labels (N) i64 or NULL; depth_gt / depth_w (N) f32 (depth_w NULL = 1);
  * ray_mask (N) u8 or NULL: the reference's `semantic_sparsity_mask` (semantic/dataset/semantic_dataset.py:65,87, passed to
  *   all semantic losses by semantic/components/training_step.py:58-88) - rays with mask 0 enter neither the cross-entropy nor
@@ -210,6 +214,9 @@ typedef struct snb_loss_params {
   int car_label;
   float lambda_sc, lambda_ds;
   int flags;                 /* SNB_COMPOSITE_* */
+  int sem_unc;               /* mode 0: 0 = SemanticLoss; 1 = SemanticUncertaintyLoss (`use_beta_for_s`, semantic/components/
+                              * loss.py:6-32,68-114: lambda_s * CE_mean * mean_r 1 / (2 beta_r^2)); 2 = the same with beta
+                              * detached (`detach_beta_for_s`).  Needs the statistics of a mode-3 pre-pass in counts[4:6]. */
 } snb_loss_params;
 int snb_composite_loss(const float* out, const float* z_vals, int n_rays, int n_samples, int n_out, int n_classes,
                        const float* gt_rgb, const int64_t* labels, const uint8_t* ray_mask, const float* depth_gt,

@@ -49,7 +49,7 @@ def step_inputs(name, C, n, s, seed, *_):
 
 
 def oracle_step_loss(O_, params, emb, spec, batch, depth, s, ignore_car, use_mask, car_reg, use_depth, beta_loss,
-                     lambda_s=0.04, lambda_c=0.1, ds_lambda=1000.0, sc_lambda=0.05):
+                     lambda_s=0.04, lambda_c=0.1, ds_lambda=1000.0, sc_lambda=0.05, sem_unc=0):
     """the oracle's restatement of RSSemanticTrainingStep.training_step (semantic/components/training_step.py:12-99)"""
     res = O_.render_rays(params, emb, spec, batch["rays"], batch["extras"], s, u=batch.get("u"), z=batch.get("z"),
                          sc_lambda=sc_lambda)
@@ -62,7 +62,11 @@ def oracle_step_loss(O_, params, emb, spec, batch, depth, s, ignore_car, use_mas
     mask = batch["semantic_sparsity_mask"] if use_mask else None
     if spec.kind != "semantic":     # the baseline pipelines' step: colour (+ depth) only (baseline/components/training_step.py)
         return sum(terms.values()), terms, res
-    terms["semantic"] = O_.semantic_loss(res, batch["semantic"], lambda_s, CAR if ignore_car else -100, mask)
+    if sem_unc:   # use_beta_for_s (training_step.py:66-75): 1 = SemanticUncertaintyLoss, 2 = with detach_beta_for_s
+        terms["semantic"] = O_.semantic_uncertainty_loss(res, batch["semantic"], lambda_s, CAR if ignore_car else -100, mask,
+                                                         detach_beta=(sem_unc == 2))
+    else:
+        terms["semantic"] = O_.semantic_loss(res, batch["semantic"], lambda_s, CAR if ignore_car else -100, mask)
     if car_reg:
         terms["car_reg"] = O_.car_reg_loss(res, batch["semantic"], CAR, lambda_c, mask)
     return sum(terms.values()), terms, res

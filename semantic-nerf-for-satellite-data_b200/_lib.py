@@ -63,7 +63,7 @@ SIGNATURES = {
 class LossParams(C.Structure):
     """snb_loss_params (include/snb.h)"""
     _fields_ = [("mode", _i), ("color", _i), ("beta_min", _f), ("inv_n", _f), ("lambda_s", _f), ("ignore_index", _i),
-                ("lambda_c", _f), ("car_label", _i), ("lambda_sc", _f), ("lambda_ds", _f), ("flags", _i)]
+                ("lambda_c", _f), ("car_label", _i), ("lambda_sc", _f), ("lambda_ds", _f), ("flags", _i), ("sem_unc", _i)]
 
 
 _lib = None

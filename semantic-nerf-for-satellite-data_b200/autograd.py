@@ -264,12 +264,13 @@ LOSS_TERMS = ("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3",
 
 
 def label_counts(labels, ray_mask, n_classes: int, ignore_index: int, car_label: int, counts=None):
-    """snb_label_counts: the masked-mean denominators of the semantic losses as a device float[4]
-    [rays in the CE mean, rays in the car term, out-of-range labels, 0] - no host sync.  `labels` int64 (N),
-    `ray_mask` uint8 (N) or None."""
+    """snb_label_counts: the masked-mean denominators of the semantic losses as a device float[8]
+    [rays in the CE mean, rays in the car term, out-of-range labels, 0, then the two statistics of the uncertainty-weighted
+    semantic loss's pre-pass (CE sum, sum 1 / (2 beta^2)), 0, 0] - no host sync.  `labels` int64 (N), `ray_mask` uint8 (N) or
+    None."""
     lib = _lib.load()
     if counts is None:
-        counts = torch.zeros(4, dtype=torch.float32, device=labels.device)
+        counts = torch.zeros(8, dtype=torch.float32, device=labels.device)
     check(lib.snb_label_counts(ptr(labels), ptr(ray_mask), labels.numel(), n_classes, ignore_index, car_label, ptr(counts),
                                stream()), "snb_label_counts")
     return counts
@@ -297,12 +298,22 @@ class CompositeLoss(torch.autograd.Function):
     `terms` (8,) is accumulated in place (logging; not differentiable)."""
 
     @staticmethod
-    def forward(ctx, out, z_vals, n_classes, params, gt_rgb, labels, depth_gt, depth_w, counts, terms, ray_mask=None):
+    def forward(ctx, out, z_vals, n_classes, params, gt_rgb, labels, depth_gt, depth_w, counts, terms, ray_mask=None,
+                reduce_stats=None):
         lib = _lib.load()
         out, z_vals = _f32c(out), _f32c(z_vals)
         n, s, n_out = out.shape
         g_out = torch.empty_like(out)
         mine = torch.zeros(8, dtype=torch.float32, device=out.device)
+        if params.mode == 0 and params.sem_unc:
+            # the uncertainty-weighted semantic loss is a product of two batch means: statistics pre-pass first (mode 3)
+            pre = _lib.LossParams.from_buffer_copy(params)
+            pre.mode = 3
+            check(lib.snb_composite_loss(ptr(out), ptr(z_vals), n, s, n_out, n_classes, None, ptr(labels), ptr(ray_mask), None,
+                                         None, ptr(counts), C.addressof(pre), None, counts[4:].data_ptr(), stream()),
+                  "snb_composite_loss (statistics pre-pass)")
+            if reduce_stats is not None:
+                reduce_stats(counts[4:6])
         check(lib.snb_composite_loss(ptr(out), ptr(z_vals), n, s, n_out, n_classes, ptr(_f32c(gt_rgb)), ptr(labels),
                                      ptr(ray_mask), ptr(_f32c(depth_gt)), ptr(_f32c(depth_w)), ptr(counts), C.addressof(params),
                                      ptr(g_out), ptr(mine), stream()), "snb_composite_loss")
@@ -318,4 +329,4 @@ class CompositeLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss):
         (g_out,) = ctx.saved_tensors
-        return g_out * g_loss, None, None, None, None, None, None, None, None, None, None
+        return g_out * g_loss, None, None, None, None, None, None, None, None, None, None, None

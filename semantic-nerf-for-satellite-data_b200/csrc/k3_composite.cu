@@ -387,6 +387,11 @@ static int check_k3(const float* out, const float* z, int n_rays, int S, int n_o
 //   mode 1 (solar pass):  solar-correction terms 2 and 3 (baseline/components/loss.py:4-13); transparency_sc / weights_sc
 //                         are detached there, so only the sun column receives a gradient
 //   mode 2 (depth batch): DepthLoss (baseline/components/loss.py:30-47)
+//   mode 3 (statistics pre-pass of the uncertainty-weighted semantic loss, `use_beta_for_s`): SemanticUncertaintyLoss
+//                         (semantic/components/loss.py:6-32,68-114) is lambda_s * CE_mean * mean_r(1 / (2 beta_r^2)) - a
+//                         product of two batch means, so its gradient needs both means first.  The pre-pass accumulates
+//                         loss_terms[0] += sum of the per-ray cross-entropies, loss_terms[1] += sum_r 1 / (2 beta_r^2) and
+//                         writes no gradient; the caller hands them to the main pass as counts[4], counts[5].
 // Means are over n_rays (inv_n), the CE mean over the non-ignored rays and the car term over the car rays: their counts
 // come from a device buffer (counts[0], counts[1]) so no host synchronisation is needed.
 // loss_terms (device float[8], accumulated): 0 colour, 1 log-beta (without the constant 3/2), 2 CE, 3 car, 4 sc term 2,
@@ -401,6 +406,7 @@ struct LossParams {
   int car_label;
   float lambda_sc, lambda_ds;
   int flags;
+  int sem_unc;
 };
 
 template <int SPL, int CMAX>
@@ -434,6 +440,9 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
   };
   const float inv_valid = counts ? 1.0f / fmaxf(counts[0], 1.0f) : 0.f;
   const float inv_car = counts ? 1.0f / fmaxf(counts[1], 1.0f) : 0.f;
+  // uncertainty-weighted semantic loss: the two batch means of the statistics pre-pass (mode 3)
+  const float unc_ce = (counts && lp.sem_unc) ? counts[4] * inv_valid : 0.f;      // CE_mean
+  const float unc_M = (counts && lp.sem_unc) ? counts[5] * lp.inv_n : 1.f;        // mean_r 1 / (2 beta_r^2)
   float lsum[7];
 #pragma unroll
   for (int i = 0; i < 7; ++i) lsum[i] = 0.f;
@@ -486,7 +495,12 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
         const float* r = rows + s * n_out;
         const float v = r[4];
         acc_d += w[j] * zs[s];
-        if (lp.mode == 0) {
+        if (lp.mode == 3) {
+          acc_beta += w[j] * r[8];
+#pragma unroll
+          for (int c = 0; c < CMAX; ++c)
+            if (c < C) acc_s[c] += w[j] * r[9 + c];
+        } else if (lp.mode == 0) {
           acc_r += w[j] * r[0] * (v + (1.0f - v) * r[5]);
           acc_g += w[j] * r[1] * (v + (1.0f - v) * r[6]);
           acc_b += w[j] * r[2] * (v + (1.0f - v) * r[7]);
@@ -504,6 +518,33 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
     float gs[CMAX > 0 ? CMAX : 1];
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) gs[c] = 0.f;
+    if (lp.mode == 3) {
+      // statistics pre-pass: per-ray cross-entropy and 1 / (2 beta^2); no gradient rows
+      acc_beta = warp_sum(acc_beta);
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) acc_s[c] = warp_sum(acc_s[c]);
+      const float Bt = acc_beta + lp.beta_min;
+      lsum[1] += 0.5f / (Bt * Bt);
+      const bool on = labels != nullptr && C > 0 && (ray_mask == nullptr || ray_mask[ray] != 0);
+      const int y = on ? (int)labels[ray] : -1;
+      if (on && y != lp.ignore_index && y >= 0 && y < C) {
+        float mx = acc_s[0];
+#pragma unroll
+        for (int c = 1; c < CMAX; ++c)
+          if (c < C) mx = fmaxf(mx, acc_s[c]);
+        float se = 0.f, ly = 0.f;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+          if (c < C) {
+            se += expf(acc_s[c] - mx);
+            if (c == y) ly = acc_s[c];
+          }
+        lsum[0] += mx + logf(se) - ly;
+      }
+      __syncwarp();
+      continue;
+    }
     if (lp.mode == 0) {
       acc_r = warp_sum(acc_r);
       acc_g = warp_sum(acc_g);
@@ -558,16 +599,25 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
               if (c == y) ly = acc_s[c];
             }
           const float lse = mx + logf(se);
-          lsum[2] += lp.lambda_s * (lse - ly) * inv_valid;
+          // plain SemanticLoss: lambda_s * CE_mean.  Uncertainty-weighted (sem_unc): lambda_s * CE_mean * M with
+          // M = mean_r 1 / (2 beta_r^2) from the pre-pass - the logits' gradient is scaled by M
+          const float ks = lp.lambda_s * inv_valid * (lp.sem_unc ? unc_M : 1.0f);
+          lsum[2] += ks * (lse - ly);
 #pragma unroll
           for (int c = 0; c < CMAX; ++c)
-            if (c < C) gs[c] = lp.lambda_s * (expf(acc_s[c] - lse) - (c == y ? 1.0f : 0.0f)) * inv_valid;
+            if (c < C) gs[c] = ks * (expf(acc_s[c] - lse) - (c == y ? 1.0f : 0.0f));
         }
         if (lp.lambda_c != 0.f && y == lp.car_label) {   // mse(1, sum w beta) over the car rays
           const float e = 1.0f - acc_beta;
           lsum[3] += lp.lambda_c * e * e * inv_car;
           gB += -2.0f * lp.lambda_c * e * inv_car;
         }
+      }
+      if (lp.sem_unc == 1 && lp.lambda_s != 0.f) {
+        // d/d beta_r of lambda_s * CE_mean * mean_r 1 / (2 beta_r^2) = -lambda_s * CE_mean / (N beta_r^3) - for EVERY ray of
+        // the batch, labelled or not: the mean over beta runs over all rays (loss.py:19-25); sem_unc == 2: beta detached
+        const float Bt = acc_beta + lp.beta_min;
+        gB += -lp.lambda_s * unc_ce * lp.inv_n / (Bt * Bt * Bt);
       }
     } else if (lp.mode == 1) {
       acc_t2 = warp_sum(acc_t2);
@@ -755,8 +805,10 @@ extern "C" int snb_composite_loss(const float* out, const float* z_vals, int n_r
                                   const float* depth_w, const float* counts, const snb_loss_params* p, float* g_out,
                                   float* loss_terms, void* stream) {
   if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes)) return r;
-  SNB_CHECK_ARG(p && g_out && loss_terms, SNB_ERR_INVALID, "composite_loss: null argument");
-  SNB_CHECK_ARG(p->mode >= 0 && p->mode <= 2, SNB_ERR_INVALID, "composite_loss: mode %d", p->mode);
+  SNB_CHECK_ARG(p && loss_terms && (g_out || p->mode == 3), SNB_ERR_INVALID, "composite_loss: null argument");
+  SNB_CHECK_ARG(p->mode >= 0 && p->mode <= 3, SNB_ERR_INVALID, "composite_loss: mode %d", p->mode);
+  SNB_CHECK_ARG(!(p->sem_unc != 0 && p->mode == 0) || (labels != nullptr && counts != nullptr), SNB_ERR_INVALID,
+                "composite_loss: the uncertainty-weighted semantic loss needs labels and the pre-pass statistics in counts[4:6]");
   SNB_CHECK_ARG(p->mode != 0 || gt_rgb != nullptr, SNB_ERR_INVALID, "composite_loss: the colour loss needs gt_rgb");
   SNB_CHECK_ARG(p->mode != 2 || depth_gt != nullptr, SNB_ERR_INVALID, "composite_loss: the depth loss needs depth_gt");
   SNB_CHECK_ARG(labels == nullptr || counts != nullptr || p->mode != 0, SNB_ERR_INVALID,
@@ -767,6 +819,7 @@ extern "C" int snb_composite_loss(const float* out, const float* z_vals, int n_r
   lp.ignore_index = p->ignore_index; lp.lambda_c = p->lambda_c; lp.car_label = p->car_label; lp.lambda_sc = p->lambda_sc;
   lp.lambda_ds = p->lambda_ds;
   lp.flags = p->flags;
+  lp.sem_unc = p->sem_unc;
   return snb::launch_k3_loss(out, z_vals, n_rays, n_samples, n_out, n_classes, gt_rgb, reinterpret_cast<const long long*>(labels),
                              ray_mask, depth_gt, depth_w, counts, lp, g_out, loss_terms, (cudaStream_t)stream);
 }

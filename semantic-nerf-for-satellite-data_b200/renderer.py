@@ -109,13 +109,15 @@ class B200Renderer:
     def render_loss(self, models: dict, rays, extras, rgbs, semantic=None, *, color: str = "satnerf", lambda_s: float = 0.0,
                     ignore_index: int = -100, lambda_c: float = 0.0, car_label: int = -1, beta_min: float = 0.05,
                     depth=None, depth_weights=None, lambda_ds: float = 0.0, ignore_mask=None, global_rays=None,
-                    reduce_counts=None, render_options=None):
+                    reduce_counts=None, semantic_uncertainty: int = 0, render_options=None):
         """Training fast path: render + the losses that sit on the render outputs + their gradients
         with the compositing fused (snb_composite_loss), without materialising any per-sample output tensor.
         Equivalent to render_rays() followed by SNerfLoss / SatNerfLoss (color = "snerf" / "satnerf", with the solar
         correction when cfgs.pipeline.sc_lambda > 0; NeRF: NerfLoss = color "snerf" without a solar pass) [+ SemanticLoss +
         SemanticCarRegLoss when `semantic` labels are given, `ignore_mask` = the reference's semantic_sparsity_mask,
         semantic/components/training_step.py:58-88], or - with `depth` targets - to the depth-supervision pass + DepthLoss.
+        semantic_uncertainty: 0 = SemanticLoss; 1 = SemanticUncertaintyLoss (`use_beta_for_s`: the cross-entropy mean weighted by
+        the batch mean of 1 / (2 beta^2), semantic/components/loss.py:6-32,68-114); 2 = the same with beta detached.
         Data parallel: `global_rays` = rays of the GLOBAL batch (the means of the reference losses run over it) and
         `reduce_counts` = a callable that sum-all-reduces the masked-mean denominators in place; the per-rank losses then
         add up to the single-process loss on the concatenated batch, and so do the gradients.
@@ -139,7 +141,8 @@ class B200Renderer:
         flags = COMPOSITE_NO_CLAMP if nerf else 0
         p = _lib.LossParams(mode=2 if depth_pass else 0, color=1 if color == "satnerf" else 0, beta_min=beta_min,
                             inv_n=inv_n, lambda_s=lambda_s, ignore_index=ignore_index, lambda_c=lambda_c,
-                            car_label=car_label, lambda_sc=sc_lambda, lambda_ds=lambda_ds, flags=flags)
+                            car_label=car_label, lambda_sc=sc_lambda, lambda_ds=lambda_ds, flags=flags,
+                            sem_unc=int(semantic_uncertainty) if (semantic is not None and not depth_pass) else 0)
         counts = mask = None
         if semantic is not None and not depth_pass:
             semantic = as_labels(semantic)          # the reference's dataset yields uint8 labels; the kernel reads int64
@@ -149,10 +152,10 @@ class B200Renderer:
                 reduce_counts(counts)
         out = mlp_rays(model, emb, enc, aux, sky, extras, n, S, HEADS_DEPTH if depth_pass else HEADS_ALL).view(n, S, -1)
         loss = CompositeLoss.apply(out, z, 0 if depth_pass else C, p, rgbs, None if depth_pass else semantic, depth,
-                                   depth_weights, counts, terms, mask)
+                                   depth_weights, counts, terms, mask, reduce_counts)
         if sc:
             p_sc = _lib.LossParams(mode=1, color=0, beta_min=beta_min, inv_n=inv_n, lambda_s=0.0, ignore_index=-100,
-                                   lambda_c=0.0, car_label=-1, lambda_sc=sc_lambda, lambda_ds=0.0, flags=0)
+                                   lambda_c=0.0, car_label=-1, lambda_sc=sc_lambda, lambda_ds=0.0, flags=0, sem_unc=0)
             out_sc = mlp_rays(model, emb, enc_sc, aux, None, extras, n, S, HEADS_SOLAR).view(n, S, -1)
             loss = loss + CompositeLoss.apply(out_sc, z, 0, p_sc, None, None, None, None, None, terms)
         self.last_counts = counts

@@ -34,7 +34,8 @@ import torch
 from . import _lib, dist as snb_dist
 from ._lib import COMPOSITE_NO_CLAMP, HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, check, ptr, stream
 from .autograd import as_labels, as_ray_mask, t_steps
-from .losses import DepthLoss, NerfLoss, SatNerfLoss, SemanticCarRegLoss, SemanticLoss, SNerfLoss
+from .losses import (DepthLoss, NerfLoss, SatNerfLoss, SemanticCarRegLoss, SemanticLoss, SemanticUncertaintyLoss,
+                     SNerfLoss)
 from .model import NeRFB200, RSSemanticNeRFB200, SatNeRFB200, ShadowNeRFB200
 from .renderer import B200Renderer
 
@@ -137,6 +138,9 @@ class Trainer:
         if kind == "semantic":
             self.semantic_loss = SemanticLoss(p.lambda_s, car_index, ignore_car_index=p.ignore_car_index)
             self.car_reg_loss = SemanticCarRegLoss(p.lambda_c, car_index) if p.use_car_reg_loss else None
+            self.uncertainty_semantic_loss = SemanticUncertaintyLoss(p.lambda_s, car_index,
+                                                                     detach_beta_for_s=getattr(p, "detach_beta_for_s", False),
+                                                                     ignore_car_index=p.ignore_car_index)
         self.lr, self.betas, self.eps = p.learnrate, (0.9, 0.999), 1e-8
         self.step_idx = 0
         # fused_loss: compositing + the loss modules + their backward in one kernel per pass; False runs
@@ -158,7 +162,7 @@ class Trainer:
         self._graphs: Dict[tuple, tuple] = {}
         self._events = None
         self._side = None
-        self._counts = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self._counts = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._terms = torch.zeros(8, dtype=torch.float32, device=self.device)
         self._seed_dev = torch.zeros(2, dtype=torch.int64, device=self.device)    # [rgb batch key, depth batch key]
         self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -209,6 +213,14 @@ class Trainer:
         color = "snerf" if (epoch < p.first_beta_epoch or self.kind in ("snerf", "nerf")) else "satnerf"
         return sem, car, color
 
+    def _sem_unc(self, epoch) -> int:
+        """which semantic loss the step uses (semantic/components/training_step.py:50-75): the plain cross-entropy before
+        `first_beta_epoch` or without `use_beta_for_s`, else the uncertainty-weighted one (2: beta detached)"""
+        p = self.cfgs.pipeline
+        if self.kind != "semantic" or epoch < p.first_beta_epoch or not getattr(p, "use_beta_for_s", False):
+            return 0
+        return 2 if getattr(p, "detach_beta_for_s", False) else 1
+
     def _reduce_counts(self, counts):
         if self.world > 1:
             torch.distributed.all_reduce(counts)
@@ -226,7 +238,7 @@ class Trainer:
                 color=color, lambda_s=p.lambda_s if sem else 0.0,
                 ignore_index=self.car_index if (sem and p.ignore_car_index) else -100,
                 lambda_c=p.lambda_c if car else 0.0, car_label=self.car_index, ignore_mask=mask, global_rays=global_rays,
-                reduce_counts=self._reduce_counts, render_options=opts)
+                reduce_counts=self._reduce_counts, semantic_uncertainty=self._sem_unc(epoch), render_options=opts)
             if depth_batch is not None:
                 w = None if p.ds_noweights else depth_batch["weights"].flatten()
                 l_d, t_d = self.renderer.render_loss(self.models, depth_batch["rays"], depth_batch["extras"], None,
@@ -251,7 +263,8 @@ class Trainer:
                 loss = loss + l_d
                 loss_dict.update(d)
             if sem:
-                l_s, d = self.semantic_loss(results, batch["semantic"], mask)
+                sl = self.uncertainty_semantic_loss if self._sem_unc(epoch) else self.semantic_loss
+                l_s, d = sl(results, batch["semantic"], mask)
                 loss = loss + l_s
                 loss_dict.update(d)
                 if car:
@@ -302,6 +315,10 @@ class Trainer:
         self._seed_dev[1].fill_(self.step_idx + (1 << 20))
         self._step_dev.fill_(self.step_idx)
         counts_done = False
+        sem_unc = self._sem_unc(epoch)
+        if sem_unc and len(pieces) > 1:
+            raise _lib.SnbError("use_beta_for_s needs the whole batch's statistics before any gradient: not available with "
+                                "micro-batching (raise micro_batch or lower the batch size)")
         if len(pieces) > 1 and sem:
             # the masked-mean denominators run over the WHOLE batch (and, data parallel, over every rank's)
             self._counts.zero_()
@@ -325,8 +342,8 @@ class Trainer:
             first, last = i == 0, i == len(pieces) - 1
             offs = (ray_offset[0] + lo, ray_offset[1])
             args = (b, d if first else None, sem, car, color, has_mask, offs, global_rays, global_depth_rays, first, last,
-                    counts_done, n / max(global_rays, 1))
-            cfg = (hi - lo, d.n if d is not None else 0, color, car, has_mask, offs, global_rays, global_depth_rays)
+                    counts_done, n / max(global_rays, 1), sem_unc)
+            cfg = (hi - lo, d.n if d is not None else 0, color, car, has_mask, offs, global_rays, global_depth_rays, sem_unc)
             if self.use_graph and len(pieces) == 1:
                 entry = self._graphs.get(cfg)
                 if entry is None:
@@ -354,7 +371,7 @@ class Trainer:
         return self._loss_out
 
     def _run_direct(self, b, d, sem, car, color, has_mask, ray_offset, global_rays, global_depth_rays, first=True, last=True,
-                    counts_done=False, share=1.0):
+                    counts_done=False, share=1.0, sem_unc=0):
         """K1 -> MLP forward (main, solar) -> K3 + losses (gradients of the packed rows) -> MLP backward (solar, main) ->
         ray-parameter gradients -> [depth batch the same way] -> all-reduce -> Adam -> re-pack.  Every buffer is persistent.
         first / last: this is the first / last micro-batch of the step (zero the accumulators / reduce and step);
@@ -434,7 +451,16 @@ class Trainer:
                              lambda_s=p.lambda_s if sem else 0.0,
                              ignore_index=self.car_index if (sem and p.ignore_car_index) else -100,
                              lambda_c=p.lambda_c if car else 0.0, car_label=self.car_index, lambda_sc=sc_lambda,
-                             lambda_ds=0.0, flags=COMPOSITE_NO_CLAMP if nerf else 0)
+                             lambda_ds=0.0, flags=COMPOSITE_NO_CLAMP if nerf else 0, sem_unc=sem_unc if sem else 0)
+        if sem and sem_unc:
+            # SemanticUncertaintyLoss = lambda_s * CE_mean * mean_r 1 / (2 beta_r^2): both batch means first (mode 3 pre-pass
+            # into counts[4:6]; data parallel: summed over the ranks), then the main pass forms the gradients
+            lp3 = _lib.LossParams.from_buffer_copy(lp)
+            lp3.mode = 3
+            check(lib.snb_composite_loss(ptr(b.out), ptr(b.z), b.n, S, n_out, Cn, None, ptr(b.labels),
+                                         ptr(b.mask) if has_mask else None, None, None, ptr(counts), C.byref(lp3), None,
+                                         counts[4:].data_ptr(), st), "snb_composite_loss (statistics pre-pass)")
+            self._reduce_counts(counts[4:6])
         check(lib.snb_composite_loss(ptr(b.out), ptr(b.z), b.n, S, n_out, Cn, ptr(b.rgbs), ptr(b.labels) if sem else None,
                                      ptr(b.mask) if (sem and has_mask) else None, None, None, ptr(counts), C.byref(lp),
                                      ptr(b.g_out), ptr(self._terms), st), "snb_composite_loss")

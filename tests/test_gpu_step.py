@@ -142,6 +142,52 @@ def test_fused_training_step_matches_the_oracle(kind, C, epoch, with_depth, with
             assert e2.grad.abs().max() == 0 and g_emb.abs().max() == 0
 
 
+@pytest.mark.parametrize("mode,detach", [("direct", False), ("direct", True), ("autograd", False), ("module", False)])
+def test_uncertainty_weighted_semantic_loss_matches_the_oracle(mode, detach):
+    """`use_beta_for_s` (SemanticUncertaintyLoss, semantic/components/loss.py:6-32,68-114): lambda_s * CE_mean * mean_r 1/(2 beta_r^2),
+    a product of two batch means - the fused kernel takes them from a statistics pre-pass.  All three trainer paths against the
+    oracle's loss (pinned to the reference's module by oracle/pin_against_reference.py), with and without detach_beta_for_s."""
+    from semnerf_b200.trainer import Trainer, default_cfgs
+    _lib_or_fail()
+    C, S, n = 6, 64, 640
+    cfgs = default_cfgs("semantic", n_samples=S, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=2, use_beta_for_s=True,
+                        detach_beta_for_s=detach, lambda_s=0.4)   # a larger weight: the term must matter in the gradient
+    kw = {"direct": dict(direct=True), "autograd": dict(direct=False), "module": dict(fused_loss=False)}[mode]
+    tr = Trainer(cfgs, "semantic", C, device=DEV, car_index=CAR, seed=0, **kw)
+    spec = O.ModelSpec(kind="semantic", n_classes=C)
+    params, emb = O.make_params(spec, seed=5)
+    tr.models["coarse"].load_state_dict(params)
+    tr.models["t"].weight.data.copy_(emb)
+    batch, depth = _batches(n, 64, C, seed=23, with_mask=True)
+    assert tr._sem_unc(3) == (2 if detach else 1) and tr._sem_unc(1) == 0      # plain cross-entropy before first_beta_epoch
+    loss = tr.training_step(_to_dev(batch), epoch=3)
+    # the jitter every path drew: Philox keyed on (step 1, ray) - recover z from a render with the same key
+    with torch.no_grad():
+        z = tr.renderer.render_rays(tr.models, batch["rays"].to(DEV), batch["extras"].to(DEV),
+                                    render_options={"seed": 1, "ray_offset": 0, "solar_pass": False})["_z_vals_coarse"].cpu()
+    if mode == "direct":
+        assert torch.equal(z, tr._bufs[("rgb", n)].z.cpu())
+    batch["z"] = z
+    p2 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    e2 = emb.clone().requires_grad_(True)
+    ref, rterms, _ = oracle_step_loss(O, p2, e2, spec, batch, depth, S, ignore_car=True, use_mask=True, car_reg=True,
+                                      use_depth=False, beta_loss=True, lambda_s=0.4, sem_unc=2 if detach else 1)
+    ref.backward()
+    if mode != "module":
+        got = dict(zip(TERMS, tr.last_loss_terms.cpu().tolist()))
+        assert abs(got["semantic"] - rterms["semantic"].item()) <= 1e-2 * rterms["semantic"].item(), (got["semantic"], rterms["semantic"].item())
+    else:
+        assert abs(float(tr.last_loss_dict["coarse_semantic"]) - rterms["semantic"].item()) <= 1e-2 * rterms["semantic"].item()
+    assert abs(loss.item() - ref.item()) <= 1e-2 * abs(ref.item())
+    # NB: the parameters have moved (Adam ran), the gradient buffer still holds this step's gradient
+    g_ref = torch.cat([p2[k].grad.flatten() for k in p2])
+    assert _cos(tr.gbuf[256:].cpu(), g_ref) >= 0.999
+    assert _cos(tr.gbuf[:tr.n_emb].cpu(), e2.grad) >= 0.995
+    # the uncertainty head's own gradient is where detach / no detach differ most
+    off = tr.models["coarse"].offset_of("beta_from_xyz.2.weight")
+    assert _cos(tr.gbuf[256 + off: 256 + off + 256].cpu(), p2["beta_from_xyz.2.weight"].grad) >= 0.995
+
+
 def test_label_dtypes_and_counts_are_device_side():
     """uint8 (N,1) labels (what the reference's dataset yields) and int64 (N,) labels give the same step; the masked-mean
     denominators come from snb_label_counts with the loss kernel's own predicates; out-of-range labels are reported."""

@@ -116,7 +116,7 @@ def test_snerf_state_dict_is_the_reference_shadow_nerf():
 
 
 def test_loss_params_struct_matches_the_header():
-    """ctypes mirror of snb_loss_params: same field order and types as include/snb.h (11 x 4 bytes)."""
+    """ctypes mirror of snb_loss_params: same field order and types as include/snb.h (12 x 4 bytes)."""
     import ctypes
     import os
     import re
@@ -130,7 +130,7 @@ def test_loss_params_struct_matches_the_header():
             typ, names = decl.split(None, 1)
             fields += [(n.strip(), typ) for n in names.split(",")]
     got = [(n, "int" if t is ctypes.c_int else "float") for n, t in _lib.LossParams._fields_]
-    assert got == fields and ctypes.sizeof(_lib.LossParams) == 4 * len(fields) == 44
+    assert got == fields and ctypes.sizeof(_lib.LossParams) == 4 * len(fields) == 48
 
 
 def test_render_loss_signature_and_term_order():
