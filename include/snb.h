@@ -100,7 +100,12 @@ int snb_encode_points(const float* xyz, const float* sun_d, const float* t, int 
  * ---------------------------------------------------------------------------------------------- */
 typedef struct snb_model snb_model; /* opaque host object: architecture + packed-weight layout */
 
-int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid);
+/* variant (semantic model only, 0 = the shipped rs_semantic.toml): head-input variants of semantic/models/rs_semantic.py -
+ * SNB_VARIANT_TJ_FOR_S: the semantic head reads cat(f, t) (`use_tj_for_s`, :207-211,330-338);
+ * SNB_VARIANT_TJ_INSTEAD_OF_BETA: the colour head reads cat(f, t) (`use_tj_instead_of_beta`, :186-189,287-288).
+ * Both are four more weight columns of their hidden block against the aux K-segment [1, sun_d, t]. */
+enum { SNB_VARIANT_TJ_FOR_S = 1, SNB_VARIANT_TJ_INSTEAD_OF_BETA = 2 };
+int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid, int variant);
 void snb_model_destroy(snb_model* m);
 /* number of fp32 parameters / the offset table: parameters live in ONE flat fp32 buffer in the
  * reference state_dict order; names[i], offsets[i], rows[i], cols[i]. */

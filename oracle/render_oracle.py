@@ -71,6 +71,9 @@ class ModelSpec:
     n_freq: int = 10
     full_features: bool = False
     semantic_sigmoid: bool = True  # configs/pipelines/rs_semantic.toml:55
+    # head-input variants of the semantic model (rs_semantic.py:186-215; all off in the shipped TOML)
+    tj_for_s: bool = False             # use_tj_for_s: the semantic head reads cat(f, t)
+    tj_instead_of_beta: bool = False   # use_tj_instead_of_beta: the colour head reads cat(f, t)
 
     @property
     def k0(self) -> int:
@@ -111,14 +114,15 @@ def param_shapes(spec: ModelSpec) -> Dict[str, tuple]:
     s["sigma_from_xyz.0.bias"] = (1,)
     s["feats_from_xyz.weight"] = (f, f)
     s["feats_from_xyz.bias"] = (f,)
-    s["rgb_from_xyzdir.0.weight"] = (fl, f + (spec.kdir if spec.kind == "nerf" else 0))
+    s["rgb_from_xyzdir.0.weight"] = (fl, f + (spec.kdir if spec.kind == "nerf" else 0) +
+                                     (spec.tau if (spec.kind == "semantic" and spec.tj_instead_of_beta) else 0))
     s["rgb_from_xyzdir.0.bias"] = (fl,)
     s["rgb_from_xyzdir.2.weight"] = (3, fl)
     s["rgb_from_xyzdir.2.bias"] = (3,)
     if spec.kind == "nerf":   # nerf.py:140-160: no further heads
         return s
     if spec.kind == "semantic":
-        s["semantic_prediction.0.weight"] = (fl, f)
+        s["semantic_prediction.0.weight"] = (fl, f + (spec.tau if spec.tj_for_s else 0))
         s["semantic_prediction.0.bias"] = (fl,)
         s["semantic_prediction.2.weight"] = (spec.n_classes, fl)
         s["semantic_prediction.2.bias"] = (spec.n_classes,)
@@ -242,7 +246,8 @@ def mlp_forward(p: Dict[str, torch.Tensor], spec: ModelSpec, xyz: torch.Tensor,
         hidden.append(h)
     sigma = F.softplus(_lin(p, "sigma_from_xyz.0", h))
     f = _lin(p, "feats_from_xyz", h)
-    rgb = torch.sigmoid(_lin(p, "rgb_from_xyzdir.2", torch.sin(_lin(p, "rgb_from_xyzdir.0", f))))
+    f_rgb = torch.cat([f, t], -1) if (spec.kind == "semantic" and spec.tj_instead_of_beta) else f   # rs_semantic.py:287-288
+    rgb = torch.sigmoid(_lin(p, "rgb_from_xyzdir.2", torch.sin(_lin(p, "rgb_from_xyzdir.0", f_rgb))))
     rgb = rgb * (1 + 2 * 0.001) - 0.001
     s = torch.cat([f, sun_d], -1)
     s = torch.sin(_lin(p, "sun_v_net.0", s))
@@ -256,7 +261,8 @@ def mlp_forward(p: Dict[str, torch.Tensor], spec: ModelSpec, xyz: torch.Tensor,
     beta = F.softplus(_lin(p, "beta_from_xyz.2", torch.sin(_lin(p, "beta_from_xyz.0", torch.cat([f, t], -1)))))
     cols = [rgb, sigma, sun_v, sky, beta]
     if spec.kind == "semantic":
-        sem = _lin(p, "semantic_prediction.2", torch.sin(_lin(p, "semantic_prediction.0", f)))
+        f_sem = torch.cat([f, t], -1) if spec.tj_for_s else f                                          # rs_semantic.py:330-338
+        sem = _lin(p, "semantic_prediction.2", torch.sin(_lin(p, "semantic_prediction.0", f_sem)))
         if spec.semantic_sigmoid:
             sem = torch.sigmoid(sem)
         cols.append(sem)

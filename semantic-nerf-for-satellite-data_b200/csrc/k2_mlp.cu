@@ -53,6 +53,8 @@ struct snb_model {
   int hh_rgb, hh_beta, hh_sem, hh_sun;
   int kho;  // K of the head-output layer: 512 + 256 + hhw
   int relu, aux_ld, kdir;   // vanilla NeRF: ReLU activations, 32-column aux rows carrying the 24 encoded view-direction values
+  int variant;              // SNB_VARIANT_* head-input variants of the semantic model (rs_semantic.py:186-215)
+  int taux_lo, taux_cols;   // columns of the fused head layer's hidden rows whose blocks take the embedding t as an input
   std::vector<snb::TensorInfo> tensors;
   int64_t n_params;
   // packed bf16 image (element offsets) ----------------------------------------------------------
@@ -186,6 +188,11 @@ static void build_layout(snb_model* m) {
   const bool nerf = m->kind == SNB_MODEL_NERF;   // nerf.py:118-160: trunk, sigma, feats, rgb(f | dir) only
   const bool has_beta = m->kind == SNB_MODEL_SATNERF || sem;   // S-NeRF (snerf.py:161-186) and NeRF have no uncertainty head
   const bool enc60 = k0 == 60;                   // positional encoding input: the [hi | lo | 0] 128-column K1 row
+  // head-input variants (semantic model only): the transient embedding t as an extra input of the semantic head
+  // (`use_tj_for_s`, rs_semantic.py:207-211,330-338) and / or of the colour head (`use_tj_instead_of_beta`, :186-189,287-288):
+  // like the uncertainty head's cat(f, t) (:251-252) they are 4 more weight columns against the aux K-segment [1, sun_d, t]
+  const bool tj_s = sem && (m->variant & SNB_VARIANT_TJ_FOR_S);
+  const bool tj_rgb = sem && (m->variant & SNB_VARIANT_TJ_INSTEAD_OF_BETA);
   // ---- flat fp32 parameter order = reference state_dict order ----
   m->n_params = 0;
   for (int i = 0; i < LAYERS; ++i) {
@@ -197,12 +204,12 @@ static void build_layout(snb_model* m) {
   add_tensor(m, "sigma_from_xyz.0.bias", 1, 0);
   add_tensor(m, "feats_from_xyz.weight", F, F);
   add_tensor(m, "feats_from_xyz.bias", F, 0);
-  add_tensor(m, "rgb_from_xyzdir.0.weight", FL, F + (nerf ? m->kdir : 0));
+  add_tensor(m, "rgb_from_xyzdir.0.weight", FL, F + (nerf ? m->kdir : 0) + (tj_rgb ? tau : 0));
   add_tensor(m, "rgb_from_xyzdir.0.bias", FL, 0);
   add_tensor(m, "rgb_from_xyzdir.2.weight", 3, FL);
   add_tensor(m, "rgb_from_xyzdir.2.bias", 3, 0);
   if (sem) {
-    add_tensor(m, "semantic_prediction.0.weight", FL, F);
+    add_tensor(m, "semantic_prediction.0.weight", FL, F + (tj_s ? tau : 0));
     add_tensor(m, "semantic_prediction.0.bias", FL, 0);
     add_tensor(m, "semantic_prediction.2.weight", C, FL);
     add_tensor(m, "semantic_prediction.2.bias", C, 0);
@@ -251,7 +258,10 @@ static void build_layout(snb_model* m) {
   m->ts4 = take(cur, (long long)FL * FL);
   m->ts2 = take(cur, (long long)FL * FL);
   m->tho = take(cur, (long long)(FL + hhw) * 16);
-  m->taux = take(cur, 16ll * FL);
+  // blocks with a t input: [rgb | beta | sem] are the first three 256-column blocks of the hidden rows
+  m->taux_lo = tj_rgb ? 0 : FL;
+  m->taux_cols = (tj_s ? 3 * FL : 2 * FL) - m->taux_lo;
+  m->taux = take(cur, 16ll * m->taux_cols);
   m->packed_bf16_elems = cur;
   long long bc = 0;
   for (int i = 0; i < LAYERS; ++i) m->bl[i] = take(bc, F);
@@ -290,11 +300,11 @@ static void build_layout(snb_model* m) {
   job(m->tf, ktf, P("feats_from_xyz.weight"), F, F, F, 1, 0);
   job(m->tf + F + 3, ktf, P("sigma_from_xyz.0.weight"), F, F, 1, 1, 0);  // dPre16 column 3 = sigma
   // fused head first layers: rows [rgb | beta | (sem) | sun]  (NeRF: the rgb block only; the others stay zero)
-  struct Blk { int row; const char* w; const char* b; int kin; };
-  std::vector<Blk> blks = {{m->hh_rgb, "rgb_from_xyzdir.0", "rgb_from_xyzdir.0", F + (nerf ? m->kdir : 0)}};
-  if (has_beta) blks.push_back({m->hh_beta, "beta_from_xyz.0", "beta_from_xyz.0", F + tau});
-  if (!nerf) blks.push_back({m->hh_sun, "sun_v_net.0", "sun_v_net.0", F + 3});
-  if (sem) blks.push_back({m->hh_sem, "semantic_prediction.0", "semantic_prediction.0", F});
+  struct Blk { int row; const char* w; const char* b; int kin; bool t_in; };
+  std::vector<Blk> blks = {{m->hh_rgb, "rgb_from_xyzdir.0", "rgb_from_xyzdir.0", F + (nerf ? m->kdir : 0) + (tj_rgb ? tau : 0), tj_rgb}};
+  if (has_beta) blks.push_back({m->hh_beta, "beta_from_xyz.0", "beta_from_xyz.0", F + tau, true});
+  if (!nerf) blks.push_back({m->hh_sun, "sun_v_net.0", "sun_v_net.0", F + 3, false});
+  if (sem) blks.push_back({m->hh_sem, "semantic_prediction.0", "semantic_prediction.0", F + (tj_s ? tau : 0), tj_s});
   for (auto& b : blks) {
     const long long w = P(std::string(b.w) + ".weight"), bb = P(std::string(b.b) + ".bias");
     job(m->wh1 + (long long)b.row * kh1, kh1, w, b.kin, FL, F, 0, 0);
@@ -305,10 +315,12 @@ static void build_layout(snb_model* m) {
     job(m->wh1 + (long long)m->hh_rgb * kh1 + F + 1, kh1, P("rgb_from_xyzdir.0.weight") + F, F + m->kdir, FL, m->kdir, 0, 0);
   } else {
     job(m->wh1 + (long long)m->hh_sun * kh1 + F + 1, kh1, P("sun_v_net.0.weight") + F, F + 3, FL, 3, 0, 0);
-    if (has_beta) {
-      job(m->wh1 + (long long)m->hh_beta * kh1 + F + 4, kh1, P("beta_from_xyz.0.weight") + F, F + tau, FL, tau, 0, 0);
-      job(m->taux + 4 * FL, FL, P("beta_from_xyz.0.weight") + F, F + tau, tau, FL, 1, 0);
-    }
+    for (auto& b : blks)
+      if (b.t_in) {   // aux columns 4..4+tau = t: the block's last tau weight columns; their transpose feeds the dgrad into t
+        const long long w = P(std::string(b.w) + ".weight");
+        job(m->wh1 + (long long)b.row * kh1 + F + 4, kh1, w + F, b.kin, FL, tau, 0, 0);
+        job(m->taux + 4ll * m->taux_cols + (b.row - m->taux_lo), m->taux_cols, w + F, b.kin, tau, FL, 1, 0);
+      }
     job(m->ws2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 0, 0);
     job(m->ts2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 1, 0);
     job(m->ws4, FL, P("sun_v_net.4.weight"), FL, FL, FL, 0, 0);
@@ -379,7 +391,8 @@ static void build_layout(snb_model* m) {
     ujob(P("rgb_from_xyzdir.0.weight") + F, F + m->kdir, m->gh1aux + (long long)m->hh_rgb * gald + 1, gald, FL, m->kdir, 0);
   } else {
     ujob(P("sun_v_net.0.weight") + F, F + 3, m->gh1aux + (long long)m->hh_sun * 16 + 1, 16, FL, 3, 0);
-    if (has_beta) ujob(P("beta_from_xyz.0.weight") + F, F + tau, m->gh1aux + (long long)m->hh_beta * 16 + 4, 16, FL, tau, 0);
+    for (auto& b : blks)
+      if (b.t_in) ujob(P(std::string(b.w) + ".weight") + F, b.kin, m->gh1aux + (long long)b.row * 16 + 4, 16, FL, tau, 0);
     ujob(P("sun_v_net.2.weight"), FL, m->gs2, FL, FL, FL, 0);
     ujob(P("sun_v_net.2.bias"), 1, m->gbs2, 1, FL, 1, 0);
     ujob(P("sun_v_net.4.weight"), FL, m->gs4, FL, FL, FL, 0);
@@ -727,17 +740,22 @@ using namespace snb;
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
-extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid) {
+extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid, int variant) {
   SNB_CHECK_ARG(out != nullptr, SNB_ERR_INVALID, "model_create: null out");
   SNB_CHECK_ARG(model_kind >= SNB_MODEL_SATNERF && model_kind <= SNB_MODEL_SNERF, SNB_ERR_INVALID, "model_create: bad kind %d",
                 model_kind);
   if (model_kind != SNB_MODEL_SEMANTIC) n_classes = 0;
+  SNB_CHECK_ARG(variant == 0 || model_kind == SNB_MODEL_SEMANTIC, SNB_ERR_UNSUPPORTED,
+                "model_create: head-input variants exist for the semantic model only");
+  SNB_CHECK_ARG((variant & ~(SNB_VARIANT_TJ_FOR_S | SNB_VARIANT_TJ_INSTEAD_OF_BETA)) == 0, SNB_ERR_UNSUPPORTED,
+                "model_create: variant bits %d not implemented", variant);
   SNB_CHECK_ARG(n_classes >= 0 && n_classes <= 10 && (model_kind != SNB_MODEL_SEMANTIC || n_classes >= 1),
                 SNB_ERR_UNSUPPORTED, "model_create: n_classes %d outside [1,10]", n_classes);
   snb_model* m = new snb_model();
   m->kind = model_kind;
   m->n_classes = n_classes;
   m->sem_sigmoid = semantic_sigmoid;
+  m->variant = variant;
   m->tau = 4;  // t_embedding_tau (configs/pipelines/*.toml)
   const bool enc60 = model_kind == SNB_MODEL_SEMANTIC || model_kind == SNB_MODEL_NERF;   // positional encoding of xyz (10 frequencies)
   m->k0 = enc60 ? 60 : 3;
@@ -1016,8 +1034,9 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
       SNB_CUDA(cudaMemsetAsync(g_aux, 0, (size_t)P * 16 * sizeof(float), st));   // no embedding-dependent head in this model
     } else if (all && g_aux) {
       // d aux = dY_beta * W_beta0[:, 512:]  -> embedding gradient (summed per ray by the caller-side kernel)
-      Seg sb[1] = {{ws + w.dyhh + (size_t)m->hh_beta * 2, hhw, FL, FL / 64}};
-      GemmArgs& a = add_rows16(p, EPI_F32ROWS, P, sb, 1, pk + m->taux, FL, FL, nullptr);
+      // (over the hidden blocks that take t: the uncertainty block, plus the semantic / colour blocks of the head variants)
+      Seg sb[1] = {{ws + w.dyhh + (size_t)m->taux_lo * 2, hhw, m->taux_cols, m->taux_cols / 64}};
+      GemmArgs& a = add_rows16(p, EPI_F32ROWS, P, sb, 1, pk + m->taux, m->taux_cols, m->taux_cols, nullptr);
       a.f32out = g_aux;
       a.ldo = 16;
     }
@@ -1143,7 +1162,12 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("sun_v_net.6"), FL, B("sun_v_net.6"), 1, F32_SIGMOID, 1.0f, o + 4, n_out)) return r;
     }
     if (!all) continue;
-    if (int r = gemm(sf, nullptr, W("rgb_from_xyzdir.0"), F, B("rgb_from_xyzdir.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
+    {
+      const bool tj_rgb = (m->variant & SNB_VARIANT_TJ_INSTEAD_OF_BETA) != 0;   // cat(f, t) -> colour head (rs_semantic.py:287-288)
+      const F32Seg st_ = per_ray(t, tau);
+      if (int r = gemm(sf, tj_rgb ? &st_ : nullptr, W("rgb_from_xyzdir.0"), F + (tj_rgb ? tau : 0), B("rgb_from_xyzdir.0"), FL,
+                       F32_SIN, 1.0f, g1, FL)) return r;
+    }
     if (int r = gemm(rows(g1, FL, FL), nullptr, W("rgb_from_xyzdir.2"), FL, B("rgb_from_xyzdir.2"), 3, F32_RGB, 1.0f, o, n_out)) return r;
     if (m->find("beta_from_xyz.0.weight") >= 0) {
       const F32Seg st_ = per_ray(t, tau);
@@ -1151,7 +1175,10 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("beta_from_xyz.2"), FL, B("beta_from_xyz.2"), 1, F32_SOFTPLUS, 1.0f, o + 8, n_out)) return r;
     }
     if (sem) {
-      if (int r = gemm(sf, nullptr, W("semantic_prediction.0"), F, B("semantic_prediction.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
+      const bool tj_s = (m->variant & SNB_VARIANT_TJ_FOR_S) != 0;               // cat(f, t) -> semantic head (rs_semantic.py:330-338)
+      const F32Seg st_ = per_ray(t, tau);
+      if (int r = gemm(sf, tj_s ? &st_ : nullptr, W("semantic_prediction.0"), F + (tj_s ? tau : 0), B("semantic_prediction.0"), FL,
+                       F32_SIN, 1.0f, g1, FL)) return r;
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("semantic_prediction.2"), FL, B("semantic_prediction.2"), C,
                        m->sem_sigmoid ? F32_SIGMOID : F32_NONE, 1.0f, o + 9, n_out)) return r;
     }

@@ -23,13 +23,13 @@ from ._lib import HEADS_ALL, MODEL_NERF, MODEL_SATNERF, MODEL_SEMANTIC, MODEL_SN
 class SnbMLP(torch.nn.Module):
     """Common base: owns the libsnb model handle, the flat parameter and the packed bf16 image."""
 
-    def __init__(self, kind: int, n_classes: int, semantic_sigmoid: bool, tau: int, cfgs=None):
+    def __init__(self, kind: int, n_classes: int, semantic_sigmoid: bool, tau: int, cfgs=None, variant: int = 0):
         super().__init__()
         if tau != 4:
             raise _lib.SnbError("libsnb implements t_embedding_tau = 4 (the value in every shipped config)")
         lib = _lib.load()
         h = C.c_void_p()
-        check(lib.snb_model_create(C.byref(h), kind, n_classes, 1 if semantic_sigmoid else 0), "snb_model_create")
+        check(lib.snb_model_create(C.byref(h), kind, n_classes, 1 if semantic_sigmoid else 0, variant), "snb_model_create")
         self._h = h
         self.kind = kind
         self.semantic_n_classes = n_classes          # read by the reference's inference(), rs_semantic.py:95
@@ -187,13 +187,16 @@ class RSSemanticNeRFB200(SnbMLP):
 
     def __init__(self, cfgs, dataset_semantic):
         p = cfgs.pipeline
-        unsupported = [k for k in ("use_tj_for_s", "use_tj_instead_of_beta", "use_separate_beta_for_s",
-                                   "use_separate_tj_for_semantic", "fc_use_full_features") if getattr(p, k, False)]
+        unsupported = [k for k in ("use_separate_beta_for_s", "use_separate_tj_for_semantic", "fc_use_full_features")
+                       if getattr(p, k, False)]
         if unsupported or p.fc_layers != 8 or p.fc_units != 512 or list(p.fc_skips) != [4] \
                 or p.activation_function != "siren" or p.mapping_pos_n_freq != 10:
             raise _lib.SnbError(f"libsnb implements the shipped rs_semantic.toml architecture; unsupported: {unsupported}")
         sig = p.semantic_activation_function == "sigmoid"
-        super().__init__(MODEL_SEMANTIC, int(dataset_semantic.semantic_n_classes), sig, p.t_embedding_tau, cfgs)
+        # head-input variants: t as an extra input of the semantic head / of the colour head (rs_semantic.py:186-215)
+        variant = (_lib.VARIANT_TJ_FOR_S if getattr(p, "use_tj_for_s", False) else 0) | \
+                  (_lib.VARIANT_TJ_INSTEAD_OF_BETA if getattr(p, "use_tj_instead_of_beta", False) else 0)
+        super().__init__(MODEL_SEMANTIC, int(dataset_semantic.semantic_n_classes), sig, p.t_embedding_tau, cfgs, variant)
         self.cfg = p
         self.layers, self.skips = p.fc_layers, list(p.fc_skips)
 

@@ -210,14 +210,19 @@ class Trainer:
         p = self.cfgs.pipeline
         sem = self.kind == "semantic"
         car = sem and self.car_reg_loss is not None and epoch >= p.car_reg_loss_start
-        color = "snerf" if (epoch < p.first_beta_epoch or self.kind in ("snerf", "nerf")) else "satnerf"
+        color = "snerf" if (epoch < self._first_beta_epoch() or self.kind in ("snerf", "nerf")) else "satnerf"
         return sem, car, color
+
+    def _first_beta_epoch(self):
+        """`use_tj_instead_of_beta` disables the beta loss for good (semantic/pipelines/rs_semantic.py:28-33)"""
+        p = self.cfgs.pipeline
+        return 10 ** 7 if getattr(p, "use_tj_instead_of_beta", False) else p.first_beta_epoch
 
     def _sem_unc(self, epoch) -> int:
         """which semantic loss the step uses (semantic/components/training_step.py:50-75): the plain cross-entropy before
         `first_beta_epoch` or without `use_beta_for_s`, else the uncertainty-weighted one (2: beta detached)"""
         p = self.cfgs.pipeline
-        if self.kind != "semantic" or epoch < p.first_beta_epoch or not getattr(p, "use_beta_for_s", False):
+        if self.kind != "semantic" or epoch < self._first_beta_epoch() or not getattr(p, "use_beta_for_s", False):
             return 0
         return 2 if getattr(p, "detach_beta_for_s", False) else 1
 

@@ -20,7 +20,7 @@ def make_cfgs(spec, n_samples: int, sc_lambda: float):
         t_embedding_tau=spec.tau, t_embedding_vocab=spec.vocab, activation_function="siren",
         mapping_pos_n_freq=spec.n_freq, mapping_dir_n_freq=4,
         semantic_activation_function="sigmoid" if spec.semantic_sigmoid else "none",
-        use_tj_for_s=False, use_tj_instead_of_beta=False, use_beta_for_s=False,
+        use_tj_for_s=spec.tj_for_s, use_tj_instead_of_beta=spec.tj_instead_of_beta, use_beta_for_s=False,
         use_separate_beta_for_s=False, use_separate_tj_for_semantic=False)
     return types.SimpleNamespace(pipeline=pl)
 
@@ -38,13 +38,15 @@ GOLDEN_CASES = [
     ("snerf_s8_nosc", "snerf", 0, 512, 16, 8, 0.0, 9),
     ("nerf_s64", "nerf", 0, 512, 24, 64, 0.0, 10),
     ("nerf_s8", "nerf", 0, 512, 16, 8, 0.0, 11),
+    ("sem_c6_s8_tj", "semantic", 6, 512, 16, 8, 0.05, 12),      # use_tj_for_s + use_tj_instead_of_beta
 ]
 
 
 def golden_inputs(case):
     from oracle import render_oracle as O
     name, kind, C, feat, n, s, sc, seed = case
-    spec = O.ModelSpec(kind=kind, n_classes=C, feat=feat)
+    tj = name.endswith("_tj")
+    spec = O.ModelSpec(kind=kind, n_classes=C, feat=feat, tj_for_s=tj, tj_instead_of_beta=tj)
     params, emb = O.make_params(spec, seed=seed, trained_like=name.endswith("trained"))
     rays, extras = O.synthetic_rays(n, seed=seed)
     rng = np.random.Generator(np.random.PCG64(seed + 77))

@@ -58,7 +58,8 @@ def test_render_rays_against_reference_golden(case):
     _lib_or_fail()
     name, kind, C, feat, n, s, sc, seed = case
     spec, params, emb, rays, extras, u, gold = golden_inputs(case)
-    _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"))
+    _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"),
+                                     tj=name.endswith("_tj"))
     renderer = B200Renderer(cfgs)
     with torch.no_grad():
         models = {"coarse": model} if kind in ("snerf", "nerf") else {"coarse": model, "t": t}
@@ -82,12 +83,18 @@ def test_render_rays_against_reference_golden(case):
         assert np.abs(got - g).max() <= tol, (k, np.abs(got - g).max())
 
 
-@pytest.mark.parametrize("kind,C,sc", [("semantic", 6, 0.05), ("satnerf", 0, 0.05), ("semantic", 6, 0.0)])
-def test_render_rays_keys_values_and_gradients(kind, C, sc):
+@pytest.mark.parametrize("kind,C,sc,tj", [("semantic", 6, 0.05, False), ("satnerf", 0, 0.05, False), ("semantic", 6, 0.0, False),
+                                          ("semantic", 6, 0.05, True)])
+def test_render_rays_keys_values_and_gradients(kind, C, sc, tj):
+    """tj: the head-input variants use_tj_for_s + use_tj_instead_of_beta (the embedding also feeds the semantic and the colour
+    head, rs_semantic.py:186-215) - their extra weight columns and the embedding gradient through three hidden blocks"""
     from semnerf_b200.renderer import B200Renderer
     _lib_or_fail()
     S, n = 64, 512
-    spec, params, emb, cfgs, model, t = _model(kind, C, seed=1, S=S, sc=sc)
+    spec, params, emb, cfgs, model, t = _model(kind, C, seed=1, S=S, sc=sc, tj=tj)
+    if tj:
+        assert tuple(model.state_dict()["semantic_prediction.0.weight"].shape) == (256, 516)
+        assert tuple(model.state_dict()["rgb_from_xyzdir.0.weight"].shape) == (256, 516)
     rays, extras = O.synthetic_rays(n, seed=11)
     u = torch.rand(n, S, generator=torch.Generator().manual_seed(3))
     p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
@@ -218,7 +225,8 @@ def test_fp32_mode_render_rays_against_reference_golden(case):
     _lib_or_fail()
     name, kind, C, feat, n, s, sc, seed = case
     spec, params, emb, rays, extras, u, gold = golden_inputs(case)
-    _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"))
+    _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"),
+                                     tj=name.endswith("_tj"))
     renderer = B200Renderer(cfgs)
     with torch.no_grad():
         models = {"coarse": model} if kind in ("snerf", "nerf") else {"coarse": model, "t": t}
