@@ -103,8 +103,10 @@ typedef struct snb_model snb_model; /* opaque host object: architecture + packed
 /* variant (semantic model only, 0 = the shipped rs_semantic.toml): head-input variants of semantic/models/rs_semantic.py -
  * SNB_VARIANT_TJ_FOR_S: the semantic head reads cat(f, t) (`use_tj_for_s`, :207-211,330-338);
  * SNB_VARIANT_TJ_INSTEAD_OF_BETA: the colour head reads cat(f, t) (`use_tj_instead_of_beta`, :186-189,287-288).
- * Both are four more weight columns of their hidden block against the aux K-segment [1, sun_d, t]. */
-enum { SNB_VARIANT_TJ_FOR_S = 1, SNB_VARIANT_TJ_INSTEAD_OF_BETA = 2 };
+ * Both are four more weight columns of their hidden block against the aux K-segment [1, sun_d, t].
+ * SNB_VARIANT_SEPARATE_BETA_S: a second uncertainty head `semantic_beta_from_xyz` (`use_separate_beta_for_s`, :228-237,
+ * 297-303): cat(f, t) -> 256 -> softplus, packed column 9, the class scores move to columns 10.. (n_classes <= 9). */
+enum { SNB_VARIANT_TJ_FOR_S = 1, SNB_VARIANT_TJ_INSTEAD_OF_BETA = 2, SNB_VARIANT_SEPARATE_BETA_S = 4 };
 int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid, int variant);
 void snb_model_destroy(snb_model* m);
 /* number of fp32 parameters / the offset table: parameters live in ONE flat fp32 buffer in the
@@ -176,8 +178,11 @@ int snb_ray_param_backward(const snb_model* m, const float* params, const float*
  * (satnerf.py:73-96, rs_semantic.py:81-126, _logit_to_label :131-136) and their autograd.
  * ---------------------------------------------------------------------------------------------- */
 /* flags: SNB_COMPOSITE_NO_CLAMP - the composited colour is NOT clamped to [0, 1]: NeRF's inference
- * (baseline/models/nerf.py:73-86) returns the raw sum, SatNeRF / S-NeRF / semantic clamp (satnerf.py:79, rs_semantic.py:103) */
-enum { SNB_COMPOSITE_NO_CLAMP = 1 };
+ * (baseline/models/nerf.py:73-86) returns the raw sum, SatNeRF / S-NeRF / semantic clamp (satnerf.py:79, rs_semantic.py:103);
+ * SNB_COMPOSITE_BETA_S - packed column 9 is the separate semantic uncertainty (`use_separate_beta_for_s`,
+ * semantic/models/rs_semantic.py:90-96): the class scores start at column 10 instead of 9; the fused loss uses its composited
+ * value for the uncertainty-weighted semantic loss and adds its log term (loss_terms[7], without the constant 3/2 lambda_s) */
+enum { SNB_COMPOSITE_NO_CLAMP = 1, SNB_COMPOSITE_BETA_S = 2 };
 int snb_composite_forward(const float* out, const float* z_vals, int n_rays, int n_samples, int n_out,
                           int n_classes, int flags, float* rgb, float* depth, float* weights, float* transparency,
                           float* sem_logits, int64_t* sem_label, void* stream);
@@ -209,7 +214,8 @@ int snb_composite_backward(const float* out, const float* z_vals, int n_rays, in
  *   produces them (NULL without labels).  Data parallel: all-reduce (sum) them first and pass inv_n = 1 / GLOBAL rays, so the
  *   per-rank terms add up to the global-batch loss and the summed gradients are the global-batch gradients;
  * g_out (P, n_out) f32 = d(sum of the terms)/d(out); loss_terms: device float[8], ACCUMULATED:
- * [0] colour [1] log-beta without its constant 3/2 [2] cross-entropy [3] car reg [4] sc term 2 [5] sc term 3 [6] depth. */
+ * [0] colour [1] log-beta without its constant 3/2 [2] cross-entropy [3] car reg [4] sc term 2 [5] sc term 3 [6] depth
+ * [7] log-beta of the separate semantic uncertainty (without its constant 3/2 lambda_s). */
 typedef struct snb_loss_params {
   int mode, color;
   float beta_min, inv_n;     /* inv_n = 1 / (rays of the batch): the means of the reference losses */

@@ -33,7 +33,7 @@ def ref_cfgs(spec: O.ModelSpec, n_samples: int, sc_lambda: float):
         mapping_pos_n_freq=spec.n_freq, mapping_dir_n_freq=4,
         semantic_activation_function="sigmoid" if spec.semantic_sigmoid else "none",
         use_tj_for_s=spec.tj_for_s, use_tj_instead_of_beta=spec.tj_instead_of_beta, use_beta_for_s=False,
-        use_separate_beta_for_s=False, use_separate_tj_for_semantic=False)
+        use_separate_beta_for_s=spec.separate_beta_s, use_separate_tj_for_semantic=False)
     return types.SimpleNamespace(pipeline=pl)
 
 
@@ -90,16 +90,19 @@ CASES = [
     ("nerf_s8", "nerf", 0, 512, 16, 8, 0.0, 11),
     # head-input variants (a "_tj" name: use_tj_for_s + use_tj_instead_of_beta, rs_semantic.py:186-215)
     ("sem_c6_s8_tj", "semantic", 6, 512, 16, 8, 0.05, 12),
+    # a "_bs" name: use_separate_beta_for_s (second uncertainty head, rs_semantic.py:228-237); C = 9 fills the 16 head rows
+    ("sem_c9_s8_bs", "semantic", 9, 512, 16, 8, 0.05, 13),
 ]
 
 GOLDEN_KEYS = ["rgb_coarse", "depth_coarse", "weights_coarse", "transparency_coarse",
                "semantic_logits_coarse", "semantic_label_coarse", "sun_sc_coarse",
-               "weights_sc_coarse", "beta_coarse", "sigmas_coarse", "sun_coarse"]
+               "weights_sc_coarse", "beta_coarse", "sigmas_coarse", "sun_coarse", "beta_semantic_coarse"]
 
 
 def case_inputs(name, kind, C, feat, n, s, sc, seed):
     tj = name.endswith("_tj")
-    spec = O.ModelSpec(kind=kind, n_classes=C, feat=feat, tj_for_s=tj, tj_instead_of_beta=tj)
+    spec = O.ModelSpec(kind=kind, n_classes=C, feat=feat, tj_for_s=tj, tj_instead_of_beta=tj,
+                       separate_beta_s=name.endswith("_bs"))
     params, emb = O.make_params(spec, seed=seed, trained_like=name.endswith("trained"))
     rays, extras = O.synthetic_rays(n, seed=seed)
     rng = np.random.Generator(np.random.PCG64(seed + 77))
@@ -253,6 +256,38 @@ def pin_batched_and_pointcloud(write):
         np.savez_compressed(os.path.join(REPO, "tests", "golden", f"{name}.npz"), **gold)
 
 
+def pin_separate_beta_uncertainty_loss():
+    """`use_beta_for_s` + `use_separate_beta_for_s`: SemanticUncertaintyLoss on a render that carries `beta_semantic_coarse`
+    (semantic/components/loss.py:6-32: the semantic head's own uncertainty, plus its log term), value and gradients, with and
+    without `detach_beta_for_s`."""
+    from semantic.components.loss import SemanticUncertaintyLoss
+    case = [c for c in CASES if c[0].endswith("_bs")][0]
+    name, kind, C, feat, n, s, sc, seed = case
+    spec, params, emb, rays, extras, u = case_inputs(*case)
+    z = O.sample_z(rays, s, u)
+    lab = torch.randint(0, C, (n, 1), generator=torch.Generator().manual_seed(seed)).to(torch.uint8)
+    for det in (False, True):
+        cfgs, model, models, renderer = build_reference(spec, params, emb, s, sc)
+        ref = ref_render(renderer, models, cfgs, rays, extras, z)
+        assert "beta_semantic_coarse" in ref
+        a, _ = SemanticUncertaintyLoss(0.04, 4, detach_beta_for_s=det, ignore_car_index=True)(ref, lab, None)
+        a.backward()
+        p2 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        e2 = emb.clone().requires_grad_(True)
+        res = O.render_rays(p2, e2, spec, rays, extras, s, z=z, sc_lambda=sc)
+        b = O.semantic_uncertainty_loss(res, lab, 0.04, 4, None, detach_beta=det)
+        b.backward()
+        assert abs(a.item() - b.item()) <= 2e-6 * max(1.0, abs(a.item())), (det, a.item(), b.item())
+        num = da = db = 0.0
+        for k, prm in model.named_parameters():
+            ga = prm.grad.flatten().double() if prm.grad is not None else torch.zeros(prm.numel(), dtype=torch.float64)
+            gb = p2[k].grad.flatten().double() if p2[k].grad is not None else torch.zeros(prm.numel(), dtype=torch.float64)
+            num += float(ga @ gb); da += float(ga @ ga); db += float(gb @ gb)
+        cos = num / max(1e-300, (da * db) ** 0.5)
+        assert cos > 1 - 1e-9, (det, cos)
+        print(f"{name}: SemanticUncertaintyLoss with the separate head, detach={det}: {a.item():.6f}, grad cosine {cos:.12f}")
+
+
 def main(write=True):
     torch.manual_seed(0)
     torch.set_num_threads(8)
@@ -345,6 +380,7 @@ def main(write=True):
             gold["grad_norms"] = np.array([prm.grad.norm().item() for _, prm in model.named_parameters()])
             np.savez_compressed(os.path.join(REPO, "tests", "golden", f"{name}.npz"), **gold)
     pin_losses_and_steps(write)
+    pin_separate_beta_uncertainty_loss()
     pin_batched_and_pointcloud(write)
     print("oracle pinned against reference; golden vectors written" if write else "oracle pinned")
 

@@ -74,6 +74,7 @@ class ModelSpec:
     # head-input variants of the semantic model (rs_semantic.py:186-215; all off in the shipped TOML)
     tj_for_s: bool = False             # use_tj_for_s: the semantic head reads cat(f, t)
     tj_instead_of_beta: bool = False   # use_tj_instead_of_beta: the colour head reads cat(f, t)
+    separate_beta_s: bool = False      # use_separate_beta_for_s: a second uncertainty head, output column 9 (rs_semantic.py:228-237)
 
     @property
     def k0(self) -> int:
@@ -93,7 +94,7 @@ class ModelSpec:
             return 4
         if self.kind == "snerf":
             return 8
-        return 9 + (self.n_classes if self.kind == "semantic" else 0)
+        return 9 + ((self.n_classes + (1 if self.separate_beta_s else 0)) if self.kind == "semantic" else 0)
 
 
 def param_shapes(spec: ModelSpec) -> Dict[str, tuple]:
@@ -143,6 +144,11 @@ def param_shapes(spec: ModelSpec) -> Dict[str, tuple]:
     s["beta_from_xyz.0.bias"] = (fl,)
     s["beta_from_xyz.2.weight"] = (1, fl)
     s["beta_from_xyz.2.bias"] = (1,)
+    if spec.kind == "semantic" and spec.separate_beta_s:
+        s["semantic_beta_from_xyz.0.weight"] = (fl, f + spec.tau)
+        s["semantic_beta_from_xyz.0.bias"] = (fl,)
+        s["semantic_beta_from_xyz.2.weight"] = (1, fl)
+        s["semantic_beta_from_xyz.2.bias"] = (1,)
     return s
 
 
@@ -260,6 +266,9 @@ def mlp_forward(p: Dict[str, torch.Tensor], spec: ModelSpec, xyz: torch.Tensor,
         return (out, hidden, f) if return_hidden else out
     beta = F.softplus(_lin(p, "beta_from_xyz.2", torch.sin(_lin(p, "beta_from_xyz.0", torch.cat([f, t], -1)))))
     cols = [rgb, sigma, sun_v, sky, beta]
+    if spec.kind == "semantic" and spec.separate_beta_s:   # rs_semantic.py:297-303
+        cols.append(F.softplus(_lin(p, "semantic_beta_from_xyz.2",
+                                    torch.sin(_lin(p, "semantic_beta_from_xyz.0", torch.cat([f, t], -1))))))
     if spec.kind == "semantic":
         f_sem = torch.cat([f, t], -1) if spec.tj_for_s else f                                          # rs_semantic.py:330-338
         sem = _lin(p, "semantic_prediction.2", torch.sin(_lin(p, "semantic_prediction.0", f_sem)))
@@ -309,8 +318,8 @@ def convert_sigmas(sigmas: torch.Tensor, z: torch.Tensor):
     return weights, depth, transparency, alphas
 
 
-def composite(out: torch.Tensor, z: torch.Tensor, n_classes: int = 0) -> Dict[str, torch.Tensor]:
-    """Tail of ``inference``: satnerf.py:73-96 / rs_semantic.py:81-126.  ``out`` is (N,S,9[+C])."""
+def composite(out: torch.Tensor, z: torch.Tensor, n_classes: int = 0, separate_beta_s: bool = False) -> Dict[str, torch.Tensor]:
+    """Tail of ``inference``: satnerf.py:73-96 / rs_semantic.py:81-126.  ``out`` is (N,S,9[+1][+C])."""
     rgbs, sigmas = out[..., :3], out[..., 3]
     weights, depth, transparency, _ = convert_sigmas(sigmas, z)
     if out.shape[-1] == 4:   # NeRF's inference (nerf.py:73-86): plain emission-absorption, no lighting model, no clamp
@@ -327,7 +336,10 @@ def composite(out: torch.Tensor, z: torch.Tensor, n_classes: int = 0) -> Dict[st
         res["beta"] = out[..., 8:9]
         res["sigmas"] = sigmas
     if n_classes > 0:
-        sem = out[..., 9:9 + n_classes]
+        so = 10 if separate_beta_s else 9                      # rs_semantic.py:90-96
+        if separate_beta_s:
+            res["beta_semantic"] = out[..., 9:10]
+        sem = out[..., so:so + n_classes]
         logits = torch.sum(weights.unsqueeze(-1) * sem, -2)
         res["semantic_logits"] = logits
         # rs_semantic.py:131-136: argmax(softmax(x)) == argmax(x)
@@ -342,7 +354,8 @@ def inference(p, spec: ModelSpec, xyz: torch.Tensor, z: torch.Tensor, sun_d: tor
     n, s = z.shape
     out = mlp_forward(p, spec, xyz.reshape(-1, 3), torch.repeat_interleave(sun_d, s, 0),
                       torch.repeat_interleave(t, s, 0) if t is not None else None)
-    return composite(out.view(n, s, -1), z, spec.n_classes if spec.kind == "semantic" else 0)
+    return composite(out.view(n, s, -1), z, spec.n_classes if spec.kind == "semantic" else 0,
+                     spec.kind == "semantic" and spec.separate_beta_s)
 
 
 def render_rays(p, emb: torch.Tensor, spec: ModelSpec, rays: torch.Tensor, extras: torch.Tensor,

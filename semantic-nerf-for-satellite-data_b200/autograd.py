@@ -260,7 +260,7 @@ class Composite(torch.autograd.Function):
         return g_out, None, None, None
 
 
-LOSS_TERMS = ("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3", "ds")
+LOSS_TERMS = ("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3", "ds", "semantic_logbeta")
 
 
 def label_counts(labels, ray_mask, n_classes: int, ignore_index: int, car_label: int, counts=None):
@@ -324,6 +324,8 @@ class CompositeLoss(torch.autograd.Function):
         if params.mode == 0 and params.color == 1:
             # (3 + mean log beta) / 2: the constant of the log-beta term (loss.py:26); a data-parallel shard carries its share
             loss = loss + 1.5 * n * params.inv_n
+        if params.mode == 0 and params.sem_unc and (params.flags & _lib.COMPOSITE_BETA_S):
+            loss = loss + 1.5 * params.lambda_s * n * params.inv_n   # the separate semantic uncertainty's log term (loss.py:27-30)
         return loss
 
     @staticmethod

@@ -554,11 +554,13 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
                 o[5] = o[6] = o[7] = 0.f;
               }
               o[8] = (hm & SNB_HEAD_BETA) ? (x[5] > 20.f ? x[5] : log1pf(expf(x[5]))) : 0.f;
+              const int bs = args.beta_s;
+              if (bs) o[9] = (hm & SNB_HEAD_BETA) ? (x[6] > 20.f ? x[6] : log1pf(expf(x[6]))) : 0.f;
 #pragma unroll
               for (int cc = 0; cc < 10; ++cc) {
                 if (cc < args.n_classes) {
-                  const float sv = x[6 + cc];
-                  o[9 + cc] = (hm & SNB_HEAD_SEM) ? (args.sem_sigmoid ? 1.0f / (1.0f + expf(-sv)) : sv) : 0.f;
+                  const float sv = bs ? x[(7 + cc) & 15] : x[6 + cc];   // (n_classes <= 9 with the extra head: 7 + cc <= 15)
+                  o[9 + bs + cc] = (hm & SNB_HEAD_SEM) ? (args.sem_sigmoid ? 1.0f / (1.0f + expf(-sv)) : sv) : 0.f;
                 }
               }
             }

@@ -66,6 +66,8 @@ struct ChainArgs {
   const float* sky;     // (rays or points, 3) per-ray sky colour from K1
   int n_out, rows_per_ray, n_classes, sem_sigmoid, head_mask;
   int nerf;             // head output: the sun column is written as 1 (no lighting model: irradiance = 1 in K3)
+  int beta_s;           // head output: pre-activation row 6 is the separate semantic uncertainty head (packed column 9, softplus);
+                        // the class rows / columns follow it
   int exp;              // SNB_EXPERIMENTS builds only (env SNB_EXP): bit 0 skip every second B load, bit 1 every second A load,
                         // bit 2 skip the epilogue math, bit 3 skip the TMA stores, bit 4 skip the multiplicand loads
   ChainMaps maps[CHAIN_MAX_LAYERS];

@@ -50,7 +50,8 @@ struct PackJob {
 struct snb_model {
   int kind, n_classes, sem_sigmoid;
   int k0, enc_ld, w0_ld, hhw, n_out, tau;   // enc_ld: K1 row width; w0_ld: packed K of the first layer
-  int hh_rgb, hh_beta, hh_sem, hh_sun;
+  int hh_rgb, hh_beta, hh_sem, hh_bs, hh_sun;
+  int beta_s;   // use_separate_beta_for_s: a second uncertainty head (packed column 9, head pre-activation row 6)
   int kho;  // K of the head-output layer: 512 + 256 + hhw
   int relu, aux_ld, kdir;   // vanilla NeRF: ReLU activations, 32-column aux rows carrying the 24 encoded view-direction values
   int variant;              // SNB_VARIANT_* head-input variants of the semantic model (rs_semantic.py:186-215)
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(256) unpack_kernel(const __grid_constant__ Job
 // g_out (P, n_out) fp32 + out -> gradient w.r.t. the 16 head pre-activations (bf16) + their column sums
 __global__ void __launch_bounds__(256)
 head_grad_kernel(const float* __restrict__ out, const float* __restrict__ g_out, long long P, int n_out, int C,
-                 int sem_sigmoid, int head_mask, __nv_bfloat16* __restrict__ dpre, float* __restrict__ gb_ho) {
+                 int sem_sigmoid, int head_mask, int beta_s, __nv_bfloat16* __restrict__ dpre, float* __restrict__ gb_ho) {
   __shared__ float red[16];
   if (threadIdx.x < 16) red[threadIdx.x] = 0.f;
   __syncthreads();
@@ -144,10 +145,12 @@ head_grad_kernel(const float* __restrict__ out, const float* __restrict__ g_out,
     if (head_mask & SNB_HEAD_SIGMA) d[3] = g[3] * -expm1f(-o[3]);
     if (head_mask & SNB_HEAD_SUN) d[4] = g[4] * o[4] * (1.0f - o[4]);
     if (head_mask & SNB_HEAD_BETA) d[5] = g[8] * -expm1f(-o[8]);
+    if (beta_s && (head_mask & SNB_HEAD_BETA)) d[6] = g[9] * -expm1f(-o[9]);   // semantic uncertainty head (softplus)
     if (head_mask & SNB_HEAD_SEM) {
+      const int so = 9 + beta_s, ro = 6 + beta_s;
 #pragma unroll
       for (int c = 0; c < 10; ++c)
-        if (c < C) d[6 + c] = sem_sigmoid ? g[9 + c] * o[9 + c] * (1.0f - o[9 + c]) : g[9 + c];
+        if (c < C && ro + c < 16) d[ro + c] = sem_sigmoid ? g[so + c] * o[so + c] * (1.0f - o[so + c]) : g[so + c];
     }
     __align__(16) __nv_bfloat16 row[16];
 #pragma unroll
@@ -193,6 +196,7 @@ static void build_layout(snb_model* m) {
   // like the uncertainty head's cat(f, t) (:251-252) they are 4 more weight columns against the aux K-segment [1, sun_d, t]
   const bool tj_s = sem && (m->variant & SNB_VARIANT_TJ_FOR_S);
   const bool tj_rgb = sem && (m->variant & SNB_VARIANT_TJ_INSTEAD_OF_BETA);
+  const bool bs = m->beta_s != 0;   // semantic_beta_from_xyz (rs_semantic.py:228-237): cat(f, t) -> 256 -> 1, softplus
   // ---- flat fp32 parameter order = reference state_dict order ----
   m->n_params = 0;
   for (int i = 0; i < LAYERS; ++i) {
@@ -234,6 +238,12 @@ static void build_layout(snb_model* m) {
     add_tensor(m, "beta_from_xyz.2.weight", 1, FL);
     add_tensor(m, "beta_from_xyz.2.bias", 1, 0);
   }
+  if (bs) {
+    add_tensor(m, "semantic_beta_from_xyz.0.weight", FL, F + tau);
+    add_tensor(m, "semantic_beta_from_xyz.0.bias", FL, 0);
+    add_tensor(m, "semantic_beta_from_xyz.2.weight", 1, FL);
+    add_tensor(m, "semantic_beta_from_xyz.2.bias", 1, 0);
+  }
 
   auto P = [&](const std::string& n) { return m->find(n.c_str()); };
   auto fcw = [&](int i) { return P("fc_net." + std::to_string(2 * i) + ".weight"); };
@@ -260,7 +270,7 @@ static void build_layout(snb_model* m) {
   m->tho = take(cur, (long long)(FL + hhw) * 16);
   // blocks with a t input: [rgb | beta | sem] are the first three 256-column blocks of the hidden rows
   m->taux_lo = tj_rgb ? 0 : FL;
-  m->taux_cols = (tj_s ? 3 * FL : 2 * FL) - m->taux_lo;
+  m->taux_cols = (bs ? 4 * FL : (tj_s ? 3 * FL : 2 * FL)) - m->taux_lo;
   m->taux = take(cur, 16ll * m->taux_cols);
   m->packed_bf16_elems = cur;
   long long bc = 0;
@@ -305,6 +315,7 @@ static void build_layout(snb_model* m) {
   if (has_beta) blks.push_back({m->hh_beta, "beta_from_xyz.0", "beta_from_xyz.0", F + tau, true});
   if (!nerf) blks.push_back({m->hh_sun, "sun_v_net.0", "sun_v_net.0", F + 3, false});
   if (sem) blks.push_back({m->hh_sem, "semantic_prediction.0", "semantic_prediction.0", F + (tj_s ? tau : 0), tj_s});
+  if (bs) blks.push_back({m->hh_bs, "semantic_beta_from_xyz.0", "semantic_beta_from_xyz.0", F + tau, true});
   for (auto& b : blks) {
     const long long w = P(std::string(b.w) + ".weight"), bb = P(std::string(b.b) + ".bias");
     job(m->wh1 + (long long)b.row * kh1, kh1, w, b.kin, FL, F, 0, 0);
@@ -332,12 +343,15 @@ static void build_layout(snb_model* m) {
   if (!nerf) job(m->who + 4ll * kho + F, kho, P("sun_v_net.6.weight"), FL, 1, FL, 0, 0);
   job(m->who + 0ll * kho + F + FL + m->hh_rgb, kho, P("rgb_from_xyzdir.2.weight"), FL, 3, FL, 0, 0);
   if (has_beta) job(m->who + 5ll * kho + F + FL + m->hh_beta, kho, P("beta_from_xyz.2.weight"), FL, 1, FL, 0, 0);
-  if (sem) job(m->who + 6ll * kho + F + FL + m->hh_sem, kho, P("semantic_prediction.2.weight"), FL, C, FL, 0, 0);
+  const int ro = 6 + (bs ? 1 : 0);   // first semantic row of the 16 head pre-activations (row 6 = the semantic uncertainty head)
+  if (bs) job(m->who + 6ll * kho + F + FL + m->hh_bs, kho, P("semantic_beta_from_xyz.2.weight"), FL, 1, FL, 0, 0);
+  if (sem) job(m->who + (long long)ro * kho + F + FL + m->hh_sem, kho, P("semantic_prediction.2.weight"), FL, C, FL, 0, 0);
   // transposed head output for dgrad: rows = [s3 | hh] features, 16 columns
   if (!nerf) job(m->tho + 4, 16, P("sun_v_net.6.weight"), FL, FL, 1, 1, 0);
   job(m->tho + (long long)(FL + m->hh_rgb) * 16 + 0, 16, P("rgb_from_xyzdir.2.weight"), FL, FL, 3, 1, 0);
   if (has_beta) job(m->tho + (long long)(FL + m->hh_beta) * 16 + 5, 16, P("beta_from_xyz.2.weight"), FL, FL, 1, 1, 0);
-  if (sem) job(m->tho + (long long)(FL + m->hh_sem) * 16 + 6, 16, P("semantic_prediction.2.weight"), FL, FL, C, 1, 0);
+  if (bs) job(m->tho + (long long)(FL + m->hh_bs) * 16 + 6, 16, P("semantic_beta_from_xyz.2.weight"), FL, FL, 1, 1, 0);
+  if (sem) job(m->tho + (long long)(FL + m->hh_sem) * 16 + ro, 16, P("semantic_prediction.2.weight"), FL, FL, C, 1, 0);
   // fp32 biases
   for (int i = 0; i < LAYERS; ++i) job(m->bl[i], 1, fcb(i), 1, F, 1, 0, 2);
   job(m->bfe, 1, P("feats_from_xyz.bias"), 1, F, 1, 0, 2);
@@ -347,7 +361,8 @@ static void build_layout(snb_model* m) {
   job(m->bho + 3, 1, P("sigma_from_xyz.0.bias"), 1, 1, 1, 0, 2);
   if (!nerf) job(m->bho + 4, 1, P("sun_v_net.6.bias"), 1, 1, 1, 0, 2);
   if (has_beta) job(m->bho + 5, 1, P("beta_from_xyz.2.bias"), 1, 1, 1, 0, 2);
-  if (sem) job(m->bho + 6, 1, P("semantic_prediction.2.bias"), 1, C, 1, 0, 2);
+  if (bs) job(m->bho + 6, 1, P("semantic_beta_from_xyz.2.bias"), 1, 1, 1, 0, 2);
+  if (sem) job(m->bho + ro, 1, P("semantic_prediction.2.bias"), 1, C, 1, 0, 2);
 
   // ---- fp32 packed-gradient scratch + unpack jobs (grads[dst] += scratch[src]) ----
   long long gc = 0;
@@ -403,12 +418,14 @@ static void build_layout(snb_model* m) {
   if (!nerf) ujob(P("sun_v_net.6.weight"), FL, m->ghot + (long long)F * 16 + 4, 16, 1, FL, 1);
   ujob(P("rgb_from_xyzdir.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_rgb) * 16 + 0, 16, 3, FL, 1);
   if (has_beta) ujob(P("beta_from_xyz.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_beta) * 16 + 5, 16, 1, FL, 1);
-  if (sem) ujob(P("semantic_prediction.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_sem) * 16 + 6, 16, C, FL, 1);
+  if (bs) ujob(P("semantic_beta_from_xyz.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_bs) * 16 + 6, 16, 1, FL, 1);
+  if (sem) ujob(P("semantic_prediction.2.weight"), FL, m->ghot + (long long)(F + FL + m->hh_sem) * 16 + ro, 16, C, FL, 1);
   ujob(P("rgb_from_xyzdir.2.bias"), 1, m->gbho + 0, 1, 3, 1, 0);
   ujob(P("sigma_from_xyz.0.bias"), 1, m->gbho + 3, 1, 1, 1, 0);
   if (!nerf) ujob(P("sun_v_net.6.bias"), 1, m->gbho + 4, 1, 1, 1, 0);
   if (has_beta) ujob(P("beta_from_xyz.2.bias"), 1, m->gbho + 5, 1, 1, 1, 0);
-  if (sem) ujob(P("semantic_prediction.2.bias"), 1, m->gbho + 6, 1, C, 1, 0);
+  if (bs) ujob(P("semantic_beta_from_xyz.2.bias"), 1, m->gbho + 6, 1, 1, 1, 0);
+  if (sem) ujob(P("semantic_prediction.2.bias"), 1, m->gbho + ro, 1, C, 1, 0);
   m->bucket_lo[2] = 0;
   m->bucket_hi[2] = m->bucket_lo[1] = fcw(4);
   m->bucket_hi[1] = m->bucket_lo[0] = P("sigma_from_xyz.0.weight");
@@ -747,8 +764,11 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   if (model_kind != SNB_MODEL_SEMANTIC) n_classes = 0;
   SNB_CHECK_ARG(variant == 0 || model_kind == SNB_MODEL_SEMANTIC, SNB_ERR_UNSUPPORTED,
                 "model_create: head-input variants exist for the semantic model only");
-  SNB_CHECK_ARG((variant & ~(SNB_VARIANT_TJ_FOR_S | SNB_VARIANT_TJ_INSTEAD_OF_BETA)) == 0, SNB_ERR_UNSUPPORTED,
-                "model_create: variant bits %d not implemented", variant);
+  SNB_CHECK_ARG((variant & ~(SNB_VARIANT_TJ_FOR_S | SNB_VARIANT_TJ_INSTEAD_OF_BETA | SNB_VARIANT_SEPARATE_BETA_S)) == 0,
+                SNB_ERR_UNSUPPORTED, "model_create: variant bits %d not implemented", variant);
+  SNB_CHECK_ARG(!(variant & SNB_VARIANT_SEPARATE_BETA_S) || n_classes <= 9, SNB_ERR_UNSUPPORTED,
+                "model_create: the separate semantic uncertainty head leaves 9 of the 16 head rows for classes (n_classes %d)",
+                n_classes);
   SNB_CHECK_ARG(n_classes >= 0 && n_classes <= 10 && (model_kind != SNB_MODEL_SEMANTIC || n_classes >= 1),
                 SNB_ERR_UNSUPPORTED, "model_create: n_classes %d outside [1,10]", n_classes);
   snb_model* m = new snb_model();
@@ -756,6 +776,7 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   m->n_classes = n_classes;
   m->sem_sigmoid = semantic_sigmoid;
   m->variant = variant;
+  m->beta_s = (variant & SNB_VARIANT_SEPARATE_BETA_S) ? 1 : 0;
   m->tau = 4;  // t_embedding_tau (configs/pipelines/*.toml)
   const bool enc60 = model_kind == SNB_MODEL_SEMANTIC || model_kind == SNB_MODEL_NERF;   // positional encoding of xyz (10 frequencies)
   m->k0 = enc60 ? 60 : 3;
@@ -764,14 +785,15 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   m->relu = model_kind == SNB_MODEL_NERF ? 1 : 0;
   m->aux_ld = model_kind == SNB_MODEL_NERF ? 32 : 16;
   m->kdir = 24;
-  m->n_out = 9 + n_classes;
+  m->n_out = 9 + m->beta_s + n_classes;   // [rgb | sigma | sun | sky | beta | (beta_s) | sem]  (rs_semantic.py:291-311)
   // hidden block order of the fused head first layers: [rgb | beta | (sem) | sun]
   m->hh_rgb = 0;
   m->hh_beta = FL;
   m->hh_sem = 2 * FL;
   // NeRF: the rgb block only (no sun / uncertainty heads: their layers are not part of its plans)
   // S-NeRF: [rgb | sun] (no uncertainty block)
-  m->hhw = model_kind == SNB_MODEL_SEMANTIC ? 4 * FL
+  m->hh_bs = 3 * FL;
+  m->hhw = model_kind == SNB_MODEL_SEMANTIC ? (4 + m->beta_s) * FL
                                             : (model_kind == SNB_MODEL_NERF ? FL : (model_kind == SNB_MODEL_SNERF ? 2 * FL : 3 * FL));
   m->hh_sun = m->hhw - FL;
   if (model_kind == SNB_MODEL_SNERF || model_kind == SNB_MODEL_NERF) m->hh_beta = m->hh_sem = 0;   // absent blocks: never addressed
@@ -875,6 +897,7 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
     cp.a.n_out = m->n_out;
     cp.a.rows_per_ray = rows_per_ray;
     cp.a.n_classes = m->n_classes;
+    cp.a.beta_s = m->beta_s;
     cp.a.sem_sigmoid = m->sem_sigmoid;
     cp.a.head_mask = head_mask;
     float* hpart = reinterpret_cast<float*>(ws + w.hpart);
@@ -952,7 +975,7 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
   {
     long long blocks = (P + 255) / 256;
     if (blocks > sms * 8) blocks = sms * 8;
-    head_grad_kernel<<<(int)blocks, 256, 0, st>>>(out, g_out, P, m->n_out, m->n_classes, m->sem_sigmoid, head_mask,
+    head_grad_kernel<<<(int)blocks, 256, 0, st>>>(out, g_out, P, m->n_out, m->n_classes, m->sem_sigmoid, head_mask, m->beta_s,
                                                   (__nv_bfloat16*)dpre, gs + m->gbho);
     if (int r = launch_status("head_grad_kernel")) return r;
   }
@@ -1174,13 +1197,19 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
       if (int r = gemm(sf, &st_, W("beta_from_xyz.0"), F + tau, B("beta_from_xyz.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("beta_from_xyz.2"), FL, B("beta_from_xyz.2"), 1, F32_SOFTPLUS, 1.0f, o + 8, n_out)) return r;
     }
+    if (m->beta_s) {   // semantic uncertainty head (rs_semantic.py:228-237,297-303): cat(f, t) -> sin -> softplus, column 9
+      const F32Seg st_ = per_ray(t, tau);
+      if (int r = gemm(sf, &st_, W("semantic_beta_from_xyz.0"), F + tau, B("semantic_beta_from_xyz.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
+      if (int r = gemm(rows(g1, FL, FL), nullptr, W("semantic_beta_from_xyz.2"), FL, B("semantic_beta_from_xyz.2"), 1, F32_SOFTPLUS, 1.0f,
+                       o + 9, n_out)) return r;
+    }
     if (sem) {
       const bool tj_s = (m->variant & SNB_VARIANT_TJ_FOR_S) != 0;               // cat(f, t) -> semantic head (rs_semantic.py:330-338)
       const F32Seg st_ = per_ray(t, tau);
       if (int r = gemm(sf, tj_s ? &st_ : nullptr, W("semantic_prediction.0"), F + (tj_s ? tau : 0), B("semantic_prediction.0"), FL,
                        F32_SIN, 1.0f, g1, FL)) return r;
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("semantic_prediction.2"), FL, B("semantic_prediction.2"), C,
-                       m->sem_sigmoid ? F32_SIGMOID : F32_NONE, 1.0f, o + 9, n_out)) return r;
+                       m->sem_sigmoid ? F32_SIGMOID : F32_NONE, 1.0f, o + 9 + m->beta_s, n_out)) return r;
     }
     if (int r = f32_sky_launch(sky, M, div, r0, o, n_out, st)) return r;
   }

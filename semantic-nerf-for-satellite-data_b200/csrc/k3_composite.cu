@@ -79,6 +79,7 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_words = S * n_out;
+  const int so = 9 + ((flags & SNB_COMPOSITE_BETA_S) ? 1 : 0);   // first class column (column 9 may hold the semantic uncertainty)
   // per warp: two input buffers {packed rows [S*n_out], z [S]} (the next ray streams in with cp.async while this
   // one is composited) + gradient rows in BWD; every region 16-byte aligned
   const int rw4 = (row_words + 3) & ~3, s4 = (S + 3) & ~3;
@@ -162,7 +163,7 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
         acc_b += w[j] * r[2] * (v + (1.0f - v) * r[7]);
 #pragma unroll
         for (int c = 0; c < CMAX; ++c)
-          if (c < C) acc_s[c] += w[j] * r[9 + c];
+          if (c < C) acc_s[c] += w[j] * r[so + c];
       }
     }
     if (!BWD) {
@@ -243,7 +244,7 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
                gb * r[2] * (v + (1.0f - v) * r[7]);
 #pragma unroll
           for (int c = 0; c < CMAX; ++c)
-            if (c < C) g += gs[c] * r[9 + c];
+            if (c < C) g += gs[c] * r[so + c];
           Gw[j] = g;
           float dT = (g_transp ? g_transp[(size_t)ray * S + s] : 0.f) + g * alpha[j];
           B[j] = dT * T[j];
@@ -273,10 +274,11 @@ k3_composite_kernel(const float* __restrict__ out, const float* __restrict__ z_v
           go[6] = gg * wj * r[1] * (1.0f - v);
           go[7] = gb * wj * r[2] * (1.0f - v);
           go[8] = 0.f;
+          if (so > 9) go[9] = 0.f;
 #pragma unroll
           for (int c = 0; c < CMAX; ++c)
-            if (c < C) go[9 + c] = gs[c] * wj;
-          for (int c = 9 + C; c < n_out; ++c) go[c] = 0.f;
+            if (c < C) go[so + c] = gs[c] * wj;
+          for (int c = so + C; c < n_out; ++c) go[c] = 0.f;
         }
         R += B[j];
       }
@@ -363,15 +365,16 @@ static int launch_k3(const float* out, const float* z, int n_rays, int S, int n_
   return launch_status("k3_composite_kernel");
 }
 
-static int check_k3(const float* out, const float* z, int n_rays, int S, int n_out, int C) {
+static int check_k3(const float* out, const float* z, int n_rays, int S, int n_out, int C, int flags = 0) {
   SNB_CHECK_ARG(out && z, SNB_ERR_INVALID, "composite: null input");
   SNB_CHECK_ARG(n_rays >= 0, SNB_ERR_INVALID, "composite: n_rays < 0");
   // S < 2: the reference itself degenerates (framework/util/rendering.py:13 builds delta_inf from
   // an empty slice, so every per-sample tensor collapses to (N,0)); not supported here.
   SNB_CHECK_ARG(S >= 2 && S <= 256, SNB_ERR_UNSUPPORTED, "composite: n_samples %d outside [2,256]", S);
   // n_out > 9 + C is allowed: trailing columns are ignored (the solar pass composites no semantics)
-  SNB_CHECK_ARG(C >= 0 && C <= 10 && n_out >= 9 + C && n_out <= 32, SNB_ERR_UNSUPPORTED,
-                "composite: n_out %d / n_classes %d unsupported (need 9 + C <= n_out <= 32, C <= 10)", n_out, C);
+  const int so = 9 + ((flags & SNB_COMPOSITE_BETA_S) ? 1 : 0);
+  SNB_CHECK_ARG(C >= 0 && C <= 10 && n_out >= so + C && n_out <= 32, SNB_ERR_UNSUPPORTED,
+                "composite: n_out %d / n_classes %d unsupported (need %d + C <= n_out <= 32, C <= 10)", n_out, C, so);
   return 0;
 }
 
@@ -419,6 +422,10 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_words = S * n_out;
+  // use_separate_beta_for_s: column 9 = the semantic uncertainty head; the uncertainty-weighted semantic loss then uses ITS
+  // composited value and adds its own log-beta term (semantic/components/loss.py:15-31)
+  const bool bsep = (lp.flags & SNB_COMPOSITE_BETA_S) != 0;
+  const int so = 9 + (bsep ? 1 : 0);
   const int rw4 = (row_words + 3) & ~3, s4 = (S + 3) & ~3;
   const int in_words = rw4 + s4;
   const int per_warp = 2 * in_words + rw4;
@@ -443,9 +450,9 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
   // uncertainty-weighted semantic loss: the two batch means of the statistics pre-pass (mode 3)
   const float unc_ce = (counts && lp.sem_unc) ? counts[4] * inv_valid : 0.f;      // CE_mean
   const float unc_M = (counts && lp.sem_unc) ? counts[5] * lp.inv_n : 1.f;        // mean_r 1 / (2 beta_r^2)
-  float lsum[7];
+  float lsum[8];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) lsum[i] = 0.f;
+  for (int i = 0; i < 8; ++i) lsum[i] = 0.f;
 
   const int ray0 = blockIdx.x * K3_WARPS + warp, stride = gridDim.x * K3_WARPS;
   int cur = 0;
@@ -481,7 +488,7 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
       }
     }
     const float prefix = warp_excl_prod(Q, lane);
-    float acc_d = 0.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_beta = 0.f, acc_t2 = 0.f, acc_t3 = 0.f;
+    float acc_d = 0.f, acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_beta = 0.f, acc_bs = 0.f, acc_t2 = 0.f, acc_t3 = 0.f;
     float acc_s[CMAX > 0 ? CMAX : 1];
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) acc_s[c] = 0.f;
@@ -496,25 +503,29 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
         const float v = r[4];
         acc_d += w[j] * zs[s];
         if (lp.mode == 3) {
-          acc_beta += w[j] * r[8];
+          acc_beta += w[j] * r[bsep ? 9 : 8];
 #pragma unroll
           for (int c = 0; c < CMAX; ++c)
-            if (c < C) acc_s[c] += w[j] * r[9 + c];
+            if (c < C) acc_s[c] += w[j] * r[so + c];
         } else if (lp.mode == 0) {
           acc_r += w[j] * r[0] * (v + (1.0f - v) * r[5]);
           acc_g += w[j] * r[1] * (v + (1.0f - v) * r[6]);
           acc_b += w[j] * r[2] * (v + (1.0f - v) * r[7]);
           acc_beta += w[j] * r[8];
+          if (bsep) acc_bs += w[j] * r[9];
 #pragma unroll
           for (int c = 0; c < CMAX; ++c)
-            if (c < C) acc_s[c] += w[j] * r[9 + c];
+            if (c < C) acc_s[c] += w[j] * r[so + c];
         } else if (lp.mode == 1) {
           acc_t2 += (T[j] - v) * (T[j] - v);
           acc_t3 += w[j] * v;
         }
       }
     }
-    float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, gB = 0.f;
+    // gB / gBs: gradient w.r.t. the composited uncertainty (column 8 / the separate semantic one, column 9);
+    // gB_w / gBs_w: the part that reaches only the compositing weights (`detach_beta_for_s` detaches the per-sample beta
+    // values, not the weights they are summed with: semantic/components/loss.py:15-19)
+    float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, gB = 0.f, gBs = 0.f, gB_w = 0.f, gBs_w = 0.f;
     float gs[CMAX > 0 ? CMAX : 1];
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) gs[c] = 0.f;
@@ -550,6 +561,7 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
       acc_g = warp_sum(acc_g);
       acc_b = warp_sum(acc_b);
       acc_beta = warp_sum(acc_beta);
+      if (bsep) acc_bs = warp_sum(acc_bs);
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
         if (c < C) acc_s[c] = warp_sum(acc_s[c]);
@@ -613,11 +625,20 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
           gB += -2.0f * lp.lambda_c * e * inv_car;
         }
       }
-      if (lp.sem_unc == 1 && lp.lambda_s != 0.f) {
+      if (lp.sem_unc != 0 && lp.lambda_s != 0.f) {
         // d/d beta_r of lambda_s * CE_mean * mean_r 1 / (2 beta_r^2) = -lambda_s * CE_mean / (N beta_r^3) - for EVERY ray of
-        // the batch, labelled or not: the mean over beta runs over all rays (loss.py:19-25); sem_unc == 2: beta detached
-        const float Bt = acc_beta + lp.beta_min;
-        gB += -lp.lambda_s * unc_ce * lp.inv_n / (Bt * Bt * Bt);
+        // the batch, labelled or not: the mean over beta runs over all rays (loss.py:19-25).  With the separate head it is
+        // beta_s, which also carries its own term lambda_s * (3 + mean log beta_s) / 2 (:27-30).  sem_unc == 2
+        // (detach_beta_for_s): the per-sample values are detached, the weights are not - the gradient reaches sigma only
+        const float Bt = (bsep ? acc_bs : acc_beta) + lp.beta_min;
+        float g = -lp.lambda_s * unc_ce * lp.inv_n / (Bt * Bt * Bt);
+        if (bsep) {
+          lsum[7] += lp.lambda_s * 0.5f * logf(Bt) * lp.inv_n;
+          g += lp.lambda_s * 0.5f * lp.inv_n / Bt;
+        }
+        const bool det = lp.sem_unc == 2;
+        if (bsep) (det ? gBs_w : gBs) += g;
+        else (det ? gB_w : gB) += g;
       }
     } else if (lp.mode == 1) {
       acc_t2 = warp_sum(acc_t2);
@@ -657,11 +678,12 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
         if (s < S) {
           const float* r = rows + s * n_out;
           const float v = r[4];
-          float g = gB * r[8] + gd * zs[s];
+          float g = (gB + gB_w) * r[8] + gd * zs[s];
+          if (bsep) g += (gBs + gBs_w) * r[9];
           g += gr * r[0] * (v + (1.0f - v) * r[5]) + gg * r[1] * (v + (1.0f - v) * r[6]) + gb * r[2] * (v + (1.0f - v) * r[7]);
 #pragma unroll
           for (int c = 0; c < CMAX; ++c)
-            if (c < C) g += gs[c] * r[9 + c];
+            if (c < C) g += gs[c] * r[so + c];
           Gw[j] = g;
           Bv[j] = g * alpha[j] * T[j];
           Bsum += Bv[j];
@@ -687,10 +709,11 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
           go[6] = gg * wj * r[1] * (1.0f - v);
           go[7] = gb * wj * r[2] * (1.0f - v);
           go[8] = gB * wj;
+          if (bsep) go[9] = gBs * wj;
 #pragma unroll
           for (int c = 0; c < CMAX; ++c)
-            if (c < C) go[9 + c] = gs[c] * wj;
-          for (int c = 9 + C; c < n_out; ++c) go[c] = 0.f;
+            if (c < C) go[so + c] = gs[c] * wj;
+          for (int c = so + C; c < n_out; ++c) go[c] = 0.f;
         }
         R += Bv[j];
       }
@@ -708,10 +731,10 @@ k3_loss_kernel(const float* __restrict__ out, const float* __restrict__ z_vals, 
     __syncwarp();
   }
   // every lane of a warp holds the same per-ray sums: one atomic per warp and term
-  if (lane < 7) {
+  if (lane < 8) {
     float v = 0.f;
 #pragma unroll
-    for (int i = 0; i < 7; ++i)
+    for (int i = 0; i < 8; ++i)
       if (lane == i) v = lsum[i];
     if (v != 0.f) atomicAdd(loss_terms + lane, v);
   }
@@ -804,7 +827,7 @@ extern "C" int snb_composite_loss(const float* out, const float* z_vals, int n_r
                                   const float* gt_rgb, const int64_t* labels, const uint8_t* ray_mask, const float* depth_gt,
                                   const float* depth_w, const float* counts, const snb_loss_params* p, float* g_out,
                                   float* loss_terms, void* stream) {
-  if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes)) return r;
+  if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes, p ? p->flags : 0)) return r;
   SNB_CHECK_ARG(p && loss_terms && (g_out || p->mode == 3), SNB_ERR_INVALID, "composite_loss: null argument");
   SNB_CHECK_ARG(p->mode >= 0 && p->mode <= 3, SNB_ERR_INVALID, "composite_loss: mode %d", p->mode);
   SNB_CHECK_ARG(!(p->sem_unc != 0 && p->mode == 0) || (labels != nullptr && counts != nullptr), SNB_ERR_INVALID,
@@ -828,7 +851,7 @@ extern "C" int snb_composite_forward(const float* out, const float* z_vals, int 
                                      int n_out, int n_classes, int flags, float* rgb, float* depth, float* weights,
                                      float* transparency, float* sem_logits, int64_t* sem_label,
                                      void* stream) {
-  if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes)) return r;
+  if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes, flags)) return r;
   SNB_CHECK_ARG(rgb && depth && weights && transparency, SNB_ERR_INVALID, "composite_forward: null output");
   SNB_CHECK_ARG(n_classes == 0 || (sem_logits && sem_label), SNB_ERR_INVALID,
                 "composite_forward: semantic outputs required when n_classes > 0");
@@ -843,7 +866,7 @@ extern "C" int snb_composite_backward(const float* out, const float* z_vals, int
                                       const float* g_weights, const float* g_transparency,
                                       const float* g_sem_logits, const float* g_out_direct, float* g_out,
                                       void* stream) {
-  if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes)) return r;
+  if (int r = snb::check_k3(out, z_vals, n_rays, n_samples, n_out, n_classes, flags)) return r;
   SNB_CHECK_ARG(g_out, SNB_ERR_INVALID, "composite_backward: null g_out");
   if (n_rays == 0) return 0;
   return snb::launch_k3<true>(out, z_vals, n_rays, n_samples, n_out, n_classes, flags, nullptr, nullptr, nullptr,

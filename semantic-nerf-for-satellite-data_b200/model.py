@@ -33,8 +33,9 @@ class SnbMLP(torch.nn.Module):
         self._h = h
         self.kind = kind
         self.semantic_n_classes = n_classes          # read by the reference's inference(), rs_semantic.py:95
-        self.number_of_outputs = 9 + n_classes       # satnerf.py:120
-        self.n_out_kernel = 9 + n_classes            # columns of the packed tensor the kernels write
+        self.beta_s = 1 if (variant & _lib.VARIANT_SEPARATE_BETA_S) else 0   # column 9 = the separate semantic uncertainty
+        self.number_of_outputs = 9 + self.beta_s + n_classes       # satnerf.py:120 / rs_semantic.py:291-311
+        self.n_out_kernel = 9 + self.beta_s + n_classes            # columns of the packed tensor the kernels write
         self.t_embedding_dims = tau
         self.enc_ld = 64 if kind in (MODEL_SATNERF, MODEL_SNERF) else 128
         n = lib.snb_model_param_count(h)
@@ -187,15 +188,15 @@ class RSSemanticNeRFB200(SnbMLP):
 
     def __init__(self, cfgs, dataset_semantic):
         p = cfgs.pipeline
-        unsupported = [k for k in ("use_separate_beta_for_s", "use_separate_tj_for_semantic", "fc_use_full_features")
-                       if getattr(p, k, False)]
+        unsupported = [k for k in ("use_separate_tj_for_semantic", "fc_use_full_features") if getattr(p, k, False)]
         if unsupported or p.fc_layers != 8 or p.fc_units != 512 or list(p.fc_skips) != [4] \
                 or p.activation_function != "siren" or p.mapping_pos_n_freq != 10:
             raise _lib.SnbError(f"libsnb implements the shipped rs_semantic.toml architecture; unsupported: {unsupported}")
         sig = p.semantic_activation_function == "sigmoid"
         # head-input variants: t as an extra input of the semantic head / of the colour head (rs_semantic.py:186-215)
         variant = (_lib.VARIANT_TJ_FOR_S if getattr(p, "use_tj_for_s", False) else 0) | \
-                  (_lib.VARIANT_TJ_INSTEAD_OF_BETA if getattr(p, "use_tj_instead_of_beta", False) else 0)
+                  (_lib.VARIANT_TJ_INSTEAD_OF_BETA if getattr(p, "use_tj_instead_of_beta", False) else 0) | \
+                  (_lib.VARIANT_SEPARATE_BETA_S if getattr(p, "use_separate_beta_for_s", False) else 0)
         super().__init__(MODEL_SEMANTIC, int(dataset_semantic.semantic_n_classes), sig, p.t_embedding_tau, cfgs, variant)
         self.cfg = p
         self.layers, self.skips = p.fc_layers, list(p.fc_skips)

@@ -21,7 +21,7 @@ from __future__ import annotations
 
 import torch
 
-from ._lib import COMPOSITE_NO_CLAMP, HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, MODEL_SEMANTIC
+from ._lib import COMPOSITE_BETA_S, COMPOSITE_NO_CLAMP, HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, MODEL_SEMANTIC
 from . import _lib
 from .autograd import (Composite, CompositeLoss, as_labels, as_ray_mask, encode_rays, label_counts, mlp_fp32,
                        mlp_rays)
@@ -78,7 +78,9 @@ class B200Renderer:
         else:
             out = mlp_rays(model, emb, enc, aux, sky, extras, n, S, mask).view(n, S, -1)
         # NeRF's inference returns the raw composited colour (nerf.py:73-86); the other models clamp it to [0, 1]
-        rgb, depth, weights, transp, sem, label = Composite.apply(out, z, C, COMPOSITE_NO_CLAMP if nerf else 0)
+        bs = getattr(model, "beta_s", 0)   # use_separate_beta_for_s: column 9 = beta_semantic, classes from column 10
+        rgb, depth, weights, transp, sem, label = Composite.apply(
+            out, z, C, (COMPOSITE_NO_CLAMP if nerf else 0) | (COMPOSITE_BETA_S if bs else 0))
         result = {
             "rgb": rgb, "depth": depth, "weights": weights, "transparency": transp,
             "albedo": out[..., :3], "sun": out[..., 4:5], "sky": out[..., 5:8], "beta": out[..., 8:9],
@@ -87,6 +89,8 @@ class B200Renderer:
         if model.kind == MODEL_SEMANTIC:
             result["semantic_logits"] = sem
             result["semantic_label"] = label
+            if bs:
+                result["beta_semantic"] = out[..., 9:10]       # rs_semantic.py:90-96,126-127
         if getattr(model, "variant", None) == "snerf":   # snerf.py:86-96 returns neither beta nor sigmas
             del result["beta"], result["sigmas"]
         if nerf:                                         # nerf.py:80-86: rgb, depth, weights, transparency only
@@ -138,7 +142,7 @@ class B200Renderer:
         C = model.semantic_n_classes
         terms = torch.zeros(8, dtype=torch.float32, device=rays.device)
         inv_n = 1.0 / max(int(global_rays) if global_rays is not None else n, 1)
-        flags = COMPOSITE_NO_CLAMP if nerf else 0
+        flags = (COMPOSITE_NO_CLAMP if nerf else 0) | (COMPOSITE_BETA_S if getattr(model, "beta_s", 0) else 0)
         p = _lib.LossParams(mode=2 if depth_pass else 0, color=1 if color == "satnerf" else 0, beta_min=beta_min,
                             inv_n=inv_n, lambda_s=lambda_s, ignore_index=ignore_index, lambda_c=lambda_c,
                             car_label=car_label, lambda_sc=sc_lambda, lambda_ds=lambda_ds, flags=flags,
@@ -169,6 +173,8 @@ class B200Renderer:
         if model.kind == MODEL_SEMANTIC:
             res["semantic_logits"] = f(0, model.semantic_n_classes)
             res["semantic_label"] = torch.empty(0, dtype=torch.int64, device=rays.device)
+            if getattr(model, "beta_s", 0):
+                res["beta_semantic"] = f(0, S, 1)
         if getattr(model, "variant", None) == "snerf":
             del res["beta"], res["sigmas"]
         if getattr(model, "variant", None) == "nerf":

@@ -32,7 +32,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib, dist as snb_dist
-from ._lib import COMPOSITE_NO_CLAMP, HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, check, ptr, stream
+from ._lib import COMPOSITE_BETA_S, COMPOSITE_NO_CLAMP, HEADS_ALL, HEADS_DEPTH, HEADS_SOLAR, check, ptr, stream
 from .autograd import as_labels, as_ray_mask, t_steps
 from .losses import (DepthLoss, NerfLoss, SatNerfLoss, SemanticCarRegLoss, SemanticLoss, SemanticUncertaintyLoss,
                      SNerfLoss)
@@ -456,7 +456,8 @@ class Trainer:
                              lambda_s=p.lambda_s if sem else 0.0,
                              ignore_index=self.car_index if (sem and p.ignore_car_index) else -100,
                              lambda_c=p.lambda_c if car else 0.0, car_label=self.car_index, lambda_sc=sc_lambda,
-                             lambda_ds=0.0, flags=COMPOSITE_NO_CLAMP if nerf else 0, sem_unc=sem_unc if sem else 0)
+                             lambda_ds=0.0, flags=(COMPOSITE_NO_CLAMP if nerf else 0) | (COMPOSITE_BETA_S if model.beta_s else 0),
+                             sem_unc=sem_unc if sem else 0)
         if sem and sem_unc:
             # SemanticUncertaintyLoss = lambda_s * CE_mean * mean_r 1 / (2 beta_r^2): both batch means first (mode 3 pre-pass
             # into counts[4:6]; data parallel: summed over the ranks), then the main pass forms the gradients
@@ -500,7 +501,9 @@ class Trainer:
         if last:
             # loss value: the terms' sum (+ the constant 3/2 of the log-beta term, baseline/components/loss.py:26); data
             # parallel, the per-rank values are shares that add up to the global-batch loss
-            self._loss_out = self._terms.sum() + (1.5 * share if color == "satnerf" else 0.0)
+            const = (1.5 * share if color == "satnerf" else 0.0) + \
+                    (1.5 * p.lambda_s * share if (sem and sem_unc and model.beta_s) else 0.0)   # semantic log-beta_s (loss.py:27-30)
+            self._loss_out = self._terms.sum() + const
             self._all_reduce_and_step(self._events if self.world > 1 else None, self._step_dev)
 
     # -- gradient all-reduce (sum: the losses are already normalised by the global batch) + Adam + re-pack -------------

@@ -106,9 +106,9 @@ def test_gemm_rejects_bad_arguments():
 # ------------------------------------------------------------------------------------------------
 # K1: sampling + encoding
 # ------------------------------------------------------------------------------------------------
-def _model(kind, C, seed=3, S=64, sc=0.05, trained_like=False, tj=False):
+def _model(kind, C, seed=3, S=64, sc=0.05, trained_like=False, tj=False, bs=False):
     from semnerf_b200.model import RSSemanticNeRFB200, SatNeRFB200
-    spec = O.ModelSpec(kind=kind, n_classes=C, tj_for_s=tj, tj_instead_of_beta=tj)
+    spec = O.ModelSpec(kind=kind, n_classes=C, tj_for_s=tj, tj_instead_of_beta=tj, separate_beta_s=bs)
     params, emb = O.make_params(spec, seed=seed, trained_like=trained_like)
     cfgs = make_cfgs(spec, S, sc)
     if kind == "snerf":

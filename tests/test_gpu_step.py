@@ -18,7 +18,7 @@ from tests.test_gpu_kernels import DEV, _lib_or_fail, _model
 
 pytestmark = pytest.mark.gpu
 
-TERMS = ("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3", "ds")
+TERMS = ("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3", "ds", "semantic_logbeta")
 
 
 def _cos(a, b):
@@ -142,22 +142,28 @@ def test_fused_training_step_matches_the_oracle(kind, C, epoch, with_depth, with
             assert e2.grad.abs().max() == 0 and g_emb.abs().max() == 0
 
 
-@pytest.mark.parametrize("mode,detach", [("direct", False), ("direct", True), ("autograd", False), ("module", False)])
-def test_uncertainty_weighted_semantic_loss_matches_the_oracle(mode, detach):
+@pytest.mark.parametrize("mode,detach,bs", [("direct", False, False), ("direct", True, False), ("autograd", False, False),
+                                            ("module", False, False), ("direct", False, True), ("direct", True, True),
+                                            ("autograd", False, True), ("module", False, True)])
+def test_uncertainty_weighted_semantic_loss_matches_the_oracle(mode, detach, bs):
     """`use_beta_for_s` (SemanticUncertaintyLoss, semantic/components/loss.py:6-32,68-114): lambda_s * CE_mean * mean_r 1/(2 beta_r^2),
     a product of two batch means - the fused kernel takes them from a statistics pre-pass.  All three trainer paths against the
-    oracle's loss (pinned to the reference's module by oracle/pin_against_reference.py), with and without detach_beta_for_s."""
+    oracle's loss (pinned to the reference's module by oracle/pin_against_reference.py), with and without detach_beta_for_s.
+    bs: `use_separate_beta_for_s` - the semantic head's own uncertainty head (output column 9, rs_semantic.py:228-237) takes
+    the place of beta in this loss and adds its log term."""
     from semnerf_b200.trainer import Trainer, default_cfgs
     _lib_or_fail()
     C, S, n = 6, 64, 640
     cfgs = default_cfgs("semantic", n_samples=S, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=2, use_beta_for_s=True,
-                        detach_beta_for_s=detach, lambda_s=0.4)   # a larger weight: the term must matter in the gradient
+                        detach_beta_for_s=detach, lambda_s=0.4,   # a larger weight: the term must matter in the gradient
+                        use_separate_beta_for_s=bs)
     kw = {"direct": dict(direct=True), "autograd": dict(direct=False), "module": dict(fused_loss=False)}[mode]
     tr = Trainer(cfgs, "semantic", C, device=DEV, car_index=CAR, seed=0, **kw)
-    spec = O.ModelSpec(kind="semantic", n_classes=C)
+    spec = O.ModelSpec(kind="semantic", n_classes=C, separate_beta_s=bs)
     params, emb = O.make_params(spec, seed=5)
     tr.models["coarse"].load_state_dict(params)
     tr.models["t"].weight.data.copy_(emb)
+    assert tr.models["coarse"].number_of_outputs == 9 + C + (1 if bs else 0)
     batch, depth = _batches(n, 64, C, seed=23, with_mask=True)
     assert tr._sem_unc(3) == (2 if detach else 1) and tr._sem_unc(1) == 0      # plain cross-entropy before first_beta_epoch
     loss = tr.training_step(_to_dev(batch), epoch=3)
@@ -175,17 +181,28 @@ def test_uncertainty_weighted_semantic_loss_matches_the_oracle(mode, detach):
     ref.backward()
     if mode != "module":
         got = dict(zip(TERMS, tr.last_loss_terms.cpu().tolist()))
-        assert abs(got["semantic"] - rterms["semantic"].item()) <= 1e-2 * rterms["semantic"].item(), (got["semantic"], rterms["semantic"].item())
+        mine = got["semantic"] + (got["semantic_logbeta"] + 1.5 * 0.4 if bs else 0.0)     # the oracle reports both as one term
+        assert abs(mine - rterms["semantic"].item()) <= 1e-2 * rterms["semantic"].item(), (mine, rterms["semantic"].item())
     else:
-        assert abs(float(tr.last_loss_dict["coarse_semantic"]) - rterms["semantic"].item()) <= 1e-2 * rterms["semantic"].item()
+        mine = float(tr.last_loss_dict["coarse_semantic"].detach()) + \
+            (float(tr.last_loss_dict["coarse_semantic_logbeta"].detach()) if bs else 0.0)
+        assert abs(mine - rterms["semantic"].item()) <= 1e-2 * rterms["semantic"].item()
     assert abs(loss.item() - ref.item()) <= 1e-2 * abs(ref.item())
     # NB: the parameters have moved (Adam ran), the gradient buffer still holds this step's gradient
-    g_ref = torch.cat([p2[k].grad.flatten() for k in p2])
+    g_ref = torch.cat([p2[k].grad.flatten() if p2[k].grad is not None else torch.zeros(p2[k].numel()) for k in p2])
     assert _cos(tr.gbuf[256:].cpu(), g_ref) >= 0.999
     assert _cos(tr.gbuf[:tr.n_emb].cpu(), e2.grad) >= 0.995
-    # the uncertainty head's own gradient is where detach / no detach differ most
-    off = tr.models["coarse"].offset_of("beta_from_xyz.2.weight")
-    assert _cos(tr.gbuf[256 + off: 256 + off + 256].cpu(), p2["beta_from_xyz.2.weight"].grad) >= 0.995
+    # the uncertainty heads' own gradients are where detach / no detach differ most
+    for name in ["beta_from_xyz.2.weight"] + (["semantic_beta_from_xyz.2.weight", "semantic_beta_from_xyz.0.weight"] if bs else []):
+        off, m = tr.models["coarse"].offset_of(name), p2[name].numel()
+        got_g, ref_g = tr.gbuf[256 + off: 256 + off + m].cpu(), p2[name].grad
+        if ref_g is None or ref_g.abs().max() == 0:     # detached: the head receives nothing from this loss
+            assert got_g.abs().max() <= 1e-7 * g_ref.abs().max()
+        else:
+            assert _cos(got_g, ref_g) >= 0.995, name
+    if bs and mode != "module":
+        got = dict(zip(TERMS, tr.last_loss_terms.cpu().tolist()))
+        assert got["semantic_logbeta"] != 0.0
 
 
 def test_label_dtypes_and_counts_are_device_side():

@@ -74,7 +74,7 @@ def test_initialiser_ranges_follow_the_reference():
 def test_unsupported_configurations_fail_loudly():
     spec = O.ModelSpec(kind="semantic")
     cfgs = make_cfgs(spec, 64, 0.05)
-    cfgs.pipeline.use_separate_beta_for_s = True
+    cfgs.pipeline.use_separate_tj_for_semantic = True
     with pytest.raises(_lib.SnbError):
         RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": 6})())
     with pytest.raises(_lib.SnbError):
@@ -139,7 +139,7 @@ def test_render_loss_signature_and_term_order():
     for name in ("models", "rays", "extras", "rgbs", "semantic", "color", "lambda_s", "ignore_index", "lambda_c", "car_label",
                  "depth", "depth_weights", "lambda_ds", "render_options"):
         assert name in sig.parameters, name
-    assert LOSS_TERMS == ("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3", "ds")
+    assert LOSS_TERMS == ("color", "logbeta", "semantic", "car_reg", "sc_term2", "sc_term3", "ds", "semantic_logbeta")
 
 
 def test_nerf_state_dict_is_the_reference_nerf():

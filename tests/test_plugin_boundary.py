@@ -125,7 +125,7 @@ def test_plugin_renderer_refuses_an_injected_inference_function(ref):
 
 def test_unsupported_head_variants_raise_at_construction(ref):
     from semnerf_b200 import _lib
-    for flag in ("use_separate_beta_for_s", "use_separate_tj_for_semantic", "fc_use_full_features"):
+    for flag in ("use_separate_tj_for_semantic", "fc_use_full_features"):
         cfgs = _cfgs(ref, "rs_semantic.toml", "semnerf_b200.pipelines.RSSemanticB200Pipeline")
         setattr(cfgs.pipeline, flag, True)
         with pytest.raises(_lib.SnbError):
