@@ -48,13 +48,16 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 50 ms from BEFORE the warm-up (its start-up takes longer than a short timed region); the
+    samples reported are those whose timestamps fall inside the timed region marked with begin() / end()."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.path = f"/tmp/snb_clocks_{os.getpid()}.csv"
         self.proc = None
+        self.t0 = self.t1 = None
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
@@ -63,32 +66,45 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)                     # let the sample that covers the end of the region land
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], None, set()
+        import datetime
+        rows = []
         for line in open(self.path):
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 8:
+            if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx = float(parts[2])
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[2]), float(parts[3]), float(parts[4]), parts[5:9]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+        os.unlink(self.path)
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.03 <= r[0] <= (self.t1 or r[0]) + 0.06]
+        use = inside if inside else rows     # a region shorter than the polling period: fall back to every sample taken
+        sm = sorted(r[1] for r in use)
+        reasons = set()
+        for r in use:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.path)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        pw = sorted(r[3] for r in use)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": use[0][2] if use else None, "reasons": sorted(reasons),
+                "samples": len(use), "samples_in_timed_region": len(inside), "power_w_median": pw[len(pw) // 2] if pw else None}
 
 
 def make_batch(n, seed, pinned=False):
@@ -388,6 +404,7 @@ def run_gpu(args):
         build.build()
     snb_dist.barrier()
     lib = _lib.load()
+    sampler = ClockSampler(local) if rank == 0 else None      # started before the warm-up: see ClockSampler
     B = args.batch
     graph = world == 1 and not args.no_graph and not args.module_losses
     cfgs = default_cfgs("semantic", n_samples=N_SAMPLES, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=0)
@@ -403,9 +420,12 @@ def run_gpu(args):
         step_resident(i)
     torch.cuda.synchronize()
     # ---- timed region 1: inputs resident in HBM, device-timed ----------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
     lib.snb_profile_begin(0)
+    if sampler:
+        sampler.begin()
     ms_total, loss = timed_steps(step_resident, args.steps, dev, world)
+    if sampler:
+        sampler.end()
     clocks = sampler.stop() if sampler else None
     gl, tl = C.c_int64(), C.c_int64()
     lib.snb_profile_end(None, C.byref(gl), C.byref(tl), None)

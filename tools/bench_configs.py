@@ -119,21 +119,19 @@ def main():
     if not args.skip_train:
         G = 65536
         B = G // world
-        if world == 1:
-            # one GPU cannot hold a 65 536-ray step (~25 KB of saved activations per sample and pass -> ~210 GB): the
-            # single-GPU denominator of the scaling curve is measured at 16 384 rays per step (rays/s is flat in the batch)
-            G = B = 16384
+        # ~25 KB of saved activations per sample and pass: a rank's share runs as 8192-ray micro-batches that accumulate into
+        # one gradient, ONE all-reduce + optimiser step per global batch (one GPU: 8 micro-batches, 8 GPUs: 1)
         cfg4 = default_cfgs("semantic", n_samples=64, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=0)
-        tr4 = Trainer(cfg4, "semantic", C, device=dev, car_index=4, world=world, rank=rank, seed=0)
+        tr4 = Trainer(cfg4, "semantic", C, device=dev, car_index=4, world=world, rank=rank, seed=0, micro_batch=8192)
         br, be = synth.make_rays(B, seed=3000 + rank)
         rgbs, labels, _ = synth.make_targets(br, C, seed=rank)
         batch = {k: v.to(dev) for k, v in {"rays": br, "extras": be, "rgbs": rgbs, "semantic": labels}.items()}
         for _ in range(2):
-            tr4.training_step(batch, epoch=3, ray_offset=rank * B)
+            tr4.training_step(batch, epoch=3, ray_offset=rank * B, global_rays=G)
 
         def train():
             for _ in range(args.train_steps):
-                tr4.training_step(batch, epoch=3, ray_offset=rank * B)
+                tr4.training_step(batch, epoch=3, ray_offset=rank * B, global_rays=G)
         t = timed_max(train, dev, world)
         lines.append({"config": "4: data-parallel semantic-NeRF training, 65536-ray GLOBAL batch, NCCL gradient all-reduce",
                       "metric": "train_rays_per_s", "value": G * args.train_steps / t, "unit": "rays/s", "n_gpus": world,
