@@ -295,6 +295,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       Cursor c;
       for (cur_init(c, seq); !c.done; cur_next(c, seq, args), ++it) {
         const int kb_total = args.layers[c.l].kb_total;
+        const int tail_k16 = args.layers[c.l].tail_k16;
         const uint32_t idesc = args.layers[c.l].epi == EPI_HEADOUT ? idesc16 : idesc256;
         const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
@@ -307,9 +308,10 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
           if (elect_one()) {
             const uint64_t ad = desc0 + (uint64_t)(a_base + sa * 1024u);
             const uint64_t bd = desc0 + (uint64_t)(b_base + sb * 1024u);
+            const int ksteps = kb == kb_total - 1 ? tail_k16 : GEMM_BLOCK_K / 16;
 #pragma unroll
             for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
-              tc_mma_bf16_2sm(d_tmem, ad + k * 2, bd + k * 2, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if (k < ksteps) tc_mma_bf16_2sm(d_tmem, ad + k * 2, bd + k * 2, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             tc_commit_2sm(&emptyA[sa]);   // frees the slots in both CTAs once these MMAs have read them
             tc_commit_2sm(&emptyB[sb]);
           }
@@ -652,7 +654,9 @@ int chain_launch(const ChainArgs& a, cudaStream_t st) {
                     "chain: head-output layer %d needs its destination", l);
     SNB_CHECK_ARG(!(ly.epi == EPI_MUL && ly.mul_siren == 1) || (ly.mask != nullptr && ly.mask_ld > 0), SNB_ERR_INVALID,
                   "chain: layer %d needs the sign mask of the saved activation", l);
-    macs += (double)a.n_blocks * 256.0 * (ly.epi == EPI_HEADOUT ? 16.0 : ly.n_tiles * 256.0) * ly.kb_total * GEMM_BLOCK_K;
+    SNB_CHECK_ARG(ly.tail_k16 >= 1 && ly.tail_k16 <= 4, SNB_ERR_INVALID, "chain: layer %d tail_k16 %d", l, ly.tail_k16);
+    macs += (double)a.n_blocks * 256.0 * (ly.epi == EPI_HEADOUT ? 16.0 : ly.n_tiles * 256.0) *
+            ((ly.kb_total - 1) * GEMM_BLOCK_K + ly.tail_k16 * 16);
   }
   const int sms = num_sms();
   if (sms <= 0) return SNB_ERR_NO_DEVICE;

@@ -37,6 +37,8 @@ struct ChainLayer {     // scalars every role reads once per tile: kept together
   int a_scratch[3];     // segment lives in the per-pair scratch (row = (pair*SLOTS + slot)*256) instead of at the block's rows
   int nseg;
   int kb_total;
+  int tail_k16;         // k = 16 MMA steps of the LAST k-block (4 = a full 64-column block): the 16-column aux / dPre16 K-segments
+                        // are zero beyond their real columns, so their other three MMAs would only add zeros
   int n_tiles;          // N / 256
   int epi;              // EPI_SIN / EPI_LINEAR / EPI_MUL (256-column tiles) or EPI_HEADOUT (one 16-column tile, see `rows`)
   int relu;             // EPI_SIN layers: max(acc + bias, 0) instead of sin (vanilla NeRF); no sign mask

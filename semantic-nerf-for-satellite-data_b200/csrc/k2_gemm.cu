@@ -564,6 +564,7 @@ extern "C" int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t 
     ly.n_tiles = N / 256;
     ly.nseg = 1;
     ly.kb_total = ly.seg_kb[0] = (K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+    ly.tail_k16 = 4;
     int r = make_tmap_2d(&mp.tmA[0], A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, GEMM_BLOCK_M);
     if (!r) r = make_tmap_2d(&mp.tmB, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, 128);
     if (!r) r = make_tmap_2d(&mp.tmO0, out0, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M);

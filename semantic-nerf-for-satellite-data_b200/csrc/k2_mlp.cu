@@ -70,7 +70,7 @@ struct snb_model {
   long long packed_bf16_elems;
   long long bias_off;  // fp32 section (byte offset = packed_bf16_elems*2), element offsets below
   long long bl[8], bfe, bs2, bs4, bho;
-  long long wf32, wh1_32;    // fp32 copies of W_f [F,F] and of the head first layers' f-columns [hhw,F] (folded feats layer)
+  long long wf32, wh1_32, bh1_32;   // fp32 copies of W_f [F,F], of the head first layers' f-columns [hhw,F] and biases [hhw]
   long long bias_elems;
   std::vector<snb::PackJob> pack_jobs;
   struct HeadBlock { int row; long long w, b; int kin; };   // hidden blocks of the fused head layer: flat offsets of W / bias
@@ -409,6 +409,7 @@ static void build_layout(snb_model* m) {
   m->bho = take(bc, 16);
   m->wf32 = take(bc, (long long)F * F);
   m->wh1_32 = take(bc, (long long)hhw * F);
+  m->bh1_32 = take(bc, hhw);
   m->bias_elems = bc;
 
   auto& J = m->pack_jobs;
@@ -451,6 +452,7 @@ static void build_layout(snb_model* m) {
     // the f-columns W' = W_b W_f (+ their transpose in tf) and the bias column b' = b_b + W_b b_f (aux column 0 = 1) are
     // composed in fp32 by snb_model_pack; here only the fp32 copy of W_b's f-columns for the gradient products
     job(m->wh1_32 + (long long)b.row * F, F, w, b.kin, FL, F, 0, 2);
+    job(m->bh1_32 + b.row, 1, bb, 1, FL, 1, 0, 2);
     m->head_blocks.push_back({b.row, w, bb, b.kin});
   }
   if (nerf) {   // aux columns 1..24 = the encoded view direction (cat(f, Mapping(dir)), nerf.py:197-199)
@@ -830,6 +832,10 @@ struct ChainPlan {
       chk(make_tmap_2d(&mp.tmA[s], segs[s].ptr, 2, (uint64_t)segs[s].cols, (uint64_t)segs[s].rows, (uint64_t)segs[s].ld * 2, 64,
                        GEMM_BLOCK_M));
     }
+    {
+      const CSeg& last = segs[nseg - 1];
+      ly.tail_k16 = (last.kb == 1 && last.cols < 64) ? (last.cols + 15) / 16 : 4;
+    }
     chk(make_tmap_2d(&mp.tmB, B, 2, (uint64_t)b_cols, (uint64_t)N, (uint64_t)ldb * 2, 64, 128));
     chk(make_tmap_2d(&mp.tmO0, out0, 2, (uint64_t)N, (uint64_t)o_rows, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
     if (epi == EPI_MUL) chk(make_tmap_2d(&mp.tmMul, mul, 2, (uint64_t)N, (uint64_t)a.M, (uint64_t)ldmul * 2, 64, GEMM_BLOCK_M));
@@ -856,6 +862,7 @@ struct ChainPlan {
     ly.n_tiles = 1;
     ly.nseg = 1;
     ly.kb_total = ly.seg_kb[0] = seg.kb;
+    ly.tail_k16 = 4;
     ly.a_scratch[0] = per_layer ? 0 : seg.scratch;
     chk(make_tmap_2d(&mp.tmA[0], seg.ptr, 2, (uint64_t)seg.cols, (uint64_t)seg.rows, (uint64_t)seg.ld * 2, 64, GEMM_BLOCK_M));
     chk(make_tmap_2d(&mp.tmB, B, 2, (uint64_t)b_cols, (uint64_t)16, (uint64_t)ldb * 2, 64, 8));
@@ -975,10 +982,8 @@ extern "C" int snb_model_pack(const snb_model* m, const float* params, void* pac
     g.o16t = pk + m->tf; g.ld16t = ktf;
     if (int r = small_gemm(g, st)) return r;
   }
-  for (auto& b : m->head_blocks)
-    if (int r = small_gemv(params + b.w, b.kin, 1, params + bf, 1, FL, F, params + b.b, nullptr, 0,
-                           pk + m->wh1 + (long long)b.row * kh1 + F, kh1, st)) return r;
-  return 0;
+  // bias column (aux column 0 = 1): b' = b_h1 + W_h1 b_f, all hidden blocks in one launch (rows of absent blocks are zero)
+  return small_gemv(f32 + m->wh1_32, F, 1, params + bf, 1, m->hhw, F, f32 + m->bh1_32, nullptr, 0, pk + m->wh1 + F, kh1, st);
 }
 
 extern "C" size_t snb_mlp_workspace_bytes(const snb_model* m, int64_t n_points, int train) {
