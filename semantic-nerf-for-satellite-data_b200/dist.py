@@ -3,7 +3,10 @@ the flat gradient buffer (NCCL over NVLink on the GPU box, gloo in the CPU tests
 
 The reference has no distributed code (framework/pipelines.py:306-320 trains on one device); the
 path shards naturally because rays are independent: ranks exchange nothing on the data
-path, and one gradient all-reduce per step (sum, then 1/world inside the optimiser kernel)."""
+path.  The trainer normalises every loss by GLOBAL counts (global ray count, all-reduced masked-mean
+denominators), so the per-rank gradients simply sum: one bucketed sum-all-reduce per step, started bucket
+by bucket from events the backward pass records (trainer.Trainer._all_reduce_and_step).  The helpers here
+are the environment / sharding plumbing and a stand-alone bucketed reducer (used by the gloo tests)."""
 from __future__ import annotations
 
 import os

@@ -285,8 +285,10 @@ class Trainer:
     def _buffers(self, tag: str, n: int, depth_only: bool) -> _PassBuffers:
         key = (tag, n)
         if key not in self._bufs:
-            for k in [k for k in self._bufs if k[0] == tag]:
-                del self._bufs[k]                 # one live batch size per role: a changed size replaces its buffers
+            # two live batch sizes per role (the full micro-batch and a short last one); a third size replaces the oldest
+            old = [k for k in self._bufs if k[0] == tag]
+            if len(old) >= 2:
+                del self._bufs[old[0]]
                 self._graphs.clear()
             model = self.models["coarse"]
             sc = (not depth_only) and self.kind != "nerf" and getattr(self.cfgs.pipeline, "sc_lambda", 0.0) > 0

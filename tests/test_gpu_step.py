@@ -142,24 +142,27 @@ def test_fused_training_step_matches_the_oracle(kind, C, epoch, with_depth, with
             assert e2.grad.abs().max() == 0 and g_emb.abs().max() == 0
 
 
-@pytest.mark.parametrize("mode,detach,bs", [("direct", False, False), ("direct", True, False), ("autograd", False, False),
-                                            ("module", False, False), ("direct", False, True), ("direct", True, True),
-                                            ("autograd", False, True), ("module", False, True)])
-def test_uncertainty_weighted_semantic_loss_matches_the_oracle(mode, detach, bs):
+@pytest.mark.parametrize("mode,detach,bs,tj", [("direct", False, False, False), ("direct", True, False, False),
+                                               ("autograd", False, False, False), ("module", False, False, False),
+                                               ("direct", False, True, False), ("direct", True, True, False),
+                                               ("autograd", False, True, False), ("module", False, True, False),
+                                               ("direct", False, True, True)])
+def test_uncertainty_weighted_semantic_loss_matches_the_oracle(mode, detach, bs, tj):
     """`use_beta_for_s` (SemanticUncertaintyLoss, semantic/components/loss.py:6-32,68-114): lambda_s * CE_mean * mean_r 1/(2 beta_r^2),
     a product of two batch means - the fused kernel takes them from a statistics pre-pass.  All three trainer paths against the
     oracle's loss (pinned to the reference's module by oracle/pin_against_reference.py), with and without detach_beta_for_s.
     bs: `use_separate_beta_for_s` - the semantic head's own uncertainty head (output column 9, rs_semantic.py:228-237) takes
-    the place of beta in this loss and adds its log term."""
+    the place of beta in this loss and adds its log term.  tj: all head variants at once (`use_tj_for_s` on top: the embedding
+    then feeds the uncertainty, the semantic-uncertainty and the semantic head)."""
     from semnerf_b200.trainer import Trainer, default_cfgs
     _lib_or_fail()
     C, S, n = 6, 64, 640
     cfgs = default_cfgs("semantic", n_samples=S, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=2, use_beta_for_s=True,
                         detach_beta_for_s=detach, lambda_s=0.4,   # a larger weight: the term must matter in the gradient
-                        use_separate_beta_for_s=bs)
+                        use_separate_beta_for_s=bs, use_tj_for_s=tj)
     kw = {"direct": dict(direct=True), "autograd": dict(direct=False), "module": dict(fused_loss=False)}[mode]
     tr = Trainer(cfgs, "semantic", C, device=DEV, car_index=CAR, seed=0, **kw)
-    spec = O.ModelSpec(kind="semantic", n_classes=C, separate_beta_s=bs)
+    spec = O.ModelSpec(kind="semantic", n_classes=C, separate_beta_s=bs, tj_for_s=tj)
     params, emb = O.make_params(spec, seed=5)
     tr.models["coarse"].load_state_dict(params)
     tr.models["t"].weight.data.copy_(emb)
