@@ -105,8 +105,13 @@ typedef struct snb_model snb_model; /* opaque host object: architecture + packed
  * SNB_VARIANT_TJ_INSTEAD_OF_BETA: the colour head reads cat(f, t) (`use_tj_instead_of_beta`, :186-189,287-288).
  * Both are four more weight columns of their hidden block against the aux K-segment [1, sun_d, t].
  * SNB_VARIANT_SEPARATE_BETA_S: a second uncertainty head `semantic_beta_from_xyz` (`use_separate_beta_for_s`, :228-237,
- * 297-303): cat(f, t) -> 256 -> softplus, packed column 9, the class scores move to columns 10.. (n_classes <= 9). */
-enum { SNB_VARIANT_TJ_FOR_S = 1, SNB_VARIANT_TJ_INSTEAD_OF_BETA = 2, SNB_VARIANT_SEPARATE_BETA_S = 4 };
+ * 297-303): cat(f, t) -> 256 -> softplus, packed column 9, the class scores move to columns 10.. (n_classes <= 9).
+ * SNB_VARIANT_SEPARATE_TJ_S: the semantic head (with TJ_FOR_S) and the semantic uncertainty head read a SECOND embedding t_s
+ * (`use_separate_tj_for_semantic`, :300-301,334-335): the caller passes both tables side by side as one (vocab, 2 tau) table
+ * to snb_sample_encode / a (P, 2 tau) `t` to snb_encode_points / snb_mlp_forward_fp32 (tau = 8 there), t_s lands in aux
+ * columns 8..11 and its gradient in columns 8..11 of g_aux. */
+enum { SNB_VARIANT_TJ_FOR_S = 1, SNB_VARIANT_TJ_INSTEAD_OF_BETA = 2, SNB_VARIANT_SEPARATE_BETA_S = 4,
+       SNB_VARIANT_SEPARATE_TJ_S = 8 };
 int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid, int variant);
 void snb_model_destroy(snb_model* m);
 /* number of fp32 parameters / the offset table: parameters live in ONE flat fp32 buffer in the

@@ -33,11 +33,11 @@ def ref_cfgs(spec: O.ModelSpec, n_samples: int, sc_lambda: float):
         mapping_pos_n_freq=spec.n_freq, mapping_dir_n_freq=4,
         semantic_activation_function="sigmoid" if spec.semantic_sigmoid else "none",
         use_tj_for_s=spec.tj_for_s, use_tj_instead_of_beta=spec.tj_instead_of_beta, use_beta_for_s=False,
-        use_separate_beta_for_s=spec.separate_beta_s, use_separate_tj_for_semantic=False)
+        use_separate_beta_for_s=spec.separate_beta_s, use_separate_tj_for_semantic=spec.separate_tj_s)
     return types.SimpleNamespace(pipeline=pl)
 
 
-def build_reference(spec: O.ModelSpec, params, emb, n_samples, sc_lambda):
+def build_reference(spec: O.ModelSpec, params, emb, n_samples, sc_lambda, emb_s_seed=0):
     cfgs = ref_cfgs(spec, n_samples, sc_lambda)
     if spec.kind == "semantic":
         from semantic.models.rs_semantic import RSSemanticNeRF
@@ -64,7 +64,11 @@ def build_reference(spec: O.ModelSpec, params, emb, n_samples, sc_lambda):
     assert not missing.missing_keys and not missing.unexpected_keys
     t = torch.nn.Embedding(spec.vocab, spec.tau)
     t.weight.data.copy_(emb)
-    return cfgs, model, {"coarse": model, "t": t}, renderer
+    models = {"coarse": model, "t": t}
+    if spec.kind == "semantic" and spec.separate_tj_s:   # semantic/pipelines/rs_semantic.py:72-77
+        models["t_s"] = torch.nn.Embedding(spec.vocab, spec.tau)
+        models["t_s"].weight.data.copy_(O.make_emb_s(spec, seed=emb_s_seed))
+    return cfgs, model, models, renderer
 
 
 def ref_render(renderer, models, cfgs, rays, extras, z):
@@ -92,6 +96,9 @@ CASES = [
     ("sem_c6_s8_tj", "semantic", 6, 512, 16, 8, 0.05, 12),
     # a "_bs" name: use_separate_beta_for_s (second uncertainty head, rs_semantic.py:228-237); C = 9 fills the 16 head rows
     ("sem_c9_s8_bs", "semantic", 9, 512, 16, 8, 0.05, 13),
+    # a "_ts" name: every head variant at once - use_tj_for_s + use_separate_beta_for_s + use_separate_tj_for_semantic (the
+    # semantic head and the semantic uncertainty head read the second embedding models["t_s"])
+    ("sem_c6_s8_ts", "semantic", 6, 512, 16, 8, 0.05, 14),
 ]
 
 GOLDEN_KEYS = ["rgb_coarse", "depth_coarse", "weights_coarse", "transparency_coarse",
@@ -101,8 +108,9 @@ GOLDEN_KEYS = ["rgb_coarse", "depth_coarse", "weights_coarse", "transparency_coa
 
 def case_inputs(name, kind, C, feat, n, s, sc, seed):
     tj = name.endswith("_tj")
-    spec = O.ModelSpec(kind=kind, n_classes=C, feat=feat, tj_for_s=tj, tj_instead_of_beta=tj,
-                       separate_beta_s=name.endswith("_bs"))
+    ts = name.endswith("_ts")
+    spec = O.ModelSpec(kind=kind, n_classes=C, feat=feat, tj_for_s=tj or ts, tj_instead_of_beta=tj,
+                       separate_beta_s=name.endswith("_bs") or ts, separate_tj_s=ts)
     params, emb = O.make_params(spec, seed=seed, trained_like=name.endswith("trained"))
     rays, extras = O.synthetic_rays(n, seed=seed)
     rng = np.random.Generator(np.random.PCG64(seed + 77))
@@ -321,11 +329,12 @@ def main(write=True):
         name, kind, C, feat, n, s, sc, seed = case
         spec, params, emb, rays, extras, u = case_inputs(*case)
         z = O.sample_z(rays, s, u)
-        cfgs, model, models, renderer = build_reference(spec, params, emb, s, sc)
+        cfgs, model, models, renderer = build_reference(spec, params, emb, s, sc, emb_s_seed=seed)
+        emb_s = O.make_emb_s(spec, seed=seed) if spec.separate_tj_s else None
         # forward parity
         with torch.no_grad():
             ref = ref_render(renderer, models, cfgs, rays, extras, z)
-            ours = O.render_rays(params, emb, spec, rays, extras, s, z=z, sc_lambda=sc)
+            ours = O.render_rays(params, emb, spec, rays, extras, s, z=z, sc_lambda=sc, emb_s=emb_s)
         for k, v in ref.items():
             assert k in ours, k
             if v.dtype.is_floating_point:
@@ -339,11 +348,13 @@ def main(write=True):
         sd = extras[:1, :3].expand(P, 3).contiguous()
         tt = emb[:1].expand(P, spec.tau).contiguous()
         with torch.no_grad():
+            tts = emb_s[1:2].expand(P, spec.tau).contiguous() if emb_s is not None else None
             if spec.kind == "nerf":
                 a = model(xyz, input_dir=sd)
             else:
-                a = model(xyz, input_sun_dir=sd) if spec.kind == "snerf" else model(xyz, input_sun_dir=sd, input_t=tt)
-            b = O.mlp_forward(params, spec, xyz, sd, tt)
+                kw = {"input_t_s": tts} if tts is not None else {}
+                a = model(xyz, input_sun_dir=sd) if spec.kind == "snerf" else model(xyz, input_sun_dir=sd, input_t=tt, **kw)
+            b = O.mlp_forward(params, spec, xyz, sd, tt, t_s=tts)
         assert (a - b).abs().max().item() <= 2e-6
         # gradient parity through the reference's own loss modules
         from baseline.components.loss import NerfLoss, SatNerfLoss, SNerfLoss
@@ -356,11 +367,20 @@ def main(write=True):
             loss_ref, _ = NerfLoss()(ref2, gt)                                        # baseline/pipelines/nerf.py:23-24
         else:
             loss_ref, _ = (SNerfLoss if snerf else SatNerfLoss)(lambda_sc=sc)(ref2, gt)   # baseline/pipelines/snerf.py:21-22
+        lab = None
+        if emb_s is not None:   # give the second embedding a gradient: only the semantic heads depend on it
+            from semantic.components.loss import SemanticLoss
+            lab = torch.randint(0, C, (n, 1), generator=torch.Generator().manual_seed(seed)).to(torch.uint8)
+            l_s, _ = SemanticLoss(0.04, 4, ignore_car_index=True)(ref2, lab, None)
+            loss_ref = loss_ref + l_s
         loss_ref.backward()
         p2 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
         e2 = emb.clone().requires_grad_(True)
-        res2 = O.render_rays(p2, e2, spec, rays, extras, s, z=z, sc_lambda=sc)
+        es2 = emb_s.clone().requires_grad_(True) if emb_s is not None else None
+        res2 = O.render_rays(p2, e2, spec, rays, extras, s, z=z, sc_lambda=sc, emb_s=es2)
         loss = (O.nerf_loss if spec.kind == "nerf" else O.snerf_loss if snerf else O.satnerf_loss)(res2, gt, lambda_sc=sc)
+        if es2 is not None:
+            loss = loss + O.semantic_loss(res2, lab, 0.04, 4)
         loss.backward()
         assert abs(loss.item() - loss_ref.item()) <= 1e-5 * max(1, abs(loss_ref.item()))
         num = den_a = den_b = 0.0
@@ -372,6 +392,9 @@ def main(write=True):
         if not snerf:
             ge = models["t"].weight.grad
             assert (ge - e2.grad).abs().max().item() <= 1e-5 * max(1.0, ge.abs().max().item())
+        if es2 is not None:
+            ges = models["t_s"].weight.grad
+            assert ges.abs().max().item() > 0 and (ges - es2.grad).abs().max().item() <= 1e-5 * max(1.0, ges.abs().max().item())
         print(f"{name}: forward keys {len(ref)} ok, loss {loss.item():.6f}, grad cosine {cos:.9f}")
         if write:
             gold = {k: ref[k].numpy() for k in GOLDEN_KEYS if k in ref}

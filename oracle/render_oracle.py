@@ -75,6 +75,7 @@ class ModelSpec:
     tj_for_s: bool = False             # use_tj_for_s: the semantic head reads cat(f, t)
     tj_instead_of_beta: bool = False   # use_tj_instead_of_beta: the colour head reads cat(f, t)
     separate_beta_s: bool = False      # use_separate_beta_for_s: a second uncertainty head, output column 9 (rs_semantic.py:228-237)
+    separate_tj_s: bool = False        # use_separate_tj_for_semantic: the semantic heads read a second embedding t_s (:300-301,334-335)
 
     @property
     def k0(self) -> int:
@@ -234,8 +235,15 @@ def _lin(p, name, x):
     return F.linear(x, p[name + ".weight"], p[name + ".bias"])
 
 
+def make_emb_s(spec: ModelSpec, seed: int = 0, dtype=torch.float32) -> torch.Tensor:
+    """the second embedding table models["t_s"] of `use_separate_tj_for_semantic` (semantic/pipelines/rs_semantic.py:72-77):
+    N(0,1) like nn.Embedding's initialiser, from its own deterministic stream"""
+    rng = np.random.Generator(np.random.PCG64(seed + 4242))
+    return torch.from_numpy(rng.standard_normal(size=(spec.vocab, spec.tau))).to(dtype)
+
+
 def mlp_forward(p: Dict[str, torch.Tensor], spec: ModelSpec, xyz: torch.Tensor,
-                sun_d: torch.Tensor, t: torch.Tensor, return_hidden: bool = False):
+                sun_d: torch.Tensor, t: torch.Tensor, return_hidden: bool = False, t_s: Optional[torch.Tensor] = None):
     """(B,3),(B,3),(B,tau) -> (B, 9[+C]) packed [rgb 0:3 | sigma 3 | sun 4 | sky 5:8 | beta 8 | sem 9:].
     satnerf.py:208-255 / rs_semantic.py:260-340; Siren: commons.py:27-38 (w0=30 on the
     first trunk layer only, satnerf.py:146)."""
@@ -266,11 +274,13 @@ def mlp_forward(p: Dict[str, torch.Tensor], spec: ModelSpec, xyz: torch.Tensor,
         return (out, hidden, f) if return_hidden else out
     beta = F.softplus(_lin(p, "beta_from_xyz.2", torch.sin(_lin(p, "beta_from_xyz.0", torch.cat([f, t], -1)))))
     cols = [rgb, sigma, sun_v, sky, beta]
+    # the semantic heads' embedding: t, or the separate t_s (rs_semantic.py:300-301,334-335)
+    t_sem = t_s if (spec.kind == "semantic" and spec.separate_tj_s) else t
     if spec.kind == "semantic" and spec.separate_beta_s:   # rs_semantic.py:297-303
         cols.append(F.softplus(_lin(p, "semantic_beta_from_xyz.2",
-                                    torch.sin(_lin(p, "semantic_beta_from_xyz.0", torch.cat([f, t], -1))))))
+                                    torch.sin(_lin(p, "semantic_beta_from_xyz.0", torch.cat([f, t_sem], -1))))))
     if spec.kind == "semantic":
-        f_sem = torch.cat([f, t], -1) if spec.tj_for_s else f                                          # rs_semantic.py:330-338
+        f_sem = torch.cat([f, t_sem], -1) if spec.tj_for_s else f                                      # rs_semantic.py:330-338
         sem = _lin(p, "semantic_prediction.2", torch.sin(_lin(p, "semantic_prediction.0", f_sem)))
         if spec.semantic_sigmoid:
             sem = torch.sigmoid(sem)
@@ -348,19 +358,20 @@ def composite(out: torch.Tensor, z: torch.Tensor, n_classes: int = 0, separate_b
 
 
 def inference(p, spec: ModelSpec, xyz: torch.Tensor, z: torch.Tensor, sun_d: torch.Tensor,
-              t: torch.Tensor) -> Dict[str, torch.Tensor]:
+              t: torch.Tensor, t_s: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """satnerf.py:8-98 / rs_semantic.py:8-128 (per-ray inputs broadcast over samples,
     model evaluated on all points, then composited)."""
     n, s = z.shape
     out = mlp_forward(p, spec, xyz.reshape(-1, 3), torch.repeat_interleave(sun_d, s, 0),
-                      torch.repeat_interleave(t, s, 0) if t is not None else None)
+                      torch.repeat_interleave(t, s, 0) if t is not None else None,
+                      t_s=torch.repeat_interleave(t_s, s, 0) if t_s is not None else None)
     return composite(out.view(n, s, -1), z, spec.n_classes if spec.kind == "semantic" else 0,
                      spec.kind == "semantic" and spec.separate_beta_s)
 
 
 def render_rays(p, emb: torch.Tensor, spec: ModelSpec, rays: torch.Tensor, extras: torch.Tensor,
                 n_samples: int, u: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None,
-                sc_lambda: float = 0.05) -> Dict[str, torch.Tensor]:
+                sc_lambda: float = 0.05, emb_s: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """BaseRenderer.render_rays (framework/components/rendering.py:125-157) +
     {SatNeRF,RSSemantic}Rendering._model_rendering (baseline/components/rendering.py:12-67,
     semantic/components/rendering.py:18-80): main pass, optional solar-correction pass on
@@ -371,14 +382,15 @@ def render_rays(p, emb: torch.Tensor, spec: ModelSpec, rays: torch.Tensor, extra
     sun_d = extras[:, 0:3]
     ts = extras[:, 3].long()
     t = emb[ts] if spec.kind not in ("snerf", "nerf") else None   # no embedding (baseline/components/rendering.py:70-118)
+    t_s = emb_s[ts] if emb_s is not None else None                # models["t_s"](ts), semantic/components/rendering.py:43-45
     if spec.kind == "nerf":   # NeRFRendering (rendering.py:103-118): view direction instead of sun direction, one pass
         res = inference(p, spec, sample_points(o, d, z), z, d, None)
         out = {f"{k}_coarse": v for k, v in res.items()}
         out["_z_vals"] = z
         return out
-    res = inference(p, spec, sample_points(o, d, z), z, sun_d, t)
+    res = inference(p, spec, sample_points(o, d, z), z, sun_d, t, t_s)
     if sc_lambda > 0:
-        tmp = inference(p, spec, sample_points(o, sun_d, z), z, sun_d, t)
+        tmp = inference(p, spec, sample_points(o, sun_d, z), z, sun_d, t, t_s)
         res["weights_sc"] = tmp["weights"]
         res["transparency_sc"] = tmp["transparency"]
         res["sun_sc"] = tmp["sun"]

@@ -325,6 +325,9 @@ static void build_layout(snb_model* m) {
   const bool tj_s = sem && (m->variant & SNB_VARIANT_TJ_FOR_S);
   const bool tj_rgb = sem && (m->variant & SNB_VARIANT_TJ_INSTEAD_OF_BETA);
   const bool bs = m->beta_s != 0;   // semantic_beta_from_xyz (rs_semantic.py:228-237): cat(f, t) -> 256 -> 1, softplus
+  // use_separate_tj_for_semantic (rs_semantic.py:300-301,334-335): the semantic head and the semantic uncertainty head read
+  // a SECOND embedding t_s: aux columns 8..11 (the caller passes the two tables side by side as one (vocab, 8) table)
+  const int ts_col = (sem && (m->variant & SNB_VARIANT_SEPARATE_TJ_S)) ? 8 : 4;
   // ---- flat fp32 parameter order = reference state_dict order ----
   m->n_params = 0;
   for (int i = 0; i < LAYERS; ++i) {
@@ -441,12 +444,12 @@ static void build_layout(snb_model* m) {
   job(m->tf + hhw + 3, ktf, P("sigma_from_xyz.0.weight"), F, F, 1, 1, 0);
   job(m->wf32, F, P("feats_from_xyz.weight"), F, F, F, 0, 2);            // fp32 copy for the weight-sized gradient products
   // fused head first layers: rows [rgb | beta | (sem) | sun]  (NeRF: the rgb block only; the others stay zero)
-  struct Blk { int row; const char* w; const char* b; int kin; bool t_in; };
-  std::vector<Blk> blks = {{m->hh_rgb, "rgb_from_xyzdir.0", "rgb_from_xyzdir.0", F + (nerf ? m->kdir : 0) + (tj_rgb ? tau : 0), tj_rgb}};
-  if (has_beta) blks.push_back({m->hh_beta, "beta_from_xyz.0", "beta_from_xyz.0", F + tau, true});
-  if (!nerf) blks.push_back({m->hh_sun, "sun_v_net.0", "sun_v_net.0", F + 3, false});
-  if (sem) blks.push_back({m->hh_sem, "semantic_prediction.0", "semantic_prediction.0", F + (tj_s ? tau : 0), tj_s});
-  if (bs) blks.push_back({m->hh_bs, "semantic_beta_from_xyz.0", "semantic_beta_from_xyz.0", F + tau, true});
+  struct Blk { int row; const char* w; const char* b; int kin; bool t_in; int t_col; };
+  std::vector<Blk> blks = {{m->hh_rgb, "rgb_from_xyzdir.0", "rgb_from_xyzdir.0", F + (nerf ? m->kdir : 0) + (tj_rgb ? tau : 0), tj_rgb, 4}};
+  if (has_beta) blks.push_back({m->hh_beta, "beta_from_xyz.0", "beta_from_xyz.0", F + tau, true, 4});
+  if (!nerf) blks.push_back({m->hh_sun, "sun_v_net.0", "sun_v_net.0", F + 3, false, 4});
+  if (sem) blks.push_back({m->hh_sem, "semantic_prediction.0", "semantic_prediction.0", F + (tj_s ? tau : 0), tj_s, ts_col});
+  if (bs) blks.push_back({m->hh_bs, "semantic_beta_from_xyz.0", "semantic_beta_from_xyz.0", F + tau, true, ts_col});
   for (auto& b : blks) {
     const long long w = P(std::string(b.w) + ".weight"), bb = P(std::string(b.b) + ".bias");
     // the f-columns W' = W_b W_f (+ their transpose in tf) and the bias column b' = b_b + W_b b_f (aux column 0 = 1) are
@@ -460,10 +463,10 @@ static void build_layout(snb_model* m) {
   } else {
     job(m->wh1 + (long long)m->hh_sun * kh1 + F + 1, kh1, P("sun_v_net.0.weight") + F, F + 3, FL, 3, 0, 0);
     for (auto& b : blks)
-      if (b.t_in) {   // aux columns 4..4+tau = t: the block's last tau weight columns; their transpose feeds the dgrad into t
+      if (b.t_in) {   // aux columns 4..4+tau = t (8.. = t_s): the block's last tau weight columns; their transpose feeds the dgrad into t
         const long long w = P(std::string(b.w) + ".weight");
-        job(m->wh1 + (long long)b.row * kh1 + F + 4, kh1, w + F, b.kin, FL, tau, 0, 0);
-        job(m->taux + 4ll * m->taux_cols + (b.row - m->taux_lo), m->taux_cols, w + F, b.kin, tau, FL, 1, 0);
+        job(m->wh1 + (long long)b.row * kh1 + F + b.t_col, kh1, w + F, b.kin, FL, tau, 0, 0);
+        job(m->taux + (long long)b.t_col * m->taux_cols + (b.row - m->taux_lo), m->taux_cols, w + F, b.kin, tau, FL, 1, 0);
       }
     job(m->ws2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 0, 0);
     job(m->ts2, FL, P("sun_v_net.2.weight"), FL, FL, FL, 1, 0);
@@ -541,7 +544,7 @@ static void build_layout(snb_model* m) {
   } else {
     ujob(P("sun_v_net.0.weight") + F, F + 3, m->gh1aux + (long long)m->hh_sun * 16 + 1, 16, FL, 3, 0);
     for (auto& b : blks)
-      if (b.t_in) ujob(P(std::string(b.w) + ".weight") + F, b.kin, m->gh1aux + (long long)b.row * 16 + 4, 16, FL, tau, 0);
+      if (b.t_in) ujob(P(std::string(b.w) + ".weight") + F, b.kin, m->gh1aux + (long long)b.row * 16 + b.t_col, 16, FL, tau, 0);
     ujob(P("sun_v_net.2.weight"), FL, m->gs2, FL, FL, FL, 0);
     ujob(P("sun_v_net.2.bias"), 1, m->gbs2, 1, FL, 1, 0);
     ujob(P("sun_v_net.4.weight"), FL, m->gs4, FL, FL, FL, 0);
@@ -900,7 +903,8 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   if (model_kind != SNB_MODEL_SEMANTIC) n_classes = 0;
   SNB_CHECK_ARG(variant == 0 || model_kind == SNB_MODEL_SEMANTIC, SNB_ERR_UNSUPPORTED,
                 "model_create: head-input variants exist for the semantic model only");
-  SNB_CHECK_ARG((variant & ~(SNB_VARIANT_TJ_FOR_S | SNB_VARIANT_TJ_INSTEAD_OF_BETA | SNB_VARIANT_SEPARATE_BETA_S)) == 0,
+  SNB_CHECK_ARG((variant & ~(SNB_VARIANT_TJ_FOR_S | SNB_VARIANT_TJ_INSTEAD_OF_BETA | SNB_VARIANT_SEPARATE_BETA_S |
+                             SNB_VARIANT_SEPARATE_TJ_S)) == 0,
                 SNB_ERR_UNSUPPORTED, "model_create: variant bits %d not implemented", variant);
   SNB_CHECK_ARG(!(variant & SNB_VARIANT_SEPARATE_BETA_S) || n_classes <= 9, SNB_ERR_UNSUPPORTED,
                 "model_create: the separate semantic uncertainty head leaves 9 of the 16 head rows for classes (n_classes %d)",
@@ -1325,6 +1329,12 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
     auto per_ray = [&](const float* a, int k) {   // (rays, k) broadcast by row index, or (points, k)
       return by_ray ? F32Seg{a, (long long)k, k, div, r0} : F32Seg{a + r0 * k, (long long)k, k, 1, 0};
     };
+    // use_separate_tj_for_semantic: `t` then carries the two embeddings side by side, (R, 2 tau) = [t | t_s]
+    const bool sep_ts = (m->variant & SNB_VARIANT_SEPARATE_TJ_S) != 0;
+    const int t_ld = sep_ts ? 2 * tau : tau;
+    auto per_ray_t = [&](int col) {   // tau columns of the per-ray embedding rows starting at `col`
+      return by_ray ? F32Seg{t + col, (long long)t_ld, tau, div, r0} : F32Seg{t + r0 * t_ld + col, (long long)t_ld, tau, 1, 0};
+    };
     const F32Seg senc = rows(enc, F32_ENC_LD, k0);
     // trunk (satnerf.py:220-229): layer i reads cur, writes the other buffer; the skip layer reads cat(enc, h)
     float* cur = hA;
@@ -1363,25 +1373,25 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
     if (!all) continue;
     {
       const bool tj_rgb = (m->variant & SNB_VARIANT_TJ_INSTEAD_OF_BETA) != 0;   // cat(f, t) -> colour head (rs_semantic.py:287-288)
-      const F32Seg st_ = per_ray(t, tau);
+      const F32Seg st_ = per_ray_t(0);
       if (int r = gemm(sf, tj_rgb ? &st_ : nullptr, W("rgb_from_xyzdir.0"), F + (tj_rgb ? tau : 0), B("rgb_from_xyzdir.0"), FL,
                        F32_SIN, 1.0f, g1, FL)) return r;
     }
     if (int r = gemm(rows(g1, FL, FL), nullptr, W("rgb_from_xyzdir.2"), FL, B("rgb_from_xyzdir.2"), 3, F32_RGB, 1.0f, o, n_out)) return r;
     if (m->find("beta_from_xyz.0.weight") >= 0) {
-      const F32Seg st_ = per_ray(t, tau);
+      const F32Seg st_ = per_ray_t(0);
       if (int r = gemm(sf, &st_, W("beta_from_xyz.0"), F + tau, B("beta_from_xyz.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("beta_from_xyz.2"), FL, B("beta_from_xyz.2"), 1, F32_SOFTPLUS, 1.0f, o + 8, n_out)) return r;
     }
     if (m->beta_s) {   // semantic uncertainty head (rs_semantic.py:228-237,297-303): cat(f, t) -> sin -> softplus, column 9
-      const F32Seg st_ = per_ray(t, tau);
+      const F32Seg st_ = per_ray_t(sep_ts ? tau : 0);
       if (int r = gemm(sf, &st_, W("semantic_beta_from_xyz.0"), F + tau, B("semantic_beta_from_xyz.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("semantic_beta_from_xyz.2"), FL, B("semantic_beta_from_xyz.2"), 1, F32_SOFTPLUS, 1.0f,
                        o + 9, n_out)) return r;
     }
     if (sem) {
       const bool tj_s = (m->variant & SNB_VARIANT_TJ_FOR_S) != 0;               // cat(f, t) -> semantic head (rs_semantic.py:330-338)
-      const F32Seg st_ = per_ray(t, tau);
+      const F32Seg st_ = per_ray_t(sep_ts ? tau : 0);
       if (int r = gemm(sf, tj_s ? &st_ : nullptr, W("semantic_prediction.0"), F + (tj_s ? tau : 0), B("semantic_prediction.0"), FL,
                        F32_SIN, 1.0f, g1, FL)) return r;
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("semantic_prediction.2"), FL, B("semantic_prediction.2"), C,

@@ -34,6 +34,9 @@ class SnbMLP(torch.nn.Module):
         self.kind = kind
         self.semantic_n_classes = n_classes          # read by the reference's inference(), rs_semantic.py:95
         self.beta_s = 1 if (variant & _lib.VARIANT_SEPARATE_BETA_S) else 0   # column 9 = the separate semantic uncertainty
+        # use_separate_tj_for_semantic: the semantic heads read a second embedding t_s; the kernels take [t | t_s] as ONE
+        # (.., 2 tau) tensor (aux columns 4..7 and 8..11), the gradient comes back the same way and autograd splits it
+        self.sep_ts = bool(variant & _lib.VARIANT_SEPARATE_TJ_S)
         self.number_of_outputs = 9 + self.beta_s + n_classes       # satnerf.py:120 / rs_semantic.py:291-311
         self.n_out_kernel = 9 + self.beta_s + n_classes            # columns of the packed tensor the kernels write
         self.t_embedding_dims = tau
@@ -153,6 +156,10 @@ class SnbMLP(torch.nn.Module):
         """(B,3),(B,3),(B,tau) -> (B, 9[+C]) packed exactly like the reference's forward
         (satnerf.py:208-255, rs_semantic.py:260-313)."""
         from .autograd import mlp_fp32, mlp_points
+        if self.sep_ts:
+            if input_t_s is None:
+                raise _lib.SnbError("use_separate_tj_for_semantic: forward() needs input_t_s (rs_semantic.py:300-301)")
+            input_t = torch.cat([input_t, input_t_s], 1)
         if getattr(self, "precision", "bf16") == "fp32":   # verification mode: fp32 end to end, inference only
             lib = _lib.load()
             xyz = input_xyz.float().contiguous()
@@ -188,7 +195,7 @@ class RSSemanticNeRFB200(SnbMLP):
 
     def __init__(self, cfgs, dataset_semantic):
         p = cfgs.pipeline
-        unsupported = [k for k in ("use_separate_tj_for_semantic", "fc_use_full_features") if getattr(p, k, False)]
+        unsupported = [k for k in ("fc_use_full_features",) if getattr(p, k, False)]
         if unsupported or p.fc_layers != 8 or p.fc_units != 512 or list(p.fc_skips) != [4] \
                 or p.activation_function != "siren" or p.mapping_pos_n_freq != 10:
             raise _lib.SnbError(f"libsnb implements the shipped rs_semantic.toml architecture; unsupported: {unsupported}")
@@ -196,7 +203,8 @@ class RSSemanticNeRFB200(SnbMLP):
         # head-input variants: t as an extra input of the semantic head / of the colour head (rs_semantic.py:186-215)
         variant = (_lib.VARIANT_TJ_FOR_S if getattr(p, "use_tj_for_s", False) else 0) | \
                   (_lib.VARIANT_TJ_INSTEAD_OF_BETA if getattr(p, "use_tj_instead_of_beta", False) else 0) | \
-                  (_lib.VARIANT_SEPARATE_BETA_S if getattr(p, "use_separate_beta_for_s", False) else 0)
+                  (_lib.VARIANT_SEPARATE_BETA_S if getattr(p, "use_separate_beta_for_s", False) else 0) | \
+                  (_lib.VARIANT_SEPARATE_TJ_S if getattr(p, "use_separate_tj_for_semantic", False) else 0)
         super().__init__(MODEL_SEMANTIC, int(dataset_semantic.semantic_n_classes), sig, p.t_embedding_tau, cfgs, variant)
         self.cfg = p
         self.layers, self.skips = p.fc_layers, list(p.fc_skips)

@@ -59,8 +59,11 @@ def get_pipeline_classes():
     class RSSemanticB200Pipeline(RSSemanticPipeline):
         def _init_models(self) -> dict:
             p = self.cfgs.pipeline
-            return {"coarse": RSSemanticNeRFB200(self.cfgs, self.datasets["rgb"]),
-                    "t": torch.nn.Embedding(p.t_embedding_vocab, p.t_embedding_tau)}
+            d = {"coarse": RSSemanticNeRFB200(self.cfgs, self.datasets["rgb"]),
+                 "t": torch.nn.Embedding(p.t_embedding_vocab, p.t_embedding_tau)}
+            if p.use_separate_tj_for_semantic:   # semantic/pipelines/rs_semantic.py:72-77
+                d["t_s"] = torch.nn.Embedding(p.t_embedding_vocab, p.t_embedding_tau)
+            return d
 
         def _init_renderer(self):
             return RSSemanticB200Rendering(self.cfgs)

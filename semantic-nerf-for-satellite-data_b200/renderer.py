@@ -42,7 +42,7 @@ class B200Renderer:
                          render_options=None):
         opts = render_options or {}
         model = models[typ]
-        emb = models["t"].weight if "t" in models else None
+        emb = self._embedding(models, model)
         n, S = rays.shape[0], self.N_samples
         if z_vals is None:
             z_vals = opts.get("z_vals")
@@ -66,7 +66,7 @@ class B200Renderer:
             # sample positions exactly as the reference forms them (framework/components/rendering.py:113-115) and the
             # per-ray inputs in fp32; K1 above still supplies z_vals (bit-exact) and the per-ray sky colour (fp32)
             o, d, sun_d = rays[:, 0:3].float(), rays[:, 3:6].float(), extras[:, 0:3].float()
-            t_ray = emb[extras[:, 3].long()].float() if emb is not None else torch.zeros(n, 4, device=rays.device)
+            t_ray = emb.detach()[extras[:, 3].long()].float() if emb is not None else torch.zeros(n, 4, device=rays.device)
             xyz_main = (o.unsqueeze(1) + d.unsqueeze(1) * z.unsqueeze(2)).reshape(-1, 3)
             if nerf:   # the per-ray input is the ENCODED view direction; the sun column is pinned to 1 (no lighting model)
                 from .model import posenc_dirs
@@ -129,7 +129,7 @@ class B200Renderer:
         its constant 3/2)."""
         opts = render_options or {}
         model = models["coarse"]
-        emb = models["t"].weight if "t" in models else None
+        emb = self._embedding(models, model)
         n, S = rays.shape[0], self.N_samples
         depth_pass = depth is not None
         nerf = getattr(model, "variant", None) == "nerf"
@@ -164,6 +164,19 @@ class B200Renderer:
             loss = loss + CompositeLoss.apply(out_sc, z, 0, p_sc, None, None, None, None, None, terms)
         self.last_counts = counts
         return loss, terms
+
+    @staticmethod
+    def _embedding(models, model):
+        """the per-image embedding table(s) as the kernels take them: models["t"].weight, or - `use_separate_tj_for_semantic`
+        (semantic/components/rendering.py:42-45) - [t | t_s] side by side as one (vocab, 2 tau) table (a differentiable cat:
+        the gradient of the combined table splits back into the two embeddings)"""
+        if "t" not in models:
+            return None
+        if getattr(model, "sep_ts", False):
+            if "t_s" not in models:
+                raise _lib.SnbError('use_separate_tj_for_semantic: models["t_s"] is missing (semantic/pipelines/rs_semantic.py:72-77)')
+            return torch.cat([models["t"].weight, models["t_s"].weight], 1)
+        return models["t"].weight
 
     @staticmethod
     def _empty_result(model, rays, S, sc):

@@ -39,7 +39,7 @@ from .losses import (DepthLoss, NerfLoss, SatNerfLoss, SemanticCarRegLoss, Seman
 from .model import NeRFB200, RSSemanticNeRFB200, SatNeRFB200, ShadowNeRFB200
 from .renderer import B200Renderer
 
-EMB_PAD = 256   # floats reserved in front of the model parameters for the embedding table (vocab * tau <= 256)
+EMB_PAD = 512   # floats reserved in front of the model parameters for the embedding tables: t at 0, t_s (if any) at 256
 
 
 def default_cfgs(kind: str = "semantic", n_samples: int = 64, sc_lambda: float = 0.05, **over):
@@ -111,12 +111,14 @@ class Trainer:
         self.models = {"coarse": model.to(self.device)}
         if kind not in ("snerf", "nerf"):
             self.models["t"] = torch.nn.Embedding(p.t_embedding_vocab, p.t_embedding_tau).to(self.device)
+        if kind == "semantic" and getattr(p, "use_separate_tj_for_semantic", False):
+            self.models["t_s"] = torch.nn.Embedding(p.t_embedding_vocab, p.t_embedding_tau).to(self.device)
         emb = self.models.get("t")
         # ONE flat buffer [embedding table (padded) | model parameters] for parameters, gradients and Adam moments: the
         # optimiser is one launch, and the embedding gradient rides the last all-reduce bucket instead of its own collective
         self.n_emb = emb.weight.numel() if emb is not None else 0
-        if self.n_emb > EMB_PAD:
-            raise _lib.SnbError(f"embedding table of {self.n_emb} floats exceeds the {EMB_PAD} reserved")
+        if self.n_emb > EMB_PAD // 2:
+            raise _lib.SnbError(f"embedding table of {self.n_emb} floats exceeds the {EMB_PAD // 2} reserved")
         n_params = model.flat.numel()
         self.pbuf = torch.zeros(EMB_PAD + n_params, dtype=torch.float32, device=self.device)
         self.pbuf[EMB_PAD:].copy_(model.flat.data)
@@ -124,6 +126,10 @@ class Trainer:
         if emb is not None:
             self.pbuf[:self.n_emb].copy_(emb.weight.data.reshape(-1))
             emb.weight.data = self.pbuf[:self.n_emb].view_as(emb.weight)
+        emb_s = self.models.get("t_s")
+        if emb_s is not None:
+            self.pbuf[EMB_PAD // 2:EMB_PAD // 2 + self.n_emb].copy_(emb_s.weight.data.reshape(-1))
+            emb_s.weight.data = self.pbuf[EMB_PAD // 2:EMB_PAD // 2 + self.n_emb].view_as(emb_s.weight)
         self.gbuf = torch.zeros_like(self.pbuf)
         self.exp_avg = torch.zeros_like(self.pbuf)
         self.exp_avg_sq = torch.zeros_like(self.pbuf)
@@ -146,7 +152,9 @@ class Trainer:
         # fused_loss: compositing + the loss modules + their backward in one kernel per pass; False runs
         # render_rays() + the reference-shaped loss modules (what a Lightning pipeline does)
         self.fused_loss = fused_loss
-        self.direct = direct and fused_loss
+        # (the direct step hands K1 one embedding table; with the second table of use_separate_tj_for_semantic the step runs
+        # through render_loss under autograd, which concatenates the two)
+        self.direct = direct and fused_loss and "t_s" not in self.models
         self.use_graph = bool(graph) and self.direct and world == 1
         # micro_batch: the direct step runs batches larger than this many rays as several forward / backward passes that
         # accumulate into the one gradient buffer before the single optimiser step (the saved activations cost ~25 KB per
@@ -175,6 +183,9 @@ class Trainer:
         model.flat.grad = self.gbuf[EMB_PAD:]
         if emb is not None:
             emb.weight.grad = self.gbuf[:self.n_emb].view_as(emb.weight)
+        if "t_s" in self.models:
+            w = self.models["t_s"].weight
+            w.grad = self.gbuf[EMB_PAD // 2:EMB_PAD // 2 + self.n_emb].view_as(w)
 
     # -- one step ---------------------------------------------------------------------------------------
     def training_step(self, batch: Dict[str, torch.Tensor], epoch: int = 2, depth_batch: Optional[dict] = None,

@@ -21,7 +21,7 @@ def make_cfgs(spec, n_samples: int, sc_lambda: float):
         mapping_pos_n_freq=spec.n_freq, mapping_dir_n_freq=4,
         semantic_activation_function="sigmoid" if spec.semantic_sigmoid else "none",
         use_tj_for_s=spec.tj_for_s, use_tj_instead_of_beta=spec.tj_instead_of_beta, use_beta_for_s=False,
-        use_separate_beta_for_s=spec.separate_beta_s, use_separate_tj_for_semantic=False)
+        use_separate_beta_for_s=spec.separate_beta_s, use_separate_tj_for_semantic=spec.separate_tj_s)
     return types.SimpleNamespace(pipeline=pl)
 
 
@@ -40,6 +40,7 @@ GOLDEN_CASES = [
     ("nerf_s8", "nerf", 0, 512, 16, 8, 0.0, 11),
     ("sem_c6_s8_tj", "semantic", 6, 512, 16, 8, 0.05, 12),      # use_tj_for_s + use_tj_instead_of_beta
     ("sem_c9_s8_bs", "semantic", 9, 512, 16, 8, 0.05, 13),      # use_separate_beta_for_s
+    ("sem_c6_s8_ts", "semantic", 6, 512, 16, 8, 0.05, 14),      # use_tj_for_s + use_separate_beta_for_s + use_separate_tj_for_semantic
 ]
 
 
@@ -47,8 +48,9 @@ def golden_inputs(case):
     from oracle import render_oracle as O
     name, kind, C, feat, n, s, sc, seed = case
     tj = name.endswith("_tj")
-    spec = O.ModelSpec(kind=kind, n_classes=C, feat=feat, tj_for_s=tj, tj_instead_of_beta=tj,
-                       separate_beta_s=name.endswith("_bs"))
+    ts = name.endswith("_ts")
+    spec = O.ModelSpec(kind=kind, n_classes=C, feat=feat, tj_for_s=tj or ts, tj_instead_of_beta=tj,
+                       separate_beta_s=name.endswith("_bs") or ts, separate_tj_s=ts)
     params, emb = O.make_params(spec, seed=seed, trained_like=name.endswith("trained"))
     rays, extras = O.synthetic_rays(n, seed=seed)
     rng = np.random.Generator(np.random.PCG64(seed + 77))

@@ -106,9 +106,10 @@ def test_gemm_rejects_bad_arguments():
 # ------------------------------------------------------------------------------------------------
 # K1: sampling + encoding
 # ------------------------------------------------------------------------------------------------
-def _model(kind, C, seed=3, S=64, sc=0.05, trained_like=False, tj=False, bs=False):
+def _model(kind, C, seed=3, S=64, sc=0.05, trained_like=False, tj=False, bs=False, ts=False):
+    """ts: every head variant at once incl. the second embedding (the caller adds models["t_s"] = O.make_emb_s(spec, seed))"""
     from semnerf_b200.model import RSSemanticNeRFB200, SatNeRFB200
-    spec = O.ModelSpec(kind=kind, n_classes=C, tj_for_s=tj, tj_instead_of_beta=tj, separate_beta_s=bs)
+    spec = O.ModelSpec(kind=kind, n_classes=C, tj_for_s=tj or ts, tj_instead_of_beta=tj, separate_beta_s=bs or ts, separate_tj_s=ts)
     params, emb = O.make_params(spec, seed=seed, trained_like=trained_like)
     cfgs = make_cfgs(spec, S, sc)
     if kind == "snerf":

@@ -9,6 +9,7 @@ import torch
 
 from oracle import render_oracle as O
 from tests.helpers import GOLDEN_CASES, golden_inputs, make_cfgs
+from semnerf_b200 import _lib
 from tests.test_gpu_kernels import DEV, _lib_or_fail, _model
 
 pytestmark = pytest.mark.gpu
@@ -59,10 +60,13 @@ def test_render_rays_against_reference_golden(case):
     name, kind, C, feat, n, s, sc, seed = case
     spec, params, emb, rays, extras, u, gold = golden_inputs(case)
     _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"),
-                                     tj=name.endswith("_tj"), bs=name.endswith("_bs"))
+                                     tj=name.endswith("_tj"), bs=name.endswith("_bs"), ts=name.endswith("_ts"))
     renderer = B200Renderer(cfgs)
     with torch.no_grad():
         models = {"coarse": model} if kind in ("snerf", "nerf") else {"coarse": model, "t": t}
+        if spec.separate_tj_s:   # the second embedding of use_separate_tj_for_semantic
+            models["t_s"] = torch.nn.Embedding(spec.vocab, spec.tau).to(DEV)
+            models["t_s"].weight.data.copy_(O.make_emb_s(spec, seed=seed))
         res = renderer.render_rays(models, rays.to(DEV), extras.to(DEV), render_options={"u": u.to(DEV)})
         assert set(gold) - {"loss_satnerf", "model_forward", "grad_norms"} <= set(res)
         if kind == "snerf":   # snerf.py:86-96: no beta / sigmas entries
@@ -226,10 +230,13 @@ def test_fp32_mode_render_rays_against_reference_golden(case):
     name, kind, C, feat, n, s, sc, seed = case
     spec, params, emb, rays, extras, u, gold = golden_inputs(case)
     _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"),
-                                     tj=name.endswith("_tj"), bs=name.endswith("_bs"))
+                                     tj=name.endswith("_tj"), bs=name.endswith("_bs"), ts=name.endswith("_ts"))
     renderer = B200Renderer(cfgs)
     with torch.no_grad():
         models = {"coarse": model} if kind in ("snerf", "nerf") else {"coarse": model, "t": t}
+        if spec.separate_tj_s:   # the second embedding of use_separate_tj_for_semantic
+            models["t_s"] = torch.nn.Embedding(spec.vocab, spec.tau).to(DEV)
+            models["t_s"].weight.data.copy_(O.make_emb_s(spec, seed=seed))
         res = renderer.render_rays(models, rays.to(DEV), extras.to(DEV),
                                    render_options={"u": u.to(DEV), "precision": "fp32"})
     worst = {}
@@ -521,3 +528,69 @@ def test_class_count_and_sample_count_limits(C, S):
     (O.satnerf_loss(ref, gt) + O.semantic_loss(ref, lab)).backward()
     (O.satnerf_loss(res, gt.to(DEV)) + O.semantic_loss(res, lab.to(DEV))).backward()
     assert _cos(model.flat.grad.cpu(), torch.cat([p[k].grad.flatten() for k in p])) >= 0.999
+
+
+def test_separate_semantic_embedding_gradients_and_training():
+    """`use_separate_tj_for_semantic` together with `use_tj_for_s` and `use_separate_beta_for_s` (rs_semantic.py:297-303,330-338):
+    the semantic head and the semantic uncertainty head read the second embedding models["t_s"].  render_rays values, every
+    parameter gradient and the gradients of BOTH embedding tables against the oracle; then a few trainer steps (the trainer
+    keeps the second table next to the first in its flat buffer and runs this configuration through render_loss)."""
+    from semnerf_b200 import synth
+    from semnerf_b200.renderer import RSSemanticB200Rendering
+    from semnerf_b200.trainer import Trainer, default_cfgs
+    _lib_or_fail()
+    S, n, C = 64, 384, 6
+    spec, params, emb, cfgs, model, t = _model("semantic", C, seed=3, S=S, ts=True)
+    emb_s = O.make_emb_s(spec, seed=3)
+    t_s = torch.nn.Embedding(spec.vocab, spec.tau).to(DEV)
+    t_s.weight.data.copy_(emb_s)
+    rays, extras = O.synthetic_rays(n, seed=21)
+    u = torch.rand(n, S, generator=torch.Generator().manual_seed(8))
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    e, es = emb.clone().requires_grad_(True), emb_s.clone().requires_grad_(True)
+    ref = O.render_rays(p, e, spec, rays, extras, S, u=u, sc_lambda=0.05, emb_s=es)
+    with pytest.raises(_lib.SnbError):      # the second table is required
+        RSSemanticB200Rendering(cfgs).render_rays({"coarse": model, "t": t}, rays.to(DEV), extras.to(DEV))
+    res = RSSemanticB200Rendering(cfgs).render_rays({"coarse": model, "t": t, "t_s": t_s}, rays.to(DEV), extras.to(DEV),
+                                                   render_options={"u": u.to(DEV)})
+    for k in ("rgb_coarse", "depth_coarse", "semantic_logits_coarse"):
+        assert (res[k].detach().cpu() - ref[k].detach()).abs().max() <= 2e-3, k
+    assert (res["beta_semantic_coarse"].detach().cpu() - ref["beta_semantic_coarse"].detach()).abs().max() <= 5e-3
+    gt = torch.rand(n, 3, generator=torch.Generator().manual_seed(9))
+    lab = torch.randint(0, C, (n, 1), generator=torch.Generator().manual_seed(4)).to(torch.uint8)
+    (O.satnerf_loss(ref, gt) + O.semantic_uncertainty_loss(ref, lab, 0.4, 4)).backward()
+    (O.satnerf_loss(res, gt.to(DEV)) + O.semantic_uncertainty_loss(res, lab.to(DEV), 0.4, 4)).backward()
+    g_all = torch.cat([p[k].grad.flatten() for k in p])
+    assert _cos(model.flat.grad.cpu(), g_all) >= 0.999
+    grads = model.named_grads()
+    for k in p:
+        if p[k].grad.norm() >= 1e-3 * g_all.norm():
+            assert _cos(grads[k].cpu(), p[k].grad) >= 0.995, k
+    assert _cos(t.weight.grad.cpu(), e.grad) >= 0.995 and _cos(t_s.weight.grad.cpu(), es.grad) >= 0.995
+    assert float(es.grad.abs().max()) > 0
+    # Model.forward with input_t_s (rs_semantic.py:260-313)
+    P = 500
+    g = torch.Generator().manual_seed(0)
+    xyz = torch.rand(P, 3, generator=g) * 2 - 1
+    sun = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=1)
+    tt, tts = torch.randn(P, 4, generator=g), torch.randn(P, 4, generator=g)
+    with torch.no_grad():
+        out = model(xyz.to(DEV), input_sun_dir=sun.to(DEV), input_t=tt.to(DEV), input_t_s=tts.to(DEV))
+        model.precision = "fp32"
+        out32 = model(xyz.to(DEV), input_sun_dir=sun.to(DEV), input_t=tt.to(DEV), input_t_s=tts.to(DEV))
+        model.precision = "bf16"
+        want = O.mlp_forward({k: v.double() for k, v in params.items()}, spec, xyz.double(), sun.double(), tt.double(), t_s=tts.double())
+    assert out.shape == (P, 10 + C) and (out32.cpu().double() - want).abs().max() <= 5e-5
+    assert (out.cpu().double() - want)[:, [0, 1, 2, 4]].abs().max() <= 2e-3 and (out.cpu().double() - want)[:, 10:].abs().max() <= 2e-3
+    # trainer
+    tcfg = default_cfgs("semantic", n_samples=16, sc_lambda=0.05, use_tj_for_s=True, use_separate_beta_for_s=True,
+                        use_separate_tj_for_semantic=True, use_beta_for_s=True)
+    tr = Trainer(tcfg, "semantic", C, device=DEV, car_index=4, seed=0)
+    assert "t_s" in tr.models and not tr.direct
+    rr, ee = synth.make_rays(1024, seed=0)
+    rgbs, labels, _ = synth.make_targets(rr, C, seed=0)
+    batch = {"rays": rr.to(DEV), "extras": ee.to(DEV), "rgbs": rgbs.to(DEV), "semantic": labels.to(DEV)}
+    ts0 = tr.models["t_s"].weight.detach().clone()
+    losses = [tr.training_step(batch, epoch=3).item() for _ in range(12)]
+    assert all(l == l for l in losses) and losses[-1] < losses[0]
+    assert not torch.equal(ts0, tr.models["t_s"].weight.detach())      # the optimiser steps the second table too

@@ -14,6 +14,7 @@ import torch
 from oracle import render_oracle as O
 from oracle.step_cases import BATCHED_CASE, BATCHED_CHUNK, CAR, oracle_step_loss
 from tests.helpers import GOLDEN
+from semnerf_b200.trainer import EMB_PAD
 from tests.test_gpu_kernels import DEV, _lib_or_fail, _model
 
 pytestmark = pytest.mark.gpu
@@ -102,7 +103,7 @@ def test_fused_training_step_matches_the_oracle(kind, C, epoch, with_depth, with
         if with_depth:
             depth["z"] = tr._bufs[("depth", nd)].z.cpu()
     got = dict(zip(TERMS, terms.cpu().tolist()))
-    g_flat = tr.gbuf[256:].cpu()
+    g_flat = tr.gbuf[EMB_PAD:].cpu()
     g_emb = tr.gbuf[:tr.n_emb].cpu() if tr.n_emb else None
 
     p2 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
@@ -193,12 +194,12 @@ def test_uncertainty_weighted_semantic_loss_matches_the_oracle(mode, detach, bs,
     assert abs(loss.item() - ref.item()) <= 1e-2 * abs(ref.item())
     # NB: the parameters have moved (Adam ran), the gradient buffer still holds this step's gradient
     g_ref = torch.cat([p2[k].grad.flatten() if p2[k].grad is not None else torch.zeros(p2[k].numel()) for k in p2])
-    assert _cos(tr.gbuf[256:].cpu(), g_ref) >= 0.999
+    assert _cos(tr.gbuf[EMB_PAD:].cpu(), g_ref) >= 0.999
     assert _cos(tr.gbuf[:tr.n_emb].cpu(), e2.grad) >= 0.995
     # the uncertainty heads' own gradients are where detach / no detach differ most
     for name in ["beta_from_xyz.2.weight"] + (["semantic_beta_from_xyz.2.weight", "semantic_beta_from_xyz.0.weight"] if bs else []):
         off, m = tr.models["coarse"].offset_of(name), p2[name].numel()
-        got_g, ref_g = tr.gbuf[256 + off: 256 + off + m].cpu(), p2[name].grad
+        got_g, ref_g = tr.gbuf[EMB_PAD + off: EMB_PAD + off + m].cpu(), p2[name].grad
         if ref_g is None or ref_g.abs().max() == 0:     # detached: the head receives nothing from this loss
             assert got_g.abs().max() <= 1e-7 * g_ref.abs().max()
         else:

@@ -74,7 +74,7 @@ def test_initialiser_ranges_follow_the_reference():
 def test_unsupported_configurations_fail_loudly():
     spec = O.ModelSpec(kind="semantic")
     cfgs = make_cfgs(spec, 64, 0.05)
-    cfgs.pipeline.use_separate_tj_for_semantic = True
+    cfgs.pipeline.fc_use_full_features = True
     with pytest.raises(_lib.SnbError):
         RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": 6})())
     with pytest.raises(_lib.SnbError):

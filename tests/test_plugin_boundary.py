@@ -125,8 +125,29 @@ def test_plugin_renderer_refuses_an_injected_inference_function(ref):
 
 def test_unsupported_head_variants_raise_at_construction(ref):
     from semnerf_b200 import _lib
-    for flag in ("use_separate_tj_for_semantic", "fc_use_full_features"):
+    for flag in ("fc_use_full_features",):
         cfgs = _cfgs(ref, "rs_semantic.toml", "semnerf_b200.pipelines.RSSemanticB200Pipeline")
         setattr(cfgs.pipeline, flag, True)
         with pytest.raises(_lib.SnbError):
             ref.pipelines.load_pipeline(cfgs)
+
+
+def test_head_variants_build_the_same_state_dict_as_the_reference(ref):
+    """every head-input variant the plug-in implements (use_tj_for_s, use_tj_instead_of_beta, use_separate_beta_for_s,
+    use_separate_tj_for_semantic) switched on at once: same models (incl. the second embedding "t_s"), same state_dict keys
+    and shapes as the reference pipeline built from the same config, checkpoints load both ways"""
+    pipes = []
+    for dotted in ("semnerf_b200.pipelines.RSSemanticB200Pipeline", "semantic.pipelines.rs_semantic.RSSemanticPipeline"):
+        cfgs = _cfgs(ref, "rs_semantic.toml", dotted)
+        for flag in ("use_tj_for_s", "use_tj_instead_of_beta", "use_separate_beta_for_s", "use_separate_tj_for_semantic"):
+            setattr(cfgs.pipeline, flag, True)
+        pipes.append(ref.pipelines.load_pipeline(cfgs))
+    ours, theirs = pipes
+    assert set(ours.models) == set(theirs.models) == {"coarse", "t", "t_s"}
+    sd, sd_ref = ours.state_dict(), theirs.state_dict()
+    assert list(sd.keys()) == list(sd_ref.keys())
+    assert all(tuple(sd[k].shape) == tuple(sd_ref[k].shape) for k in sd)
+    assert tuple(sd["model_coarse.semantic_prediction.0.weight"].shape) == (256, 516)
+    assert "model_coarse.semantic_beta_from_xyz.2.weight" in sd and ours.models["coarse"].number_of_outputs == 10 + 6
+    ours.load_state_dict(sd_ref)
+    theirs.load_state_dict(ours.state_dict())
