@@ -145,6 +145,20 @@ int snb_mlp_backward(const snb_model* m, const void* packed, void* workspace, si
                      int64_t n_points, const void* enc, const void* aux, const float* out,
                      const float* g_out, int head_mask, float* grads, float* g_aux, void* const* bucket_events,
                      void* stream);
+/* One training step's main pass AND its solar-correction pass (baseline/components/rendering.py:103-118: the same model
+ * evaluated at the points along the sun direction, sigma and sun heads only) on ONE workspace of n_points + n_solar_points
+ * rows (snb_mlp_workspace_bytes of the sum): rows [0, n_points) of enc / out / g_out are the main pass (all heads), rows
+ * [n_points, n_points + n_solar_points) the solar pass; aux row i serves both (n_solar_points <= n_points; 0 = no solar pass).
+ * Forward = the two passes' chained launches.  Backward = the two passes' dgrad chains, then ONE weight-gradient GEMM per
+ * layer both passes share (trunk, sun layers, head outputs) over all rows, one set of folded-layer products and one
+ * unpack per bucket - instead of two of each with snb_mlp_backward called per pass.  Results equal the two-call form. */
+int snb_mlp_forward_with_solar(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
+                               int64_t n_points, int64_t n_solar_points, const void* enc, const void* aux,
+                               const float* sky, int rows_per_ray, float* out, void* stream);
+int snb_mlp_backward_with_solar(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
+                                int64_t n_points, int64_t n_solar_points, const void* enc, const void* aux,
+                                const float* out, const float* g_out, float* grads, float* g_aux,
+                                void* const* bucket_events, void* stream);
 /* flat element ranges [lo[b], hi[b]) of the three gradient buckets, in completion order */
 int snb_model_grad_buckets(const snb_model* m, int64_t* lo3, int64_t* hi3);
 

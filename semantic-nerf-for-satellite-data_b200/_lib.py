@@ -41,6 +41,8 @@ SIGNATURES = {
     "snb_mlp_workspace_bytes": (_sz, [_vp, _i64, _i]),
     "snb_mlp_forward": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "snb_mlp_backward": (_i, [_vp, _vp, _vp, _sz, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "snb_mlp_forward_with_solar": (_i, [_vp, _vp, _vp, _sz, _i64, _i64, _vp, _vp, _vp, _i, _vp, _vp]),
+    "snb_mlp_backward_with_solar": (_i, [_vp, _vp, _vp, _sz, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "snb_model_grad_buckets": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "snb_nerf_aux": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "snb_mlp_fp32_workspace_bytes": (_sz, [_vp, _i64]),

@@ -71,6 +71,7 @@ struct snb_model {
   long long bias_off;  // fp32 section (byte offset = packed_bf16_elems*2), element offsets below
   long long bl[8], bfe, bs2, bs4, bho;
   long long wf32, wh1_32, bh1_32;   // fp32 copies of W_f [F,F], of the head first layers' f-columns [hhw,F] and biases [hhw]
+  long long wp32;                   // fp32 W' = W_h1 W_f [hhw,F]: accumulator of the split-K pack product (snb_model_pack)
   long long bias_elems;
   std::vector<snb::PackJob> pack_jobs;
   struct HeadBlock { int row; long long w, b; int kin; };   // hidden blocks of the fused head layer: flat offsets of W / bias
@@ -194,6 +195,8 @@ struct SmallGemm {
   const float* u; long long su; const float* v; long long sv;
   __nv_bfloat16* o16; long long ld16; __nv_bfloat16* o16t; long long ld16t;
   int splits;   // > 1: the K range is split over blockIdx.z and C is accumulated with atomics (C zeroed by the caller; fp32 C only)
+                // 0: chosen by small_gemm so that the grid fills the SMs a few times over (these products are latency-bound:
+                // one 64 x 64 tile per SM leaves every global load exposed)
 };
 
 __global__ void __launch_bounds__(256) small_gemm_kernel(const SmallGemm g) {
@@ -271,7 +274,13 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const SmallGemm g) {
 }
 
 static int small_gemm(SmallGemm g, cudaStream_t st) {
-  if (g.splits < 1 || g.C == nullptr || g.o16 != nullptr || g.o16t != nullptr) g.splits = 1;
+  if (g.C == nullptr || g.o16 != nullptr || g.o16t != nullptr) g.splits = 1;
+  if (g.splits < 1) {
+    const int tiles = ((g.N + 63) / 64) * ((g.M + 63) / 64);
+    int s = (4 * 148 + tiles - 1) / tiles;
+    const int max_s = g.K / 64 > 0 ? g.K / 64 : 1;      // at least four 16-deep k-steps per split
+    g.splits = s < 1 ? 1 : (s > max_s ? max_s : s);
+  }
   dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.splits);
   small_gemm_kernel<<<grid, 256, 0, st>>>(g);
   return launch_status("small_gemm_kernel");
@@ -295,8 +304,54 @@ __global__ void __launch_bounds__(256) small_gemv_kernel(const float* __restrict
   }
 }
 
+// the same product for a matrix stored with m as the unit-stride index (A^T x): lanes run along m, 8 k-groups per block and
+// blockIdx.y split the reduction, y is accumulated with atomics (y zeroed by the caller)
+__global__ void __launch_bounds__(256) small_gemv_t_kernel(const float* __restrict__ A, long long sak, const float* __restrict__ x,
+                                                           long long sx, int M, int K, float* __restrict__ y, long long sy) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, kg = threadIdx.x >> 5;
+  const int m = blockIdx.x * 32 + lane;
+  const int kper = (K + gridDim.y - 1) / gridDim.y;
+  const int kbeg = blockIdx.y * kper, kend = min(K, kbeg + kper);
+  float acc = 0.f;
+  if (m < M)
+    for (int k = kbeg + kg; k < kend; k += 8) acc = fmaf(A[(long long)k * sak + m], x[(long long)k * sx], acc);
+  red[kg][lane] = acc;
+  __syncthreads();
+  if (kg == 0 && m < M) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) acc += red[i][lane];
+    atomicAdd(y + (long long)m * sy, acc);
+  }
+}
+
+// W' (fp32, [rows, F]) -> its bf16 copies: o16[r*ld16 + c] (forward rows) and o16t[c*ld16t + r] (dgrad rows), 32 x 32 tiles
+__global__ void __launch_bounds__(256) wprime_bf16_kernel(const float* __restrict__ W, int rows, int cols, __nv_bfloat16* __restrict__ o16,
+                                                          long long ld16, __nv_bfloat16* __restrict__ o16t, long long ld16t) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    const float v = (r < rows && c < cols) ? W[(long long)r * cols + c] : 0.f;
+    tile[ty + 8 * i][tx] = v;
+    if (r < rows && c < cols) o16[(long long)r * ld16 + c] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (r < rows && c < cols) o16t[(long long)c * ld16t + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+  }
+}
+
 static int small_gemv(const float* A, long long sam, long long sak, const float* x, long long sx, int M, int K, const float* u,
                       float* y, long long sy, __nv_bfloat16* y16, long long sy16, cudaStream_t st) {
+  if (sam == 1 && u == nullptr && y16 == nullptr && y != nullptr) {
+    dim3 grid((M + 31) / 32, K >= 512 ? 8 : (K >= 128 ? 4 : 1));
+    small_gemv_t_kernel<<<grid, 256, 0, st>>>(A, sak, x, sx, M, K, y, sy);
+    return launch_status("small_gemv_t_kernel");
+  }
   small_gemv_kernel<<<(M + 7) / 8, 256, 0, st>>>(A, sam, sak, x, sx, M, K, u, y, sy, y16, sy16);
   return launch_status("small_gemv_kernel");
 }
@@ -413,6 +468,7 @@ static void build_layout(snb_model* m) {
   m->wf32 = take(bc, (long long)F * F);
   m->wh1_32 = take(bc, (long long)hhw * F);
   m->bh1_32 = take(bc, hhw);
+  m->wp32 = take(bc, (long long)hhw * F);
   m->bias_elems = bc;
 
   auto& J = m->pack_jobs;
@@ -653,6 +709,26 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
     w.gscratch = take_b((size_t)m->gscratch_elems * 4);
   }
   w.total = cur;
+  return w;
+}
+
+// The same layout seen from row r on: every per-point member moved by r rows.  A training step keeps the points of the
+// solar-correction pass in rows [P, P + Psc) of ONE workspace (snb_mlp_forward_with_solar): the two passes run their own
+// chained launches over their row ranges, and the weight gradients of the layers both passes share run once over all rows.
+static Workspace shift_rows(const snb_model* m, Workspace w, long long r) {
+  const size_t n = (size_t)r;
+  for (int i = 0; i < 8; ++i) {
+    w.h[i] += n * F * 2;
+    w.sg[i] += n * (F / 8);
+    w.dy[i] += n * F * 2;
+  }
+  w.hh += n * m->hhw * 2;
+  w.dyhh += n * m->hhw * 2;
+  w.sghh += n * (m->hhw / 8);
+  w.s2 += n * FL * 2;  w.s3 += n * FL * 2;  w.dys2 += n * FL * 2;  w.dys3 += n * FL * 2;
+  w.sgs2 += n * (FL / 8);  w.sgs3 += n * (FL / 8);
+  w.dpre += n * 16 * 2;
+  w.hpart += n * 16 * 4;
   return w;
 }
 
@@ -982,9 +1058,10 @@ extern "C" int snb_model_pack(const snb_model* m, const float* params, void* pac
     g.A = f32 + m->wh1_32; g.sam = F; g.sak = 1;
     g.B = params + wf; g.sbk = F; g.sbn = 1;
     g.M = m->hhw; g.N = F; g.K = F;
-    g.o16 = pk + m->wh1; g.ld16 = kh1;
-    g.o16t = pk + m->tf; g.ld16t = ktf;
+    g.C = f32 + m->wp32; g.ldc = F;                       // zeroed with the packed image above
     if (int r = small_gemm(g, st)) return r;
+    wprime_bf16_kernel<<<dim3(F / 32, (m->hhw + 31) / 32), 256, 0, st>>>(f32 + m->wp32, m->hhw, F, pk + m->wh1, kh1, pk + m->tf, ktf);
+    if (int r = launch_status("wprime_bf16_kernel")) return r;
   }
   // bias column (aux column 0 = 1): b' = b_h1 + W_h1 b_f, all hidden blocks in one launch (rows of absent blocks are zero)
   return small_gemv(f32 + m->wh1_32, F, 1, params + bf, 1, m->hhw, F, f32 + m->bh1_32, nullptr, 0, pk + m->wh1 + F, kh1, st);
@@ -994,6 +1071,10 @@ extern "C" size_t snb_mlp_workspace_bytes(const snb_model* m, int64_t n_points, 
   if (!m || n_points <= 0) return 0;
   return layout_workspace(m, n_points, train).total;
 }
+
+static int mlp_forward_rows(const snb_model* m, const void* packed, char* ws, const Workspace& w, long long P, const void* enc,
+                            const void* aux, const float* sky, int rows_per_ray, int head_mask, int train, float* out,
+                            void* stream);
 
 extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
                                int64_t n_points, const void* enc, const void* aux, const float* sky,
@@ -1010,8 +1091,34 @@ extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* wor
   const Workspace w = layout_workspace(m, n_points, train);
   SNB_CHECK_ARG(workspace_bytes >= w.total, SNB_ERR_WORKSPACE, "mlp_forward: workspace %zu < required %zu",
                 workspace_bytes, w.total);
-  const long long P = n_points;
+  return mlp_forward_rows(m, packed, reinterpret_cast<char*>(workspace), w, n_points, enc, aux, sky, rows_per_ray, head_mask,
+                          train, out, stream);
+}
+
+extern "C" int snb_mlp_forward_with_solar(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
+                                          int64_t n_points, int64_t n_solar_points, const void* enc, const void* aux,
+                                          const float* sky, int rows_per_ray, float* out, void* stream) {
+  SNB_CHECK_ARG(m && packed && workspace && enc && aux && out, SNB_ERR_INVALID, "mlp_forward_with_solar: null argument");
+  SNB_CHECK_ARG(n_points > 0 && n_solar_points >= 0 && n_solar_points <= n_points && n_points + n_solar_points < (1ll << 31),
+                SNB_ERR_INVALID, "mlp_forward_with_solar: point counts out of range");
+  SNB_CHECK_ARG(m->kind != SNB_MODEL_NERF || n_solar_points == 0, SNB_ERR_UNSUPPORTED,
+                "mlp_forward_with_solar: NeRF has no sun head - there is no solar-correction pass");
+  SNB_CHECK_ARG((((uintptr_t)workspace | (uintptr_t)packed | (uintptr_t)enc) & 127) == 0, SNB_ERR_INVALID,
+                "mlp_forward_with_solar: workspace/packed/enc must be 128-byte aligned");
+  const Workspace w = layout_workspace(m, n_points + n_solar_points, 1);
+  SNB_CHECK_ARG(workspace_bytes >= w.total, SNB_ERR_WORKSPACE, "mlp_forward_with_solar: workspace %zu < required %zu",
+                workspace_bytes, w.total);
   char* ws = reinterpret_cast<char*>(workspace);
+  if (int r = mlp_forward_rows(m, packed, ws, w, n_points, enc, aux, sky, rows_per_ray, SNB_HEADS_ALL, 1, out, stream)) return r;
+  if (n_solar_points == 0) return 0;
+  const char* enc_s = reinterpret_cast<const char*>(enc) + (size_t)n_points * m->enc_ld * 2;
+  return mlp_forward_rows(m, packed, ws, shift_rows(m, w, n_points), n_solar_points, enc_s, aux, nullptr, rows_per_ray,
+                          SNB_HEADS_SOLAR, 1, out + (size_t)n_points * m->n_out, stream);
+}
+
+static int mlp_forward_rows(const snb_model* m, const void* packed, char* ws, const Workspace& w, long long P, const void* enc,
+                            const void* aux, const float* sky, int rows_per_ray, int head_mask, int train, float* out,
+                            void* stream) {
   const __nv_bfloat16* pk = reinterpret_cast<const __nv_bfloat16*>(packed);
   const float* pb = reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + (size_t)m->packed_bf16_elems * 2);
   auto H = [&](int i) { return (void*)(ws + w.h[i]); };
@@ -1101,6 +1208,10 @@ extern "C" int snb_model_grad_buckets(const snb_model* m, int64_t* lo3, int64_t*
   return 0;
 }
 
+static int mlp_backward_rows(const snb_model* m, const void* packed, char* ws, const Workspace& w, long long P, long long Psc,
+                             const void* enc, const void* aux, const float* out, const float* g_out, int head_mask, float* grads,
+                             float* g_aux, void* const* bucket_events, cudaStream_t st);
+
 extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
                                 int64_t n_points, const void* enc, const void* aux, const float* out,
                                 const float* g_out, int head_mask, float* grads, float* g_aux, void* const* bucket_events,
@@ -1112,35 +1223,68 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
   const Workspace w = layout_workspace(m, n_points, 1);
   SNB_CHECK_ARG(workspace_bytes >= w.total, SNB_ERR_WORKSPACE, "mlp_backward: workspace %zu < required %zu",
                 workspace_bytes, w.total);
+  return mlp_backward_rows(m, packed, reinterpret_cast<char*>(workspace), w, n_points, 0, enc, aux, out, g_out, head_mask, grads,
+                           g_aux, bucket_events, (cudaStream_t)stream);
+}
+
+extern "C" int snb_mlp_backward_with_solar(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
+                                           int64_t n_points, int64_t n_solar_points, const void* enc, const void* aux,
+                                           const float* out, const float* g_out, float* grads, float* g_aux,
+                                           void* const* bucket_events, void* stream) {
+  SNB_CHECK_ARG(m && packed && workspace && enc && aux && out && g_out && grads, SNB_ERR_INVALID,
+                "mlp_backward_with_solar: null argument");
+  SNB_CHECK_ARG(n_points > 0 && n_solar_points >= 0 && n_solar_points <= n_points && n_points + n_solar_points < (1ll << 31),
+                SNB_ERR_INVALID, "mlp_backward_with_solar: point counts out of range");
+  SNB_CHECK_ARG(m->kind != SNB_MODEL_NERF || n_solar_points == 0, SNB_ERR_UNSUPPORTED,
+                "mlp_backward_with_solar: NeRF has no sun head - there is no solar-correction pass");
+  const Workspace w = layout_workspace(m, n_points + n_solar_points, 1);
+  SNB_CHECK_ARG(workspace_bytes >= w.total, SNB_ERR_WORKSPACE, "mlp_backward_with_solar: workspace %zu < required %zu",
+                workspace_bytes, w.total);
+  return mlp_backward_rows(m, packed, reinterpret_cast<char*>(workspace), w, n_points, n_solar_points, enc, aux, out, g_out,
+                           SNB_HEADS_ALL, grads, g_aux, bucket_events, (cudaStream_t)stream);
+}
+
+// P rows of the pass `head_mask`, followed (Psc > 0: head_mask is ALL) by Psc rows of the solar-correction pass
+static int mlp_backward_rows(const snb_model* m, const void* packed, char* ws, const Workspace& w, long long P, long long Psc,
+                             const void* enc, const void* aux, const float* out, const float* g_out, int head_mask, float* grads,
+                             float* g_aux, void* const* bucket_events, cudaStream_t st) {
   const int sms = num_sms();
   if (sms <= 0) return SNB_ERR_NO_DEVICE;
-  cudaStream_t st = (cudaStream_t)stream;
-  const long long P = n_points;
-  char* ws = reinterpret_cast<char*>(workspace);
   const __nv_bfloat16* pk = reinterpret_cast<const __nv_bfloat16*>(packed);
   float* gs = reinterpret_cast<float*>(ws + w.gscratch);
   auto H = [&](int i) { return (void*)(ws + w.h[i]); };
   const int hhw = m->hhw;
   const bool all = head_mask == SNB_HEADS_ALL;
-  const bool solar = head_mask == SNB_HEADS_SOLAR;
   const bool depth = head_mask == SNB_HEADS_DEPTH;
   const bool nerf = m->kind == SNB_MODEL_NERF;
   void* dpre = ws + w.dpre;
+  const Workspace wsc = shift_rows(m, w, P);   // the solar rows' view
+  const long long Pt = P + Psc;                // rows of the layers both passes share
 
   SNB_CUDA(cudaMemsetAsync(gs, 0, (size_t)m->gscratch_elems * 4, st));
-  {
-    long long blocks = (P + 255) / 256;
+  auto head_grad = [&](const Workspace& v, long long n, long long row0, int mask) -> int {
+    long long blocks = (n + 255) / 256;
     if (blocks > sms * 8) blocks = sms * 8;
-    head_grad_kernel<<<(int)blocks, 256, 0, st>>>(out, g_out, P, m->n_out, m->n_classes, m->sem_sigmoid, head_mask, m->beta_s,
-                                                  (__nv_bfloat16*)dpre, gs + m->gbho);
-    if (int r = launch_status("head_grad_kernel")) return r;
-  }
+    head_grad_kernel<<<(int)blocks, 256, 0, st>>>(out + row0 * m->n_out, g_out + row0 * m->n_out, n, m->n_out, m->n_classes,
+                                                  m->sem_sigmoid, mask, m->beta_s, (__nv_bfloat16*)(ws + v.dpre), gs + m->gbho);
+    return launch_status("head_grad_kernel");
+  };
+  if (int r = head_grad(w, P, 0, head_mask)) return r;
+  if (Psc > 0)
+    if (int r = head_grad(wsc, Psc, P, SNB_HEADS_SOLAR)) return r;
   auto DY = [&](int i) { return (void*)(ws + w.dy[i]); };
   Plan p;
   const int r0 = all ? 0 : m->hh_sun, nh = all ? hhw : FL;
   const char* dyhh_r0 = ws + w.dyhh + (size_t)r0 * 2;
   // ---- dgrad: the gradient w.r.t. every pre-activation, from the heads back to trunk layer 0 ---------------
-  {
+  auto dgrad = [&](const Workspace& w, long long P, int head_mask) -> int {
+    const bool all = head_mask == SNB_HEADS_ALL;
+    const bool depth = head_mask == SNB_HEADS_DEPTH;
+    const int r0 = all ? 0 : m->hh_sun, nh = all ? hhw : FL;
+    const char* dyhh_r0 = ws + w.dyhh + (size_t)r0 * 2;
+    void* dpre = ws + w.dpre;
+    auto H = [&](int i) { return (void*)(ws + w.h[i]); };
+    auto DY = [&](int i) { return (void*)(ws + w.dy[i]); };
     // chained (default): one persistent launch; each dY is read back from L2 by the next step of the same SM pair.
     // The SIREN derivative w0 cos(.) is rebuilt in the epilogue from the saved activation and its sign mask.
     ChainPlan cp(P, use_chain(), st);
@@ -1177,13 +1321,17 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
       cp.add(EPI_MUL, F, c, 1, pk + m->tl[i], F, F, DY(i - 1), F, P, 0, H(i - 1), F, SG(i - 1), F / 32, nullptr,
              (i - 1 == 0 && !m->relu) ? 30.0f : 1.0f);
     }
-    if (int r = cp.run()) return r;
-  }
+    return cp.run();
+  };
+  if (int r = dgrad(w, P, head_mask)) return r;
+  if (Psc > 0)
+    if (int r = dgrad(wsc, Psc, SNB_HEADS_SOLAR)) return r;
   // ---- wgrad: every weight gradient is dY^T x (layer input), split-K over the samples -----------------------
-  const long long ldt = (P + 63) & ~63ll;
+  // (the layers both passes share - trunk, sun layers, head outputs - reduce over all Pt rows in one launch each)
+  const long long ldt = (Pt + 63) & ~63ll;
   if (!depth)
     if (int r = transpose_cols(aux, m->aux_ld, m->aux_ld, P, ws + w.auxT, ldt, st)) return r;
-  if (int r = transpose_cols(enc, m->enc_ld, 64, P, ws + w.encT, ldt, st)) return r;
+  if (int r = transpose_cols(enc, m->enc_ld, 64, Pt, ws + w.encT, ldt, st)) return r;
   // the wgrads run heads first, then trunk layers 7..0; after each of the three gradient buckets (snb_model_grad_buckets)
   // its packed gradients are added into `grads` and its event (if any) is recorded: a data-parallel caller starts that
   // bucket's all-reduce on a side stream while the remaining wgrads still run
@@ -1211,7 +1359,7 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
       g.B = G1; g.sbk = F; g.sbn = 1;
       g.M = F; g.N = F; g.K = nh;
       g.C = gs + m->gf; g.ldc = F;
-      g.splits = nh >= 1024 ? 4 : (nh >= 512 ? 2 : 1);     // 64 output tiles only: split the reduction (gf is zeroed)
+      // split reductions (gf and gh1w are zeroed with the gradient scratch)
       if (int r = small_gemm(g, st)) return r;
       if (int r = small_gemv(pbf + m->wh1_32 + (long long)r0 * F, 1, F, sv, gald, F, nh, nullptr, gs + m->gbf, 1, nullptr, 0, st))
         return r;
@@ -1220,13 +1368,13 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     if (bucket_events != nullptr && bucket_events[b] != nullptr) SNB_CUDA(cudaEventRecord((cudaEvent_t)bucket_events[b], st));
     return 0;
   };
-  add_wgrad(p, F, 16, H(7), F, dpre, 16, P, gs + m->ghot, 16, sms);
-  if (!depth && !nerf) add_wgrad(p, FL, 16, ws + w.s3, FL, dpre, 16, P, gs + m->ghot + (long long)F * 16, 16, sms);
+  add_wgrad(p, F, 16, H(7), F, dpre, 16, Pt, gs + m->ghot, 16, sms);
+  if (!depth && !nerf) add_wgrad(p, FL, 16, ws + w.s3, FL, dpre, 16, Pt, gs + m->ghot + (long long)F * 16, 16, sms);
   if (all) add_wgrad(p, hhw, 16, ws + w.hh, hhw, dpre, 16, P, gs + m->ghot + (long long)(F + FL) * 16, 16, sms);
   if (!depth) {
     if (!nerf) {
-      add_wgrad(p, FL, FL, ws + w.dys3, FL, ws + w.s2, FL, P, gs + m->gs4, FL, sms, gs + m->gbs4);
-      add_wgrad(p, FL, FL, ws + w.dys2, FL, ws + w.hh + (size_t)m->hh_sun * 2, hhw, P, gs + m->gs2, FL, sms, gs + m->gbs2);
+      add_wgrad(p, FL, FL, ws + w.dys3, FL, ws + w.s2, FL, Pt, gs + m->gs4, FL, sms, gs + m->gbs4);
+      add_wgrad(p, FL, FL, ws + w.dys2, FL, ws + w.hh + (size_t)m->hh_sun * 2, hhw, Pt, gs + m->gs2, FL, sms, gs + m->gbs2);
     }
     // fused head first layers: weight / bias / per-ray-column gradients
     // ... the bias / per-ray-column gradients dY^T x aux ride the same launch as a 16-column side operand
@@ -1234,6 +1382,12 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
     const WgradSide s_aux = {ws + w.auxT, ldt, gald, gs + m->gh1aux + (long long)r0 * gald, gald, m->aux_ld};
     // G1 = dY_hh^T h7 (against h7, not f: the feats layer is folded; see finish_bucket(0) for dW_h1 / dW_f / db_f)
     add_wgrad(p, nh, F, dyhh_r0, hhw, H(7), F, P, gs + m->gh1 + (long long)r0 * F, F, sms, nullptr, &s_aux);
+    if (Psc > 0) {
+      // the solar rows reach the fused head layer through its sun block only (aux row i belongs to solar row i as well)
+      const WgradSide s_aux_sc = {ws + w.auxT, ldt, gald, gs + m->gh1aux + (long long)m->hh_sun * gald, gald, m->aux_ld};
+      add_wgrad(p, FL, F, ws + wsc.dyhh + (size_t)m->hh_sun * 2, hhw, ws + wsc.h[7], F, Psc,
+                gs + m->gh1 + (long long)m->hh_sun * F, F, sms, nullptr, &s_aux_sc);
+    }
     if (g_aux && m->find("beta_from_xyz.0.weight") < 0) {
       SNB_CUDA(cudaMemsetAsync(g_aux, 0, (size_t)P * 16 * sizeof(float), st));   // no embedding-dependent head in this model
     } else if (all && g_aux) {
@@ -1248,11 +1402,11 @@ extern "C" int snb_mlp_backward(const snb_model* m, const void* packed, void* wo
   if (int r = finish_bucket(0)) return r;
   for (int i = LAYERS - 1; i >= 0; --i) {
     if (i == 0) {
-      add_wgrad(p, F, 64, DY(0), F, enc, m->enc_ld, P, gs + m->gl[0], 64, sms, gs + m->gbl[0]);
+      add_wgrad(p, F, 64, DY(0), F, enc, m->enc_ld, Pt, gs + m->gl[0], 64, sms, gs + m->gbl[0]);
     } else {
       // skip layer: its encoding block dY4^T x enc[:, :64] is a 64-column side operand of the same launch
       const WgradSide s_enc = {ws + w.encT, ldt, 64, gs + m->gl4e, 64, 64};
-      add_wgrad(p, F, F, DY(i), F, H(i - 1), F, P, gs + m->gl[i], F, sms, gs + m->gbl[i], i == 4 ? &s_enc : nullptr);
+      add_wgrad(p, F, F, DY(i), F, H(i - 1), F, Pt, gs + m->gl[i], F, sms, gs + m->gbl[i], i == 4 ? &s_enc : nullptr);
     }
     if (i == 4)
       if (int r = finish_bucket(1)) return r;

@@ -57,8 +57,10 @@ def default_cfgs(kind: str = "semantic", n_samples: int = 64, sc_lambda: float =
 
 
 class _PassBuffers:
-    """Persistent device buffers of one ray batch size for the direct step (K1 outputs, the MLP training workspaces of the
-    main and the solar-correction pass, packed head outputs and their gradients).  ~25 KB per sample and pass."""
+    """Persistent device buffers of one ray batch size for the direct step (K1 outputs, the MLP training workspace, packed
+    head outputs and their gradients).  ~25 KB per sample and pass.  With a solar-correction pass its points are rows
+    [P, 2P) of the SAME enc / workspace / out / g_out buffers (snb_mlp_forward_with_solar): the weight gradients of the layers
+    both passes share then run once over all 2P rows."""
 
     def __init__(self, model, n: int, S: int, dev, want_sc: bool, has_emb: bool, depth_only: bool):
         lib = _lib.load()
@@ -70,19 +72,21 @@ class _PassBuffers:
         self.rays = torch.empty(n, 8, **f32)
         self.extras = torch.empty(n, 4, **f32)
         self.z = torch.empty(n, S, **f32)
-        self.enc = torch.empty(P, model.enc_ld, **bf16)
-        self.enc_sc = torch.empty(P, model.enc_ld, **bf16) if want_sc else None
+        rows = 2 * P if want_sc else P
+        self.enc_all = torch.empty(rows, model.enc_ld, **bf16)
+        self.enc = self.enc_all[:P]
+        self.enc_sc = self.enc_all[P:] if want_sc else None
         self.aux = torch.empty(P, 16, **bf16)
         self.aux32 = torch.empty(P, 32, **bf16) if nerf else None
         self.sky = None if (nerf or depth_only) else torch.empty(n, 3, **f32)
-        nbytes = lib.snb_mlp_workspace_bytes(model._h, P, 1)
+        nbytes = lib.snb_mlp_workspace_bytes(model._h, rows, 1)
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        self.ws_sc = torch.empty(nbytes, dtype=torch.uint8, device=dev) if want_sc else None
         n_out = model.n_out_kernel
-        self.out = torch.empty(P, n_out, **f32)
-        self.g_out = torch.empty(P, n_out, **f32)
-        self.out_sc = torch.empty(P, n_out, **f32) if want_sc else None
-        self.g_out_sc = torch.empty(P, n_out, **f32) if want_sc else None
+        self.out_all = torch.empty(rows, n_out, **f32)
+        self.g_out_all = torch.empty(rows, n_out, **f32)
+        self.out, self.g_out = self.out_all[:P], self.g_out_all[:P]
+        self.out_sc = self.out_all[P:] if want_sc else None
+        self.g_out_sc = self.g_out_all[P:] if want_sc else None
         self.g_aux = torch.empty(P, 16, **f32) if (has_emb and not depth_only) else None
         # targets (static addresses, so the step can be replayed as a CUDA graph)
         self.rgbs = torch.empty(n, 3, **f32)
@@ -152,9 +156,13 @@ class Trainer:
         # fused_loss: compositing + the loss modules + their backward in one kernel per pass; False runs
         # render_rays() + the reference-shaped loss modules (what a Lightning pipeline does)
         self.fused_loss = fused_loss
-        # (the direct step hands K1 one embedding table; with the second table of use_separate_tj_for_semantic the step runs
-        # through render_loss under autograd, which concatenates the two)
-        self.direct = direct and fused_loss and "t_s" not in self.models
+        self.direct = direct and fused_loss
+        if emb_s is not None:
+            # use_separate_tj_for_semantic: K1 takes the two tables side by side as one (vocab, 2 tau) table (renderer.py
+            # _embedding); the direct step keeps that table and its gradient in two small persistent buffers
+            vocab, tau = emb.weight.shape
+            self._ew2 = torch.empty(vocab, 2 * tau, dtype=torch.float32, device=self.device)
+            self._g_ew2 = torch.zeros(vocab, 2 * tau, dtype=torch.float32, device=self.device)
         self.use_graph = bool(graph) and self.direct and world == 1
         # micro_batch: the direct step runs batches larger than this many rays as several forward / backward passes that
         # accumulate into the one gradient buffer before the single optimiser step (the saved activations cost ~25 KB per
@@ -404,6 +412,12 @@ class Trainer:
         Cn = model.semantic_n_classes
         n_out = model.n_out_kernel
         ew = emb.weight.detach() if emb is not None else None
+        emb_s = self.models.get("t_s")
+        if emb_s is not None:
+            if first:
+                torch.cat([ew, emb_s.weight.detach()], 1, out=self._ew2)
+                self._g_ew2.zero_()
+            ew = self._ew2
         vocab, tau = (ew.shape if ew is not None else (0, 0))
         if nerf:
             sw = (None, None, None, None)
@@ -413,6 +427,8 @@ class Trainer:
             hidden = sw[0].shape[0]
         gflat = self.gbuf[EMB_PAD:]
         g_emb = self.gbuf[:self.n_emb] if emb is not None else None
+        if emb_s is not None:
+            g_emb = self._g_ew2
         ts = t_steps(S, self.device)
         if first:
             self._terms.zero_()
@@ -459,9 +475,11 @@ class Trainer:
                       "snb_label_counts")
                 if self.world > 1:   # global masked-mean denominators; overlaps the forward passes
                     work = torch.distributed.all_reduce(counts, async_op=True)
-        forward(b, b.ws, b.enc, b.sky, HEADS_ALL, b.out)
-        if sc:
-            forward(b, b.ws_sc, b.enc_sc, None, HEADS_SOLAR, b.out_sc)
+        if sc:   # main rows [0, P) + solar rows [P, 2P) of one workspace
+            check(lib.snb_mlp_forward_with_solar(model._h, ptr(packed), ptr(b.ws), b.ws.numel(), b.P, b.P, ptr(b.enc_all),
+                                                 ptr(b.aux), ptr(b.sky), S, ptr(b.out_all), st), "snb_mlp_forward_with_solar")
+        else:
+            forward(b, b.ws, b.enc, b.sky, HEADS_ALL, b.out)
         if work is not None:
             work.wait()
         inv_n = 1.0 / max(global_rays, 1)
@@ -502,15 +520,21 @@ class Trainer:
         if not nerf:
             check(lib.snb_ray_param_backward(model._h, ptr(model.flat.detach()), ptr(b.extras), ptr(b.sky), ptr(b.g_out), None,
                                              b.n, S, n_out, 0, 1, ptr(gflat), None, st), "snb_ray_param_backward")
-        if sc:
-            backward(b, b.ws_sc, b.enc_sc, b.out_sc, b.g_out_sc, HEADS_SOLAR, None, None)
         if self.world > 1 and last:
             ev_arr = (C.c_void_p * 3)(*[e.cuda_event for e in self._events])
-        backward(b, b.ws, b.enc, b.out, b.g_out, HEADS_ALL, b.g_aux, ev_arr)
+        if sc:   # both passes' dgrad chains, then one weight-gradient GEMM per shared layer over all 2P rows
+            check(lib.snb_mlp_backward_with_solar(model._h, ptr(packed), ptr(b.ws), b.ws.numel(), b.P, b.P, ptr(b.enc_all),
+                                                  ptr(b.aux), ptr(b.out_all), ptr(b.g_out_all), ptr(gflat), ptr(b.g_aux),
+                                                  ev_arr, st), "snb_mlp_backward_with_solar")
+        else:
+            backward(b, b.ws, b.enc, b.out, b.g_out, HEADS_ALL, b.g_aux, ev_arr)
         if b.g_aux is not None:   # embedding gradient: per-ray sums of the aux-column gradients, scattered by ts
             check(lib.snb_ray_param_backward(model._h, ptr(model.flat.detach()), ptr(b.extras), None, None, ptr(b.g_aux), b.n, S,
                                              n_out, tau, vocab, ptr(gflat), ptr(g_emb), st), "snb_ray_param_backward")
-        # loss value: the terms' sum (+ the constant 3/2 of the log-beta term, baseline/components/loss.py:26)
+        if last and emb_s is not None:   # split the gradient of the side-by-side table back into the two embeddings
+            h, t4 = EMB_PAD // 2, tau // 2
+            self.gbuf[:self.n_emb].view(vocab, t4).add_(self._g_ew2[:, :t4])
+            self.gbuf[h:h + self.n_emb].view(vocab, t4).add_(self._g_ew2[:, t4:])
         if last:
             # loss value: the terms' sum (+ the constant 3/2 of the log-beta term, baseline/components/loss.py:26); data
             # parallel, the per-rank values are shares that add up to the global-batch loss

@@ -219,6 +219,65 @@ def test_chained_mlp_equals_per_layer_mlp(kind, C, P):
     assert _cos(res[1][2], res[0][2]) >= 0.999999
 
 
+@pytest.mark.parametrize("kind,C,n,S", [("semantic", 6, 333, 64), ("satnerf", 0, 512, 16), ("semantic", 4, 77, 6), ("snerf", 0, 200, 32)])
+def test_solar_rows_in_one_workspace_equal_two_passes(kind, C, n, S):
+    """snb_mlp_forward_with_solar / snb_mlp_backward_with_solar (main pass rows [0, P), solar-correction pass rows [P, 2P) of
+    one workspace; the weight gradients of the shared layers run once over all rows) against snb_mlp_forward /
+    snb_mlp_backward called once per pass: the forward outputs are bit-identical, the parameter gradients agree up to the
+    fp32 split-K accumulation order, the per-point embedding gradients are bit-identical (main pass only).  P = n S is
+    ragged in three of the cases: the reduction blocks of the merged launches straddle the boundary between the passes."""
+    import ctypes as C_
+    from semnerf_b200.autograd import encode_rays, HEADS_ALL, HEADS_SOLAR
+    from semnerf_b200._lib import ptr, check
+    lib = _lib_or_fail()
+    spec, params, emb, cfgs, model, t = _model(kind, C, seed=3, S=S)
+    rays, extras = O.synthetic_rays(n, seed=11)
+    u = torch.rand(n, S, generator=torch.Generator().manual_seed(2)).to(DEV)
+    has_t = kind != "snerf"
+    z, enc, enc_sc, aux, sky = encode_rays(model, t.weight if has_t else None, rays.to(DEV), extras.to(DEV), S, u=u, want_sc=True)
+    P, n_out = n * S, model.n_out_kernel
+    packed = model.packed()
+    g = torch.Generator().manual_seed(7)
+    g_main = torch.randn(P, n_out, generator=g).to(DEV)
+    g_sol = torch.zeros(P, n_out, device=DEV)
+    g_sol[:, 3:5] = torch.randn(P, 2, generator=g).to(DEV)          # the solar pass produces sigma and sun only
+    st = None
+    nb = lib.snb_mlp_workspace_bytes(model._h, P, 1)
+    ws_a, ws_b = (torch.empty(nb, dtype=torch.uint8, device=DEV) for _ in range(2))
+    out_a, out_b = (torch.empty(P, n_out, device=DEV) for _ in range(2))
+    check(lib.snb_mlp_forward(model._h, ptr(packed), ptr(ws_a), nb, P, ptr(enc), ptr(aux), ptr(sky), S, HEADS_ALL, 1, ptr(out_a), st), "fwd")
+    check(lib.snb_mlp_forward(model._h, ptr(packed), ptr(ws_b), nb, P, ptr(enc_sc), ptr(aux), None, S, HEADS_SOLAR, 1, ptr(out_b), st), "fwd")
+    grads2 = torch.zeros_like(model.flat.detach())
+    g_aux2 = torch.zeros(P, 16, device=DEV)
+    check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws_b), nb, P, ptr(enc_sc), ptr(aux), ptr(out_b), ptr(g_sol), HEADS_SOLAR,
+                               ptr(grads2), None, None, st), "bwd")
+    check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws_a), nb, P, ptr(enc), ptr(aux), ptr(out_a), ptr(g_main), HEADS_ALL,
+                               ptr(grads2), ptr(g_aux2), None, st), "bwd")
+    # the same two passes as rows of one workspace
+    nb2 = lib.snb_mlp_workspace_bytes(model._h, 2 * P, 1)
+    ws = torch.empty(nb2, dtype=torch.uint8, device=DEV)
+    enc_all = torch.cat([enc, enc_sc], 0).contiguous()
+    out_all = torch.empty(2 * P, n_out, device=DEV)
+    check(lib.snb_mlp_forward_with_solar(model._h, ptr(packed), ptr(ws), nb2, P, P, ptr(enc_all), ptr(aux), ptr(sky), S,
+                                         ptr(out_all), st), "fwd2")
+    assert torch.equal(out_all[:P], out_a) and torch.equal(out_all[P:], out_b)
+    grads1 = torch.zeros_like(grads2)
+    g_aux1 = torch.zeros(P, 16, device=DEV)
+    g_all = torch.cat([g_main, g_sol], 0).contiguous()
+    check(lib.snb_mlp_backward_with_solar(model._h, ptr(packed), ptr(ws), nb2, P, P, ptr(enc_all), ptr(aux), ptr(out_all),
+                                          ptr(g_all), ptr(grads1), ptr(g_aux1), None, st), "bwd2")
+    torch.cuda.synchronize()
+    a, b = grads1.double(), grads2.double()
+    assert float(b.abs().max()) > 0
+    assert (a - b).abs().max() <= 1e-3 * b.abs().max() and _cos(a, b) >= 0.999999
+    assert torch.equal(g_aux1, g_aux2)
+    # n_solar_points = 0 is the plain main pass; more solar rows than main rows are refused
+    check(lib.snb_mlp_forward_with_solar(model._h, ptr(packed), ptr(ws), nb2, P, 0, ptr(enc), ptr(aux), ptr(sky), S, ptr(out_all), st), "fwd0")
+    assert torch.equal(out_all[:P], out_a)
+    assert lib.snb_mlp_forward_with_solar(model._h, ptr(packed), ptr(ws), nb2, P, P + 1, ptr(enc_all), ptr(aux), ptr(sky), S,
+                                          ptr(out_all), st) != 0
+
+
 # ---------------------------------------------------------------------------------------------------------
 # fp32 verification mode (snb_mlp_forward_fp32): the parity contract's "fp32 mode" - rgb / depth within 1e-3 abs of
 # the reference's fp32 path for ANY weights (the trained-like case included), here held to 2e-5
@@ -533,8 +592,9 @@ def test_class_count_and_sample_count_limits(C, S):
 def test_separate_semantic_embedding_gradients_and_training():
     """`use_separate_tj_for_semantic` together with `use_tj_for_s` and `use_separate_beta_for_s` (rs_semantic.py:297-303,330-338):
     the semantic head and the semantic uncertainty head read the second embedding models["t_s"].  render_rays values, every
-    parameter gradient and the gradients of BOTH embedding tables against the oracle; then a few trainer steps (the trainer
-    keeps the second table next to the first in its flat buffer and runs this configuration through render_loss)."""
+    parameter gradient and the gradients of BOTH embedding tables against the oracle; then trainer steps (the trainer
+    keeps the second table next to the first in its flat buffer): the direct step, its CUDA-graph replay and the
+    render_loss-under-autograd step take the same first step and all train."""
     from semnerf_b200 import synth
     from semnerf_b200.renderer import RSSemanticB200Rendering
     from semnerf_b200.trainer import Trainer, default_cfgs
@@ -585,12 +645,28 @@ def test_separate_semantic_embedding_gradients_and_training():
     # trainer
     tcfg = default_cfgs("semantic", n_samples=16, sc_lambda=0.05, use_tj_for_s=True, use_separate_beta_for_s=True,
                         use_separate_tj_for_semantic=True, use_beta_for_s=True)
-    tr = Trainer(tcfg, "semantic", C, device=DEV, car_index=4, seed=0)
-    assert "t_s" in tr.models and not tr.direct
     rr, ee = synth.make_rays(1024, seed=0)
     rgbs, labels, _ = synth.make_targets(rr, C, seed=0)
     batch = {"rays": rr.to(DEV), "extras": ee.to(DEV), "rgbs": rgbs.to(DEV), "semantic": labels.to(DEV)}
-    ts0 = tr.models["t_s"].weight.detach().clone()
-    losses = [tr.training_step(batch, epoch=3).item() for _ in range(12)]
-    assert all(l == l for l in losses) and losses[-1] < losses[0]
-    assert not torch.equal(ts0, tr.models["t_s"].weight.detach())      # the optimiser steps the second table too
+    first = {}
+    for mode, kw in (("direct", dict(direct=True)), ("graph", dict(direct=True, graph=True)), ("autograd", dict(direct=False)),
+                     ("micro", dict(direct=True, micro_batch=256))):
+        tr = Trainer(tcfg, "semantic", C, device=DEV, car_index=4, seed=0, **kw)
+        assert "t_s" in tr.models and tr.direct == (mode != "autograd")
+        ts0 = tr.models["t_s"].weight.detach().clone()
+        losses = [tr.training_step(batch, epoch=3).item()]
+        g = tr.gbuf.detach().clone()      # [t | t_s | model] gradients of the first step
+        first[mode] = (losses[0], g[:256], g[256:512], g[512:])
+        if mode != "micro":
+            losses += [tr.training_step(batch, epoch=3).item() for _ in range(11)]
+            assert all(l == l for l in losses) and losses[-1] < losses[0], mode
+        assert not torch.equal(ts0, tr.models["t_s"].weight.detach()), mode   # the optimiser steps the second table too
+    # same seed, same first step: loss values agree (micro-batches draw other samples: statistically close only)
+    for mode in ("graph", "autograd"):
+        assert abs(first[mode][0] - first["direct"][0]) <= 2e-5 * max(1.0, abs(first["direct"][0])), mode
+        for i, name in ((1, "t"), (2, "t_s"), (3, "model")):
+            assert float(first["direct"][i].abs().max()) > 0, name
+            assert _cos(first[mode][i], first["direct"][i]) >= 0.9999, (mode, name)
+    assert abs(first["micro"][0] - first["direct"][0]) <= 0.05 * abs(first["direct"][0])
+    for i in (1, 2, 3):
+        assert _cos(first["micro"][i], first["direct"][i]) >= 0.9
