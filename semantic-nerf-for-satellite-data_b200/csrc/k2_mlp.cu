@@ -34,6 +34,7 @@ namespace snb {
 
 constexpr int F = 512;    // fc_units (configs/pipelines/*.toml: fc_units = 512)
 constexpr int FL = 256;   // feat_last = fc_units / 2 (fc_use_full_features = false)
+constexpr int PACK_SPLITS = 4;   // K-splits of the folded-layer product W' = W_h1 W_f at pack time
 constexpr int LAYERS = 8; // fc_layers, skip at layer 4
 
 struct TensorInfo {
@@ -71,7 +72,7 @@ struct snb_model {
   long long bias_off;  // fp32 section (byte offset = packed_bf16_elems*2), element offsets below
   long long bl[8], bfe, bs2, bs4, bho;
   long long wf32, wh1_32, bh1_32;   // fp32 copies of W_f [F,F], of the head first layers' f-columns [hhw,F] and biases [hhw]
-  long long wp32;                   // fp32 W' = W_h1 W_f [hhw,F]: accumulator of the split-K pack product (snb_model_pack)
+  long long wp32;                   // fp32 W' = W_h1 W_f: PACK_SPLITS partial products [hhw,F] of the split-K pack product
   long long bias_elems;
   std::vector<snb::PackJob> pack_jobs;
   struct HeadBlock { int row; long long w, b; int kin; };   // hidden blocks of the fused head layer: flat offsets of W / bias
@@ -197,6 +198,7 @@ struct SmallGemm {
   int splits;   // > 1: the K range is split over blockIdx.z and C is accumulated with atomics (C zeroed by the caller; fp32 C only)
                 // 0: chosen by small_gemm so that the grid fills the SMs a few times over (these products are latency-bound:
                 // one 64 x 64 tile per SM leaves every global load exposed)
+  long long slice;   // != 0: split z STORES its partial product to C + z * slice instead (deterministic; the reader sums them)
 };
 
 __global__ void __launch_bounds__(256) small_gemm_kernel(const SmallGemm g) {
@@ -264,7 +266,8 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(const SmallGemm g) {
       float c = acc[i][j];
       if (g.u != nullptr && blockIdx.z == 0) c = fmaf(g.u[(long long)m * g.su], g.v ? g.v[(long long)n * g.sv] : 1.0f, c);
       if (g.C != nullptr) {
-        if (g.splits > 1) atomicAdd(g.C + (long long)m * g.ldc + n, c);
+        if (g.slice != 0) g.C[(long long)blockIdx.z * g.slice + (long long)m * g.ldc + n] = c;
+        else if (g.splits > 1) atomicAdd(g.C + (long long)m * g.ldc + n, c);
         else g.C[(long long)m * g.ldc + n] = c;
       }
       if (g.o16 != nullptr) g.o16[(long long)m * g.ld16 + n] = __float2bfloat16_rn(c);
@@ -325,15 +328,20 @@ __global__ void __launch_bounds__(256) small_gemv_t_kernel(const float* __restri
   }
 }
 
-// W' (fp32, [rows, F]) -> its bf16 copies: o16[r*ld16 + c] (forward rows) and o16t[c*ld16t + r] (dgrad rows), 32 x 32 tiles
-__global__ void __launch_bounds__(256) wprime_bf16_kernel(const float* __restrict__ W, int rows, int cols, __nv_bfloat16* __restrict__ o16,
-                                                          long long ld16, __nv_bfloat16* __restrict__ o16t, long long ld16t) {
+// W' (fp32, [rows, F], the sum of `slices` partial products `slice` floats apart, added in a fixed order: the packed image
+// is a deterministic function of the parameters) -> its bf16 copies: o16[r*ld16 + c] (forward rows) and o16t[c*ld16t + r]
+// (dgrad rows), 32 x 32 tiles
+__global__ void __launch_bounds__(256) wprime_bf16_kernel(const float* __restrict__ W, int slices, long long slice, int rows, int cols,
+                                                          __nv_bfloat16* __restrict__ o16, long long ld16,
+                                                          __nv_bfloat16* __restrict__ o16t, long long ld16t) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + ty + 8 * i, c = c0 + tx;
-    const float v = (r < rows && c < cols) ? W[(long long)r * cols + c] : 0.f;
+    float v = 0.f;
+    if (r < rows && c < cols)
+      for (int z = 0; z < slices; ++z) v += W[(long long)z * slice + (long long)r * cols + c];
     tile[ty + 8 * i][tx] = v;
     if (r < rows && c < cols) o16[(long long)r * ld16 + c] = __float2bfloat16_rn(v);
   }
@@ -468,7 +476,7 @@ static void build_layout(snb_model* m) {
   m->wf32 = take(bc, (long long)F * F);
   m->wh1_32 = take(bc, (long long)hhw * F);
   m->bh1_32 = take(bc, hhw);
-  m->wp32 = take(bc, (long long)hhw * F);
+  m->wp32 = take(bc, (long long)PACK_SPLITS * hhw * F);
   m->bias_elems = bc;
 
   auto& J = m->pack_jobs;
@@ -1058,9 +1066,11 @@ extern "C" int snb_model_pack(const snb_model* m, const float* params, void* pac
     g.A = f32 + m->wh1_32; g.sam = F; g.sak = 1;
     g.B = params + wf; g.sbk = F; g.sbn = 1;
     g.M = m->hhw; g.N = F; g.K = F;
-    g.C = f32 + m->wp32; g.ldc = F;                       // zeroed with the packed image above
+    g.C = f32 + m->wp32; g.ldc = F;
+    g.splits = PACK_SPLITS; g.slice = (long long)m->hhw * F;   // partial products side by side, summed in order below
     if (int r = small_gemm(g, st)) return r;
-    wprime_bf16_kernel<<<dim3(F / 32, (m->hhw + 31) / 32), 256, 0, st>>>(f32 + m->wp32, m->hhw, F, pk + m->wh1, kh1, pk + m->tf, ktf);
+    wprime_bf16_kernel<<<dim3(F / 32, (m->hhw + 31) / 32), 256, 0, st>>>(f32 + m->wp32, PACK_SPLITS, g.slice, m->hhw, F,
+                                                                        pk + m->wh1, kh1, pk + m->tf, ktf);
     if (int r = launch_status("wprime_bf16_kernel")) return r;
   }
   // bias column (aux column 0 = 1): b' = b_h1 + W_h1 b_f, all hidden blocks in one launch (rows of absent blocks are zero)

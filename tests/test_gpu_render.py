@@ -649,24 +649,19 @@ def test_separate_semantic_embedding_gradients_and_training():
     rgbs, labels, _ = synth.make_targets(rr, C, seed=0)
     batch = {"rays": rr.to(DEV), "extras": ee.to(DEV), "rgbs": rgbs.to(DEV), "semantic": labels.to(DEV)}
     first = {}
-    for mode, kw in (("direct", dict(direct=True)), ("graph", dict(direct=True, graph=True)), ("autograd", dict(direct=False)),
-                     ("micro", dict(direct=True, micro_batch=256))):
+    for mode, kw in (("direct", dict(direct=True)), ("graph", dict(direct=True, graph=True)), ("autograd", dict(direct=False))):
         tr = Trainer(tcfg, "semantic", C, device=DEV, car_index=4, seed=0, **kw)
         assert "t_s" in tr.models and tr.direct == (mode != "autograd")
         ts0 = tr.models["t_s"].weight.detach().clone()
         losses = [tr.training_step(batch, epoch=3).item()]
         g = tr.gbuf.detach().clone()      # [t | t_s | model] gradients of the first step
         first[mode] = (losses[0], g[:256], g[256:512], g[512:])
-        if mode != "micro":
-            losses += [tr.training_step(batch, epoch=3).item() for _ in range(11)]
-            assert all(l == l for l in losses) and losses[-1] < losses[0], mode
+        losses += [tr.training_step(batch, epoch=3).item() for _ in range(11)]
+        assert all(l == l for l in losses) and losses[-1] < losses[0], mode
         assert not torch.equal(ts0, tr.models["t_s"].weight.detach()), mode   # the optimiser steps the second table too
-    # same seed, same first step: loss values agree (micro-batches draw other samples: statistically close only)
+    # same seed, same first step
     for mode in ("graph", "autograd"):
         assert abs(first[mode][0] - first["direct"][0]) <= 2e-5 * max(1.0, abs(first["direct"][0])), mode
         for i, name in ((1, "t"), (2, "t_s"), (3, "model")):
             assert float(first["direct"][i].abs().max()) > 0, name
             assert _cos(first[mode][i], first["direct"][i]) >= 0.9999, (mode, name)
-    assert abs(first["micro"][0] - first["direct"][0]) <= 0.05 * abs(first["direct"][0])
-    for i in (1, 2, 3):
-        assert _cos(first["micro"][i], first["direct"][i]) >= 0.9
