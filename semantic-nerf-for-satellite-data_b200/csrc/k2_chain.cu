@@ -31,36 +31,68 @@ struct Cursor {   // position in this SM pair's tile sequence: group, layer, slo
 };
 
 struct Seq {
-  int n_my;       // row blocks this pair owns: pair, pair + n_pairs, ...
-  int n_layers;
-  // The blocks are carried through the layers in groups of up to CHAIN_SLOTS interleaved slots.  The groups are BALANCED
-  // (28 blocks = 8 x 3 + 2 x 2, 4 blocks = 2 + 2, never ... + 1): a single-slot group has nothing to interleave with, so
-  // every layer of it would wait for its own store -> load round trip through L2.
-  int groups, base, rem;
-  __device__ __forceinline__ void init(int n_my_, int n_layers_) {
-    n_my = n_my_;
-    n_layers = n_layers_;
-    groups = (n_my + CHAIN_SLOTS - 1) / CHAIN_SLOTS;
-    base = groups > 0 ? n_my / groups : 0;
-    rem = groups > 0 ? n_my - base * groups : 0;
+  // Per pass p: this pair owns the row blocks pe, pe + n_pairs, ... (pe = the pair index rotated by the pass's shift).
+  // The blocks are carried through the pass's layers in groups of up to CHAIN_SLOTS interleaved slots.  The groups are
+  // BALANCED (28 blocks = 8 x 3 + 2 x 2, 4 blocks = 2 + 2, never ... + 1): a single-slot group has nothing to interleave
+  // with, so every layer of it would wait for its own store -> load round trip through L2.
+  // Groups are numbered through the passes: [0, g0) belong to pass 0, [g0, groups) to pass 1.
+  int g0, groups;
+  int base[2], rem[2], pe[2], l0[2], l1[2], n_pairs;
+  __device__ __forceinline__ void init(const ChainArgs& a, int pair, int n_pairs_) {
+    n_pairs = n_pairs_;
+    int ng[2] = {0, 0};
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      base[p] = rem[p] = pe[p] = l0[p] = l1[p] = 0;
+      if (p >= a.n_passes) continue;
+      const ChainPass& ps = a.pass[p];
+      pe[p] = (pair + n_pairs - ps.shift % n_pairs) % n_pairs;
+      const int n_my = pe[p] < ps.n_blocks ? (ps.n_blocks - pe[p] + n_pairs - 1) / n_pairs : 0;
+      ng[p] = (n_my + CHAIN_SLOTS - 1) / CHAIN_SLOTS;
+      base[p] = ng[p] > 0 ? n_my / ng[p] : 0;
+      rem[p] = ng[p] > 0 ? n_my - base[p] * ng[p] : 0;
+      l0[p] = ps.layer0;
+      l1[p] = ps.layer0 + ps.n_layers;
+    }
+    g0 = ng[0];
+    groups = ng[0] + ng[1];
   }
-  __device__ __forceinline__ int nslots(int g) const { return base + (g < rem ? 1 : 0); }
-  __device__ __forceinline__ int first(int g) const { return g * base + (g < rem ? g : rem); }   // first own block of group g
+  __device__ __forceinline__ int pass_of(int g) const { return g >= g0 ? 1 : 0; }
+  // (selects, not indexed loads: the members stay in registers)
+  __device__ __forceinline__ int nslots(int g) const {
+    const bool p = g >= g0;
+    const int gp = p ? g - g0 : g, b = p ? base[1] : base[0], r = p ? rem[1] : rem[0];
+    return b + (gp < r ? 1 : 0);
+  }
+  // row block of slot s of group g
+  __device__ __forceinline__ int block(int g, int s) const {
+    const bool p = g >= g0;
+    const int gp = p ? g - g0 : g, b = p ? base[1] : base[0], r = p ? rem[1] : rem[0];
+    const int first = gp * b + (gp < r ? gp : r);   // first own block of the group
+    return (first + s) * n_pairs + (p ? pe[1] : pe[0]);
+  }
+  __device__ __forceinline__ int layer_begin(int g) const { return g >= g0 ? l0[1] : l0[0]; }
+  __device__ __forceinline__ int layer_end(int g) const { return g >= g0 ? l1[1] : l1[0]; }
 };
 
 __device__ __forceinline__ void cur_init(Cursor& c, const Seq& q) {
-  c.g = c.l = c.s = c.j = 0;
-  c.done = q.n_my <= 0;
+  c.g = c.s = c.j = 0;
+  c.done = q.groups <= 0;
+  c.l = c.done ? 0 : q.layer_begin(0);
 }
 __device__ __forceinline__ void cur_next(Cursor& c, const Seq& q, const ChainArgs& a) {
   if (++c.j < a.layers[c.l].n_tiles) return;
   c.j = 0;
   if (++c.s < q.nslots(c.g)) return;
   c.s = 0;
-  if (++c.l < q.n_layers) return;
-  c.l = 0;
+  if (++c.l < q.layer_end(c.g)) return;
   ++c.g;
-  if (c.g >= q.groups) c.done = true;
+  if (c.g >= q.groups) {
+    c.done = true;
+    c.l = 0;
+  } else {
+    c.l = q.layer_begin(c.g);
+  }
 }
 
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -174,7 +206,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
   const int pair = (int)(blockIdx.x >> 1);
   const int n_pairs = (int)(gridDim.x >> 1);
   Seq seq;
-  seq.init(pair < args.n_blocks ? (args.n_blocks - pair + n_pairs - 1) / n_pairs : 0, args.n_layers);
+  seq.init(args, pair, n_pairs);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 8; ++s) {
@@ -210,19 +242,24 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
   if (warp == 0) {
     // ===================================== TMA producer: operand A ===========================
     uint32_t stage = 0, phase = 0, rbits = 0;
+    uint32_t owed = 0;   // bit s: the latest tile-set of slot s was stored through TMA and its phase of ready[s] is not consumed yet
     Cursor c;
     for (cur_init(c, seq); !c.done; cur_next(c, seq, args)) {
       const ChainLayer& ly = args.layers[c.l];
-      if (c.j == 0 && !(c.g == 0 && c.l == 0) &&
-          args.layers[c.l > 0 ? c.l - 1 : seq.n_layers - 1].epi != EPI_HEADOUT) {
-        // the previous tile-set of this slot (the layer that produced this layer's input rows) has been
-        // stored completely; one barrier phase per stored tile-set keeps producer and store warp in lock step.
-        // (A head-output tile-set stores nothing through TMA and feeds no later layer: no phase for it.)
-        mbar_wait(&ready[c.s], (rbits >> c.s) & 1u);
-        rbits ^= 1u << c.s;
-        fence_proxy_async_all();
+      if (c.j == 0) {
+        if ((owed >> c.s) & 1u) {
+          // the previous tile-set of this slot (the layer that produced this layer's input rows, or the last layer of the
+          // slot's previous block) has been stored completely; one barrier phase per stored tile-set keeps producer and
+          // store warp in lock step.  (A head-output tile-set stores nothing through TMA and feeds no later layer: no
+          // phase for it.)
+          mbar_wait(&ready[c.s], (rbits >> c.s) & 1u);
+          rbits ^= 1u << c.s;
+          fence_proxy_async_all();
+        }
+        if (ly.epi != EPI_HEADOUT) owed |= 1u << c.s;
+        else owed &= ~(1u << c.s);
       }
-      const int blk = (seq.first(c.g) + c.s) * n_pairs + pair;
+      const int blk = seq.block(c.g, c.s);
       const int row_real = blk * 256 + (int)cta_rank * GEMM_BLOCK_M;
       const int row_scr = (pair * CHAIN_SLOTS + c.s) * 256 + (int)cta_rank * GEMM_BLOCK_M;
       const int kb_total = ly.kb_total;
@@ -343,7 +380,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
     auto arm = [&](const Cursor& t, int g, int ci, uint32_t par) {   // elected lane only; par = parity of the tile's index
       const ChainLayer& tl = args.layers[t.l];
       uint64_t* bar = &rdy[g * 2 + ci];
-      const int trow = ((seq.first(t.g) + t.s) * n_pairs + pair) * 256 + (int)cta_rank * GEMM_BLOCK_M;
+      const int trow = seq.block(t.g, t.s) * 256 + (int)cta_rank * GEMM_BLOCK_M;
 #ifdef SNB_EXPERIMENTS
       if (tl.epi == EPI_MUL && (args.exp & 16)) {
         mbar_arrive(bar);
@@ -364,7 +401,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       const ChainLayer& tl = args.layers[t.l];
       uint64_t* bar = &mrdy[par & 1];
       if (tl.epi == EPI_MUL && tl.mul_siren == 1) {
-        const int trow = ((seq.first(t.g) + t.s) * n_pairs + pair) * 256 + (int)cta_rank * GEMM_BLOCK_M;
+        const int trow = seq.block(t.g, t.s) * 256 + (int)cta_rank * GEMM_BLOCK_M;
         mbar_expect_tx(bar, 4096);
         tma_load_2d_hint(mask_smem + (par & 1) * 1024, &args.maps[t.l].tmMask, bar, t.j * 8, trow, L2_EVICT_FIRST);
       } else {
@@ -394,7 +431,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       if (ly.epi != EPI_HEADOUT) {
         const Cursor nc = next_chunked(c);
         const Cursor nc2 = nc.done ? nc : next_chunked(nc);
-        const int blk = (seq.first(c.g) + c.s) * n_pairs + pair;
+        const int blk = seq.block(c.g, c.s);
         const int m_out = ly.o_scratch ? (pair * CHAIN_SLOTS + c.s) * 256 + (int)cta_rank * GEMM_BLOCK_M
                                        : blk * 256 + (int)cta_rank * GEMM_BLOCK_M;
 #pragma unroll 1
@@ -491,10 +528,11 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
       const bool siren = ly.mul_siren == 1;
       const bool relu_bwd = ly.mul_siren == 2;
       const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
-      const int blk = (seq.first(c.g) + c.s) * n_pairs + pair;
+      const int blk = seq.block(c.g, c.s);
+      const ChainPass& ps = args.pass[seq.pass_of(c.g)];
       const int m_real = blk * 256 + (int)cta_rank * GEMM_BLOCK_M;
       const int n0 = c.j * 256;
-      const bool row_ok = m_real + row < args.M;
+      const bool row_ok = m_real + row < ps.M;
       const uint32_t bsm = smem_u32(wbias + (it & 1) * 64);
       // in flight while this warp waits for the accumulator: the next tile's bias slice
       float nb0 = 0.f, nb1 = 0.f;
@@ -540,18 +578,18 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
 #pragma unroll
                 for (int j = 0; j < 16; ++j) x[j] += __ldg(ly.bias + j);
               }
-              float* o = args.out_packed + grow * args.n_out;
-              const int hm = args.head_mask;
+              float* o = ps.out_packed + grow * args.n_out;
+              const int hm = ps.head_mask;
               // rs_semantic.py:282-284: rgb = sigmoid(.) * (1 + 2*0.001) - 0.001
 #pragma unroll
               for (int j = 0; j < 3; ++j) o[j] = (hm & SNB_HEAD_RGB) ? (1.0f / (1.0f + expf(-x[j]))) * 1.002f - 0.001f : 0.f;
               o[3] = (hm & SNB_HEAD_SIGMA) ? (x[3] > 20.f ? x[3] : log1pf(expf(x[3]))) : 0.f;
               o[4] = args.nerf ? 1.0f : ((hm & SNB_HEAD_SUN) ? 1.0f / (1.0f + expf(-x[4])) : 0.f);
-              if ((hm & SNB_HEAD_SKY) && args.sky != nullptr) {
+              if ((hm & SNB_HEAD_SKY) && ps.sky != nullptr) {
                 const long long ray = args.rows_per_ray > 0 ? grow / args.rows_per_ray : grow;
-                o[5] = __ldg(args.sky + ray * 3);
-                o[6] = __ldg(args.sky + ray * 3 + 1);
-                o[7] = __ldg(args.sky + ray * 3 + 2);
+                o[5] = __ldg(ps.sky + ray * 3);
+                o[6] = __ldg(ps.sky + ray * 3 + 1);
+                o[7] = __ldg(ps.sky + ray * 3 + 2);
               } else {
                 o[5] = o[6] = o[7] = 0.f;
               }
@@ -642,20 +680,32 @@ int chain_scratch_rows() {
 
 int chain_launch(const ChainArgs& a, cudaStream_t st) {
   SNB_CHECK_ARG(a.n_layers >= 1 && a.n_layers <= CHAIN_MAX_LAYERS, SNB_ERR_INVALID, "chain: %d layers", a.n_layers);
-  SNB_CHECK_ARG(a.M >= 1 && a.n_blocks == (a.M + 255) / 256, SNB_ERR_INVALID, "chain: bad row count");
+  SNB_CHECK_ARG(a.n_passes == 1 || a.n_passes == 2, SNB_ERR_INVALID, "chain: %d passes", a.n_passes);
+  int covered = 0, max_blocks = 0;
+  long long rows = 0;
+  for (int p = 0; p < a.n_passes; ++p) {
+    const ChainPass& ps = a.pass[p];
+    SNB_CHECK_ARG(ps.M >= 1 && ps.n_blocks == (ps.M + 255) / 256 && ps.shift >= 0, SNB_ERR_INVALID, "chain: bad row count");
+    SNB_CHECK_ARG(ps.layer0 == covered && ps.n_layers >= 1, SNB_ERR_INVALID, "chain: pass %d layer range", p);
+    covered += ps.n_layers;
+    max_blocks = ps.n_blocks > max_blocks ? ps.n_blocks : max_blocks;
+    rows += ps.M;
+  }
+  SNB_CHECK_ARG(covered == a.n_layers, SNB_ERR_INVALID, "chain: the passes cover %d of %d layers", covered, a.n_layers);
   double macs = 0.0;
   for (int l = 0; l < a.n_layers; ++l) {
     const ChainLayer& ly = a.layers[l];
+    const ChainPass& ps = a.pass[(a.n_passes == 2 && l >= a.pass[1].layer0) ? 1 : 0];
     SNB_CHECK_ARG(ly.n_tiles >= 1 && ly.kb_total >= 1 && ly.nseg >= 1 && ly.nseg <= 3, SNB_ERR_INVALID, "chain: layer %d shape", l);
     SNB_CHECK_ARG(ly.epi == EPI_SIN || ly.epi == EPI_LINEAR || ly.epi == EPI_MUL || ly.epi == EPI_HEADOUT, SNB_ERR_UNSUPPORTED,
                   "chain: layer %d epilogue %d", l, ly.epi);
     if (ly.epi == EPI_HEADOUT)
-      SNB_CHECK_ARG(ly.n_tiles == 1 && (ly.rows_mode == 2 ? a.out_packed != nullptr : ly.part != nullptr), SNB_ERR_INVALID,
+      SNB_CHECK_ARG(ly.n_tiles == 1 && (ly.rows_mode == 2 ? ps.out_packed != nullptr : ly.part != nullptr), SNB_ERR_INVALID,
                     "chain: head-output layer %d needs its destination", l);
     SNB_CHECK_ARG(!(ly.epi == EPI_MUL && ly.mul_siren == 1) || (ly.mask != nullptr && ly.mask_ld > 0), SNB_ERR_INVALID,
                   "chain: layer %d needs the sign mask of the saved activation", l);
     SNB_CHECK_ARG(ly.tail_k16 >= 1 && ly.tail_k16 <= 4, SNB_ERR_INVALID, "chain: layer %d tail_k16 %d", l, ly.tail_k16);
-    macs += (double)a.n_blocks * 256.0 * (ly.epi == EPI_HEADOUT ? 16.0 : ly.n_tiles * 256.0) *
+    macs += (double)ps.n_blocks * 256.0 * (ly.epi == EPI_HEADOUT ? 16.0 : ly.n_tiles * 256.0) *
             ((ly.kb_total - 1) * GEMM_BLOCK_K + ly.tail_k16 * 16);
   }
   const int sms = num_sms();
@@ -665,7 +715,7 @@ int chain_launch(const ChainArgs& a, cudaStream_t st) {
     SNB_CUDA(cudaFuncSetAttribute(snb_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM_BYTES));
     attr_set = true;
   }
-  const int pairs = a.n_blocks < sms / 2 ? a.n_blocks : sms / 2;
+  const int pairs = max_blocks < sms / 2 ? max_blocks : sms / 2;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs);
@@ -679,7 +729,7 @@ int chain_launch(const ChainArgs& a, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const bool timed = profile_gemm_begin(st, macs, 100 + a.n_layers, a.M, 0, 0, 2, 1);
+  const bool timed = profile_gemm_begin(st, macs, 100 + a.n_layers, (int)rows, 0, 0, 2, 1);
 #ifdef SNB_EXPERIMENTS
   {
     ChainArgs b = a;

@@ -14,7 +14,8 @@
 namespace snb {
 
 constexpr int CHAIN_SLOTS = 3;
-constexpr int CHAIN_MAX_LAYERS = 16;
+constexpr int CHAIN_MAX_LAYERS = 28;   // both passes of a launch together (main forward 14 + solar forward 13); ~1 KB of
+                                       // kernel parameters per layer, 32 764 bytes at most
 constexpr int CHAIN_A_STAGES = 5;      // 16 KB slots (128 rows x 64 k)
 constexpr int CHAIN_B_STAGES = 4;      // 16 KB slots (this CTA's 128 of the 256 weight rows x 64 k; weights are L2-resident)
 constexpr int CHAIN_EPI_WARPS = 16;    // two groups of 8 warps; warps w and w+4 of a group split a 64-column chunk
@@ -58,15 +59,28 @@ struct ChainLayer {     // scalars every role reads once per tile: kept together
   const float* bias;
 };
 
-struct ChainArgs {
-  ChainLayer layers[CHAIN_MAX_LAYERS];
-  int n_layers;
-  int M;
+// A launch carries one or two PASSES: row ranges with their own layer sequence (a training step's main pass and its
+// solar-correction pass).  Every SM pair first works through its blocks of pass 0, then through its blocks of pass 1; pass 1
+// deals its blocks to the pairs rotated by `shift`, so the pairs that carry one block more than the others of pass 0 carry
+// one less of pass 1: at 1024 rays x 64 samples (256 blocks per pass on 74 pairs) a pair runs 4 + 3 blocks instead of the
+// 4 + 4 of two launches.
+struct ChainPass {
+  int layer0, n_layers; // layers [layer0, layer0 + n_layers) of ChainArgs::layers
+  int M;                // rows
   int n_blocks;         // ceil(M / 256)
+  int shift;            // block b belongs to pair (b + shift) % n_pairs
+  int head_mask;
   // head output (EPI_HEADOUT, rows_mode 2): packed (M, n_out) fp32 [rgb 0:3 | sigma 3 | sun 4 | sky 5:8 | beta 8 | sem 9:]
   float* out_packed;
   const float* sky;     // (rays or points, 3) per-ray sky colour from K1
-  int n_out, rows_per_ray, n_classes, sem_sigmoid, head_mask;
+};
+
+struct ChainArgs {
+  ChainLayer layers[CHAIN_MAX_LAYERS];
+  ChainPass pass[2];
+  int n_passes;
+  int n_layers;         // all passes together
+  int n_out, rows_per_ray, n_classes, sem_sigmoid;
   int nerf;             // head output: the sun column is written as 1 (no lighting model: irradiance = 1 in K3)
   int beta_s;           // head output: pre-activation row 6 is the separate semantic uncertainty head (packed column 9, softplus);
                         // the class rows / columns follow it

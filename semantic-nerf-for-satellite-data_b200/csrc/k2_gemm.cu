@@ -555,8 +555,10 @@ extern "C" int snb_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t 
     SNB_CHECK_ARG(epi != EPI_MUL || mul != nullptr, SNB_ERR_INVALID, "gemm_bf16: mul operand required");
     ChainArgs* ca = new ChainArgs();
     memset(ca, 0, sizeof(*ca));
-    ca->M = (int)M;
-    ca->n_blocks = (int)((M + 255) / 256);
+    ca->n_passes = 1;
+    ca->pass[0].M = (int)M;
+    ca->pass[0].n_blocks = (int)((M + 255) / 256);
+    ca->pass[0].n_layers = 1;
     ca->n_layers = 1;
     ChainLayer& ly = ca->layers[0];
     ChainMaps& mp = ca->maps[0];

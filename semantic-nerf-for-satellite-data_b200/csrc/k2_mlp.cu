@@ -889,9 +889,35 @@ struct ChainPlan {
   cudaStream_t st;
   ChainPlan(long long P, bool chained, cudaStream_t stream) : per_layer(!chained), st(stream) {
     memset(&a, 0, sizeof(a));
-    a.M = (int)P;
-    a.n_blocks = (int)((P + 255) / 256);
+    begin_pass(P);
   }
+  // the following layers belong to a (second) pass over P rows of their own; both passes run in ONE launch (per-layer mode:
+  // nothing to merge, the layers are launched one by one)
+  void begin_pass(long long P) {
+    if (per_layer || a.n_passes == 0 || a.n_layers == 0) {
+      a.n_passes = 1;
+      a.n_layers = 0;
+    } else {
+      close_pass();
+      if (a.n_passes >= 2) {
+        set_error("chain plan: more than two passes");
+        chk(SNB_ERR_UNSUPPORTED);
+        return;
+      }
+      // the pairs that carry one block more of pass 0 than the others carry one less of this one
+      const int sms = num_sms();
+      const int np = a.pass[0].n_blocks < sms / 2 ? a.pass[0].n_blocks : sms / 2;
+      ++a.n_passes;
+      memset(&a.pass[1], 0, sizeof(ChainPass));
+      a.pass[1].shift = np > 0 ? a.pass[0].n_blocks % np : 0;
+    }
+    ChainPass& ps = a.pass[a.n_passes - 1];
+    ps.layer0 = a.n_layers;
+    ps.M = (int)P;
+    ps.n_blocks = (int)((P + 255) / 256);
+  }
+  ChainPass& pass() { return a.pass[a.n_passes - 1]; }
+  void close_pass() { pass().n_layers = a.n_layers - pass().layer0; }
   void chk(int r) {
     if (r && !rc) rc = r;
   }
@@ -925,13 +951,13 @@ struct ChainPlan {
     }
     chk(make_tmap_2d(&mp.tmB, B, 2, (uint64_t)b_cols, (uint64_t)N, (uint64_t)ldb * 2, 64, 128));
     chk(make_tmap_2d(&mp.tmO0, out0, 2, (uint64_t)N, (uint64_t)o_rows, (uint64_t)ldo * 2, 64, GEMM_BLOCK_M));
-    if (epi == EPI_MUL) chk(make_tmap_2d(&mp.tmMul, mul, 2, (uint64_t)N, (uint64_t)a.M, (uint64_t)ldmul * 2, 64, GEMM_BLOCK_M));
+    if (epi == EPI_MUL) chk(make_tmap_2d(&mp.tmMul, mul, 2, (uint64_t)N, (uint64_t)pass().M, (uint64_t)ldmul * 2, 64, GEMM_BLOCK_M));
     ly.mul_siren = (epi == EPI_MUL && mask != nullptr) ? (relu ? 2 : 1) : 0;
     ly.relu = (relu && epi == EPI_SIN) ? 1 : 0;
     if (epi == EPI_LINEAR || relu) mask = nullptr;   // ReLU needs no sign mask: its derivative is [h > 0]
     ly.mask = mask;
     ly.mask_ld = mask_ld;
-    if (mask) chk(make_tmap_mask(&mp.tmMask, mask, (uint64_t)(N / 32), (uint64_t)a.M, (uint64_t)mask_ld * 4));
+    if (mask) chk(make_tmap_mask(&mp.tmMask, mask, (uint64_t)(N / 32), (uint64_t)pass().M, (uint64_t)mask_ld * 4));
     ly.o_scratch = o_scratch;
     ly.bias = bias;
     ly.w0 = w0;
@@ -960,8 +986,15 @@ struct ChainPlan {
     if (per_layer) flush();
   }
   void flush() {
+    close_pass();
     if (!rc && a.n_layers > 0) chk(chain_launch(a, st));
     a.n_layers = 0;
+    if (a.n_passes > 1) {   // (a flushed two-pass plan is finished)
+      a.n_passes = 1;
+      a.pass[0] = a.pass[1];
+    }
+    a.pass[0].layer0 = 0;
+    a.pass[0].shift = 0;
   }
   int run() {
     flush();
@@ -1082,9 +1115,10 @@ extern "C" size_t snb_mlp_workspace_bytes(const snb_model* m, int64_t n_points, 
   return layout_workspace(m, n_points, train).total;
 }
 
+// plan: NULL = build and run this pass's chained launch; else the pass is appended to *plan (the caller runs it)
 static int mlp_forward_rows(const snb_model* m, const void* packed, char* ws, const Workspace& w, long long P, const void* enc,
                             const void* aux, const float* sky, int rows_per_ray, int head_mask, int train, float* out,
-                            void* stream);
+                            void* stream, ChainPlan* plan = nullptr, bool plan_started = false);
 
 extern "C" int snb_mlp_forward(const snb_model* m, const void* packed, void* workspace, size_t workspace_bytes,
                                int64_t n_points, const void* enc, const void* aux, const float* sky,
@@ -1119,16 +1153,22 @@ extern "C" int snb_mlp_forward_with_solar(const snb_model* m, const void* packed
   SNB_CHECK_ARG(workspace_bytes >= w.total, SNB_ERR_WORKSPACE, "mlp_forward_with_solar: workspace %zu < required %zu",
                 workspace_bytes, w.total);
   char* ws = reinterpret_cast<char*>(workspace);
-  if (int r = mlp_forward_rows(m, packed, ws, w, n_points, enc, aux, sky, rows_per_ray, SNB_HEADS_ALL, 1, out, stream)) return r;
-  if (n_solar_points == 0) return 0;
-  const char* enc_s = reinterpret_cast<const char*>(enc) + (size_t)n_points * m->enc_ld * 2;
-  return mlp_forward_rows(m, packed, ws, shift_rows(m, w, n_points), n_solar_points, enc_s, aux, nullptr, rows_per_ray,
-                          SNB_HEADS_SOLAR, 1, out + (size_t)n_points * m->n_out, stream);
+  // both passes in ONE chained launch (ChainPass): every SM pair carries its blocks of the main pass, then of the solar pass
+  ChainPlan cp(n_points, use_chain(), (cudaStream_t)stream);
+  if (int r = mlp_forward_rows(m, packed, ws, w, n_points, enc, aux, sky, rows_per_ray, SNB_HEADS_ALL, 1, out, stream, &cp, true))
+    return r;
+  if (n_solar_points > 0) {
+    const char* enc_s = reinterpret_cast<const char*>(enc) + (size_t)n_points * m->enc_ld * 2;
+    if (int r = mlp_forward_rows(m, packed, ws, shift_rows(m, w, n_points), n_solar_points, enc_s, aux, nullptr, rows_per_ray,
+                                 SNB_HEADS_SOLAR, 1, out + (size_t)n_points * m->n_out, stream, &cp, false))
+      return r;
+  }
+  return cp.run();
 }
 
 static int mlp_forward_rows(const snb_model* m, const void* packed, char* ws, const Workspace& w, long long P, const void* enc,
                             const void* aux, const float* sky, int rows_per_ray, int head_mask, int train, float* out,
-                            void* stream) {
+                            void* stream, ChainPlan* plan, bool plan_started) {
   const __nv_bfloat16* pk = reinterpret_cast<const __nv_bfloat16*>(packed);
   const float* pb = reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + (size_t)m->packed_bf16_elems * 2);
   auto H = [&](int i) { return (void*)(ws + w.h[i]); };
@@ -1139,7 +1179,10 @@ static int mlp_forward_rows(const snb_model* m, const void* packed, char* ws, co
     // trunk + feats + head first layers + sun layers.  Chained (default): one persistent launch, inter-layer
     // activations are read back from L2 and, in inference, live in a per-SM-pair scratch that never reaches HBM.
     const bool chained = use_chain();
-    ChainPlan cp(P, chained, (cudaStream_t)stream);
+    ChainPlan own(P, chained, (cudaStream_t)stream);
+    ChainPlan& cp = plan ? *plan : own;
+    if (plan && !plan_started) cp.begin_pass(P);
+    auto finish = [&]() -> int { return plan ? cp.rc : cp.run(); };
     cp.relu = m->relu != 0;
     cp.a.nerf = m->kind == SNB_MODEL_NERF ? 1 : 0;
     const float w_first = m->relu ? 1.0f : 30.0f;   // Siren(w0 = 30) on the first trunk layer only (satnerf.py:146)
@@ -1167,14 +1210,14 @@ static int mlp_forward_rows(const snb_model* m, const void* packed, char* ws, co
     }
     // head outputs: three N = 16 layers ([h7 | s3 | hh] x W_out^T split by K-segment), each right after the layer that
     // produced its input so it is read from L2; the last one applies the head activations and writes `out`
-    cp.a.out_packed = out;
-    cp.a.sky = sky;
+    cp.pass().out_packed = out;
+    cp.pass().sky = sky;
+    cp.pass().head_mask = head_mask;
     cp.a.n_out = m->n_out;
     cp.a.rows_per_ray = rows_per_ray;
     cp.a.n_classes = m->n_classes;
     cp.a.beta_s = m->beta_s;
     cp.a.sem_sigmoid = m->sem_sigmoid;
-    cp.a.head_mask = head_mask;
     float* hpart = reinterpret_cast<float*>(ws + w.hpart);
     {
       CSeg s7 = {H(7), F, F, F / 64, P, 0};
@@ -1195,7 +1238,7 @@ static int mlp_forward_rows(const snb_model* m, const void* packed, char* ws, co
         CSeg shh = {ws + w.hh, hhw, hhw, hhw / 64, P, 0};
         cp.add_rows16(shh, pk + m->who + F + FL, m->kho, hhw, nerf ? 2 : 1, hpart, nerf ? pb + m->bho : nullptr);
       }
-      if (nerf) return cp.run();
+      if (nerf) return finish();
       CSeg s2[1] = {{ws + w.hh + (size_t)m->hh_sun * 2, hhw, FL, FL / 64, P, 0}};
       cp.add(EPI_SIN, FL, s2, 1, pk + m->ws2, FL, FL, s2buf, FL, srows, sflag, nullptr, 0,
              train ? reinterpret_cast<uint32_t*>(ws + w.sgs2) : nullptr, FL / 32, pb + m->bs2, 1.0f);
@@ -1205,7 +1248,7 @@ static int mlp_forward_rows(const snb_model* m, const void* packed, char* ws, co
       CSeg ss3 = {ws + w.s3, FL, FL, FL / 64, P, 0};
       cp.add_rows16(ss3, pk + m->who + F, m->kho, FL, 2, hpart, pb + m->bho);
     }
-    return cp.run();
+    return finish();
   }
 }
 
@@ -1287,6 +1330,8 @@ static int mlp_backward_rows(const snb_model* m, const void* packed, char* ws, c
   const int r0 = all ? 0 : m->hh_sun, nh = all ? hhw : FL;
   const char* dyhh_r0 = ws + w.dyhh + (size_t)r0 * 2;
   // ---- dgrad: the gradient w.r.t. every pre-activation, from the heads back to trunk layer 0 ---------------
+  ChainPlan cp(P, use_chain(), st);   // both passes' dgrad chains in one launch
+  cp.relu = m->relu != 0;
   auto dgrad = [&](const Workspace& w, long long P, int head_mask) -> int {
     const bool all = head_mask == SNB_HEADS_ALL;
     const bool depth = head_mask == SNB_HEADS_DEPTH;
@@ -1297,8 +1342,6 @@ static int mlp_backward_rows(const snb_model* m, const void* packed, char* ws, c
     auto DY = [&](int i) { return (void*)(ws + w.dy[i]); };
     // chained (default): one persistent launch; each dY is read back from L2 by the next step of the same SM pair.
     // The SIREN derivative w0 cos(.) is rebuilt in the epilogue from the saved activation and its sign mask.
-    ChainPlan cp(P, use_chain(), st);
-    cp.relu = m->relu != 0;
     auto SG = [&](int i) { return reinterpret_cast<uint32_t*>(ws + w.sg[i]); };
     uint32_t* sghh = reinterpret_cast<uint32_t*>(ws + w.sghh);
     CSeg cdpre[1] = {{dpre, 16, 16, 1, P, 0}};
@@ -1331,11 +1374,14 @@ static int mlp_backward_rows(const snb_model* m, const void* packed, char* ws, c
       cp.add(EPI_MUL, F, c, 1, pk + m->tl[i], F, F, DY(i - 1), F, P, 0, H(i - 1), F, SG(i - 1), F / 32, nullptr,
              (i - 1 == 0 && !m->relu) ? 30.0f : 1.0f);
     }
-    return cp.run();
+    return cp.rc;
   };
   if (int r = dgrad(w, P, head_mask)) return r;
-  if (Psc > 0)
+  if (Psc > 0) {
+    cp.begin_pass(Psc);
     if (int r = dgrad(wsc, Psc, SNB_HEADS_SOLAR)) return r;
+  }
+  if (int r = cp.run()) return r;
   // ---- wgrad: every weight gradient is dY^T x (layer input), split-K over the samples -----------------------
   // (the layers both passes share - trunk, sun layers, head outputs - reduce over all Pt rows in one launch each)
   const long long ldt = (Pt + 63) & ~63ll;
