@@ -207,6 +207,12 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) snb_chain_kernel(const __gri
   const int n_pairs = (int)(gridDim.x >> 1);
   Seq seq;
   seq.init(args, pair, n_pairs);
+  if (args.prefetch != nullptr) {
+    const char* base = reinterpret_cast<const char*>(args.prefetch);
+    for (size_t off = ((size_t)blockIdx.x * CHAIN_THREADS + threadIdx.x) * 128; off < args.prefetch_bytes;
+         off += (size_t)gridDim.x * CHAIN_THREADS * 128)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 8; ++s) {

@@ -13,7 +13,8 @@
 
 namespace snb {
 
-constexpr int CHAIN_SLOTS = 3;
+constexpr int CHAIN_SLOTS = 3;         // (a pair's 4 blocks as ONE group of 4 instead of 2 + 2 was measured: +1.5 % step time at
+                                       // 1024 rays, profiles/r02j_tune.log)
 constexpr int CHAIN_MAX_LAYERS = 28;   // both passes of a launch together (main forward 14 + solar forward 13); ~1 KB of
                                        // kernel parameters per layer, 32 764 bytes at most
 constexpr int CHAIN_A_STAGES = 5;      // 16 KB slots (128 rows x 64 k)
@@ -84,6 +85,11 @@ struct ChainArgs {
   int nerf;             // head output: the sun column is written as 1 (no lighting model: irradiance = 1 in K3)
   int beta_s;           // head output: pre-activation row 6 is the separate semantic uncertainty head (packed column 9, softplus);
                         // the class rows / columns follow it
+  // the packed weight image (or NULL): every thread prefetches one or two of its 128-byte lines into L2 before the first
+  // tile, so the first block of a pair does not pay an HBM round trip per layer for weights the activation traffic of the
+  // previous pass has evicted (at 1024 rays a pair carries only 3-4 blocks per pass)
+  const void* prefetch;
+  unsigned prefetch_bytes;
   int exp;              // SNB_EXPERIMENTS builds only (env SNB_EXP): bit 0 skip every second B load, bit 1 every second A load,
                         // bit 2 skip the epilogue math, bit 3 skip the TMA stores, bit 4 skip the multiplicand loads
   ChainMaps maps[CHAIN_MAX_LAYERS];

@@ -1184,6 +1184,8 @@ static int mlp_forward_rows(const snb_model* m, const void* packed, char* ws, co
     if (plan && !plan_started) cp.begin_pass(P);
     auto finish = [&]() -> int { return plan ? cp.rc : cp.run(); };
     cp.relu = m->relu != 0;
+    cp.a.prefetch = packed;
+    cp.a.prefetch_bytes = (unsigned)((size_t)m->packed_bf16_elems * 2);
     cp.a.nerf = m->kind == SNB_MODEL_NERF ? 1 : 0;
     const float w_first = m->relu ? 1.0f : 30.0f;   // Siren(w0 = 30) on the first trunk layer only (satnerf.py:146)
     const long long R = chain_scratch_rows();
@@ -1332,6 +1334,8 @@ static int mlp_backward_rows(const snb_model* m, const void* packed, char* ws, c
   // ---- dgrad: the gradient w.r.t. every pre-activation, from the heads back to trunk layer 0 ---------------
   ChainPlan cp(P, use_chain(), st);   // both passes' dgrad chains in one launch
   cp.relu = m->relu != 0;
+  cp.a.prefetch = packed;
+  cp.a.prefetch_bytes = (unsigned)((size_t)m->packed_bf16_elems * 2);
   auto dgrad = [&](const Workspace& w, long long P, int head_mask) -> int {
     const bool all = head_mask == SNB_HEADS_ALL;
     const bool depth = head_mask == SNB_HEADS_DEPTH;
