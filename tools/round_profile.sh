@@ -10,6 +10,6 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_benc
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $O/${T}_ncu_launches_bench.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu --no-extras --no-graph > $O/${T}_ncu_bench.log 2>&1; echo "ncu launches rc=$?"
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,launch__registers_per_thread,sm__cycles_elapsed.avg,l1tex__m_xbar2l1tex_read_bytes.sum,l1tex__m_l1tex2xbar_write_bytes.sum,lts__t_sectors_srcunit_tex.sum
-timeout 900 ncu --metrics $M --clock-control none -k regex:"snb_chain|snb_gemm" --launch-skip 32 --launch-count 32 -f -o $O/${T}_step_gemms \
+timeout 900 ncu --metrics $M --clock-control none -k regex:"snb_chain|snb_gemm" --launch-skip 18 --launch-count 18 -f -o $O/${T}_step_gemms \
   python tools/prof_step.py 8192 2 > $O/${T}_ncu_step.log 2>&1; echo "ncu step rc=$?"
 ls -la $O | head -20
