@@ -219,13 +219,16 @@ def test_chained_mlp_equals_per_layer_mlp(kind, C, P):
     assert _cos(res[1][2], res[0][2]) >= 0.999999
 
 
-@pytest.mark.parametrize("kind,C,n,S", [("semantic", 6, 333, 64), ("satnerf", 0, 512, 16), ("semantic", 4, 77, 6), ("snerf", 0, 200, 32)])
-def test_solar_rows_in_one_workspace_equal_two_passes(kind, C, n, S):
+@pytest.mark.parametrize("kind,C,n,S,n_sol", [("semantic", 6, 333, 64, 333), ("satnerf", 0, 512, 16, 512), ("semantic", 4, 77, 6, 77),
+                                              ("snerf", 0, 200, 32, 200), ("semantic", 6, 1200, 64, 500), ("satnerf", 0, 90, 64, 1)])
+def test_solar_rows_in_one_workspace_equal_two_passes(kind, C, n, S, n_sol):
     """snb_mlp_forward_with_solar / snb_mlp_backward_with_solar (main pass rows [0, P), solar-correction pass rows [P, 2P) of
     one workspace; the weight gradients of the shared layers run once over all rows) against snb_mlp_forward /
     snb_mlp_backward called once per pass: the forward outputs are bit-identical, the parameter gradients agree up to the
     fp32 split-K accumulation order, the per-point embedding gradients are bit-identical (main pass only).  P = n S is
-    ragged in three of the cases: the reduction blocks of the merged launches straddle the boundary between the passes."""
+    ragged in three of the cases: the reduction blocks of the merged launches straddle the boundary between the passes.
+    n_sol < n: fewer solar rows than main rows (the solar pass of the first n_sol rays; 1200 x 64 rows = 300 blocks on 74 SM
+    pairs, 125 solar blocks dealt rotated by 300 mod 74)."""
     import ctypes as C_
     from semnerf_b200.autograd import encode_rays, HEADS_ALL, HEADS_SOLAR
     from semnerf_b200._lib import ptr, check
@@ -235,36 +238,37 @@ def test_solar_rows_in_one_workspace_equal_two_passes(kind, C, n, S):
     u = torch.rand(n, S, generator=torch.Generator().manual_seed(2)).to(DEV)
     has_t = kind != "snerf"
     z, enc, enc_sc, aux, sky = encode_rays(model, t.weight if has_t else None, rays.to(DEV), extras.to(DEV), S, u=u, want_sc=True)
-    P, n_out = n * S, model.n_out_kernel
+    P, Ps, n_out = n * S, n_sol * S, model.n_out_kernel
+    enc_sc = enc_sc[:Ps].contiguous()
     packed = model.packed()
     g = torch.Generator().manual_seed(7)
     g_main = torch.randn(P, n_out, generator=g).to(DEV)
-    g_sol = torch.zeros(P, n_out, device=DEV)
-    g_sol[:, 3:5] = torch.randn(P, 2, generator=g).to(DEV)          # the solar pass produces sigma and sun only
+    g_sol = torch.zeros(Ps, n_out, device=DEV)
+    g_sol[:, 3:5] = torch.randn(Ps, 2, generator=g).to(DEV)         # the solar pass produces sigma and sun only
     st = None
     nb = lib.snb_mlp_workspace_bytes(model._h, P, 1)
     ws_a, ws_b = (torch.empty(nb, dtype=torch.uint8, device=DEV) for _ in range(2))
-    out_a, out_b = (torch.empty(P, n_out, device=DEV) for _ in range(2))
+    out_a, out_b = torch.empty(P, n_out, device=DEV), torch.empty(Ps, n_out, device=DEV)
     check(lib.snb_mlp_forward(model._h, ptr(packed), ptr(ws_a), nb, P, ptr(enc), ptr(aux), ptr(sky), S, HEADS_ALL, 1, ptr(out_a), st), "fwd")
-    check(lib.snb_mlp_forward(model._h, ptr(packed), ptr(ws_b), nb, P, ptr(enc_sc), ptr(aux), None, S, HEADS_SOLAR, 1, ptr(out_b), st), "fwd")
+    check(lib.snb_mlp_forward(model._h, ptr(packed), ptr(ws_b), nb, Ps, ptr(enc_sc), ptr(aux), None, S, HEADS_SOLAR, 1, ptr(out_b), st), "fwd")
     grads2 = torch.zeros_like(model.flat.detach())
     g_aux2 = torch.zeros(P, 16, device=DEV)
-    check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws_b), nb, P, ptr(enc_sc), ptr(aux), ptr(out_b), ptr(g_sol), HEADS_SOLAR,
+    check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws_b), nb, Ps, ptr(enc_sc), ptr(aux), ptr(out_b), ptr(g_sol), HEADS_SOLAR,
                                ptr(grads2), None, None, st), "bwd")
     check(lib.snb_mlp_backward(model._h, ptr(packed), ptr(ws_a), nb, P, ptr(enc), ptr(aux), ptr(out_a), ptr(g_main), HEADS_ALL,
                                ptr(grads2), ptr(g_aux2), None, st), "bwd")
     # the same two passes as rows of one workspace
-    nb2 = lib.snb_mlp_workspace_bytes(model._h, 2 * P, 1)
+    nb2 = lib.snb_mlp_workspace_bytes(model._h, P + Ps, 1)
     ws = torch.empty(nb2, dtype=torch.uint8, device=DEV)
     enc_all = torch.cat([enc, enc_sc], 0).contiguous()
-    out_all = torch.empty(2 * P, n_out, device=DEV)
-    check(lib.snb_mlp_forward_with_solar(model._h, ptr(packed), ptr(ws), nb2, P, P, ptr(enc_all), ptr(aux), ptr(sky), S,
+    out_all = torch.empty(P + Ps, n_out, device=DEV)
+    check(lib.snb_mlp_forward_with_solar(model._h, ptr(packed), ptr(ws), nb2, P, Ps, ptr(enc_all), ptr(aux), ptr(sky), S,
                                          ptr(out_all), st), "fwd2")
     assert torch.equal(out_all[:P], out_a) and torch.equal(out_all[P:], out_b)
     grads1 = torch.zeros_like(grads2)
     g_aux1 = torch.zeros(P, 16, device=DEV)
     g_all = torch.cat([g_main, g_sol], 0).contiguous()
-    check(lib.snb_mlp_backward_with_solar(model._h, ptr(packed), ptr(ws), nb2, P, P, ptr(enc_all), ptr(aux), ptr(out_all),
+    check(lib.snb_mlp_backward_with_solar(model._h, ptr(packed), ptr(ws), nb2, P, Ps, ptr(enc_all), ptr(aux), ptr(out_all),
                                           ptr(g_all), ptr(grads1), ptr(g_aux1), None, st), "bwd2")
     torch.cuda.synchronize()
     a, b = grads1.double(), grads2.double()
