@@ -288,6 +288,11 @@ int64_t snb_profile_launch_count(void);
 void snb_profile_add_launches(int64_t n);
 int snb_profile_end(double* gemm_ms, int64_t* gemm_launches, int64_t* total_launches, double* gemm_macs);
 
+/* test hook (host only, no device needed): the row blocks SM pair `pair` of `n_pairs` carries through a chained launch of
+ * one or two passes (n_blocks1 = 0: one), in execution order, as (pass << 24 | block) words; returns their number.
+ * shift1: the rotation of the second pass's dealing (the library uses n_blocks0 % n_pairs). */
+int snb_chain_schedule(int n_blocks0, int n_blocks1, int shift1, int n_pairs, int pair, int* out, int cap);
+
 /* ------------------------------------------------------------------------------------------------
  * test hook: one bf16 GEMM through the tcgen05 kernel.  D = A (M,K) x B (N,K)^T (+ epilogue).
  * a_mn / b_mn = 1: operand stored (K,M) / (K,N) row-major (the wgrad form).

@@ -54,6 +54,7 @@ SIGNATURES = {
     "snb_label_counts": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "snb_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _vp, _f, _vp]),
     "snb_set_chained_mlp": (_i, [_i]),
+    "snb_chain_schedule": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i), _i]),
     "snb_profile_begin": (None, [_i]),
     "snb_profile_launch_count": (_i64, []),
     "snb_profile_add_launches": (None, [_i64]),

@@ -38,7 +38,7 @@ struct Seq {
   // Groups are numbered through the passes: [0, g0) belong to pass 0, [g0, groups) to pass 1.
   int g0, groups;
   int base[2], rem[2], pe[2], l0[2], l1[2], n_pairs;
-  __device__ __forceinline__ void init(const ChainArgs& a, int pair, int n_pairs_) {
+  __host__ __device__ __forceinline__ void init(const ChainArgs& a, int pair, int n_pairs_) {
     n_pairs = n_pairs_;
     int ng[2] = {0, 0};
 #pragma unroll
@@ -57,30 +57,30 @@ struct Seq {
     g0 = ng[0];
     groups = ng[0] + ng[1];
   }
-  __device__ __forceinline__ int pass_of(int g) const { return g >= g0 ? 1 : 0; }
+  __host__ __device__ __forceinline__ int pass_of(int g) const { return g >= g0 ? 1 : 0; }
   // (selects, not indexed loads: the members stay in registers)
-  __device__ __forceinline__ int nslots(int g) const {
+  __host__ __device__ __forceinline__ int nslots(int g) const {
     const bool p = g >= g0;
     const int gp = p ? g - g0 : g, b = p ? base[1] : base[0], r = p ? rem[1] : rem[0];
     return b + (gp < r ? 1 : 0);
   }
   // row block of slot s of group g
-  __device__ __forceinline__ int block(int g, int s) const {
+  __host__ __device__ __forceinline__ int block(int g, int s) const {
     const bool p = g >= g0;
     const int gp = p ? g - g0 : g, b = p ? base[1] : base[0], r = p ? rem[1] : rem[0];
     const int first = gp * b + (gp < r ? gp : r);   // first own block of the group
     return (first + s) * n_pairs + (p ? pe[1] : pe[0]);
   }
-  __device__ __forceinline__ int layer_begin(int g) const { return g >= g0 ? l0[1] : l0[0]; }
-  __device__ __forceinline__ int layer_end(int g) const { return g >= g0 ? l1[1] : l1[0]; }
+  __host__ __device__ __forceinline__ int layer_begin(int g) const { return g >= g0 ? l0[1] : l0[0]; }
+  __host__ __device__ __forceinline__ int layer_end(int g) const { return g >= g0 ? l1[1] : l1[0]; }
 };
 
-__device__ __forceinline__ void cur_init(Cursor& c, const Seq& q) {
+__host__ __device__ __forceinline__ void cur_init(Cursor& c, const Seq& q) {
   c.g = c.s = c.j = 0;
   c.done = q.groups <= 0;
   c.l = c.done ? 0 : q.layer_begin(0);
 }
-__device__ __forceinline__ void cur_next(Cursor& c, const Seq& q, const ChainArgs& a) {
+__host__ __device__ __forceinline__ void cur_next(Cursor& c, const Seq& q, const ChainArgs& a) {
   if (++c.j < a.layers[c.l].n_tiles) return;
   c.j = 0;
   if (++c.s < q.nslots(c.g)) return;
@@ -751,3 +751,32 @@ int chain_launch(const ChainArgs& a, cudaStream_t st) {
 }
 
 }  // namespace snb
+
+// test hook (runs on the host, no device needed): the row blocks SM pair `pair` of `n_pairs` carries through a launch of one or
+// two passes, in execution order, as (pass << 24 | block) words - the same Seq / Cursor code the kernel runs.
+extern "C" int snb_chain_schedule(int n_blocks0, int n_blocks1, int shift1, int n_pairs, int pair, int* out, int cap) {
+  using namespace snb;
+  if (n_blocks0 < 1 || n_blocks1 < 0 || n_pairs < 1 || pair < 0 || pair >= n_pairs || !out) return -1;
+  ChainArgs* a = new ChainArgs();
+  memset(a, 0, sizeof(*a));
+  a->n_passes = n_blocks1 > 0 ? 2 : 1;
+  a->pass[0].n_blocks = n_blocks0;
+  a->pass[0].layer0 = 0;
+  a->pass[0].n_layers = 1;
+  a->pass[1].n_blocks = n_blocks1;
+  a->pass[1].layer0 = 1;
+  a->pass[1].n_layers = 1;
+  a->pass[1].shift = shift1;
+  a->n_layers = a->n_passes;
+  a->layers[0].n_tiles = a->layers[1].n_tiles = 1;
+  Seq q;
+  q.init(*a, pair, n_pairs);
+  int n = 0;
+  Cursor c;
+  for (cur_init(c, q); !c.done; cur_next(c, q, *a)) {
+    if (n < cap) out[n] = (q.pass_of(c.g) << 24) | q.block(c.g, c.s);
+    ++n;
+  }
+  delete a;
+  return n;
+}

@@ -157,3 +157,41 @@ def test_nerf_state_dict_is_the_reference_nerf():
     assert torch.allclose(posenc_dirs(d), O.posenc(d, 4))            # the fp32-mode direction encoding = Mapping(4, 3)
     with pytest.raises(_lib.SnbError):
         NeRFB200(siren=True)
+
+
+def test_chained_launch_deals_every_block_of_both_passes_exactly_once():
+    """The two-pass chained launch (k2_chain.cuh ChainPass): every 256-row block of the main pass and of the solar pass is
+    carried by exactly one SM pair, a pair works through its main-pass blocks first, and with the library's rotation
+    (n_blocks0 mod pairs) no pair carries more than the unavoidable maximum - 4 + 3 instead of 4 + 4 blocks at the
+    reference's default batch.  Runs the kernel's own schedule
+    code on the host (snb_chain_schedule)."""
+    import ctypes as C_
+    lib = _lib.load()
+    cases = [(256, 256, 74), (2048, 2048, 74), (300, 125, 74), (23, 1, 23), (2, 2, 2), (1, 1, 1), (77, 0, 74), (1000, 999, 74),
+             (75, 75, 74), (148, 74, 74), (5, 3, 5)]
+    for nb0, nb1, sms_pairs in cases:
+        n_pairs = min(max(nb0, nb1), sms_pairs)          # chain_launch: one pair per block at most
+        shift = nb0 % min(nb0, sms_pairs)                # ChainPlan::begin_pass
+        seen = [set(), set()]
+        loads = []
+        for pair in range(n_pairs):
+            buf = (C_.c_int * 4096)()
+            n = lib.snb_chain_schedule(nb0, nb1, shift, n_pairs, pair, buf, 4096)
+            assert 0 <= n <= 4096
+            seq = [(buf[i] >> 24, buf[i] & 0xFFFFFF) for i in range(n)]
+            passes = [p for p, _ in seq]
+            assert passes == sorted(passes), (nb0, nb1, pair)         # all of pass 0, then all of pass 1
+            for p, b in seq:
+                assert b < (nb0, nb1)[p] and b not in seen[p], (nb0, nb1, pair, p, b)
+                seen[p].add(b)
+            loads.append(n)
+        assert seen[0] == set(range(nb0)) and seen[1] == set(range(nb1)), (nb0, nb1)
+        if n_pairs == sms_pairs:
+            ideal = -(-(nb0 + nb1) // n_pairs)
+            assert max(loads) <= ideal + (1 if (nb0 % n_pairs) + (nb1 % n_pairs) > n_pairs else 0), (nb0, nb1, max(loads), ideal)
+    # the reference's default batch: 1024 rays x 64 samples = 256 blocks per pass on 74 pairs -> 7 blocks per pair, not 8
+    loads = []
+    for pair in range(74):
+        buf = (C_.c_int * 64)()
+        loads.append(lib.snb_chain_schedule(256, 256, 256 % 74, 74, pair, buf, 64))
+    assert max(loads) == 7 and min(loads) == 6 and sum(loads) == 512
