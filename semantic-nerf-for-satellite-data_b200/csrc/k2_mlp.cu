@@ -657,9 +657,9 @@ static int run_jobs(const std::vector<PackJob>& all, bool unpack, const float* s
 // ---- workspace layout -----------------------------------------------------------------------------
 struct Workspace {
   // all offsets in bytes from the workspace base; 0-sized members are absent
-  size_t h[8], sg[8], f, hh, sghh, s2, sgs2, s3, sgs3;  // forward (sg*: sign masks of the SIREN derivatives, train only)
-  size_t dpre, dy[8], df, dyhh, dys3, dys2;         // backward (dy[i] = gradient w.r.t. the pre-activation of trunk layer i)
-  size_t scr_h[2], scr_f, scr_s2;                   // inference: per-SM-pair scratch of the chained kernel (L2-resident)
+  size_t h[8], sg[8], hh, sghh, s2, sgs2, s3, sgs3;  // forward (sg*: sign masks of the SIREN derivatives, train only)
+  size_t dpre, dy[8], dyhh, dys3, dys2;             // backward (dy[i] = gradient w.r.t. the pre-activation of trunk layer i)
+  size_t scr_h[2], scr_s2;                          // inference: per-SM-pair scratch of the chained kernel (L2-resident)
   size_t hpart;                                     // (P, 16) fp32 partial sums of the head pre-activations
   size_t auxT, encT;                                // [16, ldt] / [64, ldt] K-major copies of aux / enc[:, :64] (wgrad side operands)
   size_t gscratch;                                  // fp32 packed gradients
@@ -691,7 +691,7 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
   } else {
     size_t a = take_b(rowF), b = take_b(rowF);
     for (int i = 0; i < 8; ++i) w.h[i] = (i & 1) ? b : a;  // ping-pong (layer 4 reads h3, writes h4: distinct)
-    // chained kernel: layers 0..6, f and s2 live in a per-pair scratch instead (h7 / hh / s3 stay per-point:
+    // chained kernel: layers 0..6 and s2 live in a per-pair scratch instead (h7 / hh / s3 stay per-point:
     // the head-output kernel reads them)
     const size_t R = (size_t)chain_scratch_rows();
     w.scr_h[0] = take_b(R * F * 2);
@@ -1189,7 +1189,7 @@ static int mlp_forward_rows(const snb_model* m, const void* packed, char* ws, co
     cp.a.nerf = m->kind == SNB_MODEL_NERF ? 1 : 0;
     const float w_first = m->relu ? 1.0f : 30.0f;   // Siren(w0 = 30) on the first trunk layer only (satnerf.py:146)
     const long long R = chain_scratch_rows();
-    const bool scr = !train && chained;   // inference: layers 0..6, f, s2 in the per-pair scratch
+    const bool scr = !train && chained;   // inference: layers 0..6 and s2 in the per-pair scratch
     auto hbuf = [&](int i) { return scr && i < 7 ? (void*)(ws + w.scr_h[i & 1]) : H(i); };
     auto hrows = [&](int i) { return scr && i < 7 ? R : P; };
     auto hscr = [&](int i) { return scr && i < 7 ? 1 : 0; };
