@@ -108,11 +108,15 @@ typedef struct snb_model snb_model; /* opaque host object: architecture + packed
  * 297-303): cat(f, t) -> 256 -> softplus, packed column 9, the class scores move to columns 10.. (n_classes <= 9).
  * SNB_VARIANT_SEPARATE_TJ_S: the semantic head (with TJ_FOR_S) and the semantic uncertainty head read a SECOND embedding t_s
  * (`use_separate_tj_for_semantic`, :300-301,334-335): the caller passes both tables side by side as one (vocab, 2 tau) table
- * to snb_sample_encode / a (P, 2 tau) `t` to snb_encode_points / snb_mlp_forward_fp32 (tau = 8 there), t_s lands in aux
- * columns 8..11 and its gradient in columns 8..11 of g_aux. */
+ * to snb_sample_encode / a (P, 2 tau) `t` to snb_encode_points / snb_mlp_forward_fp32 (their `tau` argument is 2 tau then),
+ * t_s lands in aux columns 4+tau..4+2tau and its gradient in the same columns of g_aux.
+ * SNB_VARIANT_FULL_FEATURES (SatNeRF and the semantic model): `fc_use_full_features` - the head hidden layers and sky_color
+ * are fc_units = 512 wide instead of 256 (satnerf.py:123-124, rs_semantic.py:147-148).
+ * t_embedding_tau: width of the per-image embedding (`t_embedding_tau`, 4 in every shipped TOML; 0 = 4): at most 12, 6 with
+ * SNB_VARIANT_SEPARATE_TJ_S - the per-ray inputs travel in 16 aux columns [1 | sun_d | t | t_s]. */
 enum { SNB_VARIANT_TJ_FOR_S = 1, SNB_VARIANT_TJ_INSTEAD_OF_BETA = 2, SNB_VARIANT_SEPARATE_BETA_S = 4,
-       SNB_VARIANT_SEPARATE_TJ_S = 8 };
-int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid, int variant);
+       SNB_VARIANT_SEPARATE_TJ_S = 8, SNB_VARIANT_FULL_FEATURES = 16 };
+int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid, int variant, int t_embedding_tau);
 void snb_model_destroy(snb_model* m);
 /* number of fp32 parameters / the offset table: parameters live in ONE flat fp32 buffer in the
  * reference state_dict order; names[i], offsets[i], rows[i], cols[i]. */

@@ -99,6 +99,12 @@ CASES = [
     # a "_ts" name: every head variant at once - use_tj_for_s + use_separate_beta_for_s + use_separate_tj_for_semantic (the
     # semantic head and the semantic uncertainty head read the second embedding models["t_s"])
     ("sem_c6_s8_ts", "semantic", 6, 512, 16, 8, 0.05, 14),
+    # fc_use_full_features (512-wide head hidden layers and sky_color, satnerf.py:123-124) and other embedding widths
+    ("sem_c6_s8_full", "semantic", 6, 512, 16, 8, 0.05, 15),
+    ("sat_s8_full", "satnerf", 0, 512, 16, 8, 0.05, 16),
+    ("sem_c6_s8_tau8", "semantic", 6, 512, 16, 8, 0.05, 17),
+    ("sat_s8_tau2", "satnerf", 0, 512, 16, 8, 0.05, 18),
+    ("sem_c6_s8_full_tau6_ts", "semantic", 6, 512, 16, 8, 0.05, 19),   # everything at once
 ]
 
 GOLDEN_KEYS = ["rgb_coarse", "depth_coarse", "weights_coarse", "transparency_coarse",
@@ -107,10 +113,7 @@ GOLDEN_KEYS = ["rgb_coarse", "depth_coarse", "weights_coarse", "transparency_coa
 
 
 def case_inputs(name, kind, C, feat, n, s, sc, seed):
-    tj = name.endswith("_tj")
-    ts = name.endswith("_ts")
-    spec = O.ModelSpec(kind=kind, n_classes=C, feat=feat, tj_for_s=tj or ts, tj_instead_of_beta=tj,
-                       separate_beta_s=name.endswith("_bs") or ts, separate_tj_s=ts)
+    spec = O.spec_for_case(name, kind, C, feat)
     params, emb = O.make_params(spec, seed=seed, trained_like=name.endswith("trained"))
     rays, extras = O.synthetic_rays(n, seed=seed)
     rng = np.random.Generator(np.random.PCG64(seed + 77))

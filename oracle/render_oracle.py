@@ -235,6 +235,17 @@ def _lin(p, name, x):
     return F.linear(x, p[name + ".weight"], p[name + ".bias"])
 
 
+def spec_for_case(name: str, kind: str, n_classes: int, feat: int = 512) -> ModelSpec:
+    """the architecture a golden case's NAME asks for (oracle/pin_against_reference.py CASES, tests/helpers.py GOLDEN_CASES):
+    tokens `tj` (use_tj_for_s + use_tj_instead_of_beta), `bs` (use_separate_beta_for_s), `ts` (use_tj_for_s +
+    use_separate_beta_for_s + use_separate_tj_for_semantic), `full` (fc_use_full_features), `tauN` (t_embedding_tau = N)"""
+    tok = name.split("_")
+    tj, ts, bs = "tj" in tok, "ts" in tok, "bs" in tok
+    tau = next((int(t[3:]) for t in tok if t.startswith("tau") and t[3:].isdigit()), 4)
+    return ModelSpec(kind=kind, n_classes=n_classes, feat=feat, tau=tau, full_features="full" in tok, tj_for_s=tj or ts,
+                     tj_instead_of_beta=tj, separate_beta_s=bs or ts, separate_tj_s=ts)
+
+
 def make_emb_s(spec: ModelSpec, seed: int = 0, dtype=torch.float32) -> torch.Tensor:
     """the second embedding table models["t_s"] of `use_separate_tj_for_semantic` (semantic/pipelines/rs_semantic.py:72-77):
     N(0,1) like nn.Embedding's initialiser, from its own deterministic stream"""

@@ -18,7 +18,7 @@ MODEL_SATNERF, MODEL_SEMANTIC, MODEL_NERF, MODEL_SNERF = 0, 1, 2, 3
 K1_KIND = {0: 0, 1: 1, 2: 1, 3: 0}
 HEADS_ALL, HEADS_SOLAR, HEADS_DEPTH = 63, 5, 1
 COMPOSITE_NO_CLAMP, COMPOSITE_BETA_S = 1, 2
-VARIANT_TJ_FOR_S, VARIANT_TJ_INSTEAD_OF_BETA, VARIANT_SEPARATE_BETA_S, VARIANT_SEPARATE_TJ_S = 1, 2, 4, 8
+VARIANT_TJ_FOR_S, VARIANT_TJ_INSTEAD_OF_BETA, VARIANT_SEPARATE_BETA_S, VARIANT_SEPARATE_TJ_S, VARIANT_FULL_FEATURES = 1, 2, 4, 8, 16
 EPI_SIN, EPI_LINEAR, EPI_MUL, EPI_HEADOUT, EPI_F32ROWS, EPI_WGRAD = range(6)
 
 _vp, _i, _i64, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
@@ -31,7 +31,7 @@ SIGNATURES = {
     "snb_sample_encode": (_i, [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
                                _vp, _vp, _vp, _vp, _vp, _vp]),
     "snb_encode_points": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "snb_model_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i]),
+    "snb_model_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
     "snb_model_destroy": (None, [_vp]),
     "snb_model_param_count": (_i64, [_vp]),
     "snb_model_num_tensors": (_i, [_vp]),

@@ -33,7 +33,8 @@
 namespace snb {
 
 constexpr int F = 512;    // fc_units (configs/pipelines/*.toml: fc_units = 512)
-constexpr int FL = 256;   // feat_last = fc_units / 2 (fc_use_full_features = false)
+// feat_last (the width of the head hidden layers): fc_units / 2, or fc_units with fc_use_full_features - snb_model::fl;
+// the functions below read it into a local FL
 constexpr int PACK_SPLITS = 4;   // K-splits of the folded-layer product W' = W_h1 W_f at pack time
 constexpr int LAYERS = 8; // fc_layers, skip at layer 4
 
@@ -56,6 +57,7 @@ struct PackJob {
 
 struct snb_model {
   int kind, n_classes, sem_sigmoid;
+  int fl;   // feat_last: 256, or 512 with SNB_VARIANT_FULL_FEATURES
   int k0, enc_ld, w0_ld, hhw, n_out, tau;   // enc_ld: K1 row width; w0_ld: packed K of the first layer
   int hh_rgb, hh_beta, hh_sem, hh_bs, hh_sun;
   int beta_s;   // use_separate_beta_for_s: a second uncertainty head (packed column 9, head pre-activation row 6)
@@ -377,6 +379,7 @@ static long long take(long long& cursor, long long elems) {
 }
 
 static void build_layout(snb_model* m) {
+  const int FL = m->fl;
   const int k0 = m->k0, hhw = m->hhw, tau = m->tau, C = m->n_classes;
   const bool sem = m->kind == SNB_MODEL_SEMANTIC;
   const bool nerf = m->kind == SNB_MODEL_NERF;   // nerf.py:118-160: trunk, sigma, feats, rgb(f | dir) only
@@ -390,7 +393,7 @@ static void build_layout(snb_model* m) {
   const bool bs = m->beta_s != 0;   // semantic_beta_from_xyz (rs_semantic.py:228-237): cat(f, t) -> 256 -> 1, softplus
   // use_separate_tj_for_semantic (rs_semantic.py:300-301,334-335): the semantic head and the semantic uncertainty head read
   // a SECOND embedding t_s: aux columns 8..11 (the caller passes the two tables side by side as one (vocab, 8) table)
-  const int ts_col = (sem && (m->variant & SNB_VARIANT_SEPARATE_TJ_S)) ? 8 : 4;
+  const int ts_col = (sem && (m->variant & SNB_VARIANT_SEPARATE_TJ_S)) ? 4 + tau : 4;   // aux = [1 | sun_d | t | t_s]
   // ---- flat fp32 parameter order = reference state_dict order ----
   m->n_params = 0;
   for (int i = 0; i < LAYERS; ++i) {
@@ -676,6 +679,7 @@ static bool use_chain() {
 }
 
 static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
+  const int FL = m->fl;
   Workspace w;
   memset(&w, 0, sizeof(w));
   size_t cur = 0;
@@ -724,6 +728,7 @@ static Workspace layout_workspace(const snb_model* m, int64_t P, int train) {
 // solar-correction pass in rows [P, P + Psc) of ONE workspace (snb_mlp_forward_with_solar): the two passes run their own
 // chained launches over their row ranges, and the weight gradients of the layers both passes share run once over all rows.
 static Workspace shift_rows(const snb_model* m, Workspace w, long long r) {
+  const int FL = m->fl;
   const size_t n = (size_t)r;
   for (int i = 0; i < 8; ++i) {
     w.h[i] += n * F * 2;
@@ -1055,16 +1060,24 @@ using namespace snb;
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
-extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid, int variant) {
+extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid, int variant,
+                                int t_embedding_tau) {
   SNB_CHECK_ARG(out != nullptr, SNB_ERR_INVALID, "model_create: null out");
   SNB_CHECK_ARG(model_kind >= SNB_MODEL_SATNERF && model_kind <= SNB_MODEL_SNERF, SNB_ERR_INVALID, "model_create: bad kind %d",
                 model_kind);
   if (model_kind != SNB_MODEL_SEMANTIC) n_classes = 0;
-  SNB_CHECK_ARG(variant == 0 || model_kind == SNB_MODEL_SEMANTIC, SNB_ERR_UNSUPPORTED,
+  SNB_CHECK_ARG((variant & ~SNB_VARIANT_FULL_FEATURES) == 0 || model_kind == SNB_MODEL_SEMANTIC, SNB_ERR_UNSUPPORTED,
                 "model_create: head-input variants exist for the semantic model only");
+  SNB_CHECK_ARG(!(variant & SNB_VARIANT_FULL_FEATURES) || model_kind == SNB_MODEL_SEMANTIC || model_kind == SNB_MODEL_SATNERF,
+                SNB_ERR_UNSUPPORTED, "model_create: fc_use_full_features exists for SatNeRF and the semantic model (satnerf.py:123-124)");
   SNB_CHECK_ARG((variant & ~(SNB_VARIANT_TJ_FOR_S | SNB_VARIANT_TJ_INSTEAD_OF_BETA | SNB_VARIANT_SEPARATE_BETA_S |
-                             SNB_VARIANT_SEPARATE_TJ_S)) == 0,
+                             SNB_VARIANT_SEPARATE_TJ_S | SNB_VARIANT_FULL_FEATURES)) == 0,
                 SNB_ERR_UNSUPPORTED, "model_create: variant bits %d not implemented", variant);
+  // the per-ray columns of the head inputs travel in the 16 aux columns [1 | sun_d (3) | t (tau) | t_s (tau)]
+  if (t_embedding_tau <= 0) t_embedding_tau = 4;
+  SNB_CHECK_ARG(t_embedding_tau <= ((variant & SNB_VARIANT_SEPARATE_TJ_S) ? 6 : 12), SNB_ERR_UNSUPPORTED,
+                "model_create: t_embedding_tau %d does not fit the 16 per-ray columns (max 12, 6 with a second embedding)",
+                t_embedding_tau);
   SNB_CHECK_ARG(!(variant & SNB_VARIANT_SEPARATE_BETA_S) || n_classes <= 9, SNB_ERR_UNSUPPORTED,
                 "model_create: the separate semantic uncertainty head leaves 9 of the 16 head rows for classes (n_classes %d)",
                 n_classes);
@@ -1076,7 +1089,9 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   m->sem_sigmoid = semantic_sigmoid;
   m->variant = variant;
   m->beta_s = (variant & SNB_VARIANT_SEPARATE_BETA_S) ? 1 : 0;
-  m->tau = 4;  // t_embedding_tau (configs/pipelines/*.toml)
+  m->tau = t_embedding_tau;  // 4 in configs/pipelines/*.toml
+  m->fl = (variant & SNB_VARIANT_FULL_FEATURES) ? F : F / 2;
+  const int FL = m->fl;
   const bool enc60 = model_kind == SNB_MODEL_SEMANTIC || model_kind == SNB_MODEL_NERF;   // positional encoding of xyz (10 frequencies)
   m->k0 = enc60 ? 60 : 3;
   m->enc_ld = enc60 ? 128 : 64;
@@ -1211,6 +1226,7 @@ extern "C" int snb_mlp_forward_with_solar(const snb_model* m, const void* packed
 static int mlp_forward_rows(const snb_model* m, const void* packed, char* ws, const Workspace& w, long long P, const void* enc,
                             const void* aux, const float* sky, int rows_per_ray, int head_mask, int train, float* out,
                             void* stream, ChainPlan* plan, bool plan_started) {
+  const int FL = m->fl;
   const __nv_bfloat16* pk = reinterpret_cast<const __nv_bfloat16*>(packed);
   const float* pb = reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + (size_t)m->packed_bf16_elems * 2);
   auto H = [&](int i) { return (void*)(ws + w.h[i]); };
@@ -1345,6 +1361,7 @@ extern "C" int snb_mlp_backward_with_solar(const snb_model* m, const void* packe
 static int mlp_backward_rows(const snb_model* m, const void* packed, char* ws, const Workspace& w, long long P, long long Psc,
                              const void* enc, const void* aux, const float* out, const float* g_out, int head_mask, float* grads,
                              float* g_aux, void* const* bucket_events, cudaStream_t st) {
+  const int FL = m->fl;
   const int sms = num_sms();
   if (sms <= 0) return SNB_ERR_NO_DEVICE;
   const __nv_bfloat16* pk = reinterpret_cast<const __nv_bfloat16*>(packed);
@@ -1525,13 +1542,13 @@ namespace {
 constexpr long long F32_CHUNK = 65536;   // points per pass over the layers (bounds the fp32 activation scratch)
 constexpr int F32_ENC_LD = 64;
 // per-point scratch floats: enc | hA | hB | f | g1 | g2
-constexpr long long F32_ROW_FLOATS = F32_ENC_LD + 3 * snb::F + 2 * snb::FL;
+static long long f32_row_floats(const snb_model* m) { return F32_ENC_LD + 3 * snb::F + 2 * m->fl; }
 }  // namespace
 
 extern "C" size_t snb_mlp_fp32_workspace_bytes(const snb_model* m, int64_t n_points) {
   if (!m || n_points <= 0) return 0;
   const long long rows = n_points < F32_CHUNK ? n_points : F32_CHUNK;
-  return (size_t)rows * F32_ROW_FLOATS * sizeof(float);
+  return (size_t)rows * f32_row_floats(m) * sizeof(float);
 }
 
 extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, void* workspace, size_t workspace_bytes,
@@ -1549,6 +1566,7 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
   SNB_CHECK_ARG(workspace_bytes >= snb_mlp_fp32_workspace_bytes(m, n_points), SNB_ERR_WORKSPACE,
                 "mlp_forward_fp32: workspace %zu too small", workspace_bytes);
   cudaStream_t st = (cudaStream_t)stream;
+  const int FL = m->fl;
   const bool sem = m->kind == SNB_MODEL_SEMANTIC;
   const int hid = nerf ? F32_RELU : F32_SIN;
   const int k0 = m->k0, tau = m->tau, n_out = m->n_out, C = m->n_classes;

@@ -23,13 +23,22 @@ ray_param_bwd_kernel(const float* __restrict__ extras, const float* __restrict__
   __shared__ float fin[16];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nv = 3 + tau;
-  float a_w2[3] = {0.f, 0.f, 0.f}, a_w1[3] = {0.f, 0.f, 0.f}, a_b1 = 0.f, a_b2[3] = {0.f, 0.f, 0.f};
-  const bool hid = tid < hidden;
-  float w1r[3] = {0.f, 0.f, 0.f}, b1r = 0.f, w2r[3] = {0.f, 0.f, 0.f};
-  if (hid && sky) {
-    w1r[0] = w1[tid * 3]; w1r[1] = w1[tid * 3 + 1]; w1r[2] = w1[tid * 3 + 2];
-    b1r = b1[tid];
-    w2r[0] = w2[tid]; w2r[1] = w2[hidden + tid]; w2r[2] = w2[2 * hidden + tid];
+  // hidden unit(s) of this thread: tid (and tid + 256 with fc_use_full_features, hidden = 512)
+  constexpr int HPT = 2;
+  float a_w2[HPT][3], a_w1[HPT][3], a_b1[HPT], a_b2[3] = {0.f, 0.f, 0.f};
+  float w1r[HPT][3], b1r[HPT], w2r[HPT][3];
+#pragma unroll
+  for (int u = 0; u < HPT; ++u) {
+    const int h = tid + 256 * u;
+    const bool on = sky && h < hidden;
+    a_b1[u] = 0.f;
+    b1r[u] = on ? b1[h] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a_w2[u][c] = a_w1[u][c] = 0.f;
+      w1r[u][c] = on ? w1[h * 3 + c] : 0.f;
+      w2r[u][c] = on ? w2[c * hidden + h] : 0.f;
+    }
   }
   for (int ray = blockIdx.x; ray < n_rays; ray += gridDim.x) {
     float v[16];
@@ -65,32 +74,49 @@ ray_param_bwd_kernel(const float* __restrict__ extras, const float* __restrict__
       ti = min(max(ti, 0), vocab - 1);
       atomicAdd(g_t_table + (size_t)ti * tau + tid, fin[3 + tid]);
     }
-    if (sky && hid) {
+    if (sky) {
       const float sx = e[0], sy = e[1], sz = e[2];
-      const float y = fmaxf(fmaf(w1r[2], sz, fmaf(w1r[1], sy, fmaf(w1r[0], sx, b1r))), 0.f);
-      float dy = 0.f;
+      float d[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float o = sky[(size_t)ray * 3 + c];
-        const float d = fin[c] * o * (1.0f - o);
-        a_w2[c] += d * y;
-        if (tid == 0) a_b2[c] += d;
-        dy += d * w2r[c];
+        d[c] = fin[c] * o * (1.0f - o);
+        if (tid == 0) a_b2[c] += d[c];
       }
-      if (y <= 0.f) dy = 0.f;
-      a_w1[0] += dy * sx; a_w1[1] += dy * sy; a_w1[2] += dy * sz;
-      a_b1 += dy;
+#pragma unroll
+      for (int u = 0; u < HPT; ++u) {
+        if (tid + 256 * u < hidden) {
+          const float y = fmaxf(fmaf(w1r[u][2], sz, fmaf(w1r[u][1], sy, fmaf(w1r[u][0], sx, b1r[u]))), 0.f);
+          float dy = 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            a_w2[u][c] += d[c] * y;
+            dy += d[c] * w2r[u][c];
+          }
+          if (y <= 0.f) dy = 0.f;
+          a_w1[u][0] += dy * sx; a_w1[u][1] += dy * sy; a_w1[u][2] += dy * sz;
+          a_b1[u] += dy;
+        }
+      }
     }
     __syncthreads();
   }
-  if (sky && hid) {
+  if (sky) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      atomicAdd(gw2 + c * hidden + tid, a_w2[c]);
-      atomicAdd(gw1 + tid * 3 + c, a_w1[c]);
-      if (tid == 0) atomicAdd(gb2 + c, a_b2[c]);
+    for (int u = 0; u < HPT; ++u) {
+      const int h = tid + 256 * u;
+      if (h < hidden) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          atomicAdd(gw2 + c * hidden + h, a_w2[u][c]);
+          atomicAdd(gw1 + h * 3 + c, a_w1[u][c]);
+        }
+        atomicAdd(gb1 + h, a_b1[u]);
+      }
     }
-    atomicAdd(gb1 + tid, a_b1);
+    if (tid == 0)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) atomicAdd(gb2 + c, a_b2[c]);
   }
 }
 
@@ -143,9 +169,20 @@ extern "C" int snb_ray_param_backward(const snb_model* m, const float* params, c
   SNB_CHECK_ARG(w1 >= 0 && b1 >= 0 && w2 >= 0 && b2 >= 0, SNB_ERR_INVALID, "ray_param_backward: sky tensors missing");
   int sms = num_sms();
   if (sms <= 0) return SNB_ERR_NO_DEVICE;
+  int hidden = 0, w1_cols = 0;
+  {
+    const int nt = snb_model_num_tensors(m);
+    for (int i = 0; i < nt; ++i) {
+      const char* name;
+      int64_t off;
+      snb_model_tensor_info(m, i, &name, &off, &hidden, &w1_cols);
+      if (strcmp(name, "sky_color.0.weight") == 0) break;
+    }
+  }
+  SNB_CHECK_ARG(hidden > 0 && hidden <= 512, SNB_ERR_UNSUPPORTED, "ray_param_backward: sky_color hidden width %d", hidden);
   int blocks = n_rays < sms * 4 ? n_rays : sms * 4;
   ray_param_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      extras, sky, g_out, g_aux, n_rays, n_samples, n_out, tau, vocab, 256, params + w1, params + b1, params + w2,
+      extras, sky, g_out, g_aux, n_rays, n_samples, n_out, tau, vocab, hidden, params + w1, params + b1, params + w2,
       grads + w1, grads + b1, grads + w2, grads + b2, g_t_table);
   return launch_status("ray_param_bwd_kernel");
 }

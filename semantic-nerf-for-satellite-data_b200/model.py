@@ -25,17 +25,20 @@ class SnbMLP(torch.nn.Module):
 
     def __init__(self, kind: int, n_classes: int, semantic_sigmoid: bool, tau: int, cfgs=None, variant: int = 0):
         super().__init__()
-        if tau != 4:
-            raise _lib.SnbError("libsnb implements t_embedding_tau = 4 (the value in every shipped config)")
+        tau = int(tau)
+        max_tau = 6 if (variant & _lib.VARIANT_SEPARATE_TJ_S) else 12
+        if kind in (MODEL_SATNERF, MODEL_SEMANTIC) and not 1 <= tau <= max_tau:
+            raise _lib.SnbError(f"t_embedding_tau = {tau}: libsnb carries the per-ray head inputs in 16 columns [1 | sun_d | t | t_s], "
+                                f"so the embedding may be 1..{max_tau} wide here")
         lib = _lib.load()
         h = C.c_void_p()
-        check(lib.snb_model_create(C.byref(h), kind, n_classes, 1 if semantic_sigmoid else 0, variant), "snb_model_create")
+        check(lib.snb_model_create(C.byref(h), kind, n_classes, 1 if semantic_sigmoid else 0, variant, tau), "snb_model_create")
         self._h = h
         self.kind = kind
         self.semantic_n_classes = n_classes          # read by the reference's inference(), rs_semantic.py:95
         self.beta_s = 1 if (variant & _lib.VARIANT_SEPARATE_BETA_S) else 0   # column 9 = the separate semantic uncertainty
         # use_separate_tj_for_semantic: the semantic heads read a second embedding t_s; the kernels take [t | t_s] as ONE
-        # (.., 2 tau) tensor (aux columns 4..7 and 8..11), the gradient comes back the same way and autograd splits it
+        # (.., 2 tau) tensor (aux columns 4..4+tau and 4+tau..4+2tau), the gradient comes back the same way and autograd splits it
         self.sep_ts = bool(variant & _lib.VARIANT_SEPARATE_TJ_S)
         self.number_of_outputs = 9 + self.beta_s + n_classes       # satnerf.py:120 / rs_semantic.py:291-311
         self.n_out_kernel = 9 + self.beta_s + n_classes            # columns of the packed tensor the kernels write
@@ -184,9 +187,9 @@ class SatNeRFB200(SnbMLP):
         if layers != 8 or feat != 512 or list(skips) != [4] or mapping or not siren:
             raise _lib.SnbError("libsnb implements the shipped SatNeRF configuration: 8x512 SIREN, skip [4], "
                                 "raw-xyz input (configs/pipelines/satnerf.toml)")
-        if cfgs is not None and getattr(cfgs.pipeline, "fc_use_full_features", False):
-            raise _lib.SnbError("fc_use_full_features=true is not implemented")
-        super().__init__(MODEL_SATNERF, 0, True, t_embedding_dims, cfgs)
+        # fc_use_full_features (satnerf.py:123-124): the head hidden layers and sky_color are fc_units wide instead of half
+        full = cfgs is not None and bool(getattr(cfgs.pipeline, "fc_use_full_features", False))
+        super().__init__(MODEL_SATNERF, 0, True, t_embedding_dims, cfgs, _lib.VARIANT_FULL_FEATURES if full else 0)
         self.layers, self.skips = layers, list(skips)
 
 
@@ -195,16 +198,16 @@ class RSSemanticNeRFB200(SnbMLP):
 
     def __init__(self, cfgs, dataset_semantic):
         p = cfgs.pipeline
-        unsupported = [k for k in ("fc_use_full_features",) if getattr(p, k, False)]
-        if unsupported or p.fc_layers != 8 or p.fc_units != 512 or list(p.fc_skips) != [4] \
+        if p.fc_layers != 8 or p.fc_units != 512 or list(p.fc_skips) != [4] \
                 or p.activation_function != "siren" or p.mapping_pos_n_freq != 10:
-            raise _lib.SnbError(f"libsnb implements the shipped rs_semantic.toml architecture; unsupported: {unsupported}")
+            raise _lib.SnbError("libsnb implements the shipped rs_semantic.toml trunk: 8 x 512 SIREN, skip [4], 10 frequencies")
         sig = p.semantic_activation_function == "sigmoid"
         # head-input variants: t as an extra input of the semantic head / of the colour head (rs_semantic.py:186-215)
         variant = (_lib.VARIANT_TJ_FOR_S if getattr(p, "use_tj_for_s", False) else 0) | \
                   (_lib.VARIANT_TJ_INSTEAD_OF_BETA if getattr(p, "use_tj_instead_of_beta", False) else 0) | \
                   (_lib.VARIANT_SEPARATE_BETA_S if getattr(p, "use_separate_beta_for_s", False) else 0) | \
-                  (_lib.VARIANT_SEPARATE_TJ_S if getattr(p, "use_separate_tj_for_semantic", False) else 0)
+                  (_lib.VARIANT_SEPARATE_TJ_S if getattr(p, "use_separate_tj_for_semantic", False) else 0) | \
+                  (_lib.VARIANT_FULL_FEATURES if getattr(p, "fc_use_full_features", False) else 0)   # rs_semantic.py:147-148
         super().__init__(MODEL_SEMANTIC, int(dataset_semantic.semantic_n_classes), sig, p.t_embedding_tau, cfgs, variant)
         self.cfg = p
         self.layers, self.skips = p.fc_layers, list(p.fc_skips)

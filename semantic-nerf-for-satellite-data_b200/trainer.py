@@ -39,7 +39,8 @@ from .losses import (DepthLoss, NerfLoss, SatNerfLoss, SemanticCarRegLoss, Seman
 from .model import NeRFB200, RSSemanticNeRFB200, SatNeRFB200, ShadowNeRFB200
 from .renderer import B200Renderer
 
-EMB_PAD = 512   # floats reserved in front of the model parameters for the embedding tables: t at 0, t_s (if any) at 256
+EMB_PAD = 2048  # floats reserved in front of the model parameters for the embedding tables: t at 0, t_s (if any) at 1024
+                # (vocabulary 50 x t_embedding_tau <= 12 = 600 floats per table)
 
 
 def default_cfgs(kind: str = "semantic", n_samples: int = 64, sc_lambda: float = 0.05, **over):

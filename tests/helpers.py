@@ -41,16 +41,19 @@ GOLDEN_CASES = [
     ("sem_c6_s8_tj", "semantic", 6, 512, 16, 8, 0.05, 12),      # use_tj_for_s + use_tj_instead_of_beta
     ("sem_c9_s8_bs", "semantic", 9, 512, 16, 8, 0.05, 13),      # use_separate_beta_for_s
     ("sem_c6_s8_ts", "semantic", 6, 512, 16, 8, 0.05, 14),      # use_tj_for_s + use_separate_beta_for_s + use_separate_tj_for_semantic
+    # fc_use_full_features (512-wide head hidden layers and sky_color, satnerf.py:123-124) and other embedding widths
+    ("sem_c6_s8_full", "semantic", 6, 512, 16, 8, 0.05, 15),
+    ("sat_s8_full", "satnerf", 0, 512, 16, 8, 0.05, 16),
+    ("sem_c6_s8_tau8", "semantic", 6, 512, 16, 8, 0.05, 17),
+    ("sat_s8_tau2", "satnerf", 0, 512, 16, 8, 0.05, 18),
+    ("sem_c6_s8_full_tau6_ts", "semantic", 6, 512, 16, 8, 0.05, 19),   # everything at once
 ]
 
 
 def golden_inputs(case):
     from oracle import render_oracle as O
     name, kind, C, feat, n, s, sc, seed = case
-    tj = name.endswith("_tj")
-    ts = name.endswith("_ts")
-    spec = O.ModelSpec(kind=kind, n_classes=C, feat=feat, tj_for_s=tj or ts, tj_instead_of_beta=tj,
-                       separate_beta_s=name.endswith("_bs") or ts, separate_tj_s=ts)
+    spec = O.spec_for_case(name, kind, C, feat)
     params, emb = O.make_params(spec, seed=seed, trained_like=name.endswith("trained"))
     rays, extras = O.synthetic_rays(n, seed=seed)
     rng = np.random.Generator(np.random.PCG64(seed + 77))

@@ -106,10 +106,12 @@ def test_gemm_rejects_bad_arguments():
 # ------------------------------------------------------------------------------------------------
 # K1: sampling + encoding
 # ------------------------------------------------------------------------------------------------
-def _model(kind, C, seed=3, S=64, sc=0.05, trained_like=False, tj=False, bs=False, ts=False):
-    """ts: every head variant at once incl. the second embedding (the caller adds models["t_s"] = O.make_emb_s(spec, seed))"""
+def _model(kind, C, seed=3, S=64, sc=0.05, trained_like=False, tj=False, bs=False, ts=False, spec=None):
+    """ts: every head variant at once incl. the second embedding (the caller adds models["t_s"] = O.make_emb_s(spec, seed));
+    spec: a ready ModelSpec (fc_use_full_features, t_embedding_tau, ...) instead of the flags"""
     from semnerf_b200.model import RSSemanticNeRFB200, SatNeRFB200
-    spec = O.ModelSpec(kind=kind, n_classes=C, tj_for_s=tj or ts, tj_instead_of_beta=tj, separate_beta_s=bs or ts, separate_tj_s=ts)
+    if spec is None:
+        spec = O.ModelSpec(kind=kind, n_classes=C, tj_for_s=tj or ts, tj_instead_of_beta=tj, separate_beta_s=bs or ts, separate_tj_s=ts)
     params, emb = O.make_params(spec, seed=seed, trained_like=trained_like)
     cfgs = make_cfgs(spec, S, sc)
     if kind == "snerf":
@@ -120,7 +122,7 @@ def _model(kind, C, seed=3, S=64, sc=0.05, trained_like=False, tj=False, bs=Fals
         model = NeRFB200().to(DEV)
     else:
         model = (RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": C})()) if kind == "semantic"
-                 else SatNeRFB200(cfgs)).to(DEV)
+                 else SatNeRFB200(cfgs, t_embedding_dims=spec.tau)).to(DEV)
     model.load_state_dict(params)
     t = torch.nn.Embedding(spec.vocab, spec.tau).to(DEV)
     t.weight.data.copy_(emb)

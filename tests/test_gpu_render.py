@@ -20,16 +20,19 @@ def _cos(a, b):
     return float(a @ b) / max(1e-300, float(a.norm() * b.norm()))
 
 
-@pytest.mark.parametrize("kind,C", [("semantic", 6), ("semantic", 5), ("satnerf", 0)])
-def test_model_forward_backward_matches_oracle(kind, C):
+@pytest.mark.parametrize("kind,C,name", [("semantic", 6, ""), ("semantic", 5, ""), ("satnerf", 0, ""),
+                                         # fc_use_full_features (512-wide head layers, sky_color) and other embedding widths
+                                         ("semantic", 6, "full"), ("satnerf", 0, "full"), ("semantic", 6, "tau8"),
+                                         ("satnerf", 0, "tau2"), ("semantic", 6, "tau12"), ("satnerf", 0, "full_tau1")])
+def test_model_forward_backward_matches_oracle(kind, C, name):
     """Model.forward(xyz, sun_d, t) -> (B, 9+C): per-head outputs and every parameter gradient."""
     _lib_or_fail()
-    spec, params, emb, cfgs, model, t = _model(kind, C, seed=1)
+    spec, params, emb, cfgs, model, t = _model(kind, C, seed=1, spec=O.spec_for_case(name, kind, C))
     P = 1000
     g = torch.Generator().manual_seed(0)
     xyz = torch.rand(P, 3, generator=g) * 2 - 1
     sun = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=1)
-    tt = torch.randn(P, 4, generator=g)
+    tt = torch.randn(P, spec.tau, generator=g)
     p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
     tt64 = tt.double().requires_grad_(True)
     ref = O.mlp_forward(p64, spec, xyz.double(), sun.double(), tt64)
@@ -60,7 +63,7 @@ def test_render_rays_against_reference_golden(case):
     name, kind, C, feat, n, s, sc, seed = case
     spec, params, emb, rays, extras, u, gold = golden_inputs(case)
     _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"),
-                                     tj=name.endswith("_tj"), bs=name.endswith("_bs"), ts=name.endswith("_ts"))
+                                     spec=spec)
     renderer = B200Renderer(cfgs)
     with torch.no_grad():
         models = {"coarse": model} if kind in ("snerf", "nerf") else {"coarse": model, "t": t}
@@ -293,7 +296,7 @@ def test_fp32_mode_render_rays_against_reference_golden(case):
     name, kind, C, feat, n, s, sc, seed = case
     spec, params, emb, rays, extras, u, gold = golden_inputs(case)
     _, _, _, cfgs, model, t = _model(kind, C, seed=seed, S=s, sc=sc, trained_like=name.endswith("trained"),
-                                     tj=name.endswith("_tj"), bs=name.endswith("_bs"), ts=name.endswith("_ts"))
+                                     spec=spec)
     renderer = B200Renderer(cfgs)
     with torch.no_grad():
         models = {"coarse": model} if kind in ("snerf", "nerf") else {"coarse": model, "t": t}
@@ -601,7 +604,7 @@ def test_separate_semantic_embedding_gradients_and_training():
     render_loss-under-autograd step take the same first step and all train."""
     from semnerf_b200 import synth
     from semnerf_b200.renderer import RSSemanticB200Rendering
-    from semnerf_b200.trainer import Trainer, default_cfgs
+    from semnerf_b200.trainer import EMB_PAD, Trainer, default_cfgs
     _lib_or_fail()
     S, n, C = 64, 384, 6
     spec, params, emb, cfgs, model, t = _model("semantic", C, seed=3, S=S, ts=True)
@@ -659,7 +662,7 @@ def test_separate_semantic_embedding_gradients_and_training():
         ts0 = tr.models["t_s"].weight.detach().clone()
         losses = [tr.training_step(batch, epoch=3).item()]
         g = tr.gbuf.detach().clone()      # [t | t_s | model] gradients of the first step
-        first[mode] = (losses[0], g[:256], g[256:512], g[512:])
+        first[mode] = (losses[0], g[:EMB_PAD // 2], g[EMB_PAD // 2:EMB_PAD], g[EMB_PAD:])
         losses += [tr.training_step(batch, epoch=3).item() for _ in range(11)]
         assert all(l == l for l in losses) and losses[-1] < losses[0], mode
         assert not torch.equal(ts0, tr.models["t_s"].weight.detach()), mode   # the optimiser steps the second table too

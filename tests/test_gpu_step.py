@@ -27,12 +27,14 @@ def _cos(a, b):
     return float(a @ b) / max(1e-300, float(a.norm() * b.norm()))
 
 
-def _trainer(kind, C, S, seed, **kw):
-    """a Trainer whose parameters are the oracle's deterministic ones (so the oracle can be evaluated on the same weights)"""
+def _trainer(kind, C, S, seed, name="", **kw):
+    """a Trainer whose parameters are the oracle's deterministic ones (so the oracle can be evaluated on the same weights);
+    name: architecture tokens of O.spec_for_case (`full` = fc_use_full_features, `tauN` = t_embedding_tau)"""
     from semnerf_b200.trainer import Trainer, default_cfgs
-    cfgs = default_cfgs(kind, n_samples=S, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=2)
+    spec = O.spec_for_case(name, kind, C)
+    cfgs = default_cfgs(kind, n_samples=S, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=2,
+                        fc_use_full_features=spec.full_features, t_embedding_tau=spec.tau)
     tr = Trainer(cfgs, kind, C, device=DEV, car_index=CAR, seed=0, **kw)
-    spec = O.ModelSpec(kind=kind, n_classes=C)
     params, emb = O.make_params(spec, seed=seed)
     tr.models["coarse"].load_state_dict(params)
     if "t" in tr.models:
@@ -62,19 +64,22 @@ def _to_dev(b):
     return {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in b.items()}
 
 
-@pytest.mark.parametrize("kind,C,epoch,with_depth,with_mask,S",
-                         [("semantic", 6, 3, True, True, 64), ("semantic", 5, 1, False, False, 64),
-                          ("satnerf", 0, 3, True, False, 64), ("snerf", 0, 3, False, False, 64),
-                          ("semantic", 6, 3, True, True, 8)])
+@pytest.mark.parametrize("kind,C,epoch,with_depth,with_mask,S,name",
+                         [("semantic", 6, 3, True, True, 64, ""), ("semantic", 5, 1, False, False, 64, ""),
+                          ("satnerf", 0, 3, True, False, 64, ""), ("snerf", 0, 3, False, False, 64, ""),
+                          ("semantic", 6, 3, True, True, 8, ""),
+                          # fc_use_full_features / other embedding widths
+                          ("semantic", 6, 3, True, True, 64, "full"), ("satnerf", 0, 3, True, False, 64, "full_tau2"),
+                          ("semantic", 6, 3, False, True, 64, "tau8")])
 @pytest.mark.parametrize("direct", [True, False])
-def test_fused_training_step_matches_the_oracle(kind, C, epoch, with_depth, with_mask, S, direct):
+def test_fused_training_step_matches_the_oracle(kind, C, epoch, with_depth, with_mask, S, name, direct):
     """The fused K3 + loss kernel (through the direct step and through render_loss under autograd) against the ORACLE'S loss
     stack - itself pinned term by term to the reference's loss modules: every term, the total, every parameter gradient, the
     embedding gradient.  The oracle is evaluated on the z_vals the kernel drew (Philox), read back from the step's buffers /
     passed as `u`."""
     _lib_or_fail()
     n, nd = 640, 256
-    tr, spec, params, emb = _trainer(kind, C, S, seed=5, direct=direct)
+    tr, spec, params, emb = _trainer(kind, C, S, seed=5, name=name, direct=direct)
     batch, depth = _batches(n, nd, C, seed=17, with_mask=with_mask)
     if not direct:   # the autograd path takes the jitter from the caller: share it with the oracle
         g = torch.Generator().manual_seed(3)

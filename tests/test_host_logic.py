@@ -13,23 +13,26 @@ from semnerf_b200.renderer import B200Renderer
 from tests.helpers import make_cfgs
 
 
-def build(kind, C=6):
-    spec = O.ModelSpec(kind=kind, n_classes=C)
+def build(kind, C=6, name=""):
+    spec = O.spec_for_case(name, kind, C)
     cfgs = make_cfgs(spec, 64, 0.05)
     if kind == "semantic":
         return spec, RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": C})())
-    return spec, SatNeRFB200(cfgs, layers=8, feat=512, skips=[4], t_embedding_dims=4)
+    return spec, SatNeRFB200(cfgs, layers=8, feat=512, skips=[4], t_embedding_dims=spec.tau)
 
 
-@pytest.mark.parametrize("kind,C", [("semantic", 6), ("semantic", 5), ("satnerf", 0)])
-def test_state_dict_names_and_shapes_match_reference(kind, C):
-    spec, m = build(kind, C)
+@pytest.mark.parametrize("kind,C,name", [("semantic", 6, ""), ("semantic", 5, ""), ("satnerf", 0, ""),
+                                         # fc_use_full_features, other embedding widths, every head variant on top
+                                         ("semantic", 6, "full"), ("satnerf", 0, "full"), ("semantic", 6, "tau8"),
+                                         ("satnerf", 0, "tau2"), ("semantic", 6, "full_tau6_ts"), ("semantic", 9, "full_bs_tj")])
+def test_state_dict_names_and_shapes_match_reference(kind, C, name):
+    spec, m = build(kind, C, name)
     want = O.param_shapes(spec)   # pinned against the reference modules by oracle/pin_against_reference.py
     sd = m.state_dict()
     assert list(sd.keys()) == list(want.keys())
     for k, shape in want.items():
         assert tuple(sd[k].shape) == tuple(shape), k
-    assert m.semantic_n_classes == C and m.number_of_outputs == 9 + C
+    assert m.semantic_n_classes == C and m.number_of_outputs == 9 + C + (1 if spec.separate_beta_s else 0)
 
 
 def test_state_dict_round_trip_and_strictness():
@@ -73,10 +76,16 @@ def test_initialiser_ranges_follow_the_reference():
 
 def test_unsupported_configurations_fail_loudly():
     spec = O.ModelSpec(kind="semantic")
-    cfgs = make_cfgs(spec, 64, 0.05)
-    cfgs.pipeline.fc_use_full_features = True
-    with pytest.raises(_lib.SnbError):
+    for field, value in (("t_embedding_tau", 13), ("fc_units", 256), ("fc_layers", 6), ("activation_function", "relu")):
+        cfgs = make_cfgs(spec, 64, 0.05)
+        setattr(cfgs.pipeline, field, value)
+        with pytest.raises(_lib.SnbError):
+            RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": 6})())
+    cfgs = make_cfgs(O.ModelSpec(kind="semantic", separate_tj_s=True, tj_for_s=True, tau=7), 64, 0.05)
+    with pytest.raises(_lib.SnbError):    # two embeddings of 7 do not fit the 16 per-ray columns
         RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": 6})())
+    with pytest.raises(_lib.SnbError):    # more classes than head rows
+        RSSemanticNeRFB200(make_cfgs(spec, 64, 0.05), type("D", (), {"semantic_n_classes": 11})())
     with pytest.raises(_lib.SnbError):
         SatNeRFB200(make_cfgs(O.ModelSpec(kind="satnerf"), 64, 0.05), feat=256)
 

@@ -123,13 +123,34 @@ def test_plugin_renderer_refuses_an_injected_inference_function(ref):
         RSSemanticB200Rendering(cfgs, inference=lambda *a, **k: None)
 
 
-def test_unsupported_head_variants_raise_at_construction(ref):
+def test_unsupported_configurations_raise_at_construction(ref):
     from semnerf_b200 import _lib
-    for flag in ("fc_use_full_features",):
+    for flag, value in (("t_embedding_tau", 13), ("fc_units", 256)):
         cfgs = _cfgs(ref, "rs_semantic.toml", "semnerf_b200.pipelines.RSSemanticB200Pipeline")
-        setattr(cfgs.pipeline, flag, True)
+        setattr(cfgs.pipeline, flag, value)
         with pytest.raises(_lib.SnbError):
             ref.pipelines.load_pipeline(cfgs)
+
+
+def test_full_features_and_embedding_width_build_the_same_state_dict_as_the_reference(ref):
+    """fc_use_full_features = true and t_embedding_tau = 6 together with every head variant: same state_dict keys and shapes
+    as the reference pipeline built from the same config"""
+    pipes = []
+    for dotted in ("semnerf_b200.pipelines.RSSemanticB200Pipeline", "semantic.pipelines.rs_semantic.RSSemanticPipeline"):
+        cfgs = _cfgs(ref, "rs_semantic.toml", dotted)
+        for flag in ("use_tj_for_s", "use_separate_beta_for_s", "use_separate_tj_for_semantic", "fc_use_full_features"):
+            setattr(cfgs.pipeline, flag, True)
+        cfgs.pipeline.t_embedding_tau = 6
+        pipes.append(ref.pipelines.load_pipeline(cfgs))
+    ours, theirs = pipes
+    sd, sd_ref = ours.state_dict(), theirs.state_dict()
+    assert list(sd.keys()) == list(sd_ref.keys())
+    assert all(tuple(sd[k].shape) == tuple(sd_ref[k].shape) for k in sd)
+    assert tuple(sd["model_coarse.semantic_prediction.0.weight"].shape) == (512, 518)
+    assert tuple(sd["model_coarse.sky_color.0.weight"].shape) == (512, 3)
+    assert tuple(ours.models["t"].weight.shape) == tuple(theirs.models["t"].weight.shape) == (cfgs.pipeline.t_embedding_vocab, 6)
+    theirs.load_state_dict(sd)
+    ours.load_state_dict(sd_ref)
 
 
 def test_head_variants_build_the_same_state_dict_as_the_reference(ref):
