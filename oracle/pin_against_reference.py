@@ -29,7 +29,7 @@ def ref_cfgs(spec: O.ModelSpec, n_samples: int, sc_lambda: float):
     pl = types.SimpleNamespace(
         n_samples=n_samples, render_chunk_size=40960, fc_units=spec.feat, fc_layers=spec.layers,
         fc_skips=list(spec.skips), fc_use_full_features=spec.full_features, sc_lambda=sc_lambda,
-        t_embedding_tau=spec.tau, t_embedding_vocab=spec.vocab, activation_function="siren",
+        t_embedding_tau=spec.tau, t_embedding_vocab=spec.vocab, activation_function="siren" if spec.siren else "relu",
         mapping_pos_n_freq=spec.n_freq, mapping_dir_n_freq=4,
         semantic_activation_function="sigmoid" if spec.semantic_sigmoid else "none",
         use_tj_for_s=spec.tj_for_s, use_tj_instead_of_beta=spec.tj_instead_of_beta, use_beta_for_s=False,
@@ -57,7 +57,7 @@ def build_reference(spec: O.ModelSpec, params, emb, n_samples, sc_lambda, emb_s_
     else:
         from baseline.models.satnerf import SatNeRF
         from baseline.components.rendering import SatNeRFRendering
-        model = SatNeRF(cfgs, layers=spec.layers, feat=spec.feat, skips=list(spec.skips),
+        model = SatNeRF(cfgs, layers=spec.layers, feat=spec.feat, skips=list(spec.skips), siren=spec.siren,
                         t_embedding_dims=spec.tau)
         renderer = SatNeRFRendering(cfgs)
     missing = model.load_state_dict(params, strict=True)
@@ -105,6 +105,8 @@ CASES = [
     ("sem_c6_s8_tau8", "semantic", 6, 512, 16, 8, 0.05, 17),
     ("sat_s8_tau2", "satnerf", 0, 512, 16, 8, 0.05, 18),
     ("sem_c6_s8_full_tau6_ts", "semantic", 6, 512, 16, 8, 0.05, 19),   # everything at once
+    ("sem_c6_s8_relu", "semantic", 6, 512, 16, 8, 0.05, 20),               # activation_function = "relu"
+    ("sat_s8_relu", "satnerf", 0, 512, 16, 8, 0.05, 21),                   # SatNeRF(siren=False)
 ]
 
 GOLDEN_KEYS = ["rgb_coarse", "depth_coarse", "weights_coarse", "transparency_coarse",

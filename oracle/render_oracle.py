@@ -70,6 +70,8 @@ class ModelSpec:
     vocab: int = 50
     n_freq: int = 10
     full_features: bool = False
+    siren: bool = True              # activation_function == "siren" (rs_semantic.py:150,158): else every `nl` is a ReLU, the
+                                    # first trunk layer loses its w0 = 30 and no SIREN initialiser runs (semantic model only)
     semantic_sigmoid: bool = True  # configs/pipelines/rs_semantic.toml:55
     # head-input variants of the semantic model (rs_semantic.py:186-215; all off in the shipped TOML)
     tj_for_s: bool = False             # use_tj_for_s: the semantic head reads cat(f, t)
@@ -172,7 +174,7 @@ def make_params(spec: ModelSpec, seed: int = 0, dtype=torch.float32, trained_lik
         else:
             fan_in = shape[1]
             # NeRF is built with siren=False (baseline/pipelines/nerf.py:28-32): nn.Linear default init everywhere
-            siren_net = (name.startswith("fc_net.") or name.startswith("sun_v_net.")) and spec.kind != "nerf"
+            siren_net = (name.startswith("fc_net.") or name.startswith("sun_v_net.")) and spec.kind != "nerf" and spec.siren
             if siren_net:
                 first = name in ("fc_net.0.weight", "sun_v_net.0.weight")
                 bound = 1.0 / fan_in if first else math.sqrt(6.0 / fan_in)
@@ -238,11 +240,13 @@ def _lin(p, name, x):
 def spec_for_case(name: str, kind: str, n_classes: int, feat: int = 512) -> ModelSpec:
     """the architecture a golden case's NAME asks for (oracle/pin_against_reference.py CASES, tests/helpers.py GOLDEN_CASES):
     tokens `tj` (use_tj_for_s + use_tj_instead_of_beta), `bs` (use_separate_beta_for_s), `ts` (use_tj_for_s +
-    use_separate_beta_for_s + use_separate_tj_for_semantic), `full` (fc_use_full_features), `tauN` (t_embedding_tau = N)"""
+    use_separate_beta_for_s + use_separate_tj_for_semantic), `full` (fc_use_full_features), `tauN` (t_embedding_tau = N),
+    `relu` (activation_function = "relu")"""
     tok = name.split("_")
     tj, ts, bs = "tj" in tok, "ts" in tok, "bs" in tok
     tau = next((int(t[3:]) for t in tok if t.startswith("tau") and t[3:].isdigit()), 4)
-    return ModelSpec(kind=kind, n_classes=n_classes, feat=feat, tau=tau, full_features="full" in tok, tj_for_s=tj or ts,
+    return ModelSpec(kind=kind, n_classes=n_classes, feat=feat, tau=tau, full_features="full" in tok, siren="relu" not in tok,
+                     tj_for_s=tj or ts,
                      tj_instead_of_beta=tj, separate_beta_s=bs or ts, separate_tj_s=ts)
 
 
@@ -261,38 +265,39 @@ def mlp_forward(p: Dict[str, torch.Tensor], spec: ModelSpec, xyz: torch.Tensor,
     if spec.kind == "nerf":
         return _nerf_forward(p, spec, xyz, sun_d, return_hidden)   # `sun_d` carries the view direction here
     enc = posenc(xyz, spec.n_freq) if spec.kind == "semantic" else xyz
+    nl = torch.sin if spec.siren else torch.relu      # `nl` of rs_semantic.py:158 / satnerf.py:127
     h = enc
     hidden = []
     for i in range(spec.layers):
         if i in spec.skips:
             h = torch.cat([enc, h], -1)
         y = _lin(p, f"fc_net.{2 * i}", h)
-        h = torch.sin(30.0 * y) if i == 0 else torch.sin(y)
+        h = nl(30.0 * y) if (i == 0 and spec.siren) else nl(y)
         hidden.append(h)
     sigma = F.softplus(_lin(p, "sigma_from_xyz.0", h))
     f = _lin(p, "feats_from_xyz", h)
     f_rgb = torch.cat([f, t], -1) if (spec.kind == "semantic" and spec.tj_instead_of_beta) else f   # rs_semantic.py:287-288
-    rgb = torch.sigmoid(_lin(p, "rgb_from_xyzdir.2", torch.sin(_lin(p, "rgb_from_xyzdir.0", f_rgb))))
+    rgb = torch.sigmoid(_lin(p, "rgb_from_xyzdir.2", nl(_lin(p, "rgb_from_xyzdir.0", f_rgb))))
     rgb = rgb * (1 + 2 * 0.001) - 0.001
     s = torch.cat([f, sun_d], -1)
-    s = torch.sin(_lin(p, "sun_v_net.0", s))
-    s = torch.sin(_lin(p, "sun_v_net.2", s))
-    s = torch.sin(_lin(p, "sun_v_net.4", s))
+    s = nl(_lin(p, "sun_v_net.0", s))
+    s = nl(_lin(p, "sun_v_net.2", s))
+    s = nl(_lin(p, "sun_v_net.4", s))
     sun_v = torch.sigmoid(_lin(p, "sun_v_net.6", s))
     sky = torch.sigmoid(_lin(p, "sky_color.2", torch.relu(_lin(p, "sky_color.0", sun_d))))
     if spec.kind == "snerf":   # snerf.py:226-242: [rgb | sigma | sun_v | sky]
         out = torch.cat([rgb, sigma, sun_v, sky], 1)
         return (out, hidden, f) if return_hidden else out
-    beta = F.softplus(_lin(p, "beta_from_xyz.2", torch.sin(_lin(p, "beta_from_xyz.0", torch.cat([f, t], -1)))))
+    beta = F.softplus(_lin(p, "beta_from_xyz.2", nl(_lin(p, "beta_from_xyz.0", torch.cat([f, t], -1)))))
     cols = [rgb, sigma, sun_v, sky, beta]
     # the semantic heads' embedding: t, or the separate t_s (rs_semantic.py:300-301,334-335)
     t_sem = t_s if (spec.kind == "semantic" and spec.separate_tj_s) else t
     if spec.kind == "semantic" and spec.separate_beta_s:   # rs_semantic.py:297-303
         cols.append(F.softplus(_lin(p, "semantic_beta_from_xyz.2",
-                                    torch.sin(_lin(p, "semantic_beta_from_xyz.0", torch.cat([f, t_sem], -1))))))
+                                    nl(_lin(p, "semantic_beta_from_xyz.0", torch.cat([f, t_sem], -1))))))
     if spec.kind == "semantic":
         f_sem = torch.cat([f, t_sem], -1) if spec.tj_for_s else f                                      # rs_semantic.py:330-338
-        sem = _lin(p, "semantic_prediction.2", torch.sin(_lin(p, "semantic_prediction.0", f_sem)))
+        sem = _lin(p, "semantic_prediction.2", nl(_lin(p, "semantic_prediction.0", f_sem)))
         if spec.semantic_sigmoid:
             sem = torch.sigmoid(sem)
         cols.append(sem)

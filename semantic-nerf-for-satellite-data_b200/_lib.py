@@ -19,6 +19,7 @@ K1_KIND = {0: 0, 1: 1, 2: 1, 3: 0}
 HEADS_ALL, HEADS_SOLAR, HEADS_DEPTH = 63, 5, 1
 COMPOSITE_NO_CLAMP, COMPOSITE_BETA_S = 1, 2
 VARIANT_TJ_FOR_S, VARIANT_TJ_INSTEAD_OF_BETA, VARIANT_SEPARATE_BETA_S, VARIANT_SEPARATE_TJ_S, VARIANT_FULL_FEATURES = 1, 2, 4, 8, 16
+VARIANT_RELU = 32
 EPI_SIN, EPI_LINEAR, EPI_MUL, EPI_HEADOUT, EPI_F32ROWS, EPI_WGRAD = range(6)
 
 _vp, _i, _i64, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t

@@ -1066,12 +1066,14 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   SNB_CHECK_ARG(model_kind >= SNB_MODEL_SATNERF && model_kind <= SNB_MODEL_SNERF, SNB_ERR_INVALID, "model_create: bad kind %d",
                 model_kind);
   if (model_kind != SNB_MODEL_SEMANTIC) n_classes = 0;
-  SNB_CHECK_ARG((variant & ~SNB_VARIANT_FULL_FEATURES) == 0 || model_kind == SNB_MODEL_SEMANTIC, SNB_ERR_UNSUPPORTED,
-                "model_create: head-input variants exist for the semantic model only");
-  SNB_CHECK_ARG(!(variant & SNB_VARIANT_FULL_FEATURES) || model_kind == SNB_MODEL_SEMANTIC || model_kind == SNB_MODEL_SATNERF,
-                SNB_ERR_UNSUPPORTED, "model_create: fc_use_full_features exists for SatNeRF and the semantic model (satnerf.py:123-124)");
+  SNB_CHECK_ARG((variant & ~(SNB_VARIANT_FULL_FEATURES | SNB_VARIANT_RELU)) == 0 || model_kind == SNB_MODEL_SEMANTIC,
+                SNB_ERR_UNSUPPORTED, "model_create: head-input variants exist for the semantic model only");
+  SNB_CHECK_ARG(!(variant & (SNB_VARIANT_FULL_FEATURES | SNB_VARIANT_RELU)) || model_kind == SNB_MODEL_SEMANTIC ||
+                    model_kind == SNB_MODEL_SATNERF,
+                SNB_ERR_UNSUPPORTED,
+                "model_create: fc_use_full_features / the ReLU activation exist for SatNeRF and the semantic model (satnerf.py:123-127)");
   SNB_CHECK_ARG((variant & ~(SNB_VARIANT_TJ_FOR_S | SNB_VARIANT_TJ_INSTEAD_OF_BETA | SNB_VARIANT_SEPARATE_BETA_S |
-                             SNB_VARIANT_SEPARATE_TJ_S | SNB_VARIANT_FULL_FEATURES)) == 0,
+                             SNB_VARIANT_SEPARATE_TJ_S | SNB_VARIANT_FULL_FEATURES | SNB_VARIANT_RELU)) == 0,
                 SNB_ERR_UNSUPPORTED, "model_create: variant bits %d not implemented", variant);
   // the per-ray columns of the head inputs travel in the 16 aux columns [1 | sun_d (3) | t (tau) | t_s (tau)]
   if (t_embedding_tau <= 0) t_embedding_tau = 4;
@@ -1096,7 +1098,7 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   m->k0 = enc60 ? 60 : 3;
   m->enc_ld = enc60 ? 128 : 64;
   m->w0_ld = enc60 ? 192 : 64;
-  m->relu = model_kind == SNB_MODEL_NERF ? 1 : 0;
+  m->relu = (model_kind == SNB_MODEL_NERF || (variant & SNB_VARIANT_RELU)) ? 1 : 0;
   m->aux_ld = model_kind == SNB_MODEL_NERF ? 32 : 16;
   m->kdir = 24;
   m->n_out = 9 + m->beta_s + n_classes;   // [rgb | sigma | sun | sky | beta | (beta_s) | sem]  (rs_semantic.py:291-311)
@@ -1568,7 +1570,7 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
   cudaStream_t st = (cudaStream_t)stream;
   const int FL = m->fl;
   const bool sem = m->kind == SNB_MODEL_SEMANTIC;
-  const int hid = nerf ? F32_RELU : F32_SIN;
+  const int hid = m->relu ? F32_RELU : F32_SIN;   // `nl` of the model: every hidden activation (satnerf.py:127)
   const int k0 = m->k0, tau = m->tau, n_out = m->n_out, C = m->n_classes;
   const bool by_ray = rows_per_ray > 1;   // per-ray sun_d / t / sky rows, broadcast over the ray's samples
   const int div = by_ray ? rows_per_ray : 1;
@@ -1617,7 +1619,7 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
       const std::string nm = "fc_net." + std::to_string(2 * i);
       int rc;
       if (i == 0) {
-        rc = gemm(senc, nullptr, W(nm.c_str()), k0, B(nm.c_str()), F, hid, nerf ? 1.0f : 30.0f, cur, F);
+        rc = gemm(senc, nullptr, W(nm.c_str()), k0, B(nm.c_str()), F, hid, m->relu ? 1.0f : 30.0f, cur, F);
       } else {
         const F32Seg sh = rows(cur, F, F);
         if (i == 4) rc = gemm(senc, &sh, W(nm.c_str()), k0 + F, B(nm.c_str()), F, hid, 1.0f, nxt, F);
@@ -1639,9 +1641,9 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
     }
     {   // sun visibility: cat(f, sun_d) -> 3 x sin -> sigmoid  (satnerf.py:236-243)
       const F32Seg ss = per_ray(sun_d, 3);
-      if (int r = gemm(sf, &ss, W("sun_v_net.0"), F + 3, B("sun_v_net.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
-      if (int r = gemm(rows(g1, FL, FL), nullptr, W("sun_v_net.2"), FL, B("sun_v_net.2"), FL, F32_SIN, 1.0f, g2, FL)) return r;
-      if (int r = gemm(rows(g2, FL, FL), nullptr, W("sun_v_net.4"), FL, B("sun_v_net.4"), FL, F32_SIN, 1.0f, g1, FL)) return r;
+      if (int r = gemm(sf, &ss, W("sun_v_net.0"), F + 3, B("sun_v_net.0"), FL, hid, 1.0f, g1, FL)) return r;
+      if (int r = gemm(rows(g1, FL, FL), nullptr, W("sun_v_net.2"), FL, B("sun_v_net.2"), FL, hid, 1.0f, g2, FL)) return r;
+      if (int r = gemm(rows(g2, FL, FL), nullptr, W("sun_v_net.4"), FL, B("sun_v_net.4"), FL, hid, 1.0f, g1, FL)) return r;
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("sun_v_net.6"), FL, B("sun_v_net.6"), 1, F32_SIGMOID, 1.0f, o + 4, n_out)) return r;
     }
     if (!all) continue;
@@ -1649,17 +1651,17 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
       const bool tj_rgb = (m->variant & SNB_VARIANT_TJ_INSTEAD_OF_BETA) != 0;   // cat(f, t) -> colour head (rs_semantic.py:287-288)
       const F32Seg st_ = per_ray_t(0);
       if (int r = gemm(sf, tj_rgb ? &st_ : nullptr, W("rgb_from_xyzdir.0"), F + (tj_rgb ? tau : 0), B("rgb_from_xyzdir.0"), FL,
-                       F32_SIN, 1.0f, g1, FL)) return r;
+                       hid, 1.0f, g1, FL)) return r;
     }
     if (int r = gemm(rows(g1, FL, FL), nullptr, W("rgb_from_xyzdir.2"), FL, B("rgb_from_xyzdir.2"), 3, F32_RGB, 1.0f, o, n_out)) return r;
     if (m->find("beta_from_xyz.0.weight") >= 0) {
       const F32Seg st_ = per_ray_t(0);
-      if (int r = gemm(sf, &st_, W("beta_from_xyz.0"), F + tau, B("beta_from_xyz.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
+      if (int r = gemm(sf, &st_, W("beta_from_xyz.0"), F + tau, B("beta_from_xyz.0"), FL, hid, 1.0f, g1, FL)) return r;
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("beta_from_xyz.2"), FL, B("beta_from_xyz.2"), 1, F32_SOFTPLUS, 1.0f, o + 8, n_out)) return r;
     }
     if (m->beta_s) {   // semantic uncertainty head (rs_semantic.py:228-237,297-303): cat(f, t) -> sin -> softplus, column 9
       const F32Seg st_ = per_ray_t(sep_ts ? tau : 0);
-      if (int r = gemm(sf, &st_, W("semantic_beta_from_xyz.0"), F + tau, B("semantic_beta_from_xyz.0"), FL, F32_SIN, 1.0f, g1, FL)) return r;
+      if (int r = gemm(sf, &st_, W("semantic_beta_from_xyz.0"), F + tau, B("semantic_beta_from_xyz.0"), FL, hid, 1.0f, g1, FL)) return r;
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("semantic_beta_from_xyz.2"), FL, B("semantic_beta_from_xyz.2"), 1, F32_SOFTPLUS, 1.0f,
                        o + 9, n_out)) return r;
     }
@@ -1667,7 +1669,7 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
       const bool tj_s = (m->variant & SNB_VARIANT_TJ_FOR_S) != 0;               // cat(f, t) -> semantic head (rs_semantic.py:330-338)
       const F32Seg st_ = per_ray_t(sep_ts ? tau : 0);
       if (int r = gemm(sf, tj_s ? &st_ : nullptr, W("semantic_prediction.0"), F + (tj_s ? tau : 0), B("semantic_prediction.0"), FL,
-                       F32_SIN, 1.0f, g1, FL)) return r;
+                       hid, 1.0f, g1, FL)) return r;
       if (int r = gemm(rows(g1, FL, FL), nullptr, W("semantic_prediction.2"), FL, B("semantic_prediction.2"), C,
                        m->sem_sigmoid ? F32_SIGMOID : F32_NONE, 1.0f, o + 9 + m->beta_s, n_out)) return r;
     }

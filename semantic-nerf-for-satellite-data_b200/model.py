@@ -40,6 +40,7 @@ class SnbMLP(torch.nn.Module):
         # use_separate_tj_for_semantic: the semantic heads read a second embedding t_s; the kernels take [t | t_s] as ONE
         # (.., 2 tau) tensor (aux columns 4..4+tau and 4+tau..4+2tau), the gradient comes back the same way and autograd splits it
         self.sep_ts = bool(variant & _lib.VARIANT_SEPARATE_TJ_S)
+        self.relu = kind == MODEL_NERF or bool(variant & _lib.VARIANT_RELU)   # no SIREN: ReLU activations, nn.Linear default init
         self.number_of_outputs = 9 + self.beta_s + n_classes       # satnerf.py:120 / rs_semantic.py:291-311
         self.n_out_kernel = 9 + self.beta_s + n_classes            # columns of the packed tensor the kernels write
         self.t_embedding_dims = tau
@@ -69,7 +70,7 @@ class SnbMLP(torch.nn.Module):
                     t.uniform_(-b, b)
                     continue
                 fan_in = t.shape[1]
-                if (name.startswith("fc_net.") or name.startswith("sun_v_net.")) and self.kind != MODEL_NERF:
+                if (name.startswith("fc_net.") or name.startswith("sun_v_net.")) and not self.relu:
                     first = name in ("fc_net.0.weight", "sun_v_net.0.weight")
                     b = 1.0 / fan_in if first else math.sqrt(6.0 / fan_in)
                 else:
@@ -184,12 +185,13 @@ class SatNeRFB200(SnbMLP):
 
     def __init__(self, cfgs=None, layers=8, feat=512, mapping=False, mapping_sizes=(10, 4), skips=(4,), siren=True,
                  t_embedding_dims=4):
-        if layers != 8 or feat != 512 or list(skips) != [4] or mapping or not siren:
-            raise _lib.SnbError("libsnb implements the shipped SatNeRF configuration: 8x512 SIREN, skip [4], "
+        if layers != 8 or feat != 512 or list(skips) != [4] or mapping:
+            raise _lib.SnbError("libsnb implements the shipped SatNeRF configuration: 8x512, skip [4], "
                                 "raw-xyz input (configs/pipelines/satnerf.toml)")
         # fc_use_full_features (satnerf.py:123-124): the head hidden layers and sky_color are fc_units wide instead of half
         full = cfgs is not None and bool(getattr(cfgs.pipeline, "fc_use_full_features", False))
-        super().__init__(MODEL_SATNERF, 0, True, t_embedding_dims, cfgs, _lib.VARIANT_FULL_FEATURES if full else 0)
+        super().__init__(MODEL_SATNERF, 0, True, t_embedding_dims, cfgs,
+                         (_lib.VARIANT_FULL_FEATURES if full else 0) | (0 if siren else _lib.VARIANT_RELU))   # satnerf.py:127,146
         self.layers, self.skips = layers, list(skips)
 
 
@@ -198,16 +200,16 @@ class RSSemanticNeRFB200(SnbMLP):
 
     def __init__(self, cfgs, dataset_semantic):
         p = cfgs.pipeline
-        if p.fc_layers != 8 or p.fc_units != 512 or list(p.fc_skips) != [4] \
-                or p.activation_function != "siren" or p.mapping_pos_n_freq != 10:
-            raise _lib.SnbError("libsnb implements the shipped rs_semantic.toml trunk: 8 x 512 SIREN, skip [4], 10 frequencies")
+        if p.fc_layers != 8 or p.fc_units != 512 or list(p.fc_skips) != [4] or p.mapping_pos_n_freq != 10:
+            raise _lib.SnbError("libsnb implements the shipped rs_semantic.toml trunk: 8 x 512, skip [4], 10 frequencies")
         sig = p.semantic_activation_function == "sigmoid"
         # head-input variants: t as an extra input of the semantic head / of the colour head (rs_semantic.py:186-215)
         variant = (_lib.VARIANT_TJ_FOR_S if getattr(p, "use_tj_for_s", False) else 0) | \
                   (_lib.VARIANT_TJ_INSTEAD_OF_BETA if getattr(p, "use_tj_instead_of_beta", False) else 0) | \
                   (_lib.VARIANT_SEPARATE_BETA_S if getattr(p, "use_separate_beta_for_s", False) else 0) | \
                   (_lib.VARIANT_SEPARATE_TJ_S if getattr(p, "use_separate_tj_for_semantic", False) else 0) | \
-                  (_lib.VARIANT_FULL_FEATURES if getattr(p, "fc_use_full_features", False) else 0)   # rs_semantic.py:147-148
+                  (_lib.VARIANT_FULL_FEATURES if getattr(p, "fc_use_full_features", False) else 0) | \
+                  (0 if p.activation_function == "siren" else _lib.VARIANT_RELU)     # rs_semantic.py:147-150,158
         super().__init__(MODEL_SEMANTIC, int(dataset_semantic.semantic_n_classes), sig, p.t_embedding_tau, cfgs, variant)
         self.cfg = p
         self.layers, self.skips = p.fc_layers, list(p.fc_skips)

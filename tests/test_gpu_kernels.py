@@ -122,7 +122,7 @@ def _model(kind, C, seed=3, S=64, sc=0.05, trained_like=False, tj=False, bs=Fals
         model = NeRFB200().to(DEV)
     else:
         model = (RSSemanticNeRFB200(cfgs, type("D", (), {"semantic_n_classes": C})()) if kind == "semantic"
-                 else SatNeRFB200(cfgs, t_embedding_dims=spec.tau)).to(DEV)
+                 else SatNeRFB200(cfgs, t_embedding_dims=spec.tau, siren=spec.siren)).to(DEV)
     model.load_state_dict(params)
     t = torch.nn.Embedding(spec.vocab, spec.tau).to(DEV)
     t.weight.data.copy_(emb)

@@ -23,7 +23,9 @@ def _cos(a, b):
 @pytest.mark.parametrize("kind,C,name", [("semantic", 6, ""), ("semantic", 5, ""), ("satnerf", 0, ""),
                                          # fc_use_full_features (512-wide head layers, sky_color) and other embedding widths
                                          ("semantic", 6, "full"), ("satnerf", 0, "full"), ("semantic", 6, "tau8"),
-                                         ("satnerf", 0, "tau2"), ("semantic", 6, "tau12"), ("satnerf", 0, "full_tau1")])
+                                         ("satnerf", 0, "tau2"), ("semantic", 6, "tau12"), ("satnerf", 0, "full_tau1"),
+                                         # activation_function = "relu" / SatNeRF(siren=False)
+                                         ("semantic", 6, "relu"), ("satnerf", 0, "relu_full")])
 def test_model_forward_backward_matches_oracle(kind, C, name):
     """Model.forward(xyz, sun_d, t) -> (B, 9+C): per-head outputs and every parameter gradient."""
     _lib_or_fail()
