@@ -140,7 +140,9 @@ def test_fused_training_step_matches_the_oracle(kind, C, epoch, with_depth, with
     for k in p2:   # every tensor with a non-trivial gradient on its own
         m = p2[k].numel()
         if p2[k].grad is not None and p2[k].grad.norm() > 1e-6 * g_ref.norm():
-            assert _cos(g_flat[off:off + m], p2[k].grad) >= 0.995, k
+            # (a ReLU net is noisier per tensor in bf16 than the SIREN models: the [h > 0] masks of near-zero pre-activations
+            # flip under rounding; the whole-gradient bar above is the same - see test_nerf_model_and_render_gradients_match_oracle)
+            assert _cos(g_flat[off:off + m], p2[k].grad) >= (0.995 if spec.siren else 0.98), k
         off += m
     if g_emb is not None:
         if beta_loss:
