@@ -115,10 +115,14 @@ typedef struct snb_model snb_model; /* opaque host object: architecture + packed
  * SNB_VARIANT_RELU (SatNeRF and the semantic model): `activation_function != "siren"` (rs_semantic.py:150,158; SatNeRF's
  * `siren=False`, satnerf.py:127,146) - every hidden activation is a ReLU, the first trunk layer has no w0 = 30.
  * t_embedding_tau: width of the per-image embedding (`t_embedding_tau`, 4 in every shipped TOML; 0 = 4): at most 12, 6 with
- * SNB_VARIANT_SEPARATE_TJ_S - the per-ray inputs travel in 16 aux columns [1 | sun_d | t | t_s]. */
+ * SNB_VARIANT_SEPARATE_TJ_S - the per-ray inputs travel in 16 aux columns [1 | sun_d | t | t_s].
+ * mapping_pos_n_freq (semantic model; 0 = 10): frequencies of the positional mapping of xyz (`mapping_pos_n_freq`, 1..10).
+ * snb_sample_encode always writes the 10-frequency row; a model with fewer has 6 L input columns in its first and skip
+ * layers and zero packed weights for the frequencies it does not have. */
 enum { SNB_VARIANT_TJ_FOR_S = 1, SNB_VARIANT_TJ_INSTEAD_OF_BETA = 2, SNB_VARIANT_SEPARATE_BETA_S = 4,
        SNB_VARIANT_SEPARATE_TJ_S = 8, SNB_VARIANT_FULL_FEATURES = 16, SNB_VARIANT_RELU = 32 };
-int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid, int variant, int t_embedding_tau);
+int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid, int variant, int t_embedding_tau,
+                     int mapping_pos_n_freq);
 void snb_model_destroy(snb_model* m);
 /* number of fp32 parameters / the offset table: parameters live in ONE flat fp32 buffer in the
  * reference state_dict order; names[i], offsets[i], rows[i], cols[i]. */

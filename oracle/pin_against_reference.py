@@ -107,6 +107,7 @@ CASES = [
     ("sem_c6_s8_full_tau6_ts", "semantic", 6, 512, 16, 8, 0.05, 19),   # everything at once
     ("sem_c6_s8_relu", "semantic", 6, 512, 16, 8, 0.05, 20),               # activation_function = "relu"
     ("sat_s8_relu", "satnerf", 0, 512, 16, 8, 0.05, 21),                   # SatNeRF(siren=False)
+    ("sem_c6_s8_freq6", "semantic", 6, 512, 16, 8, 0.05, 22),              # mapping_pos_n_freq = 6
 ]
 
 GOLDEN_KEYS = ["rgb_coarse", "depth_coarse", "weights_coarse", "transparency_coarse",

@@ -241,11 +241,12 @@ def spec_for_case(name: str, kind: str, n_classes: int, feat: int = 512) -> Mode
     """the architecture a golden case's NAME asks for (oracle/pin_against_reference.py CASES, tests/helpers.py GOLDEN_CASES):
     tokens `tj` (use_tj_for_s + use_tj_instead_of_beta), `bs` (use_separate_beta_for_s), `ts` (use_tj_for_s +
     use_separate_beta_for_s + use_separate_tj_for_semantic), `full` (fc_use_full_features), `tauN` (t_embedding_tau = N),
-    `relu` (activation_function = "relu")"""
+    `relu` (activation_function = "relu"), `freqN` (mapping_pos_n_freq = N)"""
     tok = name.split("_")
     tj, ts, bs = "tj" in tok, "ts" in tok, "bs" in tok
     tau = next((int(t[3:]) for t in tok if t.startswith("tau") and t[3:].isdigit()), 4)
-    return ModelSpec(kind=kind, n_classes=n_classes, feat=feat, tau=tau, full_features="full" in tok, siren="relu" not in tok,
+    n_freq = next((int(t[4:]) for t in tok if t.startswith("freq") and t[4:].isdigit()), 10)
+    return ModelSpec(kind=kind, n_classes=n_classes, feat=feat, tau=tau, n_freq=n_freq, full_features="full" in tok, siren="relu" not in tok,
                      tj_for_s=tj or ts,
                      tj_instead_of_beta=tj, separate_beta_s=bs or ts, separate_tj_s=ts)
 

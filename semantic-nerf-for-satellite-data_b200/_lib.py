@@ -32,7 +32,7 @@ SIGNATURES = {
     "snb_sample_encode": (_i, [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i,
                                _vp, _vp, _vp, _vp, _vp, _vp]),
     "snb_encode_points": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "snb_model_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
+    "snb_model_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i]),
     "snb_model_destroy": (None, [_vp]),
     "snb_model_param_count": (_i64, [_vp]),
     "snb_model_num_tensors": (_i, [_vp]),

@@ -58,6 +58,8 @@ struct PackJob {
 struct snb_model {
   int kind, n_classes, sem_sigmoid;
   int fl;   // feat_last: 256, or 512 with SNB_VARIANT_FULL_FEATURES
+  int kin0;   // input features of the first trunk layer in the PARAMETERS: 6 x mapping_pos_n_freq (<= k0: K1 always writes the
+              // 10-frequency row, the packed weights of the frequencies a model does not have are zero), or 3
   int k0, enc_ld, w0_ld, hhw, n_out, tau;   // enc_ld: K1 row width; w0_ld: packed K of the first layer
   int hh_rgb, hh_beta, hh_sem, hh_bs, hh_sun;
   int beta_s;   // use_separate_beta_for_s: a second uncertainty head (packed column 9, head pre-activation row 6)
@@ -380,7 +382,7 @@ static long long take(long long& cursor, long long elems) {
 
 static void build_layout(snb_model* m) {
   const int FL = m->fl;
-  const int k0 = m->k0, hhw = m->hhw, tau = m->tau, C = m->n_classes;
+  const int k0 = m->k0, kin0 = m->kin0, hhw = m->hhw, tau = m->tau, C = m->n_classes;
   const bool sem = m->kind == SNB_MODEL_SEMANTIC;
   const bool nerf = m->kind == SNB_MODEL_NERF;   // nerf.py:118-160: trunk, sigma, feats, rgb(f | dir) only
   const bool has_beta = m->kind == SNB_MODEL_SATNERF || sem;   // S-NeRF (snerf.py:161-186) and NeRF have no uncertainty head
@@ -397,7 +399,7 @@ static void build_layout(snb_model* m) {
   // ---- flat fp32 parameter order = reference state_dict order ----
   m->n_params = 0;
   for (int i = 0; i < LAYERS; ++i) {
-    int kin = i == 0 ? k0 : (i == 4 ? F + k0 : F);
+    int kin = i == 0 ? m->kin0 : (i == 4 ? F + m->kin0 : F);
     add_tensor(m, "fc_net." + std::to_string(2 * i) + ".weight", F, kin);
     add_tensor(m, "fc_net." + std::to_string(2 * i) + ".bias", F, 0);
   }
@@ -488,9 +490,10 @@ static void build_layout(snb_model* m) {
   };
   if (enc60) {
     // layer 0, semantic: K-segments [enc cols 0..127 = hi | lo | 0] x [W_hi | W_hi | 0] and [enc cols 0..63 = hi | lo(0:4)] x [W_lo | 0]
-    job(m->wl[0], m->w0_ld, fcw(0), k0, F, k0, 0, 0);
-    job(m->wl[0] + k0, m->w0_ld, fcw(0), k0, F, k0, 0, 0);
-    job(m->wl[0] + 128, m->w0_ld, fcw(0), k0, F, k0, 0, 1);
+    // (a model with fewer than 10 frequencies fills the first kin0 = 6 L columns of each 60-wide slot; the rest stay zero)
+    job(m->wl[0], m->w0_ld, fcw(0), kin0, F, kin0, 0, 0);
+    job(m->wl[0] + k0, m->w0_ld, fcw(0), kin0, F, kin0, 0, 0);
+    job(m->wl[0] + 128, m->w0_ld, fcw(0), kin0, F, kin0, 0, 1);
   } else {
     // layer 0, satnerf: [hi | lo | hi] against the input row [hi | hi | lo]
     job(m->wl[0], m->w0_ld, fcw(0), k0, F, k0, 0, 0);
@@ -499,9 +502,9 @@ static void build_layout(snb_model* m) {
   }
   for (int i = 1; i < LAYERS; ++i) {
     if (i == 4) {
-      job(m->wl[4], kl4, fcw(4), F + k0, F, k0, 0, 0);            // enc columns (first k0 of the 64-wide segment)
-      job(m->wl[4] + 64, kl4, fcw(4) + k0, F + k0, F, F, 0, 0);   // h3 columns
-      job(m->tl[4], F, fcw(4) + k0, F + k0, F, F, 1, 0);
+      job(m->wl[4], kl4, fcw(4), F + kin0, F, kin0, 0, 0);            // enc columns (first kin0 of the 64-wide segment)
+      job(m->wl[4] + 64, kl4, fcw(4) + kin0, F + kin0, F, F, 0, 0);   // h3 columns
+      job(m->tl[4], F, fcw(4) + kin0, F + kin0, F, F, 1, 0);
     } else {
       job(m->wl[i], F, fcw(i), F, F, F, 0, 0);
       job(m->tl[i], F, fcw(i), F, F, F, 1, 0);
@@ -589,11 +592,11 @@ static void build_layout(snb_model* m) {
   auto ujob = [&](long long dst, int ldd, long long src, int lds, int rows, int cols, int tr) {
     U.push_back({dst, src, ldd, lds, rows, cols, tr, 0});
   };
-  ujob(fcw(0), k0, m->gl[0], 64, F, k0, 0);
+  ujob(fcw(0), kin0, m->gl[0], 64, F, kin0, 0);
   for (int i = 1; i < LAYERS; ++i) {
     if (i == 4) {
-      ujob(fcw(4), F + k0, m->gl4e, 64, F, k0, 0);
-      ujob(fcw(4) + k0, F + k0, m->gl[4], F, F, F, 0);
+      ujob(fcw(4), F + kin0, m->gl4e, 64, F, kin0, 0);
+      ujob(fcw(4) + kin0, F + kin0, m->gl[4], F, F, F, 0);
     } else {
       ujob(fcw(i), F, m->gl[i], F, F, F, 0);
     }
@@ -1061,7 +1064,7 @@ using namespace snb;
 // C ABI
 // =====================================================================================================
 extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, int semantic_sigmoid, int variant,
-                                int t_embedding_tau) {
+                                int t_embedding_tau, int mapping_pos_n_freq) {
   SNB_CHECK_ARG(out != nullptr, SNB_ERR_INVALID, "model_create: null out");
   SNB_CHECK_ARG(model_kind >= SNB_MODEL_SATNERF && model_kind <= SNB_MODEL_SNERF, SNB_ERR_INVALID, "model_create: bad kind %d",
                 model_kind);
@@ -1077,6 +1080,9 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
                 SNB_ERR_UNSUPPORTED, "model_create: variant bits %d not implemented", variant);
   // the per-ray columns of the head inputs travel in the 16 aux columns [1 | sun_d (3) | t (tau) | t_s (tau)]
   if (t_embedding_tau <= 0) t_embedding_tau = 4;
+  if (mapping_pos_n_freq <= 0) mapping_pos_n_freq = 10;
+  SNB_CHECK_ARG(mapping_pos_n_freq <= 10 && (mapping_pos_n_freq == 10 || model_kind == SNB_MODEL_SEMANTIC), SNB_ERR_UNSUPPORTED,
+                "model_create: mapping_pos_n_freq %d (1..10, semantic model: K1 writes the 10-frequency row)", mapping_pos_n_freq);
   SNB_CHECK_ARG(t_embedding_tau <= ((variant & SNB_VARIANT_SEPARATE_TJ_S) ? 6 : 12), SNB_ERR_UNSUPPORTED,
                 "model_create: t_embedding_tau %d does not fit the 16 per-ray columns (max 12, 6 with a second embedding)",
                 t_embedding_tau);
@@ -1096,6 +1102,7 @@ extern "C" int snb_model_create(snb_model** out, int model_kind, int n_classes, 
   const int FL = m->fl;
   const bool enc60 = model_kind == SNB_MODEL_SEMANTIC || model_kind == SNB_MODEL_NERF;   // positional encoding of xyz (10 frequencies)
   m->k0 = enc60 ? 60 : 3;
+  m->kin0 = model_kind == SNB_MODEL_SEMANTIC ? 6 * mapping_pos_n_freq : m->k0;
   m->enc_ld = enc60 ? 128 : 64;
   m->w0_ld = enc60 ? 192 : 64;
   m->relu = (model_kind == SNB_MODEL_NERF || (variant & SNB_VARIANT_RELU)) ? 1 : 0;
@@ -1571,7 +1578,7 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
   const int FL = m->fl;
   const bool sem = m->kind == SNB_MODEL_SEMANTIC;
   const int hid = m->relu ? F32_RELU : F32_SIN;   // `nl` of the model: every hidden activation (satnerf.py:127)
-  const int k0 = m->k0, tau = m->tau, n_out = m->n_out, C = m->n_classes;
+  const int k0 = m->kin0, tau = m->tau, n_out = m->n_out, C = m->n_classes;   // the model's own input width (6 x its frequencies)
   const bool by_ray = rows_per_ray > 1;   // per-ray sun_d / t / sky rows, broadcast over the ray's samples
   const int div = by_ray ? rows_per_ray : 1;
   auto W = [&](const char* name) { return params + m->find((std::string(name) + ".weight").c_str()); };
@@ -1587,7 +1594,7 @@ extern "C" int snb_mlp_forward_fp32(const snb_model* m, const float* params, voi
     float* g1 = f + (long long)M * F;
     float* g2 = g1 + (long long)M * FL;
     float* o = out + r0 * n_out;
-    if (int r = f32_posenc_launch(xyz + r0 * 3, M, k0 == 60 ? 10 : 0, enc, F32_ENC_LD, st)) return r;
+    if (int r = f32_posenc_launch(xyz + r0 * 3, M, m->k0 == 60 ? k0 / 6 : 0, enc, F32_ENC_LD, st)) return r;
     auto gemm = [&](F32Seg s0, const F32Seg* s1, const float* w, int ldw, const float* bias, int N, int act, float w0, float* c,
                     long long ldc) {
       F32Gemm g;

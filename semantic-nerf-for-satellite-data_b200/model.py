@@ -23,7 +23,7 @@ from ._lib import HEADS_ALL, MODEL_NERF, MODEL_SATNERF, MODEL_SEMANTIC, MODEL_SN
 class SnbMLP(torch.nn.Module):
     """Common base: owns the libsnb model handle, the flat parameter and the packed bf16 image."""
 
-    def __init__(self, kind: int, n_classes: int, semantic_sigmoid: bool, tau: int, cfgs=None, variant: int = 0):
+    def __init__(self, kind: int, n_classes: int, semantic_sigmoid: bool, tau: int, cfgs=None, variant: int = 0, n_freq: int = 10):
         super().__init__()
         tau = int(tau)
         max_tau = 6 if (variant & _lib.VARIANT_SEPARATE_TJ_S) else 12
@@ -32,7 +32,8 @@ class SnbMLP(torch.nn.Module):
                                 f"so the embedding may be 1..{max_tau} wide here")
         lib = _lib.load()
         h = C.c_void_p()
-        check(lib.snb_model_create(C.byref(h), kind, n_classes, 1 if semantic_sigmoid else 0, variant, tau), "snb_model_create")
+        check(lib.snb_model_create(C.byref(h), kind, n_classes, 1 if semantic_sigmoid else 0, variant, tau, int(n_freq)),
+              "snb_model_create")
         self._h = h
         self.kind = kind
         self.semantic_n_classes = n_classes          # read by the reference's inference(), rs_semantic.py:95
@@ -200,8 +201,8 @@ class RSSemanticNeRFB200(SnbMLP):
 
     def __init__(self, cfgs, dataset_semantic):
         p = cfgs.pipeline
-        if p.fc_layers != 8 or p.fc_units != 512 or list(p.fc_skips) != [4] or p.mapping_pos_n_freq != 10:
-            raise _lib.SnbError("libsnb implements the shipped rs_semantic.toml trunk: 8 x 512, skip [4], 10 frequencies")
+        if p.fc_layers != 8 or p.fc_units != 512 or list(p.fc_skips) != [4] or not 1 <= p.mapping_pos_n_freq <= 10:
+            raise _lib.SnbError("libsnb implements the shipped rs_semantic.toml trunk: 8 x 512, skip [4], 1..10 positional frequencies")
         sig = p.semantic_activation_function == "sigmoid"
         # head-input variants: t as an extra input of the semantic head / of the colour head (rs_semantic.py:186-215)
         variant = (_lib.VARIANT_TJ_FOR_S if getattr(p, "use_tj_for_s", False) else 0) | \
@@ -210,7 +211,8 @@ class RSSemanticNeRFB200(SnbMLP):
                   (_lib.VARIANT_SEPARATE_TJ_S if getattr(p, "use_separate_tj_for_semantic", False) else 0) | \
                   (_lib.VARIANT_FULL_FEATURES if getattr(p, "fc_use_full_features", False) else 0) | \
                   (0 if p.activation_function == "siren" else _lib.VARIANT_RELU)     # rs_semantic.py:147-150,158
-        super().__init__(MODEL_SEMANTIC, int(dataset_semantic.semantic_n_classes), sig, p.t_embedding_tau, cfgs, variant)
+        super().__init__(MODEL_SEMANTIC, int(dataset_semantic.semantic_n_classes), sig, p.t_embedding_tau, cfgs, variant,
+                         p.mapping_pos_n_freq)
         self.cfg = p
         self.layers, self.skips = p.fc_layers, list(p.fc_skips)
 

@@ -37,7 +37,7 @@ def test_model_layout_is_host_side():
     lib = _lib.load()
     for kind, C_, n in ((1, 6, 2827023), (1, 5, 2827023 - 257), (0, 0, 2635785)):
         h = C.c_void_p()
-        assert lib.snb_model_create(C.byref(h), kind, C_, 1, 0, 4) == 0
+        assert lib.snb_model_create(C.byref(h), kind, C_, 1, 0, 4, 10) == 0
         assert lib.snb_model_param_count(h) == n          # SURVEY 8a row a6 parameter counts
         assert lib.snb_model_packed_bytes(h) > 2 * n       # forward + transposed bf16 copies
         w_inf = lib.snb_mlp_workspace_bytes(h, 65536, 0)
@@ -49,13 +49,15 @@ def test_model_layout_is_host_side():
 def test_argument_validation_error_codes():
     lib = _lib.load()
     h = C.c_void_p()
-    assert lib.snb_model_create(C.byref(h), 7, 6, 1, 0, 4) == -1             # SNB_ERR_INVALID
-    assert lib.snb_model_create(C.byref(h), 1, 11, 1, 0, 4) == -2            # SNB_ERR_UNSUPPORTED (C > 10)
+    assert lib.snb_model_create(C.byref(h), 7, 6, 1, 0, 4, 10) == -1         # SNB_ERR_INVALID
+    assert lib.snb_model_create(C.byref(h), 1, 11, 1, 0, 4, 10) == -2        # SNB_ERR_UNSUPPORTED (C > 10)
     assert b"n_classes" in lib.snb_last_error()
-    assert lib.snb_model_create(C.byref(h), 1, 6, 1, 0, 13) == -2            # the embedding must fit the 16 per-ray columns
-    assert lib.snb_model_create(C.byref(h), 1, 6, 1, 8, 7) == -2             # ... twice with a second embedding
+    assert lib.snb_model_create(C.byref(h), 1, 6, 1, 0, 13, 10) == -2        # the embedding must fit the 16 per-ray columns
+    assert lib.snb_model_create(C.byref(h), 1, 6, 1, 8, 7, 10) == -2         # ... twice with a second embedding
     assert b"t_embedding_tau" in lib.snb_last_error()
-    assert lib.snb_model_create(C.byref(h), 2, 0, 1, 16, 4) == -2            # fc_use_full_features: SatNeRF / semantic model only
+    assert lib.snb_model_create(C.byref(h), 2, 0, 1, 16, 4, 10) == -2        # fc_use_full_features: SatNeRF / semantic model only
+    assert lib.snb_model_create(C.byref(h), 1, 6, 1, 0, 4, 11) == -2         # K1 writes 10 positional frequencies
+    assert lib.snb_model_create(C.byref(h), 0, 0, 1, 0, 4, 6) == -2          # ... and SatNeRF takes raw xyz
     # null pointers / S < 2 are rejected before any launch
     assert lib.snb_composite_forward(None, None, 4, 64, 15, 6, 0, None, None, None, None, None, None, None) == -1
     one = C.c_void_p(16)

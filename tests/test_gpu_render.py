@@ -25,7 +25,9 @@ def _cos(a, b):
                                          ("semantic", 6, "full"), ("satnerf", 0, "full"), ("semantic", 6, "tau8"),
                                          ("satnerf", 0, "tau2"), ("semantic", 6, "tau12"), ("satnerf", 0, "full_tau1"),
                                          # activation_function = "relu" / SatNeRF(siren=False)
-                                         ("semantic", 6, "relu"), ("satnerf", 0, "relu_full")])
+                                         ("semantic", 6, "relu"), ("satnerf", 0, "relu_full"),
+                                         # mapping_pos_n_freq < 10: zero packed weights for the missing frequencies
+                                         ("semantic", 6, "freq6"), ("semantic", 6, "freq1")])
 def test_model_forward_backward_matches_oracle(kind, C, name):
     """Model.forward(xyz, sun_d, t) -> (B, 9+C): per-head outputs and every parameter gradient."""
     _lib_or_fail()

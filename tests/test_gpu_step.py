@@ -34,7 +34,7 @@ def _trainer(kind, C, S, seed, name="", **kw):
     spec = O.spec_for_case(name, kind, C)
     cfgs = default_cfgs(kind, n_samples=S, sc_lambda=0.05, use_car_reg_loss=True, car_reg_loss_start=2,
                         fc_use_full_features=spec.full_features, t_embedding_tau=spec.tau,
-                        activation_function="siren" if spec.siren else "relu")
+                        activation_function="siren" if spec.siren else "relu", mapping_pos_n_freq=spec.n_freq)
     tr = Trainer(cfgs, kind, C, device=DEV, car_index=CAR, seed=0, **kw)
     params, emb = O.make_params(spec, seed=seed)
     tr.models["coarse"].load_state_dict(params)
@@ -71,7 +71,8 @@ def _to_dev(b):
                           ("semantic", 6, 3, True, True, 8, ""),
                           # fc_use_full_features / other embedding widths
                           ("semantic", 6, 3, True, True, 64, "full"), ("satnerf", 0, 3, True, False, 64, "full_tau2"),
-                          ("semantic", 6, 3, False, True, 64, "tau8"), ("semantic", 6, 3, True, True, 64, "relu")])
+                          ("semantic", 6, 3, False, True, 64, "tau8"), ("semantic", 6, 3, True, True, 64, "relu"),
+                          ("semantic", 6, 3, True, True, 64, "freq4")])
 @pytest.mark.parametrize("direct", [True, False])
 def test_fused_training_step_matches_the_oracle(kind, C, epoch, with_depth, with_mask, S, name, direct):
     """The fused K3 + loss kernel (through the direct step and through render_loss under autograd) against the ORACLE'S loss

@@ -25,7 +25,8 @@ def build(kind, C=6, name=""):
                                          # fc_use_full_features, other embedding widths, every head variant on top
                                          ("semantic", 6, "full"), ("satnerf", 0, "full"), ("semantic", 6, "tau8"),
                                          ("satnerf", 0, "tau2"), ("semantic", 6, "full_tau6_ts"), ("semantic", 9, "full_bs_tj"),
-                                         ("semantic", 6, "relu"), ("satnerf", 0, "relu")])
+                                         ("semantic", 6, "relu"), ("satnerf", 0, "relu"), ("semantic", 6, "freq6"),
+                                         ("semantic", 5, "freq1_full")])
 def test_state_dict_names_and_shapes_match_reference(kind, C, name):
     spec, m = build(kind, C, name)
     want = O.param_shapes(spec)   # pinned against the reference modules by oracle/pin_against_reference.py
@@ -77,7 +78,7 @@ def test_initialiser_ranges_follow_the_reference():
 
 def test_unsupported_configurations_fail_loudly():
     spec = O.ModelSpec(kind="semantic")
-    for field, value in (("t_embedding_tau", 13), ("fc_units", 256), ("fc_layers", 6), ("mapping_pos_n_freq", 6)):
+    for field, value in (("t_embedding_tau", 13), ("fc_units", 256), ("fc_layers", 6), ("mapping_pos_n_freq", 11)):
         cfgs = make_cfgs(spec, 64, 0.05)
         setattr(cfgs.pipeline, field, value)
         with pytest.raises(_lib.SnbError):
