@@ -133,14 +133,16 @@ def test_unsupported_configurations_raise_at_construction(ref):
 
 
 def test_full_features_and_embedding_width_build_the_same_state_dict_as_the_reference(ref):
-    """fc_use_full_features = true and t_embedding_tau = 6 together with every head variant: same state_dict keys and shapes
-    as the reference pipeline built from the same config"""
+    """fc_use_full_features = true, t_embedding_tau = 6, activation_function = "relu" and mapping_pos_n_freq = 6 together with
+    every head variant: same state_dict keys and shapes as the reference pipeline built from the same config"""
     pipes = []
     for dotted in ("semnerf_b200.pipelines.RSSemanticB200Pipeline", "semantic.pipelines.rs_semantic.RSSemanticPipeline"):
         cfgs = _cfgs(ref, "rs_semantic.toml", dotted)
         for flag in ("use_tj_for_s", "use_separate_beta_for_s", "use_separate_tj_for_semantic", "fc_use_full_features"):
             setattr(cfgs.pipeline, flag, True)
         cfgs.pipeline.t_embedding_tau = 6
+        cfgs.pipeline.activation_function = "relu"
+        cfgs.pipeline.mapping_pos_n_freq = 6
         pipes.append(ref.pipelines.load_pipeline(cfgs))
     ours, theirs = pipes
     sd, sd_ref = ours.state_dict(), theirs.state_dict()
@@ -148,6 +150,8 @@ def test_full_features_and_embedding_width_build_the_same_state_dict_as_the_refe
     assert all(tuple(sd[k].shape) == tuple(sd_ref[k].shape) for k in sd)
     assert tuple(sd["model_coarse.semantic_prediction.0.weight"].shape) == (512, 518)
     assert tuple(sd["model_coarse.sky_color.0.weight"].shape) == (512, 3)
+    assert tuple(sd["model_coarse.fc_net.0.weight"].shape) == (512, 36) and tuple(sd["model_coarse.fc_net.8.weight"].shape) == (512, 548)
+    assert ours.models["coarse"].relu
     assert tuple(ours.models["t"].weight.shape) == tuple(theirs.models["t"].weight.shape) == (cfgs.pipeline.t_embedding_vocab, 6)
     theirs.load_state_dict(sd)
     ours.load_state_dict(sd_ref)
